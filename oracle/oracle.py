@@ -1,0 +1,183 @@
+"""ctypes binding of the CPU oracle (oracle/libmpp_oracle.so).
+
+TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs -- never by mpp_b200 (the product).
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libmpp_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"], env={**os.environ, "CC": "gcc"})
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = C.CDLL(build())
+        L = _LIB
+        L.orc_vsfm_create.restype = C.c_void_p
+        for name in ("orc_thermal_create", "orc_th_create"):
+            if hasattr(L, name):
+                getattr(L, name).restype = C.c_void_p
+        L.orc_findgu_sbc_zerocoeff.restype = C.c_double
+        L.orc_findgu_sbc_zerocoeff.argtypes = [C.c_double, C.c_int, C.c_double]
+    return _LIB
+
+
+def dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+# ---- scalar physics helpers (for unit tests) ---------------------------------
+def density(p, t_K, itype):
+    L = lib()
+    den, dp_, dt_ = C.c_double(), C.c_double(), C.c_double()
+    L.orc_density(C.c_double(p), C.c_double(t_K), C.c_int(itype), C.byref(den), C.byref(dp_), C.byref(dt_))
+    return den.value, dp_.value, dt_.value
+
+
+def enthalpy_ifc67(t_C, p):
+    L = lib()
+    h, hp, ht = C.c_double(), C.c_double(), C.c_double()
+    L.orc_enthalpy_ifc67(C.c_double(t_C), C.c_double(p), C.c_int(1), C.byref(h), C.byref(hp), C.byref(ht))
+    return h.value, hp.value, ht.value
+
+
+class SatParams(C.Structure):
+    _fields_ = [("sat_func_type", C.c_int), ("relperm_func_type", C.c_int), ("sat_res", C.c_double),
+                ("alpha", C.c_double), ("vg_m", C.c_double), ("vg_n", C.c_double), ("bc_lambda", C.c_double),
+                ("sbc_pu", C.c_double), ("sbc_ps", C.c_double), ("sbc_b2", C.c_double), ("sbc_b3", C.c_double)]
+
+
+def satparams(name, sat_res, alpha, lam):
+    L = lib()
+    sp = SatParams()
+    if name == "van_genuchten":
+        rc = L.orc_satfunc_set_vg(C.byref(sp), C.c_double(sat_res), C.c_double(alpha), C.c_double(lam))
+    elif name == "brooks_corey":
+        rc = L.orc_satfunc_set_bc(C.byref(sp), C.c_double(sat_res), C.c_double(alpha), C.c_double(lam))
+    elif name == "smooth_brooks_corey_bz2":
+        rc = L.orc_satfunc_set_sbc_bz2(C.byref(sp), C.c_double(sat_res), C.c_double(alpha), C.c_double(lam), C.c_double(-0.9 / alpha))
+    elif name == "smooth_brooks_corey_bz3":
+        rc = L.orc_satfunc_set_sbc_bz3(C.byref(sp), C.c_double(sat_res), C.c_double(alpha), C.c_double(lam), C.c_double(-0.9 / alpha))
+    else:
+        raise ValueError(name)
+    if rc:
+        raise ValueError("bad saturation parameters rc=%d" % rc)
+    return sp
+
+
+def press_to_sat(sp, press):
+    s, ds = C.c_double(), C.c_double()
+    lib().orc_press_to_sat(C.byref(sp), C.c_double(press), C.byref(s), C.byref(ds))
+    return s.value, ds.value
+
+
+def press_to_relperm(sp, press, frac_liq=1.0):
+    k, dk = C.c_double(), C.c_double()
+    lib().orc_press_to_relperm(C.byref(sp), C.c_double(press), C.c_double(frac_liq), C.byref(k), C.byref(dk))
+    return k.value, dk.value
+
+
+SATFUNC_NAMES = {"van_genuchten": 0, "brooks_corey": 1, "smooth_brooks_corey_bz2": 2, "smooth_brooks_corey_bz3": 3}
+
+
+class OracleVSFM:
+    """Same call surface as mpp_b200.soe.VSFM (the product wrapper) so tests drive both identically."""
+
+    def __init__(self, ncol, nlev, per_column=True, nthreads=1):
+        self.L = lib()
+        self.ncol, self.nlev, self.ncells = ncol, nlev, ncol * nlev
+        self.h = C.c_void_p(self.L.orc_vsfm_create(ncol, nlev))
+        self.L.orc_vsfm_set_mode(self.h, int(per_column), int(nthreads))
+
+    def __del__(self):
+        try:
+            self.L.orc_vsfm_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_mesh(self, orientation, dz, area, col_active=None):
+        dz, area = f64(dz), f64(area)
+        assert dz.size == self.ncells and area.size == self.ncol
+        ca = i32(col_active) if col_active is not None else None
+        return self.L.orc_vsfm_set_mesh(self.h, int(orientation), dp(dz), dp(area), ip(ca) if ca is not None else None)
+
+    def add_condition(self, ss_or_bc, cond_type, region):
+        return self.L.orc_vsfm_add_condition(self.h, int(ss_or_bc), int(cond_type), int(region))
+
+    def set_soils(self, watsat, hksat, bsw, sucsat, residual_sat, satfunc_type, density_type):
+        a = [f64(x) for x in (watsat, hksat, bsw, sucsat, residual_sat)]
+        rc = self.L.orc_vsfm_set_soils(self.h, *[dp(x) for x in a], SATFUNC_NAMES[satfunc_type], int(density_type))
+        if rc:
+            raise ValueError("set_soils rc=%d" % rc)
+
+    def set_tolerances(self, atol, rtol, stol, max_it, max_funcs):
+        self.L.orc_vsfm_set_tolerances(self.h, C.c_double(atol), C.c_double(rtol), C.c_double(stol), int(max_it), int(max_funcs))
+
+    def restart(self, press):
+        press = f64(press)
+        assert press.size == self.ncells
+        return self.L.orc_vsfm_restart(self.h, dp(press))
+
+    def set_data(self, auxvar_type, var_type, cond_id, data):
+        data = f64(data)
+        rc = self.L.orc_vsfm_set_data(self.h, int(auxvar_type), int(var_type), int(cond_id), dp(data), int(data.size))
+        if rc:
+            raise ValueError("set_data rc=%d" % rc)
+
+    def get_data(self, auxvar_type, var_type, cond_id, n=None):
+        n = self.ncells if n is None else n
+        out = np.empty(n, dtype=np.float64)
+        rc = self.L.orc_vsfm_get_data(self.h, int(auxvar_type), int(var_type), int(cond_id), dp(out), int(n))
+        if rc:
+            raise ValueError("get_data rc=%d" % rc)
+        return out
+
+    def pre_step_dt(self):
+        self.L.orc_vsfm_pre_step_dt(self.h)
+
+    def post_step_dt(self):
+        self.L.orc_vsfm_post_step_dt(self.h)
+
+    def step_dt(self, dt, nstep=1):
+        conv, reason = C.c_int(), C.c_int()
+        self.L.orc_vsfm_step_dt(self.h, C.c_double(dt), int(nstep), C.byref(conv), C.byref(reason))
+        return bool(conv.value), reason.value
+
+    def stats(self):
+        its, rs, cuts, nf = (np.zeros(self.ncol, dtype=np.int32) for _ in range(4))
+        self.L.orc_vsfm_get_stats(self.h, ip(its), ip(rs), ip(cuts), ip(nf))
+        return {"newton_its": its, "reasons": rs, "dt_cuts": cuts, "nfuncs": nf}
+
+    def eval(self, dt, x_prev, x):
+        x_prev, x = f64(x_prev), f64(x)
+        f, ja, jb, jc = (np.zeros(self.ncells) for _ in range(4))
+        self.L.orc_vsfm_eval(self.h, C.c_double(dt), dp(x_prev), dp(x), dp(f), dp(ja), dp(jb), dp(jc))
+        return f, ja, jb, jc
