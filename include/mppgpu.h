@@ -1,0 +1,130 @@
+/*
+ * mppgpu.h -- C ABI of libmppgpu.so: the B200-native (sm_100a, fp64) replacement for the
+ * per-soil-column implicit solve of MPP-LSM/MPP (reference: Fortran 2003 + PETSc).
+ *
+ * Seam: the type-bound procedures of class(sysofeqns_base_type) that every reference driver
+ * calls.  A Fortran ISO_C_BINDING shim forwards them to the entry points
+ * below; the MPP problem/governing-equation setup API stays in Fortran.
+ *
+ *   reference interface (file:line under the reference root)                    entry point here
+ *   ---------------------------------------------------------------------------------------------
+ *   MPPSetupProblem / SOE creation   MultiPhysicsProbBaseType.F90:1058-1213     mppgpu_create
+ *   MeshCreate, CreateFromCLMCols    MeshType.F90:173-269, 293-645              mppgpu_set_mesh
+ *   soe%AddConditionInGovEqn         SystemOfEquationsBaseType.F90:995+         mppgpu_add_condition
+ *   VSFMMPPSetSoils                  MultiPhysicsProbVSFM.F90:211-475           mppgpu_vsfm_set_soils
+ *   MPPThermalSetSoils               MultiPhysicsProbThermal.F90:76-208         mppgpu_thermal_set_soils
+ *   MPPTHSetSoils                    MultiPhysicsProbTH.F90:75-401              mppgpu_th_set_soils
+ *   SNESSetTolerances                MultiPhysicsProbBaseType.F90:1110-1196,
+ *                                    MPPVSFMALM_Driver.F90:632-640              mppgpu_set_tolerances
+ *   mpp%Restart(data_1d)             MultiPhysicsProbVSFM.F90:603-707           mppgpu_restart
+ *   soe%SetDataFromCLM               SystemOfEquationsVSFMType.F90:663-724      mppgpu_set_data
+ *   soe%SetSolnPrevCLM/SetRDataFromCLM/SetIDataFromCLM/SetBDataFromCLM
+ *                                    SystemOfEquationsThermalType.F90:171-330   mppgpu_set_data / mppgpu_set_idata
+ *   soe%GetDataForCLM, GetSoln       SystemOfEquationsVSFMType.F90:781-845,
+ *                                    SystemOfEquationsThermalType.F90:336       mppgpu_get_data
+ *   soe%PreStepDT                    SystemOfEquationsVSFMType.F90:892-923      mppgpu_pre_step_dt
+ *   soe%StepDT                       SystemOfEquationsBaseType.F90:334-647      mppgpu_step_dt
+ *   soe%PostStepDT                   SystemOfEquationsVSFMType.F90:926-940      mppgpu_post_step_dt
+ *   per-column mass-balance check    MPPVSFMALM_Driver.F90:556-601, 845-863     mppgpu_vsfm_mass_balance
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every array argument is a HOST pointer owned by the caller
+ *     and may be freed right after the call (the reference copies eagerly too).  The *_device
+ *     variants take DEVICE pointers on the handle's device for callers that already live on the GPU.
+ *   - 1-D vectors are cell-ordered, icell = c*nlev + j (layer fastest; MultiPhysicsProbVSFM.F90:364).
+ *   - soil tables are Fortran (ncol,nlev) column-major, t[j*ncol + c] (the reference's (c,j) arrays).
+ *   - integer codes are the reference's own (MultiPhysicsProbConstants.F90:17-196).
+ *   - return value: 0 = ok (PetscErrorCode-like); non-zero = configuration error, message via
+ *     mppgpu_last_error().  Solver failure is NOT an error: *converged = 0 and *converged_reason
+ *     carries the PETSc SNESConvergedReason code (worst column).
+ *   - one handle = one system of equations on one GPU; not re-entrant (neither is the reference).
+ *   - there is no CPU fallback: without a CUDA device mppgpu_create fails.
+ */
+#ifndef MPPGPU_H
+#define MPPGPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mppgpu_soe *mppgpu_handle;
+
+/* soe_itype (MultiPhysicsProbConstants.F90:33-36) */
+#define MPPGPU_SOE_RE_ODE          101
+#define MPPGPU_SOE_THERMAL_TBASED  102
+#define MPPGPU_SOE_TH              104
+/* mesh orientation (:65-66); 313 is ours for CONN_IN_X_DIR chains (no gravity component) */
+#define MPPGPU_MESH_ALONG_GRAVITY   311
+#define MPPGPU_MESH_AGAINST_GRAVITY 312
+#define MPPGPU_MESH_HORIZONTAL      313
+/* saturation function names accepted by VSFMMPPSetSoils (MultiPhysicsProbVSFM.F90:391-417) */
+#define MPPGPU_SATFUNC_VAN_GENUCHTEN 0
+#define MPPGPU_SATFUNC_BROOKS_COREY  1
+#define MPPGPU_SATFUNC_SBC_BZ2       2
+#define MPPGPU_SATFUNC_SBC_BZ3       3
+
+const char *mppgpu_last_error(void);
+int  mppgpu_version(void);
+int  mppgpu_device_count(void);
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+int  mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppgpu_handle *out);
+int  mppgpu_destroy(mppgpu_handle h);
+/* run all work of this handle on a caller-provided cudaStream_t (NULL = the handle's own stream) */
+int  mppgpu_set_stream(mppgpu_handle h, void *cuda_stream);
+int  mppgpu_synchronize(mppgpu_handle h);
+
+/* ---- setup ------------------------------------------------------------------------------------ */
+/* dz: (ncol,nlev) Fortran order [m]; area: ncol [m^2]; col_active: ncol ints or NULL (all active) */
+int  mppgpu_set_mesh(mppgpu_handle h, int orientation, const double *dz, const double *area, const int *col_active);
+/* ieqn: 1-based governing-equation rank in the SoE (TH: 1 = mass, 2 = energy); ss_or_bc: COND_SS/COND_BC;
+ * returns the 1-based condition id in *cond_id (separate numbering for BCs and SSs, = soe_auxvar_id) */
+int  mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int cond_type, int region, int *cond_id);
+int  mppgpu_vsfm_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
+                           const double *sucsat, const double *residual_sat, int satfunc_type, int density_type);
+int  mppgpu_thermal_set_soils(mppgpu_handle h, const double *watsat, const double *csol, const double *tkmg,
+                              const double *tkdry, const int *lun_type, int nlevsoi, int istsoil);
+int  mppgpu_thermal_set_cnfac(mppgpu_handle h, double cnfac);
+int  mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
+                         const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,
+                         int satfunc_type, int density_type, int int_energy_enthalpy_type);
+int  mppgpu_set_tolerances(mppgpu_handle h, double atol, double rtol, double stol, int max_it, int max_funcs);
+/* VSFM/thermal: x has ncells entries (pressure or temperature); TH: 2*ncells, [P(0..N-1) | T(0..N-1)] */
+int  mppgpu_restart(mppgpu_handle h, const double *x, int n);
+
+/* ---- per-step data exchange ------------------------------------------------------------------- */
+int  mppgpu_set_data(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, const double *data, int n);
+int  mppgpu_set_idata(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, const int *data, int n);
+int  mppgpu_get_data(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, double *data, int n);
+int  mppgpu_set_data_device(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, const double *d_data, int n);
+int  mppgpu_get_data_device(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, double *d_data, int n);
+
+/* ---- time stepping ---------------------------------------------------------------------------- */
+int  mppgpu_pre_step_dt(mppgpu_handle h);
+int  mppgpu_step_dt(mppgpu_handle h, double dt, int nstep, int *converged, int *converged_reason);
+/* same, without the blocking read-back of converged/converged_reason (query them later) */
+int  mppgpu_step_dt_async(mppgpu_handle h, double dt, int nstep);
+int  mppgpu_step_result(mppgpu_handle h, int *converged, int *converged_reason);
+int  mppgpu_post_step_dt(mppgpu_handle h);
+
+/* ---- diagnostics ------------------------------------------------------------------------------ */
+/* per-column Newton iterations, SNES reason, dt cuts, residual evaluations of the last StepDT (any may be NULL) */
+int  mppgpu_get_column_stats(mppgpu_handle h, int *newton_its, int *reasons, int *dt_cuts, int *nfuncs);
+/* Rank-local reduction of the ELM driver's mass-balance bookkeeping (MPPVSFMALM_Driver.F90:556-601,845-863):
+ * sums[0] = sum mass at the start of the last StepDT, sums[1] = at its end, sums[2] = sum of all mass-rate
+ * sources * dt, sums[3] = sum boundary mass exchanged; maxs[0] = max per-column |m_beg - m_end + q dt| [kg],
+ * maxs[1] = max Newton its, maxs[2] = any column diverged (0/1), maxs[3] = max dt cuts.
+ * The same 8 doubles live in a device buffer (mppgpu_reduction_buffer_device: sums[4] then maxs[4]) so a
+ * multi-GPU driver can all-reduce them with NCCL without a host round trip. */
+int  mppgpu_vsfm_mass_balance(mppgpu_handle h, double dt, double sums[4], double maxs[4]);
+int  mppgpu_reduction_buffer_device(mppgpu_handle h, double **d_buf);
+/* launches made by the library since creation, and device-time of the last StepDT kernel(s) in ms */
+int  mppgpu_launch_count(mppgpu_handle h, long long *n);
+int  mppgpu_last_step_ms(mppgpu_handle h, float *ms);
+/* one residual + Jacobian evaluation (VSFM: f, ja, jb, jc of ncells; TH: 2N / 4N blocks) for kernel unit tests */
+int  mppgpu_eval(mppgpu_handle h, double dt, const double *x_prev, const double *x, double *f, double *ja, double *jb, double *jc);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,75 @@
+"""Loader of the in-tree CUDA library libmppgpu.so (C ABI in include/mppgpu.h).
+
+There is no CPU fallback: if the library is missing the import of any solver class fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmppgpu.so")
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+_SIGS = {
+    "mppgpu_last_error": (C.c_char_p, []),
+    "mppgpu_version": (C.c_int, []),
+    "mppgpu_device_count": (C.c_int, []),
+    "mppgpu_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "mppgpu_destroy": (C.c_int, [C.c_void_p]),
+    "mppgpu_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "mppgpu_synchronize": (C.c_int, [C.c_void_p]),
+    "mppgpu_set_mesh": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip]),
+    "mppgpu_add_condition": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_ip]),
+    "mppgpu_vsfm_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int]),
+    "mppgpu_thermal_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_int]),
+    "mppgpu_thermal_set_cnfac": (C.c_int, [C.c_void_p, C.c_double]),
+    "mppgpu_th_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int]),
+    "mppgpu_set_tolerances": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "mppgpu_restart": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
+    "mppgpu_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_int]),
+    "mppgpu_set_idata": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.c_int]),
+    "mppgpu_get_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_int]),
+    "mppgpu_set_data_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "mppgpu_get_data_device": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int]),
+    "mppgpu_pre_step_dt": (C.c_int, [C.c_void_p]),
+    "mppgpu_step_dt": (C.c_int, [C.c_void_p, C.c_double, C.c_int, c_ip, c_ip]),
+    "mppgpu_step_dt_async": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
+    "mppgpu_step_result": (C.c_int, [C.c_void_p, c_ip, c_ip]),
+    "mppgpu_post_step_dt": (C.c_int, [C.c_void_p]),
+    "mppgpu_get_column_stats": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_ip]),
+    "mppgpu_vsfm_mass_balance": (C.c_int, [C.c_void_p, C.c_double, c_dp, c_dp]),
+    "mppgpu_reduction_buffer_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mppgpu_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
+    "mppgpu_last_step_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mppgpu_eval": (C.c_int, [C.c_void_p, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
+}
+
+EXPORTS = tuple(_SIGS)
+
+
+def lib():
+    """Return the loaded CUDA library; raise if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "mpp_b200: %s is missing -- build it with `make -C mpp_b200/csrc` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+class MPPError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc != 0:
+        raise MPPError(lib().mppgpu_last_error().decode("utf-8", "replace"))

@@ -1,0 +1,650 @@
+// mppgpu.cu -- C ABI (include/mppgpu.h) and host-side runtime of libmppgpu.so.
+//
+// Host logic mirrors the reference's system-of-equations objects for 1-D column batches:
+//   sysofeqns_vsfm_type     src/mpp/soe/SystemOfEquationsVSFMType.F90
+//   sysofeqns_thermal_type  src/mpp/soe/SystemOfEquationsThermalType.F90
+//   sysofeqns_th_type       src/mpp/soe/SystemOfEquationsTHType.F90
+// but owns device-resident structure-of-arrays state and launches the fused kernels in
+// vsfm_kernels.cuh / thermal_kernels.cuh / th_kernels.cuh.  No CPU fallback exists: every entry point
+// either runs on the GPU or fails loudly.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "../../include/mppgpu.h"
+#include "physics.cuh"
+#include "vsfm_kernels.cuh"
+#include "vsfm_generic_kernel.cuh"
+#include "thermal_kernels.cuh"
+#include "th_kernels.cuh"
+
+using namespace mpp;
+
+// ---- ids (MultiPhysicsProbConstants.F90) -------------------------------------------------------------
+enum { COND_BC = 501, COND_SS = 502, COND_MASS_RATE = 503, COND_MASS_FLUX = 504, COND_DIRICHLET = 505,
+       COND_HEAT_FLUX = 507, COND_SEEPAGE_BC = 509, COND_HEAT_RATE = 511 };
+enum { VAR_PRESSURE = 604, VAR_TEMPERATURE = 605, VAR_BC_SS_CONDITION = 607, VAR_LIQ_SAT = 608, VAR_MASS = 610,
+       VAR_SOIL_MATRIX_POT = 611, VAR_FRAC_LIQ_SAT = 612, VAR_BC_MASS_EXCHANGED = 614, VAR_LIQ_AREAL_DEN = 615,
+       VAR_ICE_AREAL_DEN = 617, VAR_FRAC = 618, VAR_SNOW_WATER = 619, VAR_NUM_SNOW_LYR = 620, VAR_DHS_DT = 621,
+       VAR_THERMAL_COND = 622, VAR_HEAT_CAP = 623, VAR_ACTIVE = 624, VAR_DZ = 627, VAR_DIST_UP = 628,
+       VAR_DIST_DN = 629, VAR_TUNING_FACTOR = 630, VAR_MASS_FLUX = 644 };
+enum { AUXVAR_INTERNAL = 701, AUXVAR_BC = 702, AUXVAR_SS = 703 };
+
+static thread_local std::string g_err;
+static int fail(const char *fmt, ...)
+{
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof(buf), fmt, ap); va_end(ap);
+  g_err = buf;
+  return 1;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
+#define CHECK_H(h) do { if (!(h)) return fail("null handle"); CK(cudaSetDevice((h)->device)); } while (0)
+
+template <class T> struct DevBuf {
+  T *p = nullptr; size_t n = 0;
+  cudaError_t alloc(size_t count) { release(); n = count; if (!count) return cudaSuccess; return cudaMalloc((void **)&p, count * sizeof(T)); }
+  void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+  ~DevBuf() { release(); }
+};
+
+struct HostCond {
+  int ieqn, ss_or_bc, itype, region;
+  size_t n;                 // entries: ncol (top/bottom) or ncells (SOIL_CELLS)
+  DevBuf<double> value, flux, mass_exc, dhsdT, frac;
+};
+
+struct mppgpu_soe {
+  int soe_itype, ncol, nlev, device;
+  size_t ncells;
+  cudaStream_t stream = nullptr; bool own_stream = true;
+  long long launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  float last_ms = 0.f;
+  // mesh
+  int orientation = MPPGPU_MESH_ALONG_GRAVITY; bool mesh_set = false, soils_set = false;
+  DevBuf<double> dz, area; DevBuf<int> active; bool has_active = false;
+  // conditions
+  std::vector<HostCond *> bcs, sss;
+  // solver options
+  SnesOpts so;
+  // ---- VSFM ----
+  int satfunc_name = 0, density_type = DENSITY_CONSTANT;
+  DevBuf<double> por, perm, sat_res, alpha, lam, vgn, pu, ps, b2, b3;
+  DevBuf<double> frac_liq, temperature, liq_sat, pressure, mass, smp;
+  DevBuf<double> xA, xB; double *x_committed = nullptr, *x_current = nullptr;   // soln_prev_clm / soln
+  DevBuf<int> stat_its, stat_reason, stat_cuts, stat_nf;
+  DevBuf<double> col_mass, col_err, col_src, block_partials, red_out;
+  double *h_red = nullptr;     // pinned mirror of red_out (9 doubles)
+  int nblocks_last = 0;
+  bool result_pending = false;
+  // ---- thermal / TH state lives in their own structs ----
+  ThermalState *thermal = nullptr;
+  THState *th = nullptr;
+};
+
+// host-side pieces of the thermal / TH systems (thermal_host.inl, th_host.inl)
+static int thermal_create(ThermalState *t, int ncol, int nlev, cudaStream_t s);
+static void thermal_destroy(ThermalState *t);
+static int thermal_set_mesh(ThermalState *t, int orientation, const double *d_dz, const double *d_area);
+static int thermal_set_temperature(ThermalState *t, const double *T, bool restart);
+static int thermal_field(mppgpu_soe *h, ThermalState *t, int auxvar_type, int var_type, int cond_id, bool for_set, double **p, size_t *cap);
+static int thermal_set_idata(mppgpu_soe *h, ThermalState *t, int auxvar_type, int var_type, int cond_id, const int *data, int n);
+static int thermal_pre_step_dt(ThermalState *t);
+static int thermal_post_step_dt(ThermalState *t);
+static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt);
+static int thermal_set_soils(mppgpu_soe *h, ThermalState *t, const double *watsat, const double *csol, const double *tkmg,
+                             const double *tkdry, const int *lun_type, int nlevsoi, int istsoil);
+static int th_create(THState *t, int ncol, int nlev, cudaStream_t s);
+static void th_destroy(THState *t);
+static int th_set_mesh(THState *t, int orientation, const double *d_dz, const double *d_area);
+static int th_restart(THState *t, const double *x);
+static int th_field(mppgpu_soe *h, THState *t, int ieqn, int auxvar_type, int var_type, int cond_id, bool for_set, double **p, size_t *cap);
+static int th_pre_step_dt(THState *t);
+static int th_post_step_dt(THState *t);
+static int th_step(mppgpu_soe *h, THState *t, double dt);
+static int th_eval(mppgpu_soe *h, THState *t, double dt, const double *x_prev, const double *x, double *f, double *ja, double *jb, double *jc);
+static int th_set_soils(mppgpu_soe *h, THState *t, const double *watsat, const double *hksat, const double *bsw, const double *sucsat,
+                        const double *residual_sat, const double *csol, const double *tkdry, int satfunc_type, int density_type, int iee_type);
+
+static void default_snes(SnesOpts &so)
+{
+  so.atol = 1.e-50; so.rtol = 1.e-8; so.stol = 1.e-10; so.divtol = 1.e4;      // MultiPhysicsProbBaseType.F90:1110-1114 + PETSc defaults
+  so.max_it = 50; so.max_funcs = 10000;
+  so.ls_alpha = 1.e-4; so.ls_minlambda = 1.e-12; so.ls_maxstep = 1.e8; so.ls_max_its = 40;
+}
+
+extern "C" const char *mppgpu_last_error(void) { return g_err.c_str(); }
+extern "C" int mppgpu_version(void) { return 100; }
+extern "C" int mppgpu_device_count(void) { int n = 0; if (cudaGetDeviceCount(&n) != cudaSuccess) return 0; return n; }
+
+// ---- small utility kernels ------------------------------------------------------------------------------
+// (ncol,nlev) Fortran-order table -> cell order
+__global__ void transpose_to_cells_kernel(const double *__restrict__ t, double *__restrict__ out, int ncol, int nlev)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)ncol * nlev;
+  if (i < n) { const int c = (int)(i / nlev), j = (int)(i % nlev); out[i] = t[(size_t)j * ncol + c]; }
+}
+__global__ void fill_kernel(double *p, double v, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+__global__ void convert_soils_kernel(int satfunc_name, const double *watsat, const double *hksat, const double *bsw,
+                                     const double *sucsat, const double *residual_sat, int ncol, int nlev,
+                                     double *por, double *perm, double *sat_res, double *alpha, double *lam, double *vgn,
+                                     double *pu, double *ps, double *b2, double *b3, int *bad_flag)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)ncol * nlev;
+  if (i >= n) return;
+  const int c = (int)(i / nlev), j = (int)(i % nlev);
+  const size_t t = (size_t)j * ncol + c;
+  SatParams sp; double po, pe;
+  const int bad = convert_soil(satfunc_name, watsat[t], hksat[t], bsw[t], sucsat[t], residual_sat[t], po, pe, sp);
+  por[i] = po; perm[i] = pe; sat_res[i] = sp.sat_res; alpha[i] = sp.alpha; lam[i] = sp.m;
+  if (vgn) vgn[i] = sp.n;
+  if (pu) { pu[i] = sp.pu; ps[i] = sp.ps; b2[i] = sp.b2; b3[i] = sp.b3; }
+  if (bad) atomicExch(bad_flag, 1);
+}
+
+static inline int nblk(long long n, int bs) { return (int)((n + bs - 1) / bs); }
+
+static int upload_table(mppgpu_soe *h, const double *host, DevBuf<double> &tmp)
+{
+  CK(tmp.alloc(h->ncells));
+  CK(cudaMemcpyAsync(tmp.p, host, h->ncells * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+// ---- life cycle ---------------------------------------------------------------------------------------------
+extern "C" int mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppgpu_handle *out)
+{
+  if (!out) return fail("mppgpu_create: out is null");
+  *out = nullptr;
+  if (soe_itype != MPPGPU_SOE_RE_ODE && soe_itype != MPPGPU_SOE_THERMAL_TBASED && soe_itype != MPPGPU_SOE_TH)
+    return fail("mppgpu_create: unknown soe_itype %d", soe_itype);
+  if (ncol <= 0 || nlev <= 0) return fail("mppgpu_create: ncol and nlev must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("mppgpu_create: no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("mppgpu_create: device %d out of range (0..%d)", device, ndev - 1);
+  CK(cudaSetDevice(device));
+  mppgpu_soe *h = new mppgpu_soe();
+  h->soe_itype = soe_itype; h->ncol = ncol; h->nlev = nlev; h->device = device;
+  h->ncells = (size_t)ncol * (size_t)nlev;
+  default_snes(h->so);
+  CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
+  CK(h->red_out.alloc(16));
+  CK(cudaMemsetAsync(h->red_out.p, 0, 16 * sizeof(double), h->stream));
+  CK(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
+  memset(h->h_red, 0, 16 * sizeof(double));
+  CK(h->stat_its.alloc(ncol)); CK(h->stat_reason.alloc(ncol)); CK(h->stat_cuts.alloc(ncol)); CK(h->stat_nf.alloc(ncol));
+  CK(cudaMemsetAsync(h->stat_its.p, 0, ncol * sizeof(int), h->stream)); CK(cudaMemsetAsync(h->stat_reason.p, 0, ncol * sizeof(int), h->stream));
+  CK(cudaMemsetAsync(h->stat_cuts.p, 0, ncol * sizeof(int), h->stream)); CK(cudaMemsetAsync(h->stat_nf.p, 0, ncol * sizeof(int), h->stream));
+  if (soe_itype == MPPGPU_SOE_RE_ODE) {
+    const size_t N = h->ncells;
+    CK(h->frac_liq.alloc(N)); CK(h->liq_sat.alloc(N)); CK(h->pressure.alloc(N)); CK(h->mass.alloc(N)); CK(h->smp.alloc(N));
+    CK(h->xA.alloc(N)); CK(h->xB.alloc(N));
+    h->x_committed = h->xA.p; h->x_current = h->xA.p;
+    fill_kernel<<<nblk(N, 256), 256, 0, h->stream>>>(h->frac_liq.p, 1.0, (long long)N);   // SystemOfEquationsVSFMAuxType.F90:66
+    CK(cudaMemsetAsync(h->liq_sat.p, 0, N * 8, h->stream)); CK(cudaMemsetAsync(h->pressure.p, 0, N * 8, h->stream));
+    CK(cudaMemsetAsync(h->mass.p, 0, N * 8, h->stream)); CK(cudaMemsetAsync(h->smp.p, 0, N * 8, h->stream));
+    CK(cudaMemsetAsync(h->xA.p, 0, N * 8, h->stream)); CK(cudaMemsetAsync(h->xB.p, 0, N * 8, h->stream));
+    CK(h->col_mass.alloc(ncol)); CK(h->col_err.alloc(ncol)); CK(h->col_src.alloc(ncol));
+    CK(cudaMemsetAsync(h->col_mass.p, 0, ncol * 8, h->stream)); CK(cudaMemsetAsync(h->col_err.p, 0, ncol * 8, h->stream));
+    CK(cudaMemsetAsync(h->col_src.p, 0, ncol * 8, h->stream));
+  } else if (soe_itype == MPPGPU_SOE_THERMAL_TBASED) {
+    h->thermal = new ThermalState();
+    if (thermal_create(h->thermal, ncol, nlev, h->stream)) return fail("thermal_create failed: %s", cudaGetErrorString(cudaGetLastError()));
+  } else {
+    h->th = new THState();
+    if (th_create(h->th, ncol, nlev, h->stream)) return fail("th_create failed: %s", cudaGetErrorString(cudaGetLastError()));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  *out = h;
+  return 0;
+}
+
+extern "C" int mppgpu_destroy(mppgpu_handle h)
+{
+  if (!h) return 0;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  for (auto *c : h->bcs) delete c;
+  for (auto *c : h->sss) delete c;
+  if (h->thermal) { thermal_destroy(h->thermal); delete h->thermal; }
+  if (h->th) { th_destroy(h->th); delete h->th; }
+  if (h->h_red) cudaFreeHost(h->h_red);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+extern "C" int mppgpu_set_stream(mppgpu_handle h, void *cuda_stream)
+{
+  CHECK_H(h);
+  CK(cudaStreamSynchronize(h->stream));
+  if (cuda_stream) {
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream; h->own_stream = false;
+  } else if (!h->own_stream) {
+    CK(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)); h->own_stream = true;
+  }
+  if (h->thermal) h->thermal->stream = h->stream;
+  if (h->th) h->th->stream = h->stream;
+  return 0;
+}
+
+extern "C" int mppgpu_synchronize(mppgpu_handle h) { CHECK_H(h); CK(cudaStreamSynchronize(h->stream)); return 0; }
+
+// ---- setup ----------------------------------------------------------------------------------------------------
+extern "C" int mppgpu_set_mesh(mppgpu_handle h, int orientation, const double *dz, const double *area, const int *col_active)
+{
+  CHECK_H(h);
+  if (!dz || !area) return fail("mppgpu_set_mesh: dz and area are required");
+  if (orientation != MPPGPU_MESH_ALONG_GRAVITY && orientation != MPPGPU_MESH_AGAINST_GRAVITY && orientation != MPPGPU_MESH_HORIZONTAL)
+    return fail("mppgpu_set_mesh: unknown orientation %d", orientation);
+  if (!h->bcs.empty() || !h->sss.empty()) return fail("mppgpu_set_mesh: the mesh must be set before conditions are added");
+  h->orientation = orientation;
+  DevBuf<double> tmp;
+  if (upload_table(h, dz, tmp)) return 1;
+  CK(h->dz.alloc(h->ncells));
+  transpose_to_cells_kernel<<<nblk(h->ncells, 256), 256, 0, h->stream>>>(tmp.p, h->dz.p, h->ncol, h->nlev);
+  CK(cudaGetLastError());
+  CK(h->area.alloc(h->ncol));
+  CK(cudaMemcpyAsync(h->area.p, area, h->ncol * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->has_active = (col_active != nullptr);
+  if (col_active) {
+    CK(h->active.alloc(h->ncol));
+    CK(cudaMemcpyAsync(h->active.p, col_active, h->ncol * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  }
+  CK(cudaStreamSynchronize(h->stream));
+  h->mesh_set = true;
+  if (h->thermal) return thermal_set_mesh(h->thermal, orientation, h->dz.p, h->area.p) ? fail("thermal_set_mesh failed") : 0;
+  if (h->th) return th_set_mesh(h->th, orientation, h->dz.p, h->area.p) ? fail("th_set_mesh failed") : 0;
+  return 0;
+}
+
+extern "C" int mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int cond_type, int region, int *cond_id)
+{
+  CHECK_H(h);
+  if (!h->mesh_set) return fail("mppgpu_add_condition: set the mesh first");
+  if (ss_or_bc != COND_BC && ss_or_bc != COND_SS) return fail("mppgpu_add_condition: ss_or_bc must be COND_BC (501) or COND_SS (502)");
+  if (region != REGION_TOP && region != REGION_BOTTOM && region != REGION_CELLS)
+    return fail("mppgpu_add_condition: unsupported region %d (SOIL_TOP_CELLS 401, SOIL_BOTTOM_CELLS 402, SOIL_CELLS 403)", region);
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) {
+    if (ieqn != 1) return fail("mppgpu_add_condition: the VSFM SoE has one governing equation (ieqn = 1)");
+    if (ss_or_bc == COND_BC) {
+      // RichardsFlux accepts only these for Darcy boundary connections (RichardsMod.F90:262-273)
+      if (cond_type != COND_DIRICHLET && cond_type != COND_SEEPAGE_BC)
+        return fail("mppgpu_add_condition: VSFM boundary condition type %d unsupported (COND_DIRICHLET 505, COND_SEEPAGE_BC 509)", cond_type);
+      if (region == REGION_CELLS) return fail("mppgpu_add_condition: boundary conditions live on SOIL_TOP_CELLS / SOIL_BOTTOM_CELLS");
+      for (auto *c : h->bcs) if (c->region == region) return fail("mppgpu_add_condition: one boundary condition per region is supported");
+      if ((int)h->bcs.size() >= MAX_BC) return fail("mppgpu_add_condition: at most %d boundary conditions", MAX_BC);
+    } else {
+      if (cond_type != COND_MASS_RATE) return fail("mppgpu_add_condition: VSFM source/sink type %d unsupported (COND_MASS_RATE 503)", cond_type);
+      if ((int)h->sss.size() >= MAX_SS) return fail("mppgpu_add_condition: at most %d source/sink conditions", MAX_SS);
+    }
+  } else if (h->soe_itype == MPPGPU_SOE_THERMAL_TBASED) {
+    if (ieqn != 1) return fail("mppgpu_add_condition: the soil thermal SoE has one governing equation here (ieqn = 1)");
+    if (ss_or_bc == COND_BC && cond_type != COND_HEAT_FLUX && cond_type != COND_DIRICHLET)
+      return fail("mppgpu_add_condition: thermal boundary condition type %d unsupported (COND_HEAT_FLUX 507, COND_DIRICHLET 505)", cond_type);
+    if (ss_or_bc == COND_SS && cond_type != COND_HEAT_RATE)
+      return fail("mppgpu_add_condition: thermal source type %d unsupported (COND_HEAT_RATE 511)", cond_type);
+  } else {
+    if (ieqn != 1 && ieqn != 2) return fail("mppgpu_add_condition: TH has ieqn 1 (mass) and 2 (energy)");
+  }
+  HostCond *c = new HostCond();
+  c->ieqn = ieqn; c->ss_or_bc = ss_or_bc; c->itype = cond_type; c->region = region;
+  c->n = (region == REGION_CELLS) ? h->ncells : (size_t)h->ncol;
+  CK(c->value.alloc(c->n)); CK(cudaMemsetAsync(c->value.p, 0, c->n * 8, h->stream));
+  if (ss_or_bc == COND_BC) {
+    CK(c->flux.alloc(c->n)); CK(cudaMemsetAsync(c->flux.p, 0, c->n * 8, h->stream));
+    CK(c->mass_exc.alloc(c->n)); CK(cudaMemsetAsync(c->mass_exc.p, 0, c->n * 8, h->stream));
+    if (h->soe_itype == MPPGPU_SOE_THERMAL_TBASED) {
+      CK(c->dhsdT.alloc(c->n)); CK(cudaMemsetAsync(c->dhsdT.p, 0, c->n * 8, h->stream));
+      CK(c->frac.alloc(c->n));  CK(cudaMemsetAsync(c->frac.p, 0, c->n * 8, h->stream));     // ThermalKSPTemperatureBaseAuxType.F90:60
+    }
+    h->bcs.push_back(c);
+    if (cond_id) *cond_id = (int)h->bcs.size();
+  } else {
+    h->sss.push_back(c);
+    if (cond_id) *cond_id = (int)h->sss.size();
+  }
+  return 0;
+}
+
+extern "C" int mppgpu_vsfm_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
+                                     const double *sucsat, const double *residual_sat, int satfunc_type, int density_type)
+{
+  CHECK_H(h);
+  if (h->soe_itype != MPPGPU_SOE_RE_ODE) return fail("mppgpu_vsfm_set_soils: handle is not a VSFM SoE");
+  if (!watsat || !hksat || !bsw || !sucsat || !residual_sat) return fail("mppgpu_vsfm_set_soils: null table");
+  if (satfunc_type < 0 || satfunc_type > 3) return fail("ERROR:: Unknown vsfm_satfunc_type = %d", satfunc_type);   // MultiPhysicsProbVSFM.F90:415
+  if (density_type < DENSITY_CONSTANT || density_type > DENSITY_IFC67) return fail("Unknown value for VAR_DENSITY_TYPE %d", density_type);
+  if (density_type == DENSITY_IFC67) return fail("mppgpu_vsfm_set_soils: DENSITY_IFC67 is only wired for the TH SoE");
+  const size_t N = h->ncells;
+  DevBuf<double> t[5]; const double *src[5] = {watsat, hksat, bsw, sucsat, residual_sat};
+  for (int i = 0; i < 5; ++i) if (upload_table(h, src[i], t[i])) return 1;
+  CK(h->por.alloc(N)); CK(h->perm.alloc(N)); CK(h->sat_res.alloc(N)); CK(h->alpha.alloc(N)); CK(h->lam.alloc(N));
+  h->vgn.release(); h->pu.release(); h->ps.release(); h->b2.release(); h->b3.release();
+  if (satfunc_type == MPPGPU_SATFUNC_VAN_GENUCHTEN) CK(h->vgn.alloc(N));
+  if (satfunc_type >= MPPGPU_SATFUNC_SBC_BZ2) { CK(h->pu.alloc(N)); CK(h->ps.alloc(N)); CK(h->b2.alloc(N)); CK(h->b3.alloc(N)); }
+  DevBuf<int> bad; CK(bad.alloc(1)); CK(cudaMemsetAsync(bad.p, 0, sizeof(int), h->stream));
+  convert_soils_kernel<<<nblk(N, 128), 128, 0, h->stream>>>(satfunc_type, t[0].p, t[1].p, t[2].p, t[3].p, t[4].p, h->ncol, h->nlev,
+      h->por.p, h->perm.p, h->sat_res.p, h->alpha.p, h->lam.p, h->vgn.p, h->pu.p, h->ps.p, h->b2.p, h->b3.p, bad.p);
+  CK(cudaGetLastError());
+  int hbad = 0;
+  CK(cudaMemcpyAsync(&hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  if (hbad) return fail("SatFunc_Set_*: bad param (SaturationFunction.F90:141-146,177-182,285-291,343-349)");
+  h->satfunc_name = satfunc_type; h->density_type = density_type; h->soils_set = true;
+  return 0;
+}
+
+extern "C" int mppgpu_set_tolerances(mppgpu_handle h, double atol, double rtol, double stol, int max_it, int max_funcs)
+{
+  CHECK_H(h);
+  h->so.atol = atol; h->so.rtol = rtol; h->so.stol = stol; h->so.max_it = max_it; h->so.max_funcs = max_funcs;
+  if (h->th) h->th->so = h->so;
+  return 0;
+}
+
+extern "C" int mppgpu_restart(mppgpu_handle h, const double *x, int n)
+{
+  CHECK_H(h);
+  if (!x) return fail("mppgpu_restart: null data");
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) {
+    if ((size_t)n != h->ncells) return fail("VSFMMPPRestart: size(data_1d) /= ncells_local (%d vs %zu)", n, h->ncells);
+    // soln, soln_prev and soln_prev_clm all take the restart vector (MultiPhysicsProbVSFM.F90:675-686)
+    CK(cudaMemcpyAsync(h->xA.p, x, h->ncells * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->x_committed = h->xA.p; h->x_current = h->xA.p;
+    return 0;
+  }
+  if (h->thermal) {
+    if ((size_t)n != h->ncells) return fail("mppgpu_restart: thermal expects ncells temperatures");
+    return thermal_set_temperature(h->thermal, x, true) ? fail("thermal restart failed") : 0;
+  }
+  if ((size_t)n != 2 * h->ncells) return fail("mppgpu_restart: TH expects 2*ncells values [P | T]");
+  return th_restart(h->th, x) ? fail("th restart failed") : 0;
+}
+
+// ---- data exchange ----------------------------------------------------------------------------------------------
+static HostCond *find_cond(mppgpu_soe *h, int auxvar_type, int cond_id)
+{
+  std::vector<HostCond *> &v = (auxvar_type == AUXVAR_BC) ? h->bcs : h->sss;
+  if (cond_id < 1 || cond_id > (int)v.size()) return nullptr;
+  return v[cond_id - 1];
+}
+
+static int vsfm_field(mppgpu_soe *h, int auxvar_type, int var_type, int cond_id, bool for_set, double **p, size_t *cap)
+{
+  if (auxvar_type == AUXVAR_INTERNAL) {
+    *cap = h->ncells;
+    switch (var_type) {
+    case VAR_FRAC_LIQ_SAT: *p = h->frac_liq.p; return 0;
+    case VAR_TEMPERATURE:
+      // stored in the SoE mailbox only; never reaches the Richards aux vars (GoveqnRichardsODEPressureType.F90:573-575)
+      if (!h->temperature.p) { if (h->temperature.alloc(h->ncells) != cudaSuccess) return fail("alloc temperature");
+        fill_kernel<<<nblk(h->ncells, 256), 256, 0, h->stream>>>(h->temperature.p, 298.15, (long long)h->ncells); }
+      *p = h->temperature.p; return 0;
+    case VAR_PRESSURE: *p = h->pressure.p; return 0;
+    case VAR_LIQ_SAT: *p = h->liq_sat.p; return 0;
+    case VAR_MASS: *p = h->mass.p; return 0;
+    case VAR_SOIL_MATRIX_POT: *p = h->smp.p; return 0;
+    }
+    return fail("In VSFMSOEAuxVar%sValue: unknown var_type %d", for_set ? "Set" : "Get", var_type);
+  }
+  if (auxvar_type != AUXVAR_BC && auxvar_type != AUXVAR_SS) return fail("VSFMSOE%sData: Unknown soe_auxvar_type %d", for_set ? "Set" : "Get", auxvar_type);
+  HostCond *c = find_cond(h, auxvar_type, cond_id);
+  if (!c) return fail("VSFMSOE%sData: condition id %d out of range", for_set ? "Set" : "Get", cond_id);
+  *cap = c->n;
+  if (var_type == VAR_BC_SS_CONDITION) { *p = c->value.p; return 0; }
+  if (!for_set && auxvar_type == AUXVAR_BC && var_type == VAR_MASS_FLUX) { *p = c->flux.p; return 0; }
+  if (!for_set && auxvar_type == AUXVAR_BC && var_type == VAR_BC_MASS_EXCHANGED) { *p = c->mass_exc.p; return 0; }
+  if (!for_set && auxvar_type == AUXVAR_SS && var_type == VAR_MASS_FLUX) { *p = c->value.p; return 0; }   // ss_flux = value (GoveqnRichards...:1873)
+  return fail("In VSFMSOEAuxVar%sValue: unknown var_type %d", for_set ? "Set" : "Get", var_type);
+}
+
+static int xfer(mppgpu_soe *h, int ieqn, int auxvar_type, int var_type, int cond_id, const double *src, double *dst, int n, bool set, bool device_ptr)
+{
+  if (n < 0) return fail("negative size");
+  double *p = nullptr; size_t cap = 0;
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) {
+    if (vsfm_field(h, auxvar_type, var_type, cond_id, set, &p, &cap)) return 1;
+  } else if (h->thermal) {
+    if (thermal_field(h, h->thermal, auxvar_type, var_type, cond_id, set, &p, &cap)) return 1;
+  } else {
+    if (th_field(h, h->th, ieqn, auxvar_type, var_type, cond_id, set, &p, &cap)) return 1;
+  }
+  if ((size_t)n > cap) return fail("size(data_1d) > nauxvar (%d > %zu)", n, cap);     // SystemOfEquationsVSFMType.F90:711-716
+  const cudaMemcpyKind kind = device_ptr ? cudaMemcpyDeviceToDevice : (set ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost);
+  if (set) CK(cudaMemcpyAsync(p, src, (size_t)n * 8, kind, h->stream));
+  else     CK(cudaMemcpyAsync(dst, p, (size_t)n * 8, kind, h->stream));
+  if (!device_ptr) CK(cudaStreamSynchronize(h->stream));     // caller may free / read the host array right after the call
+  return 0;
+}
+
+extern "C" int mppgpu_set_data(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, const double *data, int n)
+{ CHECK_H(h); if (!data) return fail("mppgpu_set_data: null data"); return xfer(h, ieqn, auxvar_type, var_type, cond_id, data, nullptr, n, true, false); }
+extern "C" int mppgpu_get_data(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, double *data, int n)
+{ CHECK_H(h); if (!data) return fail("mppgpu_get_data: null data"); return xfer(h, ieqn, auxvar_type, var_type, cond_id, nullptr, data, n, false, false); }
+extern "C" int mppgpu_set_data_device(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, const double *d, int n)
+{ CHECK_H(h); if (!d) return fail("mppgpu_set_data_device: null data"); return xfer(h, ieqn, auxvar_type, var_type, cond_id, d, nullptr, n, true, true); }
+extern "C" int mppgpu_get_data_device(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, double *d, int n)
+{ CHECK_H(h); if (!d) return fail("mppgpu_get_data_device: null data"); return xfer(h, ieqn, auxvar_type, var_type, cond_id, nullptr, d, n, false, true); }
+
+extern "C" int mppgpu_set_idata(mppgpu_handle h, int ieqn, int auxvar_type, int var_type, int cond_id, const int *data, int n)
+{
+  CHECK_H(h);
+  if (!h->thermal) return fail("mppgpu_set_idata: only the thermal SoE has integer/logical data (SetIDataFromCLM/SetBDataFromCLM)");
+  if (!data) return fail("mppgpu_set_idata: null data");
+  return thermal_set_idata(h, h->thermal, auxvar_type, var_type, cond_id, data, n);
+}
+
+// ---- time stepping ----------------------------------------------------------------------------------------------
+extern "C" int mppgpu_pre_step_dt(mppgpu_handle h)
+{
+  CHECK_H(h);
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) {
+    // VSFMSPreStepDT (SystemOfEquationsVSFMType.F90:892-923): soln = soln_prev = soln_prev_clm; reset boundary mass exchanged
+    h->x_current = h->x_committed;
+    for (auto *c : h->bcs) CK(cudaMemsetAsync(c->mass_exc.p, 0, c->n * 8, h->stream));
+    return 0;
+  }
+  if (h->thermal) return thermal_pre_step_dt(h->thermal) ? fail("thermal_pre_step_dt failed") : 0;
+  return th_pre_step_dt(h->th) ? fail("th_pre_step_dt failed") : 0;
+}
+
+extern "C" int mppgpu_post_step_dt(mppgpu_handle h)
+{
+  CHECK_H(h);
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) {
+    // VSFMSPostStepDT (:926-940): soln_prev_clm = soln_prev
+    h->x_committed = h->x_current;
+    return 0;
+  }
+  if (h->thermal) return thermal_post_step_dt(h->thermal) ? fail("thermal_post_step_dt failed") : 0;
+  return th_post_step_dt(h->th) ? fail("th_post_step_dt failed") : 0;
+}
+
+static int vsfm_fill_args(mppgpu_soe *h, VsfmArgs &A, double dt)
+{
+  memset(&A, 0, sizeof(A));
+  A.ncol = h->ncol; A.nlev = h->nlev;
+  A.uz = (h->orientation == MPPGPU_MESH_ALONG_GRAVITY) ? -1.0 : (h->orientation == MPPGPU_MESH_AGAINST_GRAVITY ? 1.0 : 0.0);
+  A.top_is_first = (h->orientation != MPPGPU_MESH_AGAINST_GRAVITY);
+  A.dtab = make_density_table(h->density_type, 273.15 + 25.0);       // RichardsODEPressureAuxType.F90:92
+  A.por = h->por.p; A.perm = h->perm.p; A.sat_res = h->sat_res.p; A.alpha = h->alpha.p; A.lam = h->lam.p; A.vgn = h->vgn.p;
+  A.pu = h->pu.p; A.ps = h->ps.p; A.b2 = h->b2.p; A.b3 = h->b3.p; A.dz = h->dz.p; A.area = h->area.p;
+  A.active = h->has_active ? h->active.p : nullptr;
+  A.frac_liq = h->frac_liq.p;
+  A.nss = (int)h->sss.size(); A.nbc = (int)h->bcs.size();
+  for (int k = 0; k < A.nss; ++k) { A.ss[k].value = h->sss[k]->value.p; A.ss[k].itype = h->sss[k]->itype; A.ss[k].region = h->sss[k]->region; A.ss[k].flux = nullptr; A.ss[k].mass_exc = nullptr; }
+  for (int k = 0; k < A.nbc; ++k) { A.bc[k].value = h->bcs[k]->value.p; A.bc[k].itype = h->bcs[k]->itype; A.bc[k].region = h->bcs[k]->region; A.bc[k].flux = h->bcs[k]->flux.p; A.bc[k].mass_exc = h->bcs[k]->mass_exc.p; }
+  A.liq_sat = h->liq_sat.p; A.pressure = h->pressure.p; A.mass = h->mass.p; A.smp = h->smp.p;
+  A.stat_its = h->stat_its.p; A.stat_reason = h->stat_reason.p; A.stat_cuts = h->stat_cuts.p; A.stat_nf = h->stat_nf.p;
+  A.col_mass = h->col_mass.p; A.col_err = h->col_err.p; A.col_src = h->col_src.p;
+  A.dt = dt; A.so = h->so;
+  return 0;
+}
+
+template <int GROUP>
+static void launch_vsfm_fast(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
+{
+  const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
+  if (sf == SATFUNC_VG)      vsfm_step_kernel<GROUP, SATFUNC_VG><<<nblocks, 128, 0, h->stream>>>(A);
+  else if (sf == SATFUNC_BC) vsfm_step_kernel<GROUP, SATFUNC_BC><<<nblocks, 128, 0, h->stream>>>(A);
+  else                       vsfm_step_kernel<GROUP, SATFUNC_SBC><<<nblocks, 128, 0, h->stream>>>(A);
+}
+
+static int vsfm_step(mppgpu_soe *h, double dt)
+{
+  if (!h->mesh_set || !h->soils_set) return fail("mppgpu_step_dt: mesh and soils must be set first");
+  if (!(dt > 0.0)) return fail("mppgpu_step_dt: dt must be positive");
+  VsfmArgs A;
+  vsfm_fill_args(h, A, dt);
+  // soln == soln_prev at entry; write to the spare buffer if the current one is the committed (soln_prev_clm) copy
+  A.x_in = h->x_current;
+  double *spare = (h->x_committed == h->xA.p) ? h->xB.p : h->xA.p;
+  A.x_out = (h->x_current == h->x_committed) ? spare : h->x_current;
+  int nblocks;
+  const int nlev = h->nlev;
+  if (nlev <= 32) {
+    const int group = (nlev <= 16) ? 16 : 32;
+    nblocks = nblk((long long)h->ncol * group, 128);
+  } else {
+    nblocks = nblk((long long)h->ncol, VSFM_GENERIC_WARPS);
+  }
+  if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
+  A.block_partials = h->block_partials.p;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  if (nlev <= 16)      launch_vsfm_fast<16>(h, A, nblocks);
+  else if (nlev <= 32) launch_vsfm_fast<32>(h, A, nblocks);
+  else {
+    const size_t smem = vsfm_generic_smem_bytes(nlev);
+    if (smem > 200 * 1024) return fail("mppgpu_step_dt: nlev = %d exceeds the generic kernel's shared-memory budget", nlev);
+    CK(cudaFuncSetAttribute(vsfm_step_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vsfm_step_generic_kernel<<<nblocks, 32 * VSFM_GENERIC_WARPS, smem, h->stream>>>(A, h->satfunc_name == 0 ? SATFUNC_VG : (h->satfunc_name == 1 ? SATFUNC_BC : SATFUNC_SBC));
+  }
+  CK(cudaGetLastError());
+  reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->block_partials.p, nblocks, h->red_out.p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->launches += 2;
+  h->x_current = A.x_out;
+  h->nblocks_last = nblocks;
+  CK(cudaMemcpyAsync(h->h_red, h->red_out.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  h->result_pending = true;
+  return 0;
+}
+
+extern "C" int mppgpu_step_dt_async(mppgpu_handle h, double dt, int nstep)
+{
+  CHECK_H(h);
+  (void)nstep;
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) return vsfm_step(h, dt);
+  if (h->thermal) return thermal_step(h, h->thermal, dt);
+  return th_step(h, h->th, dt);
+}
+
+extern "C" int mppgpu_step_result(mppgpu_handle h, int *converged, int *converged_reason)
+{
+  CHECK_H(h);
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  h->result_pending = false;
+  if (h->thermal) { if (converged) *converged = 1; if (converged_reason) *converged_reason = 0; return 0; }   // KSP path: tridiagonal solve cannot diverge
+  const double *r = h->h_red;
+  if (converged) *converged = (r[6] == 0.0) ? 1 : 0;
+  if (converged_reason) *converged_reason = (int)r[8];
+  return 0;
+}
+
+extern "C" int mppgpu_step_dt(mppgpu_handle h, double dt, int nstep, int *converged, int *converged_reason)
+{
+  if (mppgpu_step_dt_async(h, dt, nstep)) return 1;
+  return mppgpu_step_result(h, converged, converged_reason);
+}
+
+// ---- diagnostics --------------------------------------------------------------------------------------------------
+extern "C" int mppgpu_get_column_stats(mppgpu_handle h, int *newton_its, int *reasons, int *dt_cuts, int *nfuncs)
+{
+  CHECK_H(h);
+  const size_t nb = (size_t)h->ncol * sizeof(int);
+  if (newton_its) CK(cudaMemcpyAsync(newton_its, h->stat_its.p, nb, cudaMemcpyDeviceToHost, h->stream));
+  if (reasons)    CK(cudaMemcpyAsync(reasons, h->stat_reason.p, nb, cudaMemcpyDeviceToHost, h->stream));
+  if (dt_cuts)    CK(cudaMemcpyAsync(dt_cuts, h->stat_cuts.p, nb, cudaMemcpyDeviceToHost, h->stream));
+  if (nfuncs)     CK(cudaMemcpyAsync(nfuncs, h->stat_nf.p, nb, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+extern "C" int mppgpu_vsfm_mass_balance(mppgpu_handle h, double dt, double sums[4], double maxs[4])
+{
+  CHECK_H(h);
+  (void)dt;
+  if (h->soe_itype != MPPGPU_SOE_RE_ODE && !h->th) return fail("mppgpu_vsfm_mass_balance: not a flow SoE");
+  CK(cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < 4; ++k) { if (sums) sums[k] = h->h_red[k]; if (maxs) maxs[k] = h->h_red[4 + k]; }
+  return 0;
+}
+
+extern "C" int mppgpu_reduction_buffer_device(mppgpu_handle h, double **d_buf)
+{ CHECK_H(h); if (!d_buf) return fail("null"); *d_buf = h->red_out.p; return 0; }
+
+extern "C" int mppgpu_launch_count(mppgpu_handle h, long long *n) { CHECK_H(h); if (n) *n = h->launches; return 0; }
+extern "C" int mppgpu_last_step_ms(mppgpu_handle h, float *ms)
+{
+  CHECK_H(h);
+  CK(cudaStreamSynchronize(h->stream));
+  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  if (ms) *ms = h->last_ms;
+  return 0;
+}
+
+extern "C" int mppgpu_eval(mppgpu_handle h, double dt, const double *x_prev, const double *x, double *f, double *ja, double *jb, double *jc)
+{
+  CHECK_H(h);
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) return fail("mppgpu_eval: VSFM residual/Jacobian probes are exercised through StepDT parity (not implemented)");
+  if (h->th) return th_eval(h, h->th, dt, x_prev, x, f, ja, jb, jc);
+  return fail("mppgpu_eval: not available for the thermal SoE");
+}
+
+// thermal / TH set-soils entry points live next to their state
+extern "C" int mppgpu_thermal_set_soils(mppgpu_handle h, const double *watsat, const double *csol, const double *tkmg,
+                                        const double *tkdry, const int *lun_type, int nlevsoi, int istsoil)
+{
+  CHECK_H(h);
+  if (!h->thermal) return fail("mppgpu_thermal_set_soils: handle is not a thermal SoE");
+  if (!h->mesh_set) return fail("mppgpu_thermal_set_soils: set the mesh first");
+  return thermal_set_soils(h, h->thermal, watsat, csol, tkmg, tkdry, lun_type, nlevsoi, istsoil);
+}
+extern "C" int mppgpu_thermal_set_cnfac(mppgpu_handle h, double cnfac)
+{
+  CHECK_H(h);
+  if (!h->thermal) return fail("mppgpu_thermal_set_cnfac: handle is not a thermal SoE");
+  h->thermal->cnfac = cnfac; return 0;
+}
+extern "C" int mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
+                                   const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,
+                                   int satfunc_type, int density_type, int int_energy_enthalpy_type)
+{
+  CHECK_H(h);
+  if (!h->th) return fail("mppgpu_th_set_soils: handle is not a TH SoE");
+  if (!h->mesh_set) return fail("mppgpu_th_set_soils: set the mesh first");
+  return th_set_soils(h, h->th, watsat, hksat, bsw, sucsat, residual_sat, csol, tkdry, satfunc_type, density_type, int_energy_enthalpy_type);
+}
+
+#include "thermal_host.inl"
+#include "th_host.inl"

@@ -1,0 +1,249 @@
+"""Host-side mirrors of the reference's system-of-equations objects, over the C ABI.
+
+Method names follow the type-bound procedures every reference driver calls on
+``class(sysofeqns_base_type)`` (src/mpp/soe/SystemOfEquationsBaseType.F90:34-93) and on the
+MPP objects (src/mpp/mpp/MultiPhysicsProbVSFM.F90): ``AddConditionInGovEqn``, ``SetSoils``,
+``Restart``, ``SetDataFromCLM``, ``GetDataForCLM``, ``PreStepDT``, ``StepDT``, ``PostStepDT``.
+snake_case aliases are provided.  Everything here only marshals numpy arrays into
+libmppgpu.so; there is no Python or CPU compute path.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import constants as K
+from ._lib import MPPError, c_dp, c_ip, check, lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _ip(a):
+    return a.ctypes.data_as(c_ip)
+
+
+def _table(a, ncol, nlev):
+    """(ncol, nlev) array -> Fortran column-major flat buffer t[j*ncol + c]."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.shape != (ncol, nlev):
+        raise ValueError("soil table must have shape (ncol, nlev) = (%d, %d), got %s" % (ncol, nlev, a.shape))
+    return np.ascontiguousarray(a.T).reshape(-1)
+
+
+class _SoE:
+    soe_itype = None
+
+    def __init__(self, ncol, nlev, device=0):
+        self.L = lib()
+        self.ncol, self.nlev, self.ncells = int(ncol), int(nlev), int(ncol) * int(nlev)
+        self.h = C.c_void_p()
+        check(self.L.mppgpu_create(self.soe_itype, self.ncol, self.nlev, int(device), C.byref(self.h)))
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.L.mppgpu_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- setup -------------------------------------------------------------------------------------
+    def set_mesh(self, orientation, dz, area, col_active=None):
+        """dz: (ncol, nlev) [m]; area: (ncol,) [m^2] (MeshType.F90:173-269, 401-428)."""
+        dzt = _table(dz, self.ncol, self.nlev)
+        area = _f64(area)
+        if area.size != self.ncol:
+            raise ValueError("area must have ncol entries")
+        act = _i32(col_active) if col_active is not None else None
+        check(self.L.mppgpu_set_mesh(self.h, int(orientation), _dp(dzt), _dp(area), _ip(act) if act is not None else None))
+
+    SetMesh = set_mesh
+
+    def add_condition(self, ieqn, ss_or_bc, cond_type, region):
+        """soe%AddConditionInGovEqn(ieqn, COND_BC|COND_SS, name, units, cond_type, region) -> 1-based condition id."""
+        cid = C.c_int()
+        check(self.L.mppgpu_add_condition(self.h, int(ieqn), int(ss_or_bc), int(cond_type), int(region), C.byref(cid)))
+        return cid.value
+
+    AddConditionInGovEqn = add_condition
+
+    def set_tolerances(self, atol=1e-50, rtol=1e-8, stol=1e-10, max_it=50, max_funcs=10000):
+        check(self.L.mppgpu_set_tolerances(self.h, atol, rtol, stol, int(max_it), int(max_funcs)))
+
+    SNESSetTolerances = set_tolerances
+
+    def restart(self, x):
+        x = _f64(x)
+        check(self.L.mppgpu_restart(self.h, _dp(x), int(x.size)))
+
+    Restart = restart
+
+    # -- data exchange -----------------------------------------------------------------------------
+    def set_data(self, auxvar_type, var_type, cond_id, data, ieqn=1):
+        data = _f64(data)
+        check(self.L.mppgpu_set_data(self.h, int(ieqn), int(auxvar_type), int(var_type), int(cond_id), _dp(data), int(data.size)))
+
+    SetDataFromCLM = set_data
+
+    def get_data(self, auxvar_type, var_type, cond_id, n=None, ieqn=1, out=None):
+        if out is None:
+            out = np.empty(self.ncells if n is None else int(n), dtype=np.float64)
+        check(self.L.mppgpu_get_data(self.h, int(ieqn), int(auxvar_type), int(var_type), int(cond_id), _dp(out), int(out.size)))
+        return out
+
+    GetDataForCLM = get_data
+
+    def set_data_device(self, auxvar_type, var_type, cond_id, dev_ptr, n, ieqn=1):
+        check(self.L.mppgpu_set_data_device(self.h, int(ieqn), int(auxvar_type), int(var_type), int(cond_id), C.c_void_p(dev_ptr), int(n)))
+
+    def get_data_device(self, auxvar_type, var_type, cond_id, dev_ptr, n, ieqn=1):
+        check(self.L.mppgpu_get_data_device(self.h, int(ieqn), int(auxvar_type), int(var_type), int(cond_id), C.c_void_p(dev_ptr), int(n)))
+
+    # -- time stepping -----------------------------------------------------------------------------
+    def pre_step_dt(self):
+        check(self.L.mppgpu_pre_step_dt(self.h))
+
+    PreStepDT = pre_step_dt
+
+    def post_step_dt(self):
+        check(self.L.mppgpu_post_step_dt(self.h))
+
+    PostStepDT = post_step_dt
+
+    def step_dt(self, dt, nstep=1):
+        """soe%StepDT(dt, nstep, converged, converged_reason, ierr) -> (converged, converged_reason)."""
+        conv, reason = C.c_int(), C.c_int()
+        check(self.L.mppgpu_step_dt(self.h, float(dt), int(nstep), C.byref(conv), C.byref(reason)))
+        return bool(conv.value), reason.value
+
+    StepDT = step_dt
+
+    def step_dt_async(self, dt, nstep=1):
+        check(self.L.mppgpu_step_dt_async(self.h, float(dt), int(nstep)))
+
+    def step_result(self):
+        conv, reason = C.c_int(), C.c_int()
+        check(self.L.mppgpu_step_result(self.h, C.byref(conv), C.byref(reason)))
+        return bool(conv.value), reason.value
+
+    def set_stream(self, cuda_stream):
+        check(self.L.mppgpu_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        check(self.L.mppgpu_synchronize(self.h))
+
+    # -- diagnostics -------------------------------------------------------------------------------
+    def stats(self):
+        its, rs, cuts, nf = (np.zeros(self.ncol, dtype=np.int32) for _ in range(4))
+        check(self.L.mppgpu_get_column_stats(self.h, _ip(its), _ip(rs), _ip(cuts), _ip(nf)))
+        return {"newton_its": its, "reasons": rs, "dt_cuts": cuts, "nfuncs": nf}
+
+    def mass_balance(self, dt=0.0):
+        sums, maxs = np.zeros(4), np.zeros(4)
+        check(self.L.mppgpu_vsfm_mass_balance(self.h, float(dt), _dp(sums), _dp(maxs)))
+        return sums, maxs
+
+    def reduction_buffer_ptr(self):
+        p = C.c_void_p()
+        check(self.L.mppgpu_reduction_buffer_device(self.h, C.byref(p)))
+        return p.value
+
+    def launch_count(self):
+        n = C.c_longlong()
+        check(self.L.mppgpu_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def last_step_ms(self):
+        ms = C.c_float()
+        check(self.L.mppgpu_last_step_ms(self.h, C.byref(ms)))
+        return ms.value
+
+
+class VSFM(_SoE):
+    """sysofeqns_vsfm_type + mpp_vsfm_type for batches of independent soil columns."""
+    soe_itype = K.SOE_RE_ODE
+
+    def set_soils(self, watsat, hksat, bsw, sucsat, residual_sat, satfunc_type="van_genuchten", density_type=K.DENSITY_TGDPB01):
+        """VSFMMPPSetSoils (MultiPhysicsProbVSFM.F90:211-475); tables are (ncol, nlev)."""
+        if satfunc_type not in K.SATFUNC:
+            raise MPPError("ERROR:: Unknown vsfm_satfunc_type = " + str(satfunc_type))
+        t = [_table(x, self.ncol, self.nlev) for x in (watsat, hksat, bsw, sucsat, residual_sat)]
+        check(self.L.mppgpu_vsfm_set_soils(self.h, *[_dp(x) for x in t], K.SATFUNC[satfunc_type], int(density_type)))
+
+    VSFMMPPSetSoils = set_soils
+
+
+class Thermal(_SoE):
+    """sysofeqns_thermal_type (soil governing equation, KSP path)."""
+    soe_itype = K.SOE_THERMAL_TBASED
+
+    def set_soils(self, watsat, csol, tkmg, tkdry, lun_type, nlevsoi, istsoil=K.ISTSOIL):
+        """MPPThermalSetSoils (MultiPhysicsProbThermal.F90:76-208); tables are (ncol, nlev); lun_type is (ncol,)."""
+        t = [_table(x, self.ncol, self.nlev) for x in (watsat, csol, tkmg, tkdry)]
+        lt = _i32(lun_type)
+        check(self.L.mppgpu_thermal_set_soils(self.h, *[_dp(x) for x in t], _ip(lt), int(nlevsoi), int(istsoil)))
+
+    MPPThermalSetSoils = set_soils
+
+    def set_cnfac(self, cnfac):
+        check(self.L.mppgpu_thermal_set_cnfac(self.h, float(cnfac)))
+
+    def set_soln_prev(self, T):
+        self.restart(T)
+
+    SetSolnPrevCLM = set_soln_prev
+
+    def set_rdata(self, auxvar_type, var_type, cond_id, data):
+        self.set_data(auxvar_type, var_type, cond_id, data)
+
+    SetRDataFromCLM = set_rdata
+
+    def set_idata(self, auxvar_type, var_type, cond_id, data):
+        data = _i32(data)
+        check(self.L.mppgpu_set_idata(self.h, 1, int(auxvar_type), int(var_type), int(cond_id), _ip(data), int(data.size)))
+
+    SetIDataFromCLM = set_idata
+    SetBDataFromCLM = set_idata
+
+    def get_soln(self):
+        return self.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, -1)
+
+    GetSoln = get_soln
+
+
+class TH(_SoE):
+    """sysofeqns_th_type: Richards (ieqn 1) + enthalpy (ieqn 2) on the same columns."""
+    soe_itype = K.SOE_TH
+
+    def set_soils(self, watsat, hksat, bsw, sucsat, residual_sat, csol, tkdry, satfunc_type="van_genuchten",
+                  density_type=K.DENSITY_TGDPB01, int_energy_enthalpy_type=K.INT_ENERGY_ENTHALPY_CONSTANT):
+        t = [_table(x, self.ncol, self.nlev) for x in (watsat, hksat, bsw, sucsat, residual_sat, csol, tkdry)]
+        check(self.L.mppgpu_th_set_soils(self.h, *[_dp(x) for x in t], K.SATFUNC[satfunc_type], int(density_type),
+                                         int(int_energy_enthalpy_type)))
+
+    MPPTHSetSoils = set_soils
+
+    def restart(self, press, temp=None):
+        x = _f64(press) if temp is None else np.concatenate([_f64(press), _f64(temp)])
+        check(self.L.mppgpu_restart(self.h, _dp(x), int(x.size)))
+
+    def eval(self, dt, x_prev, x):
+        x_prev, x = _f64(x_prev), _f64(x)
+        n = self.ncells
+        f = np.zeros(2 * n)
+        ja, jb, jc = (np.zeros(4 * n) for _ in range(3))
+        check(self.L.mppgpu_eval(self.h, float(dt), _dp(x_prev), _dp(x), _dp(f), _dp(ja), _dp(jb), _dp(jc)))
+        return f, ja, jb, jc

@@ -54,6 +54,14 @@ def i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 
 
+def table(a, ncol, nlev):
+    """(ncol, nlev) array -> Fortran column-major flat buffer t[j*ncol + c] (the reference's (c,j) tables)."""
+    a = np.asarray(a, dtype=np.float64)
+    if a.shape != (ncol, nlev):
+        raise ValueError("table must have shape (ncol, nlev)")
+    return np.ascontiguousarray(a.T).reshape(-1)
+
+
 # ---- scalar physics helpers (for unit tests) ---------------------------------
 def density(p, t_K, itype):
     L = lib()
@@ -124,16 +132,16 @@ class OracleVSFM:
             pass
 
     def set_mesh(self, orientation, dz, area, col_active=None):
-        dz, area = f64(dz), f64(area)
-        assert dz.size == self.ncells and area.size == self.ncol
+        dz, area = table(dz, self.ncol, self.nlev), f64(area)
+        assert area.size == self.ncol
         ca = i32(col_active) if col_active is not None else None
         return self.L.orc_vsfm_set_mesh(self.h, int(orientation), dp(dz), dp(area), ip(ca) if ca is not None else None)
 
-    def add_condition(self, ss_or_bc, cond_type, region):
+    def add_condition(self, ieqn, ss_or_bc, cond_type, region):
         return self.L.orc_vsfm_add_condition(self.h, int(ss_or_bc), int(cond_type), int(region))
 
-    def set_soils(self, watsat, hksat, bsw, sucsat, residual_sat, satfunc_type, density_type):
-        a = [f64(x) for x in (watsat, hksat, bsw, sucsat, residual_sat)]
+    def set_soils(self, watsat, hksat, bsw, sucsat, residual_sat, satfunc_type="van_genuchten", density_type=2):
+        a = [table(x, self.ncol, self.nlev) for x in (watsat, hksat, bsw, sucsat, residual_sat)]
         rc = self.L.orc_vsfm_set_soils(self.h, *[dp(x) for x in a], SATFUNC_NAMES[satfunc_type], int(density_type))
         if rc:
             raise ValueError("set_soils rc=%d" % rc)
@@ -146,13 +154,13 @@ class OracleVSFM:
         assert press.size == self.ncells
         return self.L.orc_vsfm_restart(self.h, dp(press))
 
-    def set_data(self, auxvar_type, var_type, cond_id, data):
+    def set_data(self, auxvar_type, var_type, cond_id, data, ieqn=1):
         data = f64(data)
         rc = self.L.orc_vsfm_set_data(self.h, int(auxvar_type), int(var_type), int(cond_id), dp(data), int(data.size))
         if rc:
             raise ValueError("set_data rc=%d" % rc)
 
-    def get_data(self, auxvar_type, var_type, cond_id, n=None):
+    def get_data(self, auxvar_type, var_type, cond_id, n=None, ieqn=1):
         n = self.ncells if n is None else n
         out = np.empty(n, dtype=np.float64)
         rc = self.L.orc_vsfm_get_data(self.h, int(auxvar_type), int(var_type), int(cond_id), dp(out), int(n))

@@ -1,0 +1,157 @@
+"""Problem recipes shared by the oracle and the CUDA library (same call surface on both).
+
+Each builder follows a reference driver:
+  celia          src/driver/standalone/vsfm/vsfm_celia1990_problem.F90
+  elm_vsfm_batch src/driver/alm/MPPVSFMALM_Initialize.F90 (mesh :401-530, conditions :814-858, IC :1058-1060)
+                 + SURVEY.md section 8(d) synthetic inputs (seed 20240607)
+"""
+import numpy as np
+
+from mpp_b200 import constants as K
+
+SEED = 20240607
+
+
+# ---------------------------------------------------------------------------------------------------
+# Celia et al. (1990) infiltration column -- config #1
+# ---------------------------------------------------------------------------------------------------
+def build_celia(cls, nz=100, **kw):
+    p = cls(1, nz, **kw)
+    dz = np.full((1, nz), 1.0 / nz)                                   # z_column = 1 m, MeshCreate :198-200
+    p.set_mesh(K.MESH_AGAINST_GRAVITY, dz, np.array([1.0]))
+    top = p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS)      # :252-254
+    bot = p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS)   # :256-258
+    porosity, lam, alpha, perm = 0.368, 0.5, 3.4257e-4, 8.3913e-12    # :295-298
+    vish2o, denh2o, grav = 0.001002, 1000.0, K.GRAV
+    hksat = perm / vish2o * (denh2o * grav) / 0.001                   # :325
+    sucsat = 1.0 / (alpha * K.GRAVITY_CONSTANT)                       # :327
+    full = lambda v: np.full((1, nz), v)
+    p.set_soils(full(porosity), full(hksat), full(1.0 / lam), full(sucsat), full(0.2772),
+                "van_genuchten", K.DENSITY_TGDPB01)                   # :331-335
+    p.restart(np.full(nz, 3.5355e3))                                  # :358-362
+    return p, top, bot
+
+
+def run_celia(p, top, bot, nstep=24, dt=3600.0):
+    its = []
+    for istep in range(nstep):
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, top, np.array([9.3991e4]))    # :383-394
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, bot, np.array([3.5355e3]))
+        conv, reason = p.step_dt(dt, istep + 1)
+        assert conv, "Celia step %d did not converge (reason %d)" % (istep + 1, reason)
+        its.append(int(p.stats()["newton_its"][0]))
+    P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, -1)
+    S = p.get_data(K.AUXVAR_INTERNAL, K.VAR_LIQ_SAT, -1)
+    return P, S, its
+
+
+# ---------------------------------------------------------------------------------------------------
+# regression file format -- src/driver/standalone/util/regression.F90:76-124
+# ---------------------------------------------------------------------------------------------------
+def regression_block(name, category, data, num_cells):
+    def fmt(v):
+        v = 0.0 if abs(v) < 1e-50 else v
+        s = "%.12E" % v                       # 13 significant digits; Fortran e21.13 prints them as 0.dddddddddddddE+ee
+        mant, exp = s.split("E")
+        sign = "-" if mant.startswith("-") else ""
+        digits = mant.replace("-", "").replace(".", "")
+        e = int(exp) + 1
+        if float(v) == 0.0:
+            e = 0
+        return ("%s0.%sE%+03d" % (sign, digits[:13], e)).rjust(21)
+    lines = ["[%s]" % name, "category = %s" % category,
+             "min = " + fmt(np.min(data)), "max = " + fmt(np.max(data)), "mean = " + fmt(np.sum(data) / data.size)]
+    n = min(num_cells, data.size)
+    inc = data.size // n
+    for cell in range(1, data.size + 1, inc):
+        lines.append("cell %4d = %s" % (cell, fmt(data[cell - 1])))
+    lines.append("")
+    return lines
+
+
+def parse_regression(path):
+    out, cur = {}, None
+    for line in open(path):
+        line = line.strip()
+        if not line:
+            continue
+        if line.startswith("["):
+            cur = line[1:-1]
+            out[cur] = {}
+        elif "=" in line:
+            k, v = [t.strip() for t in line.split("=")]
+            if k != "category":
+                out[cur][k] = float(v)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# ELM-like batched columns -- configs #3/#4
+# ---------------------------------------------------------------------------------------------------
+def elm_layers(nlev=15):
+    """ELM node depths z_j = 0.025 (exp(0.5 (j - 0.5)) - 1), interfaces at mid-points."""
+    j = np.arange(1, nlev + 1)
+    z = 0.025 * (np.exp(0.5 * (j - 0.5)) - 1.0)
+    zi = np.zeros(nlev + 1)
+    zi[1:nlev] = 0.5 * (z[:-1] + z[1:])
+    zi[nlev] = z[-1] + 0.5 * (z[-1] - z[-2])
+    dz = zi[1:] - zi[:-1]
+    return z, zi, dz
+
+
+def elm_vsfm_inputs(ncol, nlev=15, seed=SEED, satfunc="van_genuchten"):
+    rng = np.random.default_rng(seed)
+    z, zi, dz = elm_layers(nlev)
+    d = {}
+    d["dz"] = np.tile(dz, (ncol, 1))
+    d["area"] = np.ones(ncol)
+    d["watsat"] = rng.uniform(0.35, 0.55, (ncol, nlev))
+    d["hksat"] = np.exp(rng.uniform(np.log(5e-4), np.log(5e-2), (ncol, nlev)))      # mm/s
+    d["bsw"] = rng.uniform(3.0, 12.0, (ncol, nlev))
+    d["sucsat"] = rng.uniform(50.0, 600.0, (ncol, nlev))                            # mm
+    d["residual_sat"] = np.zeros((ncol, nlev))                                      # MPPVSFMALM_Initialize.F90:966
+    zwt = rng.uniform(1.0, 20.0, ncol)
+    depth = 0.5 * (zi[:-1] + zi[1:])
+    # MPPVSFMALM_Initialize.F90:1058-1060
+    d["press_ic"] = (K.PRESSURE_REF + 997.16 * K.GRAVITY_CONSTANT * (-zwt[:, None] - (-depth[None, :]))).reshape(-1)
+    d["infil"] = rng.uniform(0.0, 2e-4, ncol)                                       # kg/s into the top cell
+    et_tot = -rng.uniform(0.0, 8e-5, ncol)
+    w = np.exp(-z[:10]); w /= w.sum()
+    et = np.zeros((ncol, nlev)); et[:, :10] = et_tot[:, None] * w[None, :]
+    d["et"] = et.reshape(-1)
+    d["dew"] = np.zeros(ncol); d["snow"] = np.zeros(ncol); d["sublim"] = np.zeros(ncol)
+    d["drain"] = np.zeros(ncol * nlev)
+    d["frac_liq"] = np.ones(ncol * nlev)
+    d["satfunc"] = satfunc
+    d["ncol"], d["nlev"] = ncol, nlev
+    return d
+
+
+def build_elm_vsfm(cls, d, **kw):
+    ncol, nlev = d["ncol"], d["nlev"]
+    p = cls(ncol, nlev, **kw)
+    p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"])
+    ids = {}
+    # MPPVSFMALM_Initialize.F90:836-858, in this order
+    ids["infil"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
+    ids["et"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_CELLS)
+    ids["dew"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
+    ids["drain"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_CELLS)
+    ids["snow"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
+    ids["sublim"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
+    p.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], d["satfunc"], K.DENSITY_TGDPB01)
+    p.restart(d["press_ic"])
+    return p, ids
+
+
+def elm_vsfm_step(p, ids, d, dt=1800.0, nstep=1, scale=1.0):
+    """One ELM coupling step as MPPVSFMALM_Solve does it (MPPVSFMALM_Driver.F90:379-463, 603, 642, 674-705, 935)."""
+    for name in ("infil", "et", "dew", "drain", "snow", "sublim"):
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids[name], d[name] * scale)
+    p.set_data(K.AUXVAR_INTERNAL, K.VAR_FRAC_LIQ_SAT, 1, d["frac_liq"])
+    p.pre_step_dt()
+    conv, reason = p.step_dt(dt, nstep)
+    out = {k: p.get_data(K.AUXVAR_INTERNAL, v, 1) for k, v in
+           (("sat", K.VAR_LIQ_SAT), ("mass", K.VAR_MASS), ("smp", K.VAR_SOIL_MATRIX_POT), ("pressure", K.VAR_PRESSURE))}
+    p.post_step_dt()
+    return conv, reason, out

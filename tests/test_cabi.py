@@ -1,0 +1,49 @@
+"""The C-ABI shared library loads and exports every symbol include/mppgpu.h declares (no compute calls: no GPU here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "mppgpu.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mppgpu_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_header_declares_the_python_binding_exactly():
+    from mpp_b200 import _lib
+    assert sorted(_lib.EXPORTS) == declared_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    from mpp_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build libmppgpu.so first: python -c 'import __graft_entry__ as g; g.build()'"
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(L, name), name
+    L.mppgpu_version.restype = C.c_int
+    assert L.mppgpu_version() >= 100
+
+
+def test_no_cpu_fallback_without_a_device():
+    """Without a CUDA device the library must fail loudly, never compute on the CPU."""
+    import mpp_b200
+    from mpp_b200._lib import lib
+    if lib().mppgpu_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(mpp_b200.MPPError) as e:
+        mpp_b200.VSFM(4, 15)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    """oracle/ is test infrastructure: nothing under mpp_b200/ may reference it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "mpp_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".cpp", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "mpp_oracle" not in text and "import oracle" not in text and "from oracle" not in text, f

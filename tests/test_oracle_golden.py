@@ -1,0 +1,128 @@
+"""Pin the CPU oracle to the reference's own golden vectors."""
+import numpy as np
+import pytest
+
+import problems as PB
+from mpp_b200 import constants as K
+
+
+def test_eos_density_known_answers(oracle, golden):
+    # src/tests/test_eos_{constant,tgdp01,ifc67}_density.F90:16-25
+    g = golden["eos_density"]
+    for name, itype in (("constant", K.DENSITY_CONSTANT), ("tgdpb01", K.DENSITY_TGDPB01), ("ifc67", K.DENSITY_IFC67)):
+        den, ddp, ddt = oracle.density(g["p"], g["t_K"], itype)
+        assert abs(den - g[name]["den"]) < g["tol"]["den"]
+        assert abs(ddp - g[name]["dden_dp"]) < g["tol"]["dden_dp"]
+        assert abs(ddt - g[name]["dden_dT"]) < g["tol"]["dden_dT"]
+
+
+def _assert_matches_printed(ours, ref_val, tol_abs=None):
+    """The baseline holds 13 printed significant digits; require agreement to the last printed digit
+    (and to the reference's own absolute tolerance when that is looser)."""
+    quantum = 10.0 ** (np.floor(np.log10(abs(ref_val))) - 12) if ref_val != 0 else 1e-13
+    tol = max(0.51 * quantum, tol_abs or 0.0)
+    assert abs(ours - ref_val) <= tol, (ours, ref_val, tol)
+
+
+@pytest.mark.parametrize("per_column", [False, True])
+def test_celia1990_reproduces_reference_baseline(oracle, golden, per_column):
+    # regression_tests/vsfm/vsfm_celia1990.regression.baseline (pressure 1e-10 abs: vsfm.cfg:4-5)
+    p, top, bot = PB.build_celia(oracle.OracleVSFM, per_column=per_column)
+    P, S, its = PB.run_celia(p, top, bot)
+    assert sum(its) == 226 and its[0] == 34
+    for name, data, tol in (("liquid_pressure", P, 1e-10), ("liquid_saturation", S, 1e-16)):
+        ref = golden["vsfm_celia1990"][name]
+        _assert_matches_printed(data.min(), ref["min"], tol)
+        _assert_matches_printed(data.max(), ref["max"], tol)
+        _assert_matches_printed(data.sum() / data.size, ref["mean"], tol)
+        for key, val in ref.items():
+            if key.startswith("cell"):
+                _assert_matches_printed(data[int(key.split()[1]) - 1], val, tol)
+
+
+def test_celia_regression_file_format(oracle, golden):
+    # src/driver/standalone/util/regression.F90:76-124 -- the writer must reproduce the baseline text
+    p, top, bot = PB.build_celia(oracle.OracleVSFM, per_column=False)
+    P, S, _ = PB.run_celia(p, top, bot)
+    lines = PB.regression_block("liquid_pressure", "pressure", P, 5)
+    assert lines[0] == "[liquid_pressure]" and lines[1] == "category = pressure"
+    assert lines[2] == "min =   0.3535500000000E+04"
+    assert lines[5].startswith("cell    1 = ") and lines[9].startswith("cell   81 = ")
+    assert lines[3] == "max =   0.9398362808479E+05"
+
+
+def test_saturation_curves_are_consistent(oracle):
+    # no reference unit test exists for SaturationFunction.F90; check analytic derivatives against central differences
+    rng = np.random.default_rng(3)
+    for name in ("van_genuchten", "brooks_corey", "smooth_brooks_corey_bz2", "smooth_brooks_corey_bz3"):
+        for _ in range(20):
+            alpha = 1.0 / (rng.uniform(50, 600) * K.GRAV)
+            lam = 1.0 / rng.uniform(3, 12)
+            sp = oracle.satparams(name, 0.05, alpha, lam)
+            pc = -rng.uniform(1.2, 50.0) / alpha
+            press = K.PRESSURE_REF + pc
+            h = 1e-4 * abs(pc)
+            s, ds = oracle.press_to_sat(sp, press)
+            k, dk = oracle.press_to_relperm(sp, press)
+            sp_, _ = oracle.press_to_sat(sp, press + h); sm_, _ = oracle.press_to_sat(sp, press - h)
+            kp_, _ = oracle.press_to_relperm(sp, press + h); km_, _ = oracle.press_to_relperm(sp, press - h)
+            assert 0 < s < 1 and 0 < k < 1
+            assert abs((sp_ - sm_) / (2 * h) - ds) <= 1e-6 * abs(ds) + 1e-18
+            assert abs((kp_ - km_) / (2 * h) - dk) <= 1e-5 * abs(dk) + 1e-22
+        # saturated branch
+        s, ds = oracle.press_to_sat(sp, K.PRESSURE_REF + 10.0)
+        assert s == 1.0 and ds == 0.0
+
+
+def test_sbc_smoothing_is_continuous(oracle):
+    # SatFunc_Set_SBC_bz2/bz3 choose pu so that the cubic joins Brooks-Corey with matching value at pu (:296-372)
+    alpha, lam = 1.0 / (200.0 * K.GRAV), 0.2
+    for name in ("smooth_brooks_corey_bz2", "smooth_brooks_corey_bz3"):
+        sp = oracle.satparams(name, 0.0, alpha, lam)
+        assert sp.sbc_pu < sp.sbc_ps < 0
+        eps = 1e-9 * abs(sp.sbc_pu)
+        s0, _ = oracle.press_to_sat(sp, K.PRESSURE_REF + sp.sbc_pu - eps)
+        s1, _ = oracle.press_to_sat(sp, K.PRESSURE_REF + sp.sbc_pu + eps)
+        assert abs(s0 - s1) < 1e-8
+        s2, _ = oracle.press_to_sat(sp, K.PRESSURE_REF + sp.sbc_ps - eps)
+        assert abs(s2 - 1.0) < 1e-8
+
+
+def test_elm_like_batch_global_vs_per_column(oracle):
+    """The reference runs ONE SNES over all columns of a rank (global norms, one lambda, one dt cut); the GPU runs
+    one per column.  Both stop at rtol = 1e-8 of their own ||F0||, so at the default tolerances the two answers differ
+    at the O(rtol) level (the reference's own answer depends on how columns are dealt to MPI ranks at that level);
+    with the tolerances tightened the fixed points agree to 1e-10 relative (SURVEY.md section 7 hard part (a))."""
+    d = PB.elm_vsfm_inputs(24, 15)
+
+    def run(per_column, tight):
+        p, ids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=per_column)
+        if tight:
+            p.set_tolerances(1e-50, 1e-10, 1e-16, 50, 10000)
+        for step in range(3):
+            conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, step + 1)
+            assert conv and reason > 0
+        return out
+
+    def relmax(a, b):
+        return np.max(np.abs(a - b) / np.maximum(np.abs(a), 1e-300))
+
+    loose = {pc: run(pc, False) for pc in (False, True)}
+    tight = {pc: run(pc, True) for pc in (False, True)}
+    for k in ("pressure", "sat", "mass"):
+        assert relmax(loose[False][k], loose[True][k]) < 1e-6, k
+        assert relmax(tight[False][k], tight[True][k]) < 1e-10, k
+        assert relmax(tight[True][k], loose[True][k]) < 1e-6, k
+
+
+def test_elm_like_mass_balance(oracle):
+    # MPPVSFMALM_Driver.F90:860-863: |m_beg - m_end + sum(q) dt| < 1e-5 kg per column
+    d = PB.elm_vsfm_inputs(16, 15)
+    p, ids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True)
+    conv, reason, out0 = PB.elm_vsfm_step(p, ids, d, 1800.0, 1)
+    m0 = out0["mass"].reshape(16, 15).sum(1)
+    conv, reason, out1 = PB.elm_vsfm_step(p, ids, d, 1800.0, 2)
+    m1 = out1["mass"].reshape(16, 15).sum(1)
+    q = d["infil"] + d["et"].reshape(16, 15).sum(1)
+    err = np.abs(m0 - m1 + q * 1800.0)
+    assert conv and err.max() < 1e-5

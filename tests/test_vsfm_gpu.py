@@ -1,0 +1,193 @@
+"""VSFM parity: the CUDA path (through the C ABI) against the oracle on identical inputs, and against the
+reference's own Celia-1990 baseline.  Tolerance: 1e-10 relative on pressure / saturation / mass
+(BASELINE.json north_star); Celia additionally to the 13 printed digits of the reference baseline."""
+import numpy as np
+import pytest
+
+import problems as PB
+from mpp_b200 import constants as K
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+@pytest.fixture(scope="module")
+def mpp():
+    import mpp_b200
+    from mpp_b200._lib import lib
+    assert lib().mppgpu_device_count() > 0, "no CUDA device: the gpu tests must run on the B200 box"
+    return mpp_b200
+
+
+def _printed_ok(ours, ref_val, tol_abs):
+    quantum = 10.0 ** (np.floor(np.log10(abs(ref_val))) - 12)
+    return abs(ours - ref_val) <= max(0.51 * quantum, tol_abs)
+
+
+def test_celia1990_generic_kernel_vs_reference_baseline(mpp, golden, oracle):
+    # nz = 100 > 32 layers -> vsfm_step_generic_kernel
+    p, top, bot = PB.build_celia(mpp.VSFM)
+    P, S, its = PB.run_celia(p, top, bot)
+    o, ot, ob = PB.build_celia(oracle.OracleVSFM, per_column=True)
+    Po, So, its_o = PB.run_celia(o, ot, ob)
+    assert its == its_o and sum(its) == 226
+    assert relmax(P, Po) < RTOL and relmax(S, So) < RTOL
+    for name, data, tol in (("liquid_pressure", P, 1e-10), ("liquid_saturation", S, 1e-16)):
+        ref = golden["vsfm_celia1990"][name]
+        assert _printed_ok(data.min(), ref["min"], tol) and _printed_ok(data.max(), ref["max"], tol)
+        assert _printed_ok(data.sum() / data.size, ref["mean"], tol)
+        for key, val in ref.items():
+            if key.startswith("cell"):
+                assert _printed_ok(data[int(key.split()[1]) - 1], val, tol), (name, key)
+
+
+@pytest.mark.parametrize("nz", [12, 16, 30])
+def test_celia_short_columns_fast_kernel(mpp, oracle, nz):
+    # same physics on <= 32 layers -> vsfm_step_kernel<16> / <32>, Dirichlet top and bottom
+    p, top, bot = PB.build_celia(mpp.VSFM, nz=nz)
+    o, ot, ob = PB.build_celia(oracle.OracleVSFM, nz=nz, per_column=True)
+    P, S, its = PB.run_celia(p, top, bot, nstep=6)
+    Po, So, its_o = PB.run_celia(o, ot, ob, nstep=6)
+    assert relmax(P, Po) < RTOL and relmax(S, So) < RTOL
+    assert its == its_o
+
+
+@pytest.mark.parametrize("satfunc", ["van_genuchten", "brooks_corey", "smooth_brooks_corey_bz2", "smooth_brooks_corey_bz3"])
+def test_elm_like_batch_matches_oracle(mpp, oracle, satfunc):
+    ncol = 1000 if satfunc == "van_genuchten" else 300
+    d = PB.elm_vsfm_inputs(ncol, 15, satfunc=satfunc)
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
+    for step in range(3):
+        conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, step + 1)
+        convo, reasono, outo = PB.elm_vsfm_step(o, oids, d, 1800.0, step + 1)
+        assert conv == convo and conv
+        for k in ("pressure", "sat", "mass"):
+            assert relmax(out[k], outo[k]) < RTOL, (satfunc, step, k)
+        assert np.max(np.abs(out["smp"] - outo["smp"])) < 1e-9 * max(1.0, np.max(np.abs(outo["smp"])))
+        sg, so_ = p.stats(), o.stats()
+        # identical algorithm => identical iteration / evaluation counts except where a test sits on a rounding edge
+        assert np.mean(sg["newton_its"] != so_["newton_its"]) < 0.01
+        assert np.all(sg["dt_cuts"] == so_["dt_cuts"])
+        assert reason == reasono or (reason > 0 and reasono > 0)
+
+
+def test_elm_like_mass_balance_and_reductions(mpp, oracle):
+    # MPPVSFMALM_Driver.F90:860-863 per-column check + the rank-local reduction buffer
+    ncol = 2048 + 37     # ragged: last block partially filled
+    d = PB.elm_vsfm_inputs(ncol, 15)
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    PB.elm_vsfm_step(p, ids, d, 1800.0, 1)
+    m0 = p.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1).reshape(ncol, 15).sum(1)
+    conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, 2)
+    m1 = out["mass"].reshape(ncol, 15).sum(1)
+    q = d["infil"] + d["et"].reshape(ncol, 15).sum(1)
+    err = np.abs(m0 - m1 + q * 1800.0)
+    assert conv and err.max() < 1e-5
+    sums, maxs = p.mass_balance(1800.0)
+    assert abs(sums[0] - m0.sum()) < 1e-9 * m0.sum() and abs(sums[1] - m1.sum()) < 1e-9 * m1.sum()
+    assert abs(sums[2] - (q * 1800.0).sum()) < 1e-9 * np.abs(q * 1800.0).sum()
+    assert abs(maxs[0] - err.max()) < 1e-7 and maxs[2] == 0.0
+    assert maxs[1] == p.stats()["newton_its"].max()
+
+
+def test_ragged_and_edge_shapes(mpp, oracle):
+    # nlev = 1 (no internal connection), nlev = 16 (full group), nlev = 17..32 (GROUP = 32), ncol = 1
+    for ncol, nlev in ((1, 1), (3, 2), (5, 16), (7, 17), (2, 32), (33, 15)):
+        d = PB.elm_vsfm_inputs(ncol, nlev) if nlev >= 11 else None
+        if d is None:
+            rng = np.random.default_rng(nlev)
+            d = PB.elm_vsfm_inputs(ncol, 15)
+            for k in ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat"):
+                d[k] = d[k][:, :nlev].copy()
+            d["press_ic"] = d["press_ic"].reshape(ncol, 15)[:, :nlev].reshape(-1).copy()
+            d["et"] = np.zeros(ncol * nlev); d["drain"] = np.zeros(ncol * nlev); d["frac_liq"] = np.ones(ncol * nlev)
+            d["nlev"] = nlev
+        p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+        o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True)
+        for step in range(2):
+            conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, step + 1)
+            convo, reasono, outo = PB.elm_vsfm_step(o, oids, d, 1800.0, step + 1)
+            assert conv == convo
+            for k in ("pressure", "sat", "mass"):
+                assert relmax(out[k], outo[k]) < RTOL, (ncol, nlev, k)
+
+
+def test_inactive_columns_are_left_untouched(mpp):
+    d = PB.elm_vsfm_inputs(64, 15)
+    mppmod = mpp
+    p = mppmod.VSFM(64, 15)
+    active = np.ones(64, dtype=np.int32); active[::3] = 0
+    p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"], col_active=active)
+    cid = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
+    p.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], "van_genuchten", K.DENSITY_TGDPB01)
+    p.restart(d["press_ic"])
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, cid, d["infil"])
+    conv, reason = p.step_dt(1800.0, 1)
+    P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1).reshape(64, 15)
+    sat = p.get_data(K.AUXVAR_INTERNAL, K.VAR_LIQ_SAT, 1).reshape(64, 15)
+    assert conv
+    assert np.all(sat[active == 0] == 0.0) and np.all(sat[active == 1] > 0.0)     # mailbox of inactive cells never written
+    assert np.all(P[active == 0] == 0.0)
+
+
+def test_dt_cut_path_matches_oracle(mpp, oracle):
+    """Force SNES failures (max_it = 2) so the dt-halving branch of SOEBaseStepDT_SNES (:500-507) runs."""
+    d = PB.elm_vsfm_inputs(200, 15)
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
+    for s in (p, o):
+        s.set_tolerances(1e-50, 1e-8, 1e-10, 2, 10000)
+    conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, 1, scale=5.0)
+    convo, reasono, outo = PB.elm_vsfm_step(o, oids, d, 1800.0, 1, scale=5.0)
+    sg, so_ = p.stats(), o.stats()
+    assert so_["dt_cuts"].max() > 0, "test problem no longer triggers a dt cut"
+    assert np.array_equal(sg["dt_cuts"], so_["dt_cuts"])
+    assert conv == convo
+    ok = so_["reasons"] > 0
+    Pg, Po = out["pressure"].reshape(200, 15), outo["pressure"].reshape(200, 15)
+    assert relmax(Pg[ok], Po[ok]) < 1e-8          # sub-stepped answers: both sides re-converge each sub-step to rtol
+
+
+def test_pre_post_step_dt_rollback(mpp):
+    """PreStepDT restores soln from soln_prev_clm (retry loop of MPPVSFMALM_Driver.F90:628-923)."""
+    d = PB.elm_vsfm_inputs(128, 15)
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    conv, reason, out1 = PB.elm_vsfm_step(p, ids, d, 1800.0, 1)      # includes PostStepDT: committed
+    for name in ("infil", "et", "dew", "drain", "snow", "sublim"):
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids[name], d[name])
+    p.pre_step_dt(); p.step_dt(1800.0, 2)
+    a = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1)
+    p.pre_step_dt(); p.step_dt(1800.0, 2)                              # retry from the same committed state
+    b = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1)
+    assert np.array_equal(a, b)
+    p.step_dt(1800.0, 3)                                               # no PreStepDT: continues from the new state
+    c = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1)
+    assert not np.array_equal(b, c)
+
+
+def test_error_behaviour(mpp):
+    p = mpp.VSFM(4, 15)
+    with pytest.raises(mpp.MPPError):
+        p.step_dt(1800.0, 1)                      # no mesh / soils yet
+    with pytest.raises(mpp.MPPError):
+        p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)   # mesh first
+    d = PB.elm_vsfm_inputs(4, 15)
+    p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"])
+    with pytest.raises(mpp.MPPError):
+        p.add_condition(1, K.COND_BC, K.COND_HEAT_FLUX, K.SOIL_TOP_CELLS)   # not a Richards BC
+    bad = d["bsw"].copy(); bad[0, 0] = 0.4                                  # lambda = 2.5 > 1: SatFunc_Set_VG aborts
+    with pytest.raises(mpp.MPPError):
+        p.set_soils(d["watsat"], d["hksat"], bad, d["sucsat"], d["residual_sat"], "van_genuchten", K.DENSITY_TGDPB01)
+    with pytest.raises(mpp.MPPError):
+        p.restart(np.zeros(7))
+    cid = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
+    with pytest.raises(mpp.MPPError):
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, cid, np.zeros(5))    # size(data_1d) > nauxvar
+    with pytest.raises(mpp.MPPError):
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, cid + 1, np.zeros(4))
