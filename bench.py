@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the VSFM hot path (BASELINE.json: soil column-timesteps/s, fp64, Newton-converged).
+
+    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host cores
+
+Workload (BASELINE.json configs[3]): 4 M synthetic ELM-like soil columns x 15 layers, van Genuchten curves,
+Tanaka density, six COND_MASS_RATE source/sinks, dt = 1800 s, SNES tolerances = reference defaults, sharded by
+column over the N GPUs of one box (strong scaling; one process per GPU).  One "step" = one ELM coupling step =
+PreStepDT + StepDT + PostStepDT over the whole batch (MPPVSFMALM_Driver.F90:603-935).
+
+Prints ONE JSON line (rank 0).  `value` is timed with all inputs resident in HBM; `e2e` repeats the same steps
+through the C ABI with HOST buffers (SetDataFromCLM x7 in, GetDataForCLM x4 out, as MPPVSFMALM_Solve does).
+The reference itself (Fortran + PETSc + MPI) cannot be built in this image, so `cpu_baseline` / `--impl reference`
+time the oracle -- the C restatement of the reference algorithm (oracle/, kind "port") -- on the box's host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import problems as PB  # noqa: E402
+from mpp_b200 import constants as K  # noqa: E402
+
+NLEV = 15
+DT = 1800.0
+CHUNK = 65536                      # columns per seeded chunk (shards are unions of chunks)
+ALG_BYTES_PER_COLSTEP = 1224       # SURVEY.md section 8(d), VSFM-VG base variant
+SS_NAMES = ("infil", "et", "dew", "drain", "snow", "sublim")
+
+
+def shard_inputs(c0, c1):
+    """Columns [c0, c1) of the global seeded batch: chunk k uses seed SEED + k so any rank builds only its shard."""
+    parts = []
+    k0, k1 = c0 // CHUNK, (c1 - 1) // CHUNK
+    for k in range(k0, k1 + 1):
+        d = PB.elm_vsfm_inputs(CHUNK, NLEV, seed=PB.SEED + k)
+        lo, hi = max(c0, k * CHUNK) - k * CHUNK, min(c1, (k + 1) * CHUNK) - k * CHUNK
+        parts.append((d, lo, hi))
+    out = {"ncol": c1 - c0, "nlev": NLEV, "satfunc": "van_genuchten"}
+    for key in ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat"):
+        out[key] = np.concatenate([d[key][lo:hi] for d, lo, hi in parts], axis=0)
+    for key in ("area", "infil", "dew", "snow", "sublim"):
+        out[key] = np.concatenate([d[key][lo:hi] for d, lo, hi in parts])
+    for key in ("press_ic", "et", "drain", "frac_liq"):
+        out[key] = np.concatenate([d[key].reshape(CHUNK, NLEV)[lo:hi].reshape(-1) for d, lo, hi in parts])
+    return out
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush(); self.f.seek(0)
+        sm, smax, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            t = [x.strip() for x in line.split(",")]
+            if len(t) < 9:
+                continue
+            try:
+                sm.append(float(t[1])); smax.append(float(t[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def set_forcing_host(p, ids, d):
+    for name in SS_NAMES:
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids[name], d[name])
+    p.set_data(K.AUXVAR_INTERNAL, K.VAR_FRAC_LIQ_SAT, 1, d["frac_liq"])
+
+
+def cpu_baseline(steps, warmup, target_seconds=20.0):
+    """The oracle (reference algorithm, per-column SNES) on a bounded column sample with every host thread."""
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    ncol = 4096
+    d = shard_inputs(0, ncol)
+    o, ids = PB.build_elm_vsfm(O.OracleVSFM, d, per_column=True, nthreads=cores)
+    t0 = time.perf_counter()
+    PB.elm_vsfm_step(o, ids, d, DT, 1)
+    probe = time.perf_counter() - t0                       # first (most expensive) step on 4096 columns
+    # size the sample so that warmup + steps take about target_seconds
+    ncol = int(min(1 << 20, max(4096, 4096 * target_seconds / max(probe, 1e-3) / (steps + warmup) * 2.0)))
+    ncol = (ncol // 4096) * 4096
+    d = shard_inputs(0, ncol)
+    o, ids = PB.build_elm_vsfm(O.OracleVSFM, d, per_column=True, nthreads=cores)
+    for s in range(warmup):
+        PB.elm_vsfm_step(o, ids, d, DT, s + 1)
+    t0 = time.perf_counter()
+    for s in range(steps):
+        conv, reason, _ = PB.elm_vsfm_step(o, ids, d, DT, warmup + s + 1)
+    el = time.perf_counter() - t0
+    return {"value": ncol * steps / el, "unit": "column-timesteps/s", "cores": cores, "kind": "port",
+            "sample": "%d of the benchmark's columns (global columns 0..%d), same %d warm-up + %d timed steps, "
+                      "oracle/ C restatement of the reference algorithm (per-column SNES newtonls+bt, Thomas), OpenMP over columns; "
+                      "the Fortran+PETSc reference cannot be built in this image" % (ncol, ncol - 1, warmup, steps),
+            "seconds": el, "converged": bool(conv)}, ncol, el
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb, ncol, el = cpu_baseline(args.steps, args.warmup, target_seconds=30.0)
+    line = {"impl": "reference", "metric": "soil_column_timesteps_per_sec", "value": cb["value"], "unit": "column-timesteps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.ncol, args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(ncol, ngpus):
+    return {"workload": "VSFM Richards (BASELINE.json configs[3]): %d synthetic ELM-like soil columns x %d layers, van Genuchten-Mualem, "
+                        "Tanaka density, 6 COND_MASS_RATE source/sinks, dt=%.0f s, SNES rtol 1e-8 / stol 1e-10 / max_it 50 "
+                        "(reference defaults), per-column Newton + bt line search + tridiagonal solve" % (ncol, NLEV, DT),
+            "ncol_total": ncol, "nlev": NLEV, "dt_s": DT, "satfunc": "van_genuchten",
+            "parallelism": "columns sharded contiguously over %d GPU(s); NCCL all-reduce of 8 mass-balance/convergence doubles per step" % ngpus,
+            "cache": "inputs larger than L2: %.1f GB of HBM-resident arrays touched per step per GPU vs 126 MB L2"
+                     % (ncol / ngpus * 2008 / 1e9)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="mpp_b200")
+    ap.add_argument("--ncol", type=int, default=4 * 1024 * 1024, help="total columns over all GPUs")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3                                      # timing rules: W >= 3
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import mpp_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    assert world == args.gpus or world == 1
+
+    ncol_total = args.ncol
+    c0, c1 = rank * ncol_total // world, (rank + 1) * ncol_total // world
+    d = shard_inputs(c0, c1)
+    ncol = c1 - c0
+    # a dedicated (non-default) stream: the library, the CUDA events and NCCL all run on it
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
+
+    def fresh():
+        p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d, device=local_rank)
+        p.set_stream(stream.cuda_stream)
+        set_forcing_host(p, ids, d)
+        return p, ids
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ device-resident throughput
+    p, ids = fresh()
+    red_ptr = p.reduction_buffer_ptr()
+
+    class _Red:                                      # torch view of the library's 8-double reduction buffer
+        __cuda_array_interface__ = {"shape": (8,), "typestr": "<f8", "data": (red_ptr, False), "version": 3}
+    red = torch.as_tensor(_Red(), device=torch.device("cuda", local_rank))
+
+    def step(nstep):
+        p.pre_step_dt()
+        p.step_dt_async(DT, nstep)
+        p.post_step_dt()
+        if world > 1:                                # global mass-balance / convergence reductions
+            dist.all_reduce(red[0:4], op=dist.ReduceOp.SUM)
+            dist.all_reduce(red[4:8], op=dist.ReduceOp.MAX)
+
+    for s in range(args.warmup):
+        step(s + 1)
+    barrier()
+    l0 = p.launch_count()
+    sampler = ClockSampler(local_rank)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for s in range(args.steps):
+        step(args.warmup + s + 1)
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms = ev0.elapsed_time(ev1)
+    launches = p.launch_count() - l0
+    last_kernel_ms = p.last_step_ms()
+    conv, reason = p.step_result()
+    sums, maxs = p.mass_balance(DT)
+    st = p.stats()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = ncol_total * args.steps / (ms_max * 1e-3)
+    its_mean, its_max, nf_mean = float(st["newton_its"].mean()), int(st["newton_its"].max()), float(st["nfuncs"].mean())
+    p.close()
+    del p
+
+    # ------------------------------------------------------------------ end to end through the C ABI with host buffers
+    e2e = None
+    if not args.no_e2e:
+        p, ids = fresh()
+        pin = {k: torch.from_numpy(d[k]).pin_memory().numpy() for k in SS_NAMES + ("frac_liq",)}
+        outs = {k: torch.empty(ncol * NLEV, dtype=torch.float64).pin_memory().numpy() for k in ("sat", "mass", "smp", "pressure")}
+        h2d = sum(pin[k].nbytes for k in pin)
+        d2h = sum(outs[k].nbytes for k in outs)
+
+        def e2e_step(nstep):
+            for name in SS_NAMES:
+                p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids[name], pin[name])
+            p.set_data(K.AUXVAR_INTERNAL, K.VAR_FRAC_LIQ_SAT, 1, pin["frac_liq"])
+            p.pre_step_dt()
+            cv, rs = p.step_dt(DT, nstep)
+            for key, var in (("sat", K.VAR_LIQ_SAT), ("mass", K.VAR_MASS), ("smp", K.VAR_SOIL_MATRIX_POT), ("pressure", K.VAR_PRESSURE)):
+                p.get_data(K.AUXVAR_INTERNAL, var, 1, out=outs[key])
+            p.post_step_dt()
+            if world > 1:
+                dist.all_reduce(red2[0:4], op=dist.ReduceOp.SUM)
+                dist.all_reduce(red2[4:8], op=dist.ReduceOp.MAX)
+            return cv
+
+        red_ptr2 = p.reduction_buffer_ptr()
+
+        class _Red2:
+            __cuda_array_interface__ = {"shape": (8,), "typestr": "<f8", "data": (red_ptr2, False), "version": 3}
+        red2 = torch.as_tensor(_Red2(), device=torch.device("cuda", local_rank))
+        for s in range(args.warmup):
+            e2e_step(s + 1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            cv = e2e_step(args.warmup + s + 1)
+        e1.record(stream)
+        barrier()
+        wall = time.perf_counter() - t0
+        ems = max(e0.elapsed_time(e1), wall * 1e3)           # host staging happens off-stream: take the larger clock
+        t = torch.tensor([ems], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": ncol_total * args.steps / (float(t.item()) * 1e-3), "unit": "column-timesteps/s",
+               "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
+               "ms_per_step": float(t.item()) / args.steps, "converged": bool(cv),
+               "api": "mppgpu_set_data x7 (pinned host) + pre_step_dt + step_dt + mppgpu_get_data x4 + post_step_dt"}
+        p.close()
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        per_launch_ms = ms_max / args.steps
+        achieved = ALG_BYTES_PER_COLSTEP * ncol / (per_launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": "soil_column_timesteps_per_sec", "value": value, "unit": "column-timesteps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_launch_ms,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(ncol_total, world),
+            "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
+            "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "vsfm_step_kernel<16,VG>",
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
+                         "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLSTEP,
+                         "note": "fp64-issue bound (3 log + 3 exp + sqrt + divides per cell per residual evaluation, "
+                                 "%.1f evaluations and %.1f Newton iterations per column-step); see DESIGN.md" % (nf_mean, its_mean)},
+            "solver": {"converged_all": bool(conv), "worst_reason": int(reason), "newton_its_mean": its_mean, "newton_its_max": its_max,
+                       "residual_evals_mean": nf_mean, "max_abs_mass_error_kg": float(maxs[0]), "last_step_kernel_ms": last_kernel_ms},
+        }
+        if not args.no_cpu and world == 1:
+            cb, _, _ = cpu_baseline(args.steps, args.warmup)
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmppgpu.so")
+LIB_PATH = os.environ.get("MPPGPU_LIB_PATH", os.path.join(_HERE, "libmppgpu.so"))   # override: kernel-variant experiments only
 _lib = None
 
 c_dp = C.POINTER(C.c_double)

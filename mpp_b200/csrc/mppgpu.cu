@@ -78,7 +78,7 @@ struct mppgpu_soe {
   DevBuf<double> frac_liq, temperature, liq_sat, pressure, mass, smp;
   DevBuf<double> xA, xB; double *x_committed = nullptr, *x_current = nullptr;   // soln_prev_clm / soln
   DevBuf<int> stat_its, stat_reason, stat_cuts, stat_nf;
-  DevBuf<double> col_mass, col_err, col_src, block_partials, red_out;
+  DevBuf<double> col_mass, col_err, col_src, block_partials, red_out, red_scratch; DevBuf<unsigned int> red_counter;
   double *h_red = nullptr;     // pinned mirror of red_out (9 doubles)
   int nblocks_last = 0;
   bool result_pending = false;
@@ -153,6 +153,7 @@ __global__ void convert_soils_kernel(int satfunc_name, const double *watsat, con
   if (bad) atomicExch(bad_flag, 1);
 }
 
+constexpr int REDUCE_BLOCKS = 148;
 static inline int nblk(long long n, int bs) { return (int)((n + bs - 1) / bs); }
 
 static int upload_table(mppgpu_soe *h, const double *host, DevBuf<double> &tmp)
@@ -183,6 +184,8 @@ extern "C" int mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppg
   CK(cudaEventCreate(&h->ev0)); CK(cudaEventCreate(&h->ev1));
   CK(h->red_out.alloc(16));
   CK(cudaMemsetAsync(h->red_out.p, 0, 16 * sizeof(double), h->stream));
+  CK(h->red_scratch.alloc(REDUCE_BLOCKS * 9)); CK(h->red_counter.alloc(1));
+  CK(cudaMemsetAsync(h->red_counter.p, 0, sizeof(unsigned int), h->stream));
   CK(cudaMallocHost((void **)&h->h_red, 16 * sizeof(double)));
   memset(h->h_red, 0, 16 * sizeof(double));
   CK(h->stat_its.alloc(ncol)); CK(h->stat_reason.alloc(ncol)); CK(h->stat_cuts.alloc(ncol)); CK(h->stat_nf.alloc(ncol));
@@ -538,7 +541,7 @@ static int vsfm_step(mppgpu_soe *h, double dt)
     vsfm_step_generic_kernel<<<nblocks, 32 * VSFM_GENERIC_WARPS, smem, h->stream>>>(A, h->satfunc_name == 0 ? SATFUNC_VG : (h->satfunc_name == 1 ? SATFUNC_BC : SATFUNC_SBC));
   }
   CK(cudaGetLastError());
-  reduce_partials_kernel<<<1, 256, 0, h->stream>>>(h->block_partials.p, nblocks, h->red_out.p);
+  reduce_partials_kernel<<<nblocks < REDUCE_BLOCKS ? 1 : REDUCE_BLOCKS, 256, 0, h->stream>>>(h->block_partials.p, nblocks, h->red_scratch.p, h->red_counter.p, h->red_out.p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
   h->launches += 2;

@@ -23,6 +23,9 @@
 
 namespace mpp {
 
+#ifndef VSFM_MIN_BLOCKS
+#define VSFM_MIN_BLOCKS 4
+#endif
 constexpr int MAX_SS = 16;
 constexpr int MAX_BC = 2;
 
@@ -76,11 +79,16 @@ struct VsfmArgs {
 
 enum { PH_INIT = 0, PH_NEWTON = 1, PH_LS_FULL = 2, PH_LS_QUAD = 3, PH_LS_CUBIC = 4, PH_DONE = 5 };
 
+// All shuffles in this file use the compile-time full mask and are executed by the whole warp under
+// warp-uniform control flow: partial (run-time) masks make nvcc wrap every SHFL in a MATCH/WARPSYNC sequence
+// (measured: 26% of all executed instructions in the first version, profiles/r1_vsfm_first.md).
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
 template <int GROUP>
-__device__ __forceinline__ double group_sum(double v, unsigned mask)
+__device__ __forceinline__ double group_sum(double v)
 {
 #pragma unroll
-  for (int s = GROUP / 2; s > 0; s >>= 1) v += __shfl_xor_sync(mask, v, s, GROUP);
+  for (int s = GROUP / 2; s > 0; s >>= 1) v += __shfl_xor_sync(FULL_MASK, v, s, GROUP);
   return v;
 }
 
@@ -88,11 +96,12 @@ __device__ __forceinline__ double group_sum(double v, unsigned mask)
 // The a/c couplings that would reach outside the chain are exactly zero at every stage, so the values that
 // out-of-range shuffles return are multiplied by zero.
 template <int GROUP>
-__device__ __forceinline__ double pcr_solve(double a, double b, double c, double d, unsigned mask)
+__device__ __forceinline__ double pcr_solve(double a, double b, double c, double d)
 {
+  const unsigned mask = FULL_MASK;
 #pragma unroll
   for (int s = 1; s < GROUP; s <<= 1) {
-    const double r   = 1.0 / b;
+    const double r   = __drcp_rn(b);
     const double a_m = __shfl_up_sync(mask, a, s, GROUP),   c_m = __shfl_up_sync(mask, c, s, GROUP);
     const double d_m = __shfl_up_sync(mask, d, s, GROUP),   r_m = __shfl_up_sync(mask, r, s, GROUP);
     const double a_p = __shfl_down_sync(mask, a, s, GROUP), c_p = __shfl_down_sync(mask, c, s, GROUP);
@@ -103,19 +112,19 @@ __device__ __forceinline__ double pcr_solve(double a, double b, double c, double
     a = -a_m * k1;
     c = -c_p * k2;
   }
-  return d / b;
+  return d * __drcp_rn(b);
 }
 
 template <int GROUP, int SATFUNC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, VSFM_MIN_BLOCKS)
 vsfm_step_kernel(const VsfmArgs A)
 {
   const int tid   = blockIdx.x * blockDim.x + threadIdx.x;
   const int col   = tid / GROUP;
   const int j     = tid % GROUP;                       // lane within the group == layer index
   const int lane  = threadIdx.x & 31;
-  const unsigned gmask = (GROUP == 32) ? 0xffffffffu : (0xffffu << (lane & 16));
-  const unsigned FULL = 0xffffffffu;
+  constexpr unsigned FULL = FULL_MASK;
+  constexpr double RVIS = 1.0 / VISCOSITY, RFMW = 1.0 / FMWH2O;
   const int nlev  = A.nlev;
   const bool col_ok = (col < A.ncol) && (A.active == nullptr || A.active[col] != 0);
   const bool valid  = col_ok && (j < nlev);
@@ -172,7 +181,7 @@ vsfm_step_kernel(const VsfmArgs A)
     bool mine = false; long long idx = 0;
     if (c.region == REGION_CELLS) { mine = valid; idx = cell; }
     else { mine = valid && (j == (c.region == REGION_TOP ? jtop : jbot)); idx = col; }
-    if (mine) { const double v = c.value[idx]; src += v / FMWH2O; src_kg += v; }
+    if (mine) { const double v = c.value[idx]; src += v * RFMW; src_kg += v; }
   }
 
   // ---- time-step / Newton state (group-uniform unless noted) -------------------------------------
@@ -192,31 +201,34 @@ vsfm_step_kernel(const VsfmArgs A)
 
   for (;;) {
     // ================= Newton step set-up: Jacobian, linear solve, line-search initialisation =================
-    if (phase == PH_NEWTON) {
+    // Executed by the WHOLE warp whenever either of its columns starts a Newton iteration (warp-uniform branch, so
+    // every shuffle below is convergent); lanes of a column that is not in PH_NEWTON compute and discard.
+    if (__any_sync(FULL, phase == PH_NEWTON)) {
+      const bool nw = (phase == PH_NEWTON);
       // neighbour (dn) state of connection j
-      const double P_d   = __shfl_down_sync(gmask, X, 1, GROUP);
-      const double kr_d  = __shfl_down_sync(gmask, kr, 1, GROUP);
-      const double den_d = __shfl_down_sync(gmask, den, 1, GROUP);
-      const double dkr_d = __shfl_down_sync(gmask, dkr, 1, GROUP);
-      const double dden_d = __shfl_down_sync(gmask, dden, 1, GROUP);
+      const double P_d    = __shfl_down_sync(FULL, X, 1, GROUP);
+      const double kr_d   = __shfl_down_sync(FULL, kr, 1, GROUP);
+      const double den_d  = __shfl_down_sync(FULL, den, 1, GROUP);
+      const double dkr_d  = __shfl_down_sync(FULL, dkr, 1, GROUP);
+      const double dden_d = __shfl_down_sync(FULL, dden, 1, GROUP);
       double Jup = 0.0, Jdn = 0.0;
       if (has_conn) {       // RichardsFlux_Internal with compute_deriv (RichardsMod.F90:298-336)
         const double den_ave = upw * den + (1.0 - upw) * den_d;
         const double dphi    = X - P_d + den_ave * gfac;
         const bool   upwind  = (dphi >= 0.0);
-        const double ukvr    = (upwind ? kr : kr_d) / VISCOSITY;
+        const double ukvr    = (upwind ? kr : kr_d) * RVIS;
         const double q       = (-Dq * ukvr * dphi) * area;
         const double dphi_dP_up =  1.0 + (upw * gfac) * dden;
         const double dphi_dP_dn = -1.0 + ((1.0 - upw) * gfac) * dden_d;
-        const double dukvr_up = upwind ? dkr / VISCOSITY : 0.0;
-        const double dukvr_dn = upwind ? 0.0 : dkr_d / VISCOSITY;
+        const double dukvr_up = upwind ? dkr * RVIS : 0.0;
+        const double dukvr_dn = upwind ? 0.0 : dkr_d * RVIS;
         const double dq_up = Dq * (dukvr_up * dphi + ukvr * dphi_dP_up) * area;
         const double dq_dn = Dq * (dukvr_dn * dphi + ukvr * dphi_dP_dn) * area;
         Jup = dq_up * den_ave - q * (upw * dden);
         Jdn = dq_dn * den_ave - q * ((1.0 - upw) * dden_d);
       }
-      const double Jup_m = __shfl_up_sync(gmask, Jup, 1, GROUP);
-      const double Jdn_m = __shfl_up_sync(gmask, Jdn, 1, GROUP);
+      const double Jup_m = __shfl_up_sync(FULL, Jup, 1, GROUP);
+      const double Jdn_m = __shfl_up_sync(FULL, Jdn, 1, GROUP);
       // row j of the tridiagonal Jacobian (GoveqnRichards...:2054-2069 insertion order)
       double ja = 0.0, jb = 0.0, jc = 0.0;
       if (valid) {
@@ -228,37 +240,41 @@ vsfm_step_kernel(const VsfmArgs A)
           const bool seep = (A.bc[k].itype == CT_SEEPAGE) && (dphi0 > 0.0) && (bcP[k] <= PRESSURE_REF);
           const double dphi = seep ? 0.0 : dphi0;
           const bool upwind = (dphi >= 0.0);
-          const double ukvr = (upwind ? bcKr[k] : kr) / VISCOSITY;
+          const double ukvr = (upwind ? bcKr[k] : kr) * RVIS;
           const double q    = (-DqBC * ukvr * dphi) * area;
           const double dphi_dP_dn = seep ? 0.0 : (-1.0 + bcGfac[k] * dden);
-          const double dukvr_dn = upwind ? 0.0 : dkr / VISCOSITY;
+          const double dukvr_dn = upwind ? 0.0 : dkr * RVIS;
           const double dq_dn = DqBC * (dukvr_dn * dphi + ukvr * dphi_dP_dn) * area;
           jb += -(dq_dn * den - q * dden);
         }
         jb += (por * dden * sat + por * den * dsat) * vol * dtInv;   // AccumDeriv (:1673-1675), dpor_dP = 0
       } else { jb = 1.0; }
 
-      Y = pcr_solve<GROUP>(ja, jb, jc, valid ? F : 0.0, gmask);       // J Y = F
-      ynorm = sqrt(group_sum<GROUP>(valid ? Y * Y : 0.0, gmask));
-      xnorm = sqrt(group_sum<GROUP>(valid ? X * X : 0.0, gmask));
+      const double Yn = pcr_solve<GROUP>(ja, jb, jc, valid ? F : 0.0);   // J Y = F
+      const double yn2 = group_sum<GROUP>(valid ? Yn * Yn : 0.0);
+      const double xn2 = group_sum<GROUP>(valid ? X * X : 0.0);
       // initslope = F . (J Y), forced negative (SNESLineSearchApply_BT)
-      const double Y_m = __shfl_up_sync(gmask, Y, 1, GROUP), Y_p = __shfl_down_sync(gmask, Y, 1, GROUP);
-      double JY = jb * Y;
+      const double Y_m = __shfl_up_sync(FULL, Yn, 1, GROUP), Y_p = __shfl_down_sync(FULL, Yn, 1, GROUP);
+      double JY = jb * Yn;
       if (j > 0) JY = ja * Y_m + JY;
       if (has_conn) JY += jc * Y_p;
-      initslope = group_sum<GROUP>(valid ? F * JY : 0.0, gmask);
-      if (initslope > 0.0) initslope = -initslope;
-      if (initslope == 0.0) initslope = -1.0;
-      lambda = 1.0; f2 = fnorm * fnorm; ls_count = 0;
-      if (ynorm == 0.0) {
-        // zero step: line search "fails"; stol*xnorm > ynorm => SNES_CONVERGED_SNORM_RELATIVE (ls.c)
-        last_reason = (so.stol * xnorm > ynorm) ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
-        phase = -1;   // SNES finished, handled below
-      } else {
-        if (ynorm > so.ls_maxstep) { Y *= so.ls_maxstep / ynorm; ynorm = so.ls_maxstep; }
-        W = X - lambda * Y;
-        phase = PH_LS_FULL;
-        if (nfuncs >= so.max_funcs && so.max_funcs >= 0) { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
+      double slope = group_sum<GROUP>(valid ? F * JY : 0.0);
+      if (nw) {
+        Y = Yn; ynorm = sqrt(yn2); xnorm = sqrt(xn2);
+        if (slope > 0.0) slope = -slope;
+        if (slope == 0.0) slope = -1.0;
+        initslope = slope;
+        lambda = 1.0; f2 = fnorm * fnorm; ls_count = 0;
+        if (ynorm == 0.0) {
+          // zero step: line search "fails"; stol*xnorm > ynorm => SNES_CONVERGED_SNORM_RELATIVE (ls.c)
+          last_reason = (so.stol * xnorm > ynorm) ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
+          phase = -1;   // SNES finished, handled below
+        } else {
+          if (ynorm > so.ls_maxstep) { Y *= so.ls_maxstep / ynorm; ynorm = so.ls_maxstep; }
+          W = X - lambda * Y;
+          phase = PH_LS_FULL;
+          if (nfuncs >= so.max_funcs && so.max_funcs >= 0) { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
+        }
       }
     }
 
@@ -298,7 +314,7 @@ vsfm_step_kernel(const VsfmArgs A)
       if (has_conn) {                                                  // RichardsFlux_Internal (:257-296)
         const double den_ave = upw * den_w + (1.0 - upw) * den_d;
         const double dphi    = W - P_d + den_ave * gfac;
-        const double ukvr    = ((dphi >= 0.0) ? st.kr : kr_d) / VISCOSITY;
+        const double ukvr    = ((dphi >= 0.0) ? st.kr : kr_d) * RVIS;
         flux = ((-Dq * ukvr * dphi) * area) * den_ave;
       }
       const double flux_m = __shfl_up_sync(FULL, flux, 1, GROUP);
@@ -311,7 +327,7 @@ vsfm_step_kernel(const VsfmArgs A)
         if (bcMine[k]) {                                               // boundary connection, upweight = 0 (:262-264)
           double dphi = bcP[k] - W + den_w * bcGfac[k];
           if ((A.bc[k].itype == CT_SEEPAGE) && (dphi > 0.0) && (bcP[k] <= PRESSURE_REF)) dphi = 0.0;
-          const double ukvr = ((dphi >= 0.0) ? bcKr[k] : st.kr) / VISCOSITY;
+          const double ukvr = ((dphi >= 0.0) ? bcKr[k] : st.kr) * RVIS;
           const double fl = ((-DqBC * ukvr * dphi) * area) * den_w;
           G = G + fl; G_bcflux[k] = fl * FMWH2O;
         }
@@ -319,8 +335,8 @@ vsfm_step_kernel(const VsfmArgs A)
       G = G - src;
       if (!valid) G = 0.0;
     }
-    const double g2 = group_sum<GROUP>(G * G, FULL);
-    const double w2 = group_sum<GROUP>(valid ? W * W : 0.0, FULL);
+    const double g2 = group_sum<GROUP>(G * G);
+    const double w2 = group_sum<GROUP>(valid ? W * W : 0.0);
     nfuncs += 1;
 
     // ================= after the evaluation: line-search / convergence logic =================
@@ -421,8 +437,8 @@ vsfm_step_kernel(const VsfmArgs A)
       }
     }
   }
-  const double m_end = group_sum<GROUP>(mass, FULL);
-  const double q_col = group_sum<GROUP>(src_kg, FULL);
+  const double m_end = group_sum<GROUP>(mass);
+  const double q_col = group_sum<GROUP>(src_kg);
   double err = 0.0, m_beg = 0.0;
   if (col_ok && j == 0) {
     A.stat_its[col] = tot_its; A.stat_reason[col] = last_reason; A.stat_cuts[col] = cuts; A.stat_nf[col] = tot_nf;
@@ -477,15 +493,20 @@ vsfm_step_kernel(const VsfmArgs A)
   }
 }
 
-// second stage: one block folds the per-block partials in a fixed order
-// out[0..3] sums, out[4..7] maxima, out[8] worst reason
-__global__ void reduce_partials_kernel(const double *partials, int nblocks, double *out)
+// Second stage of the deterministic reduction: `gridDim.x` blocks each fold a contiguous slice of the per-block
+// partials (fixed order), the last block to finish folds the slice results (fixed order) into out[0..8]:
+// out[0..3] sums, out[4..7] maxima, out[8] worst (minimum) SNES reason.  scratch: gridDim.x*9 doubles + 1 counter.
+__global__ void reduce_partials_kernel(const double *__restrict__ partials, int nblocks, double *scratch,
+                                       unsigned int *counter, double *out)
 {
   __shared__ double sh[9][256];
+  __shared__ bool last;
+  const int per = (nblocks + gridDim.x - 1) / gridDim.x;
+  const int b0 = blockIdx.x * per, b1 = min(nblocks, b0 + per);
   double v[9];
   for (int k = 0; k < 8; ++k) v[k] = 0.0;
   v[8] = 2147483647.0;
-  for (int b = threadIdx.x; b < nblocks; b += blockDim.x) {
+  for (int b = b0 + threadIdx.x; b < b1; b += blockDim.x) {
     const double *bp = partials + (size_t)b * 9;
     for (int k = 0; k < 4; ++k) v[k] += bp[k];
     for (int k = 4; k < 8; ++k) v[k] = fmax(v[k], bp[k]);
@@ -501,7 +522,26 @@ __global__ void reduce_partials_kernel(const double *partials, int nblocks, doub
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) for (int k = 0; k < 9; ++k) out[k] = sh[k][0];
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 9; ++k) scratch[(size_t)blockIdx.x * 9 + k] = sh[k][0];
+    __threadfence();
+    last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    __threadfence();
+    double o[9];
+    for (int k = 0; k < 8; ++k) o[k] = 0.0;
+    o[8] = 2147483647.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) {
+      const volatile double *bp = scratch + (size_t)b * 9;
+      for (int k = 0; k < 4; ++k) o[k] += bp[k];
+      for (int k = 4; k < 8; ++k) o[k] = fmax(o[k], bp[k]);
+      o[8] = fmin(o[8], bp[8]);
+    }
+    for (int k = 0; k < 9; ++k) out[k] = o[k];
+    *counter = 0u;
+  }
 }
 
 }  // namespace mpp
