@@ -10,6 +10,8 @@
  *   ---------------------------------------------------------------------------------------------
  *   MPPSetupProblem / SOE creation   MultiPhysicsProbBaseType.F90:1058-1213     mppgpu_create
  *   MeshCreate, CreateFromCLMCols    MeshType.F90:173-269, 293-645              mppgpu_set_mesh
+ *   mpp%CreateAndAddConnectionSet    MPPThermalTBasedALM_Initialize.F90:379-381,
+ *                                    466-468                                     mppgpu_set_connection_distances
  *   soe%AddConditionInGovEqn         SystemOfEquationsBaseType.F90:995+         mppgpu_add_condition
  *   VSFMMPPSetSoils                  MultiPhysicsProbVSFM.F90:211-475           mppgpu_vsfm_set_soils
  *   MPPThermalSetSoils               MultiPhysicsProbThermal.F90:76-208         mppgpu_thermal_set_soils
@@ -77,6 +79,9 @@ int  mppgpu_synchronize(mppgpu_handle h);
 /* ---- setup ------------------------------------------------------------------------------------ */
 /* dz: (ncol,nlev) Fortran order [m]; area: ncol [m^2]; col_active: ncol ints or NULL (all active) */
 int  mppgpu_set_mesh(mppgpu_handle h, int orientation, const double *dz, const double *area, const int *col_active);
+/* centroid-to-face distances of the internal (vertical) connections j -> j+1, (ncol, nlev-1) Fortran order;
+ * default (never called) = dz/2 of the two cells.  Thermal SoE only (ELM's soil thermal mesh). */
+int  mppgpu_set_connection_distances(mppgpu_handle h, const double *dist_up, const double *dist_dn);
 /* ieqn: 1-based governing-equation rank in the SoE (TH: 1 = mass, 2 = energy); ss_or_bc: COND_SS/COND_BC;
  * returns the 1-based condition id in *cond_id (separate numbering for BCs and SSs, = soe_auxvar_id) */
 int  mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int cond_type, int region, int *cond_id);

@@ -21,6 +21,7 @@ _SIGS = {
     "mppgpu_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "mppgpu_synchronize": (C.c_int, [C.c_void_p]),
     "mppgpu_set_mesh": (C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_ip]),
+    "mppgpu_set_connection_distances": (C.c_int, [C.c_void_p, c_dp, c_dp]),
     "mppgpu_add_condition": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_ip]),
     "mppgpu_vsfm_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int]),
     "mppgpu_thermal_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_int]),

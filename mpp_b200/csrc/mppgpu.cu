@@ -277,6 +277,36 @@ extern "C" int mppgpu_set_mesh(mppgpu_handle h, int orientation, const double *d
   return 0;
 }
 
+// (ncol, nlev-1) Fortran-order connection table -> per-cell array (cell j carries connection j -> j+1)
+__global__ void conn_table_to_cells_kernel(const double *__restrict__ t, double *__restrict__ out, int ncol, int nlev)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n = (long long)ncol * nlev;
+  if (i < n) { const int c = (int)(i / nlev), j = (int)(i % nlev); out[i] = (j < nlev - 1) ? t[(size_t)j * ncol + c] : 0.0; }
+}
+
+extern "C" int mppgpu_set_connection_distances(mppgpu_handle h, const double *dist_up, const double *dist_dn)
+{
+  CHECK_H(h);
+  if (!h->thermal) return fail("mppgpu_set_connection_distances: only the thermal SoE takes explicit connection distances");
+  if (!h->mesh_set) return fail("mppgpu_set_connection_distances: set the mesh first");
+  if (!dist_up || !dist_dn) return fail("mppgpu_set_connection_distances: null table");
+  if (h->nlev < 2) return 0;
+  ThermalState *t = h->thermal;
+  const size_t nconn = (size_t)h->ncol * (h->nlev - 1);
+  const double *src[2] = {dist_up, dist_dn}; double **dst[2] = {&t->dist_up, &t->dist_dn};
+  for (int i = 0; i < 2; ++i) {
+    DevBuf<double> tmp; CK(tmp.alloc(nconn));
+    CK(cudaMemcpyAsync(tmp.p, src[i], nconn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (!*dst[i]) CK(cudaMalloc((void **)dst[i], h->ncells * sizeof(double)));
+    conn_table_to_cells_kernel<<<nblk(h->ncells, 256), 256, 0, h->stream>>>(tmp.p, *dst[i], h->ncol, h->nlev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  t->custom_dist = true;
+  return 0;
+}
+
 extern "C" int mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int cond_type, int region, int *cond_id)
 {
   CHECK_H(h);

@@ -66,17 +66,20 @@ MPP_HD void sat_values(const SatParams &sp, double press, double frac_liq, SatSt
   s.pc = pc;
   if (SATFUNC == SATFUNC_VG) {
     if (pc < 0.0) {
+      // Reference: Se = (1 + x^n)^-m, AA = x^n / (1 + x^n), kr = sqrt(Se) (1 - AA^m)^2 with x = -alpha pc
+      // (5 pow calls, SaturationFunction.F90:777-836).  Here: 2 log + 3 exp, using AA^m = x^(n m) Se and n m = n - 1.
       const double L1  = log(-sp.alpha * pc);
-      const double pcn = exp(sp.n * L1);               // (-alpha pc)^n
+      const double pcn = exp(sp.n * L1);               // x^n
       const double opn = 1.0 + pcn;
       const double L2  = log(opn);
-      const double Se  = exp(-sp.m * L2);              // (1 + (-alpha pc)^n)^(-m)
-      const double AA  = pcn / opn;
-      const double AAm = exp(sp.m * log(AA));          // AA^m
+      const double mL2 = sp.m * L2;
+      const double Se  = exp(-mL2);                    // (1 + x^n)^(-m)
+      const double AAm = exp((sp.n - 1.0) * L1 - mL2); // AA^m
       const double BB  = 1.0 - AAm;
+      const double rS  = sqrt(Se);
       s.sat = sp.sat_res + (1.0 - sp.sat_res) * Se;
-      s.kr  = sqrt(Se) * BB * BB;
-      s.Se = Se; s.AA = AA; s.AAm = AAm; s.L2 = L2; s.regime = 1;
+      s.kr  = rS * BB * BB;
+      s.Se = Se; s.AA = pcn; s.AAm = AAm; s.L2 = rS; s.regime = 1;   // (AA slot carries x^n, L2 slot carries sqrt(Se))
     } else {
       s.sat = 1.0; s.kr = 1.0; s.regime = 0;
     }
@@ -116,10 +119,14 @@ MPP_HD void sat_derivs(const SatParams &sp, const SatState &s, double frac_liq, 
 {
   if (s.regime == 0) { dsat_dP = 0.0; dkr_dP = 0.0; return; }
   if (SATFUNC == SATFUNC_VG) {
-    const double dSe_dpc = -sp.m * sp.n * s.Se * s.AA / s.pc;
-    const double BB      = 1.0 - s.AAm;
-    // Se^(1/m - 1/2) = exp(-m L2 (1/m - 1/2)) ; AA^(m-1) = AA^m / AA
-    const double dkr_dSe = 0.5 * s.kr / s.Se + 2.0 * exp(-(1.0 - 0.5 * sp.m) * s.L2) * (s.AAm / s.AA) * BB;
+    // dSe/dpc = -m n Se AA / pc with AA = x^n / (1 + x^n)                       (SaturationFunction.F90:790, 829)
+    // dkr/dSe = kr / (2 Se) + 2 Se^(1/m - 1/2) AA^(m-1) BB                       (:836-838)
+    //         = BB (BB / 2 + 2 AA^m / x^n) / sqrt(Se)      since Se^(1/m) = 1 / (1 + x^n)
+    // (same functions, regrouped so that no further exp/pow is needed; derivative round-off only steers the Newton
+    //  path, never the converged answer)
+    const double pcn = s.AA, rS = s.L2, BB = 1.0 - s.AAm;
+    const double dSe_dpc = -sp.m * sp.n * s.Se * pcn / ((1.0 + pcn) * s.pc);
+    const double dkr_dSe = BB * (0.5 * BB + 2.0 * s.AAm / pcn) / rS;
     dsat_dP = (1.0 - sp.sat_res) * dSe_dpc;
     dkr_dP  = dkr_dSe * dSe_dpc;
   } else {

@@ -1,11 +1,196 @@
-// thermal_host.inl -- placeholder (filled in by the thermal milestone)
-static int thermal_create(ThermalState *t, int, int, cudaStream_t s) { t->stream = s; return 0; }
-static void thermal_destroy(ThermalState *) {}
-static int thermal_set_mesh(ThermalState *, int, const double *, const double *) { return 0; }
-static int thermal_set_temperature(ThermalState *, const double *, bool) { return 1; }
-static int thermal_field(mppgpu_soe *, ThermalState *, int, int, int, bool, double **, size_t *) { return fail("thermal SoE not implemented yet"); }
-static int thermal_set_idata(mppgpu_soe *, ThermalState *, int, int, int, const int *, int) { return fail("thermal SoE not implemented yet"); }
-static int thermal_pre_step_dt(ThermalState *) { return 0; }
+// thermal_host.inl -- host side of the soil thermal SoE (sysofeqns_thermal_type, soil governing equation only):
+// device-resident mailbox, set/get routing, StepDT launch.  Included at the end of mppgpu.cu.
+
+static int th_alloc_d(double **p, size_t n, double fill, cudaStream_t s)
+{
+  if (cudaMalloc((void **)p, n * sizeof(double)) != cudaSuccess) return 1;
+  if (fill == 0.0) cudaMemsetAsync(*p, 0, n * sizeof(double), s);
+  else fill_kernel<<<nblk(n, 256), 256, 0, s>>>(*p, fill, (long long)n);
+  return 0;
+}
+__global__ void fill_int_kernel(int *p, int v, long long n)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+static int thermal_create(ThermalState *t, int ncol, int nlev, cudaStream_t s)
+{
+  t->stream = s; t->ncol = ncol; t->nlev = nlev;
+  const size_t N = (size_t)ncol * nlev;
+  int rc = 0;
+  rc |= th_alloc_d(&t->T_clm, N, 273.15, s); rc |= th_alloc_d(&t->T_work, N, 273.15, s);
+  rc |= th_alloc_d(&t->liq, N, 0.0, s); rc |= th_alloc_d(&t->ice, N, 0.0, s); rc |= th_alloc_d(&t->snow_water, N, 0.0, s);
+  rc |= th_alloc_d(&t->tuning, N, 1.0, s);                      // ThermalKSPTemperatureSoilAuxType.F90:56
+  if (cudaMalloc((void **)&t->nsnow, N * sizeof(int)) != cudaSuccess) rc = 1;
+  if (cudaMalloc((void **)&t->active, N * sizeof(int)) != cudaSuccess) rc = 1;
+  if (!rc) { cudaMemsetAsync(t->nsnow, 0, N * sizeof(int), s); cudaMemsetAsync(t->active, 0, N * sizeof(int), s); }
+  t->T_cur = t->T_clm;
+  return rc;
+}
+
+static void thermal_destroy(ThermalState *t)
+{
+  double *d[] = {t->por, t->tkmg, t->tkdry, t->csol, t->dist_up, t->dist_dn, t->T_clm, t->T_work, t->liq, t->ice, t->snow_water,
+                 t->tuning, t->frac, t->aux_dz, t->aux_dist_up, t->aux_dist_dn, t->therm_cond, t->heat_cap, t->work};
+  for (double *p : d) if (p) cudaFree(p);
+  if (t->lun_type) cudaFree(t->lun_type);
+  if (t->nsnow) cudaFree(t->nsnow);
+  if (t->active) cudaFree(t->active);
+}
+
+static int thermal_set_mesh(ThermalState *t, int orientation, const double *d_dz, const double *d_area)
+{
+  t->orientation = orientation; t->d_dz = d_dz; t->d_area = d_area;
+  // the stale `area` of the reference's Dirichlet branch = area of the mesh's last internal connection = last column's
+  double a = 1.0;
+  if (cudaMemcpy(&a, d_area + (t->ncol - 1), sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return 1;
+  t->stale_area = a;
+  return 0;
+}
+
+static int thermal_set_temperature(ThermalState *t, const double *T, bool)
+{
+  // ThermalSOESetSolnPrevCLM (SystemOfEquationsThermalType.F90:171-199)
+  if (cudaMemcpyAsync(t->T_clm, T, (size_t)t->ncol * t->nlev * sizeof(double), cudaMemcpyHostToDevice, t->stream) != cudaSuccess) return 1;
+  return cudaStreamSynchronize(t->stream) != cudaSuccess;
+}
+
+static int thermal_set_soils(mppgpu_soe *h, ThermalState *t, const double *watsat, const double *csol, const double *tkmg,
+                             const double *tkdry, const int *lun_type, int nlevsoi, int istsoil)
+{
+  if (!watsat || !csol || !tkmg || !tkdry || !lun_type) return fail("MPPThermalSetSoils: null table");
+  const size_t N = h->ncells;
+  const double *src[4] = {watsat, tkmg, tkdry, csol};
+  double **dst[4] = {&t->por, &t->tkmg, &t->tkdry, &t->csol};
+  for (int i = 0; i < 4; ++i) {
+    DevBuf<double> tmp;
+    if (upload_table(h, src[i], tmp)) return 1;
+    if (!*dst[i]) CK(cudaMalloc((void **)dst[i], N * sizeof(double)));
+    transpose_to_cells_kernel<<<nblk(N, 256), 256, 0, h->stream>>>(tmp.p, *dst[i], h->ncol, h->nlev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  if (!t->lun_type) CK(cudaMalloc((void **)&t->lun_type, h->ncol * sizeof(int)));
+  CK(cudaMemcpyAsync(t->lun_type, lun_type, h->ncol * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  // every column active (filter_thermal = 1): aux_vars_in%is_active = .true. (MultiPhysicsProbThermal.F90:165-170)
+  fill_int_kernel<<<nblk(N, 256), 256, 0, h->stream>>>(t->active, 1, (long long)N);
+  CK(cudaStreamSynchronize(h->stream));
+  t->nlevsoi = nlevsoi; t->istsoil = istsoil; t->soils_set = true; h->soils_set = true;
+  return 0;
+}
+
+static int thermal_lazy(double **p, size_t n, double fill, cudaStream_t s)
+{
+  if (*p) return 0;
+  return th_alloc_d(p, n, fill, s) ? fail("out of device memory") : 0;
+}
+
+static int thermal_field(mppgpu_soe *h, ThermalState *t, int auxvar_type, int var_type, int cond_id, bool for_set, double **p, size_t *cap)
+{
+  const size_t N = h->ncells;
+  if (auxvar_type == AUXVAR_INTERNAL) {
+    *cap = N;
+    switch (var_type) {
+    case VAR_TEMPERATURE:   *p = for_set ? t->T_clm : t->T_cur; return 0;      // SetSolnPrevCLM / GetSoln
+    case VAR_LIQ_AREAL_DEN: *p = t->liq; return 0;
+    case VAR_ICE_AREAL_DEN: *p = t->ice; return 0;
+    case VAR_SNOW_WATER:    *p = t->snow_water; return 0;
+    case VAR_TUNING_FACTOR: *p = t->tuning; return 0;
+    // stored for the SoE mailbox; only the snow / standing-water coupling conditions read them (out of scope)
+    case VAR_FRAC:          if (thermal_lazy(&t->frac, N, 0.0, h->stream)) return 1; *p = t->frac; return 0;
+    case VAR_DZ:            if (thermal_lazy(&t->aux_dz, N, 0.0, h->stream)) return 1; *p = t->aux_dz; return 0;
+    case VAR_DIST_UP:       if (thermal_lazy(&t->aux_dist_up, N, 0.0, h->stream)) return 1; *p = t->aux_dist_up; return 0;
+    case VAR_DIST_DN:       if (thermal_lazy(&t->aux_dist_dn, N, 0.0, h->stream)) return 1; *p = t->aux_dist_dn; return 0;
+    case VAR_THERMAL_COND:
+    case VAR_HEAT_CAP:
+      if (for_set) break;
+      if (thermal_lazy(&t->therm_cond, N, 0.0, h->stream) || thermal_lazy(&t->heat_cap, N, 0.0, h->stream)) return 1;
+      if (!t->diagnostics) return fail("thermal conductivity / heat capacity diagnostics are filled by the next StepDT (request them once before stepping)");
+      *p = (var_type == VAR_THERMAL_COND) ? t->therm_cond : t->heat_cap; return 0;
+    }
+    return fail("SOEThermalAux%sRData: unknown var_type %d", for_set ? "Set" : "Get", var_type);
+  }
+  if (auxvar_type != AUXVAR_BC && auxvar_type != AUXVAR_SS) return fail("ThermalSOE%sRDataFromCLM: Unknown soe_auxvar_type %d", for_set ? "Set" : "Get", auxvar_type);
+  HostCond *c = find_cond(h, auxvar_type, cond_id);
+  if (!c) return fail("ThermalSOE%sRDataFromCLM: condition id %d out of range", for_set ? "Set" : "Get", cond_id);
+  *cap = c->n;
+  if (var_type == VAR_BC_SS_CONDITION) { *p = c->value.p; return 0; }
+  if (auxvar_type == AUXVAR_BC && var_type == VAR_DHS_DT) { *p = c->dhsdT.p; return 0; }
+  if (auxvar_type == AUXVAR_BC && var_type == VAR_FRAC) { *p = c->frac.p; return 0; }
+  if (auxvar_type == AUXVAR_BC && var_type == VAR_ACTIVE && for_set) {
+    // real-valued VAR_ACTIVE on boundary aux vars (ThermKSPTempSoilAuxVarSetRValues, thermal_mms_problem.F90:633): stored as 0/1 doubles
+    if (!c->mass_exc.p) return fail("internal: boundary condition without an active-flag buffer");
+    *p = c->mass_exc.p; return 0;
+  }
+  return fail("SOEThermalAux%sRData: unknown var_type %d", for_set ? "Set" : "Get", var_type);
+}
+
+static int thermal_set_idata(mppgpu_soe *h, ThermalState *t, int auxvar_type, int var_type, int cond_id, const int *data, int n)
+{
+  (void)cond_id;
+  if (auxvar_type != AUXVAR_INTERNAL) return fail("ThermalSOESetIDataFromCLM: only AUXVAR_INTERNAL is supported");
+  if ((size_t)n > h->ncells) return fail("size(data_1d) > nauxvar (%d > %zu)", n, h->ncells);
+  int *dst = nullptr;
+  if (var_type == VAR_NUM_SNOW_LYR) dst = t->nsnow;
+  else if (var_type == VAR_ACTIVE) dst = t->active;
+  else return fail("SOEThermalAuxSetIData: unknown var_type %d", var_type);
+  CK(cudaMemcpyAsync(dst, data, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+static int thermal_pre_step_dt(ThermalState *t) { t->T_cur = t->T_clm; return 0; }     // ThermalSOEPreStepDT :393-408
 static int thermal_post_step_dt(ThermalState *) { return 0; }
-static int thermal_step(mppgpu_soe *, ThermalState *, double) { return fail("thermal SoE not implemented yet"); }
-static int thermal_set_soils(mppgpu_soe *, ThermalState *, const double *, const double *, const double *, const double *, const int *, int, int) { return fail("thermal SoE not implemented yet"); }
+
+static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
+{
+  if (!h->mesh_set || !t->soils_set) return fail("mppgpu_step_dt: mesh and soils must be set first");
+  if (!(dt > 0.0)) return fail("mppgpu_step_dt: dt must be positive");
+  ThermalArgs A;
+  memset(&A, 0, sizeof(A));
+  A.ncol = h->ncol; A.nlev = h->nlev; A.nlevsoi = t->nlevsoi;
+  A.istsoil = t->istsoil; A.istcrop = t->istcrop; A.istice = t->istice; A.istice_mec = t->istice_mec; A.istwet = t->istwet;
+  A.dt = dt; A.cnfac = t->cnfac;
+  A.por = t->por; A.tkmg = t->tkmg; A.tkdry = t->tkdry; A.csol = t->csol; A.dz = h->dz.p; A.area = h->area.p;
+  A.dist_up = t->custom_dist ? t->dist_up : nullptr; A.dist_dn = t->custom_dist ? t->dist_dn : nullptr;
+  A.lun_type = t->lun_type;
+  A.T_in = t->T_cur; A.liq = t->liq; A.ice = t->ice; A.snow_water = t->snow_water; A.tuning = t->tuning;
+  A.nsnow = t->nsnow; A.active = t->active;
+  A.top_is_first = (h->orientation != MPPGPU_MESH_AGAINST_GRAVITY);
+  A.stale_area = t->stale_area;
+  for (auto *c : h->bcs) {
+    const int k = (c->region == REGION_TOP) ? 0 : 1;
+    if (A.bc_type[k]) return fail("mppgpu_step_dt: one thermal boundary condition per region is supported");
+    A.bc_type[k] = c->itype; A.bc_value[k] = c->value.p; A.bc_dhsdT[k] = c->dhsdT.p; A.bc_frac[k] = c->frac.p;
+    A.bc_active[k] = c->mass_exc.p;                  // boundary aux var is_active flags (0/1 doubles)
+  }
+  for (auto *c : h->sss) {
+    if (A.nss >= TH_MAX_SS) return fail("mppgpu_step_dt: at most %d thermal source conditions", TH_MAX_SS);
+    A.ss_value[A.nss] = c->value.p; A.ss_region[A.nss] = c->region; A.nss++;
+  }
+  A.T_out = (t->T_cur == t->T_clm) ? t->T_work : t->T_cur;
+  if (t->therm_cond && t->heat_cap) { A.therm_cond = t->therm_cond; A.heat_cap = t->heat_cap; t->diagnostics = true; }
+  CK(cudaEventRecord(h->ev0, h->stream));
+  const int nlev = h->nlev;
+  if (nlev <= 32) {
+    const int stride = nlev | 1;
+    const size_t smem = (size_t)3 * TH_TILE * stride * sizeof(double);
+    const int nblocks = nblk(h->ncol, TH_TILE);
+    if (nlev <= 16) {
+      CK(cudaFuncSetAttribute(thermal_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      thermal_step_kernel<16><<<nblocks, TH_TILE, smem, h->stream>>>(A);
+    } else {
+      CK(cudaFuncSetAttribute(thermal_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      thermal_step_kernel<32><<<nblocks, TH_TILE, smem, h->stream>>>(A);
+    }
+  } else {
+    if (!t->work) CK(cudaMalloc((void **)&t->work, 4 * h->ncells * sizeof(double)));
+    thermal_step_generic_kernel<<<nblk(h->ncol, 64), 64, 0, h->stream>>>(A, t->work);
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  t->T_cur = A.T_out;                              // PostSolve: soln -> soln_prev (SOEBasePostSolve :650-668)
+  return 0;
+}

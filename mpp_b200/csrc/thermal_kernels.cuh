@@ -1,6 +1,280 @@
-// thermal_kernels.cuh -- placeholder state (filled in by the thermal milestone)
+// thermal_kernels.cuh -- fused soil heat-conduction time step (T-based, KSP path) for batches of independent columns.
+//
+// One launch = one sysofeqns%StepDT (SOEBaseStepDT_KSP, src/mpp/soe/SystemOfEquationsBaseType.F90:555-647):
+//   PreSolve / ComputeRHS / ComputeOperators  src/mpp/soe/SystemOfEquationsThermalType.F90:412-759
+//   conductivity + heat capacity              src/mpp/auxvar/ThermalKSPTemperatureSoilAuxType.F90:71-171
+//   Accum, Divergence, DiffHeatFlux           src/mpp/ge/GoveqnThermalKSPTemperatureSoilType.F90:671-1003
+//   ComputeOperatorsDiag                      src/mpp/ge/GoveqnThermalKSPTemperatureSoilType.F90:1007-1229
+//   KSPSolve (GMRES + ILU(0) on a tridiagonal AIJ == exact LU == Thomas)
+//
+// Mapping (B200-first; DESIGN.md "thermal kernel").  The step is linear and HBM-bound, so the kernel is laid out for
+// bandwidth: every array is read once, in the reference's own cell order (icell = c*nlev + j), by a lane-per-cell
+// pass (GROUP lanes per column, fully coalesced, neighbour layers via warp shuffles) that turns the twelve inputs
+// of a cell into its tridiagonal row (b, c, rhs; the matrix is symmetric so a_j = c_{j-1}) parked in shared
+// memory; then a thread-per-column pass runs the Thomas algorithm out of shared memory (odd row stride =>
+// conflict-free), and a last lane-per-cell pass streams the new temperatures back, again fully coalesced.
 #pragma once
 #include <cuda_runtime.h>
+#include "physics.cuh"
+
 namespace mpp {
-struct ThermalState { cudaStream_t stream = nullptr; double cnfac = 0.5; };
+
+constexpr int TH_TILE = 128;            // columns per block == threads per block
+constexpr int TH_MAX_SS = 4;
+
+struct ThermalArgs {
+  int ncol, nlev, nlevsoi;
+  int istsoil, istcrop, istice, istice_mec, istwet;
+  double dt, cnfac;
+  // static
+  const double *por, *tkmg, *tkdry, *csol, *dz, *area;
+  const double *dist_up, *dist_dn;     // per cell: connection j -> j+1 (nullptr: dz/2 of the two cells)
+  const int *lun_type;                  // per column
+  // per-step inputs (SoE mailbox)
+  const double *T_in, *liq, *ice, *snow_water, *tuning;
+  const int *nsnow, *active;
+  // boundary conditions: slot 0 = SOIL_TOP_CELLS, slot 1 = SOIL_BOTTOM_CELLS
+  int bc_type[2];                       // 0 none, 505 Dirichlet, 507 heat flux
+  const double *bc_value[2], *bc_dhsdT[2], *bc_frac[2];
+  const double *bc_active[2];           // 0/1 flags as doubles (real-valued VAR_ACTIVE, thermal_mms_problem.F90:633)
+  int top_is_first;
+  double stale_area;                    // see ThermalKSPTempSoilDivergence's Dirichlet branch (:883-908)
+  int nss; const double *ss_value[TH_MAX_SS]; int ss_region[TH_MAX_SS];
+  double *T_out;
+  double *therm_cond, *heat_cap;        // optional diagnostics (nullptr to skip)
+};
+
+// ThermKSPTempSoilAuxVarCompute, ThermalKSPTemperatureSoilAuxType.F90:71-171
+__device__ __forceinline__ void thermal_auxvar(const ThermalArgs &A, int itype, bool shallow, double T, double liq, double ice,
+                                               double snoww, int nsnow, double por, double tkmg, double tkdry, double csol,
+                                               double dz, double &tk, double &hc)
+{
+  const double LN_TKWAT = -0.56211891815354120;   // ln(0.57)
+  const double LN_TKICE = 0.82855181756614820;    // ln(2.29)
+  tk = 0.0; hc = 0.0;
+  if (itype == A.istsoil || itype == A.istcrop) {
+    if (shallow) {
+      double satw = (liq / DENH2O + ice / DENICE) / (dz * por);
+      satw = fmin(1.0, satw);
+      if (satw > (double).1e-6f) {
+        const double dke = (T >= TFRZ) ? fmax(0.0, log10(satw) + 1.0) : satw;
+        const double l = liq / (DENH2O * dz), i = ice / (DENICE * dz);
+        const double fl = l / (l + i);
+        // tkmg * tkwat^(fl por) * tkice^((1-fl) por)
+        const double dksat = tkmg * exp(por * (fl * LN_TKWAT + (1.0 - fl) * LN_TKICE));
+        tk = dke * dksat + (1.0 - dke) * tkdry;
+      } else {
+        tk = tkdry;
+      }
+      hc = csol * (1.0 - por) * dz + ice * CPICE + liq * CPLIQ;
+      if (nsnow == 0) hc = hc + snoww * CPICE;
+    } else {
+      tk = THK_BEDROCK;
+      hc = csol * (1.0 - por) * dz + ice * CPICE + liq * CPLIQ;
+    }
+    hc = hc / dz;
+  } else if (itype == A.istwet) {
+    if (shallow) {
+      tk = (T < TFRZ) ? TKICE : TKWAT;
+      hc = ice * CPICE + liq * CPLIQ;
+      if (nsnow == 0) hc = hc + snoww * CPICE;
+      hc = hc / dz;
+    } else { tk = THK_BEDROCK; hc = csol; }
+  } else if (itype == A.istice || itype == A.istice_mec) {
+    tk = (T < TFRZ) ? TKICE : TKWAT;
+    hc = ice * CPICE + liq * CPLIQ;
+    if (nsnow == 0) hc = hc + snoww * CPICE;
+    hc = hc / dz;
+  }
 }
+
+template <int GROUP>
+__global__ void __launch_bounds__(TH_TILE)
+thermal_step_kernel(const ThermalArgs A)
+{
+  extern __shared__ double sm[];
+  const int nlev = A.nlev;
+  const int stride = nlev | 1;                       // odd row stride: conflict-free thread-per-column access
+  double *sb = sm, *sc = sb + TH_TILE * stride, *sd = sc + TH_TILE * stride;
+  constexpr unsigned FULL = 0xffffffffu;
+  constexpr int COLS_PER_WAVE = TH_TILE / GROUP;
+  const int tile0 = blockIdx.x * TH_TILE;
+  const int j = threadIdx.x % GROUP, g = threadIdx.x / GROUP;
+  const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
+  const double dt = A.dt, cnfac = A.cnfac;
+
+  // ---------------- phase 1: lane per cell -> tridiagonal rows in shared memory ----------------
+  for (int w = 0; w < GROUP; ++w) {
+    const int cl = w * COLS_PER_WAVE + g;            // column within the tile
+    const int col = tile0 + cl;
+    const bool valid = (col < A.ncol) && (j < nlev);
+    const long long cell = (long long)col * nlev + j;
+    double T = 0.0, tk = 1.0, hc = 0.0, dz = 1.0, area = 1.0, tf = 1.0;
+    int act = 0;
+    if (valid) {
+      T = A.T_in[cell]; dz = A.dz[cell]; area = A.area[col]; tf = A.tuning[cell]; act = A.active[cell];
+      thermal_auxvar(A, A.lun_type[col], j < A.nlevsoi, T, A.liq[cell], A.ice[cell], A.snow_water[cell], A.nsnow[cell],
+                     A.por[cell], A.tkmg[cell], A.tkdry[cell], A.csol[cell], dz, tk, hc);
+      if (A.therm_cond) { A.therm_cond[cell] = tk; A.heat_cap[cell] = hc; }
+    }
+    const double vol = area * dz;
+    // connection j -> j+1
+    const double T_d = __shfl_down_sync(FULL, T, 1, GROUP), tk_d = __shfl_down_sync(FULL, tk, 1, GROUP);
+    const double dz_d = __shfl_down_sync(FULL, dz, 1, GROUP);
+    const int act_d = __shfl_down_sync(FULL, act, 1, GROUP);
+    double cval = 0.0, flux = 0.0;
+    if (valid && j < nlev - 1 && act && act_d) {
+      const double du = A.dist_up ? A.dist_up[cell] : 0.5 * dz, dd = A.dist_dn ? A.dist_dn[cell] : 0.5 * dz_d;
+      const double dist = du + dd;
+      const double kav = tk * tk_d * dist / (tk * dd + tk_d * du);          // distance-weighted harmonic mean
+      flux = -kav * (T - T_d) / dist * area;                                  // DiffHeatFlux * area
+      cval = (1.0 - cnfac) * kav / dist * area;
+    }
+    const double cval_m = __shfl_up_sync(FULL, cval, 1, GROUP), flux_m = __shfl_up_sync(FULL, flux, 1, GROUP);
+    double bb, rhs;
+    if (act) { bb = hc * vol / (dt * tf); rhs = bb * T; } else { bb = 1.0; rhs = 0.0; }
+    // NB reference evaluates heat_cap*vol/(dt*tfactor)*T left to right: same association as bb * T
+    rhs = rhs + cnfac * flux; bb += cval;
+    if (j > 0) { rhs = rhs - cnfac * flux_m; bb += cval_m; }
+    if (valid && act) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (A.bc_type[k] == 0 || j != (k == 0 ? jtop : jbot)) continue;
+        if (A.bc_type[k] == 507) {                  // COND_HEAT_FLUX: value = H - dH/dT * T_cell (GoveqnThermalKSP...:344-348)
+          const double H = A.bc_value[k][col], dH = A.bc_dhsdT[k][col], fr = A.bc_frac[k][col];
+          rhs = rhs + (H - dH * T) * fr * area;
+          bb += -fr * ((area == 1.0) ? dH : pow(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
+        } else if (A.bc_active[k][col] != 0.0) {    // COND_DIRICHLET
+          double tkb, hcb;
+          const double Tb = A.bc_value[k][col];
+          // boundary aux vars never receive is_soil_shallow / water contents (MultiPhysicsProbThermal.F90:195-203)
+          thermal_auxvar(A, A.lun_type[col], false, Tb, 0.0, 0.0, 0.0, 0, A.por[cell], A.tkmg[cell], A.tkdry[cell], A.csol[cell], dz, tkb, hcb);
+          const double du = 0.0, dd = 0.5 * dz, dist = du + dd;
+          const double kav = tkb * tk * dist / (tkb * dd + tk * du);
+          rhs = rhs + kav / dist * Tb * A.stale_area;
+          bb += A.bc_frac[k][col] * (1.0 - cnfac) * kav / dist * area;
+        }
+      }
+      for (int k = 0; k < A.nss; ++k) {             // COND_HEAT_RATE
+        if (A.ss_region[k] == 403) rhs = rhs + A.ss_value[k][cell];
+        else if (j == (A.ss_region[k] == 401 ? jtop : jbot)) rhs = rhs + A.ss_value[k][col];
+      }
+    }
+    if (j < nlev) { sb[cl * stride + j] = bb; sc[cl * stride + j] = -cval; sd[cl * stride + j] = rhs; }
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: thread per column, Thomas (symmetric: a_j = c_{j-1}) ----------------
+  if (tile0 + (int)threadIdx.x < A.ncol) {
+    double *b = sb + threadIdx.x * stride, *c = sc + threadIdx.x * stride, *d = sd + threadIdx.x * stride;
+    double cprev = c[0];
+    double cp = cprev / b[0], dp = d[0] / b[0];
+    c[0] = cp; d[0] = dp;
+    for (int i = 1; i < nlev; ++i) {
+      const double a_i = cprev;                      // sub-diagonal = the untouched super-diagonal of the row above
+      cprev = c[i];
+      const double m = b[i] - a_i * cp;
+      cp = cprev / m;
+      dp = (d[i] - a_i * dp) / m;
+      c[i] = cp; d[i] = dp;
+    }
+    double x = dp;
+    for (int i = nlev - 2; i >= 0; --i) { x = d[i] - c[i] * x; d[i] = x; }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3: lane per cell, coalesced store ----------------
+  for (int w = 0; w < GROUP; ++w) {
+    const int cl = w * COLS_PER_WAVE + g;
+    const int col = tile0 + cl;
+    if (col < A.ncol && j < nlev) A.T_out[(long long)col * nlev + j] = sd[cl * stride + j];
+  }
+}
+
+// Any nlev: one thread per column straight from global memory (correctness path for tall columns).
+__global__ void thermal_step_generic_kernel(const ThermalArgs A, double *work /* 4 * ncells */)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= A.ncol) return;
+  const int nlev = A.nlev;
+  const long long c0 = (long long)col * nlev, N = (long long)A.ncol * nlev;
+  double *b = work + c0, *c = work + N + c0, *d = work + 2 * N + c0, *tkv = work + 3 * N + c0;
+  const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
+  const double area = A.area[col], dt = A.dt, cnfac = A.cnfac;
+  const int itype = A.lun_type[col];
+  for (int j = 0; j < nlev; ++j) {
+    const long long cell = c0 + j;
+    double tk, hc;
+    thermal_auxvar(A, itype, j < A.nlevsoi, A.T_in[cell], A.liq[cell], A.ice[cell], A.snow_water[cell], A.nsnow[cell],
+                   A.por[cell], A.tkmg[cell], A.tkdry[cell], A.csol[cell], A.dz[cell], tk, hc);
+    if (A.therm_cond) { A.therm_cond[cell] = tk; A.heat_cap[cell] = hc; }
+    tkv[j] = tk; c[j] = 0.0;
+    if (A.active[cell]) { b[j] = hc * (area * A.dz[cell]) / (dt * A.tuning[cell]); d[j] = b[j] * A.T_in[cell]; }
+    else { b[j] = 1.0; d[j] = 0.0; }
+  }
+  for (int j = 0; j < nlev - 1; ++j) {
+    const long long cell = c0 + j;
+    if (!A.active[cell] || !A.active[cell + 1]) continue;
+    const double du = A.dist_up ? A.dist_up[cell] : 0.5 * A.dz[cell], dd = A.dist_dn ? A.dist_dn[cell] : 0.5 * A.dz[cell + 1];
+    const double dist = du + dd;
+    const double kav = tkv[j] * tkv[j + 1] * dist / (tkv[j] * dd + tkv[j + 1] * du);
+    const double flux = -kav * (A.T_in[cell] - A.T_in[cell + 1]) / dist * area;
+    const double cval = (1.0 - cnfac) * kav / dist * area;
+    d[j] = d[j] + cnfac * flux; d[j + 1] = d[j + 1] - cnfac * flux;
+    b[j] += cval; b[j + 1] += cval; c[j] = -cval;
+  }
+  for (int k = 0; k < 2; ++k) {
+    if (A.bc_type[k] == 0) continue;
+    const int j = (k == 0) ? jtop : jbot;
+    const long long cell = c0 + j;
+    if (!A.active[cell]) continue;
+    const double T = A.T_in[cell], dz = A.dz[cell];
+    if (A.bc_type[k] == 507) {
+      const double H = A.bc_value[k][col], dH = A.bc_dhsdT[k][col], fr = A.bc_frac[k][col];
+      d[j] = d[j] + (H - dH * T) * fr * area;
+      b[j] += -fr * ((area == 1.0) ? dH : pow(dH, area));
+    } else if (A.bc_active[k][col] != 0.0) {
+      double tkb, hcb;
+      const double Tb = A.bc_value[k][col];
+      thermal_auxvar(A, itype, false, Tb, 0.0, 0.0, 0.0, 0, A.por[cell], A.tkmg[cell], A.tkdry[cell], A.csol[cell], dz, tkb, hcb);
+      const double du = 0.0, dd = 0.5 * dz, dist = du + dd;
+      const double kav = tkb * tkv[j] * dist / (tkb * dd + tkv[j] * du);
+      d[j] = d[j] + kav / dist * Tb * A.stale_area;
+      b[j] += A.bc_frac[k][col] * (1.0 - cnfac) * kav / dist * area;
+    }
+  }
+  for (int k = 0; k < A.nss; ++k) {
+    if (A.ss_region[k] == 403) { for (int j = 0; j < nlev; ++j) if (A.active[c0 + j]) d[j] = d[j] + A.ss_value[k][c0 + j]; }
+    else { const int j = (A.ss_region[k] == 401) ? jtop : jbot; if (A.active[c0 + j]) d[j] = d[j] + A.ss_value[k][col]; }
+  }
+  // Thomas, a_j = c_{j-1}
+  double cprev = c[0], cp = c[0] / b[0], dp = d[0] / b[0];
+  c[0] = cp; d[0] = dp;
+  for (int i = 1; i < nlev; ++i) {
+    const double a_i = cprev;
+    cprev = c[i];
+    const double m = b[i] - a_i * c[i - 1];
+    c[i] = c[i] / m;
+    d[i] = (d[i] - a_i * d[i - 1]) / m;
+  }
+  for (int i = nlev - 2; i >= 0; --i) d[i] = d[i] - c[i] * d[i + 1];
+  for (int j = 0; j < nlev; ++j) A.T_out[c0 + j] = d[j];
+}
+
+struct ThermalState {
+  cudaStream_t stream = nullptr;
+  int ncol = 0, nlev = 0, orientation = 311, nlevsoi = 0;
+  int istsoil = 1, istcrop = 2, istice = 3, istice_mec = 4, istwet = 6;
+  double cnfac = 0.5;                    // mpp_varcon.F90:28
+  bool soils_set = false, custom_dist = false, diagnostics = false;
+  const double *d_dz = nullptr, *d_area = nullptr;   // owned by the handle
+  double *por = nullptr, *tkmg = nullptr, *tkdry = nullptr, *csol = nullptr, *dist_up = nullptr, *dist_dn = nullptr;
+  int *lun_type = nullptr;
+  double *T_clm = nullptr, *T_work = nullptr, *T_cur = nullptr;
+  double *liq = nullptr, *ice = nullptr, *snow_water = nullptr, *tuning = nullptr, *frac = nullptr, *aux_dz = nullptr,
+         *aux_dist_up = nullptr, *aux_dist_dn = nullptr, *therm_cond = nullptr, *heat_cap = nullptr, *work = nullptr;
+  int *nsnow = nullptr, *active = nullptr;
+  double stale_area = 1.0;
+};
+
+}  // namespace mpp

@@ -72,6 +72,11 @@ class _SoE:
 
     SetMesh = set_mesh
 
+    def set_connection_distances(self, dist_up, dist_dn):
+        """mpp%CreateAndAddConnectionSet(..., dist_up, dist_dn, ...): (ncol, nlev-1) centroid-to-face distances."""
+        du, dd = _table(dist_up, self.ncol, self.nlev - 1), _table(dist_dn, self.ncol, self.nlev - 1)
+        check(self.L.mppgpu_set_connection_distances(self.h, _dp(du), _dp(dd)))
+
     def add_condition(self, ieqn, ss_or_bc, cond_type, region):
         """soe%AddConditionInGovEqn(ieqn, COND_BC|COND_SS, name, units, cond_type, region) -> 1-based condition id."""
         cid = C.c_int()

@@ -199,6 +199,7 @@ void      orc_thermal_destroy(orc_thermal *p);
 void      orc_thermal_set_threads(orc_thermal *p, int nthreads);
 int       orc_thermal_set_mesh(orc_thermal *p, int orientation, const double *dz, const double *area,
                                const double *face_area /* internal conn area per column or NULL */);
+int       orc_thermal_set_conn_dist(orc_thermal *p, const double *dist_up /*(ncol,nlev-1) F-order*/, const double *dist_dn);
 int       orc_thermal_add_condition(orc_thermal *p, int ss_or_bc, int cond_type, int region);
 int       orc_thermal_set_soils(orc_thermal *p, const double *watsat, const double *csol, const double *tkmg,
                                 const double *tkdry, const int *lun_type /*ncol*/, int nlevsoi, int istsoil_id);

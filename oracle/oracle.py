@@ -189,3 +189,84 @@ class OracleVSFM:
         f, ja, jb, jc = (np.zeros(self.ncells) for _ in range(4))
         self.L.orc_vsfm_eval(self.h, C.c_double(dt), dp(x_prev), dp(x), dp(f), dp(ja), dp(jb), dp(jc))
         return f, ja, jb, jc
+
+
+class OracleThermal:
+    """Same call surface as mpp_b200.soe.Thermal."""
+
+    def __init__(self, ncol, nlev, nthreads=1, **kw):
+        self.L = lib()
+        self.ncol, self.nlev, self.ncells = ncol, nlev, ncol * nlev
+        self.h = C.c_void_p(self.L.orc_thermal_create(ncol, nlev))
+        self.L.orc_thermal_set_threads(self.h, int(nthreads))
+
+    def __del__(self):
+        try:
+            self.L.orc_thermal_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_mesh(self, orientation, dz, area, col_active=None):
+        dz, area = table(dz, self.ncol, self.nlev), f64(area)
+        return self.L.orc_thermal_set_mesh(self.h, int(orientation), dp(dz), dp(area), None)
+
+    def set_connection_distances(self, dist_up, dist_dn):
+        du, dd = table(dist_up, self.ncol, self.nlev - 1), table(dist_dn, self.ncol, self.nlev - 1)
+        return self.L.orc_thermal_set_conn_dist(self.h, dp(du), dp(dd))
+
+    def add_condition(self, ieqn, ss_or_bc, cond_type, region):
+        return self.L.orc_thermal_add_condition(self.h, int(ss_or_bc), int(cond_type), int(region))
+
+    def set_soils(self, watsat, csol, tkmg, tkdry, lun_type, nlevsoi, istsoil=1):
+        a = [table(x, self.ncol, self.nlev) for x in (watsat, csol, tkmg, tkdry)]
+        lt = i32(lun_type)
+        return self.L.orc_thermal_set_soils(self.h, *[dp(x) for x in a], ip(lt), int(nlevsoi), int(istsoil))
+
+    def set_cnfac(self, cnfac):
+        self.L.orc_thermal_set_cnfac(self.h, C.c_double(cnfac))
+
+    def set_soln_prev(self, T):
+        T = f64(T)
+        assert T.size == self.ncells
+        self.L.orc_thermal_set_soln_prev(self.h, dp(T))
+
+    restart = set_soln_prev
+
+    def set_data(self, auxvar_type, var_type, cond_id, data, ieqn=1):
+        data = f64(data)
+        rc = self.L.orc_thermal_set_rdata(self.h, int(auxvar_type), int(var_type), int(cond_id), dp(data), int(data.size))
+        if rc:
+            raise ValueError("set_rdata rc=%d" % rc)
+
+    set_rdata = set_data
+
+    def set_idata(self, auxvar_type, var_type, cond_id, data):
+        data = i32(data)
+        rc = self.L.orc_thermal_set_idata(self.h, int(auxvar_type), int(var_type), int(cond_id), ip(data), int(data.size))
+        if rc:
+            raise ValueError("set_idata rc=%d" % rc)
+
+    def pre_step_dt(self):
+        self.L.orc_thermal_pre_step_dt(self.h)
+
+    def post_step_dt(self):
+        pass
+
+    def step_dt(self, dt, nstep=1):
+        conv = C.c_int()
+        self.L.orc_thermal_step_dt(self.h, C.c_double(dt), int(nstep), C.byref(conv))
+        return bool(conv.value), 0
+
+    def get_soln(self):
+        out = np.empty(self.ncells)
+        self.L.orc_thermal_get_soln(self.h, dp(out))
+        return out
+
+    def get_data(self, auxvar_type, var_type, cond_id, n=None, ieqn=1):
+        if var_type == 605:
+            return self.get_soln()
+        out = np.empty(self.ncells)
+        rc = self.L.orc_thermal_get_aux(self.h, int(var_type), dp(out))
+        if rc:
+            raise ValueError("get_aux rc=%d" % rc)
+        return out

@@ -155,3 +155,101 @@ def elm_vsfm_step(p, ids, d, dt=1800.0, nstep=1, scale=1.0):
            (("sat", K.VAR_LIQ_SAT), ("mass", K.VAR_MASS), ("smp", K.VAR_SOIL_MATRIX_POT), ("pressure", K.VAR_PRESSURE))}
     p.post_step_dt()
     return conv, reason, out
+
+
+# ---------------------------------------------------------------------------------------------------
+# thermal_mms (1-D steady state, KSP path) -- src/driver/standalone/thermal/thermal_mms_problem.F90
+#   + thermal_mms_steady_state_problem_1D.F90; baseline regression_tests/thermal/thermal_mms.regression.baseline
+# ---------------------------------------------------------------------------------------------------
+def build_thermal_mms(cls, nx=20, **kw):
+    """20 cells along x (one chain = one 'column' with nx layers), cnfac = 0, conductivity exp(x) through tkdry,
+    no water (so kappa = kappa_dry and zero heat capacity), Dirichlet at both ends, manufactured source."""
+    dx = 1.0 / nx
+    xc = dx / 2.0 + dx * np.arange(nx)
+    p = cls(1, nx, **kw)
+    p.set_mesh(K.MESH_HORIZONTAL, np.full((1, nx), dx), np.array([1.0]))           # area = dy*dz = 1
+    p.set_cnfac(0.0)                                                               # :72
+    b0 = p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS)          # ii = 1 end
+    b1 = p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS)       # ii = nx end
+    ss = p.add_condition(1, K.COND_SS, K.COND_HEAT_RATE, K.SOIL_CELLS)              # ALL_CELLS
+    full = lambda v: np.full((1, nx), v)
+    p.set_soils(full(0.1), full(0.0), full(0.0), np.exp(xc)[None, :], np.array([K.ISTSOIL]), nx, K.ISTSOIL)   # :521-541
+    p.set_soln_prev(np.full(nx, 290.0))                                            # :602, :619
+    p.set_data(K.AUXVAR_INTERNAL, K.VAR_TUNING_FACTOR, 1, np.ones(nx))
+    p.set_data(K.AUXVAR_INTERNAL, K.VAR_LIQ_AREAL_DEN, 1, np.zeros(nx))
+    T = lambda x: 10.0 * np.sin(np.pi * x) + 270.0
+    for cid, xb in ((b0, xc[0] - dx / 2.0), (b1, xc[-1] + dx / 2.0)):
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, cid, np.array([T(xb)]))
+        p.set_data(K.AUXVAR_BC, K.VAR_ACTIVE, cid, np.array([1.0]))                # :633-637
+        p.set_data(K.AUXVAR_BC, K.VAR_FRAC, cid, np.array([1.0]))
+    lam, dlam = np.exp(xc), np.exp(xc)
+    dT, d2T = 10.0 * np.pi * np.cos(np.pi * xc), -10.0 * np.pi * np.pi * np.sin(np.pi * xc)
+    src = (-dlam * dT - lam * d2T) * dx * 1.0 * 1.0                                # 1D.F90:152-163
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ss, src)
+    return p
+
+
+def run_thermal_mms(p):
+    p.pre_step_dt()
+    conv, _ = p.step_dt(1.0, 1)                                                    # :200
+    assert conv
+    return p.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# ELM-like batched soil thermal columns -- config #2 (SURVEY.md section 8d; MPPThermalTBasedALM_Driver.F90:290-452)
+# ---------------------------------------------------------------------------------------------------
+def elm_thermal_inputs(ncol, nlev=15, seed=SEED, nlevsoi=10):
+    rng = np.random.default_rng(seed + 1)
+    z, zi, dz = elm_layers(nlev)
+    d = {"ncol": ncol, "nlev": nlev, "nlevsoi": nlevsoi}
+    d["dz"] = np.tile(dz, (ncol, 1)); d["area"] = np.ones(ncol)
+    # MPPThermalTBasedALM_Initialize.F90:379-381: dist_up = zi(j) - z(j), dist_dn = z(j+1) - zi(j)
+    d["dist_up"] = np.tile(zi[1:nlev] - z[:nlev - 1], (ncol, 1)); d["dist_dn"] = np.tile(z[1:] - zi[1:nlev], (ncol, 1))
+    d["watsat"] = rng.uniform(0.35, 0.55, (ncol, nlev))
+    d["csol"] = rng.uniform(1.9e6, 2.4e6, (ncol, nlev))
+    d["tkmg"] = rng.uniform(1.5, 3.5, (ncol, nlev))
+    d["tkdry"] = rng.uniform(0.15, 0.3, (ncol, nlev))
+    d["lun_type"] = np.full(ncol, K.ISTSOIL, dtype=np.int32)
+    T0 = 270.0 + 20.0 * rng.uniform(size=(ncol, nlev))
+    theta = rng.uniform(0.1, 0.9, (ncol, nlev)) * d["watsat"]
+    water = theta * 1000.0 * d["dz"]                                   # kg m^-2
+    frozen = T0 <= 273.15
+    d["ice"] = np.where(frozen, 0.3 * water, 0.0).reshape(-1)
+    d["liq"] = np.where(frozen, 0.7 * water, water).reshape(-1)
+    d["T0"] = T0.reshape(-1)
+    d["snow_water"] = np.zeros(ncol * nlev)
+    d["nsnow"] = np.zeros(ncol * nlev, dtype=np.int32)
+    d["tuning"] = np.ones(ncol * nlev)
+    d["hs"] = rng.uniform(-50.0, 150.0, ncol)                          # W m^-2
+    d["dhsdT"] = rng.uniform(-20.0, -5.0, ncol)
+    d["frac"] = np.ones(ncol)
+    d["sabg"] = np.zeros(ncol * nlev)
+    return d
+
+
+def build_elm_thermal(cls, d, **kw):
+    ncol, nlev = d["ncol"], d["nlev"]
+    p = cls(ncol, nlev, **kw)
+    p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"])
+    p.set_connection_distances(d["dist_up"], d["dist_dn"])
+    ids = {"hs": p.add_condition(1, K.COND_BC, K.COND_HEAT_FLUX, K.SOIL_TOP_CELLS),       # MPPThermalTBasedALM_Initialize.F90:596-601
+           "sabg": p.add_condition(1, K.COND_SS, K.COND_HEAT_RATE, K.SOIL_CELLS)}
+    p.set_soils(d["watsat"], d["csol"], d["tkmg"], d["tkdry"], d["lun_type"], d["nlevsoi"], K.ISTSOIL)
+    return p, ids
+
+
+def elm_thermal_step(p, ids, d, T, dt=1800.0, nstep=1):
+    """One ELM thermal coupling step (MPPThermalTBasedALM_Driver.F90:331-452)."""
+    p.set_soln_prev(T)
+    for var, key in ((K.VAR_LIQ_AREAL_DEN, "liq"), (K.VAR_ICE_AREAL_DEN, "ice"), (K.VAR_SNOW_WATER, "snow_water"),
+                     (K.VAR_TUNING_FACTOR, "tuning")):
+        p.set_data(K.AUXVAR_INTERNAL, var, 1, d[key])
+    p.set_idata(K.AUXVAR_INTERNAL, K.VAR_NUM_SNOW_LYR, 1, d["nsnow"])
+    p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids["hs"], d["hs"])
+    p.set_data(K.AUXVAR_BC, K.VAR_DHS_DT, ids["hs"], d["dhsdT"])
+    p.set_data(K.AUXVAR_BC, K.VAR_FRAC, ids["hs"], d["frac"])
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["sabg"], d["sabg"])
+    p.pre_step_dt()
+    conv, _ = p.step_dt(dt, nstep)
+    return conv, p.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, 1)

@@ -126,3 +126,28 @@ def test_elm_like_mass_balance(oracle):
     q = d["infil"] + d["et"].reshape(16, 15).sum(1)
     err = np.abs(m0 - m1 + q * 1800.0)
     assert conv and err.max() < 1e-5
+
+
+def test_thermal_mms_reproduces_reference_baseline(oracle, golden):
+    # regression_tests/thermal/thermal_mms.regression.baseline (category general => 1e-16 abs: every printed digit)
+    T = PB.run_thermal_mms(PB.build_thermal_mms(oracle.OracleThermal))
+    ref = golden["thermal_mms"]["temperature"]
+    _assert_matches_printed(T.min(), ref["min"])
+    _assert_matches_printed(T.max(), ref["max"])
+    _assert_matches_printed(T.sum() / T.size, ref["mean"])
+    for key, val in ref.items():
+        if key.startswith("cell"):
+            _assert_matches_printed(T[int(key.split()[1]) - 1], val)
+    lines = PB.regression_block("temperature", "general", T, 5)
+    assert lines[2] == "min =   0.2707677262973E+03" and lines[5] == "cell    1 =   0.2707677262973E+03"
+    assert lines[9] == "cell   17 =   0.2752526149775E+03"
+
+
+def test_thermal_energy_balance_oracle(oracle):
+    d = PB.elm_thermal_inputs(32, 15)
+    d["dhsdT"] = np.zeros(32)
+    o, ids = PB.build_elm_thermal(oracle.OracleThermal, d)
+    conv, T1 = PB.elm_thermal_step(o, ids, d, d["T0"], 1800.0, 1)
+    hc = d["csol"] * (1 - d["watsat"]) * d["dz"] + d["ice"].reshape(32, 15) * 2.11727e3 + d["liq"].reshape(32, 15) * 4.188e3
+    dE = (hc * (T1.reshape(32, 15) - d["T0"].reshape(32, 15))).sum(1)
+    assert np.max(np.abs(dE - d["hs"] * 1800.0)) < 1e-6 * np.max(np.abs(d["hs"] * 1800.0))

@@ -1,17 +1,32 @@
-"""Quick device-resident timing of the VSFM step kernel (development aid; not the headline bench)."""
+"""Quick device-resident timing of the step kernels (development aid; not the headline bench)."""
 import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
 import problems as PB, bench
 import mpp_b200
-ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
-d = bench.shard_inputs(0, ncol)
-p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
-bench.set_forcing_host(p, ids, d)
-ms = []
-for s in range(8):
-    p.pre_step_dt(); p.step_dt(1800.0, s + 1); p.post_step_dt()
-    ms.append(p.last_step_ms())
-st = p.stats()
-print(os.environ.get("MPPGPU_LIB_PATH", "default"), "ncol", ncol, "ms/step", ["%.2f" % m for m in ms], "col-steps/s %.3e" % (ncol / (np.mean(ms[3:]) * 1e-3)),
-      "its mean %.2f nf mean %.2f" % (st["newton_its"].mean(), st["nfuncs"].mean()))
+from mpp_b200 import constants as K
+mode = sys.argv[1] if len(sys.argv) > 1 else "vsfm"
+ncol = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
+if mode == "vsfm":
+    d = bench.shard_inputs(0, ncol)
+    p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
+    bench.set_forcing_host(p, ids, d)
+    ms = []
+    for s in range(8):
+        p.pre_step_dt(); p.step_dt(1800.0, s + 1); p.post_step_dt()
+        ms.append(p.last_step_ms())
+    st = p.stats()
+    print(os.environ.get("MPPGPU_LIB_PATH", "default"), "vsfm ncol", ncol, "ms/step", ["%.2f" % m for m in ms], "col-steps/s %.3e" % (ncol / (np.mean(ms[3:]) * 1e-3)),
+          "its mean %.2f nf mean %.2f" % (st["newton_its"].mean(), st["nfuncs"].mean()))
+else:
+    d = PB.elm_thermal_inputs(ncol, 15)
+    p, ids = PB.build_elm_thermal(mpp_b200.Thermal, d)
+    T = d["T0"]
+    conv, T = PB.elm_thermal_step(p, ids, d, T, 1800.0, 1)
+    ms = []
+    for s in range(10):
+        p.step_dt(1800.0, s + 2)           # device-resident chain: soln -> soln_prev
+        ms.append(p.last_step_ms())
+    m = float(np.mean(ms[3:]))
+    print("thermal ncol", ncol, "ms/step", ["%.3f" % x for x in ms], "col-steps/s %.3e" % (ncol / (m * 1e-3)),
+          "alg GB/s (1224 B/col) %.0f" % (1224 * ncol / (m * 1e-3) / 1e9))
