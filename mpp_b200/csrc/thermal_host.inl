@@ -174,16 +174,8 @@ static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
   CK(cudaEventRecord(h->ev0, h->stream));
   const int nlev = h->nlev;
   if (nlev <= 32) {
-    const int stride = nlev | 1;
-    const size_t smem = (size_t)3 * TH_TILE * stride * sizeof(double);
-    const int nblocks = nblk(h->ncol, TH_TILE);
-    if (nlev <= 16) {
-      CK(cudaFuncSetAttribute(thermal_step_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      thermal_step_kernel<16><<<nblocks, TH_TILE, smem, h->stream>>>(A);
-    } else {
-      CK(cudaFuncSetAttribute(thermal_step_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      thermal_step_kernel<32><<<nblocks, TH_TILE, smem, h->stream>>>(A);
-    }
+    if (nlev <= 16) thermal_step_kernel<16><<<nblk((long long)h->ncol * 16, TH_TILE), TH_TILE, 0, h->stream>>>(A);
+    else            thermal_step_kernel<32><<<nblk((long long)h->ncol * 32, TH_TILE), TH_TILE, 0, h->stream>>>(A);
   } else {
     if (!t->work) CK(cudaMalloc((void **)&t->work, 4 * h->ncells * sizeof(double)));
     thermal_step_generic_kernel<<<nblk(h->ncol, 64), 64, 0, h->stream>>>(A, t->work);

@@ -54,12 +54,12 @@ __device__ __forceinline__ void thermal_auxvar(const ThermalArgs &A, int itype, 
   tk = 0.0; hc = 0.0;
   if (itype == A.istsoil || itype == A.istcrop) {
     if (shallow) {
-      double satw = (liq / DENH2O + ice / DENICE) / (dz * por);
+      const double l = liq * (1.0 / DENH2O), i = ice * (1.0 / DENICE);      // water / ice depth [m]
+      double satw = (l + i) / (dz * por);
       satw = fmin(1.0, satw);
       if (satw > (double).1e-6f) {
         const double dke = (T >= TFRZ) ? fmax(0.0, log10(satw) + 1.0) : satw;
-        const double l = liq / (DENH2O * dz), i = ice / (DENICE * dz);
-        const double fl = l / (l + i);
+        const double fl = l / (l + i);                                        // the reference's common 1/dz cancels
         // tkmg * tkwat^(fl por) * tkice^((1-fl) por)
         const double dksat = tkmg * exp(por * (fl * LN_TKWAT + (1.0 - fl) * LN_TKICE));
         tk = dke * dksat + (1.0 - dke) * tkdry;
@@ -88,107 +88,101 @@ __device__ __forceinline__ void thermal_auxvar(const ThermalArgs &A, int itype, 
   }
 }
 
+// Parallel cyclic reduction across a GROUP-lane group (one tridiagonal row per lane, identity rows pad the group).
+template <int GROUP>
+__device__ __forceinline__ double thermal_pcr(double a, double b, double c, double d)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll
+  for (int s = 1; s < GROUP; s <<= 1) {
+    const double r   = __drcp_rn(b);
+    const double a_m = __shfl_up_sync(FULL, a, s, GROUP),   c_m = __shfl_up_sync(FULL, c, s, GROUP);
+    const double d_m = __shfl_up_sync(FULL, d, s, GROUP),   r_m = __shfl_up_sync(FULL, r, s, GROUP);
+    const double a_p = __shfl_down_sync(FULL, a, s, GROUP), c_p = __shfl_down_sync(FULL, c, s, GROUP);
+    const double d_p = __shfl_down_sync(FULL, d, s, GROUP), r_p = __shfl_down_sync(FULL, r, s, GROUP);
+    const double k1 = a * r_m, k2 = c * r_p;
+    b = b - c_m * k1 - a_p * k2;
+    d = d - d_m * k1 - d_p * k2;
+    a = -a_m * k1;
+    c = -c_p * k2;
+  }
+  return d * __drcp_rn(b);
+}
+
+// One lane per soil cell, GROUP lanes per column: every array is streamed once in the reference's cell order
+// (fully coalesced), neighbour layers come from warp shuffles, the tridiagonal system is solved in registers by
+// parallel cyclic reduction, and the new temperature goes straight back to HBM.  No shared memory, no block
+// barriers: occupancy is bounded by registers only, which is what hides the HBM latency.
 template <int GROUP>
 __global__ void __launch_bounds__(TH_TILE)
 thermal_step_kernel(const ThermalArgs A)
 {
-  extern __shared__ double sm[];
-  const int nlev = A.nlev;
-  const int stride = nlev | 1;                       // odd row stride: conflict-free thread-per-column access
-  double *sb = sm, *sc = sb + TH_TILE * stride, *sd = sc + TH_TILE * stride;
   constexpr unsigned FULL = 0xffffffffu;
-  constexpr int COLS_PER_WAVE = TH_TILE / GROUP;
-  const int tile0 = blockIdx.x * TH_TILE;
-  const int j = threadIdx.x % GROUP, g = threadIdx.x / GROUP;
+  const int nlev = A.nlev;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = (int)(tid / GROUP), j = (int)(tid % GROUP);
   const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
   const double dt = A.dt, cnfac = A.cnfac;
+  const bool valid = (col < A.ncol) && (j < nlev);
+  const long long cell = (long long)col * nlev + j;
 
-  // ---------------- phase 1: lane per cell -> tridiagonal rows in shared memory ----------------
-  for (int w = 0; w < GROUP; ++w) {
-    const int cl = w * COLS_PER_WAVE + g;            // column within the tile
-    const int col = tile0 + cl;
-    const bool valid = (col < A.ncol) && (j < nlev);
-    const long long cell = (long long)col * nlev + j;
-    double T = 0.0, tk = 1.0, hc = 0.0, dz = 1.0, area = 1.0, tf = 1.0;
-    int act = 0;
-    if (valid) {
-      T = A.T_in[cell]; dz = A.dz[cell]; area = A.area[col]; tf = A.tuning[cell]; act = A.active[cell];
-      thermal_auxvar(A, A.lun_type[col], j < A.nlevsoi, T, A.liq[cell], A.ice[cell], A.snow_water[cell], A.nsnow[cell],
-                     A.por[cell], A.tkmg[cell], A.tkdry[cell], A.csol[cell], dz, tk, hc);
-      if (A.therm_cond) { A.therm_cond[cell] = tk; A.heat_cap[cell] = hc; }
-    }
-    const double vol = area * dz;
-    // connection j -> j+1
-    const double T_d = __shfl_down_sync(FULL, T, 1, GROUP), tk_d = __shfl_down_sync(FULL, tk, 1, GROUP);
-    const double dz_d = __shfl_down_sync(FULL, dz, 1, GROUP);
-    const int act_d = __shfl_down_sync(FULL, act, 1, GROUP);
-    double cval = 0.0, flux = 0.0;
-    if (valid && j < nlev - 1 && act && act_d) {
-      const double du = A.dist_up ? A.dist_up[cell] : 0.5 * dz, dd = A.dist_dn ? A.dist_dn[cell] : 0.5 * dz_d;
-      const double dist = du + dd;
-      const double kav = tk * tk_d * dist / (tk * dd + tk_d * du);          // distance-weighted harmonic mean
-      flux = -kav * (T - T_d) / dist * area;                                  // DiffHeatFlux * area
-      cval = (1.0 - cnfac) * kav / dist * area;
-    }
-    const double cval_m = __shfl_up_sync(FULL, cval, 1, GROUP), flux_m = __shfl_up_sync(FULL, flux, 1, GROUP);
-    double bb, rhs;
-    if (act) { bb = hc * vol / (dt * tf); rhs = bb * T; } else { bb = 1.0; rhs = 0.0; }
-    // NB reference evaluates heat_cap*vol/(dt*tfactor)*T left to right: same association as bb * T
-    rhs = rhs + cnfac * flux; bb += cval;
-    if (j > 0) { rhs = rhs - cnfac * flux_m; bb += cval_m; }
-    if (valid && act) {
+  double T = 0.0, tk = 1.0, hc = 0.0, dz = 1.0, area = 1.0, tf = 1.0, du = 0.5, dd = 0.5;
+  int act = 0;
+  if (valid) {
+    T = A.T_in[cell]; dz = A.dz[cell]; area = A.area[col]; tf = A.tuning[cell]; act = A.active[cell];
+    const double liq = A.liq[cell], ice = A.ice[cell], snoww = A.snow_water[cell];
+    const double por = A.por[cell], tkmg = A.tkmg[cell], tkdry = A.tkdry[cell], csol = A.csol[cell];
+    const int nsnow = A.nsnow[cell];
+    if (A.dist_up) { du = A.dist_up[cell]; dd = A.dist_dn[cell]; }
+    thermal_auxvar(A, A.lun_type[col], j < A.nlevsoi, T, liq, ice, snoww, nsnow, por, tkmg, tkdry, csol, dz, tk, hc);
+    if (A.therm_cond) { A.therm_cond[cell] = tk; A.heat_cap[cell] = hc; }
+  }
+  const double vol = area * dz;
+  // connection j -> j+1 (owned by lane j)
+  const double T_d = __shfl_down_sync(FULL, T, 1, GROUP), tk_d = __shfl_down_sync(FULL, tk, 1, GROUP);
+  const double dz_d = __shfl_down_sync(FULL, dz, 1, GROUP);
+  const int act_d = __shfl_down_sync(FULL, act, 1, GROUP);
+  if (!A.dist_up) { du = 0.5 * dz; dd = 0.5 * dz_d; }
+  double cval = 0.0, flux = 0.0;
+  if (valid && j < nlev - 1 && act && act_d) {
+    // kav / dist with kav the distance-weighted harmonic mean: tk tk_d (du+dd) / (tk dd + tk_d du) / (du+dd)
+    const double kod = tk * tk_d / (tk * dd + tk_d * du) * area;
+    flux = -kod * (T - T_d);                                               // DiffHeatFlux * area  (:976-1003)
+    cval = (1.0 - cnfac) * kod;                                            // ComputeOperatorsDiag (:1112)
+  }
+  const double cval_m = __shfl_up_sync(FULL, cval, 1, GROUP), flux_m = __shfl_up_sync(FULL, flux, 1, GROUP);
+  double bb, rhs;
+  if (act) { bb = hc * vol / (dt * tf); rhs = bb * T; } else { bb = 1.0; rhs = 0.0; }
+  rhs = rhs + cnfac * flux; bb += cval;
+  if (j > 0) { rhs = rhs - cnfac * flux_m; bb += cval_m; }
+  if (valid && act) {
 #pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        if (A.bc_type[k] == 0 || j != (k == 0 ? jtop : jbot)) continue;
-        if (A.bc_type[k] == 507) {                  // COND_HEAT_FLUX: value = H - dH/dT * T_cell (GoveqnThermalKSP...:344-348)
-          const double H = A.bc_value[k][col], dH = A.bc_dhsdT[k][col], fr = A.bc_frac[k][col];
-          rhs = rhs + (H - dH * T) * fr * area;
-          bb += -fr * ((area == 1.0) ? dH : pow(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
-        } else if (A.bc_active[k][col] != 0.0) {    // COND_DIRICHLET
-          double tkb, hcb;
-          const double Tb = A.bc_value[k][col];
-          // boundary aux vars never receive is_soil_shallow / water contents (MultiPhysicsProbThermal.F90:195-203)
-          thermal_auxvar(A, A.lun_type[col], false, Tb, 0.0, 0.0, 0.0, 0, A.por[cell], A.tkmg[cell], A.tkdry[cell], A.csol[cell], dz, tkb, hcb);
-          const double du = 0.0, dd = 0.5 * dz, dist = du + dd;
-          const double kav = tkb * tk * dist / (tkb * dd + tk * du);
-          rhs = rhs + kav / dist * Tb * A.stale_area;
-          bb += A.bc_frac[k][col] * (1.0 - cnfac) * kav / dist * area;
-        }
-      }
-      for (int k = 0; k < A.nss; ++k) {             // COND_HEAT_RATE
-        if (A.ss_region[k] == 403) rhs = rhs + A.ss_value[k][cell];
-        else if (j == (A.ss_region[k] == 401 ? jtop : jbot)) rhs = rhs + A.ss_value[k][col];
+    for (int k = 0; k < 2; ++k) {
+      if (A.bc_type[k] == 0 || j != (k == 0 ? jtop : jbot)) continue;
+      if (A.bc_type[k] == 507) {                    // COND_HEAT_FLUX: value = H - dH/dT * T_cell (GoveqnThermalKSP...:344-348)
+        const double H = A.bc_value[k][col], dH = A.bc_dhsdT[k][col], fr = A.bc_frac[k][col];
+        rhs = rhs + (H - dH * T) * fr * area;
+        bb += -fr * ((area == 1.0) ? dH : pow(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
+      } else if (A.bc_active[k][col] != 0.0) {      // COND_DIRICHLET
+        double tkb, hcb;
+        const double Tb = A.bc_value[k][col];
+        // boundary aux vars never receive is_soil_shallow / water contents (MultiPhysicsProbThermal.F90:195-203)
+        thermal_auxvar(A, A.lun_type[col], false, Tb, 0.0, 0.0, 0.0, 0, A.por[cell], A.tkmg[cell], A.tkdry[cell], A.csol[cell], dz, tkb, hcb);
+        const double bdu = 0.0, bdd = 0.5 * dz, dist = bdu + bdd;
+        const double kav = tkb * tk * dist / (tkb * bdd + tk * bdu);
+        rhs = rhs + kav / dist * Tb * A.stale_area;
+        bb += A.bc_frac[k][col] * (1.0 - cnfac) * kav / dist * area;
       }
     }
-    if (j < nlev) { sb[cl * stride + j] = bb; sc[cl * stride + j] = -cval; sd[cl * stride + j] = rhs; }
-  }
-  __syncthreads();
-
-  // ---------------- phase 2: thread per column, Thomas (symmetric: a_j = c_{j-1}) ----------------
-  if (tile0 + (int)threadIdx.x < A.ncol) {
-    double *b = sb + threadIdx.x * stride, *c = sc + threadIdx.x * stride, *d = sd + threadIdx.x * stride;
-    double cprev = c[0];
-    double cp = cprev / b[0], dp = d[0] / b[0];
-    c[0] = cp; d[0] = dp;
-    for (int i = 1; i < nlev; ++i) {
-      const double a_i = cprev;                      // sub-diagonal = the untouched super-diagonal of the row above
-      cprev = c[i];
-      const double m = b[i] - a_i * cp;
-      cp = cprev / m;
-      dp = (d[i] - a_i * dp) / m;
-      c[i] = cp; d[i] = dp;
+    for (int k = 0; k < A.nss; ++k) {               // COND_HEAT_RATE
+      if (A.ss_region[k] == 403) rhs = rhs + A.ss_value[k][cell];
+      else if (j == (A.ss_region[k] == 401 ? jtop : jbot)) rhs = rhs + A.ss_value[k][col];
     }
-    double x = dp;
-    for (int i = nlev - 2; i >= 0; --i) { x = d[i] - c[i] * x; d[i] = x; }
   }
-  __syncthreads();
-
-  // ---------------- phase 3: lane per cell, coalesced store ----------------
-  for (int w = 0; w < GROUP; ++w) {
-    const int cl = w * COLS_PER_WAVE + g;
-    const int col = tile0 + cl;
-    if (col < A.ncol && j < nlev) A.T_out[(long long)col * nlev + j] = sd[cl * stride + j];
-  }
+  if (!valid) { bb = 1.0; rhs = 0.0; }
+  // symmetric tridiagonal row: a_j = -cval_{j-1}, c_j = -cval_j   (KSPSolve: exact for a tridiagonal matrix)
+  const double x = thermal_pcr<GROUP>((j > 0) ? -cval_m : 0.0, bb, -cval, rhs);
+  if (valid) A.T_out[cell] = x;
 }
 
 // Any nlev: one thread per column straight from global memory (correctness path for tall columns).
