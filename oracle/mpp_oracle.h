@@ -128,6 +128,10 @@ void orc_richards_flux(const orc_rich_auxvar *up, const orc_rich_auxvar *dn, con
                        int compute_deriv, int internal_conn, int swap_order, int cond_type,
                        double *flux, double *dflux_dP_up, double *dflux_dP_dn);
 
+/* src/mpp/ge/RichardsMod.F90:343-648 (true derivatives wrt temperature; swap_order = .false.) */
+void orc_richards_flux_dT(const orc_rich_auxvar *up, const orc_rich_auxvar *dn, const orc_conn *conn,
+                          int internal_conn, int cond_type, double *flux, double *dflux_dT_up, double *dflux_dT_dn);
+
 /* ---- PETSc-restated nonlinear / linear solver pieces (snes.c) ---------------- */
 typedef struct {
   double atol, rtol, stol, divtol;

@@ -270,3 +270,82 @@ class OracleThermal:
         if rc:
             raise ValueError("get_aux rc=%d" % rc)
         return out
+
+
+class OracleTH:
+    """Same call surface as mpp_b200.soe.TH."""
+
+    def __init__(self, ncol, nlev, per_column=True, nthreads=1, **kw):
+        self.L = lib()
+        self.ncol, self.nlev, self.ncells = ncol, nlev, ncol * nlev
+        self.h = C.c_void_p(self.L.orc_th_create(ncol, nlev))
+        self.L.orc_th_set_mode(self.h, int(per_column), int(nthreads))
+
+    def __del__(self):
+        try:
+            self.L.orc_th_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_mesh(self, orientation, dz, area, col_active=None):
+        dz, area = table(dz, self.ncol, self.nlev), f64(area)
+        return self.L.orc_th_set_mesh(self.h, int(orientation), dp(dz), dp(area), None)
+
+    def add_condition(self, ieqn, ss_or_bc, cond_type, region):
+        return self.L.orc_th_add_condition(self.h, int(ieqn), int(ss_or_bc), int(cond_type), int(region))
+
+    def set_soils(self, watsat, hksat, bsw, sucsat, residual_sat, csol, tkdry, satfunc_type="van_genuchten",
+                  density_type=2, int_energy_enthalpy_type=1):
+        a = [table(x, self.ncol, self.nlev) for x in (watsat, hksat, bsw, sucsat, residual_sat, csol, tkdry)]
+        rc = self.L.orc_th_set_soils(self.h, *[dp(x) for x in a], SATFUNC_NAMES[satfunc_type], int(density_type), int(int_energy_enthalpy_type))
+        if rc:
+            raise ValueError("set_soils rc=%d" % rc)
+
+    def set_tolerances(self, atol=1e-50, rtol=1e-8, stol=1e-10, max_it=50, max_funcs=10000):
+        self.L.orc_th_set_tolerances(self.h, C.c_double(atol), C.c_double(rtol), C.c_double(stol), int(max_it), int(max_funcs))
+
+    def restart(self, press, temp):
+        press, temp = f64(press), f64(temp)
+        assert press.size == self.ncells and temp.size == self.ncells
+        self.L.orc_th_restart(self.h, dp(press), dp(temp))
+
+    def set_data(self, auxvar_type, var_type, cond_id, data, ieqn=1):
+        data = f64(data)
+        if int(auxvar_type) == 702 and int(var_type) == 604:      # AUXVAR_BC, VAR_PRESSURE: boundary aux-var pressure of the energy equation
+            rc = self.L.orc_th_set_bc_pressure(self.h, int(ieqn), int(cond_id), dp(data), int(data.size))
+        else:
+            rc = self.L.orc_th_set_data(self.h, int(ieqn), int(auxvar_type), int(var_type), int(cond_id), dp(data), int(data.size))
+        if rc:
+            raise ValueError("th set_data rc=%d" % rc)
+
+    def get_data(self, auxvar_type, var_type, cond_id, n=None, ieqn=1):
+        out = np.empty(self.ncells)
+        rc = self.L.orc_th_get_data(self.h, int(var_type), dp(out), int(out.size))
+        if rc:
+            raise ValueError("th get_data rc=%d" % rc)
+        return out
+
+    def pre_step_dt(self):
+        pass
+
+    def post_step_dt(self):
+        pass
+
+    def step_dt(self, dt, nstep=1):
+        conv, reason = C.c_int(), C.c_int()
+        self.L.orc_th_step_dt(self.h, C.c_double(dt), int(nstep), C.byref(conv), C.byref(reason))
+        return bool(conv.value), reason.value
+
+    def stats(self):
+        its, rs, cuts, nf = (np.zeros(self.ncol, dtype=np.int32) for _ in range(4))
+        self.L.orc_th_get_stats(self.h, ip(its), ip(rs), ip(cuts), ip(nf))
+        return {"newton_its": its, "reasons": rs, "dt_cuts": cuts, "nfuncs": nf}
+
+    def eval(self, dt, x_prev, x):
+        """x, x_prev interleaved (P,T) per cell; returns f (2N) and the 2x2 block bands ja, jb, jc (4N each)."""
+        x_prev, x = f64(x_prev), f64(x)
+        n = self.ncells
+        f = np.zeros(2 * n)
+        ja, jb, jc = (np.zeros(4 * n) for _ in range(3))
+        self.L.orc_th_eval(self.h, C.c_double(dt), dp(x_prev), dp(x), dp(f), dp(ja), dp(jb), dp(jc))
+        return f, ja, jb, jc

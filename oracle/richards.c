@@ -140,3 +140,58 @@ void orc_richards_flux(const orc_rich_auxvar *up, const orc_rich_auxvar *dn, con
     *flux = -f; *dflux_dP_up = -df_dn; *dflux_dP_dn = -df_up;
   }
 }
+
+/* RichardsMod.F90:343-648 RichardsFluxDerivativeWrtTemperature (non-swapped order only: every caller on the
+ * column hot path passes swap_order = .false.).  NB the reference flips the sign at the end (:640-641), so unlike
+ * orc_richards_flux these are the TRUE derivatives d(flux)/dT. */
+void orc_richards_flux_dT(const orc_rich_auxvar *aux_var_up, const orc_rich_auxvar *aux_var_dn, const orc_conn *conn,
+                          int internal_conn, int cond_type, double *flux, double *dflux_dT_up, double *dflux_dT_dn)
+{
+  double area = conn->area, dist_up = conn->dist_up, dist_dn = conn->dist_dn;
+  const double *dist_unitvec = conn->unitvec;
+  double Pres_up = aux_var_up->pressure, kr_up = aux_var_up->kr, den_up = aux_var_up->den, dden_dT_up = aux_var_up->dden_dT;
+  double vis_up = aux_var_up->vis, dvis_dT_up = aux_var_up->dvis_dT;
+  double Pres_dn = aux_var_dn->pressure, kr_dn = aux_var_dn->kr, den_dn = aux_var_dn->den, dden_dT_dn = aux_var_dn->dden_dT;
+  double vis_dn = aux_var_dn->vis, dvis_dT_dn = aux_var_dn->dvis_dT;
+  double perm_up, perm_dn, upweight, Dq, udist_dot_ugrav, dist_gravity, den_ave, gravityterm, dphi, ukvr, v_darcy, q;
+  double dden_ave_dT_up, dden_ave_dT_dn, dgravityterm_dden_up, dgravityterm_dden_dn, dphi_dT_up, dphi_dT_dn;
+  double dukvr_dT_up, dukvr_dT_dn, dq_dT_up, dq_dT_dn;
+  int seepage_bc_update = 0;
+
+  perm_up = fabs(dist_unitvec[0]) * aux_var_up->perm[0] + fabs(dist_unitvec[1]) * aux_var_up->perm[1] + fabs(dist_unitvec[2]) * aux_var_up->perm[2];
+  perm_dn = fabs(dist_unitvec[0]) * aux_var_dn->perm[0] + fabs(dist_unitvec[1]) * aux_var_dn->perm[1] + fabs(dist_unitvec[2]) * aux_var_dn->perm[2];
+  if (internal_conn || cond_type == COND_DIRICHLET_FRM_OTR_GOVEQ) {
+    upweight = dist_up / (dist_up + dist_dn);
+    Dq       = (perm_up * perm_dn) / (dist_up * perm_dn + dist_dn * perm_up);
+  } else {
+    upweight = 0.0;
+    Dq       = perm_dn / (dist_up + dist_dn);
+  }
+  udist_dot_ugrav = dist_unitvec[0] * 0.0 + dist_unitvec[1] * 0.0 + dist_unitvec[2] * (-ORC_GRAVITY_CONSTANT);
+  dist_gravity = (dist_up + dist_dn) * udist_dot_ugrav;
+  den_ave      = upweight * den_up + (1.0 - upweight) * den_dn;
+  gravityterm  = (upweight * den_up + (1.0 - upweight) * den_dn) * ORC_FMWH2O * dist_gravity;
+  dphi         = Pres_up - Pres_dn + gravityterm;
+  if (!internal_conn && cond_type == COND_SEEPAGE_BC && dphi > 0.0 && Pres_up <= ORC_PRESSURE_REF) seepage_bc_update = 1;
+  if (seepage_bc_update) dphi = 0.0;
+  if (dphi >= 0.0) ukvr = kr_up / vis_up; else ukvr = kr_dn / vis_dn;
+  if (!internal_conn && cond_type == COND_MASS_FLUX) v_darcy = 0.0; else v_darcy = -Dq * ukvr * dphi;
+  q = v_darcy * area;
+  *flux = q * den_ave;
+
+  dden_ave_dT_up       = upweight * dden_dT_up;
+  dden_ave_dT_dn       = (1.0 - upweight) * dden_dT_dn;
+  dgravityterm_dden_up = upweight * dist_gravity * ORC_FMWH2O;
+  dgravityterm_dden_dn = (1.0 - upweight) * dist_gravity * ORC_FMWH2O;
+  dphi_dT_up           = dgravityterm_dden_up * dden_dT_up;
+  dphi_dT_dn           = dgravityterm_dden_dn * dden_dT_dn;
+  if (seepage_bc_update) dphi_dT_dn = 0.0;
+  if (dphi >= 0) { dukvr_dT_up = -kr_up / (vis_up * vis_up) * dvis_dT_up; dukvr_dT_dn = 0.0; }
+  else           { dukvr_dT_up = 0.0; dukvr_dT_dn = -kr_dn / (vis_dn * vis_dn) * dvis_dT_dn; }
+  dq_dT_up = Dq * (dukvr_dT_up * dphi + ukvr * dphi_dT_up) * area;
+  dq_dT_dn = Dq * (dukvr_dT_dn * dphi + ukvr * dphi_dT_dn) * area;
+  if (!internal_conn && cond_type == COND_MASS_FLUX) { *dflux_dT_up = 0.0; *dflux_dT_dn = 0.0; }
+  else { *dflux_dT_up = (dq_dT_up * den_ave - q * dden_ave_dT_up); *dflux_dT_dn = (dq_dT_dn * den_ave - q * dden_ave_dT_dn); }
+  *dflux_dT_up = -(*dflux_dT_up);
+  *dflux_dT_dn = -(*dflux_dT_dn);
+}

@@ -253,3 +253,34 @@ def elm_thermal_step(p, ids, d, T, dt=1800.0, nstep=1):
     p.pre_step_dt()
     conv, _ = p.step_dt(dt, nstep)
     return conv, p.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# TH mass_and_heat -- src/driver/standalone/thermal-e/mass_and_heat_model_problem.F90
+#   baseline regression_tests/th/mass_and_heat.regression.baseline
+# ---------------------------------------------------------------------------------------------------
+def build_mass_and_heat(cls, nx=100, **kw):
+    p = cls(1, nx, **kw)
+    dx = 1.0 / nx
+    p.set_mesh(K.MESH_HORIZONTAL, np.full((1, nx), dx), np.array([1.0]))                  # CONN_IN_X_DIR, area = dy*dz = 1
+    b0 = p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS)                 # cell 1, unit vector (+1,0,0)  :289-310
+    b1 = p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS)              # cell nx, unit vector (-1,0,0) :312-327
+    porosity, lam, alpha, perm = 0.368, 0.5, 3.4257e-4, 8.3913e-12
+    hksat = perm / 0.001002 * (1000.0 * K.GRAV) / 0.001
+    sucsat = 1.0 / (alpha * K.GRAVITY_CONSTANT)
+    full = lambda v: np.full((1, nx), v)
+    p.set_soils(full(porosity), full(hksat), full(1.0 / lam), full(sucsat), full(0.2772), full(837.0), full(0.25),
+                "van_genuchten", K.DENSITY_IFC67, K.INT_ENERGY_ENTHALPY_IFC67)             # :458-472
+    p.restart(np.full(nx, 91325.0), np.full(nx, 283.15))                                   # :529-531
+    return p, b0, b1
+
+
+def run_mass_and_heat(p, b0, b1, dt=3600.0):
+    p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, b0, np.array([303.15]), ieqn=2)         # :586-597
+    p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, b1, np.array([293.15]), ieqn=2)
+    p.set_data(K.AUXVAR_BC, K.VAR_PRESSURE, b0, np.array([91325.0]), ieqn=2)               # :616-621 (pokes aux_vars_bc%pressure)
+    p.set_data(K.AUXVAR_BC, K.VAR_PRESSURE, b1, np.array([91325.0]), ieqn=2)
+    conv, reason = p.step_dt(dt, 1)
+    P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, -1, ieqn=1)
+    T = p.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, -1, ieqn=2)
+    return conv, reason, P, T
