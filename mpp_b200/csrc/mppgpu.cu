@@ -111,6 +111,8 @@ static int th_eval(mppgpu_soe *h, THState *t, double dt, const double *x_prev, c
 static int th_set_soils(mppgpu_soe *h, THState *t, const double *watsat, const double *hksat, const double *bsw, const double *sucsat,
                         const double *residual_sat, const double *csol, const double *tkdry, int satfunc_type, int density_type, int iee_type);
 
+static int vsfm_fill_args(mppgpu_soe *h, VsfmArgs &A, double dt);
+
 static void default_snes(SnesOpts &so)
 {
   so.atol = 1.e-50; so.rtol = 1.e-8; so.stol = 1.e-10; so.divtol = 1.e4;      // MultiPhysicsProbBaseType.F90:1110-1114 + PETSc defaults
@@ -151,6 +153,32 @@ __global__ void convert_soils_kernel(int satfunc_name, const double *watsat, con
   if (vgn) vgn[i] = sp.n;
   if (pu) { pu[i] = sp.pu; ps[i] = sp.ps; b2[i] = sp.b2; b3[i] = sp.b3; }
   if (bad) atomicExch(bad_flag, 1);
+}
+
+// Aux vars of the restart state (VSFMMPPRestart then the first GetDataForCLM of the ELM driver, MPPVSFMALM_Driver.F90:556-601):
+// fills the SoE mailbox (pressure, liq_sat, mass, smp) and the per-column mass that the next StepDT's balance starts from.
+__global__ void vsfm_restart_mailbox_kernel(int satfunc, VsfmArgs A)
+{
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= A.ncol) return;
+  if (A.active && !A.active[col]) return;
+  const double area = A.area[col];
+  double msum = 0.0;
+  for (int j = 0; j < A.nlev; ++j) {
+    const long long cell = (long long)col * A.nlev + j;
+    SatParams sp; sp.sat_res = A.sat_res[cell]; sp.alpha = A.alpha[cell]; sp.m = A.lam[cell]; sp.n = A.vgn ? A.vgn[cell] : 0.0;
+    sp.pu = sp.ps = sp.b2 = sp.b3 = 0.0;
+    if (A.pu) { sp.pu = A.pu[cell]; sp.ps = A.ps[cell]; sp.b2 = A.b2[cell]; sp.b3 = A.b3[cell]; }
+    const double X = A.x_in[cell];
+    SatState st; double den, dden;
+    sat_values_rt(satfunc, sp, X, A.frac_liq[cell], st);
+    density_fixedT(A.dtab, X, den, dden);
+    const double mass = A.por[cell] * den * FMWH2O * st.sat * (area * A.dz[cell]);
+    A.liq_sat[cell] = st.sat; A.pressure[cell] = X; A.mass[cell] = mass;
+    A.smp[cell] = (X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
+    msum += mass;
+  }
+  A.col_mass[col] = msum;
 }
 
 constexpr int REDUCE_BLOCKS = 148;
@@ -400,8 +428,17 @@ extern "C" int mppgpu_restart(mppgpu_handle h, const double *x, int n)
     if ((size_t)n != h->ncells) return fail("VSFMMPPRestart: size(data_1d) /= ncells_local (%d vs %zu)", n, h->ncells);
     // soln, soln_prev and soln_prev_clm all take the restart vector (MultiPhysicsProbVSFM.F90:675-686)
     CK(cudaMemcpyAsync(h->xA.p, x, h->ncells * 8, cudaMemcpyHostToDevice, h->stream));
-    CK(cudaStreamSynchronize(h->stream));
     h->x_committed = h->xA.p; h->x_current = h->xA.p;
+    if (h->mesh_set && h->soils_set) {
+      VsfmArgs A;
+      vsfm_fill_args(h, A, 1.0);
+      A.x_in = h->xA.p;
+      const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
+      vsfm_restart_mailbox_kernel<<<nblk(h->ncol, 128), 128, 0, h->stream>>>(sf, A);
+      CK(cudaGetLastError());
+      h->launches += 1;
+    }
+    CK(cudaStreamSynchronize(h->stream));
     return 0;
   }
   if (h->thermal) {

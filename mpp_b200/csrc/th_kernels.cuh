@@ -37,7 +37,11 @@ struct THArgs {
   double *block_partials;
   double dt;
   SnesOpts so;
+  // kernel unit-test probe (mppgpu_eval): accumulation at x_in, residual + Jacobian blocks at eval_x, no time step
+  const double *eval_x; double *eval_f, *eval_ja, *eval_jb, *eval_jc;
 };
+
+constexpr int PH_EVAL = 6, PH_EVAL_J = 7;
 
 struct THCell {      // aux vars of one cell at one state (both governing equations)
   double sat, kr, dsat, dkr;                      // identical for the two equations (same P, frac_liq_sat = 1)
@@ -171,7 +175,7 @@ th_step_generic_kernel(const THArgs A)
   double f2 = 0.0, initslope = -1.0, lambda = 1.0, lambdaprev = 1.0, gprev = 0.0;
 
   while (phase != PH_DONE) {
-    if (phase == PH_NEWTON) {
+    if (phase == PH_NEWTON || phase == PH_EVAL_J) {
       for (int j = lane; j < nlev; j += 32) for (int k = 0; k < 4; ++k) { v.ja[4 * j + k] = 0.0; v.jb[4 * j + k] = 0.0; v.jc[4 * j + k] = 0.0; }
       __syncwarp();
       // connection contributions, staged per connection in cp (8 values: as "up" row) ... computed twice (once per side) to avoid races
@@ -243,6 +247,12 @@ th_step_generic_kernel(const THArgs A)
         v.jb[4 * j + 0] = b00; v.jb[4 * j + 1] = b01; v.jb[4 * j + 2] = b10; v.jb[4 * j + 3] = b11;
       }
       __syncwarp();
+      if (phase == PH_EVAL_J) {
+        for (int j = lane; j < nlev; j += 32) for (int k = 0; k < 4; ++k) {
+          A.eval_ja[4 * (c0 + j) + k] = v.ja[4 * j + k]; A.eval_jb[4 * (c0 + j) + k] = v.jb[4 * j + k]; A.eval_jc[4 * (c0 + j) + k] = v.jc[4 * j + k];
+        }
+        break;
+      }
       if (lane == 0) {       // block Thomas: J Y = F
         auto inv2 = [](const double *m, double *r) { const double det = m[0] * m[3] - m[1] * m[2]; r[0] = m[3] / det; r[1] = -m[1] / det; r[2] = -m[2] / det; r[3] = m[0] / det; };
         auto mul22 = [](const double *x, const double *y, double *r) { r[0] = x[0] * y[0] + x[1] * y[2]; r[1] = x[0] * y[1] + x[1] * y[3]; r[2] = x[2] * y[0] + x[3] * y[2]; r[3] = x[2] * y[1] + x[3] * y[3]; };
@@ -371,7 +381,16 @@ th_step_generic_kernel(const THArgs A)
     const bool g_bad = !(g2 == g2) || (g2 > 1.7e308);
     const bool out_of_funcs = (nfuncs >= so.max_funcs && so.max_funcs >= 0);
     auto new_trial = [&]() { for (int j = lane; j < nlev; j += 32) { v.Wm[j] = v.P[j] - lambda * v.Ym[j]; v.We[j] = v.T[j] - lambda * v.Ye[j]; } };
-    if (phase == PH_INIT) {
+    if (A.eval_x && phase == PH_INIT) {
+      for (int j = lane; j < nlev; j += 32) { v.Wm[j] = A.eval_x[2 * (c0 + j)]; v.We[j] = A.eval_x[2 * (c0 + j) + 1]; }
+      phase = PH_EVAL; __syncwarp(); continue;
+    } else if (phase == PH_EVAL) {
+      for (int j = lane; j < nlev; j += 32) {
+        v.P[j] = v.Wm[j]; v.T[j] = v.We[j]; v.Fm[j] = v.Gm[j]; v.Fe[j] = v.Ge[j];
+        A.eval_f[2 * (c0 + j)] = v.Gm[j]; A.eval_f[2 * (c0 + j) + 1] = v.Ge[j];
+      }
+      phase = PH_EVAL_J; __syncwarp(); continue;
+    } else if (phase == PH_INIT) {
       take = true;
     } else if (phase == PH_LS_FULL) {
       if (g_bad) {
@@ -430,7 +449,7 @@ th_step_generic_kernel(const THArgs A)
     __syncwarp();
   }
 
-  if (col_ok) {
+  if (col_ok && !A.eval_x) {
     for (int j = lane; j < nlev; j += 32) {
       A.x_out[2 * (c0 + j)] = v.P[j]; A.x_out[2 * (c0 + j) + 1] = v.T[j];
       if (converged) {
@@ -444,7 +463,7 @@ th_step_generic_kernel(const THArgs A)
       for (int k = 0; k < 9; ++k) bp[k] = 0.0;
       bp[5] = (double)tot_its; bp[6] = converged ? 0.0 : 1.0; bp[7] = (double)cuts; bp[8] = (double)last_reason;
     }
-  } else if (lane == 0) {
+  } else if (lane == 0 && !A.eval_x) {
     double *bp = A.block_partials + (size_t)blockIdx.x * 9;
     for (int k = 0; k < 8; ++k) bp[k] = 0.0;
     bp[8] = 2147483647.0;

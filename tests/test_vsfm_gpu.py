@@ -154,6 +154,44 @@ def test_dt_cut_path_matches_oracle(mpp, oracle):
     assert relmax(Pg[ok], Po[ok]) < 1e-8          # sub-stepped answers: both sides re-converge each sub-step to rtol
 
 
+def test_hard_columns_of_the_benchmark_batch_match_oracle(mpp, oracle):
+    """tests/golden/hard_columns.json: the columns of bench.py's 4 Mi-column batch that cut dt (up to 10 halvings, 2117
+    Newton iterations) or fail outright (> 20 cuts) under the reference's algorithm and default tolerances.  The CUDA
+    path must cut, fail and converge exactly where the oracle does."""
+    import json, os
+    import bench
+    cols = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hard_columns.json")))["columns"]
+    parts = []
+    for c in cols:                                   # each column comes from its own seeded 65536-column chunk
+        k = c // bench.CHUNK
+        dk = PB.elm_vsfm_inputs(bench.CHUNK, 15, seed=PB.SEED + k)
+        i = c - k * bench.CHUNK
+        parts.append({key: (dk[key][i:i + 1] if key in ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "area", "infil", "dew", "snow", "sublim")
+                            else dk[key].reshape(bench.CHUNK, 15)[i:i + 1].reshape(-1))
+                      for key in ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "area", "infil", "dew", "snow", "sublim", "press_ic", "et", "drain", "frac_liq")})
+    d = {key: np.concatenate([q[key] for q in parts], axis=0) for key in parts[0]}
+    d.update(ncol=len(cols), nlev=15, satfunc="van_genuchten")
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
+    seen_cut = seen_fail = False
+    for step in range(4):
+        conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, step + 1)
+        convo, reasono, outo = PB.elm_vsfm_step(o, oids, d, 1800.0, step + 1)
+        sg, so_ = p.stats(), o.stats()
+        assert conv == convo and reason == reasono
+        assert np.array_equal(sg["dt_cuts"], so_["dt_cuts"]) and np.array_equal(sg["reasons"], so_["reasons"])
+        nocut = so_["dt_cuts"] == 0
+        assert np.array_equal(sg["newton_its"][nocut], so_["newton_its"][nocut])
+        # over hundreds of sub-steps one rtol test may sit on a rounding edge (seen: 176 vs 177 iterations over 128 sub-steps)
+        assert np.all(np.abs(sg["newton_its"] - so_["newton_its"]) <= np.maximum(1, so_["newton_its"] // 50))
+        seen_cut |= bool(sg["dt_cuts"].max() >= 2); seen_fail |= bool((sg["reasons"] < 0).any())
+        xg = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1)
+        assert relmax(xg, outo["pressure"]) < 1e-9      # sub-stepped columns re-converge every sub-step to rtol
+        ok = so_["dt_cuts"] == 0
+        assert relmax(out["pressure"].reshape(-1, 15)[ok], outo["pressure"].reshape(-1, 15)[ok]) < RTOL
+    assert seen_cut and seen_fail, "fixture no longer exercises the dt-cut / failure paths"
+
+
 def test_pre_post_step_dt_rollback(mpp):
     """PreStepDT restores soln from soln_prev_clm (retry loop of MPPVSFMALM_Driver.F90:628-923)."""
     d = PB.elm_vsfm_inputs(128, 15)
