@@ -17,6 +17,7 @@ void hc_sat(int satfunc /*0 VG 1 BC 2 SBC*/, const double *p /*sat_res,alpha,m,n
   double ds, dk; sat_derivs_rt(satfunc, sp, s, frac_liq, ds, dk);
   out[0] = s.sat; out[1] = ds; out[2] = s.kr; out[3] = dk;
 }
+void hc_log_exp(int n, const double *x, double *lg, double *ex) { for (int i = 0; i < n; ++i) { lg[i] = mpp_log(x[i]); ex[i] = mpp_exp(x[i]); } }
 void hc_density(int itype, double p, double t_K, double *out) { density(itype, p, t_K, out[0], out[1], out[2]); }
 void hc_density_fixedT(int itype, double t_K, double p, double *out) { DensityTable t = make_density_table(itype, t_K); density_fixedT(t, p, out[0], out[1]); }
 void hc_enthalpy_ifc67(double t_C, double p, double *out) { enthalpy_ifc67(t_C, p, out[0], out[1], out[2]); }

@@ -18,6 +18,7 @@
 #include "../../include/mppgpu.h"
 #include "physics.cuh"
 #include "vsfm_kernels.cuh"
+#include "vsfm_kernels2.cuh"
 #include "vsfm_generic_kernel.cuh"
 #include "thermal_kernels.cuh"
 #include "th_kernels.cuh"
@@ -578,6 +579,17 @@ static void launch_vsfm_fast(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
   else                       vsfm_step_kernel<GROUP, SATFUNC_SBC><<<nblocks, 128, 0, h->stream>>>(A);
 }
 
+template <int LPC>
+static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
+{
+  const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
+  const bool bc = A.nbc > 0;
+#define MPP_L2(SF) do { if (bc) vsfm_step2_kernel<LPC, SF, true><<<nblocks, 128, 0, h->stream>>>(A); \
+                        else    vsfm_step2_kernel<LPC, SF, false><<<nblocks, 128, 0, h->stream>>>(A); } while (0)
+  if (sf == SATFUNC_VG) MPP_L2(SATFUNC_VG); else if (sf == SATFUNC_BC) MPP_L2(SATFUNC_BC); else MPP_L2(SATFUNC_SBC);
+#undef MPP_L2
+}
+
 static int vsfm_step(mppgpu_soe *h, double dt)
 {
   if (!h->mesh_set || !h->soils_set) return fail("mppgpu_step_dt: mesh and soils must be set first");
@@ -590,17 +602,18 @@ static int vsfm_step(mppgpu_soe *h, double dt)
   A.x_out = (h->x_current == h->x_committed) ? spare : h->x_current;
   int nblocks;
   const int nlev = h->nlev;
+  static const bool old_kernel = (getenv("MPPGPU_VSFM_V2") != nullptr);     // A/B switch for kernel development only
   if (nlev <= 32) {
     const int group = (nlev <= 16) ? 16 : 32;
-    nblocks = nblk((long long)h->ncol * group, 128);
+    nblocks = nblk((long long)h->ncol * (old_kernel ? group : group / 2), 128);
   } else {
     nblocks = nblk((long long)h->ncol, VSFM_GENERIC_WARPS);
   }
   if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
   A.block_partials = h->block_partials.p;
   CK(cudaEventRecord(h->ev0, h->stream));
-  if (nlev <= 16)      launch_vsfm_fast<16>(h, A, nblocks);
-  else if (nlev <= 32) launch_vsfm_fast<32>(h, A, nblocks);
+  if (nlev <= 16)      { if (old_kernel) launch_vsfm_fast<16>(h, A, nblocks); else launch_vsfm2<8>(h, A, nblocks); }
+  else if (nlev <= 32) { if (old_kernel) launch_vsfm_fast<32>(h, A, nblocks); else launch_vsfm2<16>(h, A, nblocks); }
   else {
     const size_t smem = vsfm_generic_smem_bytes(nlev);
     if (smem > 200 * 1024) return fail("mppgpu_step_dt: nlev = %d exceeds the generic kernel's shared-memory budget", nlev);

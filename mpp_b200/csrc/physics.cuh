@@ -9,13 +9,14 @@
 //   enthalpy            EOSWaterMod.F90:347-565 (IFC-67), 629-707
 //
 // B200 design notes.  The path is fp64-issue bound, not HBM bound: the reference's
-// 5 pow() per van Genuchten cell are restated as 3 log + 3 exp for the values (shared between
+// 5 pow() per van Genuchten cell are restated as 2 log + 2 exp + 1 reciprocal for the values (shared between
 // saturation and permeability, which the reference evaluates twice) and the derivative terms are
 // split off (`*_deriv`) so that line-search trial points, which never need a Jacobian, skip them.
 // Everything is __host__ __device__ so the CPU test-suite can check these exact functions against
 // the oracle without a GPU (tests/test_physics_host.py).
 #pragma once
 #include <math.h>
+#include <string.h>
 
 #ifdef __CUDACC__
 #define MPP_HD __host__ __device__ __forceinline__
@@ -24,6 +25,160 @@
 #endif
 
 namespace mpp {
+
+// ------------------------------------------------------------------------------------------------
+// Lean fp64 log / exp / reciprocal for the saturation curves.
+//
+// Why not the CUDA math library here: its log()/exp() materialise every polynomial coefficient with two IMAD.MOV
+// (22 % of all executed instructions of the first kernels were constant moves, profiles/r1_vsfm_v4.md), branch on
+// denormals / NaN / Inf (BSSY/BSYNC pairs that serialise the two cells a lane owns) and take ~70 instructions per
+// call.  The arguments here are always positive, finite and far from the denormal range, so:
+//   * coefficients live in __constant__ memory and enter DFMA as constant-bank operands (no move instructions);
+//   * no special-case branches; the polynomials are split even/odd (Estrin) so two chains overlap;
+//   * the reciprocal is MUFU.RCP64H + two Newton steps.
+// Accuracy (tests/test_physics_host.py, checked against libm over the ranges the soil curves produce): < 2 ulp.
+// Coefficients were derived for this file by Chebyshev interpolation in 50-digit arithmetic (mpmath):
+//   exp(r) = 1 + r + r^2 q(r), q of degree 9 on |r| <= ln2/2        (approximation error 0.15 ulp)
+//   log(1+f) = f - f^2/2 + s (f^2/2 + R(s^2)), s = f/(2+f), R of degree 7 in s^2, 1+f in [sqrt(1/2), sqrt(2)]  (0.05 ulp)
+// ------------------------------------------------------------------------------------------------
+#define MPP_CMATH_TABLE { \
+  /* 0..6  log: Lg1..Lg7 */ \
+  0x1.5555555555558p-1, 0x1.99999999952b6p-2, 0x1.2492492df62cfp-2, 0x1.c71c62df4373bp-3, 0x1.7462b6717d448p-3, \
+  0x1.39fe256b357ffp-3, 0x1.2b5b2383c1004p-3, \
+  /* 7,8   ln2 split for log (hi has 21 trailing zero bits) */ 0x1.62e42fee00000p-1, 0x1.a39ef35793c76p-33, \
+  /* 9..18 exp: c2..c11 */ \
+  0x1.0000000000001p-1, 0x1.5555555555556p-3, 0x1.5555555553d63p-5, 0x1.11111111109b3p-7, 0x1.6c16c1788bd90p-10, \
+  0x1.a01a01a7c41d5p-13, 0x1.a019b90d2ae7ap-16, 0x1.71de0dae63bb3p-19, 0x1.289185613a3d6p-22, 0x1.af38a9b0ec855p-26, \
+  /* 19..21 1/ln2, ln2 split for exp (hi has 11 trailing zero bits) */ 1.4426950408889634, 0.6931471805598903, 5.497923018708371e-14 }
+#ifdef __CUDACC__
+static __constant__ double mpp_cmath_dev[22] = MPP_CMATH_TABLE;
+#endif
+static const double mpp_cmath_host[22] = MPP_CMATH_TABLE;
+#ifdef __CUDA_ARCH__
+#define MPPC(i) mpp_cmath_dev[i]
+#else
+#define MPPC(i) mpp_cmath_host[i]
+#endif
+
+// Pairs.  A lane of the fast VSFM kernel owns two cells; ptxas schedules two calls of a scalar function one after the
+// other (profiles/r1_vsfm_v6.md: every DFMA of the log/exp chains waited its full ~9-cycle latency), so the curve math
+// is written once, generically, and instantiated for `double` and for the pair type `d2`, whose element-wise
+// operators put the two independent chains next to each other in program order.
+struct d2 { double a, b; };
+MPP_HD d2 operator+(d2 x, d2 y) { return d2{x.a + y.a, x.b + y.b}; }
+MPP_HD d2 operator-(d2 x, d2 y) { return d2{x.a - y.a, x.b - y.b}; }
+MPP_HD d2 operator*(d2 x, d2 y) { return d2{x.a * y.a, x.b * y.b}; }
+MPP_HD d2 operator-(d2 x) { return d2{-x.a, -x.b}; }
+MPP_HD double vfma(double x, double y, double z) { return fma(x, y, z); }
+MPP_HD d2 vfma(d2 x, d2 y, d2 z) { return d2{fma(x.a, y.a, z.a), fma(x.b, y.b, z.b)}; }
+template <class T> MPP_HD T vbc(double c);
+template <> MPP_HD double vbc<double>(double c) { return c; }
+template <> MPP_HD d2 vbc<d2>(double c) { return d2{c, c}; }
+MPP_HD double vsel(bool pa, bool, double x, double y) { return pa ? x : y; }            // element-wise p ? x : y
+MPP_HD d2 vsel(bool pa, bool pb, d2 x, d2 y) { return d2{pa ? x.a : y.a, pb ? x.b : y.b}; }
+
+MPP_HD void mpp_split(double x, int &hi, unsigned &lo)
+{
+#ifdef __CUDA_ARCH__
+  hi = __double2hiint(x); lo = (unsigned)__double2loint(x);
+#else
+  unsigned long long u; memcpy(&u, &x, 8); hi = (int)(u >> 32); lo = (unsigned)u;
+#endif
+}
+MPP_HD double mpp_join(int hi, unsigned lo)
+{
+#ifdef __CUDA_ARCH__
+  return __hiloint2double(hi, (int)lo);
+#else
+  unsigned long long u = ((unsigned long long)(unsigned)hi << 32) | lo; double x; memcpy(&x, &u, 8); return x;
+#endif
+}
+
+// reciprocal seed (MUFU.RCP64H, ~2^-23) refined by two Newton steps to <= 1 ulp
+MPP_HD double rcp_seed(double x)
+{
+#ifdef __CUDA_ARCH__
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  return r;
+#else
+  return 1.0 / x;
+#endif
+}
+MPP_HD d2 rcp_seed(d2 x) { return d2{rcp_seed(x.a), rcp_seed(x.b)}; }
+template <class T> MPP_HD T rcp(T x)
+{
+  const T one = vbc<T>(1.0);
+  T r = rcp_seed(x);
+  T e = vfma(-x, r, one); r = vfma(r, e, r);                    // 2^-46
+  e = vfma(-x, r, one);   r = vfma(r, e, r);                    // <= 1 ulp
+  return r;
+}
+
+// log: x = 2^k (1 + f), 1 + f in [sqrt(1/2), sqrt(2))
+MPP_HD void log_reduce(double x, double &f, double &dk)
+{
+  int hi; unsigned lo;
+  mpp_split(x, hi, lo);
+  int k = (hi >> 20) - 1023;
+  hi &= 0x000fffff;
+  const int i = (hi + 0x95f64) & 0x100000;                    // mantissa >= sqrt(2): halve it, bump the exponent
+  hi |= (i ^ 0x3ff00000);
+  k += (i >> 20);
+  f = mpp_join(hi, lo) - 1.0;
+  dk = (double)k;
+}
+MPP_HD void log_reduce(d2 x, d2 &f, d2 &dk) { log_reduce(x.a, f.a, dk.a); log_reduce(x.b, f.b, dk.b); }
+
+// natural logarithm of positive, finite, normal doubles
+template <class T> MPP_HD T mpp_log(T x)
+{
+  T f, dk;
+  log_reduce(x, f, dk);
+  const T s = f * rcp(vbc<T>(2.0) + f);
+  const T z = s * s, w = z * z;
+  const T t1 = w * vfma(w, vfma(w, vbc<T>(MPPC(5)), vbc<T>(MPPC(3))), vbc<T>(MPPC(1)));
+  const T t2 = z * vfma(w, vfma(w, vfma(w, vbc<T>(MPPC(6)), vbc<T>(MPPC(4))), vbc<T>(MPPC(2))), vbc<T>(MPPC(0)));
+  const T R = t2 + t1;
+  const T hfsq = vbc<T>(0.5) * f * f;
+  return dk * vbc<T>(MPPC(7)) - ((hfsq - (s * (hfsq + R) + dk * vbc<T>(MPPC(8)))) - f);
+}
+
+// exp: clamp to [-708, 708] on the high word (one integer compare + selects), and 2^k from the magic-number sum
+MPP_HD double exp_clamp(double x)
+{
+  int xh; unsigned xl;
+  mpp_split(x, xh, xl);
+  if ((xh & 0x7fffffff) >= 0x40862000) x = (xh < 0) ? -708.0 : 708.0;     // |x| >= 708
+  return x;
+}
+MPP_HD d2 exp_clamp(d2 x) { return d2{exp_clamp(x.a), exp_clamp(x.b)}; }
+MPP_HD double exp_scale(double fn)
+{
+  int hi; unsigned lo;
+  mpp_split(fn, hi, lo);                                       // fn = 1.5 * 2^52 + round(x / ln2): the low word holds the integer
+  return mpp_join(((int)lo + 1023) << 20, 0u);
+}
+MPP_HD d2 exp_scale(d2 fn) { return d2{exp_scale(fn.a), exp_scale(fn.b)}; }
+
+// exponential; the argument is clamped to [-708, 708] (results stay normal and finite)
+template <class T> MPP_HD T mpp_exp(T x)
+{
+  x = exp_clamp(x);
+  const T magic = vbc<T>(6755399441055744.0);
+  const T fn = vfma(x, vbc<T>(MPPC(19)), magic);
+  const T kd = fn - magic;
+  T r = vfma(-kd, vbc<T>(MPPC(20)), x);
+  r = vfma(-kd, vbc<T>(MPPC(21)), r);                          // |r| <= ln2 / 2
+  const T r2 = r * r;
+  const T p0 = vfma(r, vbc<T>(MPPC(10)), vbc<T>(MPPC(9))),  p1 = vfma(r, vbc<T>(MPPC(12)), vbc<T>(MPPC(11)));
+  const T p2 = vfma(r, vbc<T>(MPPC(14)), vbc<T>(MPPC(13))), p3 = vfma(r, vbc<T>(MPPC(16)), vbc<T>(MPPC(15)));
+  const T p4 = vfma(r, vbc<T>(MPPC(18)), vbc<T>(MPPC(17)));
+  T q = vfma(r2, p4, p3);
+  q = vfma(r2, q, p2); q = vfma(r2, q, p1); q = vfma(r2, q, p0);
+  const T e = vfma(r2, q, r) + vbc<T>(1.0);
+  return e * exp_scale(fn);
+}
 
 // MultiPhysicsProbConstants.F90:199-202, mpp_varcon.F90:12-28
 constexpr double PRESSURE_REF     = 101325.0;
@@ -55,9 +210,51 @@ struct SatParams {
 // values needed by the residual + what the derivative pass re-uses
 struct SatState {
   double sat, kr;
-  double Se, AA, AAm, L2, pc;   // VG intermediates; for BC/SBC: Se, pc, AA = dSe_dpc
+  double Se, AA, AAm, L2, rx, pc;   // VG intermediates (rx = 1 / (-alpha pc)); for BC/SBC: Se, pc
   int    regime;                 // 0 saturated, 1 unsaturated (VG / full BC), 2 SBC cubic
 };
+
+// van Genuchten - Mualem curves, generic over double / d2 (see the pair types above).
+// Reference: Se = (1 + x^n)^-m, AA = x^n / (1 + x^n), kr = sqrt(Se) (1 - AA^m)^2 with x = -alpha pc for pc < 0,
+// sat = kr = 1 otherwise (5 pow calls, SaturationFunction.F90:776-836).  Here: 2 log + 2 exp + 1 reciprocal, using
+//   sqrt(Se) = (1 + x^n)^(-m/2),  AA^m = x^(n m) Se = x^(n-1) Se = x^n Se / x      (n m = n - 1).
+// Branch-free on purpose: saturated cells evaluate the chain at x = 1 and discard it, so the chains of the cells a lane
+// owns stay in one basic block and overlap.
+template <class T> struct VGState { T sat, kr, Se, pcn, AAm, rS, rx; };
+
+template <class T>
+MPP_HD void vg_values(T sat_res, T alpha, T m, T n, T pc, bool unsat_a, bool unsat_b, VGState<T> &o)
+{
+  const T one = vbc<T>(1.0);
+  const T x   = vsel(unsat_a, unsat_b, -alpha * pc, one);
+  const T L1  = mpp_log(x);
+  const T rx  = rcp(x);
+  const T pcn = mpp_exp(n * L1);                      // x^n
+  const T L2  = mpp_log(one + pcn);
+  const T rS  = mpp_exp(vbc<T>(-0.5) * m * L2);       // sqrt(Se)
+  const T Se  = rS * rS;
+  const T AAm = pcn * Se * rx;                        // AA^m
+  const T BB  = one - AAm;
+  o.sat = vsel(unsat_a, unsat_b, sat_res + (one - sat_res) * Se, one);
+  o.kr  = vsel(unsat_a, unsat_b, rS * BB * BB, one);
+  o.Se = Se; o.pcn = pcn; o.AAm = AAm; o.rS = rS; o.rx = rx;
+}
+
+// dSe/dpc = -m n Se AA / pc with AA = x^n / (1 + x^n)                       (SaturationFunction.F90:790, 829)
+// dkr/dSe = kr / (2 Se) + 2 Se^(1/m - 1/2) AA^(m-1) BB                       (:836-838)
+//         = BB (BB / 2 + 2 AA^m / x^n) / sqrt(Se)      since Se^(1/m) = 1 / (1 + x^n)
+// (same functions, regrouped so that no further exp/pow is needed; derivative round-off only steers the Newton path,
+//  never the converged answer).  1 / pc = -alpha / x and AA^m / x^n = Se / x: two reciprocals, no division.
+template <class T>
+MPP_HD void vg_derivs(T sat_res, T alpha, T m, T n, bool unsat_a, bool unsat_b, const VGState<T> &o, T &dsat_dP, T &dkr_dP)
+{
+  const T one = vbc<T>(1.0), zero = vbc<T>(0.0);
+  const T BB = one - o.AAm;
+  const T dSe_dpc = vsel(unsat_a, unsat_b, (m * n) * o.Se * o.pcn * rcp(one + o.pcn) * (alpha * o.rx), zero);
+  const T dkr_dSe = BB * (vbc<T>(0.5) * BB + vbc<T>(2.0) * o.Se * o.rx) * rcp(o.rS);
+  dsat_dP = (one - sat_res) * dSe_dpc;
+  dkr_dP  = dkr_dSe * dSe_dpc;
+}
 
 template <int SATFUNC>
 MPP_HD void sat_values(const SatParams &sp, double press, double frac_liq, SatState &s)
@@ -65,24 +262,11 @@ MPP_HD void sat_values(const SatParams &sp, double press, double frac_liq, SatSt
   const double pc = press - PRESSURE_REF;
   s.pc = pc;
   if (SATFUNC == SATFUNC_VG) {
-    if (pc < 0.0) {
-      // Reference: Se = (1 + x^n)^-m, AA = x^n / (1 + x^n), kr = sqrt(Se) (1 - AA^m)^2 with x = -alpha pc
-      // (5 pow calls, SaturationFunction.F90:777-836).  Here: 2 log + 3 exp, using AA^m = x^(n m) Se and n m = n - 1.
-      const double L1  = log(-sp.alpha * pc);
-      const double pcn = exp(sp.n * L1);               // x^n
-      const double opn = 1.0 + pcn;
-      const double L2  = log(opn);
-      const double mL2 = sp.m * L2;
-      const double Se  = exp(-mL2);                    // (1 + x^n)^(-m)
-      const double AAm = exp((sp.n - 1.0) * L1 - mL2); // AA^m
-      const double BB  = 1.0 - AAm;
-      const double rS  = sqrt(Se);
-      s.sat = sp.sat_res + (1.0 - sp.sat_res) * Se;
-      s.kr  = rS * BB * BB;
-      s.Se = Se; s.AA = pcn; s.AAm = AAm; s.L2 = rS; s.regime = 1;   // (AA slot carries x^n, L2 slot carries sqrt(Se))
-    } else {
-      s.sat = 1.0; s.kr = 1.0; s.regime = 0;
-    }
+    VGState<double> o;
+    const bool unsat = (pc < 0.0);
+    vg_values<double>(sp.sat_res, sp.alpha, sp.m, sp.n, pc, unsat, unsat, o);
+    s.sat = o.sat; s.kr = o.kr;
+    s.Se = o.Se; s.AA = o.pcn; s.AAm = o.AAm; s.L2 = o.rS; s.rx = o.rx; s.regime = unsat ? 1 : 0;   // (AA slot carries x^n, L2 slot carries sqrt(Se))
   } else if (SATFUNC == SATFUNC_BC) {
     const double pc_alpha = -sp.alpha * pc;
     if (pc_alpha > 1.0) {
@@ -117,19 +301,12 @@ MPP_HD void sat_values(const SatParams &sp, double press, double frac_liq, SatSt
 template <int SATFUNC>
 MPP_HD void sat_derivs(const SatParams &sp, const SatState &s, double frac_liq, double &dsat_dP, double &dkr_dP)
 {
-  if (s.regime == 0) { dsat_dP = 0.0; dkr_dP = 0.0; return; }
   if (SATFUNC == SATFUNC_VG) {
-    // dSe/dpc = -m n Se AA / pc with AA = x^n / (1 + x^n)                       (SaturationFunction.F90:790, 829)
-    // dkr/dSe = kr / (2 Se) + 2 Se^(1/m - 1/2) AA^(m-1) BB                       (:836-838)
-    //         = BB (BB / 2 + 2 AA^m / x^n) / sqrt(Se)      since Se^(1/m) = 1 / (1 + x^n)
-    // (same functions, regrouped so that no further exp/pow is needed; derivative round-off only steers the Newton
-    //  path, never the converged answer)
-    const double pcn = s.AA, rS = s.L2, BB = 1.0 - s.AAm;
-    const double dSe_dpc = -sp.m * sp.n * s.Se * pcn / ((1.0 + pcn) * s.pc);
-    const double dkr_dSe = BB * (0.5 * BB + 2.0 * s.AAm / pcn) / rS;
-    dsat_dP = (1.0 - sp.sat_res) * dSe_dpc;
-    dkr_dP  = dkr_dSe * dSe_dpc;
+    VGState<double> o;
+    o.Se = s.Se; o.pcn = s.AA; o.AAm = s.AAm; o.rS = s.L2; o.rx = s.rx;
+    vg_derivs<double>(sp.sat_res, sp.alpha, sp.m, sp.n, s.regime != 0, s.regime != 0, o, dsat_dP, dkr_dP);
   } else {
+    if (s.regime == 0) { dsat_dP = 0.0; dkr_dP = 0.0; return; }
     double dSe_dpc;
     if (s.regime == 1) dSe_dpc = -sp.m * s.Se / s.pc;
     else { const double dpc = s.pc - sp.ps; dSe_dpc = dpc * (2.0 * sp.b2 + 3.0 * dpc * sp.b3); }
@@ -137,6 +314,38 @@ MPP_HD void sat_derivs(const SatParams &sp, const SatState &s, double frac_liq, 
     dsat_dP = (1.0 - sp.sat_res) * dSe_dpc;
     dkr_dP  = (2.5 + 2.0 / sp.m) * s.kr / s.Se * dSe_dpc;
     (void)frac_liq;
+  }
+}
+
+// two cells at once (the fast VSFM kernel): van Genuchten goes through the pair instantiation, the others call the scalar code twice
+template <int SATFUNC>
+MPP_HD void sat_values_pair(const SatParams &pa, const SatParams &pb, double Pa, double Pb, double fla, double flb, SatState &sa, SatState &sb)
+{
+  if (SATFUNC == SATFUNC_VG) {
+    VGState<d2> o;
+    const d2 pc = d2{Pa - PRESSURE_REF, Pb - PRESSURE_REF};
+    const bool ua = (pc.a < 0.0), ub = (pc.b < 0.0);
+    vg_values<d2>(d2{pa.sat_res, pb.sat_res}, d2{pa.alpha, pb.alpha}, d2{pa.m, pb.m}, d2{pa.n, pb.n}, pc, ua, ub, o);
+    sa.pc = pc.a; sa.sat = o.sat.a; sa.kr = o.kr.a; sa.Se = o.Se.a; sa.AA = o.pcn.a; sa.AAm = o.AAm.a; sa.L2 = o.rS.a; sa.rx = o.rx.a; sa.regime = ua ? 1 : 0;
+    sb.pc = pc.b; sb.sat = o.sat.b; sb.kr = o.kr.b; sb.Se = o.Se.b; sb.AA = o.pcn.b; sb.AAm = o.AAm.b; sb.L2 = o.rS.b; sb.rx = o.rx.b; sb.regime = ub ? 1 : 0;
+  } else {
+    sat_values<SATFUNC>(pa, Pa, fla, sa);
+    sat_values<SATFUNC>(pb, Pb, flb, sb);
+  }
+}
+template <int SATFUNC>
+MPP_HD void sat_derivs_pair(const SatParams &pa, const SatParams &pb, const SatState &sa, const SatState &sb, double fla, double flb,
+                            double &dsat_a, double &dkr_a, double &dsat_b, double &dkr_b)
+{
+  if (SATFUNC == SATFUNC_VG) {
+    VGState<d2> o;
+    o.Se = d2{sa.Se, sb.Se}; o.pcn = d2{sa.AA, sb.AA}; o.AAm = d2{sa.AAm, sb.AAm}; o.rS = d2{sa.L2, sb.L2}; o.rx = d2{sa.rx, sb.rx};
+    d2 ds, dk;
+    vg_derivs<d2>(d2{pa.sat_res, pb.sat_res}, d2{pa.alpha, pb.alpha}, d2{pa.m, pb.m}, d2{pa.n, pb.n}, sa.regime != 0, sb.regime != 0, o, ds, dk);
+    dsat_a = ds.a; dkr_a = dk.a; dsat_b = ds.b; dkr_b = dk.b;
+  } else {
+    sat_derivs<SATFUNC>(pa, sa, fla, dsat_a, dkr_a);
+    sat_derivs<SATFUNC>(pb, sb, flb, dsat_b, dkr_b);
   }
 }
 
@@ -246,8 +455,9 @@ MPP_HD DensityTable make_density_table(int density_type, double t_K)
 }
 MPP_HD void density_fixedT(const DensityTable &t, double p, double &den, double &dden_dp)
 {
-  if (t.type == DENSITY_TGDPB01 && p > 101325.0) { den = t.dent_over_fmw * (1.0 + t.kcoef * (p - 101325.0)); dden_dp = t.dent_over_fmw * t.kcoef; }
-  else { den = t.dent_over_fmw; dden_dp = 0.0; }
+  const bool comp = (t.type == DENSITY_TGDPB01) && (p > 101325.0);          // compressible only above P_ref (EOSWaterMod.F90:151-155)
+  den     = comp ? t.dent_over_fmw * (1.0 + t.kcoef * (p - 101325.0)) : t.dent_over_fmw;
+  dden_dp = comp ? t.dent_over_fmw * t.kcoef : 0.0;
 }
 
 MPP_HD double ipow(double x, int n) { double r = 1.0; for (int i = 0; i < n; ++i) r *= x; return r; }

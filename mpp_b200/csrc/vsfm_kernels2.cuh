@@ -1,0 +1,538 @@
+// vsfm_kernels2.cuh -- fused VSFM (Richards equation) time step, two soil cells per lane.
+//
+// One launch = one sysofeqns%StepDT for every column of the batch (same reference citations as vsfm_kernels.cuh):
+//   SOEBaseStepDT_SNES         src/mpp/soe/SystemOfEquationsBaseType.F90:368-552  (dt cuts, <= 20)
+//   VSFMSOEPreSolve/PostSolve  src/mpp/soe/SystemOfEquationsVSFMType.F90:506-660
+//   VSFMSOEResidual/Jacobian   src/mpp/soe/SystemOfEquationsVSFMType.F90:94-403
+//   Richards residual/Jacobian src/mpp/ge/GoveqnRichardsODEPressureType.F90:1603-2200
+//   RichardsFlux               src/mpp/ge/RichardsMod.F90:118-340
+//   PETSc SNES newtonls + bt line search + SNESConvergedDefault, KSP on a tridiagonal matrix
+//
+// Mapping (DESIGN.md "VSFM kernel").  The path is bound by fp64 issue LATENCY, not by HBM: the first lane-per-cell
+// version ran at 0.45 IPC per scheduler with the fp64 pipe 29 % busy (profiles/r1_vsfm_v2.md) because every lane
+// carried one serial log -> exp -> log -> exp chain and 128 registers allowed only 4 warps per scheduler.  Here LPC
+// (8 or 16) lanes own one column and each lane owns TWO adjacent cells (2l, 2l+1):
+//   * two independent transcendental chains per lane (ILP 2) hide the DFMA latency;
+//   * a warp advances 4 (or 2) columns, so the per-warp control flow, norms and shuffles are amortised over twice
+//     as many cells; the connection between a lane's two cells needs no shuffle at all;
+//   * the tridiagonal Newton system is reduced in-lane to one row per lane (odd-even elimination of the lane's second
+//     cell), solved by parallel cyclic reduction over LPC lanes in normalised form (3 shuffled doubles per side per
+//     stage instead of 4, log2(LPC) stages), then back-substituted in-lane;
+//   * all norms are carried squared (no sqrt in the Newton loop) and are bitwise identical in every lane of a column,
+//     so control flow is uniform per column; converged columns idle until their warp's slowest column is done.
+// HBM traffic is the algorithmic minimum: every input array is read once, every output written once, in the
+// reference's own cell order (icell = c*nlev + j), fully coalesced.
+#pragma once
+#include "vsfm_kernels.cuh"
+
+namespace mpp {
+
+#ifndef VSFM2_MIN_BLOCKS
+#define VSFM2_MIN_BLOCKS 3
+#endif
+
+template <int LPC>
+__device__ __forceinline__ double col_sum(double v)
+{
+#pragma unroll
+  for (int s = LPC / 2; s > 0; s >>= 1) v += __shfl_xor_sync(FULL_MASK, v, s, LPC);
+  return v;
+}
+
+// Parallel cyclic reduction over LPC lanes of a tridiagonal system in normalised form (unit diagonal):
+//   al x[l-1] + x[l] + ga x[l+1] = de.   The couplings that would reach outside the chain are exactly zero at every
+// stage, so whatever an out-of-range shuffle returns (the lane's own finite value) is multiplied by zero.
+template <int LPC>
+__device__ __forceinline__ double pcr_unit_diag(double al, double ga, double de)
+{
+#pragma unroll
+  for (int s = 1; s < LPC; s <<= 1) {
+    const double al_m = __shfl_up_sync(FULL_MASK, al, s, LPC),   ga_m = __shfl_up_sync(FULL_MASK, ga, s, LPC);
+    const double de_m = __shfl_up_sync(FULL_MASK, de, s, LPC);
+    const double al_p = __shfl_down_sync(FULL_MASK, al, s, LPC), ga_p = __shfl_down_sync(FULL_MASK, ga, s, LPC);
+    const double de_p = __shfl_down_sync(FULL_MASK, de, s, LPC);
+    const double r = __drcp_rn(1.0 - al * ga_m - ga * al_p);
+    de = (de - al * de_m - ga * de_p) * r;
+    al = (-al * al_m) * r;
+    ga = (-ga * ga_p) * r;
+  }
+  return de;
+}
+
+// static data and Newton state of one soil cell, all in registers
+template <int SATFUNC>
+struct Cell2 {
+  SatParams sp;
+  double por, vol, frac_liq, src;
+  double upw, Dq, gfac;            // connection this cell -> next cell (MeshType.F90:509-530; RichardsMod.F90:257-259, 279-285)
+  double X, Xprev, F, Y, W, accum_prev;
+  double kr, dkr, sat, dsat;       // aux vars at the accepted iterate X
+  bool valid, has_conn;
+};
+
+template <int SATFUNC>
+__device__ __forceinline__ void cell_load(const VsfmArgs &A, Cell2<SATFUNC> &c, bool valid, long long cell, double area, double &perm, double &dz)
+{
+  c.valid = valid;
+  c.sp.sat_res = 0.0; c.sp.alpha = 1.0; c.sp.m = 0.5; c.sp.n = 2.0; c.sp.pu = c.sp.ps = c.sp.b2 = c.sp.b3 = 0.0;
+  c.por = 0.0; c.frac_liq = 1.0; c.X = PRESSURE_REF; perm = 1.0; dz = 1.0;
+  if (valid) {
+    c.por = A.por[cell]; perm = A.perm[cell]; dz = A.dz[cell];
+    c.sp.sat_res = A.sat_res[cell]; c.sp.alpha = A.alpha[cell]; c.sp.m = A.lam[cell];
+    if (SATFUNC == SATFUNC_VG)  c.sp.n = A.vgn[cell];
+    if (SATFUNC == SATFUNC_SBC) { c.sp.pu = A.pu[cell]; c.sp.ps = A.ps[cell]; c.sp.b2 = A.b2[cell]; c.sp.b3 = A.b3[cell]; }
+    if (SATFUNC != SATFUNC_VG)  c.frac_liq = A.frac_liq[cell];      // only the Brooks-Corey k_r reads it (SaturationFunction.F90:987)
+    c.X = A.x_in[cell];
+  }
+  c.vol = area * dz;                                                // MeshType.F90:427
+  c.Xprev = c.X; c.W = c.X; c.F = 0.0; c.Y = 0.0; c.accum_prev = 0.0; c.src = 0.0;
+  c.kr = 1.0; c.dkr = 0.0; c.sat = 1.0; c.dsat = 0.0;
+}
+
+__device__ __forceinline__ void conn_setup(double perm_up, double dz_up, double perm_dn, double dz_dn, double uz, double &upw, double &Dq, double &gfac)
+{
+  const double dist_up = 0.5 * dz_up, dist_dn = 0.5 * dz_dn;
+  upw  = dist_up / (dist_up + dist_dn);
+  Dq   = (perm_up * perm_dn) / (dist_up * perm_dn + dist_dn * perm_up);
+  gfac = FMWH2O * ((dist_up + dist_dn) * (uz * (-GRAVITY_CONSTANT)));       // FMWH2O * dist_gravity
+}
+
+// RichardsFlux_Internal, residual part (RichardsMod.F90:257-296)
+__device__ __forceinline__ double rich_flux(double P_u, double kr_u, double den_u, double P_d, double kr_d, double den_d,
+                                            double upw, double Dq, double gfac, double area)
+{
+  constexpr double RVIS = 1.0 / VISCOSITY;
+  const double den_ave = upw * den_u + (1.0 - upw) * den_d;
+  const double dphi    = P_u - P_d + den_ave * gfac;
+  const double ukvr    = ((dphi >= 0.0) ? kr_u : kr_d) * RVIS;
+  return ((-Dq * ukvr * dphi) * area) * den_ave;
+}
+
+// RichardsFlux_Internal with compute_deriv (RichardsMod.F90:298-336): Jup = -d flux / dP_up, Jdn = -d flux / dP_dn
+__device__ __forceinline__ void rich_flux_deriv(double P_u, double kr_u, double dkr_u, double den_u, double dden_u,
+                                                double P_d, double kr_d, double dkr_d, double den_d, double dden_d,
+                                                double upw, double Dq, double gfac, double area, double &Jup, double &Jdn)
+{
+  constexpr double RVIS = 1.0 / VISCOSITY;
+  const double den_ave = upw * den_u + (1.0 - upw) * den_d;
+  const double dphi    = P_u - P_d + den_ave * gfac;
+  const bool   upwind  = (dphi >= 0.0);
+  const double ukvr    = (upwind ? kr_u : kr_d) * RVIS;
+  const double q       = (-Dq * ukvr * dphi) * area;
+  const double dphi_dP_up =  1.0 + (upw * gfac) * dden_u;
+  const double dphi_dP_dn = -1.0 + ((1.0 - upw) * gfac) * dden_d;
+  const double dukvr_up = upwind ? dkr_u * RVIS : 0.0;
+  const double dukvr_dn = upwind ? 0.0 : dkr_d * RVIS;
+  const double dq_up = Dq * (dukvr_up * dphi + ukvr * dphi_dP_up) * area;
+  const double dq_dn = Dq * (dukvr_dn * dphi + ukvr * dphi_dP_dn) * area;
+  Jup = dq_up * den_ave - q * (upw * dden_u);
+  Jdn = dq_dn * den_ave - q * ((1.0 - upw) * dden_d);
+}
+
+template <int LPC, int SATFUNC, bool HAS_BC>
+__global__ void __launch_bounds__(128, VSFM2_MIN_BLOCKS)
+vsfm_step2_kernel(const VsfmArgs A)
+{
+  constexpr unsigned FULL = FULL_MASK;
+  constexpr double RVIS = 1.0 / VISCOSITY, RFMW = 1.0 / FMWH2O;
+  constexpr int NBC = HAS_BC ? MAX_BC : 1;
+  const int tid  = blockIdx.x * blockDim.x + threadIdx.x;
+  const int col  = tid / LPC;
+  const int l    = tid % LPC;                        // lane within the column; owns layers 2l and 2l+1
+  const int lane = threadIdx.x & 31;
+  const int nlev = A.nlev;
+  const int j0 = 2 * l, j1 = 2 * l + 1;
+  const bool col_ok = (col < A.ncol) && (A.active == nullptr || A.active[col] != 0);
+  const long long cell0 = (long long)col * nlev + j0;
+  const double area = col_ok ? A.area[col] : 1.0;
+
+  // ---- static per-cell data -----------------------------------------------------------------------
+  Cell2<SATFUNC> a, b;
+  double perm0, dz0, perm1, dz1;
+  cell_load<SATFUNC>(A, a, col_ok && j0 < nlev, cell0, area, perm0, dz0);
+  cell_load<SATFUNC>(A, b, col_ok && j1 < nlev, cell0 + 1, area, perm1, dz1);
+  {
+    const double perm_n = __shfl_down_sync(FULL, perm0, 1, LPC), dz_n = __shfl_down_sync(FULL, dz0, 1, LPC);
+    a.has_conn = b.valid;                            // 2l -> 2l+1
+    b.has_conn = b.valid && (j1 < nlev - 1);         // 2l+1 -> 2(l+1)
+    conn_setup(perm0, dz0, perm1, dz1, A.uz, a.upw, a.Dq, a.gfac);
+    conn_setup(perm1, dz1, perm_n, dz_n, A.uz, b.upw, b.Dq, b.gfac);
+  }
+
+  // mass-rate source/sinks (GoveqnRichards...:1871-1875): F -= value / FMWH2O.  All loads are issued up front.
+  const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
+  double src_kg = 0.0;
+  {
+    double v0[MAX_SS], v1[MAX_SS];
+#pragma unroll
+    for (int k = 0; k < MAX_SS; ++k) {
+      v0[k] = 0.0; v1[k] = 0.0;
+      if (k < A.nss) {
+        const CondDev &c = A.ss[k];
+        const bool percell = (c.region == REGION_CELLS);
+        const int jown = (c.region == REGION_TOP) ? jtop : jbot;
+        const bool m0 = a.valid && (percell || j0 == jown), m1 = b.valid && (percell || j1 == jown);
+        const double *p = c.value + (percell ? cell0 : (long long)col);
+        if (m0) v0[k] = __ldg(p);
+        if (m1) v1[k] = __ldg(p + (percell ? 1 : 0));
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MAX_SS; ++k) { a.src += v0[k] * RFMW; b.src += v1[k] * RFMW; src_kg += v0[k] + v1[k]; }
+  }
+
+  // boundary conditions (MeshType.F90:723-806): top -> unit vector (0,0,-1), bottom -> (0,0,+1); dist_up = 0
+  double bcP[NBC], bcKr[NBC], bcGfac[NBC], bcDq[NBC], bcMassExc[NBC], bcFlux[NBC];
+  int    bcOwn[NBC];                                 // 0: not on this lane, 1: cell a, 2: cell b
+#pragma unroll
+  for (int k = 0; k < NBC; ++k) {
+    bcOwn[k] = 0; bcP[k] = PRESSURE_REF; bcKr[k] = 1.0; bcGfac[k] = 0.0; bcDq[k] = 0.0; bcMassExc[k] = 0.0; bcFlux[k] = 0.0;
+    if (HAS_BC && k < A.nbc) {
+      const bool top = (A.bc[k].region == REGION_TOP);
+      const int jown = top ? jtop : jbot;
+      if (a.valid && j0 == jown) bcOwn[k] = 1;
+      if (b.valid && j1 == jown) bcOwn[k] = 2;
+      if (bcOwn[k]) {
+        const double dzc = (bcOwn[k] == 1) ? dz0 : dz1, permc = (bcOwn[k] == 1) ? perm0 : perm1;
+        const double uzbc = (A.uz == 0.0) ? 0.0 : (top ? -1.0 : 1.0);
+        bcGfac[k] = FMWH2O * ((0.0 + 0.5 * dzc) * (uzbc * (-GRAVITY_CONSTANT)));
+        bcDq[k] = permc / (0.0 + 0.5 * dzc);
+        bcP[k] = A.bc[k].value[col];
+        SatState sb;
+        sat_values<SATFUNC>((bcOwn[k] == 1) ? a.sp : b.sp, bcP[k], 1.0, sb);   // BC aux vars keep frac_liq_sat = 1 (RichardsODEPressureAuxType.F90:93)
+        bcKr[k] = sb.kr;
+      }
+    }
+  }
+
+  // ---- time-step / Newton state (uniform per column unless noted) ---------------------------------
+  const SnesOpts so = A.so;
+  const double atol2 = so.atol * so.atol, rtol2 = so.rtol * so.rtol, stol2 = so.stol * so.stol;
+  const double divtol2 = so.divtol * so.divtol, maxstep2 = so.ls_maxstep * so.ls_maxstep;
+  double dt_iter = A.dt, time_done = 0.0, dtInv = 1.0 / dt_iter;
+  int    cuts = 0, tot_its = 0, tot_nf = 0, last_reason = 0, converged = 0;
+  int    phase = col_ok ? PH_INIT : PH_DONE;
+  int    its = 0, nfuncs = 0, ls_count = 0;
+  double f2 = 0.0, x2 = 0.0, y2 = 0.0, ttol2 = 0.0, f2_0 = 0.0;      // squared norms ||F||^2, ||X||^2, ||Y||^2
+  double initslope = -1.0, lambda = 1.0, lambdaprev = 1.0, gprev = 0.0;
+
+  for (;;) {
+    // ================= Newton step set-up: Jacobian, linear solve, line-search initialisation =================
+    // Executed by the WHOLE warp whenever any of its columns starts a Newton iteration (warp-uniform branch, so every
+    // shuffle below is convergent); lanes of a column that is not in PH_NEWTON compute and discard.
+    if (__any_sync(FULL, phase == PH_NEWTON)) {
+      const bool nw = (phase == PH_NEWTON);
+      double den_a, dden_a, den_b, dden_b;
+      density_fixedT(A.dtab, a.X, den_a, dden_a);
+      density_fixedT(A.dtab, b.X, den_b, dden_b);
+      // first cell of the next lane = dn side of connection b
+      const double Xn    = __shfl_down_sync(FULL, a.X, 1, LPC),   krn   = __shfl_down_sync(FULL, a.kr, 1, LPC);
+      const double dkrn  = __shfl_down_sync(FULL, a.dkr, 1, LPC), denn  = __shfl_down_sync(FULL, den_a, 1, LPC);
+      const double ddenn = __shfl_down_sync(FULL, dden_a, 1, LPC);
+      double Jup_a = 0.0, Jdn_a = 0.0, Jup_b = 0.0, Jdn_b = 0.0;
+      if (a.has_conn) rich_flux_deriv(a.X, a.kr, a.dkr, den_a, dden_a, b.X, b.kr, b.dkr, den_b, dden_b, a.upw, a.Dq, a.gfac, area, Jup_a, Jdn_a);
+      if (b.has_conn) rich_flux_deriv(b.X, b.kr, b.dkr, den_b, dden_b, Xn, krn, dkrn, denn, ddenn, b.upw, b.Dq, b.gfac, area, Jup_b, Jdn_b);
+      const double Jup_p = __shfl_up_sync(FULL, Jup_b, 1, LPC), Jdn_p = __shfl_up_sync(FULL, Jdn_b, 1, LPC);   // connection (2l-1) -> 2l
+      // rows 2l and 2l+1 of the tridiagonal Jacobian (GoveqnRichards...:2054-2069 insertion order)
+      double sub_a = 0.0, dia_a = 1.0, sup_a = 0.0, sub_b = 0.0, dia_b = 1.0, sup_b = 0.0;
+      if (a.valid) {
+        dia_a = 0.0;
+        if (l > 0) { sub_a = -Jup_p; dia_a += -Jdn_p; }
+        dia_a += Jup_a; sup_a = Jdn_a;
+      }
+      if (b.valid) { sub_b = -Jup_a; dia_b = -Jdn_a; dia_b += Jup_b; sup_b = Jdn_b; }
+      if (HAS_BC) {
+#pragma unroll
+        for (int k = 0; k < NBC; ++k) if (bcOwn[k]) {                // boundary: (dn,dn) -= Jdn  (:2136-2140)
+          const bool onA = (bcOwn[k] == 1);
+          const double Xc = onA ? a.X : b.X, krc = onA ? a.kr : b.kr, dkrc = onA ? a.dkr : b.dkr;
+          const double denc = onA ? den_a : den_b, ddenc = onA ? dden_a : dden_b;
+          const double dphi0 = bcP[k] - Xc + denc * bcGfac[k];
+          const bool seep = (A.bc[k].itype == CT_SEEPAGE) && (dphi0 > 0.0) && (bcP[k] <= PRESSURE_REF);
+          const double dphi = seep ? 0.0 : dphi0;
+          const bool upwind = (dphi >= 0.0);
+          const double ukvr = (upwind ? bcKr[k] : krc) * RVIS;
+          const double q    = (-bcDq[k] * ukvr * dphi) * area;
+          const double dphi_dP_dn = seep ? 0.0 : (-1.0 + bcGfac[k] * ddenc);
+          const double dukvr_dn = upwind ? 0.0 : dkrc * RVIS;
+          const double dq_dn = bcDq[k] * (dukvr_dn * dphi + ukvr * dphi_dP_dn) * area;
+          const double t = -(dq_dn * denc - q * ddenc);
+          if (onA) dia_a += t; else dia_b += t;
+        }
+      }
+      if (a.valid) dia_a += (a.por * dden_a * a.sat + a.por * den_a * a.dsat) * a.vol * dtInv;   // AccumDeriv (:1673-1675), dpor_dP = 0
+      if (b.valid) dia_b += (b.por * dden_b * b.sat + b.por * den_b * b.dsat) * b.vol * dtInv;
+
+      // ---- J Y = F: eliminate this lane's second unknown, PCR over the first unknowns, back-substitute ----
+      const double Fa = a.valid ? a.F : 0.0, Fb = b.valid ? b.F : 0.0;
+      const double rb = __drcp_rn(dia_b);
+      const double bs = sub_b * rb, bu = sup_b * rb, bf = Fb * rb;   // y_b = bf - bs y_a(l) - bu y_a(l+1)
+      const double bs_p = __shfl_up_sync(FULL, bs, 1, LPC), bu_p = __shfl_up_sync(FULL, bu, 1, LPC), bf_p = __shfl_up_sync(FULL, bf, 1, LPC);
+      // reduced row l: sub_a y_b(l-1) + dia_a y_a(l) + sup_a y_b(l) = Fa   (sub_a = 0 on lane 0)
+      const double rB = __drcp_rn(dia_a - sub_a * bu_p - sup_a * bs);
+      const double al = (-sub_a * bs_p) * rB, ga = (-sup_a * bu) * rB, de = (Fa - sub_a * bf_p - sup_a * bf) * rB;
+      const double Ya = pcr_unit_diag<LPC>(al, ga, de);
+      const double Ya_n = __shfl_down_sync(FULL, Ya, 1, LPC);
+      const double Yb = bf - bs * Ya - bu * Ya_n;                    // bu = 0 where there is no next cell
+      const double Yb_p = __shfl_up_sync(FULL, Yb, 1, LPC);
+      // initslope = F . (J Y), forced negative (SNESLineSearchApply_BT)
+      double JYa = dia_a * Ya + sup_a * Yb, JYb = sub_b * Ya + dia_b * Yb;
+      if (l > 0) JYa += sub_a * Yb_p;
+      if (b.has_conn) JYb += sup_b * Ya_n;
+      const double yn2 = col_sum<LPC>((a.valid ? Ya * Ya : 0.0) + (b.valid ? Yb * Yb : 0.0));
+      double slope = col_sum<LPC>(Fa * JYa + Fb * JYb);
+      if (nw) {
+        a.Y = Ya; b.Y = Yb; y2 = yn2;                                // x2 = ||X||^2 was taken when X was accepted
+        if (slope > 0.0) slope = -slope;
+        if (slope == 0.0) slope = -1.0;
+        initslope = slope;
+        lambda = 1.0; ls_count = 0;
+        if (y2 == 0.0) {
+          // zero step: line search "fails"; stol*xnorm > ynorm => SNES_CONVERGED_SNORM_RELATIVE (ls.c)
+          last_reason = (stol2 * x2 > y2) ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
+          phase = -1;   // SNES finished, handled below
+        } else {
+          if (y2 > maxstep2) { const double sc = so.ls_maxstep / sqrt(y2); a.Y *= sc; b.Y *= sc; y2 = maxstep2; }
+          a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X);
+          phase = PH_LS_FULL;
+          if (nfuncs >= so.max_funcs && so.max_funcs >= 0) { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
+        }
+      }
+    }
+
+    // ================= end-of-SNES bookkeeping (SOEBaseStepDT_SNES :481-536) =================
+    if (phase == -1) {
+      tot_nf += nfuncs;
+      if (last_reason < 0) {
+        cuts += 1; dt_iter = 0.5 * dt_iter; dtInv = 1.0 / dt_iter;
+        a.X = a.Xprev; b.X = b.Xprev;                       // VecCopy(soln_prev, soln)
+        if (cuts > 20) { converged = 0; phase = PH_DONE; }
+        else { a.W = a.X; b.W = b.X; phase = PH_INIT; }
+      } else {
+        converged = 1; time_done += dt_iter; tot_its += its;
+        a.Xprev = a.X; b.Xprev = b.X;                       // PostSolve: soln -> soln_prev
+        if (HAS_BC) {
+#pragma unroll
+          for (int k = 0; k < NBC; ++k) if (bcOwn[k]) bcMassExc[k] += bcFlux[k] * dt_iter;
+        }
+        if (time_done >= A.dt) phase = PH_DONE;
+        else { a.W = a.X; b.W = b.X; phase = PH_INIT; }
+      }
+      its = 0; nfuncs = 0;
+    }
+
+    if (__all_sync(FULL, phase == PH_DONE)) break;
+
+    // ================= residual evaluation at W (VSFMSOEResidual) =================
+    SatState sa, sb;
+    sat_values_pair<SATFUNC>(a.sp, b.sp, a.W, b.W, a.frac_liq, b.frac_liq, sa, sb);
+    double dena, ddena, denb, ddenb, Ga, Gb, G_bcflux[NBC];
+    density_fixedT(A.dtab, a.W, dena, ddena);
+    density_fixedT(A.dtab, b.W, denb, ddenb);
+    {
+      const double acc_a = a.por * dena * sa.sat * a.vol * dtInv;       // Accum (:1626-1630)
+      const double acc_b = b.por * denb * sb.sat * b.vol * dtInv;
+      if (phase == PH_INIT) { a.accum_prev = acc_a; b.accum_prev = acc_b; }   // PreSolve: accumulation at soln_prev (== W here)
+      const double Wn = __shfl_down_sync(FULL, a.W, 1, LPC), krn = __shfl_down_sync(FULL, sa.kr, 1, LPC), denn = __shfl_down_sync(FULL, dena, 1, LPC);
+      const double flux_a = a.has_conn ? rich_flux(a.W, sa.kr, dena, b.W, sb.kr, denb, a.upw, a.Dq, a.gfac, area) : 0.0;
+      const double flux_b = b.has_conn ? rich_flux(b.W, sb.kr, denb, Wn, krn, denn, b.upw, b.Dq, b.gfac, area) : 0.0;
+      const double flux_p = __shfl_up_sync(FULL, flux_b, 1, LPC);
+      Ga = acc_a - a.accum_prev;
+      if (l > 0) Ga = Ga + flux_p;                                      // ff(dn) += flux  (:1806)
+      Ga = Ga - flux_a;                                                 // ff(up) -= flux  (:1805)
+      Gb = acc_b - b.accum_prev;
+      Gb = Gb + flux_a;
+      Gb = Gb - flux_b;
+#pragma unroll
+      for (int k = 0; k < NBC; ++k) {
+        G_bcflux[k] = 0.0;
+        if (HAS_BC && bcOwn[k]) {                                       // boundary connection, upweight = 0 (:262-264)
+          const bool onA = (bcOwn[k] == 1);
+          const double Wc = onA ? a.W : b.W, krc = onA ? sa.kr : sb.kr, denc = onA ? dena : denb;
+          double dphi = bcP[k] - Wc + denc * bcGfac[k];
+          if ((A.bc[k].itype == CT_SEEPAGE) && (dphi > 0.0) && (bcP[k] <= PRESSURE_REF)) dphi = 0.0;
+          const double ukvr = ((dphi >= 0.0) ? bcKr[k] : krc) * RVIS;
+          const double fl = ((-bcDq[k] * ukvr * dphi) * area) * denc;
+          if (onA) Ga = Ga + fl; else Gb = Gb + fl;
+          G_bcflux[k] = fl * FMWH2O;
+        }
+      }
+      Ga = Ga - a.src; Gb = Gb - b.src;
+      if (!a.valid) Ga = 0.0;
+      if (!b.valid) Gb = 0.0;
+    }
+    const double g2 = col_sum<LPC>(Ga * Ga + Gb * Gb);
+    const double w2 = col_sum<LPC>((a.valid ? a.W * a.W : 0.0) + (b.valid ? b.W * b.W : 0.0));
+    nfuncs += 1;
+
+    // ================= after the evaluation: line-search / convergence logic (squared norms) =================
+    bool take = false;          // adopt W as the new iterate (and its aux vars)
+    const bool g_bad = !(g2 == g2) || (g2 > 1.7e308);                   // NaN or Inf
+    const bool out_of_funcs = (nfuncs >= so.max_funcs && so.max_funcs >= 0);
+    const bool tiny_step = (stol2 * x2 > y2);                           // stol * xnorm > ynorm
+    if (phase == PH_INIT) {
+      // SNESSolve_NEWTONLS: F(X0) and the iteration-0 convergence test
+      take = true;
+    } else if (phase == PH_LS_FULL) {
+      if (g_bad) {
+        if (lambda <= so.ls_minlambda) { last_reason = SNES_DIVERGED_FNORM_NAN; phase = -1; }
+        else if (out_of_funcs)         { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
+        else { lambda = .5 * lambda; a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); }
+      } else if (.5 * g2 <= .5 * f2 + lambda * so.ls_alpha * initslope) {
+        take = true;
+      } else if (tiny_step) {
+        // "full step didn't work and the step is tiny": line search fails, SNES then sees stol*xnorm > ynorm
+        last_reason = SNES_CONVERGED_SNORM_RELATIVE; phase = -1;
+      } else if (out_of_funcs) {
+        last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1;
+      } else {
+        double lt = -initslope / (g2 - f2 - 2.0 * lambda * initslope);  // quadratic fit
+        lambdaprev = lambda; gprev = g2;
+        if (lt > .5 * lambda) lt = .5 * lambda;
+        lambda = (lt <= .1 * lambda) ? .1 * lambda : lt;
+        a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); phase = PH_LS_QUAD; ls_count = 0;
+      }
+    } else if (phase == PH_LS_QUAD || phase == PH_LS_CUBIC) {
+      if (phase == PH_LS_CUBIC) ls_count += 1;                          // cubic trial points evaluated so far
+      const int ls_fail = tiny_step ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
+      if (g_bad) {
+        last_reason = ls_fail; phase = -1;
+      } else if (.5 * g2 < .5 * f2 + lambda * so.ls_alpha * initslope) {
+        take = true;
+      } else if (ls_count >= so.ls_max_its) {
+        take = true;                                                    // PETSc leaves the cubic loop after max_its fits and keeps the last point
+      } else if (lambda <= so.ls_minlambda) {
+        last_reason = ls_fail; phase = -1;
+      } else if (out_of_funcs) {
+        last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1;
+      } else {
+        const double t1 = .5 * (g2 - f2) - lambda * initslope;           // cubic fit
+        const double t2 = .5 * (gprev - f2) - lambdaprev * initslope;
+        const double rl2 = __drcp_rn(lambda * lambda), rp2 = __drcp_rn(lambdaprev * lambdaprev), rd = __drcp_rn(lambda - lambdaprev);
+        const double ca = (t1 * rl2 - t2 * rp2) * rd;
+        const double cb = (-lambdaprev * t1 * rl2 + lambda * t2 * rp2) * rd;
+        double d = cb * cb - 3 * ca * initslope;
+        if (d < 0.0) d = 0.0;
+        double lt = (ca == 0.0) ? -initslope / (2.0 * cb) : (-cb + sqrt(d)) / (3.0 * ca);
+        lambdaprev = lambda; gprev = g2;
+        if (lt > .5 * lambda) lt = .5 * lambda;
+        lambda = (lt <= .1 * lambda) ? .1 * lambda : lt;
+        a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); phase = PH_LS_CUBIC;
+      }
+    }
+
+    if (take) {
+      // "copy the solution over": X <- W, F <- G; the aux vars of this point feed the next Jacobian / PostSolve
+      a.X = a.W; b.X = b.W; a.F = Ga; b.F = Gb;
+      a.kr = sa.kr; a.sat = sa.sat; b.kr = sb.kr; b.sat = sb.sat;
+      sat_derivs_pair<SATFUNC>(a.sp, b.sp, sa, sb, a.frac_liq, b.frac_liq, a.dsat, a.dkr, b.dsat, b.dkr);
+      if (HAS_BC) {
+#pragma unroll
+        for (int k = 0; k < NBC; ++k) bcFlux[k] = G_bcflux[k];
+      }
+      f2 = g2; x2 = w2;
+      int reason = 0;
+      if (phase == PH_INIT) {
+        its = 0; ttol2 = g2 * rtol2; f2_0 = g2;                         // SNESConvergedDefault, it == 0: ttol = fnorm * rtol
+        if (g_bad)           reason = SNES_DIVERGED_FNORM_NAN;
+        else if (g2 < atol2) reason = SNES_CONVERGED_FNORM_ABS;
+      } else {
+        its += 1;
+        if (g2 < atol2)           reason = SNES_CONVERGED_FNORM_ABS;    // SNESConvergedDefault, it > 0
+        else if (out_of_funcs)    reason = SNES_DIVERGED_FUNCTION_COUNT;
+        else if (g2 <= ttol2)     reason = SNES_CONVERGED_FNORM_RELATIVE;
+        else if (y2 < stol2 * x2) reason = SNES_CONVERGED_SNORM_RELATIVE;
+        else if (so.divtol > 0 && g2 > divtol2 * f2_0) reason = SNES_DIVERGED_DTOL;
+        else if (its >= so.max_it) reason = SNES_DIVERGED_MAX_IT;
+      }
+      if (reason) { last_reason = reason; phase = -1; } else phase = PH_NEWTON;
+    }
+  }
+
+  // ---- VSFMSOEPostSolve -> SetDataInSOEAuxVar (GoveqnRichards...:1170-1195) ---------------------------------
+  double mass = 0.0;
+  if (a.valid) {
+    A.x_out[cell0] = a.X;
+    if (converged) {
+      double den, dden; density_fixedT(A.dtab, a.X, den, dden);
+      const double m = a.por * den * FMWH2O * a.sat * a.vol;
+      A.liq_sat[cell0] = a.sat; A.pressure[cell0] = a.X; A.mass[cell0] = m;
+      A.smp[cell0] = (a.X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
+      mass += m;
+    }
+  }
+  if (b.valid) {
+    A.x_out[cell0 + 1] = b.X;
+    if (converged) {
+      double den, dden; density_fixedT(A.dtab, b.X, den, dden);
+      const double m = b.por * den * FMWH2O * b.sat * b.vol;
+      A.liq_sat[cell0 + 1] = b.sat; A.pressure[cell0 + 1] = b.X; A.mass[cell0 + 1] = m;
+      A.smp[cell0 + 1] = (b.X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
+      mass += m;
+    }
+  }
+  double bc_exc = 0.0;
+  if (HAS_BC && converged) {
+#pragma unroll
+    for (int k = 0; k < NBC; ++k) if (bcOwn[k]) {
+      A.bc[k].flux[col] = bcFlux[k];
+      A.bc[k].mass_exc[col] += bcMassExc[k];
+      bc_exc += bcMassExc[k];
+    }
+  }
+  const double m_end = col_sum<LPC>(mass);
+  const double q_col = col_sum<LPC>(src_kg);
+  if (HAS_BC) bc_exc = col_sum<LPC>(bc_exc);
+  const bool leader = col_ok && (l == 0);
+  double err = 0.0, m_beg = 0.0;
+  if (leader) {
+    A.stat_its[col] = tot_its; A.stat_reason[col] = last_reason; A.stat_cuts[col] = cuts; A.stat_nf[col] = tot_nf;
+    m_beg = A.col_mass[col];
+    if (converged) {
+      err = fabs(m_beg - m_end + q_col * A.dt);
+      A.col_mass[col] = m_end;
+    }
+    A.col_err[col] = err; A.col_src[col] = q_col;
+  }
+
+  // ---- block partials for the global mass-balance / convergence reductions (deterministic order) ----------
+  // only the column leaders (lanes 0, LPC, 2 LPC, ...) carry values: fold them with log2(32 / LPC) shuffles
+  double v[8];
+  v[0] = leader ? m_beg : 0.0;                                  // sum mass before
+  v[1] = leader ? (converged ? m_end : m_beg) : 0.0;            // sum mass after
+  v[2] = leader ? q_col * A.dt : 0.0;                           // sum sources * dt
+  v[3] = leader ? bc_exc : 0.0;                                 // sum boundary mass exchanged
+  v[4] = leader ? err : 0.0;                                    // max |mass error|
+  v[5] = leader ? (double)tot_its : 0.0;                        // max Newton its
+  v[6] = leader ? (converged ? 0.0 : 1.0) : 0.0;                // any diverged
+  v[7] = leader ? (double)cuts : 0.0;                           // max dt cuts
+  int worst = leader ? last_reason : 0x7fffffff;
+#pragma unroll
+  for (int s = 16; s >= LPC; s >>= 1) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(FULL, v[k], s);
+#pragma unroll
+    for (int k = 4; k < 8; ++k) v[k] = fmax(v[k], __shfl_xor_sync(FULL, v[k], s));
+    worst = min(worst, __shfl_xor_sync(FULL, worst, s));
+  }
+  __shared__ double red[8][128 / 32];
+  __shared__ int redw[128 / 32];
+  const int warp = threadIdx.x >> 5;
+  if (lane == 0) { for (int k = 0; k < 8; ++k) red[k][warp] = v[k]; redw[warp] = worst; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int nw = blockDim.x >> 5;
+    double o[8]; int ow = 0x7fffffff;
+    for (int k = 0; k < 8; ++k) o[k] = 0.0;
+    for (int w = 0; w < nw; ++w) {
+      for (int k = 0; k < 4; ++k) o[k] += red[k][w];
+      for (int k = 4; k < 8; ++k) o[k] = fmax(o[k], red[k][w]);
+      ow = min(ow, redw[w]);
+    }
+    double *bp = A.block_partials + (size_t)blockIdx.x * 9;
+    for (int k = 0; k < 8; ++k) bp[k] = o[k];
+    bp[8] = (double)ow;
+  }
+}
+
+}  // namespace mpp

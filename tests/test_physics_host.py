@@ -24,6 +24,7 @@ def hc():
     L.hc_convert_soil.argtypes = [C.c_int] + [C.c_double] * 5 + [c_dp]
     L.hc_sat.argtypes = [C.c_int, c_dp, C.c_double, C.c_double, c_dp]
     L.hc_density.argtypes = [C.c_int, C.c_double, C.c_double, c_dp]
+    L.hc_log_exp.argtypes = [C.c_int, c_dp, c_dp, c_dp]
     L.hc_density_fixedT.argtypes = [C.c_int, C.c_double, C.c_double, c_dp]
     L.hc_enthalpy_ifc67.argtypes = [C.c_double, C.c_double, c_dp]
     L.hc_internal_energy_enthalpy.argtypes = [C.c_int] + [C.c_double] * 5 + [c_dp]
@@ -118,3 +119,28 @@ def test_enthalpy_matches_oracle(hc, oracle):
         assert abs(out[0] - ref[0]) < 2e-4 and rel(out[0], ref[0]) < 1e-9
         assert rel(out[1], ref[1]) < 1e-13
         assert rel(out[2], ref[2]) < 1e-10
+
+
+def test_lean_log_exp_are_accurate_to_2ulp(hc):
+    """mpp_log / mpp_exp of physics.cuh (branch-free, constant-bank coefficients) against libm over the ranges the soil
+    curves produce: x = -alpha pc in [1e-12, 1e12], 1 + x^n up to 1e300, exponents n L1 and -m L2 / 2 in [-700, 700]."""
+    rng = np.random.default_rng(17)
+    x = np.concatenate([np.exp(rng.uniform(np.log(1e-12), np.log(1e12), 200000)), 1.0 + np.exp(rng.uniform(-40, 690, 100000)),
+                        1.0 + rng.uniform(-0.3, 0.45, 100000), [1.0, 2.0, 0.5, np.sqrt(2.0), np.sqrt(0.5), 1e300, 1e-300]])
+    lg, ex = np.zeros_like(x), np.zeros_like(x)
+    hc.hc_log_exp(x.size, x.ctypes.data_as(c_dp), lg.ctypes.data_as(c_dp), ex.ctypes.data_as(c_dp))
+    ref = np.log(x)
+    ulp = np.abs(lg - ref) / np.maximum(np.spacing(np.abs(ref)), 1e-300)
+    assert ulp.max() <= 2.0, ulp.max()
+    assert lg[-7] == 0.0                                              # log(1) is exact
+    # exp on its own argument set (the log output of this call is ignored)
+    y = np.concatenate([rng.uniform(-700.0, 700.0, 200000), rng.uniform(-2.0, 2.0, 200000), [0.0, -707.9, 707.9, 1e-300, -1e-300]])
+    dummy, ex = np.zeros_like(y), np.zeros_like(y)
+    hc.hc_log_exp(y.size, y.ctypes.data_as(c_dp), dummy.ctypes.data_as(c_dp), ex.ctypes.data_as(c_dp))
+    ref = np.exp(y)
+    ulp = np.abs(ex - ref) / np.spacing(ref)
+    assert ulp.max() <= 2.0, ulp.max()
+    # clamped tails stay finite and normal
+    out, big = np.zeros(2), np.array([-1e6, 1e6])
+    hc.hc_log_exp(2, big.ctypes.data_as(c_dp), dummy[:2].ctypes.data_as(c_dp), out.ctypes.data_as(c_dp))
+    assert 0.0 < out[0] < 1e-300 and 1e307 < out[1] < np.inf
