@@ -4,10 +4,12 @@
     python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host cores
 
-Workload (BASELINE.json configs[3]): 4 M synthetic ELM-like soil columns x 15 layers, van Genuchten curves,
-Tanaka density, six COND_MASS_RATE source/sinks, dt = 1800 s, SNES tolerances = reference defaults, sharded by
-column over the N GPUs of one box (strong scaling; one process per GPU).  One "step" = one ELM coupling step =
-PreStepDT + StepDT + PostStepDT over the whole batch (MPPVSFMALM_Driver.F90:603-935).
+Workload (BASELINE.json configs[3]): 4 Mi synthetic ELM-like soil columns x 15 layers PER GPU, van Genuchten curves,
+Tanaka density, six COND_MASS_RATE source/sinks, dt = 1800 s, SNES tolerances = reference defaults; columns are
+independent, so every rank owns its own contiguous 4 Mi-column shard of one global seeded batch (weak scaling; one
+process per GPU; `--scaling strong` splits a single 4 Mi batch instead).  One "step" = one ELM coupling step =
+PreStepDT + StepDT + PostStepDT over the whole batch (MPPVSFMALM_Driver.F90:603-935) + one NCCL all-gather of the
+9 mass-balance / convergence doubles of every rank.
 
 Prints ONE JSON line (rank 0).  `value` is timed with all inputs resident in HBM; `e2e` repeats the same steps
 through the C ABI with HOST buffers (SetDataFromCLM x7 in, GetDataForCLM x4 out, as MPPVSFMALM_Solve does).
@@ -35,11 +37,16 @@ NLEV = 15
 DT = 1800.0
 CHUNK = 65536                      # columns per seeded chunk (shards are unions of chunks)
 ALG_BYTES_PER_COLSTEP = 1224       # SURVEY.md section 8(d), VSFM-VG base variant
+# DRAM bytes per column-step of vsfm_step2_kernel measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum over
+# 1 Mi columns, profiles/r1_vsfm_v6.md: 1.3087 GB + 0.6489 GB); the kernel also reads the six source arrays unsummed
+# and writes mass, smp and the committed solution, which the 1224 B base variant does not count
+TRAFFIC_BYTES_PER_COLSTEP = (1.308718e9 + 0.648915e9) / 1048576
 SS_NAMES = ("infil", "et", "dew", "drain", "snow", "sublim")
 
 
-def shard_inputs(c0, c1):
+def shard_inputs(c0, c1, chunk=CHUNK):
     """Columns [c0, c1) of the global seeded batch: chunk k uses seed SEED + k so any rank builds only its shard."""
+    CHUNK = chunk
     parts = []
     k0, k1 = c0 // CHUNK, (c1 - 1) // CHUNK
     for k in range(k0, k1 + 1):
@@ -142,21 +149,22 @@ def run_reference(args):
     cb, ncol, el = cpu_baseline(args.steps, args.warmup, target_seconds=30.0)
     line = {"impl": "reference", "metric": "soil_column_timesteps_per_sec", "value": cb["value"], "unit": "column-timesteps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.ncol, args.gpus), "cpu_baseline": cb,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.ncol * args.gpus if args.scaling == "weak" else args.ncol, args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 def workload_config(ncol, ngpus):
-    return {"workload": "VSFM Richards (BASELINE.json configs[3]): %d synthetic ELM-like soil columns x %d layers, van Genuchten-Mualem, "
+    return {"workload": "VSFM Richards (BASELINE.json configs[3]): %d synthetic ELM-like soil columns x %d layers per GPU, van Genuchten-Mualem, "
                         "Tanaka density, 6 COND_MASS_RATE source/sinks, dt=%.0f s, SNES rtol 1e-8 / stol 1e-10 / max_it 50 "
-                        "(reference defaults), per-column Newton + bt line search + tridiagonal solve" % (ncol, NLEV, DT),
-            "ncol_total": ncol, "nlev": NLEV, "dt_s": DT, "satfunc": "van_genuchten",
-            "parallelism": "columns sharded contiguously over %d GPU(s); NCCL all-reduce of 8 mass-balance/convergence doubles per step" % ngpus,
+                        "(reference defaults), per-column Newton + bt line search + tridiagonal solve" % (ncol // ngpus, NLEV, DT),
+            "ncol_total": ncol, "ncol_per_gpu": ncol // ngpus, "nlev": NLEV, "dt_s": DT, "satfunc": "van_genuchten",
+            "parallelism": "columns sharded contiguously over %d GPU(s), no data-path collective; one NCCL all-gather of 9 "
+                           "mass-balance/convergence doubles per rank per step" % ngpus,
             "cache": "inputs larger than L2: %.1f GB of HBM-resident arrays touched per step per GPU vs 126 MB L2"
-                     % (ncol / ngpus * 2008 / 1e9)}
+                     % (ncol / ngpus * TRAFFIC_BYTES_PER_COLSTEP / 1e9)}
 
 
 def main():
@@ -165,7 +173,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mpp_b200")
-    ap.add_argument("--ncol", type=int, default=4 * 1024 * 1024, help="total columns over all GPUs")
+    ap.add_argument("--ncol", type=int, default=4 * 1024 * 1024, help="columns per GPU (weak scaling) / in total (strong scaling)")
+    ap.add_argument("--scaling", default="weak", choices=("weak", "strong"))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -188,8 +197,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     assert world == args.gpus or world == 1
 
-    ncol_total = args.ncol
-    c0, c1 = rank * ncol_total // world, (rank + 1) * ncol_total // world
+    from mpp_b200 import parallel as PL
+    ncol_total = args.ncol * world if args.scaling == "weak" else args.ncol
+    c0, c1 = PL.shard_range(ncol_total, rank, world)
     d = shard_inputs(c0, c1)
     ncol = c1 - c0
     # a dedicated (non-default) stream: the library, the CUDA events and NCCL all run on it
@@ -209,19 +219,14 @@ def main():
 
     # ------------------------------------------------------------------ device-resident throughput
     p, ids = fresh()
-    red_ptr = p.reduction_buffer_ptr()
-
-    class _Red:                                      # torch view of the library's 8-double reduction buffer
-        __cuda_array_interface__ = {"shape": (8,), "typestr": "<f8", "data": (red_ptr, False), "version": 3}
-    red = torch.as_tensor(_Red(), device=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    gred = PL.GlobalReductions(PL.device_view(p.reduction_buffer_ptr(), PL.NRED, dev))
 
     def step(nstep):
         p.pre_step_dt()
         p.step_dt_async(DT, nstep)
         p.post_step_dt()
-        if world > 1:                                # global mass-balance / convergence reductions
-            dist.all_reduce(red[0:4], op=dist.ReduceOp.SUM)
-            dist.all_reduce(red[4:8], op=dist.ReduceOp.MAX)
+        gred.step()                                  # global mass-balance / convergence reductions
 
     for s in range(args.warmup):
         step(s + 1)
@@ -241,6 +246,11 @@ def main():
     conv, reason = p.step_result()
     sums, maxs = p.mass_balance(DT)
     st = p.stats()
+    glob = gred.as_dict()
+    nfailed = torch.tensor([float((st["reasons"] < 0).sum()), float((st["dt_cuts"] > 0).sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nfailed)
+    nfailed = nfailed.tolist()
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -268,16 +278,10 @@ def main():
             for key, var in (("sat", K.VAR_LIQ_SAT), ("mass", K.VAR_MASS), ("smp", K.VAR_SOIL_MATRIX_POT), ("pressure", K.VAR_PRESSURE)):
                 p.get_data(K.AUXVAR_INTERNAL, var, 1, out=outs[key])
             p.post_step_dt()
-            if world > 1:
-                dist.all_reduce(red2[0:4], op=dist.ReduceOp.SUM)
-                dist.all_reduce(red2[4:8], op=dist.ReduceOp.MAX)
+            gred2.step()
             return cv
 
-        red_ptr2 = p.reduction_buffer_ptr()
-
-        class _Red2:
-            __cuda_array_interface__ = {"shape": (8,), "typestr": "<f8", "data": (red_ptr2, False), "version": 3}
-        red2 = torch.as_tensor(_Red2(), device=torch.device("cuda", local_rank))
+        gred2 = PL.GlobalReductions(PL.device_view(p.reduction_buffer_ptr(), PL.NRED, dev))
         for s in range(args.warmup):
             e2e_step(s + 1)
         barrier()
@@ -311,18 +315,23 @@ def main():
         line = {
             "metric": "soil_column_timesteps_per_sec", "value": value, "unit": "column-timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_launch_ms,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(ncol_total, world),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "vsfm_step_kernel<16,VG>",
+                         "traffic": TRAFFIC_BYTES_PER_COLSTEP * ncol, "traffic_unit": "bytes per launch (ncu dram__bytes, per column x columns of this launch)",
+                         "kernel": "vsfm_step2_kernel<8,VG,noBC>",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLSTEP,
-                         "note": "fp64-issue bound (3 log + 3 exp + sqrt + divides per cell per residual evaluation, "
-                                 "%.1f evaluations and %.1f Newton iterations per column-step); see DESIGN.md" % (nf_mean, its_mean)},
-            "solver": {"converged_all": bool(conv), "worst_reason": int(reason), "newton_its_mean": its_mean, "newton_its_max": its_max,
-                       "residual_evals_mean": nf_mean, "max_abs_mass_error_kg": float(maxs[0]), "last_step_kernel_ms": last_kernel_ms},
+                         "note": "fp64-latency bound, not HBM bound (2 log + 2 exp + 3 reciprocals per cell per residual evaluation, "
+                                 "%.1f evaluations and %.1f Newton iterations per column-step; fp64 pipe ~40 %% busy); see DESIGN.md" % (nf_mean, its_mean)},
+            "solver": {"converged_all": not glob["any_diverged"], "worst_reason": glob["worst_reason"], "newton_its_mean": its_mean, "newton_its_max": its_max,
+                       "residual_evals_mean": nf_mean, "max_abs_mass_error_kg": float(maxs[0]), "last_step_kernel_ms": last_kernel_ms,
+                       "columns_failed_last_step": int(nfailed[0]), "columns_with_dt_cuts_last_step": int(nfailed[1]),
+                       "global_reductions_last_step": glob,
+                       "note": "the reference algorithm at its default tolerances cuts dt / fails on a handful of the 4 Mi synthetic columns; "
+                               "the oracle reproduces every cut and failure (tests/golden/hard_columns.json)"},
         }
         if not args.no_cpu and world == 1:
             cb, _, _ = cpu_baseline(args.steps, args.warmup)
