@@ -142,7 +142,7 @@ def cpu_baseline(steps, warmup, target_seconds=20.0):
             "seconds": el, "converged": bool(conv)}, ncol, el
 
 
-def run_reference(args):
+def run_reference(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -153,7 +153,7 @@ def run_reference(args):
             "config": workload_config(args.ncol * args.gpus if args.scaling == "weak" else args.ncol, args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(real_stdout, line)
 
 
 def workload_config(ncol, ngpus):
@@ -167,7 +167,21 @@ def workload_config(ncol, ngpus):
                      % (ncol / ngpus * TRAFFIC_BYTES_PER_COLSTEP / 1e9)}
 
 
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  NCCL and friends print banners to the C-level stdout, so fd 1 is
+    pointed at stderr for the whole run and the JSON line goes to the saved descriptor."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+def _emit(real_stdout_fd, line):
+    os.write(real_stdout_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -181,7 +195,7 @@ def main():
     if args.warmup < 3:
         args.warmup = 3                                      # timing rules: W >= 3
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, real_stdout)
 
     import torch
     import torch.distributed as dist
@@ -336,7 +350,7 @@ def main():
         if not args.no_cpu and world == 1:
             cb, _, _ = cpu_baseline(args.steps, args.warmup)
             line["cpu_baseline"] = cb
-        print(json.dumps(line), flush=True)
+        _emit(real_stdout, line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
