@@ -19,9 +19,7 @@ time the oracle -- the C restatement of the reference algorithm (oracle/, kind "
 import argparse
 import json
 import os
-import subprocess
 import sys
-import tempfile
 import time
 
 import numpy as np
@@ -64,47 +62,49 @@ def shard_inputs(c0, c1, chunk=CHUNK):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled from a thread every few
+    milliseconds (nvidia-smi -lms needs about a second to start, longer than the timed region of a short run)."""
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+    def __init__(self, gpu_index, period_s=0.004):
+        import threading
+        self.sm, self.mask, self.smax, self.ok = [], 0, None, False
+        self._stop = threading.Event()
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
         except Exception:
-            self.p = None
+            return
+        self.period = period_s
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.smax, "reasons": [], "samples": 0}
+        if not self.ok:
             return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except Exception:
-            self.p.kill()
-        self.f.flush(); self.f.seek(0)
-        sm, smax, reasons = [], [], set()
-        for line in self.f.read().splitlines():
-            t = [x.strip() for x in line.split(",")]
-            if len(t) < 9:
-                continue
-            try:
-                sm.append(float(t[1])); smax.append(float(t[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        self.f.close()
-        try:
-            os.unlink(self.f.name)
-        except OSError:
-            pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(np.max(smax)), reasons=sorted(reasons), samples=len(sm))
+        self._stop.set()
+        self.t.join(timeout=2)
+        if self.sm:
+            out.update(sm_mhz=float(np.median(self.sm)), reasons=[n for b, n in self.REASONS if self.mask & b], samples=len(self.sm))
         return out
 
 
@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--ncol", type=int, default=4 * 1024 * 1024, help="columns per GPU (weak scaling) / in total (strong scaling)")
     ap.add_argument("--scaling", default="weak", choices=("weak", "strong"))
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--chunks", type=int, default=16, help="column chunks of the pipelined coupling step (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -283,14 +284,15 @@ def main():
         h2d = sum(pin[k].nbytes for k in pin)
         d2h = sum(outs[k].nbytes for k in outs)
 
+        ins = [(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids[name], pin[name]) for name in SS_NAMES]
+        ins.append((K.AUXVAR_INTERNAL, K.VAR_FRAC_LIQ_SAT, 1, pin["frac_liq"]))
+        olist = [(K.AUXVAR_INTERNAL, var, 1, outs[key]) for key, var in
+                 (("sat", K.VAR_LIQ_SAT), ("mass", K.VAR_MASS), ("smp", K.VAR_SOIL_MATRIX_POT), ("pressure", K.VAR_PRESSURE))]
+
         def e2e_step(nstep):
-            for name in SS_NAMES:
-                p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids[name], pin[name])
-            p.set_data(K.AUXVAR_INTERNAL, K.VAR_FRAC_LIQ_SAT, 1, pin["frac_liq"])
-            p.pre_step_dt()
-            cv, rs = p.step_dt(DT, nstep)
-            for key, var in (("sat", K.VAR_LIQ_SAT), ("mass", K.VAR_MASS), ("smp", K.VAR_SOIL_MATRIX_POT), ("pressure", K.VAR_PRESSURE)):
-                p.get_data(K.AUXVAR_INTERNAL, var, 1, out=outs[key])
+            # one ELM coupling step through the C ABI with host buffers (MPPVSFMALM_Driver.F90:379-463, 603, 642, 674-705):
+            # 7 inputs host->device, PreStepDT + StepDT, 4 outputs device->host, pipelined over column chunks
+            cv, rs = p.coupled_step(DT, nstep, ins, olist, args.chunks)
             p.post_step_dt()
             gred2.step()
             return cv
@@ -314,7 +316,8 @@ def main():
         e2e = {"value": ncol_total * args.steps / (float(t.item()) * 1e-3), "unit": "column-timesteps/s",
                "h2d_bytes_per_step": int(h2d * world), "d2h_bytes_per_step": int(d2h * world),
                "ms_per_step": float(t.item()) / args.steps, "converged": bool(cv),
-               "api": "mppgpu_set_data x7 (pinned host) + pre_step_dt + step_dt + mppgpu_get_data x4 + post_step_dt"}
+               "api": "mppgpu_vsfm_coupled_step (= SetDataFromCLM x7 from pinned host + PreStepDT + StepDT + GetDataForCLM x4 to pinned host, "
+                      "software-pipelined over %d column chunks on 3 streams) + mppgpu_post_step_dt + NCCL all-gather" % (args.chunks or 16)}
         p.close()
 
     if rank == 0:

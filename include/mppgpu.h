@@ -28,6 +28,7 @@
  *   soe%StepDT                       SystemOfEquationsBaseType.F90:334-647      mppgpu_step_dt
  *   soe%PostStepDT                   SystemOfEquationsVSFMType.F90:926-940      mppgpu_post_step_dt
  *   per-column mass-balance check    MPPVSFMALM_Driver.F90:556-601, 845-863     mppgpu_vsfm_mass_balance
+ *   ELM coupling step (set x7, step, get x4)  MPPVSFMALM_Driver.F90:379-705   mppgpu_vsfm_coupled_step
  *
  * Conventions
  *   - plain pointers and sizes only; every array argument is a HOST pointer owned by the caller
@@ -111,6 +112,17 @@ int  mppgpu_step_dt(mppgpu_handle h, double dt, int nstep, int *converged, int *
 int  mppgpu_step_dt_async(mppgpu_handle h, double dt, int nstep);
 int  mppgpu_step_result(mppgpu_handle h, int *converged, int *converged_reason);
 int  mppgpu_post_step_dt(mppgpu_handle h);
+
+/* One ELM coupling step of the VSFM SoE with HOST buffers, software-pipelined over column chunks:
+ *   for every in[i]:  SetDataFromCLM(in[i]);   PreStepDT;  StepDT(dt, nstep);   for every out[i]: GetDataForCLM(out[i])
+ * (MPPVSFMALM_Driver.F90:379-463, 603, 642, 674-705) -- same results as those separate calls, but the host->device copies of
+ * chunk k+1, the Newton kernel of chunk k and the device->host copies of chunk k-1 overlap on three CUDA streams.
+ * Host arrays should be page-locked (cudaHostRegister / pinned allocation) for the copies to be asynchronous; pageable
+ * memory works but serialises.  Every array covers the whole handle (ncells or ncol entries, by the condition's region).
+ * nchunks <= 0 picks a default.  The caller still calls PostStepDT to commit. */
+typedef struct { int ieqn, auxvar_type, var_type, cond_id; double *host; } mppgpu_xfer;
+int  mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, int nin, const mppgpu_xfer *in, int nout, const mppgpu_xfer *out,
+                              int nchunks, int *converged, int *converged_reason);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 /* per-column Newton iterations, SNES reason, dt cuts, residual evaluations of the last StepDT (any may be NULL) */

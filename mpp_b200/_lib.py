@@ -12,6 +12,11 @@ _lib = None
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int)
 
+class Xfer(C.Structure):
+    """mppgpu_xfer (include/mppgpu.h)."""
+    _fields_ = [("ieqn", C.c_int), ("auxvar_type", C.c_int), ("var_type", C.c_int), ("cond_id", C.c_int), ("host", C.POINTER(C.c_double))]
+
+
 _SIGS = {
     "mppgpu_last_error": (C.c_char_p, []),
     "mppgpu_version": (C.c_int, []),
@@ -39,6 +44,7 @@ _SIGS = {
     "mppgpu_step_dt_async": (C.c_int, [C.c_void_p, C.c_double, C.c_int]),
     "mppgpu_step_result": (C.c_int, [C.c_void_p, c_ip, c_ip]),
     "mppgpu_post_step_dt": (C.c_int, [C.c_void_p]),
+    "mppgpu_vsfm_coupled_step": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.c_int, C.POINTER(Xfer), C.c_int, C.POINTER(Xfer), C.c_int, c_ip, c_ip]),
     "mppgpu_get_column_stats": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_ip]),
     "mppgpu_vsfm_mass_balance": (C.c_int, [C.c_void_p, C.c_double, c_dp, c_dp]),
     "mppgpu_reduction_buffer_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),

@@ -12,6 +12,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -63,6 +64,8 @@ struct mppgpu_soe {
   int soe_itype, ncol, nlev, device;
   size_t ncells;
   cudaStream_t stream = nullptr; bool own_stream = true;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;      // coupled-step pipeline
+  std::vector<cudaEvent_t> ev_in, ev_comp; cudaEvent_t ev_out_done = nullptr, ev_start = nullptr;
   long long launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   float last_ms = 0.f;
@@ -256,6 +259,12 @@ extern "C" int mppgpu_destroy(mppgpu_handle h)
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  for (auto e : h->ev_in) cudaEventDestroy(e);
+  for (auto e : h->ev_comp) cudaEventDestroy(e);
+  if (h->ev_out_done) cudaEventDestroy(h->ev_out_done);
+  if (h->ev_start) cudaEventDestroy(h->ev_start);
+  if (h->copy_in) cudaStreamDestroy(h->copy_in);
+  if (h->copy_out) cudaStreamDestroy(h->copy_out);
   if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -570,15 +579,6 @@ static int vsfm_fill_args(mppgpu_soe *h, VsfmArgs &A, double dt)
   return 0;
 }
 
-template <int GROUP>
-static void launch_vsfm_fast(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
-{
-  const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
-  if (sf == SATFUNC_VG)      vsfm_step_kernel<GROUP, SATFUNC_VG><<<nblocks, 128, 0, h->stream>>>(A);
-  else if (sf == SATFUNC_BC) vsfm_step_kernel<GROUP, SATFUNC_BC><<<nblocks, 128, 0, h->stream>>>(A);
-  else                       vsfm_step_kernel<GROUP, SATFUNC_SBC><<<nblocks, 128, 0, h->stream>>>(A);
-}
-
 template <int LPC>
 static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 {
@@ -590,45 +590,86 @@ static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 #undef MPP_L2
 }
 
-static int vsfm_step(mppgpu_soe *h, double dt)
+// shift every per-cell / per-column pointer of A to the sub-batch [col0, col0 + n)
+static void vsfm_offset_args(VsfmArgs &A, int nlev, long long col0, int n, long long block0)
+{
+  const long long c = col0 * nlev;
+  const double **cellp[] = {&A.por, &A.perm, &A.sat_res, &A.alpha, &A.lam, &A.vgn, &A.pu, &A.ps, &A.b2, &A.b3, &A.dz, &A.frac_liq, &A.x_in};
+  for (auto pp : cellp) if (*pp) *pp += c;
+  double **cellw[] = {&A.x_out, &A.liq_sat, &A.pressure, &A.mass, &A.smp};
+  for (auto pp : cellw) if (*pp) *pp += c;
+  A.area += col0; if (A.active) A.active += col0;
+  for (int k = 0; k < A.nss; ++k) A.ss[k].value += (A.ss[k].region == REGION_CELLS) ? c : col0;
+  for (int k = 0; k < A.nbc; ++k) { A.bc[k].value += col0; A.bc[k].flux += col0; A.bc[k].mass_exc += col0; }
+  A.stat_its += col0; A.stat_reason += col0; A.stat_cuts += col0; A.stat_nf += col0;
+  A.col_mass += col0; A.col_err += col0; A.col_src += col0;
+  A.block_partials += block0 * 9;
+  A.ncol = n;
+}
+
+static int vsfm_blocks_for(mppgpu_soe *h, long long ncol)
+{
+  const int nlev = h->nlev;
+  if (nlev <= 32) return nblk(ncol * ((nlev <= 16) ? 8 : 16), 128);
+  return nblk(ncol, VSFM_GENERIC_WARPS);
+}
+
+// launch the step kernel on columns [col0, col0 + n) (A holds whole-batch pointers); partials go to blocks [block0, ...)
+static int vsfm_launch_range(mppgpu_soe *h, const VsfmArgs &A0, long long col0, int n, long long block0, cudaStream_t s)
+{
+  VsfmArgs A = A0;
+  vsfm_offset_args(A, h->nlev, col0, n, block0);
+  const int nlev = h->nlev, nblocks = vsfm_blocks_for(h, n);
+  cudaStream_t keep = h->stream; h->stream = s;
+  if (nlev <= 16)      launch_vsfm2<8>(h, A, nblocks);
+  else if (nlev <= 32) launch_vsfm2<16>(h, A, nblocks);
+  else {
+    const size_t smem = vsfm_generic_smem_bytes(nlev);
+    if (smem > 200 * 1024) { h->stream = keep; return fail("mppgpu_step_dt: nlev = %d exceeds the generic kernel's shared-memory budget", nlev); }
+    CK(cudaFuncSetAttribute(vsfm_step_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vsfm_step_generic_kernel<<<nblocks, 32 * VSFM_GENERIC_WARPS, smem, s>>>(A, h->satfunc_name == 0 ? SATFUNC_VG : (h->satfunc_name == 1 ? SATFUNC_BC : SATFUNC_SBC));
+  }
+  h->stream = keep;
+  CK(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
+static int vsfm_prepare_step(mppgpu_soe *h, double dt, VsfmArgs &A)
 {
   if (!h->mesh_set || !h->soils_set) return fail("mppgpu_step_dt: mesh and soils must be set first");
   if (!(dt > 0.0)) return fail("mppgpu_step_dt: dt must be positive");
-  VsfmArgs A;
   vsfm_fill_args(h, A, dt);
   // soln == soln_prev at entry; write to the spare buffer if the current one is the committed (soln_prev_clm) copy
   A.x_in = h->x_current;
   double *spare = (h->x_committed == h->xA.p) ? h->xB.p : h->xA.p;
   A.x_out = (h->x_current == h->x_committed) ? spare : h->x_current;
-  int nblocks;
-  const int nlev = h->nlev;
-  static const bool old_kernel = (getenv("MPPGPU_VSFM_V2") != nullptr);     // A/B switch for kernel development only
-  if (nlev <= 32) {
-    const int group = (nlev <= 16) ? 16 : 32;
-    nblocks = nblk((long long)h->ncol * (old_kernel ? group : group / 2), 128);
-  } else {
-    nblocks = nblk((long long)h->ncol, VSFM_GENERIC_WARPS);
-  }
-  if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
-  A.block_partials = h->block_partials.p;
-  CK(cudaEventRecord(h->ev0, h->stream));
-  if (nlev <= 16)      { if (old_kernel) launch_vsfm_fast<16>(h, A, nblocks); else launch_vsfm2<8>(h, A, nblocks); }
-  else if (nlev <= 32) { if (old_kernel) launch_vsfm_fast<32>(h, A, nblocks); else launch_vsfm2<16>(h, A, nblocks); }
-  else {
-    const size_t smem = vsfm_generic_smem_bytes(nlev);
-    if (smem > 200 * 1024) return fail("mppgpu_step_dt: nlev = %d exceeds the generic kernel's shared-memory budget", nlev);
-    CK(cudaFuncSetAttribute(vsfm_step_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vsfm_step_generic_kernel<<<nblocks, 32 * VSFM_GENERIC_WARPS, smem, h->stream>>>(A, h->satfunc_name == 0 ? SATFUNC_VG : (h->satfunc_name == 1 ? SATFUNC_BC : SATFUNC_SBC));
-  }
-  CK(cudaGetLastError());
+  return 0;
+}
+
+static int vsfm_finish_step(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
+{
   reduce_partials_kernel<<<nblocks < REDUCE_BLOCKS ? 1 : REDUCE_BLOCKS, 256, 0, h->stream>>>(h->block_partials.p, nblocks, h->red_scratch.p, h->red_counter.p, h->red_out.p);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev1, h->stream));
-  h->launches += 2;
+  h->launches += 1;
   h->x_current = A.x_out;
   h->nblocks_last = nblocks;
   CK(cudaMemcpyAsync(h->h_red, h->red_out.p, 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   h->result_pending = true;
+  return 0;
+}
+
+static int vsfm_step(mppgpu_soe *h, double dt)
+{
+  VsfmArgs A;
+  if (vsfm_prepare_step(h, dt, A)) return 1;
+  const int nblocks = vsfm_blocks_for(h, h->ncol);
+  if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
+  A.block_partials = h->block_partials.p;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  if (vsfm_launch_range(h, A, 0, h->ncol, 0, h->stream)) return 1;
+  if (vsfm_finish_step(h, A, nblocks)) return 1;
+  CK(cudaEventRecord(h->ev1, h->stream));
   return 0;
 }
 
@@ -657,6 +698,74 @@ extern "C" int mppgpu_step_result(mppgpu_handle h, int *converged, int *converge
 extern "C" int mppgpu_step_dt(mppgpu_handle h, double dt, int nstep, int *converged, int *converged_reason)
 {
   if (mppgpu_step_dt_async(h, dt, nstep)) return 1;
+  return mppgpu_step_result(h, converged, converged_reason);
+}
+
+// ---- ELM coupling step, pipelined over column chunks -------------------------------------------------------------------
+extern "C" int mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, int nin, const mppgpu_xfer *in, int nout, const mppgpu_xfer *out,
+                                        int nchunks, int *converged, int *converged_reason)
+{
+  CHECK_H(h);
+  (void)nstep;
+  if (h->soe_itype != MPPGPU_SOE_RE_ODE) return fail("mppgpu_vsfm_coupled_step: handle is not a VSFM SoE");
+  if ((nin > 0 && !in) || (nout > 0 && !out) || nin < 0 || nout < 0) return fail("mppgpu_vsfm_coupled_step: bad transfer lists");
+  struct Field { double *dev; size_t per_col; double *host; };
+  std::vector<Field> fin(nin), fout(nout);
+  for (int i = 0; i < nin + nout; ++i) {
+    const bool is_in = i < nin;
+    const mppgpu_xfer &x = is_in ? in[i] : out[i - nin];
+    if (!x.host) return fail("mppgpu_vsfm_coupled_step: null host array");
+    double *p = nullptr; size_t cap = 0;
+    if (vsfm_field(h, x.auxvar_type, x.var_type, x.cond_id, is_in, &p, &cap)) return 1;
+    Field f{p, cap / (size_t)h->ncol, x.host};
+    if (is_in) fin[i] = f; else fout[i - nin] = f;
+  }
+  // VSFMSPreStepDT (SystemOfEquationsVSFMType.F90:892-923)
+  h->x_current = h->x_committed;
+  for (auto *c : h->bcs) CK(cudaMemsetAsync(c->mass_exc.p, 0, c->n * 8, h->stream));
+  VsfmArgs A;
+  if (vsfm_prepare_step(h, dt, A)) return 1;
+  // chunking: whole blocks of the step kernel (16 columns per 128-thread block at nlev <= 16), 16 chunks by default
+  if (nchunks <= 0) nchunks = 16;
+  const long long align = 1024;
+  long long per = ((long long)h->ncol + nchunks - 1) / nchunks;
+  per = ((per + align - 1) / align) * align;
+  nchunks = (int)(((long long)h->ncol + per - 1) / per);
+  long long total_blocks = 0;
+  for (int k = 0; k < nchunks; ++k) total_blocks += vsfm_blocks_for(h, std::min<long long>(per, h->ncol - k * per));
+  if (h->block_partials.n < (size_t)total_blocks * 9) CK(h->block_partials.alloc((size_t)total_blocks * 9));
+  A.block_partials = h->block_partials.p;
+  if (!h->copy_in)  CK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+  if (!h->copy_out) CK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+  if (!h->ev_out_done) { CK(cudaEventCreateWithFlags(&h->ev_out_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming)); }
+  while ((int)h->ev_in.size() < nchunks) {
+    cudaEvent_t a, b; CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    h->ev_in.push_back(a); h->ev_comp.push_back(b);
+  }
+  // the copy streams start after whatever is already queued on the compute stream (earlier steps, PreStepDT memsets)
+  CK(cudaEventRecord(h->ev_start, h->stream));
+  CK(cudaStreamWaitEvent(h->copy_in, h->ev_start, 0));
+  CK(cudaStreamWaitEvent(h->copy_out, h->ev_start, 0));
+  CK(cudaEventRecord(h->ev0, h->stream));
+  long long block0 = 0;
+  for (int k = 0; k < nchunks; ++k) {
+    const long long col0 = k * per; const int n = (int)std::min<long long>(per, h->ncol - col0);
+    for (const Field &f : fin)
+      CK(cudaMemcpyAsync(f.dev + col0 * f.per_col, f.host + col0 * f.per_col, (size_t)n * f.per_col * 8, cudaMemcpyHostToDevice, h->copy_in));
+    CK(cudaEventRecord(h->ev_in[k], h->copy_in));
+    CK(cudaStreamWaitEvent(h->stream, h->ev_in[k], 0));
+    if (vsfm_launch_range(h, A, col0, n, block0, h->stream)) return 1;
+    CK(cudaEventRecord(h->ev_comp[k], h->stream));
+    CK(cudaStreamWaitEvent(h->copy_out, h->ev_comp[k], 0));
+    for (const Field &f : fout)
+      CK(cudaMemcpyAsync(f.host + col0 * f.per_col, f.dev + col0 * f.per_col, (size_t)n * f.per_col * 8, cudaMemcpyDeviceToHost, h->copy_out));
+    block0 += vsfm_blocks_for(h, n);
+  }
+  CK(cudaEventRecord(h->ev_out_done, h->copy_out));
+  if (vsfm_finish_step(h, A, (int)total_blocks)) return 1;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  CK(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));          // later work on the handle's stream sees the host arrays complete
+  CK(cudaStreamSynchronize(h->copy_out));                         // the caller may read its arrays as soon as this returns
   return mppgpu_step_result(h, converged, converged_reason);
 }
 

@@ -12,7 +12,7 @@ import ctypes as C
 import numpy as np
 
 from . import constants as K
-from ._lib import MPPError, c_dp, c_ip, check, lib
+from ._lib import MPPError, Xfer, c_dp, c_ip, check, lib
 
 
 def _f64(a):
@@ -189,6 +189,22 @@ class VSFM(_SoE):
         check(self.L.mppgpu_vsfm_set_soils(self.h, *[_dp(x) for x in t], K.SATFUNC[satfunc_type], int(density_type)))
 
     VSFMMPPSetSoils = set_soils
+
+    def coupled_step(self, dt, nstep, inputs, outputs, nchunks=0):
+        """One ELM coupling step with host buffers, pipelined over column chunks (mppgpu_vsfm_coupled_step):
+        SetDataFromCLM for every (auxvar_type, var_type, cond_id, array) of `inputs`, PreStepDT, StepDT, GetDataForCLM into every
+        array of `outputs`.  Arrays must be C-contiguous float64 (pinned host memory makes the copies asynchronous)."""
+        def pack(items):
+            arr = (Xfer * max(len(items), 1))()
+            for i, (at, vt, cid, a) in enumerate(items):
+                if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                    raise ValueError("coupled_step needs C-contiguous float64 arrays")
+                arr[i] = Xfer(1, int(at), int(vt), int(cid), _dp(a))
+            return arr
+        conv, reason = C.c_int(), C.c_int()
+        check(self.L.mppgpu_vsfm_coupled_step(self.h, float(dt), int(nstep), len(inputs), pack(inputs), len(outputs), pack(outputs),
+                                              int(nchunks), C.byref(conv), C.byref(reason)))
+        return bool(conv.value), reason.value
 
 
 class Thermal(_SoE):

@@ -248,3 +248,27 @@ def test_error_behaviour(mpp):
         p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, cid, np.zeros(5))    # size(data_1d) > nauxvar
     with pytest.raises(mpp.MPPError):
         p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, cid + 1, np.zeros(4))
+
+
+@pytest.mark.parametrize("ncol,nchunks", [(5000, 3), (2048, 0), (100, 8)])
+def test_coupled_step_pipeline_is_bitwise_the_separate_calls(mpp, ncol, nchunks):
+    """mppgpu_vsfm_coupled_step (chunked, three streams) == SetDataFromCLM x7 + PreStepDT + StepDT + GetDataForCLM x4."""
+    d = PB.elm_vsfm_inputs(ncol, 15)
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    q, qids = PB.build_elm_vsfm(mpp.VSFM, d)
+    names = ("infil", "et", "dew", "drain", "snow", "sublim")
+    ins = [(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, qids[n], np.ascontiguousarray(d[n])) for n in names]
+    ins.append((K.AUXVAR_INTERNAL, K.VAR_FRAC_LIQ_SAT, 1, np.ascontiguousarray(d["frac_liq"])))
+    outs = {k: np.zeros(ncol * 15) for k in ("sat", "mass", "smp", "pressure")}
+    olist = [(K.AUXVAR_INTERNAL, v, 1, outs[k]) for k, v in (("sat", K.VAR_LIQ_SAT), ("mass", K.VAR_MASS), ("smp", K.VAR_SOIL_MATRIX_POT), ("pressure", K.VAR_PRESSURE))]
+    for step in range(3):
+        conv, reason, ref = PB.elm_vsfm_step(p, ids, d, 1800.0, step + 1)
+        conv2, reason2 = q.coupled_step(1800.0, step + 1, ins, olist, nchunks)
+        q.post_step_dt()
+        assert conv == conv2 and reason == reason2
+        for k in outs:
+            assert np.array_equal(outs[k], ref[k]), (step, k)
+        sp, sq = p.stats(), q.stats()
+        assert np.array_equal(sp["newton_its"], sq["newton_its"]) and np.array_equal(sp["nfuncs"], sq["nfuncs"])
+        a, b = p.mass_balance(), q.mass_balance()
+        assert np.allclose(a[0], b[0], rtol=1e-13) and np.array_equal(a[1], b[1])

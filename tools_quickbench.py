@@ -18,6 +18,19 @@ if mode == "vsfm":
     st = p.stats()
     print(os.environ.get("MPPGPU_LIB_PATH", "default"), "vsfm ncol", ncol, "ms/step", ["%.2f" % m for m in ms], "col-steps/s %.3e" % (ncol / (np.mean(ms[3:]) * 1e-3)),
           "its mean %.2f nf mean %.2f" % (st["newton_its"].mean(), st["nfuncs"].mean()))
+elif mode == "th":
+    dens = K.DENSITY_IFC67 if (len(sys.argv) > 3 and sys.argv[3] == "ifc67") else K.DENSITY_TGDPB01
+    iee = K.INT_ENERGY_ENTHALPY_IFC67 if dens == K.DENSITY_IFC67 else K.INT_ENERGY_ENTHALPY_CONSTANT
+    d = PB.elm_th_inputs(ncol, 15, density_type=dens, iee_type=iee)
+    p, ids = PB.build_elm_th(mpp_b200.TH, d)
+    ms = []
+    for s in range(6):
+        conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, s + 1)
+        ms.append(p.last_step_ms())
+    st = p.stats()
+    m = float(np.mean(ms[2:]))
+    print("th ncol", ncol, "dens", dens, "ms/step", ["%.2f" % x for x in ms], "col-steps/s %.3e" % (ncol / (m * 1e-3)),
+          "alg GB/s (1824 B/col) %.0f" % (1824 * ncol / (m * 1e-3) / 1e9), "its mean %.2f nf mean %.2f conv %s" % (st["newton_its"].mean(), st["nfuncs"].mean(), conv))
 else:
     d = PB.elm_thermal_inputs(ncol, 15)
     p, ids = PB.build_elm_thermal(mpp_b200.Thermal, d)
