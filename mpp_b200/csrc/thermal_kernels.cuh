@@ -55,66 +55,71 @@ __device__ __forceinline__ void thermal_auxvar(const ThermalArgs &A, int itype, 
   if (itype == A.istsoil || itype == A.istcrop) {
     if (shallow) {
       const double l = liq * (1.0 / DENH2O), i = ice * (1.0 / DENICE);      // water / ice depth [m]
-      double satw = (l + i) / (dz * por);
-      satw = fmin(1.0, satw);
-      if (satw > (double).1e-6f) {
-        const double dke = (T >= TFRZ) ? fmax(0.0, log10(satw) + 1.0) : satw;
-        const double fl = l / (l + i);                                        // the reference's common 1/dz cancels
-        // tkmg * tkwat^(fl por) * tkice^((1-fl) por)
-        const double dksat = tkmg * exp(por * (fl * LN_TKWAT + (1.0 - fl) * LN_TKICE));
-        tk = dke * dksat + (1.0 - dke) * tkdry;
-      } else {
-        tk = tkdry;
-      }
+      double satw = (l + i) * rcp(dz * por);
+      satw = (satw < 1.0) ? satw : 1.0;
+      // branch-free with the lean log / exp / reciprocal of physics.cuh (arguments are positive and normal; a dry cell
+      // evaluates them at 1 and discards the result): dke = max(0, log10(satw) + 1) unfrozen, satw frozen
+      const bool wet = satw > (double).1e-6f;
+      const double sw = wet ? satw : 1.0, li = wet ? (l + i) : 1.0;
+      const double lg = mpp_log(sw) * 0.43429448190325182765 + 1.0;
+      const double dke = (T >= TFRZ) ? ((lg > 0.0) ? lg : 0.0) : sw;
+      const double fl = l * rcp(li);                                        // the reference's common 1/dz cancels
+      // tkmg * tkwat^(fl por) * tkice^((1-fl) por)
+      const double dksat = tkmg * mpp_exp(por * (fl * LN_TKWAT + (1.0 - fl) * LN_TKICE));
+      tk = wet ? dke * dksat + (1.0 - dke) * tkdry : tkdry;
       hc = csol * (1.0 - por) * dz + ice * CPICE + liq * CPLIQ;
       if (nsnow == 0) hc = hc + snoww * CPICE;
     } else {
       tk = THK_BEDROCK;
       hc = csol * (1.0 - por) * dz + ice * CPICE + liq * CPLIQ;
     }
-    hc = hc / dz;
+    hc = hc * rcp(dz);
   } else if (itype == A.istwet) {
     if (shallow) {
       tk = (T < TFRZ) ? TKICE : TKWAT;
       hc = ice * CPICE + liq * CPLIQ;
       if (nsnow == 0) hc = hc + snoww * CPICE;
-      hc = hc / dz;
+      hc = hc * rcp(dz);
     } else { tk = THK_BEDROCK; hc = csol; }
   } else if (itype == A.istice || itype == A.istice_mec) {
     tk = (T < TFRZ) ? TKICE : TKWAT;
     hc = ice * CPICE + liq * CPLIQ;
     if (nsnow == 0) hc = hc + snoww * CPICE;
-    hc = hc / dz;
+    hc = hc * rcp(dz);
   }
 }
 
-// Parallel cyclic reduction across a GROUP-lane group (one tridiagonal row per lane, identity rows pad the group).
+// Parallel cyclic reduction across a GROUP-lane group (one tridiagonal row per lane, identity rows pad the group), rows
+// kept in normalised form (unit diagonal): 3 shuffled doubles per side per stage, one lean reciprocal per stage.
 template <int GROUP>
 __device__ __forceinline__ double thermal_pcr(double a, double b, double c, double d)
 {
   constexpr unsigned FULL = 0xffffffffu;
+  double r = rcp(b);
+  double al = a * r, ga = c * r, de = d * r;
 #pragma unroll
   for (int s = 1; s < GROUP; s <<= 1) {
-    const double r   = __drcp_rn(b);
-    const double a_m = __shfl_up_sync(FULL, a, s, GROUP),   c_m = __shfl_up_sync(FULL, c, s, GROUP);
-    const double d_m = __shfl_up_sync(FULL, d, s, GROUP),   r_m = __shfl_up_sync(FULL, r, s, GROUP);
-    const double a_p = __shfl_down_sync(FULL, a, s, GROUP), c_p = __shfl_down_sync(FULL, c, s, GROUP);
-    const double d_p = __shfl_down_sync(FULL, d, s, GROUP), r_p = __shfl_down_sync(FULL, r, s, GROUP);
-    const double k1 = a * r_m, k2 = c * r_p;
-    b = b - c_m * k1 - a_p * k2;
-    d = d - d_m * k1 - d_p * k2;
-    a = -a_m * k1;
-    c = -c_p * k2;
+    const double al_m = __shfl_up_sync(FULL, al, s, GROUP),   ga_m = __shfl_up_sync(FULL, ga, s, GROUP);
+    const double de_m = __shfl_up_sync(FULL, de, s, GROUP);
+    const double al_p = __shfl_down_sync(FULL, al, s, GROUP), ga_p = __shfl_down_sync(FULL, ga, s, GROUP);
+    const double de_p = __shfl_down_sync(FULL, de, s, GROUP);
+    r  = rcp(1.0 - al * ga_m - ga * al_p);
+    de = (de - al * de_m - ga * de_p) * r;
+    al = (-al * al_m) * r;
+    ga = (-ga * ga_p) * r;
   }
-  return d * __drcp_rn(b);
+  return de;
 }
 
 // One lane per soil cell, GROUP lanes per column: every array is streamed once in the reference's cell order
 // (fully coalesced), neighbour layers come from warp shuffles, the tridiagonal system is solved in registers by
 // parallel cyclic reduction, and the new temperature goes straight back to HBM.  No shared memory, no block
 // barriers: occupancy is bounded by registers only, which is what hides the HBM latency.
+#ifndef THERMAL_MIN_BLOCKS
+#define THERMAL_MIN_BLOCKS 8
+#endif
 template <int GROUP>
-__global__ void __launch_bounds__(TH_TILE)
+__global__ void __launch_bounds__(TH_TILE, THERMAL_MIN_BLOCKS)
 thermal_step_kernel(const ThermalArgs A)
 {
   constexpr unsigned FULL = 0xffffffffu;
@@ -127,9 +132,24 @@ thermal_step_kernel(const ThermalArgs A)
   const long long cell = (long long)col * nlev + j;
 
   double T = 0.0, tk = 1.0, hc = 0.0, dz = 1.0, area = 1.0, tf = 1.0, du = 0.5, dd = 0.5;
+  double ssv[TH_MAX_SS], bcH[2], bcdH[2], bcfr[2];
   int act = 0;
+#pragma unroll
+  for (int k = 0; k < TH_MAX_SS; ++k) ssv[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) { bcH[k] = 0.0; bcdH[k] = 0.0; bcfr[k] = 0.0; }
   if (valid) {
     T = A.T_in[cell]; dz = A.dz[cell]; area = A.area[col]; tf = A.tuning[cell]; act = A.active[cell];
+    // condition values: issued with the other loads, consumed after the aux-var math
+#pragma unroll
+    for (int k = 0; k < TH_MAX_SS; ++k) if (k < A.nss) {
+      if (A.ss_region[k] == 403) ssv[k] = A.ss_value[k][cell];
+      else if (j == (A.ss_region[k] == 401 ? jtop : jbot)) ssv[k] = A.ss_value[k][col];
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) if (A.bc_type[k] == 507 && j == (k == 0 ? jtop : jbot)) {
+      bcH[k] = A.bc_value[k][col]; bcdH[k] = A.bc_dhsdT[k][col]; bcfr[k] = A.bc_frac[k][col];
+    }
     const double liq = A.liq[cell], ice = A.ice[cell], snoww = A.snow_water[cell];
     const double por = A.por[cell], tkmg = A.tkmg[cell], tkdry = A.tkdry[cell], csol = A.csol[cell];
     const int nsnow = A.nsnow[cell];
@@ -146,13 +166,13 @@ thermal_step_kernel(const ThermalArgs A)
   double cval = 0.0, flux = 0.0;
   if (valid && j < nlev - 1 && act && act_d) {
     // kav / dist with kav the distance-weighted harmonic mean: tk tk_d (du+dd) / (tk dd + tk_d du) / (du+dd)
-    const double kod = tk * tk_d / (tk * dd + tk_d * du) * area;
+    const double kod = tk * tk_d * rcp(tk * dd + tk_d * du) * area;
     flux = -kod * (T - T_d);                                               // DiffHeatFlux * area  (:976-1003)
     cval = (1.0 - cnfac) * kod;                                            // ComputeOperatorsDiag (:1112)
   }
   const double cval_m = __shfl_up_sync(FULL, cval, 1, GROUP), flux_m = __shfl_up_sync(FULL, flux, 1, GROUP);
   double bb, rhs;
-  if (act) { bb = hc * vol / (dt * tf); rhs = bb * T; } else { bb = 1.0; rhs = 0.0; }
+  if (act) { bb = hc * vol * rcp(dt * tf); rhs = bb * T; } else { bb = 1.0; rhs = 0.0; }
   rhs = rhs + cnfac * flux; bb += cval;
   if (j > 0) { rhs = rhs - cnfac * flux_m; bb += cval_m; }
   if (valid && act) {
@@ -160,7 +180,7 @@ thermal_step_kernel(const ThermalArgs A)
     for (int k = 0; k < 2; ++k) {
       if (A.bc_type[k] == 0 || j != (k == 0 ? jtop : jbot)) continue;
       if (A.bc_type[k] == 507) {                    // COND_HEAT_FLUX: value = H - dH/dT * T_cell (GoveqnThermalKSP...:344-348)
-        const double H = A.bc_value[k][col], dH = A.bc_dhsdT[k][col], fr = A.bc_frac[k][col];
+        const double H = bcH[k], dH = bcdH[k], fr = bcfr[k];
         rhs = rhs + (H - dH * T) * fr * area;
         bb += -fr * ((area == 1.0) ? dH : pow(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
       } else if (A.bc_active[k][col] != 0.0) {      // COND_DIRICHLET
@@ -174,10 +194,8 @@ thermal_step_kernel(const ThermalArgs A)
         bb += A.bc_frac[k][col] * (1.0 - cnfac) * kav / dist * area;
       }
     }
-    for (int k = 0; k < A.nss; ++k) {               // COND_HEAT_RATE
-      if (A.ss_region[k] == 403) rhs = rhs + A.ss_value[k][cell];
-      else if (j == (A.ss_region[k] == 401 ? jtop : jbot)) rhs = rhs + A.ss_value[k][col];
-    }
+#pragma unroll
+    for (int k = 0; k < TH_MAX_SS; ++k) rhs = rhs + ssv[k];      // COND_HEAT_RATE (zero where the condition does not touch this cell)
   }
   if (!valid) { bb = 1.0; rhs = 0.0; }
   // symmetric tridiagonal row: a_j = -cval_{j-1}, c_j = -cval_j   (KSPSolve: exact for a tridiagonal matrix)
