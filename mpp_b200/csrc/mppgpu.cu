@@ -23,6 +23,7 @@
 #include "vsfm_generic_kernel.cuh"
 #include "thermal_kernels.cuh"
 #include "th_kernels.cuh"
+#include "th_kernels2.cuh"
 
 using namespace mpp;
 

@@ -157,15 +157,29 @@ static int th_fill_args(mppgpu_soe *h, THState *t, THArgs &A, double dt)
   return 0;
 }
 
+// nlev <= 16: lane-per-cell register kernel (th_kernels2.cuh); taller columns: one warp per column out of shared memory
 static int th_launch(mppgpu_soe *h, THState *, THArgs &A, int *nblocks_out)
 {
-  const int nblocks = h->ncol;                       // generic kernel: one warp (= one block) per column
-  if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
-  A.block_partials = h->block_partials.p;
-  const size_t smem = (size_t)TH_NARR * h->nlev * sizeof(double);
-  if (smem > 200 * 1024) return fail("mppgpu_step_dt: nlev = %d exceeds the TH kernel's shared-memory budget", h->nlev);
-  CK(cudaFuncSetAttribute(th_step_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  th_step_generic_kernel<<<nblocks, 32, smem, h->stream>>>(A);
+  const bool fast = h->nlev <= 16;
+  const int nblocks = fast ? nblk((long long)h->ncol * 16, 128) : h->ncol;
+  if (!A.eval_x) {
+    if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
+    A.block_partials = h->block_partials.p;
+  }
+  if (fast) {
+    // the two model combinations the reference's drivers use get compile-time specialisations; anything else dispatches at run time
+    if (A.satfunc == SATFUNC_VG && A.density_type == DENSITY_TGDPB01 && A.iee_type == INT_ENERGY_ENTHALPY_CONSTANT)
+      th_step2_kernel<16, SATFUNC_VG, DENSITY_TGDPB01, INT_ENERGY_ENTHALPY_CONSTANT><<<nblocks, 128, 0, h->stream>>>(A);
+    else if (A.satfunc == SATFUNC_VG && A.density_type == DENSITY_IFC67 && A.iee_type == INT_ENERGY_ENTHALPY_IFC67)
+      th_step2_kernel<16, SATFUNC_VG, DENSITY_IFC67, INT_ENERGY_ENTHALPY_IFC67><<<nblocks, 128, 0, h->stream>>>(A);
+    else
+      th_step2_kernel<16, -1, -1, -1><<<nblocks, 128, 0, h->stream>>>(A);
+  } else {
+    const size_t smem = (size_t)TH_NARR * h->nlev * sizeof(double);
+    if (smem > 200 * 1024) return fail("mppgpu_step_dt: nlev = %d exceeds the TH kernel's shared-memory budget", h->nlev);
+    CK(cudaFuncSetAttribute(th_step_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    th_step_generic_kernel<<<nblocks, 32, smem, h->stream>>>(A);
+  }
   CK(cudaGetLastError());
   *nblocks_out = nblocks;
   return 0;
@@ -205,10 +219,8 @@ static int th_eval(mppgpu_soe *h, THState *t, double dt, const double *x_prev, c
   if (th_fill_args(h, t, A, dt)) return 1;
   A.x_in = dxp.p; A.x_out = nullptr;
   A.eval_x = dx.p; A.eval_f = df.p; A.eval_ja = da.p; A.eval_jb = db.p; A.eval_jc = dc.p;
-  const size_t smem = (size_t)TH_NARR * h->nlev * sizeof(double);
-  CK(cudaFuncSetAttribute(th_step_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  th_step_generic_kernel<<<h->ncol, 32, smem, h->stream>>>(A);
-  CK(cudaGetLastError());
+  int nb = 0;
+  if (th_launch(h, t, A, &nb)) return 1;
   h->launches += 1;
   CK(cudaMemcpyAsync(f, df.p, 2 * N * 8, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaMemcpyAsync(ja, da.p, 4 * N * 8, cudaMemcpyDeviceToHost, h->stream));

@@ -50,21 +50,26 @@ struct THCell {      // aux vars of one cell at one state (both governing equati
   double ul, hl, dulT, dhlT, dulP, dhlP, tc, dtcP;
 };
 
+// SF / DT / IEE >= 0: saturation function, density and enthalpy models fixed at compile time (no dispatch branches, so the
+// independent chains -- curves, two densities, enthalpy -- share one basic block and overlap); -1: read from A at run time.
+template <int SF = -1, int DT = -1, int IEE = -1>
 __device__ __forceinline__ void th_cell_compute(const THArgs &A, const SatParams &sp, double tkdry, double P, double T, THCell &c)
 {
+  const int dtype = (DT >= 0) ? DT : A.density_type, itype = (IEE >= 0) ? IEE : A.iee_type;
   SatState st;
-  sat_values_rt(A.satfunc, sp, P, 1.0, st);
-  sat_derivs_rt(A.satfunc, sp, st, 1.0, c.dsat, c.dkr);
+  if (SF >= 0) { sat_values<(SF >= 0 ? SF : 0)>(sp, P, 1.0, st); sat_derivs<(SF >= 0 ? SF : 0)>(sp, st, 1.0, c.dsat, c.dkr); }
+  else { sat_values_rt(A.satfunc, sp, P, 1.0, st); sat_derivs_rt(A.satfunc, sp, st, 1.0, c.dsat, c.dkr); }
   c.sat = st.sat; c.kr = st.kr;
-  density(A.density_type, P, T, c.den_m, c.ddenP_m, c.ddenT_m);
+  density(dtype, P, T, c.den_m, c.ddenP_m, c.ddenT_m);
   const double Pe = (P < PRESSURE_REF) ? PRESSURE_REF : P;                 // ThermalEnthalpySoilAuxType.F90:251-252
-  density(A.density_type, Pe, T, c.den_e, c.ddenP_e, c.ddenT_e);
-  internal_energy_enthalpy(A.iee_type, Pe, T, c.den_e * FMWH2O, c.ddenT_e * FMWH2O, c.ddenP_e * FMWH2O,
+  density(dtype, Pe, T, c.den_e, c.ddenP_e, c.ddenT_e);
+  internal_energy_enthalpy(itype, Pe, T, c.den_e * FMWH2O, c.ddenT_e * FMWH2O, c.ddenP_e * FMWH2O,
                            c.ul, c.hl, c.dulT, c.dhlT, c.dulP, c.dhlP);
   const double therm_alpha = 0.45, wet = 1.3;                              // MultiPhysicsProbTH.F90:331-332
-  const double L = log(c.sat + 1.e-6);
-  const double Kel = exp(therm_alpha * L);
-  const double dKel = therm_alpha * exp((therm_alpha - 1.0) * L) * c.dsat;
+  // Kel = (sat + 1e-6)^alpha, dKel/dP = alpha (sat + 1e-6)^(alpha - 1) dsat/dP   (ThermalEnthalpySoilAuxType.F90:269-275)
+  const double se = c.sat + 1.e-6;
+  const double Kel = mpp_exp(therm_alpha * mpp_log(se));
+  const double dKel = therm_alpha * Kel * rcp(se) * c.dsat;
   c.tc = wet * Kel + tkdry * (1.0 - Kel);
   c.dtcP = (wet - tkdry) * dKel;
 }
