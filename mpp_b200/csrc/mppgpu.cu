@@ -585,8 +585,8 @@ static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 {
   const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
   const bool bc = A.nbc > 0;
-#define MPP_L2(SF) do { if (bc) vsfm_step2_kernel<LPC, SF, true><<<nblocks, 128, 0, h->stream>>>(A); \
-                        else    vsfm_step2_kernel<LPC, SF, false><<<nblocks, 128, 0, h->stream>>>(A); } while (0)
+#define MPP_L2(SF) do { if (bc) vsfm_step2_kernel<LPC, SF, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
+                        else    vsfm_step2_kernel<LPC, SF, false><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); } while (0)
   if (sf == SATFUNC_VG) MPP_L2(SATFUNC_VG); else if (sf == SATFUNC_BC) MPP_L2(SATFUNC_BC); else MPP_L2(SATFUNC_SBC);
 #undef MPP_L2
 }
@@ -611,7 +611,7 @@ static void vsfm_offset_args(VsfmArgs &A, int nlev, long long col0, int n, long 
 static int vsfm_blocks_for(mppgpu_soe *h, long long ncol)
 {
   const int nlev = h->nlev;
-  if (nlev <= 32) return nblk(ncol * ((nlev <= 16) ? 8 : 16), 128);
+  if (nlev <= 32) return nblk(ncol * ((nlev <= 16) ? 8 : 16), VSFM2_THREADS);
   return nblk(ncol, VSFM_GENERIC_WARPS);
 }
 

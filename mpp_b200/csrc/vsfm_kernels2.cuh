@@ -27,8 +27,14 @@
 
 namespace mpp {
 
+// Threads per block and resident blocks per SM.  A block cannot retire before its slowest column has converged, and the
+// iteration counts have a long tail (mean 3.4, max 40+), so small blocks matter: with one warp per block a finished warp
+// frees its registers at once instead of idling next to a straggler.
+#ifndef VSFM2_THREADS
+#define VSFM2_THREADS 32
+#endif
 #ifndef VSFM2_MIN_BLOCKS
-#define VSFM2_MIN_BLOCKS 3
+#define VSFM2_MIN_BLOCKS 12
 #endif
 
 template <int LPC>
@@ -59,34 +65,55 @@ __device__ __forceinline__ double pcr_unit_diag(double al, double ga, double de)
   return de;
 }
 
-// static data and Newton state of one soil cell, all in registers
+// Newton state of one soil cell (registers).  Its static data -- curve parameters, porosity, volume, net source, the
+// connection to the next cell (upwind weight, Dq, gravity factor: MeshType.F90:509-530; RichardsMod.F90:257-259, 279-285)
+// -- and the two values that change only once per sub-step (soln_prev, accumulation at soln_prev) are parked in shared
+// memory, [field][thread] (conflict-free), and re-read where they are used: 48 registers less of persistent state per
+// lane, which the register allocator spends on overlapping the two cells' dependency chains instead of spilling
+// (154 registers, no spills, 12 one-warp blocks per SM; forcing 128 registers for 16 warps serialises the chains again
+// and ends up no faster -- occupancy sweep in profiles/r1_vsfm_occupancy.md).
 template <int SATFUNC>
 struct Cell2 {
-  SatParams sp;
-  double por, vol, frac_liq, src;
-  double upw, Dq, gfac;            // connection this cell -> next cell (MeshType.F90:509-530; RichardsMod.F90:257-259, 279-285)
-  double X, Xprev, F, Y, W, accum_prev;
+  double X, F, Y, W;
   double kr, dkr, sat, dsat;       // aux vars at the accepted iterate X
   bool valid, has_conn;
 };
+enum { PI_SATRES, PI_ALPHA, PI_M, PI_N, PI_POR, PI_VOL, PI_SRC, PI_UPW, PI_DQ, PI_GFAC, PI_XPREV, PI_ACCP, PI_FLIQ, PI_PU, PI_PS, PI_B2, PI_B3 };
+template <int SATFUNC> struct ParCount { static constexpr int value = (SATFUNC == SATFUNC_VG) ? 12 : (SATFUNC == SATFUNC_BC ? 13 : 17); };
 
 template <int SATFUNC>
-__device__ __forceinline__ void cell_load(const VsfmArgs &A, Cell2<SATFUNC> &c, bool valid, long long cell, double area, double &perm, double &dz)
+__device__ __forceinline__ void cell_load(const VsfmArgs &A, Cell2<SATFUNC> &c, double (*par)[VSFM2_THREADS], bool valid, long long cell, double area, double &perm, double &dz)
 {
+  const int t = threadIdx.x;
   c.valid = valid;
-  c.sp.sat_res = 0.0; c.sp.alpha = 1.0; c.sp.m = 0.5; c.sp.n = 2.0; c.sp.pu = c.sp.ps = c.sp.b2 = c.sp.b3 = 0.0;
-  c.por = 0.0; c.frac_liq = 1.0; c.X = PRESSURE_REF; perm = 1.0; dz = 1.0;
+  double sat_res = 0.0, alpha = 1.0, m = 0.5, n = 2.0, pu = 0.0, ps = 0.0, b2 = 0.0, b3 = 0.0, por = 0.0, fl = 1.0;
+  c.X = PRESSURE_REF; perm = 1.0; dz = 1.0;
   if (valid) {
-    c.por = A.por[cell]; perm = A.perm[cell]; dz = A.dz[cell];
-    c.sp.sat_res = A.sat_res[cell]; c.sp.alpha = A.alpha[cell]; c.sp.m = A.lam[cell];
-    if (SATFUNC == SATFUNC_VG)  c.sp.n = A.vgn[cell];
-    if (SATFUNC == SATFUNC_SBC) { c.sp.pu = A.pu[cell]; c.sp.ps = A.ps[cell]; c.sp.b2 = A.b2[cell]; c.sp.b3 = A.b3[cell]; }
-    if (SATFUNC != SATFUNC_VG)  c.frac_liq = A.frac_liq[cell];      // only the Brooks-Corey k_r reads it (SaturationFunction.F90:987)
+    por = A.por[cell]; perm = A.perm[cell]; dz = A.dz[cell];
+    sat_res = A.sat_res[cell]; alpha = A.alpha[cell]; m = A.lam[cell];
+    if (SATFUNC == SATFUNC_VG)  n = A.vgn[cell];
+    if (SATFUNC == SATFUNC_SBC) { pu = A.pu[cell]; ps = A.ps[cell]; b2 = A.b2[cell]; b3 = A.b3[cell]; }
+    if (SATFUNC != SATFUNC_VG)  fl = A.frac_liq[cell];            // only the Brooks-Corey k_r reads it (SaturationFunction.F90:987)
     c.X = A.x_in[cell];
   }
-  c.vol = area * dz;                                                // MeshType.F90:427
-  c.Xprev = c.X; c.W = c.X; c.F = 0.0; c.Y = 0.0; c.accum_prev = 0.0; c.src = 0.0;
+  par[PI_SATRES][t] = sat_res; par[PI_ALPHA][t] = alpha; par[PI_M][t] = m; par[PI_N][t] = n;
+  par[PI_POR][t] = por; par[PI_VOL][t] = area * dz;               // MeshType.F90:427
+  par[PI_SRC][t] = 0.0; par[PI_XPREV][t] = c.X; par[PI_ACCP][t] = 0.0;
+  if (SATFUNC != SATFUNC_VG)  par[PI_FLIQ][t] = fl;
+  if (SATFUNC == SATFUNC_SBC) { par[PI_PU][t] = pu; par[PI_PS][t] = ps; par[PI_B2][t] = b2; par[PI_B3][t] = b3; }
+  c.W = c.X; c.F = 0.0; c.Y = 0.0;
   c.kr = 1.0; c.dkr = 0.0; c.sat = 1.0; c.dsat = 0.0;
+}
+
+template <int SATFUNC>
+__device__ __forceinline__ SatParams par_sp(double (*par)[VSFM2_THREADS])
+{
+  const int t = threadIdx.x;
+  SatParams sp;
+  sp.sat_res = par[PI_SATRES][t]; sp.alpha = par[PI_ALPHA][t]; sp.m = par[PI_M][t]; sp.n = par[PI_N][t];
+  sp.pu = sp.ps = sp.b2 = sp.b3 = 0.0;
+  if (SATFUNC == SATFUNC_SBC) { sp.pu = par[PI_PU][t]; sp.ps = par[PI_PS][t]; sp.b2 = par[PI_B2][t]; sp.b3 = par[PI_B3][t]; }
+  return sp;
 }
 
 __device__ __forceinline__ void conn_setup(double perm_up, double dz_up, double perm_dn, double dz_dn, double uz, double &upw, double &Dq, double &gfac)
@@ -130,7 +157,7 @@ __device__ __forceinline__ void rich_flux_deriv(double P_u, double kr_u, double 
 }
 
 template <int LPC, int SATFUNC, bool HAS_BC>
-__global__ void __launch_bounds__(128, VSFM2_MIN_BLOCKS)
+__global__ void __launch_bounds__(VSFM2_THREADS, VSFM2_MIN_BLOCKS)
 vsfm_step2_kernel(const VsfmArgs A)
 {
   constexpr unsigned FULL = FULL_MASK;
@@ -147,16 +174,22 @@ vsfm_step2_kernel(const VsfmArgs A)
   const double area = col_ok ? A.area[col] : 1.0;
 
   // ---- static per-cell data -----------------------------------------------------------------------
+  __shared__ double s_par[2][ParCount<SATFUNC>::value][VSFM2_THREADS];
+  double (*const pa)[VSFM2_THREADS] = s_par[0], (*const pb)[VSFM2_THREADS] = s_par[1];
+  const int tx = threadIdx.x;
+#define PA(i) pa[i][tx]
+#define PB(i) pb[i][tx]
   Cell2<SATFUNC> a, b;
   double perm0, dz0, perm1, dz1;
-  cell_load<SATFUNC>(A, a, col_ok && j0 < nlev, cell0, area, perm0, dz0);
-  cell_load<SATFUNC>(A, b, col_ok && j1 < nlev, cell0 + 1, area, perm1, dz1);
+  cell_load<SATFUNC>(A, a, pa, col_ok && j0 < nlev, cell0, area, perm0, dz0);
+  cell_load<SATFUNC>(A, b, pb, col_ok && j1 < nlev, cell0 + 1, area, perm1, dz1);
   {
     const double perm_n = __shfl_down_sync(FULL, perm0, 1, LPC), dz_n = __shfl_down_sync(FULL, dz0, 1, LPC);
     a.has_conn = b.valid;                            // 2l -> 2l+1
     b.has_conn = b.valid && (j1 < nlev - 1);         // 2l+1 -> 2(l+1)
-    conn_setup(perm0, dz0, perm1, dz1, A.uz, a.upw, a.Dq, a.gfac);
-    conn_setup(perm1, dz1, perm_n, dz_n, A.uz, b.upw, b.Dq, b.gfac);
+    double upw, Dq, gfac;
+    conn_setup(perm0, dz0, perm1, dz1, A.uz, upw, Dq, gfac);   PA(PI_UPW) = upw; PA(PI_DQ) = Dq; PA(PI_GFAC) = gfac;
+    conn_setup(perm1, dz1, perm_n, dz_n, A.uz, upw, Dq, gfac); PB(PI_UPW) = upw; PB(PI_DQ) = Dq; PB(PI_GFAC) = gfac;
   }
 
   // mass-rate source/sinks (GoveqnRichards...:1871-1875): F -= value / FMWH2O.  All loads are issued up front.
@@ -178,7 +211,10 @@ vsfm_step2_kernel(const VsfmArgs A)
       }
     }
 #pragma unroll
-    for (int k = 0; k < MAX_SS; ++k) { a.src += v0[k] * RFMW; b.src += v1[k] * RFMW; src_kg += v0[k] + v1[k]; }
+    double sa_ = 0.0, sb_ = 0.0;
+#pragma unroll
+    for (int k = 0; k < MAX_SS; ++k) { sa_ += v0[k] * RFMW; sb_ += v1[k] * RFMW; src_kg += v0[k] + v1[k]; }
+    PA(PI_SRC) = sa_; PB(PI_SRC) = sb_;
   }
 
   // boundary conditions (MeshType.F90:723-806): top -> unit vector (0,0,-1), bottom -> (0,0,+1); dist_up = 0
@@ -199,7 +235,7 @@ vsfm_step2_kernel(const VsfmArgs A)
         bcDq[k] = permc / (0.0 + 0.5 * dzc);
         bcP[k] = A.bc[k].value[col];
         SatState sb;
-        sat_values<SATFUNC>((bcOwn[k] == 1) ? a.sp : b.sp, bcP[k], 1.0, sb);   // BC aux vars keep frac_liq_sat = 1 (RichardsODEPressureAuxType.F90:93)
+        sat_values<SATFUNC>((bcOwn[k] == 1) ? par_sp<SATFUNC>(pa) : par_sp<SATFUNC>(pb), bcP[k], 1.0, sb);   // BC aux vars keep frac_liq_sat = 1 (RichardsODEPressureAuxType.F90:93)
         bcKr[k] = sb.kr;
       }
     }
@@ -222,6 +258,7 @@ vsfm_step2_kernel(const VsfmArgs A)
     // shuffle below is convergent); lanes of a column that is not in PH_NEWTON compute and discard.
     if (__any_sync(FULL, phase == PH_NEWTON)) {
       const bool nw = (phase == PH_NEWTON);
+      __syncwarp();                                  // (also keeps the compiler from hoisting the shared-memory reads out of the loop)
       double den_a, dden_a, den_b, dden_b;
       density_fixedT(A.dtab, a.X, den_a, dden_a);
       density_fixedT(A.dtab, b.X, den_b, dden_b);
@@ -230,8 +267,8 @@ vsfm_step2_kernel(const VsfmArgs A)
       const double dkrn  = __shfl_down_sync(FULL, a.dkr, 1, LPC), denn  = __shfl_down_sync(FULL, den_a, 1, LPC);
       const double ddenn = __shfl_down_sync(FULL, dden_a, 1, LPC);
       double Jup_a = 0.0, Jdn_a = 0.0, Jup_b = 0.0, Jdn_b = 0.0;
-      if (a.has_conn) rich_flux_deriv(a.X, a.kr, a.dkr, den_a, dden_a, b.X, b.kr, b.dkr, den_b, dden_b, a.upw, a.Dq, a.gfac, area, Jup_a, Jdn_a);
-      if (b.has_conn) rich_flux_deriv(b.X, b.kr, b.dkr, den_b, dden_b, Xn, krn, dkrn, denn, ddenn, b.upw, b.Dq, b.gfac, area, Jup_b, Jdn_b);
+      if (a.has_conn) rich_flux_deriv(a.X, a.kr, a.dkr, den_a, dden_a, b.X, b.kr, b.dkr, den_b, dden_b, PA(PI_UPW), PA(PI_DQ), PA(PI_GFAC), area, Jup_a, Jdn_a);
+      if (b.has_conn) rich_flux_deriv(b.X, b.kr, b.dkr, den_b, dden_b, Xn, krn, dkrn, denn, ddenn, PB(PI_UPW), PB(PI_DQ), PB(PI_GFAC), area, Jup_b, Jdn_b);
       const double Jup_p = __shfl_up_sync(FULL, Jup_b, 1, LPC), Jdn_p = __shfl_up_sync(FULL, Jdn_b, 1, LPC);   // connection (2l-1) -> 2l
       // rows 2l and 2l+1 of the tridiagonal Jacobian (GoveqnRichards...:2054-2069 insertion order)
       double sub_a = 0.0, dia_a = 1.0, sup_a = 0.0, sub_b = 0.0, dia_b = 1.0, sup_b = 0.0;
@@ -260,8 +297,8 @@ vsfm_step2_kernel(const VsfmArgs A)
           if (onA) dia_a += t; else dia_b += t;
         }
       }
-      if (a.valid) dia_a += (a.por * dden_a * a.sat + a.por * den_a * a.dsat) * a.vol * dtInv;   // AccumDeriv (:1673-1675), dpor_dP = 0
-      if (b.valid) dia_b += (b.por * dden_b * b.sat + b.por * den_b * b.dsat) * b.vol * dtInv;
+      if (a.valid) { const double por = PA(PI_POR); dia_a += (por * dden_a * a.sat + por * den_a * a.dsat) * PA(PI_VOL) * dtInv; }   // AccumDeriv (:1673-1675), dpor_dP = 0
+      if (b.valid) { const double por = PB(PI_POR); dia_b += (por * dden_b * b.sat + por * den_b * b.dsat) * PB(PI_VOL) * dtInv; }
 
       // ---- J Y = F: eliminate this lane's second unknown, PCR over the first unknowns, back-substitute ----
       const double Fa = a.valid ? a.F : 0.0, Fb = b.valid ? b.F : 0.0;
@@ -305,12 +342,12 @@ vsfm_step2_kernel(const VsfmArgs A)
       tot_nf += nfuncs;
       if (last_reason < 0) {
         cuts += 1; dt_iter = 0.5 * dt_iter; dtInv = 1.0 / dt_iter;
-        a.X = a.Xprev; b.X = b.Xprev;                       // VecCopy(soln_prev, soln)
+        a.X = PA(PI_XPREV); b.X = PB(PI_XPREV);             // VecCopy(soln_prev, soln)
         if (cuts > 20) { converged = 0; phase = PH_DONE; }
         else { a.W = a.X; b.W = b.X; phase = PH_INIT; }
       } else {
         converged = 1; time_done += dt_iter; tot_its += its;
-        a.Xprev = a.X; b.Xprev = b.X;                       // PostSolve: soln -> soln_prev
+        PA(PI_XPREV) = a.X; PB(PI_XPREV) = b.X;             // PostSolve: soln -> soln_prev
         if (HAS_BC) {
 #pragma unroll
           for (int k = 0; k < NBC; ++k) if (bcOwn[k]) bcMassExc[k] += bcFlux[k] * dt_iter;
@@ -324,23 +361,26 @@ vsfm_step2_kernel(const VsfmArgs A)
     if (__all_sync(FULL, phase == PH_DONE)) break;
 
     // ================= residual evaluation at W (VSFMSOEResidual) =================
+    __syncwarp();
     SatState sa, sb;
-    sat_values_pair<SATFUNC>(a.sp, b.sp, a.W, b.W, a.frac_liq, b.frac_liq, sa, sb);
+    const SatParams spa = par_sp<SATFUNC>(pa), spb = par_sp<SATFUNC>(pb);
+    const double fla = (SATFUNC != SATFUNC_VG) ? PA(PI_FLIQ) : 1.0, flb = (SATFUNC != SATFUNC_VG) ? PB(PI_FLIQ) : 1.0;
+    sat_values_pair<SATFUNC>(spa, spb, a.W, b.W, fla, flb, sa, sb);
     double dena, ddena, denb, ddenb, Ga, Gb, G_bcflux[NBC];
     density_fixedT(A.dtab, a.W, dena, ddena);
     density_fixedT(A.dtab, b.W, denb, ddenb);
     {
-      const double acc_a = a.por * dena * sa.sat * a.vol * dtInv;       // Accum (:1626-1630)
-      const double acc_b = b.por * denb * sb.sat * b.vol * dtInv;
-      if (phase == PH_INIT) { a.accum_prev = acc_a; b.accum_prev = acc_b; }   // PreSolve: accumulation at soln_prev (== W here)
+      const double acc_a = PA(PI_POR) * dena * sa.sat * PA(PI_VOL) * dtInv;       // Accum (:1626-1630)
+      const double acc_b = PB(PI_POR) * denb * sb.sat * PB(PI_VOL) * dtInv;
+      if (phase == PH_INIT) { PA(PI_ACCP) = acc_a; PB(PI_ACCP) = acc_b; }   // PreSolve: accumulation at soln_prev (== W here)
       const double Wn = __shfl_down_sync(FULL, a.W, 1, LPC), krn = __shfl_down_sync(FULL, sa.kr, 1, LPC), denn = __shfl_down_sync(FULL, dena, 1, LPC);
-      const double flux_a = a.has_conn ? rich_flux(a.W, sa.kr, dena, b.W, sb.kr, denb, a.upw, a.Dq, a.gfac, area) : 0.0;
-      const double flux_b = b.has_conn ? rich_flux(b.W, sb.kr, denb, Wn, krn, denn, b.upw, b.Dq, b.gfac, area) : 0.0;
+      const double flux_a = a.has_conn ? rich_flux(a.W, sa.kr, dena, b.W, sb.kr, denb, PA(PI_UPW), PA(PI_DQ), PA(PI_GFAC), area) : 0.0;
+      const double flux_b = b.has_conn ? rich_flux(b.W, sb.kr, denb, Wn, krn, denn, PB(PI_UPW), PB(PI_DQ), PB(PI_GFAC), area) : 0.0;
       const double flux_p = __shfl_up_sync(FULL, flux_b, 1, LPC);
-      Ga = acc_a - a.accum_prev;
+      Ga = acc_a - ((phase == PH_INIT) ? acc_a : PA(PI_ACCP));
       if (l > 0) Ga = Ga + flux_p;                                      // ff(dn) += flux  (:1806)
       Ga = Ga - flux_a;                                                 // ff(up) -= flux  (:1805)
-      Gb = acc_b - b.accum_prev;
+      Gb = acc_b - ((phase == PH_INIT) ? acc_b : PB(PI_ACCP));
       Gb = Gb + flux_a;
       Gb = Gb - flux_b;
 #pragma unroll
@@ -357,7 +397,7 @@ vsfm_step2_kernel(const VsfmArgs A)
           G_bcflux[k] = fl * FMWH2O;
         }
       }
-      Ga = Ga - a.src; Gb = Gb - b.src;
+      Ga = Ga - PA(PI_SRC); Gb = Gb - PB(PI_SRC);
       if (!a.valid) Ga = 0.0;
       if (!b.valid) Gb = 0.0;
     }
@@ -425,7 +465,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       // "copy the solution over": X <- W, F <- G; the aux vars of this point feed the next Jacobian / PostSolve
       a.X = a.W; b.X = b.W; a.F = Ga; b.F = Gb;
       a.kr = sa.kr; a.sat = sa.sat; b.kr = sb.kr; b.sat = sb.sat;
-      sat_derivs_pair<SATFUNC>(a.sp, b.sp, sa, sb, a.frac_liq, b.frac_liq, a.dsat, a.dkr, b.dsat, b.dkr);
+      sat_derivs_pair<SATFUNC>(spa, spb, sa, sb, fla, flb, a.dsat, a.dkr, b.dsat, b.dkr);
       if (HAS_BC) {
 #pragma unroll
         for (int k = 0; k < NBC; ++k) bcFlux[k] = G_bcflux[k];
@@ -455,7 +495,7 @@ vsfm_step2_kernel(const VsfmArgs A)
     A.x_out[cell0] = a.X;
     if (converged) {
       double den, dden; density_fixedT(A.dtab, a.X, den, dden);
-      const double m = a.por * den * FMWH2O * a.sat * a.vol;
+      const double m = PA(PI_POR) * den * FMWH2O * a.sat * PA(PI_VOL);
       A.liq_sat[cell0] = a.sat; A.pressure[cell0] = a.X; A.mass[cell0] = m;
       A.smp[cell0] = (a.X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
       mass += m;
@@ -465,7 +505,7 @@ vsfm_step2_kernel(const VsfmArgs A)
     A.x_out[cell0 + 1] = b.X;
     if (converged) {
       double den, dden; density_fixedT(A.dtab, b.X, den, dden);
-      const double m = b.por * den * FMWH2O * b.sat * b.vol;
+      const double m = PB(PI_POR) * den * FMWH2O * b.sat * PB(PI_VOL);
       A.liq_sat[cell0 + 1] = b.sat; A.pressure[cell0 + 1] = b.X; A.mass[cell0 + 1] = m;
       A.smp[cell0 + 1] = (b.X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
       mass += m;
@@ -515,8 +555,8 @@ vsfm_step2_kernel(const VsfmArgs A)
     for (int k = 4; k < 8; ++k) v[k] = fmax(v[k], __shfl_xor_sync(FULL, v[k], s));
     worst = min(worst, __shfl_xor_sync(FULL, worst, s));
   }
-  __shared__ double red[8][128 / 32];
-  __shared__ int redw[128 / 32];
+  __shared__ double red[8][VSFM2_THREADS / 32];
+  __shared__ int redw[VSFM2_THREADS / 32];
   const int warp = threadIdx.x >> 5;
   if (lane == 0) { for (int k = 0; k < 8; ++k) red[k][warp] = v[k]; redw[warp] = worst; }
   __syncthreads();
@@ -533,6 +573,8 @@ vsfm_step2_kernel(const VsfmArgs A)
     for (int k = 0; k < 8; ++k) bp[k] = o[k];
     bp[8] = (double)ow;
   }
+#undef PA
+#undef PB
 }
 
 }  // namespace mpp
