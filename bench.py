@@ -142,6 +142,43 @@ def cpu_baseline(steps, warmup, target_seconds=20.0):
             "seconds": el, "converged": bool(conv)}, ncol, el
 
 
+def other_workloads(device, stream):
+    """BASELINE.json configs[1] (soil thermal, 1 Mi columns x 15) and configs[4] (TH, 2 Mi columns x 15 over 8 GPUs = 256 Ki per
+    GPU) on this GPU, device-resident, CUDA-event time of the StepDT kernels: reported beside the headline, not part of it."""
+    import mpp_b200
+    out = {}
+    # thermal: one ELM coupling step loads the per-step data, then StepDT chained on the device
+    ncol = 1 << 20
+    d = PB.elm_thermal_inputs(ncol, NLEV)
+    p, ids = PB.build_elm_thermal(mpp_b200.Thermal, d, device=device)
+    p.set_stream(stream)
+    PB.elm_thermal_step(p, ids, d, d["T0"], DT, 1)
+    ms = []
+    for s in range(13):
+        p.step_dt(DT, s + 2); ms.append(p.last_step_ms())
+    m = float(np.mean(ms[3:]))
+    out["thermal_1Mi_x15"] = {"column_timesteps_per_sec": ncol / (m * 1e-3), "ms_per_step": m, "kernel": "thermal_step_kernel<16>",
+                              "roofline": {"bound": "hbm", "algorithmic_bytes_per_column_step": 1224, "achieved": 1224 * ncol / (m * 1e-3) / 1e9, "unit": "GB/s"}}
+    p.close()
+    # TH: Tanaka density + constant heat capacity (the throughput variant of SURVEY.md section 8d)
+    ncol = 1 << 18
+    d = PB.elm_th_inputs(ncol, NLEV)
+    p, ids = PB.build_elm_th(mpp_b200.TH, d, device=device)
+    p.set_stream(stream)
+    ms, conv = [], True
+    for s in range(8):
+        cv, reason, _ = PB.elm_th_step(p, ids, d, DT, s + 1); ms.append(p.last_step_ms()); conv = conv and cv
+    st = p.stats()
+    m = float(np.median(ms[2:]))
+    out["th_256Ki_x15"] = {"column_timesteps_per_sec": ncol / (m * 1e-3), "ms_per_step_median": m, "ms_per_step_all": [round(x, 2) for x in ms],
+                           "kernel": "th_step2_kernel<16,VG,TGDPB01,const>", "converged_all": bool(conv),
+                           "newton_its_mean": float(st["newton_its"].mean()), "residual_evals_mean": float(st["nfuncs"].mean()),
+                           "roofline": {"bound": "hbm", "algorithmic_bytes_per_column_step": 1824, "achieved": 1824 * ncol / (m * 1e-3) / 1e9, "unit": "GB/s"},
+                           "note": "step time is set by the slowest column of the batch (dt cuts of the reference algorithm), hence the median"}
+    p.close()
+    return out
+
+
 def run_reference(args, real_stdout):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -192,6 +229,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunks", type=int, default=16, help="column chunks of the pipelined coupling step (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-other", action="store_true", help="skip the thermal / TH side measurements")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                                      # timing rules: W >= 3
@@ -350,6 +388,11 @@ def main():
                        "note": "the reference algorithm at its default tolerances cuts dt / fails on a handful of the 4 Mi synthetic columns; "
                                "the oracle reproduces every cut and failure (tests/golden/hard_columns.json)"},
         }
+        if world == 1 and not args.no_other:
+            peak_ = peak
+            line["other_workloads"] = other_workloads(local_rank, stream.cuda_stream)
+            for v in line["other_workloads"].values():
+                v["roofline"]["peak"] = peak_; v["roofline"]["frac"] = v["roofline"]["achieved"] / peak_
         if not args.no_cpu and world == 1:
             cb, _, _ = cpu_baseline(args.steps, args.warmup)
             line["cpu_baseline"] = cb
