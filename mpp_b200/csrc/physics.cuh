@@ -419,6 +419,40 @@ MPP_HD int convert_soil(int satfunc_name, double watsat, double hksat, double bs
 // Water EOS
 // ------------------------------------------------------------------------------------------------
 // Tanaka et al. (2001), EOSWaterMod.F90:102-178.  den in kmol m^-3.
+// Fast variant for the TH step kernel: split into the temperature part (shared by every pressure at which the density is
+// needed -- the TH aux vars evaluate it at P and at max(P, P_ref)) and the pressure part; divisions by constants and by
+// (t_c + a4) are reciprocal multiplies (1-ulp differences from the reference order below).
+struct TanakaT { double dent, ddent_dt, kc, dkc_dt; };
+MPP_HD TanakaT tanaka_T(double t_K)
+{
+  const double a1 = -3.983035, a2 = 301.797, a3 = 522528.9, a4 = 69.34881, a5 = 999.974950;
+  const double k0 = 50.74e-11, k1 = -0.326e-11, k2 = 0.00416e-11;
+  const double t_c = t_K - 273.15;
+  const double r4 = rcp(t_c + a4), ra3 = 1.0 / a3;
+  const double s1 = (t_c + a1) * (t_c + a1);
+  const double q  = (t_c + a2) * ra3 * r4;
+  TanakaT o;
+  o.dent = a5 * (1.0 - s1 * q);
+  o.kc = k0 + k1 * t_c + k2 * t_c * t_c;
+  o.dkc_dt = k1 + 2.0 * k2 * t_c;
+  const double d1 = -s1 * ra3 * r4;
+  const double d2 = -2.0 * (t_c + a1) * q;
+  const double d3 = s1 * q * r4;
+  o.ddent_dt = a5 * (d1 + d2 + d3);
+  return o;
+}
+MPP_HD void tanaka_P(const TanakaT &t, double p, double &den, double &dden_dp, double &dden_dT)
+{
+  const double p0 = 101325.0, rfmw = 1.0 / FMWH2O;
+  const bool comp = (p > p0);                                   // compressible only above P_ref (EOSWaterMod.F90:151-155)
+  const double kappa = comp ? 1.0 + t.kc * (p - p0) : 1.0;
+  const double dkappa_dp = comp ? t.kc : 0.0, dkappa_dt = comp ? t.dkc_dt * (p - p0) : 0.0;
+  den = t.dent * kappa * rfmw;
+  dden_dT = (t.ddent_dt * kappa + t.dent * dkappa_dt) * rfmw;
+  dden_dp = (t.dent * dkappa_dp) * rfmw;
+}
+// reference operation order (divisions kept): used wherever the value is computed once -- the VSFM density table, the
+// generic kernels, the host-side checks against the oracle, which it matches bit for bit
 MPP_HD void density_tgdpb01(double p, double t_K, double &den, double &dden_dp, double &dden_dT)
 {
   const double a1 = -3.983035, a2 = 301.797, a3 = 522528.9, a4 = 69.34881, a5 = 999.974950;

@@ -60,9 +60,15 @@ __device__ __forceinline__ void th_cell_compute(const THArgs &A, const SatParams
   if (SF >= 0) { sat_values<(SF >= 0 ? SF : 0)>(sp, P, 1.0, st); sat_derivs<(SF >= 0 ? SF : 0)>(sp, st, 1.0, c.dsat, c.dkr); }
   else { sat_values_rt(A.satfunc, sp, P, 1.0, st); sat_derivs_rt(A.satfunc, sp, st, 1.0, c.dsat, c.dkr); }
   c.sat = st.sat; c.kr = st.kr;
-  density(dtype, P, T, c.den_m, c.ddenP_m, c.ddenT_m);
   const double Pe = (P < PRESSURE_REF) ? PRESSURE_REF : P;                 // ThermalEnthalpySoilAuxType.F90:251-252
-  density(dtype, Pe, T, c.den_e, c.ddenP_e, c.ddenT_e);
+  if (DT == DENSITY_TGDPB01) {                                              // one temperature part for both pressures
+    const TanakaT tt = tanaka_T(T);
+    tanaka_P(tt, P, c.den_m, c.ddenP_m, c.ddenT_m);
+    tanaka_P(tt, Pe, c.den_e, c.ddenP_e, c.ddenT_e);
+  } else {
+    density(dtype, P, T, c.den_m, c.ddenP_m, c.ddenT_m);
+    density(dtype, Pe, T, c.den_e, c.ddenP_e, c.ddenT_e);
+  }
   internal_energy_enthalpy(itype, Pe, T, c.den_e * FMWH2O, c.ddenT_e * FMWH2O, c.ddenP_e * FMWH2O,
                            c.ul, c.hl, c.dulT, c.dhlT, c.dulP, c.dhlP);
   const double therm_alpha = 0.45, wet = 1.3;                              // MultiPhysicsProbTH.F90:331-332
@@ -82,11 +88,12 @@ __device__ __forceinline__ void th_rich_flux(const FluxIn &u, const FluxIn &d, d
   const double den_ave = upw * u.den + (1.0 - upw) * d.den;
   const double dphi = u.P - d.P + den_ave * gfac;
   const bool upwind = (dphi >= 0.0);
-  const double ukvr = (upwind ? u.kr : d.kr) / VISCOSITY;
+  constexpr double RVIS = 1.0 / VISCOSITY;
+  const double ukvr = (upwind ? u.kr : d.kr) * RVIS;
   const double q = (-Dq * ukvr * dphi) * area;
   flux = q * den_ave;
   const double dphi_dP_up = 1.0 + (upw * gfac) * u.ddenP, dphi_dP_dn = -1.0 + ((1.0 - upw) * gfac) * d.ddenP;
-  const double dukvr_up = upwind ? u.dkr / VISCOSITY : 0.0, dukvr_dn = upwind ? 0.0 : d.dkr / VISCOSITY;
+  const double dukvr_up = upwind ? u.dkr * RVIS : 0.0, dukvr_dn = upwind ? 0.0 : d.dkr * RVIS;
   const double dq_up = Dq * (dukvr_up * dphi + ukvr * dphi_dP_up) * area, dq_dn = Dq * (dukvr_dn * dphi + ukvr * dphi_dP_dn) * area;
   mJup = dq_up * den_ave - q * (upw * u.ddenP);
   mJdn = dq_dn * den_ave - q * ((1.0 - upw) * d.ddenP);
