@@ -5,9 +5,11 @@
     python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host cores
 
 Workload (BASELINE.json configs[3]): 4 Mi synthetic ELM-like soil columns x 15 layers PER GPU, van Genuchten curves,
-Tanaka density, six COND_MASS_RATE source/sinks, dt = 1800 s, SNES tolerances = reference defaults; columns are
-independent, so every rank owns its own contiguous 4 Mi-column shard of one global seeded batch (weak scaling; one
-process per GPU; `--scaling strong` splits a single 4 Mi batch instead).  One "step" = one ELM coupling step =
+Tanaka density, six COND_MASS_RATE source/sinks, dt = 1800 s, SNES tolerances = reference defaults.  Columns are
+independent; weak scaling (default): every rank solves the SAME 4 Mi-column batch the 1-GPU run solves, so the work per
+GPU is identical by construction (`--scaling weak-distinct` gives every rank its own 4 Mi columns of one 4N Mi global
+batch -- then the step time is the slowest column among 4N Mi, see DESIGN.md "hard columns"; `--scaling strong` splits
+one 4 Mi batch over the ranks).  One "step" = one ELM coupling step =
 PreStepDT + StepDT + PostStepDT over the whole batch (MPPVSFMALM_Driver.F90:603-935) + one NCCL all-gather of the
 9 mass-balance / convergence doubles of every rank.
 
@@ -186,8 +188,8 @@ def run_reference(args, real_stdout):
     cb, ncol, el = cpu_baseline(args.steps, args.warmup, target_seconds=30.0)
     line = {"impl": "reference", "metric": "soil_column_timesteps_per_sec", "value": cb["value"], "unit": "column-timesteps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
-            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.ncol * args.gpus if args.scaling == "weak" else args.ncol, args.gpus), "cpu_baseline": cb,
+            "higher_is_better": True, "scaling": "strong" if args.scaling == "strong" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.ncol if args.scaling == "strong" else args.ncol * args.gpus, args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": "column-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     _emit(real_stdout, line)
@@ -225,7 +227,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="mpp_b200")
     ap.add_argument("--ncol", type=int, default=4 * 1024 * 1024, help="columns per GPU (weak scaling) / in total (strong scaling)")
-    ap.add_argument("--scaling", default="weak", choices=("weak", "strong"))
+    ap.add_argument("--scaling", default="weak", choices=("weak", "weak-distinct", "strong"))
+    ap.add_argument("--step-budget", type=int, default=0, help="mppgpu_set_step_budget (0 = off = reference behaviour)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--chunks", type=int, default=16, help="column chunks of the pipelined coupling step (0 = library default)")
     ap.add_argument("--no-cpu", action="store_true")
@@ -251,8 +254,11 @@ def main():
     assert world == args.gpus or world == 1
 
     from mpp_b200 import parallel as PL
-    ncol_total = args.ncol * world if args.scaling == "weak" else args.ncol
-    c0, c1 = PL.shard_range(ncol_total, rank, world)
+    ncol_total = args.ncol if args.scaling == "strong" else args.ncol * world
+    if args.scaling == "weak":
+        c0, c1 = 0, args.ncol                       # every rank solves the same 4 Mi-column batch
+    else:
+        c0, c1 = PL.shard_range(ncol_total, rank, world)
     d = shard_inputs(c0, c1)
     ncol = c1 - c0
     # a dedicated (non-default) stream: the library, the CUDA events and NCCL all run on it
@@ -262,6 +268,8 @@ def main():
     def fresh():
         p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d, device=local_rank)
         p.set_stream(stream.cuda_stream)
+        if args.step_budget:
+            p.set_step_budget(args.step_budget)
         set_forcing_host(p, ids, d)
         return p, ids
 
@@ -370,8 +378,8 @@ def main():
         line = {
             "metric": "soil_column_timesteps_per_sec", "value": value, "unit": "column-timesteps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_launch_ms,
-            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(ncol_total, world),
+            "higher_is_better": True, "scaling": "strong" if args.scaling == "strong" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(ncol_total, world), shards={"weak": "every rank solves the same seeded 4 Mi-column batch", "weak-distinct": "rank r solves columns [r, r+1) x 4 Mi of one seeded global batch", "strong": "one 4 Mi batch split over the ranks"}[args.scaling], step_budget=args.step_budget),
             "clocks": {"sm_mhz": clocks["sm_mhz"], "sm_max_mhz": clocks["sm_max_mhz"], "reasons": clocks["reasons"], "samples": clocks["samples"]},
             "e2e": e2e, "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

@@ -95,6 +95,12 @@ int  mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hk
                          const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,
                          int satfunc_type, int density_type, int int_energy_enthalpy_type);
 int  mppgpu_set_tolerances(mppgpu_handle h, double atol, double rtol, double stol, int max_it, int max_funcs);
+/* NOT in the reference (default 0 = off = the reference's behaviour).  The reference's StepDT halves dt up to 20 times and then
+ * sub-steps with the smallest dt that converged, so one pathological column can spend millions of residual evaluations in one
+ * StepDT; in a batch that stalls every other column of the launch.  With a budget > 0 a column that has used this many residual
+ * evaluations inside one StepDT gives up exactly like one that ran out of dt cuts: converged = 0, reason
+ * SNES_DIVERGED_FUNCTION_COUNT (-2), solution left at the last converged sub-step. */
+int  mppgpu_set_step_budget(mppgpu_handle h, int max_residual_evaluations);
 /* VSFM/thermal: x has ncells entries (pressure or temperature); TH: 2*ncells, [P(0..N-1) | T(0..N-1)] */
 int  mppgpu_restart(mppgpu_handle h, const double *x, int n);
 

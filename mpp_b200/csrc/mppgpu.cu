@@ -121,7 +121,7 @@ static int vsfm_fill_args(mppgpu_soe *h, VsfmArgs &A, double dt);
 static void default_snes(SnesOpts &so)
 {
   so.atol = 1.e-50; so.rtol = 1.e-8; so.stol = 1.e-10; so.divtol = 1.e4;      // MultiPhysicsProbBaseType.F90:1110-1114 + PETSc defaults
-  so.max_it = 50; so.max_funcs = 10000;
+  so.max_it = 50; so.max_funcs = 10000; so.step_budget = 0;
   so.ls_alpha = 1.e-4; so.ls_minlambda = 1.e-12; so.ls_maxstep = 1.e8; so.ls_max_its = 40;
 }
 
@@ -426,7 +426,16 @@ extern "C" int mppgpu_vsfm_set_soils(mppgpu_handle h, const double *watsat, cons
 extern "C" int mppgpu_set_tolerances(mppgpu_handle h, double atol, double rtol, double stol, int max_it, int max_funcs)
 {
   CHECK_H(h);
-  h->so.atol = atol; h->so.rtol = rtol; h->so.stol = stol; h->so.max_it = max_it; h->so.max_funcs = max_funcs;
+  h->so.atol = atol; h->so.rtol = rtol; h->so.stol = stol; h->so.max_it = max_it; h->so.max_funcs = max_funcs;   // (step_budget is kept)
+  if (h->th) h->th->so = h->so;
+  return 0;
+}
+
+extern "C" int mppgpu_set_step_budget(mppgpu_handle h, int max_residual_evaluations)
+{
+  CHECK_H(h);
+  if (max_residual_evaluations < 0) return fail("mppgpu_set_step_budget: the budget must be >= 0 (0 = unlimited, the reference's behaviour)");
+  h->so.step_budget = max_residual_evaluations;
   if (h->th) h->th->so = h->so;
   return 0;
 }

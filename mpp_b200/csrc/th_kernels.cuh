@@ -322,6 +322,9 @@ th_step_generic_kernel(const THArgs A)
         else { for (int j = lane; j < nlev; j += 32) { v.Wm[j] = v.P[j]; v.We[j] = v.T[j]; } phase = PH_INIT; }
       }
       its = 0; nfuncs = 0;
+      // optional give-up budget (mppgpu_set_step_budget; not in the reference, off by default): a column that has burnt this
+      // many residual evaluations inside one StepDT fails like one that ran out of dt cuts, instead of stalling the batch
+      if (so.step_budget > 0 && tot_nf >= so.step_budget && phase != PH_DONE) { converged = 0; last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = PH_DONE; }
       __syncwarp();
       if (phase == PH_DONE) break;
     }

@@ -32,6 +32,7 @@ struct CondDev {
 struct SnesOpts {
   double atol, rtol, stol, divtol;
   int max_it, max_funcs;
+  int step_budget;         // > 0: give up on a column once one StepDT has spent this many residual evaluations (not in the reference)
   double ls_alpha, ls_minlambda, ls_maxstep;
   int ls_max_its;
 };

@@ -356,6 +356,9 @@ vsfm_step2_kernel(const VsfmArgs A)
         else { a.W = a.X; b.W = b.X; phase = PH_INIT; }
       }
       its = 0; nfuncs = 0;
+      // optional give-up budget (mppgpu_set_step_budget; not in the reference, off by default): a column that has burnt this
+      // many residual evaluations inside one StepDT fails like one that ran out of dt cuts, instead of stalling the batch
+      if (so.step_budget > 0 && tot_nf >= so.step_budget && phase != PH_DONE) { converged = 0; last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = PH_DONE; }
     }
 
     if (__all_sync(FULL, phase == PH_DONE)) break;

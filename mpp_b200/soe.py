@@ -90,6 +90,10 @@ class _SoE:
 
     SNESSetTolerances = set_tolerances
 
+    def set_step_budget(self, max_residual_evaluations):
+        """Optional give-up budget per column per StepDT (not in the reference; 0 = unlimited): see include/mppgpu.h."""
+        check(self.L.mppgpu_set_step_budget(self.h, int(max_residual_evaluations)))
+
     def restart(self, x):
         x = _f64(x)
         check(self.L.mppgpu_restart(self.h, _dp(x), int(x.size)))

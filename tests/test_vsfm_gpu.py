@@ -168,19 +168,7 @@ def test_hard_columns_of_the_benchmark_batch_match_oracle(mpp, oracle):
     """tests/golden/hard_columns.json: the columns of bench.py's 4 Mi-column batch that cut dt (up to 10 halvings, 2117
     Newton iterations) or fail outright (> 20 cuts) under the reference's algorithm and default tolerances.  The CUDA
     path must cut, fail and converge exactly where the oracle does."""
-    import json, os
-    import bench
-    cols = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hard_columns.json")))["columns"]
-    parts = []
-    for c in cols:                                   # each column comes from its own seeded 65536-column chunk
-        k = c // bench.CHUNK
-        dk = PB.elm_vsfm_inputs(bench.CHUNK, 15, seed=PB.SEED + k)
-        i = c - k * bench.CHUNK
-        parts.append({key: (dk[key][i:i + 1] if key in ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "area", "infil", "dew", "snow", "sublim")
-                            else dk[key].reshape(bench.CHUNK, 15)[i:i + 1].reshape(-1))
-                      for key in ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "area", "infil", "dew", "snow", "sublim", "press_ic", "et", "drain", "frac_liq")})
-    d = {key: np.concatenate([q[key] for q in parts], axis=0) for key in parts[0]}
-    d.update(ncol=len(cols), nlev=15, satfunc="van_genuchten")
+    d = _hard_columns_inputs()
     p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
     o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
     seen_cut = seen_fail = False
@@ -209,6 +197,46 @@ def test_hard_columns_of_the_benchmark_batch_match_oracle(mpp, oracle):
         if few.any():
             assert relmax_p(Pg[few], Po[few]) < 1e-8
     assert seen_cut and seen_fail, "fixture no longer exercises the dt-cut / failure paths"
+
+
+def _hard_columns_inputs():
+    import json, os
+    import bench
+    cols = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hard_columns.json")))["columns"]
+    parts = []
+    per_col = ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "area", "infil", "dew", "snow", "sublim")
+    for c in cols:                                   # each column comes from its own seeded 65536-column chunk
+        k = c // bench.CHUNK
+        dk = PB.elm_vsfm_inputs(bench.CHUNK, 15, seed=PB.SEED + k)
+        i = c - k * bench.CHUNK
+        parts.append({key: (dk[key][i:i + 1] if key in per_col else dk[key].reshape(bench.CHUNK, 15)[i:i + 1].reshape(-1))
+                      for key in per_col + ("press_ic", "et", "drain", "frac_liq")})
+    d = {key: np.concatenate([q[key] for q in parts], axis=0) for key in parts[0]}
+    d.update(ncol=len(cols), nlev=15, satfunc="van_genuchten")
+    return d
+
+
+def test_step_budget_only_touches_columns_that_exceed_it(mpp):
+    """mppgpu_set_step_budget (not in the reference, off by default): a column that has spent the budget of residual evaluations
+    inside one StepDT and still has sub-steps to go gives up with SNES_DIVERGED_FUNCTION_COUNT; columns that stay below the
+    budget are bit-for-bit unaffected."""
+    d = _hard_columns_inputs()
+    B = 180
+    runs = {}
+    for budget in (0, B):
+        p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+        p.set_step_budget(budget)
+        conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, 1)
+        runs[budget] = (conv, reason, p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1).reshape(-1, 15), p.stats())
+    st0, st1 = runs[0][3], runs[B][3]
+    gave_up = st1["reasons"] == -2
+    assert gave_up.any(), "fixture no longer contains a column that exceeds the budget"
+    assert np.all(st0["nfuncs"][gave_up] >= B) and np.all(st1["nfuncs"][gave_up] < st0["nfuncs"][gave_up])
+    small = st0["nfuncs"] < B
+    assert small.any() and np.array_equal(st1["reasons"][small], st0["reasons"][small])
+    assert np.array_equal(runs[0][2][small], runs[B][2][small])
+    with pytest.raises(mpp.MPPError):
+        p.set_step_budget(-1)
 
 
 def test_pre_post_step_dt_rollback(mpp):
