@@ -110,6 +110,19 @@ class ClockSampler:
         return out
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this process to the CPUs closest to its GPU (NVML topology) so that the pinned host buffers of the end-to-end
+    path are allocated on the GPU's NUMA node; harmless when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[gpu_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu_index
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+    except Exception:
+        pass
+
+
 def set_forcing_host(p, ids, d):
     for name in SS_NAMES:
         p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids[name], d[name])
@@ -248,6 +261,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    bind_to_gpu_numa_node(local_rank)            # before any pinned allocation: host staging buffers land next to the GPU
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
