@@ -162,14 +162,19 @@ __global__ void convert_soils_kernel(int satfunc_name, const double *watsat, con
 
 // Aux vars of the restart state (VSFMMPPRestart then the first GetDataForCLM of the ELM driver, MPPVSFMALM_Driver.F90:556-601):
 // fills the SoE mailbox (pressure, liq_sat, mass, smp) and the per-column mass that the next StepDT's balance starts from.
+// GROUP lanes per column (16 or 32; one cell per lane, coalesced, column mass by a fixed-order butterfly); GROUP = 0: one
+// thread per column for taller columns.
+template <int GROUP>
 __global__ void vsfm_restart_mailbox_kernel(int satfunc, VsfmArgs A)
 {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= A.ncol) return;
-  if (A.active && !A.active[col]) return;
-  const double area = A.area[col];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = (GROUP > 0) ? GROUP : 1;
+  const int col = (int)(tid / G), j0 = (int)(tid % G);
+  const bool col_ok = (col < A.ncol) && (A.active == nullptr || A.active[col] != 0);
+  const double area = col_ok ? A.area[col] : 1.0;
   double msum = 0.0;
-  for (int j = 0; j < A.nlev; ++j) {
+  for (int j = j0; j < ((GROUP > 0) ? j0 + 1 : A.nlev); ++j) {
+    if (!col_ok || j >= A.nlev) break;
     const long long cell = (long long)col * A.nlev + j;
     SatParams sp; sp.sat_res = A.sat_res[cell]; sp.alpha = A.alpha[cell]; sp.m = A.lam[cell]; sp.n = A.vgn ? A.vgn[cell] : 0.0;
     sp.pu = sp.ps = sp.b2 = sp.b3 = 0.0;
@@ -183,7 +188,11 @@ __global__ void vsfm_restart_mailbox_kernel(int satfunc, VsfmArgs A)
     A.smp[cell] = (X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
     msum += mass;
   }
-  A.col_mass[col] = msum;
+  if (GROUP > 0) {
+#pragma unroll
+    for (int s = G / 2; s > 0; s >>= 1) msum += __shfl_xor_sync(0xffffffffu, msum, s, G);
+  }
+  if (col_ok && j0 == 0) A.col_mass[col] = msum;
 }
 
 constexpr int REDUCE_BLOCKS = 148;
@@ -454,7 +463,9 @@ extern "C" int mppgpu_restart(mppgpu_handle h, const double *x, int n)
       vsfm_fill_args(h, A, 1.0);
       A.x_in = h->xA.p;
       const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
-      vsfm_restart_mailbox_kernel<<<nblk(h->ncol, 128), 128, 0, h->stream>>>(sf, A);
+      if (h->nlev <= 16)      vsfm_restart_mailbox_kernel<16><<<nblk((long long)h->ncol * 16, 128), 128, 0, h->stream>>>(sf, A);
+      else if (h->nlev <= 32) vsfm_restart_mailbox_kernel<32><<<nblk((long long)h->ncol * 32, 128), 128, 0, h->stream>>>(sf, A);
+      else                    vsfm_restart_mailbox_kernel<0><<<nblk(h->ncol, 128), 128, 0, h->stream>>>(sf, A);
       CK(cudaGetLastError());
       h->launches += 1;
     }

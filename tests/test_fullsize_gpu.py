@@ -1,0 +1,120 @@
+"""Parity at BASELINE.json's full sizes: size-independent properties over the whole batch (per-column mass / energy balance,
+determinism, sortedness of nothing -- columns are independent) plus the oracle on a random sample of the batch's own columns."""
+import numpy as np
+import pytest
+
+import problems as PB
+from mpp_b200 import constants as K
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def mpp():
+    import mpp_b200
+    from mpp_b200._lib import lib
+    assert lib().mppgpu_device_count() > 0
+    return mpp_b200
+
+
+def relmax(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300)))
+
+
+def relmax_p(a, b):
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), np.abs(b - K.PRESSURE_REF))))
+
+
+def _take_columns(d, cols, per_col, per_cell, nlev):
+    out = {k: d[k][cols] for k in per_col}
+    out.update({k: d[k].reshape(-1, nlev)[cols].reshape(-1) for k in per_cell})
+    return out
+
+
+def test_vsfm_4Mi_columns_mass_balance_determinism_and_sampled_parity(mpp, oracle):
+    """configs[3]: 4 Mi columns x 15 layers.  (i) every converged column closes its mass balance to 1e-5 kg
+    (MPPVSFMALM_Driver.F90:860-863); (ii) two runs are bitwise identical; (iii) 1024 columns drawn from the batch, run
+    through the oracle on their own, agree to 1e-10 after two steps."""
+    import bench
+    ncol, nlev = 4 * 1024 * 1024, 15
+    d = bench.shard_inputs(0, ncol)
+    runs = []
+    for rep in range(2):
+        p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+        bench.set_forcing_host(p, ids, d)
+        for step in range(2):
+            p.pre_step_dt(); conv, reason = p.step_dt(1800.0, step + 1); p.post_step_dt()
+            if step == 0:
+                m0 = p.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1).reshape(ncol, nlev).sum(1)
+        P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1)
+        m1 = p.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1).reshape(ncol, nlev).sum(1)
+        st = p.stats()
+        runs.append((P, m0, m1, st))
+        p.close()
+    P, m0, m1, st = runs[0]
+    assert np.array_equal(P, runs[1][0]) and np.array_equal(st["newton_its"], runs[1][3]["newton_its"])
+    ok = (st["reasons"] > 0)
+    assert ok.mean() > 0.99999                                           # a handful of hard columns may fail
+    q = d["infil"] + d["et"].reshape(ncol, nlev).sum(1)
+    err = np.abs(m0 - m1 + q * 1800.0)
+    clean = ok & (st["dt_cuts"] == 0)
+    assert err[clean].max() < 1e-5
+    assert np.isfinite(P).all()
+    rng = np.random.default_rng(7)
+    cols = np.sort(rng.choice(ncol, 1024, replace=False))
+    ds = _take_columns(d, cols, ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "area", "infil", "dew", "snow", "sublim"),
+                       ("press_ic", "et", "drain", "frac_liq"), nlev)
+    ds.update(ncol=len(cols), nlev=nlev, satfunc="van_genuchten")
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, ds, per_column=True, nthreads=16)
+    for step in range(2):
+        convo, reasono, outo = PB.elm_vsfm_step(o, oids, ds, 1800.0, step + 1)
+    so = o.stats()
+    same = (so["dt_cuts"] == 0) & (so["reasons"] > 0)
+    Pg = P.reshape(ncol, nlev)[cols]
+    assert relmax_p(Pg[same], outo["pressure"].reshape(-1, nlev)[same]) < RTOL
+    assert np.array_equal(st["newton_its"][cols][same], so["newton_its"][same])
+
+
+def test_thermal_1Mi_columns_energy_balance_and_sampled_parity(mpp, oracle):
+    """configs[1]: 1 Mi columns x 15 layers.  With dhsdT = 0 the column's heat content changes by exactly the surface flux
+    times dt (no other source); 512 sampled columns agree with the oracle to 1e-10."""
+    ncol, nlev = 1 << 20, 15
+    d = PB.elm_thermal_inputs(ncol, nlev)
+    d["dhsdT"] = np.zeros(ncol)
+    p, ids = PB.build_elm_thermal(mpp.Thermal, d)
+    conv, T1 = PB.elm_thermal_step(p, ids, d, d["T0"], 1800.0, 1)
+    hc = d["csol"] * (1 - d["watsat"]) * d["dz"] + d["ice"].reshape(ncol, nlev) * 2.11727e3 + d["liq"].reshape(ncol, nlev) * 4.188e3
+    dE = (hc * (T1.reshape(ncol, nlev) - d["T0"].reshape(ncol, nlev))).sum(1)
+    assert conv and np.max(np.abs(dE - d["hs"] * 1800.0)) < 1e-6 * np.max(np.abs(d["hs"] * 1800.0))
+    rng = np.random.default_rng(8)
+    cols = np.sort(rng.choice(ncol, 512, replace=False))
+    ds = _take_columns(d, cols, ("dz", "area", "dist_up", "dist_dn", "watsat", "csol", "tkmg", "tkdry", "lun_type", "hs", "dhsdT", "frac"),
+                       ("ice", "liq", "T0", "snow_water", "nsnow", "tuning", "sabg"), nlev)
+    ds.update(ncol=len(cols), nlev=nlev, nlevsoi=d["nlevsoi"])
+    o, oids = PB.build_elm_thermal(oracle.OracleThermal, ds, nthreads=8)
+    convo, To = PB.elm_thermal_step(o, oids, ds, ds["T0"], 1800.0, 1)
+    assert relmax(T1.reshape(ncol, nlev)[cols].reshape(-1), To) < RTOL
+
+
+def test_th_256Ki_columns_sampled_parity(mpp, oracle):
+    """configs[4] per-GPU share (2 Mi columns over 8 GPUs): 256 Ki columns x 15 layers, one step; 256 sampled columns vs the oracle."""
+    ncol, nlev = 1 << 18, 15
+    d = PB.elm_th_inputs(ncol, nlev)
+    p, ids = PB.build_elm_th(mpp.TH, d)
+    conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, 1)
+    st = p.stats()
+    assert (st["reasons"] > 0).mean() > 0.9999 and np.isfinite(out["pressure"]).all() and np.isfinite(out["temperature"]).all()
+    rng = np.random.default_rng(9)
+    cols = np.sort(rng.choice(ncol, 256, replace=False))
+    ds = _take_columns(d, cols, ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "area", "infil", "dew", "snow", "sublim", "csol", "tkdry", "T_top", "P_top_bc"),
+                       ("press_ic", "et", "drain", "frac_liq", "temp_ic", "heat"), nlev)
+    ds.update(ncol=len(cols), nlev=nlev, satfunc="van_genuchten", density_type=d["density_type"], iee_type=d["iee_type"])
+    o, oids = PB.build_elm_th(oracle.OracleTH, ds, per_column=True, nthreads=8)
+    convo, reasono, outo = PB.elm_th_step(o, oids, ds, 1800.0, 1)
+    so = o.stats()
+    same = (so["dt_cuts"] == 0) & (so["reasons"] > 0) & (so["newton_its"] == st["newton_its"][cols])
+    assert same.mean() > 0.97
+    for k in ("pressure", "temperature", "sat"):
+        a, b = out[k].reshape(ncol, nlev)[cols][same], outo[k].reshape(-1, nlev)[same]
+        assert (relmax_p if k == "pressure" else relmax)(a, b) < RTOL, k

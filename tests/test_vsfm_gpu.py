@@ -91,7 +91,14 @@ def test_elm_like_mass_balance_and_reductions(mpp, oracle):
     ncol = 2048 + 37     # ragged: last block partially filled
     d = PB.elm_vsfm_inputs(ncol, 15)
     p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
-    PB.elm_vsfm_step(p, ids, d, 1800.0, 1)
+    # the restart fills the mailbox and the column masses (vsfm_restart_mailbox_kernel): the FIRST step's balance closes too
+    mr = p.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1).reshape(ncol, 15).sum(1)
+    assert np.all(p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1) == d["press_ic"])
+    conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, 1)
+    q0 = d["infil"] + d["et"].reshape(ncol, 15).sum(1)
+    assert conv and np.max(np.abs(mr - out["mass"].reshape(ncol, 15).sum(1) + q0 * 1800.0)) < 1e-5
+    sums, maxs = p.mass_balance(1800.0)
+    assert abs(sums[0] - mr.sum()) < 1e-9 * mr.sum() and maxs[0] < 1e-5
     m0 = p.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1).reshape(ncol, 15).sum(1)
     conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, 2)
     m1 = out["mass"].reshape(ncol, 15).sum(1)
