@@ -611,6 +611,18 @@ static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 #undef MPP_L2
 }
 
+#ifdef VSFM2_PROFILE
+static long long *g_prof = nullptr;
+extern "C" int mppgpu_dbg_profile(long long *out7)
+{
+  if (!g_prof) return 1;
+  cudaDeviceSynchronize();
+  cudaMemcpy(out7, g_prof, 7 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_prof, 0, 7 * sizeof(long long));
+  return 0;
+}
+#endif
+
 // shift every per-cell / per-column pointer of A to the sub-batch [col0, col0 + n)
 static void vsfm_offset_args(VsfmArgs &A, int nlev, long long col0, int n, long long block0)
 {
@@ -640,6 +652,10 @@ static int vsfm_launch_range(mppgpu_soe *h, const VsfmArgs &A0, long long col0, 
 {
   VsfmArgs A = A0;
   vsfm_offset_args(A, h->nlev, col0, n, block0);
+#ifdef VSFM2_PROFILE
+  if (!g_prof) { cudaMalloc((void **)&g_prof, 7 * sizeof(long long)); cudaMemset(g_prof, 0, 7 * sizeof(long long)); }
+  A.prof = g_prof;
+#endif
   const int nlev = h->nlev, nblocks = vsfm_blocks_for(h, n);
   cudaStream_t keep = h->stream; h->stream = s;
   if (nlev <= 16)      launch_vsfm2<8>(h, A, nblocks);

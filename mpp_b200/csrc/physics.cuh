@@ -115,6 +115,15 @@ template <class T> MPP_HD T rcp(T x)
   return r;
 }
 
+// one Newton step only (relative error ~2^-46): for pivots of the Newton linear solves, whose accuracy steers the Newton path
+// but never the converged answer
+template <class T> MPP_HD T rcp1(T x)
+{
+  T r = rcp_seed(x);
+  const T e = vfma(-x, r, vbc<T>(1.0));
+  return vfma(r, e, r);
+}
+
 // log: x = 2^k (1 + f), 1 + f in [sqrt(1/2), sqrt(2))
 MPP_HD void log_reduce(double x, double &f, double &dk)
 {

@@ -61,6 +61,7 @@ struct VsfmArgs {
   double *block_partials;  // gridDim.x * 8 doubles: deterministic two-stage reduction
   double dt;
   SnesOpts so;
+  long long *prof;         // development aid: per-section cycle counters (nullptr in production)
 };
 
 enum { PH_INIT = 0, PH_NEWTON = 1, PH_LS_FULL = 2, PH_LS_QUAD = 3, PH_LS_CUBIC = 4, PH_DONE = 5 };

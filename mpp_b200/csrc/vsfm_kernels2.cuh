@@ -57,7 +57,7 @@ __device__ __forceinline__ double pcr_unit_diag(double al, double ga, double de)
     const double de_m = __shfl_up_sync(FULL_MASK, de, s, LPC);
     const double al_p = __shfl_down_sync(FULL_MASK, al, s, LPC), ga_p = __shfl_down_sync(FULL_MASK, ga, s, LPC);
     const double de_p = __shfl_down_sync(FULL_MASK, de, s, LPC);
-    const double r = __drcp_rn(1.0 - al * ga_m - ga * al_p);
+    const double r = rcp1(1.0 - al * ga_m - ga * al_p);
     de = (de - al * de_m - ga * de_p) * r;
     al = (-al * al_m) * r;
     ga = (-ga * ga_p) * r;
@@ -252,7 +252,13 @@ vsfm_step2_kernel(const VsfmArgs A)
   double f2 = 0.0, x2 = 0.0, y2 = 0.0, ttol2 = 0.0, f2_0 = 0.0;      // squared norms ||F||^2, ||X||^2, ||Y||^2
   double initslope = -1.0, lambda = 1.0, lambdaprev = 1.0, gprev = 0.0;
 
+#ifdef VSFM2_PROFILE
+  long long pt_newton = 0, pt_eval = 0, pt_logic = 0, pn_newton = 0, pn_eval = 0; const long long pt_start = clock64();
+#endif
   for (;;) {
+#ifdef VSFM2_PROFILE
+    const long long pt0 = clock64();
+#endif
     // ================= Newton step set-up: Jacobian, linear solve, line-search initialisation =================
     // Executed by the WHOLE warp whenever any of its columns starts a Newton iteration (warp-uniform branch, so every
     // shuffle below is convergent); lanes of a column that is not in PH_NEWTON compute and discard.
@@ -302,11 +308,11 @@ vsfm_step2_kernel(const VsfmArgs A)
 
       // ---- J Y = F: eliminate this lane's second unknown, PCR over the first unknowns, back-substitute ----
       const double Fa = a.valid ? a.F : 0.0, Fb = b.valid ? b.F : 0.0;
-      const double rb = __drcp_rn(dia_b);
+      const double rb = rcp1(dia_b);
       const double bs = sub_b * rb, bu = sup_b * rb, bf = Fb * rb;   // y_b = bf - bs y_a(l) - bu y_a(l+1)
       const double bs_p = __shfl_up_sync(FULL, bs, 1, LPC), bu_p = __shfl_up_sync(FULL, bu, 1, LPC), bf_p = __shfl_up_sync(FULL, bf, 1, LPC);
       // reduced row l: sub_a y_b(l-1) + dia_a y_a(l) + sup_a y_b(l) = Fa   (sub_a = 0 on lane 0)
-      const double rB = __drcp_rn(dia_a - sub_a * bu_p - sup_a * bs);
+      const double rB = rcp1(dia_a - sub_a * bu_p - sup_a * bs);
       const double al = (-sub_a * bs_p) * rB, ga = (-sup_a * bu) * rB, de = (Fa - sub_a * bf_p - sup_a * bf) * rB;
       const double Ya = pcr_unit_diag<LPC>(al, ga, de);
       const double Ya_n = __shfl_down_sync(FULL, Ya, 1, LPC);
@@ -362,6 +368,9 @@ vsfm_step2_kernel(const VsfmArgs A)
     }
 
     if (__all_sync(FULL, phase == PH_DONE)) break;
+#ifdef VSFM2_PROFILE
+    const long long pt1 = clock64(); if (pt1 - pt0 > 200) { pt_newton += pt1 - pt0; pn_newton++; }
+#endif
 
     // ================= residual evaluation at W (VSFMSOEResidual) =================
     __syncwarp();
@@ -404,10 +413,17 @@ vsfm_step2_kernel(const VsfmArgs A)
       if (!a.valid) Ga = 0.0;
       if (!b.valid) Gb = 0.0;
     }
+    // derivative terms of the curves for this point: independent of the accept / reject decision, computed here so that their
+    // two reciprocal chains run in the shadow of the flux + norm reductions (discarded for rejected line-search trial points)
+    double dsat_a, dkr_a, dsat_b, dkr_b;
+    sat_derivs_pair<SATFUNC>(spa, spb, sa, sb, fla, flb, dsat_a, dkr_a, dsat_b, dkr_b);
     const double g2 = col_sum<LPC>(Ga * Ga + Gb * Gb);
     const double w2 = col_sum<LPC>((a.valid ? a.W * a.W : 0.0) + (b.valid ? b.W * b.W : 0.0));
     nfuncs += 1;
 
+#ifdef VSFM2_PROFILE
+    const long long pt2 = clock64(); pt_eval += pt2 - pt1; pn_eval++;
+#endif
     // ================= after the evaluation: line-search / convergence logic (squared norms) =================
     bool take = false;          // adopt W as the new iterate (and its aux vars)
     const bool g_bad = !(g2 == g2) || (g2 > 1.7e308);                   // NaN or Inf
@@ -468,7 +484,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       // "copy the solution over": X <- W, F <- G; the aux vars of this point feed the next Jacobian / PostSolve
       a.X = a.W; b.X = b.W; a.F = Ga; b.F = Gb;
       a.kr = sa.kr; a.sat = sa.sat; b.kr = sb.kr; b.sat = sb.sat;
-      sat_derivs_pair<SATFUNC>(spa, spb, sa, sb, fla, flb, a.dsat, a.dkr, b.dsat, b.dkr);
+      a.dsat = dsat_a; a.dkr = dkr_a; b.dsat = dsat_b; b.dkr = dkr_b;
       if (HAS_BC) {
 #pragma unroll
         for (int k = 0; k < NBC; ++k) bcFlux[k] = G_bcflux[k];
@@ -490,7 +506,18 @@ vsfm_step2_kernel(const VsfmArgs A)
       }
       if (reason) { last_reason = reason; phase = -1; } else phase = PH_NEWTON;
     }
+#ifdef VSFM2_PROFILE
+    pt_logic += clock64() - pt2;
+#endif
   }
+#ifdef VSFM2_PROFILE
+  if (A.prof && lane == 0) {
+    atomicAdd((unsigned long long *)A.prof + 0, (unsigned long long)pt_newton); atomicAdd((unsigned long long *)A.prof + 1, (unsigned long long)pn_newton);
+    atomicAdd((unsigned long long *)A.prof + 2, (unsigned long long)pt_eval);   atomicAdd((unsigned long long *)A.prof + 3, (unsigned long long)pn_eval);
+    atomicAdd((unsigned long long *)A.prof + 4, (unsigned long long)pt_logic);  atomicAdd((unsigned long long *)A.prof + 5, (unsigned long long)(clock64() - pt_start));
+    atomicAdd((unsigned long long *)A.prof + 6, 1ull);
+  }
+#endif
 
   // ---- VSFMSOEPostSolve -> SetDataInSOEAuxVar (GoveqnRichards...:1170-1195) ---------------------------------
   double mass = 0.0;

@@ -183,7 +183,7 @@ def test_hard_columns_of_the_benchmark_batch_match_oracle(mpp, oracle):
         conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, step + 1)
         convo, reasono, outo = PB.elm_vsfm_step(o, oids, d, 1800.0, step + 1)
         sg, so_ = p.stats(), o.stats()
-        assert conv == convo and (reason == reasono or (reason > 0 and reasono > 0))
+        assert conv == convo and (reason > 0) == (reasono > 0)      # (a column out of dt cuts may die on max_it in one and on the line search in the other)
         assert np.array_equal(sg["dt_cuts"], so_["dt_cuts"])
         easy = so_["dt_cuts"] <= 2
         assert np.array_equal(sg["reasons"][easy], so_["reasons"][easy])
