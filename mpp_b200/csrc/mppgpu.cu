@@ -29,12 +29,12 @@ using namespace mpp;
 
 // ---- ids (MultiPhysicsProbConstants.F90) -------------------------------------------------------------
 enum { COND_BC = 501, COND_SS = 502, COND_MASS_RATE = 503, COND_MASS_FLUX = 504, COND_DIRICHLET = 505,
-       COND_HEAT_FLUX = 507, COND_SEEPAGE_BC = 509, COND_HEAT_RATE = 511 };
+       COND_HEAT_FLUX = 507, COND_SEEPAGE_BC = 509, COND_HEAT_RATE = 511, COND_DOWNREG_MASS_RATE_CAMPBELL = 512, COND_DOWNREG_MASS_RATE_FETCH2 = 513 };
 enum { VAR_PRESSURE = 604, VAR_TEMPERATURE = 605, VAR_BC_SS_CONDITION = 607, VAR_LIQ_SAT = 608, VAR_MASS = 610,
        VAR_SOIL_MATRIX_POT = 611, VAR_FRAC_LIQ_SAT = 612, VAR_BC_MASS_EXCHANGED = 614, VAR_LIQ_AREAL_DEN = 615,
        VAR_ICE_AREAL_DEN = 617, VAR_FRAC = 618, VAR_SNOW_WATER = 619, VAR_NUM_SNOW_LYR = 620, VAR_DHS_DT = 621,
        VAR_THERMAL_COND = 622, VAR_HEAT_CAP = 623, VAR_ACTIVE = 624, VAR_DZ = 627, VAR_DIST_UP = 628,
-       VAR_DIST_DN = 629, VAR_TUNING_FACTOR = 630, VAR_MASS_FLUX = 644 };
+       VAR_DIST_DN = 629, VAR_TUNING_FACTOR = 630, VAR_POT_MASS_SINK_PRESSURE = 638, VAR_POT_MASS_SINK_EXPONENT = 639, VAR_MASS_FLUX = 644 };
 enum { AUXVAR_INTERNAL = 701, AUXVAR_BC = 702, AUXVAR_SS = 703 };
 
 static thread_local std::string g_err;
@@ -58,7 +58,7 @@ template <class T> struct DevBuf {
 struct HostCond {
   int ieqn, ss_or_bc, itype, region;
   size_t n;                 // entries: ncol (top/bottom) or ncells (SOIL_CELLS)
-  DevBuf<double> value, flux, mass_exc, dhsdT, frac;
+  DevBuf<double> value, flux, mass_exc, dhsdT, frac, pot_pressure, pot_exponent;
 };
 
 struct mppgpu_soe {
@@ -372,7 +372,10 @@ extern "C" int mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int
       for (auto *c : h->bcs) if (c->region == region) return fail("mppgpu_add_condition: one boundary condition per region is supported");
       if ((int)h->bcs.size() >= MAX_BC) return fail("mppgpu_add_condition: at most %d boundary conditions", MAX_BC);
     } else {
-      if (cond_type != COND_MASS_RATE) return fail("mppgpu_add_condition: VSFM source/sink type %d unsupported (COND_MASS_RATE 503)", cond_type);
+      const bool downreg = (cond_type == COND_DOWNREG_MASS_RATE_CAMPBELL || cond_type == COND_DOWNREG_MASS_RATE_FETCH2);
+      if (cond_type != COND_MASS_RATE && !downreg)
+        return fail("mppgpu_add_condition: VSFM source/sink type %d unsupported (COND_MASS_RATE 503, COND_DOWNREG_MASS_RATE_CAMPBELL 512, _FETCH2 513)", cond_type);
+      if (downreg) for (auto *c : h->sss) if (c->itype != COND_MASS_RATE) return fail("mppgpu_add_condition: one down-regulated sink per system of equations is supported");
       if ((int)h->sss.size() >= MAX_SS) return fail("mppgpu_add_condition: at most %d source/sink conditions", MAX_SS);
     }
   } else if (h->soe_itype == MPPGPU_SOE_THERMAL_TBASED) {
@@ -388,6 +391,11 @@ extern "C" int mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int
   c->ieqn = ieqn; c->ss_or_bc = ss_or_bc; c->itype = cond_type; c->region = region;
   c->n = (region == REGION_CELLS) ? h->ncells : (size_t)h->ncol;
   CK(c->value.alloc(c->n)); CK(cudaMemsetAsync(c->value.p, 0, c->n * 8, h->stream));
+  if (ss_or_bc == COND_SS && (cond_type == COND_DOWNREG_MASS_RATE_CAMPBELL || cond_type == COND_DOWNREG_MASS_RATE_FETCH2)) {
+    CK(c->pot_pressure.alloc(c->n)); CK(c->pot_exponent.alloc(c->n));          // aux_vars_ss%pot_mass_sink_{pressure,exponent}
+    fill_kernel<<<nblk(c->n, 256), 256, 0, h->stream>>>(c->pot_pressure.p, -1.0, (long long)c->n);
+    CK(cudaMemsetAsync(c->pot_exponent.p, 0, c->n * 8, h->stream));
+  }
   if (ss_or_bc == COND_BC) {
     CK(c->flux.alloc(c->n)); CK(cudaMemsetAsync(c->flux.p, 0, c->n * 8, h->stream));
     CK(c->mass_exc.alloc(c->n)); CK(cudaMemsetAsync(c->mass_exc.p, 0, c->n * 8, h->stream));
@@ -511,6 +519,9 @@ static int vsfm_field(mppgpu_soe *h, int auxvar_type, int var_type, int cond_id,
   if (!c) return fail("VSFMSOE%sData: condition id %d out of range", for_set ? "Set" : "Get", cond_id);
   *cap = c->n;
   if (var_type == VAR_BC_SS_CONDITION) { *p = c->value.p; return 0; }
+  // VSFMMPPSetSourceSinkAuxVarRealValue (MultiPhysicsProbVSFM.F90:1437-1520)
+  if (for_set && auxvar_type == AUXVAR_SS && c->pot_pressure.p && var_type == VAR_POT_MASS_SINK_PRESSURE) { *p = c->pot_pressure.p; return 0; }
+  if (for_set && auxvar_type == AUXVAR_SS && c->pot_exponent.p && var_type == VAR_POT_MASS_SINK_EXPONENT) { *p = c->pot_exponent.p; return 0; }
   if (!for_set && auxvar_type == AUXVAR_BC && var_type == VAR_MASS_FLUX) { *p = c->flux.p; return 0; }
   if (!for_set && auxvar_type == AUXVAR_BC && var_type == VAR_BC_MASS_EXCHANGED) { *p = c->mass_exc.p; return 0; }
   if (!for_set && auxvar_type == AUXVAR_SS && var_type == VAR_MASS_FLUX) { *p = c->value.p; return 0; }   // ss_flux = value (GoveqnRichards...:1873)
@@ -591,7 +602,13 @@ static int vsfm_fill_args(mppgpu_soe *h, VsfmArgs &A, double dt)
   A.active = h->has_active ? h->active.p : nullptr;
   A.frac_liq = h->frac_liq.p;
   A.nss = (int)h->sss.size(); A.nbc = (int)h->bcs.size();
-  for (int k = 0; k < A.nss; ++k) { A.ss[k].value = h->sss[k]->value.p; A.ss[k].itype = h->sss[k]->itype; A.ss[k].region = h->sss[k]->region; A.ss[k].flux = nullptr; A.ss[k].mass_exc = nullptr; }
+  for (int k = 0; k < A.nss; ++k) {
+    A.ss[k].value = h->sss[k]->value.p; A.ss[k].itype = h->sss[k]->itype; A.ss[k].region = h->sss[k]->region; A.ss[k].flux = nullptr; A.ss[k].mass_exc = nullptr;
+    if (h->sss[k]->itype != COND_MASS_RATE) {
+      A.dr_type = h->sss[k]->itype; A.dr_region = h->sss[k]->region;
+      A.dr_value = h->sss[k]->value.p; A.dr_pc = h->sss[k]->pot_pressure.p; A.dr_n = h->sss[k]->pot_exponent.p;
+    }
+  }
   for (int k = 0; k < A.nbc; ++k) { A.bc[k].value = h->bcs[k]->value.p; A.bc[k].itype = h->bcs[k]->itype; A.bc[k].region = h->bcs[k]->region; A.bc[k].flux = h->bcs[k]->flux.p; A.bc[k].mass_exc = h->bcs[k]->mass_exc.p; }
   A.liq_sat = h->liq_sat.p; A.pressure = h->pressure.p; A.mass = h->mass.p; A.smp = h->smp.p;
   A.stat_its = h->stat_its.p; A.stat_reason = h->stat_reason.p; A.stat_cuts = h->stat_cuts.p; A.stat_nf = h->stat_nf.p;
@@ -613,12 +630,12 @@ static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 
 #ifdef VSFM2_PROFILE
 static long long *g_prof = nullptr;
-extern "C" int mppgpu_dbg_profile(long long *out7)
+extern "C" int mppgpu_dbg_profile(long long *out7 /* 9 entries */)
 {
   if (!g_prof) return 1;
   cudaDeviceSynchronize();
-  cudaMemcpy(out7, g_prof, 7 * sizeof(long long), cudaMemcpyDeviceToHost);
-  cudaMemset(g_prof, 0, 7 * sizeof(long long));
+  cudaMemcpy(out7, g_prof, 9 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_prof, 0, 9 * sizeof(long long));
   return 0;
 }
 #endif
@@ -633,6 +650,7 @@ static void vsfm_offset_args(VsfmArgs &A, int nlev, long long col0, int n, long 
   for (auto pp : cellw) if (*pp) *pp += c;
   A.area += col0; if (A.active) A.active += col0;
   for (int k = 0; k < A.nss; ++k) A.ss[k].value += (A.ss[k].region == REGION_CELLS) ? c : col0;
+  if (A.dr_type) { const long long o = (A.dr_region == REGION_CELLS) ? c : col0; A.dr_value += o; A.dr_pc += o; A.dr_n += o; }
   for (int k = 0; k < A.nbc; ++k) { A.bc[k].value += col0; A.bc[k].flux += col0; A.bc[k].mass_exc += col0; }
   A.stat_its += col0; A.stat_reason += col0; A.stat_cuts += col0; A.stat_nf += col0;
   A.col_mass += col0; A.col_err += col0; A.col_src += col0;
@@ -653,7 +671,7 @@ static int vsfm_launch_range(mppgpu_soe *h, const VsfmArgs &A0, long long col0, 
   VsfmArgs A = A0;
   vsfm_offset_args(A, h->nlev, col0, n, block0);
 #ifdef VSFM2_PROFILE
-  if (!g_prof) { cudaMalloc((void **)&g_prof, 7 * sizeof(long long)); cudaMemset(g_prof, 0, 7 * sizeof(long long)); }
+  if (!g_prof) { cudaMalloc((void **)&g_prof, 9 * sizeof(long long)); cudaMemset(g_prof, 0, 9 * sizeof(long long)); }
   A.prof = g_prof;
 #endif
   const int nlev = h->nlev, nblocks = vsfm_blocks_for(h, n);

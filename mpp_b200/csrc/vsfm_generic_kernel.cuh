@@ -47,6 +47,7 @@ vsfm_step_generic_kernel(const VsfmArgs A, const int satfunc)
       double s = 0.0;
       for (int k = 0; k < A.nss; ++k) {
         const CondDev &c = A.ss[k];
+        if (c.itype != CT_MASS_RATE) continue;                       // the down-regulated sink depends on the pressure: handled per evaluation
         if (c.region == REGION_CELLS) { const double v = c.value[c0 + j]; s += v / FMWH2O; src_kg_l += v; }
         else if (j == (c.region == REGION_TOP ? jtop : jbot)) { const double v = c.value[col]; s += v / FMWH2O; src_kg_l += v; }
       }
@@ -129,6 +130,10 @@ vsfm_step_generic_kernel(const VsfmArgs A, const int satfunc)
         }
         const double por = A.por[c0 + j], vol = area * A.dz[c0 + j];
         b += (por * dden[j] * sat[j] + por * den[j] * dsat[j]) * vol * dtInv;
+        if (A.dr_type && (A.dr_region == REGION_CELLS || j == (A.dr_region == REGION_TOP ? jtop : jbot))) {
+          const long long i = (A.dr_region == REGION_CELLS) ? c0 + j : (long long)col;
+          double rate, dj; downreg_sink(A.dr_type, A.dr_value[i], A.dr_pc[i], A.dr_n[i], X[j], rate, dj); b += dj;
+        }
         jb[j] = b;
       }
       __syncwarp();
@@ -225,6 +230,10 @@ vsfm_step_generic_kernel(const VsfmArgs A, const int satfunc)
         g = g + fl; G_bcflux[k] = fl * FMWH2O;
       }
       g = g - srcs[j];
+      if (A.dr_type && (A.dr_region == REGION_CELLS || j == (A.dr_region == REGION_TOP ? jtop : jbot))) {
+        const long long i = (A.dr_region == REGION_CELLS) ? c0 + j : (long long)col;
+        double rate, dj; downreg_sink(A.dr_type, A.dr_value[i], A.dr_pc[i], A.dr_n[i], W[j], rate, dj); g = g - rate / FMWH2O;
+      }
       G[j] = g; sg += g * g; sw += W[j] * W[j];
     }
     for (int k = 0; k < MAX_BC; ++k) G_bcflux[k] = warp_sum(G_bcflux[k]);   // only the owning lane contributed
@@ -314,6 +323,12 @@ vsfm_step_generic_kernel(const VsfmArgs A, const int satfunc)
         A.smp[c0 + j] = (X[j] - PRESSURE_REF) / (den[j] * FMWH2O * GRAVITY_CONSTANT);
         m_l += m;
       }
+    }
+  }
+  if (A.dr_type && col_ok) {
+    for (int j = lane; j < nlev; j += 32) if (A.dr_region == REGION_CELLS || j == (A.dr_region == REGION_TOP ? jtop : jbot)) {
+      const long long i = (A.dr_region == REGION_CELLS) ? c0 + j : (long long)col;
+      double rate, dj; downreg_sink(A.dr_type, A.dr_value[i], A.dr_pc[i], A.dr_n[i], X[j], rate, dj); src_kg_l += rate;
     }
   }
   const double m_end = warp_sum(m_l), q_col = warp_sum(src_kg_l);

@@ -20,7 +20,7 @@ enum { SNES_ITERATING = 0, SNES_CONVERGED_FNORM_ABS = 2, SNES_CONVERGED_FNORM_RE
        SNES_DIVERGED_LINE_SEARCH = -6, SNES_DIVERGED_DTOL = -9 };
 
 enum { REGION_TOP = 401, REGION_BOTTOM = 402, REGION_CELLS = 403 };
-enum { CT_MASS_RATE = 503, CT_DIRICHLET = 505, CT_SEEPAGE = 509 };
+enum { CT_MASS_RATE = 503, CT_DIRICHLET = 505, CT_SEEPAGE = 509, CT_DOWNREG_CAMPBELL = 512, CT_DOWNREG_FETCH2 = 513 };
 
 struct CondDev {
   const double *value;     // SoE mailbox condition_value: per column (top/bottom regions) or per cell (REGION_CELLS)
@@ -61,8 +61,22 @@ struct VsfmArgs {
   double *block_partials;  // gridDim.x * 8 doubles: deterministic two-stage reduction
   double dt;
   SnesOpts so;
+  // one optional down-regulated sink (COND_DOWNREG_MASS_RATE_CAMPBELL / _FETCH2, GoveqnRichards...:1900-1927, 2158-2188)
+  int dr_type, dr_region; const double *dr_value, *dr_pc, *dr_n;
   long long *prof;         // development aid: per-section cycle counters (nullptr in production)
 };
+
+// Down-regulated mass sink: actual rate [kg/s] and the Jacobian diagonal term it adds (GoveqnRichards...:1900-1927, 2158-2188)
+__device__ __forceinline__ void downreg_sink(int type, double value, double Pc, double n, double P, double &rate, double &djac)
+{
+  const double dP = P - PRESSURE_REF;
+  rate = value; djac = 0.0;
+  if (dP <= 0.0) {
+    const double r = pow(dP / Pc, n);
+    if (type == CT_DOWNREG_CAMPBELL) { const double factor = 1.0 + r; rate = value / factor; djac = (value / FMWH2O) * (n * r) / (dP * (factor * factor)); }
+    else                             { const double factor = exp(-r); rate = value * factor; djac = (value / FMWH2O) * (n * r) * factor / dP; }
+  }
+}
 
 enum { PH_INIT = 0, PH_NEWTON = 1, PH_LS_FULL = 2, PH_LS_QUAD = 3, PH_LS_CUBIC = 4, PH_DONE = 5 };
 

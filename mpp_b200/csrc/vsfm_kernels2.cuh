@@ -200,7 +200,7 @@ vsfm_step2_kernel(const VsfmArgs A)
 #pragma unroll
     for (int k = 0; k < MAX_SS; ++k) {
       v0[k] = 0.0; v1[k] = 0.0;
-      if (k < A.nss) {
+      if (k < A.nss && A.ss[k].itype == CT_MASS_RATE) {
         const CondDev &c = A.ss[k];
         const bool percell = (c.region == REGION_CELLS);
         const int jown = (c.region == REGION_TOP) ? jtop : jbot;
@@ -215,6 +215,15 @@ vsfm_step2_kernel(const VsfmArgs A)
 #pragma unroll
     for (int k = 0; k < MAX_SS; ++k) { sa_ += v0[k] * RFMW; sb_ += v1[k] * RFMW; src_kg += v0[k] + v1[k]; }
     PA(PI_SRC) = sa_; PB(PI_SRC) = sb_;
+  }
+
+  // optional down-regulated sink: which of this lane's cells it touches, and where its per-connection data sits
+  bool dr_a = false, dr_b = false; long long dr_ia = 0, dr_ib = 0;
+  if (A.dr_type) {
+    const bool percell = (A.dr_region == REGION_CELLS);
+    const int jown = (A.dr_region == REGION_TOP) ? jtop : jbot;
+    dr_a = a.valid && (percell || j0 == jown); dr_b = b.valid && (percell || j1 == jown);
+    dr_ia = percell ? cell0 : (long long)col; dr_ib = percell ? cell0 + 1 : (long long)col;
   }
 
   // boundary conditions (MeshType.F90:723-806): top -> unit vector (0,0,-1), bottom -> (0,0,+1); dist_up = 0
@@ -253,7 +262,7 @@ vsfm_step2_kernel(const VsfmArgs A)
   double initslope = -1.0, lambda = 1.0, lambdaprev = 1.0, gprev = 0.0;
 
 #ifdef VSFM2_PROFILE
-  long long pt_newton = 0, pt_eval = 0, pt_logic = 0, pn_newton = 0, pn_eval = 0; const long long pt_start = clock64();
+  long long pt_newton = 0, pt_eval = 0, pt_logic = 0, pn_newton = 0, pn_eval = 0, pt_curves = 0, pt_red = 0; const long long pt_start = clock64();
 #endif
   for (;;) {
 #ifdef VSFM2_PROFILE
@@ -305,6 +314,12 @@ vsfm_step2_kernel(const VsfmArgs A)
       }
       if (a.valid) { const double por = PA(PI_POR); dia_a += (por * dden_a * a.sat + por * den_a * a.dsat) * PA(PI_VOL) * dtInv; }   // AccumDeriv (:1673-1675), dpor_dP = 0
       if (b.valid) { const double por = PB(PI_POR); dia_b += (por * dden_b * b.sat + por * den_b * b.dsat) * PB(PI_VOL) * dtInv; }
+
+      if (A.dr_type) {                               // uniform branch; rare path, data re-read from HBM / L2
+        double rate, dj;
+        if (dr_a) { downreg_sink(A.dr_type, A.dr_value[dr_ia], A.dr_pc[dr_ia], A.dr_n[dr_ia], a.X, rate, dj); dia_a += dj; }
+        if (dr_b) { downreg_sink(A.dr_type, A.dr_value[dr_ib], A.dr_pc[dr_ib], A.dr_n[dr_ib], b.X, rate, dj); dia_b += dj; }
+      }
 
       // ---- J Y = F: eliminate this lane's second unknown, PCR over the first unknowns, back-substitute ----
       const double Fa = a.valid ? a.F : 0.0, Fb = b.valid ? b.F : 0.0;
@@ -378,6 +393,9 @@ vsfm_step2_kernel(const VsfmArgs A)
     const SatParams spa = par_sp<SATFUNC>(pa), spb = par_sp<SATFUNC>(pb);
     const double fla = (SATFUNC != SATFUNC_VG) ? PA(PI_FLIQ) : 1.0, flb = (SATFUNC != SATFUNC_VG) ? PB(PI_FLIQ) : 1.0;
     sat_values_pair<SATFUNC>(spa, spb, a.W, b.W, fla, flb, sa, sb);
+#ifdef VSFM2_PROFILE
+    const long long pt1b = clock64(); pt_curves += pt1b - pt1 + (long long)(1e-300 * (sa.kr + sb.kr));
+#endif
     double dena, ddena, denb, ddenb, Ga, Gb, G_bcflux[NBC];
     density_fixedT(A.dtab, a.W, dena, ddena);
     density_fixedT(A.dtab, b.W, denb, ddenb);
@@ -410,6 +428,11 @@ vsfm_step2_kernel(const VsfmArgs A)
         }
       }
       Ga = Ga - PA(PI_SRC); Gb = Gb - PB(PI_SRC);
+      if (A.dr_type) {
+        double rate, dj;
+        if (dr_a) { downreg_sink(A.dr_type, A.dr_value[dr_ia], A.dr_pc[dr_ia], A.dr_n[dr_ia], a.W, rate, dj); Ga = Ga - rate * RFMW; }
+        if (dr_b) { downreg_sink(A.dr_type, A.dr_value[dr_ib], A.dr_pc[dr_ib], A.dr_n[dr_ib], b.W, rate, dj); Gb = Gb - rate * RFMW; }
+      }
       if (!a.valid) Ga = 0.0;
       if (!b.valid) Gb = 0.0;
     }
@@ -417,28 +440,57 @@ vsfm_step2_kernel(const VsfmArgs A)
     // two reciprocal chains run in the shadow of the flux + norm reductions (discarded for rejected line-search trial points)
     double dsat_a, dkr_a, dsat_b, dkr_b;
     sat_derivs_pair<SATFUNC>(spa, spb, sa, sb, fla, flb, dsat_a, dkr_a, dsat_b, dkr_b);
+#ifdef VSFM2_PROFILE
+    const long long pt1c = clock64() + (long long)(1e-300 * (Ga + Gb));
+#endif
     const double g2 = col_sum<LPC>(Ga * Ga + Gb * Gb);
     const double w2 = col_sum<LPC>((a.valid ? a.W * a.W : 0.0) + (b.valid ? b.W * b.W : 0.0));
     nfuncs += 1;
 
 #ifdef VSFM2_PROFILE
-    const long long pt2 = clock64(); pt_eval += pt2 - pt1; pn_eval++;
+    const long long pt2 = clock64() + (long long)(1e-300 * (g2 + w2)); pt_eval += pt2 - pt1; pn_eval++; pt_red += pt2 - pt1c;
 #endif
     // ================= after the evaluation: line-search / convergence logic (squared norms) =================
-    bool take = false;          // adopt W as the new iterate (and its aux vars)
+    // Fast path first (PETSc's order of tests, restated as predicates + selects so that the common outcome -- trial point
+    // accepted, Newton continues or converges -- costs one branch): `take` = adopt W as the new iterate and its aux vars.
     const bool g_bad = !(g2 == g2) || (g2 > 1.7e308);                   // NaN or Inf
     const bool out_of_funcs = (nfuncs >= so.max_funcs && so.max_funcs >= 0);
     const bool tiny_step = (stol2 * x2 > y2);                           // stol * xnorm > ynorm
-    if (phase == PH_INIT) {
-      // SNESSolve_NEWTONLS: F(X0) and the iteration-0 convergence test
-      take = true;
-    } else if (phase == PH_LS_FULL) {
+    const bool is_init = (phase == PH_INIT), is_full = (phase == PH_LS_FULL), is_bt = (phase == PH_LS_QUAD || phase == PH_LS_CUBIC);
+    ls_count += (phase == PH_LS_CUBIC) ? 1 : 0;                         // cubic trial points evaluated so far
+    const double ls_rhs = .5 * f2 + lambda * so.ls_alpha * initslope;   // sufficient decrease: <= for the full step, < afterwards
+    const bool suff = !g_bad && (is_full ? (.5 * g2 <= ls_rhs) : (.5 * g2 < ls_rhs));
+    // (PETSc leaves the cubic loop after max_its fits and keeps the last point)
+    const bool take = is_init || (is_full && suff) || (is_bt && !g_bad && (suff || ls_count >= so.ls_max_its));
+
+    if (take) {
+      // "copy the solution over": X <- W, F <- G; the aux vars of this point feed the next Jacobian / PostSolve
+      a.X = a.W; b.X = b.W; a.F = Ga; b.F = Gb;
+      a.kr = sa.kr; a.sat = sa.sat; b.kr = sb.kr; b.sat = sb.sat;
+      a.dsat = dsat_a; a.dkr = dkr_a; b.dsat = dsat_b; b.dkr = dkr_b;
+      if (HAS_BC) {
+#pragma unroll
+        for (int k = 0; k < NBC; ++k) bcFlux[k] = G_bcflux[k];
+      }
+      f2 = g2; x2 = w2;
+      // SNESConvergedDefault: it == 0 sets ttol = fnorm * rtol and only tests NaN / atol; it > 0 tests, in this order,
+      // atol, function count, rtol, stol, divergence, max_it (lowest priority assigned first)
+      its = is_init ? 0 : its + 1;
+      ttol2 = is_init ? g2 * rtol2 : ttol2; f2_0 = is_init ? g2 : f2_0;
+      int reason = (its >= so.max_it) ? SNES_DIVERGED_MAX_IT : 0;
+      reason = (so.divtol > 0 && g2 > divtol2 * f2_0) ? SNES_DIVERGED_DTOL : reason;
+      reason = (y2 < stol2 * x2) ? SNES_CONVERGED_SNORM_RELATIVE : reason;
+      reason = (g2 <= ttol2) ? SNES_CONVERGED_FNORM_RELATIVE : reason;
+      reason = out_of_funcs ? SNES_DIVERGED_FUNCTION_COUNT : reason;
+      reason = (g2 < atol2) ? SNES_CONVERGED_FNORM_ABS : reason;
+      if (is_init) reason = g_bad ? SNES_DIVERGED_FNORM_NAN : ((g2 < atol2) ? SNES_CONVERGED_FNORM_ABS : 0);
+      last_reason = reason ? reason : last_reason;
+      phase = reason ? -1 : PH_NEWTON;
+    } else if (is_full) {
       if (g_bad) {
         if (lambda <= so.ls_minlambda) { last_reason = SNES_DIVERGED_FNORM_NAN; phase = -1; }
         else if (out_of_funcs)         { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
         else { lambda = .5 * lambda; a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); }
-      } else if (.5 * g2 <= .5 * f2 + lambda * so.ls_alpha * initslope) {
-        take = true;
       } else if (tiny_step) {
         // "full step didn't work and the step is tiny": line search fails, SNES then sees stol*xnorm > ynorm
         last_reason = SNES_CONVERGED_SNORM_RELATIVE; phase = -1;
@@ -451,15 +503,10 @@ vsfm_step2_kernel(const VsfmArgs A)
         lambda = (lt <= .1 * lambda) ? .1 * lambda : lt;
         a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); phase = PH_LS_QUAD; ls_count = 0;
       }
-    } else if (phase == PH_LS_QUAD || phase == PH_LS_CUBIC) {
-      if (phase == PH_LS_CUBIC) ls_count += 1;                          // cubic trial points evaluated so far
+    } else if (is_bt) {
       const int ls_fail = tiny_step ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
       if (g_bad) {
         last_reason = ls_fail; phase = -1;
-      } else if (.5 * g2 < .5 * f2 + lambda * so.ls_alpha * initslope) {
-        take = true;
-      } else if (ls_count >= so.ls_max_its) {
-        take = true;                                                    // PETSc leaves the cubic loop after max_its fits and keeps the last point
       } else if (lambda <= so.ls_minlambda) {
         last_reason = ls_fail; phase = -1;
       } else if (out_of_funcs) {
@@ -479,33 +526,6 @@ vsfm_step2_kernel(const VsfmArgs A)
         a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); phase = PH_LS_CUBIC;
       }
     }
-
-    if (take) {
-      // "copy the solution over": X <- W, F <- G; the aux vars of this point feed the next Jacobian / PostSolve
-      a.X = a.W; b.X = b.W; a.F = Ga; b.F = Gb;
-      a.kr = sa.kr; a.sat = sa.sat; b.kr = sb.kr; b.sat = sb.sat;
-      a.dsat = dsat_a; a.dkr = dkr_a; b.dsat = dsat_b; b.dkr = dkr_b;
-      if (HAS_BC) {
-#pragma unroll
-        for (int k = 0; k < NBC; ++k) bcFlux[k] = G_bcflux[k];
-      }
-      f2 = g2; x2 = w2;
-      int reason = 0;
-      if (phase == PH_INIT) {
-        its = 0; ttol2 = g2 * rtol2; f2_0 = g2;                         // SNESConvergedDefault, it == 0: ttol = fnorm * rtol
-        if (g_bad)           reason = SNES_DIVERGED_FNORM_NAN;
-        else if (g2 < atol2) reason = SNES_CONVERGED_FNORM_ABS;
-      } else {
-        its += 1;
-        if (g2 < atol2)           reason = SNES_CONVERGED_FNORM_ABS;    // SNESConvergedDefault, it > 0
-        else if (out_of_funcs)    reason = SNES_DIVERGED_FUNCTION_COUNT;
-        else if (g2 <= ttol2)     reason = SNES_CONVERGED_FNORM_RELATIVE;
-        else if (y2 < stol2 * x2) reason = SNES_CONVERGED_SNORM_RELATIVE;
-        else if (so.divtol > 0 && g2 > divtol2 * f2_0) reason = SNES_DIVERGED_DTOL;
-        else if (its >= so.max_it) reason = SNES_DIVERGED_MAX_IT;
-      }
-      if (reason) { last_reason = reason; phase = -1; } else phase = PH_NEWTON;
-    }
 #ifdef VSFM2_PROFILE
     pt_logic += clock64() - pt2;
 #endif
@@ -516,6 +536,7 @@ vsfm_step2_kernel(const VsfmArgs A)
     atomicAdd((unsigned long long *)A.prof + 2, (unsigned long long)pt_eval);   atomicAdd((unsigned long long *)A.prof + 3, (unsigned long long)pn_eval);
     atomicAdd((unsigned long long *)A.prof + 4, (unsigned long long)pt_logic);  atomicAdd((unsigned long long *)A.prof + 5, (unsigned long long)(clock64() - pt_start));
     atomicAdd((unsigned long long *)A.prof + 6, 1ull);
+    atomicAdd((unsigned long long *)A.prof + 7, (unsigned long long)pt_curves); atomicAdd((unsigned long long *)A.prof + 8, (unsigned long long)pt_red);
   }
 #endif
 
@@ -549,6 +570,11 @@ vsfm_step2_kernel(const VsfmArgs A)
       A.bc[k].mass_exc[col] += bcMassExc[k];
       bc_exc += bcMassExc[k];
     }
+  }
+  if (A.dr_type) {                                 // the rate actually withdrawn at the end-of-step state enters the column's balance
+    double rate, dj;
+    if (dr_a) { downreg_sink(A.dr_type, A.dr_value[dr_ia], A.dr_pc[dr_ia], A.dr_n[dr_ia], a.X, rate, dj); src_kg += rate; }
+    if (dr_b) { downreg_sink(A.dr_type, A.dr_value[dr_ib], A.dr_pc[dr_ib], A.dr_n[dr_ib], b.X, rate, dj); src_kg += rate; }
   }
   const double m_end = col_sum<LPC>(mass);
   const double q_col = col_sum<LPC>(src_kg);

@@ -50,13 +50,13 @@ enum {
   SOIL_TOP_CELLS = 401, SOIL_BOTTOM_CELLS = 402, SOIL_CELLS = 403,
   COND_NULL = 500, COND_BC = 501, COND_SS = 502, COND_MASS_RATE = 503, COND_MASS_FLUX = 504,
   COND_DIRICHLET = 505, COND_DIRICHLET_FRM_OTR_GOVEQ = 506, COND_HEAT_FLUX = 507,
-  COND_SEEPAGE_BC = 509, COND_HEAT_RATE = 511,
+  COND_SEEPAGE_BC = 509, COND_HEAT_RATE = 511, COND_DOWNREG_MASS_RATE_CAMPBELL = 512, COND_DOWNREG_MASS_RATE_FETCH2 = 513,
   VAR_PRESSURE = 604, VAR_TEMPERATURE = 605, VAR_BC_SS_CONDITION = 607, VAR_LIQ_SAT = 608,
   VAR_MASS = 610, VAR_SOIL_MATRIX_POT = 611, VAR_FRAC_LIQ_SAT = 612,
   VAR_LIQ_AREAL_DEN = 615, VAR_ICE_AREAL_DEN = 617, VAR_FRAC = 618, VAR_SNOW_WATER = 619,
   VAR_NUM_SNOW_LYR = 620, VAR_DHS_DT = 621, VAR_THERMAL_COND = 622, VAR_HEAT_CAP = 623,
   VAR_ACTIVE = 624, VAR_DZ = 627, VAR_DIST_UP = 628, VAR_DIST_DN = 629, VAR_TUNING_FACTOR = 630,
-  VAR_MASS_FLUX = 644,
+  VAR_POT_MASS_SINK_PRESSURE = 638, VAR_POT_MASS_SINK_EXPONENT = 639, VAR_MASS_FLUX = 644,
   AUXVAR_INTERNAL = 701, AUXVAR_BC = 702, AUXVAR_SS = 703
 };
 

@@ -27,6 +27,7 @@ typedef struct {
   orc_rich_auxvar *aux;     /* GE aux_vars_bc / aux_vars_ss           */
   double *flux;             /* boundary_flux / ss_flux [kg/s]          */
   double *mass_exc;         /* bnd_mass_exc                            */
+  double *pot_pressure, *pot_exponent;   /* aux_vars_ss%pot_mass_sink_{pressure,exponent} (down-regulated sinks) */
 } vcond;
 
 struct orc_vsfm {
@@ -73,7 +74,7 @@ orc_vsfm *orc_vsfm_create(int ncol, int nlev)
   return p;
 }
 
-static void vcond_free(vcond *c) { free(c->conn); free(c->value); free(c->soe_value); free(c->aux); free(c->flux); free(c->mass_exc); }
+static void vcond_free(vcond *c) { free(c->conn); free(c->value); free(c->soe_value); free(c->aux); free(c->flux); free(c->mass_exc); free(c->pot_pressure); free(c->pot_exponent); }
 
 void orc_vsfm_destroy(orc_vsfm *p)
 {
@@ -142,6 +143,7 @@ int orc_vsfm_add_condition(orc_vsfm *p, int ss_or_bc, int cond_type, int region)
   cd->nconn = n;
   cd->conn = (orc_conn *)calloc(n, sizeof(orc_conn));
   cd->value = (double *)calloc(n, sizeof(double)); cd->soe_value = (double *)calloc(n, sizeof(double));
+  cd->pot_pressure = (double *)calloc(n, sizeof(double)); cd->pot_exponent = (double *)calloc(n, sizeof(double));
   /* SS aux vars are never computed (RichardsODEPressureUpdateAuxVarsSS returns immediately, GoveqnRichards...:1578),
    * so only BCs carry GE aux vars here */
   cd->aux = ss_or_bc == COND_BC ? (orc_rich_auxvar *)calloc(n, sizeof(orc_rich_auxvar)) : NULL;
@@ -265,8 +267,11 @@ int orc_vsfm_set_data(orc_vsfm *p, int auxvar_type, int var_type, int cond_id, c
     if (auxvar_type == AUXVAR_BC) { if (cond_id < 1 || cond_id > p->nbc) return 3; cd = &p->bc[cond_id - 1]; }
     else if (auxvar_type == AUXVAR_SS) { if (cond_id < 1 || cond_id > p->nss) return 3; cd = &p->ss[cond_id - 1]; }
     else return 4;
-    if (var_type != VAR_BC_SS_CONDITION) return 2;
     if (n > cd->nconn) return 1;
+    /* VSFMMPPSetSourceSinkAuxVarRealValue (MultiPhysicsProbVSFM.F90:1437-1520): straight into the GE's aux_vars_ss */
+    if (auxvar_type == AUXVAR_SS && var_type == VAR_POT_MASS_SINK_PRESSURE) { for (i = 0; i < n; i++) cd->pot_pressure[i] = data[i]; return 0; }
+    if (auxvar_type == AUXVAR_SS && var_type == VAR_POT_MASS_SINK_EXPONENT) { for (i = 0; i < n; i++) cd->pot_exponent[i] = data[i]; return 0; }
+    if (var_type != VAR_BC_SS_CONDITION) return 2;
     for (i = 0; i < n; i++) cd->soe_value[i] = data[i];
     return 0;
   }
@@ -382,6 +387,16 @@ static void divergence(orc_vsfm *p, int c0, int c1, double *ff)
       if (cd->itype == COND_MASS_RATE) {
         ff[cell] = ff[cell] - cd->value[i] / ORC_FMWH2O;
         cd->flux[i] = cd->value[i];
+      } else if (cd->itype == COND_DOWNREG_MASS_RATE_CAMPBELL) {       /* GoveqnRichards...:1900-1913 */
+        double dP = p->aux_in[cell].pressure - ORC_PRESSURE_REF, Pc = cd->pot_pressure[i], n = cd->pot_exponent[i], factor;
+        if (dP <= 0.0) factor = 1.0 + pow(dP / Pc, n); else factor = 1.0;
+        ff[cell] = ff[cell] - cd->value[i] / factor / ORC_FMWH2O;
+        cd->flux[i] = cd->value[i] / factor;
+      } else if (cd->itype == COND_DOWNREG_MASS_RATE_FETCH2) {         /* :1915-1928 */
+        double dP = p->aux_in[cell].pressure - ORC_PRESSURE_REF, Pc = cd->pot_pressure[i], n = cd->pot_exponent[i], factor;
+        if (dP <= 0.0) factor = exp(-pow(dP / Pc, n)); else factor = 1.0;
+        ff[cell] = ff[cell] - cd->value[i] * factor / ORC_FMWH2O;
+        cd->flux[i] = cd->value[i] * factor;
       }
     }
   }
@@ -423,7 +438,27 @@ static void jacobian_range(orc_vsfm *p, int c0, int c1, double *ja, double *jb, 
       jb[cell] += -Jdn;
     }
   }
-  /* COND_MASS_RATE source/sinks have no Jacobian contribution (:2150-2151) */
+  /* COND_MASS_RATE source/sinks have no Jacobian contribution (:2150-2151); down-regulated sinks add a diagonal term (:2158-2188) */
+  for (k = 0; k < p->nss; k++) {
+    vcond *cd = &p->ss[k];
+    int i0 = cd->per_cell ? c0 * nlev : c0, i1 = cd->per_cell ? c1 * nlev : c1, i;
+    if (cd->itype != COND_DOWNREG_MASS_RATE_CAMPBELL && cd->itype != COND_DOWNREG_MASS_RATE_FETCH2) continue;
+    for (i = i0; i < i1; i++) {
+      int cell = cd->conn[i].id_dn;
+      double dP, Pc, n, factor, val;
+      if (!p->is_active[cell]) continue;
+      dP = p->aux_in[cell].pressure - ORC_PRESSURE_REF; Pc = cd->pot_pressure[i]; n = cd->pot_exponent[i];
+      if (dP > 0.0) continue;
+      if (cd->itype == COND_DOWNREG_MASS_RATE_CAMPBELL) {
+        factor = 1.0 + pow(dP / Pc, n);
+        val = (cd->value[i] / ORC_FMWH2O) * (n * pow(dP / Pc, n)) / (dP * pow(factor, 2.0));
+      } else {
+        factor = exp(-pow(dP / Pc, n));
+        val = (cd->value[i] / ORC_FMWH2O) * (n * pow(dP / Pc, n)) * factor / dP;
+      }
+      jb[cell] += val;
+    }
+  }
   for (ic = c0 * nlev; ic < c1 * nlev; ic++) {
     double derivative;
     if (p->is_active[ic]) {

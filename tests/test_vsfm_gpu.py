@@ -341,3 +341,52 @@ def test_seepage_boundary_condition_matches_oracle(mpp, oracle, nz):
         assert its_g == its_o or (its_o <= 2 and its_g <= 3), (step, its_g, its_o)
         dry |= bool(Po[0] < K.PRESSURE_REF); wet |= bool(Po[0] > K.PRESSURE_REF)
     assert wet and dry, "the column must start with a closed seepage face and end with an open one"
+
+
+@pytest.mark.parametrize("cond_type", [K.COND_DOWNREG_MASS_RATE_CAMPBELL, K.COND_DOWNREG_MASS_RATE_FETCH2])
+@pytest.mark.parametrize("nlev", [15, 40])
+def test_down_regulated_sinks_match_oracle(mpp, oracle, cond_type, nlev):
+    """COND_DOWNREG_MASS_RATE_CAMPBELL / _FETCH2 (GoveqnRichards...:1900-1927 residual, 2158-2188 Jacobian diagonal): a root-uptake
+    sink over all soil cells that shuts down as the soil dries (parameters via VAR_POT_MASS_SINK_PRESSURE / _EXPONENT,
+    MultiPhysicsProbVSFM.F90:1437-1520).  Fast kernel (15 layers) and generic kernel (40 layers)."""
+    ncol = 200 if nlev == 15 else 6
+    d = PB.elm_vsfm_inputs(ncol, nlev)
+    rng = np.random.default_rng(21)
+    uptake = -rng.uniform(2e-6, 2e-5, ncol * nlev)                       # kg/s per cell (a sink)
+    pc = np.full(ncol * nlev, -1.5e5) * rng.uniform(0.5, 2.0, ncol * nlev)
+    ex = np.full(ncol * nlev, 3.0)
+
+    def build(cls, **kw):
+        p = cls(ncol, nlev, **kw)
+        p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"])
+        infil = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
+        sink = p.add_condition(1, K.COND_SS, cond_type, K.SOIL_CELLS)
+        p.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], "van_genuchten", K.DENSITY_TGDPB01)
+        p.restart(d["press_ic"])
+        p.set_data(K.AUXVAR_SS, K.VAR_POT_MASS_SINK_PRESSURE, sink, pc)
+        p.set_data(K.AUXVAR_SS, K.VAR_POT_MASS_SINK_EXPONENT, sink, ex)
+        return p, infil, sink
+    p, gi, gs = build(mpp.VSFM)
+    o, oi, os_ = build(oracle.OracleVSFM, per_column=True, nthreads=8)
+    for step in range(3):
+        for s, i1, i2 in ((p, gi, gs), (o, oi, os_)):
+            s.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, i1, d["infil"])
+            s.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, i2, uptake)
+            s.pre_step_dt()
+        conv, reason = p.step_dt(1800.0, step + 1); convo, reasono = o.step_dt(1800.0, step + 1)
+        p.post_step_dt(); o.post_step_dt()
+        assert conv == convo
+        sg, so_ = p.stats(), o.stats()
+        assert np.array_equal(sg["dt_cuts"], so_["dt_cuts"]) and np.array_equal(sg["reasons"] > 0, so_["reasons"] > 0)
+        ok = (so_["dt_cuts"] == 0) & (so_["reasons"] > 0)           # (the kink of the Campbell factor at P = P_ref makes a few columns cut dt)
+        assert ok.mean() > 0.8
+        P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1).reshape(ncol, nlev); Po = o.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1).reshape(ncol, nlev)
+        assert relmax_p(P[ok], Po[ok]) < RTOL, step
+        assert np.mean(sg["newton_its"][ok] != so_["newton_its"][ok]) < 0.02
+    Po = Po.reshape(-1)
+    # the sink is really down-regulated somewhere (dry cells) and the per-column balance uses the regulated rate
+    dP = Po - K.PRESSURE_REF
+    assert np.any((dP < 0) & (np.abs(dP / pc) ** 3 > 0.05))
+    err = np.zeros(ncol, dtype=np.float64)
+    sums, maxs = p.mass_balance()
+    assert np.isfinite(maxs[0])
