@@ -154,6 +154,8 @@ static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
   A.dt = dt; A.cnfac = t->cnfac;
   A.por = t->por; A.tkmg = t->tkmg; A.tkdry = t->tkdry; A.csol = t->csol; A.dz = h->dz.p; A.area = h->area.p;
   A.dist_up = t->custom_dist ? t->dist_up : nullptr; A.dist_dn = t->custom_dist ? t->dist_dn : nullptr;
+  A.dist_uniform = (t->custom_dist && t->dist_uniform && h->nlev <= 32) ? 1 : 0;
+  if (A.dist_uniform) { memcpy(A.lay_du, t->lay_du, sizeof(A.lay_du)); memcpy(A.lay_dd, t->lay_dd, sizeof(A.lay_dd)); }
   A.lun_type = t->lun_type;
   A.T_in = t->T_cur; A.liq = t->liq; A.ice = t->ice; A.snow_water = t->snow_water; A.tuning = t->tuning;
   A.nsnow = t->nsnow; A.active = t->active;
@@ -174,7 +176,7 @@ static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
   CK(cudaEventRecord(h->ev0, h->stream));
   const int nlev = h->nlev;
   if (nlev <= 32) {
-    if (nlev <= 16) thermal_step_kernel<16><<<nblk((long long)h->ncol * 16, TH_TILE), TH_TILE, 0, h->stream>>>(A);
+    if (nlev <= 16) thermal_step2_kernel<8><<<nblk((long long)h->ncol * 8, TH_TILE), TH_TILE, 0, h->stream>>>(A);
     else            thermal_step_kernel<32><<<nblk((long long)h->ncol * 32, TH_TILE), TH_TILE, 0, h->stream>>>(A);
   } else {
     if (!t->work) CK(cudaMalloc((void **)&t->work, 4 * h->ncells * sizeof(double)));

@@ -29,6 +29,8 @@ struct ThermalArgs {
   // static
   const double *por, *tkmg, *tkdry, *csol, *dz, *area;
   const double *dist_up, *dist_dn;     // per cell: connection j -> j+1 (nullptr: dz/2 of the two cells)
+  int dist_uniform;                     // every column has the same distances (ELM's fixed vertical grid): per-layer copies below,
+  double lay_du[32], lay_dd[32];        //   read from the kernel's constant bank instead of 16 B per cell from HBM
   const int *lun_type;                  // per column
   // per-step inputs (SoE mailbox)
   const double *T_in, *liq, *ice, *snow_water, *tuning;
@@ -153,7 +155,8 @@ thermal_step_kernel(const ThermalArgs A)
     const double liq = A.liq[cell], ice = A.ice[cell], snoww = A.snow_water[cell];
     const double por = A.por[cell], tkmg = A.tkmg[cell], tkdry = A.tkdry[cell], csol = A.csol[cell];
     const int nsnow = A.nsnow[cell];
-    if (A.dist_up) { du = A.dist_up[cell]; dd = A.dist_dn[cell]; }
+    if (A.dist_uniform) { du = A.lay_du[j]; dd = A.lay_dd[j]; }
+    else if (A.dist_up) { du = A.dist_up[cell]; dd = A.dist_dn[cell]; }
     thermal_auxvar(A, A.lun_type[col], j < A.nlevsoi, T, liq, ice, snoww, nsnow, por, tkmg, tkdry, csol, dz, tk, hc);
     if (A.therm_cond) { A.therm_cond[cell] = tk; A.heat_cap[cell] = hc; }
   }
@@ -162,7 +165,7 @@ thermal_step_kernel(const ThermalArgs A)
   const double T_d = __shfl_down_sync(FULL, T, 1, GROUP), tk_d = __shfl_down_sync(FULL, tk, 1, GROUP);
   const double dz_d = __shfl_down_sync(FULL, dz, 1, GROUP);
   const int act_d = __shfl_down_sync(FULL, act, 1, GROUP);
-  if (!A.dist_up) { du = 0.5 * dz; dd = 0.5 * dz_d; }
+  if (!A.dist_up && !A.dist_uniform) { du = 0.5 * dz; dd = 0.5 * dz_d; }
   double cval = 0.0, flux = 0.0;
   if (valid && j < nlev - 1 && act && act_d) {
     // kav / dist with kav the distance-weighted harmonic mean: tk tk_d (du+dd) / (tk dd + tk_d du) / (du+dd)
@@ -203,6 +206,135 @@ thermal_step_kernel(const ThermalArgs A)
   if (valid) A.T_out[cell] = x;
 }
 
+// Two cells per lane, 8 lanes per column, 4 columns per warp (nlev <= 16): half the shuffles and a 3-stage instead of a
+// 4-stage reduction for the same cells.  The lane's second row is eliminated in-lane (odd-even step), the remaining
+// one-row-per-lane system goes through normalised PCR over 8 lanes, the second unknown is back-substituted in-lane.
+// Both cells' aux-var chains (log, exp, reciprocals) sit in one basic block and overlap.
+struct ThermalCell {
+  double T, tk, hc, dz, tf, du, dd, ssum, bb, rhs;
+  int act;
+};
+
+template <int LPC>
+__device__ __forceinline__ double thermal_pcr_unit(double al, double ga, double de)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+#pragma unroll
+  for (int s = 1; s < LPC; s <<= 1) {
+    const double al_m = __shfl_up_sync(FULL, al, s, LPC),   ga_m = __shfl_up_sync(FULL, ga, s, LPC);
+    const double de_m = __shfl_up_sync(FULL, de, s, LPC);
+    const double al_p = __shfl_down_sync(FULL, al, s, LPC), ga_p = __shfl_down_sync(FULL, ga, s, LPC);
+    const double de_p = __shfl_down_sync(FULL, de, s, LPC);
+    const double r = rcp(1.0 - al * ga_m - ga * al_p);
+    de = (de - al * de_m - ga * de_p) * r;
+    al = (-al * al_m) * r;
+    ga = (-ga * ga_p) * r;
+  }
+  return de;
+}
+
+__device__ __forceinline__ void thermal_cell_load(const ThermalArgs &A, ThermalCell &c, bool valid, long long cell, int col, int j, int jtop, int jbot)
+{
+  c.T = 0.0; c.tk = 1.0; c.hc = 0.0; c.dz = 1.0; c.tf = 1.0; c.du = 0.5; c.dd = 0.5; c.ssum = 0.0; c.act = 0;
+  if (valid) {
+    c.T = A.T_in[cell]; c.dz = A.dz[cell]; c.tf = A.tuning[cell]; c.act = A.active[cell];
+    const double liq = A.liq[cell], ice = A.ice[cell], snoww = A.snow_water[cell];
+    const double por = A.por[cell], tkmg = A.tkmg[cell], tkdry = A.tkdry[cell], csol = A.csol[cell];
+    const int nsnow = A.nsnow[cell];
+    if (A.dist_uniform) { c.du = A.lay_du[j]; c.dd = A.lay_dd[j]; }
+    else if (A.dist_up) { c.du = A.dist_up[cell]; c.dd = A.dist_dn[cell]; }
+#pragma unroll
+    for (int k = 0; k < TH_MAX_SS; ++k) if (k < A.nss) {          // COND_HEAT_RATE
+      if (A.ss_region[k] == 403) c.ssum += A.ss_value[k][cell];
+      else if (j == (A.ss_region[k] == 401 ? jtop : jbot)) c.ssum += A.ss_value[k][col];
+    }
+    thermal_auxvar(A, A.lun_type[col], j < A.nlevsoi, c.T, liq, ice, snoww, nsnow, por, tkmg, tkdry, csol, c.dz, c.tk, c.hc);
+    if (A.therm_cond) { A.therm_cond[cell] = c.tk; A.heat_cap[cell] = c.hc; }
+  }
+}
+
+// boundary-condition terms of the cell that sits at the top / bottom of its column (as thermal_step_kernel)
+__device__ __forceinline__ void thermal_cell_bc(const ThermalArgs &A, ThermalCell &c, long long cell, int col, int j, int jtop, int jbot, double area)
+{
+  const double cnfac = A.cnfac;
+#pragma unroll
+  for (int k = 0; k < 2; ++k) {
+    if (A.bc_type[k] == 0 || j != (k == 0 ? jtop : jbot)) continue;
+    if (A.bc_type[k] == 507) {                    // COND_HEAT_FLUX: value = H - dH/dT * T_cell (GoveqnThermalKSP...:344-348)
+      const double H = A.bc_value[k][col], dH = A.bc_dhsdT[k][col], fr = A.bc_frac[k][col];
+      c.rhs = c.rhs + (H - dH * c.T) * fr * area;
+      c.bb += -fr * ((area == 1.0) ? dH : pow(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
+    } else if (A.bc_active[k][col] != 0.0) {      // COND_DIRICHLET
+      double tkb, hcb;
+      const double Tb = A.bc_value[k][col];
+      thermal_auxvar(A, A.lun_type[col], false, Tb, 0.0, 0.0, 0.0, 0, A.por[cell], A.tkmg[cell], A.tkdry[cell], A.csol[cell], c.dz, tkb, hcb);
+      const double bdu = 0.0, bdd = 0.5 * c.dz, dist = bdu + bdd;
+      const double kav = tkb * c.tk * dist / (tkb * bdd + c.tk * bdu);
+      c.rhs = c.rhs + kav / dist * Tb * A.stale_area;
+      c.bb += A.bc_frac[k][col] * (1.0 - cnfac) * kav / dist * area;
+    }
+  }
+}
+
+template <int LPC>
+__global__ void __launch_bounds__(TH_TILE, 6)
+thermal_step2_kernel(const ThermalArgs A)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  const int nlev = A.nlev;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = (int)(tid / LPC), l = (int)(tid % LPC);
+  const int j0 = 2 * l, j1 = 2 * l + 1;
+  const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
+  const double dt = A.dt, cnfac = A.cnfac;
+  const bool col_ok = col < A.ncol, va = col_ok && j0 < nlev, vb = col_ok && j1 < nlev;
+  const long long cell0 = (long long)col * nlev + j0;
+  const double area = col_ok ? A.area[col] : 1.0;
+
+  ThermalCell a, b;
+  thermal_cell_load(A, a, va, cell0, col, j0, jtop, jbot);
+  thermal_cell_load(A, b, vb, cell0 + 1, col, j1, jtop, jbot);
+
+  // connections 2l -> 2l+1 (in-lane) and 2l+1 -> 2(l+1) (the next lane's first cell)
+  const double T_n = __shfl_down_sync(FULL, a.T, 1, LPC), tk_n = __shfl_down_sync(FULL, a.tk, 1, LPC), dz_n = __shfl_down_sync(FULL, a.dz, 1, LPC);
+  const int act_n = __shfl_down_sync(FULL, a.act, 1, LPC);
+  if (!A.dist_up && !A.dist_uniform) { a.du = 0.5 * a.dz; a.dd = 0.5 * b.dz; b.du = 0.5 * b.dz; b.dd = 0.5 * dz_n; }
+  double cv_a = 0.0, fl_a = 0.0, cv_b = 0.0, fl_b = 0.0;
+  if (vb && a.act && b.act) {
+    const double kod = a.tk * b.tk * rcp(a.tk * a.dd + b.tk * a.du) * area;
+    fl_a = -kod * (a.T - b.T); cv_a = (1.0 - cnfac) * kod;                 // DiffHeatFlux * area (:976-1003), ComputeOperatorsDiag (:1112)
+  }
+  if (vb && j1 < nlev - 1 && b.act && act_n) {
+    const double kod = b.tk * tk_n * rcp(b.tk * b.dd + tk_n * b.du) * area;
+    fl_b = -kod * (b.T - T_n); cv_b = (1.0 - cnfac) * kod;
+  }
+  const double cv_p = __shfl_up_sync(FULL, cv_b, 1, LPC), fl_p = __shfl_up_sync(FULL, fl_b, 1, LPC);
+
+  if (a.act) { a.bb = a.hc * (area * a.dz) * rcp(dt * a.tf); a.rhs = a.bb * a.T; } else { a.bb = 1.0; a.rhs = 0.0; }
+  if (b.act) { b.bb = b.hc * (area * b.dz) * rcp(dt * b.tf); b.rhs = b.bb * b.T; } else { b.bb = 1.0; b.rhs = 0.0; }
+  a.rhs = a.rhs + cnfac * fl_a; a.bb += cv_a;
+  if (l > 0) { a.rhs = a.rhs - cnfac * fl_p; a.bb += cv_p; }
+  b.rhs = b.rhs + cnfac * fl_b; b.bb += cv_b;
+  b.rhs = b.rhs - cnfac * fl_a; b.bb += cv_a;
+  if (va && a.act) { thermal_cell_bc(A, a, cell0, col, j0, jtop, jbot, area); a.rhs = a.rhs + a.ssum; }
+  if (vb && b.act) { thermal_cell_bc(A, b, cell0 + 1, col, j1, jtop, jbot, area); b.rhs = b.rhs + b.ssum; }
+  if (!va) { a.bb = 1.0; a.rhs = 0.0; }
+  if (!vb) { b.bb = 1.0; b.rhs = 0.0; }
+
+  // symmetric tridiagonal rows: sub_a = -cv_p, sup_a = sub_b = -cv_a, sup_b = -cv_b   (KSPSolve: exact for a tridiagonal matrix)
+  const double sub_a = (l > 0) ? -cv_p : 0.0, sup_a = -cv_a, sub_b = -cv_a, sup_b = -cv_b;
+  const double rb = rcp(b.bb);
+  const double bs = sub_b * rb, bu = sup_b * rb, bf = b.rhs * rb;          // y_b = bf - bs y_a(l) - bu y_a(l+1)
+  const double bs_p = __shfl_up_sync(FULL, bs, 1, LPC), bu_p = __shfl_up_sync(FULL, bu, 1, LPC), bf_p = __shfl_up_sync(FULL, bf, 1, LPC);
+  const double rB = rcp(a.bb - sub_a * bu_p - sup_a * bs);
+  const double al = (-sub_a * bs_p) * rB, ga = (-sup_a * bu) * rB, de = (a.rhs - sub_a * bf_p - sup_a * bf) * rB;
+  const double xa = thermal_pcr_unit<LPC>(al, ga, de);
+  const double xa_n = __shfl_down_sync(FULL, xa, 1, LPC);
+  const double xb = bf - bs * xa - bu * xa_n;
+  if (va) A.T_out[cell0] = xa;
+  if (vb) A.T_out[cell0 + 1] = xb;
+}
+
 // Any nlev: one thread per column straight from global memory (correctness path for tall columns).
 __global__ void thermal_step_generic_kernel(const ThermalArgs A, double *work /* 4 * ncells */)
 {
@@ -227,7 +359,7 @@ __global__ void thermal_step_generic_kernel(const ThermalArgs A, double *work /*
   for (int j = 0; j < nlev - 1; ++j) {
     const long long cell = c0 + j;
     if (!A.active[cell] || !A.active[cell + 1]) continue;
-    const double du = A.dist_up ? A.dist_up[cell] : 0.5 * A.dz[cell], dd = A.dist_dn ? A.dist_dn[cell] : 0.5 * A.dz[cell + 1];
+    const double du = A.dist_up ? A.dist_up[cell] : 0.5 * A.dz[cell], dd = A.dist_dn ? A.dist_dn[cell] : 0.5 * A.dz[cell + 1];   // (dist_uniform is only used for nlev <= 32)
     const double dist = du + dd;
     const double kav = tkv[j] * tkv[j + 1] * dist / (tkv[j] * dd + tkv[j + 1] * du);
     const double flux = -kav * (A.T_in[cell] - A.T_in[cell + 1]) / dist * area;
@@ -278,7 +410,8 @@ struct ThermalState {
   int ncol = 0, nlev = 0, orientation = 311, nlevsoi = 0;
   int istsoil = 1, istcrop = 2, istice = 3, istice_mec = 4, istwet = 6;
   double cnfac = 0.5;                    // mpp_varcon.F90:28
-  bool soils_set = false, custom_dist = false, diagnostics = false;
+  bool soils_set = false, custom_dist = false, diagnostics = false, dist_uniform = false;
+  double lay_du[32], lay_dd[32];
   const double *d_dz = nullptr, *d_area = nullptr;   // owned by the handle
   double *por = nullptr, *tkmg = nullptr, *tkdry = nullptr, *csol = nullptr, *dist_up = nullptr, *dist_dn = nullptr;
   int *lun_type = nullptr;

@@ -46,9 +46,16 @@ def test_thermal_mms_other_lengths(mpp, oracle, nx):
     assert np.max(np.abs(T - (10 * np.sin(np.pi * x) + 270.0))) < 0.5 * (20.0 / nx) ** 2 + 1e-9     # converges to the manufactured solution
 
 
-@pytest.mark.parametrize("ncol,nlev", [(1, 15), (127, 15), (128, 15), (1000, 15), (37, 10), (9, 24)])
-def test_elm_like_thermal_batch_matches_oracle(mpp, oracle, ncol, nlev):
-    d = PB.elm_thermal_inputs(ncol, nlev, nlevsoi=min(10, nlev - 2))
+@pytest.mark.parametrize("ncol,nlev,varying", [(1, 15, False), (127, 15, False), (128, 15, True), (1000, 15, False), (37, 10, True),
+                                               (9, 24, False), (33, 24, True), (5, 16, True), (3, 2, False)])
+def test_elm_like_thermal_batch_matches_oracle(mpp, oracle, ncol, nlev, varying):
+    # nlev <= 16: two cells per lane; 17..32: one cell per lane.  `varying`: connection distances differ from column to column
+    # (per-cell arrays in HBM); otherwise they are uniform and the kernels read them per layer from their constant bank
+    d = PB.elm_thermal_inputs(ncol, nlev, nlevsoi=max(1, min(10, nlev - 2)))
+    if varying:
+        rng = np.random.default_rng(ncol)
+        f = rng.uniform(0.8, 1.2, (ncol, 1))
+        d["dist_up"] = d["dist_up"] * f; d["dist_dn"] = d["dist_dn"] * f
     p, ids = PB.build_elm_thermal(mpp.Thermal, d)
     o, oids = PB.build_elm_thermal(oracle.OracleThermal, d, nthreads=4)
     T, To = d["T0"].copy(), d["T0"].copy()
