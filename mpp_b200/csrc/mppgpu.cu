@@ -636,7 +636,7 @@ template <int LPC>
 static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 {
   const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
-  const bool bc = A.nbc > 0;
+  const bool bc = A.nbc > 0 || A.dr_type != 0;        // the specialisation that carries boundary conditions and the down-regulated sink
 #define MPP_L2(SF) do { if (bc) vsfm_step2_kernel<LPC, SF, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
                         else    vsfm_step2_kernel<LPC, SF, false><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); } while (0)
   if (sf == SATFUNC_VG) MPP_L2(SATFUNC_VG); else if (sf == SATFUNC_BC) MPP_L2(SATFUNC_BC); else MPP_L2(SATFUNC_SBC);
@@ -645,12 +645,12 @@ static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 
 #ifdef VSFM2_PROFILE
 static long long *g_prof = nullptr;
-extern "C" int mppgpu_dbg_profile(long long *out7 /* 9 entries */)
+extern "C" int mppgpu_dbg_profile(long long *out7 /* 12 entries */)
 {
   if (!g_prof) return 1;
   cudaDeviceSynchronize();
-  cudaMemcpy(out7, g_prof, 9 * sizeof(long long), cudaMemcpyDeviceToHost);
-  cudaMemset(g_prof, 0, 9 * sizeof(long long));
+  cudaMemcpy(out7, g_prof, 12 * sizeof(long long), cudaMemcpyDeviceToHost);
+  cudaMemset(g_prof, 0, 12 * sizeof(long long));
   return 0;
 }
 #endif
@@ -686,7 +686,7 @@ static int vsfm_launch_range(mppgpu_soe *h, const VsfmArgs &A0, long long col0, 
   VsfmArgs A = A0;
   vsfm_offset_args(A, h->nlev, col0, n, block0);
 #ifdef VSFM2_PROFILE
-  if (!g_prof) { cudaMalloc((void **)&g_prof, 9 * sizeof(long long)); cudaMemset(g_prof, 0, 9 * sizeof(long long)); }
+  if (!g_prof) { cudaMalloc((void **)&g_prof, 12 * sizeof(long long)); cudaMemset(g_prof, 0, 12 * sizeof(long long)); }
   A.prof = g_prof;
 #endif
   const int nlev = h->nlev, nblocks = vsfm_blocks_for(h, n);

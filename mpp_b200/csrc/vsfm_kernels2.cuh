@@ -156,6 +156,7 @@ __device__ __forceinline__ void rich_flux_deriv(double P_u, double kr_u, double 
   Jdn = dq_dn * den_ave - q * ((1.0 - upw) * dden_d);
 }
 
+// HAS_BC: the batch has boundary conditions and / or a down-regulated sink (compiled out for plain ELM-like batches)
 template <int LPC, int SATFUNC, bool HAS_BC>
 __global__ void __launch_bounds__(VSFM2_THREADS, VSFM2_MIN_BLOCKS)
 vsfm_step2_kernel(const VsfmArgs A)
@@ -219,7 +220,7 @@ vsfm_step2_kernel(const VsfmArgs A)
 
   // optional down-regulated sink: which of this lane's cells it touches, and where its per-connection data sits
   bool dr_a = false, dr_b = false; long long dr_ia = 0, dr_ib = 0;
-  if (A.dr_type) {
+  if (HAS_BC && A.dr_type) {
     const bool percell = (A.dr_region == REGION_CELLS);
     const int jown = (A.dr_region == REGION_TOP) ? jtop : jbot;
     dr_a = a.valid && (percell || j0 == jown); dr_b = b.valid && (percell || j1 == jown);
@@ -262,7 +263,7 @@ vsfm_step2_kernel(const VsfmArgs A)
   double initslope = -1.0, lambda = 1.0, lambdaprev = 1.0, gprev = 0.0;
 
 #ifdef VSFM2_PROFILE
-  long long pt_newton = 0, pt_eval = 0, pt_logic = 0, pn_newton = 0, pn_eval = 0, pt_curves = 0, pt_red = 0; const long long pt_start = clock64();
+  long long pt_newton = 0, pt_eval = 0, pt_logic = 0, pn_newton = 0, pn_eval = 0, pt_curves = 0, pt_red = 0, pt_nasm = 0, pt_nelim = 0, pt_npcr = 0; const long long pt_start = clock64();
 #endif
   for (;;) {
 #ifdef VSFM2_PROFILE
@@ -315,12 +316,15 @@ vsfm_step2_kernel(const VsfmArgs A)
       if (a.valid) { const double por = PA(PI_POR); dia_a += (por * dden_a * a.sat + por * den_a * a.dsat) * PA(PI_VOL) * dtInv; }   // AccumDeriv (:1673-1675), dpor_dP = 0
       if (b.valid) { const double por = PB(PI_POR); dia_b += (por * dden_b * b.sat + por * den_b * b.dsat) * PB(PI_VOL) * dtInv; }
 
-      if (A.dr_type) {                               // uniform branch; rare path, data re-read from HBM / L2
+      if (HAS_BC && A.dr_type) {                               // uniform branch; rare path, data re-read from HBM / L2
         double rate, dj;
         if (dr_a) { downreg_sink(A.dr_type, A.dr_value[dr_ia], A.dr_pc[dr_ia], A.dr_n[dr_ia], a.X, rate, dj); dia_a += dj; }
         if (dr_b) { downreg_sink(A.dr_type, A.dr_value[dr_ib], A.dr_pc[dr_ib], A.dr_n[dr_ib], b.X, rate, dj); dia_b += dj; }
       }
 
+#ifdef VSFM2_PROFILE
+      const long long pn1 = clock64() + (long long)(1e-300 * (dia_a + dia_b)); pt_nasm += pn1 - pt0;
+#endif
       // ---- J Y = F: eliminate this lane's second unknown, PCR over the first unknowns, back-substitute ----
       const double Fa = a.valid ? a.F : 0.0, Fb = b.valid ? b.F : 0.0;
       const double rb = rcp1(dia_b);
@@ -329,7 +333,13 @@ vsfm_step2_kernel(const VsfmArgs A)
       // reduced row l: sub_a y_b(l-1) + dia_a y_a(l) + sup_a y_b(l) = Fa   (sub_a = 0 on lane 0)
       const double rB = rcp1(dia_a - sub_a * bu_p - sup_a * bs);
       const double al = (-sub_a * bs_p) * rB, ga = (-sup_a * bu) * rB, de = (Fa - sub_a * bf_p - sup_a * bf) * rB;
+#ifdef VSFM2_PROFILE
+      const long long pn2 = clock64() + (long long)(1e-300 * (al + ga + de)); pt_nelim += pn2 - pn1;
+#endif
       const double Ya = pcr_unit_diag<LPC>(al, ga, de);
+#ifdef VSFM2_PROFILE
+      const long long pn3 = clock64() + (long long)(1e-300 * Ya); pt_npcr += pn3 - pn2;
+#endif
       const double Ya_n = __shfl_down_sync(FULL, Ya, 1, LPC);
       const double Yb = bf - bs * Ya - bu * Ya_n;                    // bu = 0 where there is no next cell
       const double Yb_p = __shfl_up_sync(FULL, Yb, 1, LPC);
@@ -428,7 +438,7 @@ vsfm_step2_kernel(const VsfmArgs A)
         }
       }
       Ga = Ga - PA(PI_SRC); Gb = Gb - PB(PI_SRC);
-      if (A.dr_type) {
+      if (HAS_BC && A.dr_type) {
         double rate, dj;
         if (dr_a) { downreg_sink(A.dr_type, A.dr_value[dr_ia], A.dr_pc[dr_ia], A.dr_n[dr_ia], a.W, rate, dj); Ga = Ga - rate * RFMW; }
         if (dr_b) { downreg_sink(A.dr_type, A.dr_value[dr_ib], A.dr_pc[dr_ib], A.dr_n[dr_ib], b.W, rate, dj); Gb = Gb - rate * RFMW; }
@@ -537,6 +547,8 @@ vsfm_step2_kernel(const VsfmArgs A)
     atomicAdd((unsigned long long *)A.prof + 4, (unsigned long long)pt_logic);  atomicAdd((unsigned long long *)A.prof + 5, (unsigned long long)(clock64() - pt_start));
     atomicAdd((unsigned long long *)A.prof + 6, 1ull);
     atomicAdd((unsigned long long *)A.prof + 7, (unsigned long long)pt_curves); atomicAdd((unsigned long long *)A.prof + 8, (unsigned long long)pt_red);
+    atomicAdd((unsigned long long *)A.prof + 9, (unsigned long long)pt_nasm); atomicAdd((unsigned long long *)A.prof + 10, (unsigned long long)pt_nelim);
+    atomicAdd((unsigned long long *)A.prof + 11, (unsigned long long)pt_npcr);
   }
 #endif
 
@@ -571,7 +583,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       bc_exc += bcMassExc[k];
     }
   }
-  if (A.dr_type) {                                 // the rate actually withdrawn at the end-of-step state enters the column's balance
+  if (HAS_BC && A.dr_type) {                                 // the rate actually withdrawn at the end-of-step state enters the column's balance
     double rate, dj;
     if (dr_a) { downreg_sink(A.dr_type, A.dr_value[dr_ia], A.dr_pc[dr_ia], A.dr_n[dr_ia], a.X, rate, dj); src_kg += rate; }
     if (dr_b) { downreg_sink(A.dr_type, A.dr_value[dr_ib], A.dr_pc[dr_ib], A.dr_n[dr_ib], b.X, rate, dj); src_kg += rate; }
