@@ -282,18 +282,20 @@ vsfm_step2_kernel(const VsfmArgs A)
       const double Xn    = __shfl_down_sync(FULL, a.X, 1, LPC),   krn   = __shfl_down_sync(FULL, a.kr, 1, LPC);
       const double dkrn  = __shfl_down_sync(FULL, a.dkr, 1, LPC), denn  = __shfl_down_sync(FULL, den_a, 1, LPC);
       const double ddenn = __shfl_down_sync(FULL, dden_a, 1, LPC);
-      double Jup_a = 0.0, Jdn_a = 0.0, Jup_b = 0.0, Jdn_b = 0.0;
-      if (a.has_conn) rich_flux_deriv(a.X, a.kr, a.dkr, den_a, dden_a, b.X, b.kr, b.dkr, den_b, dden_b, PA(PI_UPW), PA(PI_DQ), PA(PI_GFAC), area, Jup_a, Jdn_a);
-      if (b.has_conn) rich_flux_deriv(b.X, b.kr, b.dkr, den_b, dden_b, Xn, krn, dkrn, denn, ddenn, PB(PI_UPW), PB(PI_DQ), PB(PI_GFAC), area, Jup_b, Jdn_b);
+      // both connections evaluated unconditionally (all inputs are finite on padding lanes) and masked afterwards: no divergent
+      // branch, and the two derivative chains overlap
+      double Jup_a, Jdn_a, Jup_b, Jdn_b;
+      rich_flux_deriv(a.X, a.kr, a.dkr, den_a, dden_a, b.X, b.kr, b.dkr, den_b, dden_b, PA(PI_UPW), PA(PI_DQ), PA(PI_GFAC), area, Jup_a, Jdn_a);
+      rich_flux_deriv(b.X, b.kr, b.dkr, den_b, dden_b, Xn, krn, dkrn, denn, ddenn, PB(PI_UPW), PB(PI_DQ), PB(PI_GFAC), area, Jup_b, Jdn_b);
+      Jup_a = a.has_conn ? Jup_a : 0.0; Jdn_a = a.has_conn ? Jdn_a : 0.0;
+      Jup_b = b.has_conn ? Jup_b : 0.0; Jdn_b = b.has_conn ? Jdn_b : 0.0;
       const double Jup_p = __shfl_up_sync(FULL, Jup_b, 1, LPC), Jdn_p = __shfl_up_sync(FULL, Jdn_b, 1, LPC);   // connection (2l-1) -> 2l
       // rows 2l and 2l+1 of the tridiagonal Jacobian (GoveqnRichards...:2054-2069 insertion order)
-      double sub_a = 0.0, dia_a = 1.0, sup_a = 0.0, sub_b = 0.0, dia_b = 1.0, sup_b = 0.0;
-      if (a.valid) {
-        dia_a = 0.0;
-        if (l > 0) { sub_a = -Jup_p; dia_a += -Jdn_p; }
-        dia_a += Jup_a; sup_a = Jdn_a;
-      }
-      if (b.valid) { sub_b = -Jup_a; dia_b = -Jdn_a; dia_b += Jup_b; sup_b = Jdn_b; }
+      // (padding cells: identity rows; their couplings are already zero because has_conn is false around them)
+      const double sub_a = (a.valid && l > 0) ? -Jup_p : 0.0, sup_a = Jdn_a;
+      double dia_a = a.valid ? ((l > 0) ? -Jdn_p : 0.0) + Jup_a : 1.0;
+      const double sub_b = -Jup_a, sup_b = Jdn_b;
+      double dia_b = b.valid ? -Jdn_a + Jup_b : 1.0;
       if (HAS_BC) {
 #pragma unroll
         for (int k = 0; k < NBC; ++k) if (bcOwn[k]) {                // boundary: (dn,dn) -= Jdn  (:2136-2140)
@@ -313,8 +315,12 @@ vsfm_step2_kernel(const VsfmArgs A)
           if (onA) dia_a += t; else dia_b += t;
         }
       }
-      if (a.valid) { const double por = PA(PI_POR); dia_a += (por * dden_a * a.sat + por * den_a * a.dsat) * PA(PI_VOL) * dtInv; }   // AccumDeriv (:1673-1675), dpor_dP = 0
-      if (b.valid) { const double por = PB(PI_POR); dia_b += (por * dden_b * b.sat + por * den_b * b.dsat) * PB(PI_VOL) * dtInv; }
+      {                                             // AccumDeriv (:1673-1675), dpor_dP = 0
+        const double pora = PA(PI_POR), porb = PB(PI_POR);
+        const double da = (pora * dden_a * a.sat + pora * den_a * a.dsat) * PA(PI_VOL) * dtInv;
+        const double db = (porb * dden_b * b.sat + porb * den_b * b.dsat) * PB(PI_VOL) * dtInv;
+        dia_a += a.valid ? da : 0.0; dia_b += b.valid ? db : 0.0;
+      }
 
       if (HAS_BC && A.dr_type) {                               // uniform branch; rare path, data re-read from HBM / L2
         double rate, dj;
@@ -349,12 +355,16 @@ vsfm_step2_kernel(const VsfmArgs A)
       if (b.has_conn) JYb += sup_b * Ya_n;
       const double yn2 = col_sum<LPC>((a.valid ? Ya * Ya : 0.0) + (b.valid ? Yb * Yb : 0.0));
       double slope = col_sum<LPC>(Fa * JYa + Fb * JYb);
-      if (nw) {
-        a.Y = Ya; b.Y = Yb; y2 = yn2;                                // x2 = ||X||^2 was taken when X was accepted
-        if (slope > 0.0) slope = -slope;
-        if (slope == 0.0) slope = -1.0;
-        initslope = slope;
-        lambda = 1.0; ls_count = 0;
+      // line-search initialisation: the common case (a usable step, full step tried first) is written with selects; the rare
+      // exits (zero step, step clipped at maxstep, function budget) take the branch
+      if (slope > 0.0) slope = -slope;
+      if (slope == 0.0) slope = -1.0;
+      a.Y = nw ? Ya : a.Y; b.Y = nw ? Yb : b.Y; y2 = nw ? yn2 : y2;   // x2 = ||X||^2 was taken when X was accepted
+      initslope = nw ? slope : initslope;
+      lambda = nw ? 1.0 : lambda; ls_count = nw ? 0 : ls_count;
+      a.W = nw ? a.X - Ya : a.W; b.W = nw ? b.X - Yb : b.W;           // W = X - lambda Y with lambda = 1
+      phase = nw ? PH_LS_FULL : phase;
+      if (nw && (yn2 == 0.0 || yn2 > maxstep2 || (nfuncs >= so.max_funcs && so.max_funcs >= 0))) {
         if (y2 == 0.0) {
           // zero step: line search "fails"; stol*xnorm > ynorm => SNES_CONVERGED_SNORM_RELATIVE (ls.c)
           last_reason = (stol2 * x2 > y2) ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
@@ -362,7 +372,6 @@ vsfm_step2_kernel(const VsfmArgs A)
         } else {
           if (y2 > maxstep2) { const double sc = so.ls_maxstep / sqrt(y2); a.Y *= sc; b.Y *= sc; y2 = maxstep2; }
           a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X);
-          phase = PH_LS_FULL;
           if (nfuncs >= so.max_funcs && so.max_funcs >= 0) { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
         }
       }
@@ -414,8 +423,9 @@ vsfm_step2_kernel(const VsfmArgs A)
       const double acc_b = PB(PI_POR) * denb * sb.sat * PB(PI_VOL) * dtInv;
       if (phase == PH_INIT) { PA(PI_ACCP) = acc_a; PB(PI_ACCP) = acc_b; }   // PreSolve: accumulation at soln_prev (== W here)
       const double Wn = __shfl_down_sync(FULL, a.W, 1, LPC), krn = __shfl_down_sync(FULL, sa.kr, 1, LPC), denn = __shfl_down_sync(FULL, dena, 1, LPC);
-      const double flux_a = a.has_conn ? rich_flux(a.W, sa.kr, dena, b.W, sb.kr, denb, PA(PI_UPW), PA(PI_DQ), PA(PI_GFAC), area) : 0.0;
-      const double flux_b = b.has_conn ? rich_flux(b.W, sb.kr, denb, Wn, krn, denn, PB(PI_UPW), PB(PI_DQ), PB(PI_GFAC), area) : 0.0;
+      const double fa_ = rich_flux(a.W, sa.kr, dena, b.W, sb.kr, denb, PA(PI_UPW), PA(PI_DQ), PA(PI_GFAC), area);
+      const double fb_ = rich_flux(b.W, sb.kr, denb, Wn, krn, denn, PB(PI_UPW), PB(PI_DQ), PB(PI_GFAC), area);
+      const double flux_a = a.has_conn ? fa_ : 0.0, flux_b = b.has_conn ? fb_ : 0.0;        // masked, not branched
       const double flux_p = __shfl_up_sync(FULL, flux_b, 1, LPC);
       Ga = acc_a - ((phase == PH_INIT) ? acc_a : PA(PI_ACCP));
       if (l > 0) Ga = Ga + flux_p;                                      // ff(dn) += flux  (:1806)
