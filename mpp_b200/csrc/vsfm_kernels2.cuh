@@ -34,7 +34,7 @@ namespace mpp {
 #define VSFM2_THREADS 32
 #endif
 #ifndef VSFM2_MIN_BLOCKS
-#define VSFM2_MIN_BLOCKS 12
+#define VSFM2_MIN_BLOCKS 16
 #endif
 
 template <int LPC>
@@ -70,16 +70,18 @@ __device__ __forceinline__ double pcr_unit_diag(double al, double ga, double de)
 // -- and the two values that change only once per sub-step (soln_prev, accumulation at soln_prev) are parked in shared
 // memory, [field][thread] (conflict-free), and re-read where they are used: 48 registers less of persistent state per
 // lane, which the register allocator spends on overlapping the two cells' dependency chains instead of spilling
-// (154 registers, no spills, 12 one-warp blocks per SM; forcing 128 registers for 16 warps serialises the chains again
-// and ends up no faster -- occupancy sweep in profiles/r1_vsfm_occupancy.md).
+// (once the residual and the aux vars of the accepted iterate moved here too, 122 registers without spills: 16 one-warp blocks per
+// SM; squeezing further -- 18+ blocks, 96 registers -- spills and is slower again).
 template <int SATFUNC>
 struct Cell2 {
-  double X, F, Y, W;
-  double kr, dkr, sat, dsat;       // aux vars at the accepted iterate X
+  double X, W;
   bool valid, has_conn;
 };
-enum { PI_SATRES, PI_ALPHA, PI_M, PI_N, PI_POR, PI_VOL, PI_SRC, PI_UPW, PI_DQ, PI_GFAC, PI_XPREV, PI_ACCP, PI_FLIQ, PI_PU, PI_PS, PI_B2, PI_B3 };
-template <int SATFUNC> struct ParCount { static constexpr int value = (SATFUNC == SATFUNC_VG) ? 12 : (SATFUNC == SATFUNC_BC ? 13 : 17); };
+// shared-memory fields per cell: static data, then what changes once per sub-step (soln_prev, accumulation there), then what changes
+// once per accepted iterate (residual and aux vars at X: the Jacobian reads them, and the next cell's, from here)
+enum { PI_SATRES, PI_ALPHA, PI_M, PI_N, PI_POR, PI_VOL, PI_SRC, PI_UPW, PI_DQ, PI_GFAC, PI_XPREV, PI_ACCP, PI_F, PI_KR, PI_DKR, PI_SAT, PI_DSAT, PI_Y,
+       PI_FLIQ, PI_PU, PI_PS, PI_B2, PI_B3 };
+template <int SATFUNC> struct ParCount { static constexpr int value = (SATFUNC == SATFUNC_VG) ? 18 : (SATFUNC == SATFUNC_BC ? 19 : 23); };
 
 template <int SATFUNC>
 __device__ __forceinline__ void cell_load(const VsfmArgs &A, Cell2<SATFUNC> &c, double (*par)[VSFM2_THREADS], bool valid, long long cell, double area, double &perm, double &dz)
@@ -101,8 +103,8 @@ __device__ __forceinline__ void cell_load(const VsfmArgs &A, Cell2<SATFUNC> &c, 
   par[PI_SRC][t] = 0.0; par[PI_XPREV][t] = c.X; par[PI_ACCP][t] = 0.0;
   if (SATFUNC != SATFUNC_VG)  par[PI_FLIQ][t] = fl;
   if (SATFUNC == SATFUNC_SBC) { par[PI_PU][t] = pu; par[PI_PS][t] = ps; par[PI_B2][t] = b2; par[PI_B3][t] = b3; }
-  c.W = c.X; c.F = 0.0; c.Y = 0.0;
-  c.kr = 1.0; c.dkr = 0.0; c.sat = 1.0; c.dsat = 0.0;
+  c.W = c.X;
+  par[PI_Y][t] = 0.0; par[PI_F][t] = 0.0; par[PI_KR][t] = 1.0; par[PI_DKR][t] = 0.0; par[PI_SAT][t] = 1.0; par[PI_DSAT][t] = 0.0;
 }
 
 template <int SATFUNC>
@@ -255,12 +257,18 @@ vsfm_step2_kernel(const VsfmArgs A)
   const SnesOpts so = A.so;
   const double atol2 = so.atol * so.atol, rtol2 = so.rtol * so.rtol, stol2 = so.stol * so.stol;
   const double divtol2 = so.divtol * so.divtol, maxstep2 = so.ls_maxstep * so.ls_maxstep;
-  double dt_iter = A.dt, time_done = 0.0, dtInv = 1.0 / dt_iter;
+  // per-column scalars that are touched once per sub-step or only while back-tracking live in shared memory as well
+  __shared__ double s_sc[3][VSFM2_THREADS];
+#define SC_TDONE   s_sc[0][tx]
+#define SC_LAMPREV s_sc[1][tx]
+#define SC_GPREV   s_sc[2][tx]
+  SC_TDONE = 0.0; SC_LAMPREV = 1.0; SC_GPREV = 0.0;
+  double dt_iter = A.dt, dtInv = 1.0 / dt_iter;
   int    cuts = 0, tot_its = 0, tot_nf = 0, last_reason = 0, converged = 0;
   int    phase = col_ok ? PH_INIT : PH_DONE;
   int    its = 0, nfuncs = 0, ls_count = 0;
-  double f2 = 0.0, x2 = 0.0, y2 = 0.0, ttol2 = 0.0, f2_0 = 0.0;      // squared norms ||F||^2, ||X||^2, ||Y||^2
-  double initslope = -1.0, lambda = 1.0, lambdaprev = 1.0, gprev = 0.0;
+  double f2 = 0.0, x2 = 0.0, y2 = 0.0, f2_0 = 0.0;                   // squared norms ||F||^2, ||X||^2, ||Y||^2, ||F0||^2
+  double initslope = -1.0, lambda = 1.0;
 
 #ifdef VSFM2_PROFILE
   long long pt_newton = 0, pt_eval = 0, pt_logic = 0, pn_newton = 0, pn_eval = 0, pt_curves = 0, pt_red = 0, pt_nasm = 0, pt_nelim = 0, pt_npcr = 0; const long long pt_start = clock64();
@@ -278,15 +286,20 @@ vsfm_step2_kernel(const VsfmArgs A)
       double den_a, dden_a, den_b, dden_b;
       density_fixedT(A.dtab, a.X, den_a, dden_a);
       density_fixedT(A.dtab, b.X, den_b, dden_b);
-      // first cell of the next lane = dn side of connection b
-      const double Xn    = __shfl_down_sync(FULL, a.X, 1, LPC),   krn   = __shfl_down_sync(FULL, a.kr, 1, LPC);
-      const double dkrn  = __shfl_down_sync(FULL, a.dkr, 1, LPC), denn  = __shfl_down_sync(FULL, den_a, 1, LPC);
-      const double ddenn = __shfl_down_sync(FULL, dden_a, 1, LPC);
+      // aux vars at X of this lane's cells, and of the first cell of the next lane (dn side of connection b) straight from
+      // shared memory; only the pressure itself lives in a register and needs a shuffle
+      const double kr_a = PA(PI_KR), dkr_a_ = PA(PI_DKR), sat_a = PA(PI_SAT), dsat_a_ = PA(PI_DSAT);
+      const double kr_b = PB(PI_KR), dkr_b_ = PB(PI_DKR), sat_b = PB(PI_SAT), dsat_b_ = PB(PI_DSAT);
+      const int txn = b.has_conn ? tx + 1 : tx;
+      const double krn = pa[PI_KR][txn], dkrn = pa[PI_DKR][txn];
+      const double Xn = __shfl_down_sync(FULL, a.X, 1, LPC);
+      double denn, ddenn;
+      density_fixedT(A.dtab, Xn, denn, ddenn);
       // both connections evaluated unconditionally (all inputs are finite on padding lanes) and masked afterwards: no divergent
       // branch, and the two derivative chains overlap
       double Jup_a, Jdn_a, Jup_b, Jdn_b;
-      rich_flux_deriv(a.X, a.kr, a.dkr, den_a, dden_a, b.X, b.kr, b.dkr, den_b, dden_b, PA(PI_UPW), PA(PI_DQ), PA(PI_GFAC), area, Jup_a, Jdn_a);
-      rich_flux_deriv(b.X, b.kr, b.dkr, den_b, dden_b, Xn, krn, dkrn, denn, ddenn, PB(PI_UPW), PB(PI_DQ), PB(PI_GFAC), area, Jup_b, Jdn_b);
+      rich_flux_deriv(a.X, kr_a, dkr_a_, den_a, dden_a, b.X, kr_b, dkr_b_, den_b, dden_b, PA(PI_UPW), PA(PI_DQ), PA(PI_GFAC), area, Jup_a, Jdn_a);
+      rich_flux_deriv(b.X, kr_b, dkr_b_, den_b, dden_b, Xn, krn, dkrn, denn, ddenn, PB(PI_UPW), PB(PI_DQ), PB(PI_GFAC), area, Jup_b, Jdn_b);
       Jup_a = a.has_conn ? Jup_a : 0.0; Jdn_a = a.has_conn ? Jdn_a : 0.0;
       Jup_b = b.has_conn ? Jup_b : 0.0; Jdn_b = b.has_conn ? Jdn_b : 0.0;
       const double Jup_p = __shfl_up_sync(FULL, Jup_b, 1, LPC), Jdn_p = __shfl_up_sync(FULL, Jdn_b, 1, LPC);   // connection (2l-1) -> 2l
@@ -300,7 +313,7 @@ vsfm_step2_kernel(const VsfmArgs A)
 #pragma unroll
         for (int k = 0; k < NBC; ++k) if (bcOwn[k]) {                // boundary: (dn,dn) -= Jdn  (:2136-2140)
           const bool onA = (bcOwn[k] == 1);
-          const double Xc = onA ? a.X : b.X, krc = onA ? a.kr : b.kr, dkrc = onA ? a.dkr : b.dkr;
+          const double Xc = onA ? a.X : b.X, krc = onA ? kr_a : kr_b, dkrc = onA ? dkr_a_ : dkr_b_;
           const double denc = onA ? den_a : den_b, ddenc = onA ? dden_a : dden_b;
           const double dphi0 = bcP[k] - Xc + denc * bcGfac[k];
           const bool seep = (A.bc[k].itype == CT_SEEPAGE) && (dphi0 > 0.0) && (bcP[k] <= PRESSURE_REF);
@@ -317,8 +330,8 @@ vsfm_step2_kernel(const VsfmArgs A)
       }
       {                                             // AccumDeriv (:1673-1675), dpor_dP = 0
         const double pora = PA(PI_POR), porb = PB(PI_POR);
-        const double da = (pora * dden_a * a.sat + pora * den_a * a.dsat) * PA(PI_VOL) * dtInv;
-        const double db = (porb * dden_b * b.sat + porb * den_b * b.dsat) * PB(PI_VOL) * dtInv;
+        const double da = (pora * dden_a * sat_a + pora * den_a * dsat_a_) * PA(PI_VOL) * dtInv;
+        const double db = (porb * dden_b * sat_b + porb * den_b * dsat_b_) * PB(PI_VOL) * dtInv;
         dia_a += a.valid ? da : 0.0; dia_b += b.valid ? db : 0.0;
       }
 
@@ -332,7 +345,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       const long long pn1 = clock64() + (long long)(1e-300 * (dia_a + dia_b)); pt_nasm += pn1 - pt0;
 #endif
       // ---- J Y = F: eliminate this lane's second unknown, PCR over the first unknowns, back-substitute ----
-      const double Fa = a.valid ? a.F : 0.0, Fb = b.valid ? b.F : 0.0;
+      const double Fa = a.valid ? PA(PI_F) : 0.0, Fb = b.valid ? PB(PI_F) : 0.0;
       const double rb = rcp1(dia_b);
       const double bs = sub_b * rb, bu = sup_b * rb, bf = Fb * rb;   // y_b = bf - bs y_a(l) - bu y_a(l+1)
       const double bs_p = __shfl_up_sync(FULL, bs, 1, LPC), bu_p = __shfl_up_sync(FULL, bu, 1, LPC), bf_p = __shfl_up_sync(FULL, bf, 1, LPC);
@@ -359,7 +372,8 @@ vsfm_step2_kernel(const VsfmArgs A)
       // exits (zero step, step clipped at maxstep, function budget) take the branch
       if (slope > 0.0) slope = -slope;
       if (slope == 0.0) slope = -1.0;
-      a.Y = nw ? Ya : a.Y; b.Y = nw ? Yb : b.Y; y2 = nw ? yn2 : y2;   // x2 = ||X||^2 was taken when X was accepted
+      if (nw) { PA(PI_Y) = Ya; PB(PI_Y) = Yb; }
+      y2 = nw ? yn2 : y2;                                             // x2 = ||X||^2 was taken when X was accepted
       initslope = nw ? slope : initslope;
       lambda = nw ? 1.0 : lambda; ls_count = nw ? 0 : ls_count;
       a.W = nw ? a.X - Ya : a.W; b.W = nw ? b.X - Yb : b.W;           // W = X - lambda Y with lambda = 1
@@ -370,8 +384,8 @@ vsfm_step2_kernel(const VsfmArgs A)
           last_reason = (stol2 * x2 > y2) ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
           phase = -1;   // SNES finished, handled below
         } else {
-          if (y2 > maxstep2) { const double sc = so.ls_maxstep / sqrt(y2); a.Y *= sc; b.Y *= sc; y2 = maxstep2; }
-          a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X);
+          if (y2 > maxstep2) { const double sc = so.ls_maxstep / sqrt(y2); PA(PI_Y) = Ya * sc; PB(PI_Y) = Yb * sc; y2 = maxstep2; }
+          a.W = fma(-lambda, PA(PI_Y), a.X); b.W = fma(-lambda, PB(PI_Y), b.X);
           if (nfuncs >= so.max_funcs && so.max_funcs >= 0) { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
         }
       }
@@ -386,7 +400,7 @@ vsfm_step2_kernel(const VsfmArgs A)
         if (cuts > 20) { converged = 0; phase = PH_DONE; }
         else { a.W = a.X; b.W = b.X; phase = PH_INIT; }
       } else {
-        converged = 1; time_done += dt_iter; tot_its += its;
+        converged = 1; const double time_done = SC_TDONE + dt_iter; SC_TDONE = time_done; tot_its += its;
         PA(PI_XPREV) = a.X; PB(PI_XPREV) = b.X;             // PostSolve: soln -> soln_prev
         if (HAS_BC) {
 #pragma unroll
@@ -485,9 +499,9 @@ vsfm_step2_kernel(const VsfmArgs A)
 
     if (take) {
       // "copy the solution over": X <- W, F <- G; the aux vars of this point feed the next Jacobian / PostSolve
-      a.X = a.W; b.X = b.W; a.F = Ga; b.F = Gb;
-      a.kr = sa.kr; a.sat = sa.sat; b.kr = sb.kr; b.sat = sb.sat;
-      a.dsat = dsat_a; a.dkr = dkr_a; b.dsat = dsat_b; b.dkr = dkr_b;
+      a.X = a.W; b.X = b.W; PA(PI_F) = Ga; PB(PI_F) = Gb;
+      PA(PI_KR) = sa.kr; PA(PI_SAT) = sa.sat; PB(PI_KR) = sb.kr; PB(PI_SAT) = sb.sat;
+      PA(PI_DSAT) = dsat_a; PA(PI_DKR) = dkr_a; PB(PI_DSAT) = dsat_b; PB(PI_DKR) = dkr_b;
       if (HAS_BC) {
 #pragma unroll
         for (int k = 0; k < NBC; ++k) bcFlux[k] = G_bcflux[k];
@@ -496,11 +510,11 @@ vsfm_step2_kernel(const VsfmArgs A)
       // SNESConvergedDefault: it == 0 sets ttol = fnorm * rtol and only tests NaN / atol; it > 0 tests, in this order,
       // atol, function count, rtol, stol, divergence, max_it (lowest priority assigned first)
       its = is_init ? 0 : its + 1;
-      ttol2 = is_init ? g2 * rtol2 : ttol2; f2_0 = is_init ? g2 : f2_0;
+      f2_0 = is_init ? g2 : f2_0;                                       // it == 0: ttol = fnorm * rtol
       int reason = (its >= so.max_it) ? SNES_DIVERGED_MAX_IT : 0;
       reason = (so.divtol > 0 && g2 > divtol2 * f2_0) ? SNES_DIVERGED_DTOL : reason;
       reason = (y2 < stol2 * x2) ? SNES_CONVERGED_SNORM_RELATIVE : reason;
-      reason = (g2 <= ttol2) ? SNES_CONVERGED_FNORM_RELATIVE : reason;
+      reason = (g2 <= f2_0 * rtol2) ? SNES_CONVERGED_FNORM_RELATIVE : reason;
       reason = out_of_funcs ? SNES_DIVERGED_FUNCTION_COUNT : reason;
       reason = (g2 < atol2) ? SNES_CONVERGED_FNORM_ABS : reason;
       if (is_init) reason = g_bad ? SNES_DIVERGED_FNORM_NAN : ((g2 < atol2) ? SNES_CONVERGED_FNORM_ABS : 0);
@@ -510,7 +524,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       if (g_bad) {
         if (lambda <= so.ls_minlambda) { last_reason = SNES_DIVERGED_FNORM_NAN; phase = -1; }
         else if (out_of_funcs)         { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
-        else { lambda = .5 * lambda; a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); }
+        else { lambda = .5 * lambda; a.W = fma(-lambda, PA(PI_Y), a.X); b.W = fma(-lambda, PB(PI_Y), b.X); }
       } else if (tiny_step) {
         // "full step didn't work and the step is tiny": line search fails, SNES then sees stol*xnorm > ynorm
         last_reason = SNES_CONVERGED_SNORM_RELATIVE; phase = -1;
@@ -518,10 +532,10 @@ vsfm_step2_kernel(const VsfmArgs A)
         last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1;
       } else {
         double lt = -initslope / (g2 - f2 - 2.0 * lambda * initslope);  // quadratic fit
-        lambdaprev = lambda; gprev = g2;
+        SC_LAMPREV = lambda; SC_GPREV = g2;
         if (lt > .5 * lambda) lt = .5 * lambda;
         lambda = (lt <= .1 * lambda) ? .1 * lambda : lt;
-        a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); phase = PH_LS_QUAD; ls_count = 0;
+        a.W = fma(-lambda, PA(PI_Y), a.X); b.W = fma(-lambda, PB(PI_Y), b.X); phase = PH_LS_QUAD; ls_count = 0;
       }
     } else if (is_bt) {
       const int ls_fail = tiny_step ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
@@ -533,6 +547,7 @@ vsfm_step2_kernel(const VsfmArgs A)
         last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1;
       } else {
         const double t1 = .5 * (g2 - f2) - lambda * initslope;           // cubic fit
+        const double lambdaprev = SC_LAMPREV, gprev = SC_GPREV;
         const double t2 = .5 * (gprev - f2) - lambdaprev * initslope;
         const double rl2 = __drcp_rn(lambda * lambda), rp2 = __drcp_rn(lambdaprev * lambdaprev), rd = __drcp_rn(lambda - lambdaprev);
         const double ca = (t1 * rl2 - t2 * rp2) * rd;
@@ -540,10 +555,10 @@ vsfm_step2_kernel(const VsfmArgs A)
         double d = cb * cb - 3 * ca * initslope;
         if (d < 0.0) d = 0.0;
         double lt = (ca == 0.0) ? -initslope / (2.0 * cb) : (-cb + sqrt(d)) / (3.0 * ca);
-        lambdaprev = lambda; gprev = g2;
+        SC_LAMPREV = lambda; SC_GPREV = g2;
         if (lt > .5 * lambda) lt = .5 * lambda;
         lambda = (lt <= .1 * lambda) ? .1 * lambda : lt;
-        a.W = fma(-lambda, a.Y, a.X); b.W = fma(-lambda, b.Y, b.X); phase = PH_LS_CUBIC;
+        a.W = fma(-lambda, PA(PI_Y), a.X); b.W = fma(-lambda, PB(PI_Y), b.X); phase = PH_LS_CUBIC;
       }
     }
 #ifdef VSFM2_PROFILE
@@ -568,8 +583,9 @@ vsfm_step2_kernel(const VsfmArgs A)
     A.x_out[cell0] = a.X;
     if (converged) {
       double den, dden; density_fixedT(A.dtab, a.X, den, dden);
-      const double m = PA(PI_POR) * den * FMWH2O * a.sat * PA(PI_VOL);
-      A.liq_sat[cell0] = a.sat; A.pressure[cell0] = a.X; A.mass[cell0] = m;
+      const double sat = PA(PI_SAT);
+      const double m = PA(PI_POR) * den * FMWH2O * sat * PA(PI_VOL);
+      A.liq_sat[cell0] = sat; A.pressure[cell0] = a.X; A.mass[cell0] = m;
       A.smp[cell0] = (a.X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
       mass += m;
     }
@@ -578,8 +594,9 @@ vsfm_step2_kernel(const VsfmArgs A)
     A.x_out[cell0 + 1] = b.X;
     if (converged) {
       double den, dden; density_fixedT(A.dtab, b.X, den, dden);
-      const double m = PB(PI_POR) * den * FMWH2O * b.sat * PB(PI_VOL);
-      A.liq_sat[cell0 + 1] = b.sat; A.pressure[cell0 + 1] = b.X; A.mass[cell0 + 1] = m;
+      const double sat = PB(PI_SAT);
+      const double m = PB(PI_POR) * den * FMWH2O * sat * PB(PI_VOL);
+      A.liq_sat[cell0 + 1] = sat; A.pressure[cell0 + 1] = b.X; A.mass[cell0 + 1] = m;
       A.smp[cell0 + 1] = (b.X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
       mass += m;
     }
@@ -653,6 +670,9 @@ vsfm_step2_kernel(const VsfmArgs A)
   }
 #undef PA
 #undef PB
+#undef SC_TDONE
+#undef SC_LAMPREV
+#undef SC_GPREV
 }
 
 }  // namespace mpp
