@@ -20,7 +20,7 @@
 namespace mpp {
 
 #ifndef TH2_MIN_BLOCKS
-#define TH2_MIN_BLOCKS 2
+#define TH2_MIN_BLOCKS 3
 #endif
 
 struct M2 { double a, b, c, d; };     // row-major 2x2: [a b; c d]
@@ -74,6 +74,13 @@ __device__ __forceinline__ void ax_load(double (*s)[128], int t, THCell &c)
   c.dulP = s[14][t]; c.dhlP = s[15][t]; c.tc = s[16][t]; c.dtcP = s[17][t];
 }
 
+__device__ __forceinline__ SatParams th_load_sp(double (*s)[128], int t)
+{
+  SatParams p;
+  p.sat_res = s[14][t]; p.alpha = s[15][t]; p.m = s[16][t]; p.n = s[17][t]; p.pu = s[18][t]; p.ps = s[19][t]; p.b2 = s[20][t]; p.b3 = s[21][t];
+  return p;
+}
+
 template <int G, int SF, int DT, int IEE>
 __global__ void __launch_bounds__(128, TH2_MIN_BLOCKS)
 th_step2_kernel(const THArgs A)
@@ -115,7 +122,7 @@ th_step2_kernel(const THArgs A)
   const double Dqe = (PERM_E * PERM_E) / (dist_up * PERM_E + dist_dn * PERM_E);
 
   // boundary conditions owned by this lane (at most one per region and equation)
-  struct BCL { int ieqn; double P, T, gfac, Dq; FluxIn fin; double hl, tc; };
+  struct BCL { int ieqn; double P, T, bgf, Dq; FluxIn fin; double hl, tc; };
   BCL bcs[4]; int nmybc = 0;
   for (int k = 0; k < A.nbc; ++k) {
     const bool top = (A.bc[k].region == REGION_TOP);
@@ -123,7 +130,7 @@ th_step2_kernel(const THArgs A)
     BCL &b = bcs[nmybc++];
     b.ieqn = A.bc[k].ieqn;
     const double uzbc = (A.uz == 0.0) ? 0.0 : (top ? -1.0 : 1.0);
-    b.gfac = FMWH2O * ((0.0 + 0.5 * dz) * (uzbc * (-GRAVITY_CONSTANT)));
+    b.bgf = FMWH2O * ((0.0 + 0.5 * dz) * (uzbc * (-GRAVITY_CONSTANT)));
     THCell c;
     if (b.ieqn == 1) {       // mass equation: pressure = condition value, temperature stays at its default 298.15 K
       b.P = A.bc[k].value[col]; b.T = 273.15 + 25.0; b.Dq = perm / (0.0 + 0.5 * dz);
@@ -135,6 +142,32 @@ th_step2_kernel(const THArgs A)
       b.fin = FluxIn{b.P, c.kr, c.dkr, c.den_e, c.ddenP_e, c.ddenT_e}; b.hl = c.hl; b.tc = c.tc;
     }
   }
+
+  // Static per-cell data goes to shared memory ([field][thread]) and is re-read where used: ~45 registers less per lane, i.e. a
+  // third (and fourth) block per SM for this latency-bound kernel.  The macros below shadow the set-up variables from here on.
+  __shared__ double s_tp[22][128];
+  {
+    const int t = threadIdx.x;
+    s_tp[0][t] = por; s_tp[1][t] = vol; s_tp[2][t] = csol; s_tp[3][t] = tkdry; s_tp[4][t] = srcm; s_tp[5][t] = srce; s_tp[6][t] = upw;
+    s_tp[7][t] = Dqm; s_tp[8][t] = Dqe; s_tp[9][t] = gfac; s_tp[10][t] = dist_up; s_tp[11][t] = dist_dn; s_tp[12][t] = area; s_tp[13][t] = dz;
+    s_tp[14][t] = sp.sat_res; s_tp[15][t] = sp.alpha; s_tp[16][t] = sp.m; s_tp[17][t] = sp.n;
+    s_tp[18][t] = sp.pu; s_tp[19][t] = sp.ps; s_tp[20][t] = sp.b2; s_tp[21][t] = sp.b3;
+  }
+#define por     s_tp[0][threadIdx.x]
+#define vol     s_tp[1][threadIdx.x]
+#define csol    s_tp[2][threadIdx.x]
+#define tkdry   s_tp[3][threadIdx.x]
+#define srcm    s_tp[4][threadIdx.x]
+#define srce    s_tp[5][threadIdx.x]
+#define upw     s_tp[6][threadIdx.x]
+#define Dqm     s_tp[7][threadIdx.x]
+#define Dqe     s_tp[8][threadIdx.x]
+#define gfac    s_tp[9][threadIdx.x]
+#define dist_up s_tp[10][threadIdx.x]
+#define dist_dn s_tp[11][threadIdx.x]
+#define area    s_tp[12][threadIdx.x]
+#define dz      s_tp[13][threadIdx.x]
+#define sp      th_load_sp(s_tp, threadIdx.x)
 
   // ---- time-step / Newton state (uniform per column) -------------------------------------------------------------------
   const double atol2 = so.atol * so.atol, rtol2 = so.rtol * so.rtol, stol2 = so.stol * so.stol;
@@ -202,12 +235,12 @@ th_step2_kernel(const THArgs A)
           if (b.ieqn == 1) {
             const FluxIn dn = {P, ax.kr, ax.dkr, ax.den_m, ax.ddenP_m, ax.ddenT_m};
             double fl, bJup, bJdn, a1, a2;
-            th_rich_flux(b.fin, dn, 0.0, b.Dq, b.gfac, area, fl, bJup, bJdn, a1, a2);
+            th_rich_flux(b.fin, dn, 0.0, b.Dq, b.bgf, area, fl, bJup, bJdn, a1, a2);
             b00 += -bJdn;
           } else {
             const FluxIn dn = {P, ax.kr, ax.dkr, ax.den_e, ax.ddenP_e, ax.ddenT_e};
             double mfl, eJup, eJdn, edTu, edTd;
-            th_rich_flux(b.fin, dn, 0.0, b.Dq, b.gfac, area, mfl, eJup, eJdn, edTu, edTd);
+            th_rich_flux(b.fin, dn, 0.0, b.Dq, b.bgf, area, mfl, eJup, eJdn, edTu, edTd);
             const double kod = ax.tc / (0.0 + 0.5 * dz);
             const double h = (mfl <= 0.0) ? b.hl : ax.hl;
             const double dhT_d = (mfl < 0.0) ? 0.0 : ax.dhlT, dhP_d = (mfl < 0.0) ? 0.0 : ax.dhlP;
@@ -299,11 +332,11 @@ th_step2_kernel(const THArgs A)
         double fl, a1, a2, a3, a4;
         if (b.ieqn == 1) {
           const FluxIn dn = {Wm, c.kr, 0, c.den_m, 0, 0};
-          th_rich_flux(b.fin, dn, 0.0, b.Dq, b.gfac, area, fl, a1, a2, a3, a4);
+          th_rich_flux(b.fin, dn, 0.0, b.Dq, b.bgf, area, fl, a1, a2, a3, a4);
           Gm = Gm + fl;
         } else {
           const FluxIn dn = {Wm, c.kr, 0, c.den_e, 0, 0};
-          th_rich_flux(b.fin, dn, 0.0, b.Dq, b.gfac, area, fl, a1, a2, a3, a4);
+          th_rich_flux(b.fin, dn, 0.0, b.Dq, b.bgf, area, fl, a1, a2, a3, a4);
           const double kod = c.tc / (0.0 + 0.5 * dz);
           const double h = (fl <= 0.0) ? b.hl : c.hl;
           Ge = Ge + (fl * h + (-kod * (b.T - We) * area));
@@ -419,6 +452,21 @@ th_step2_kernel(const THArgs A)
     for (int k = 0; k < 5; ++k) bp[k] = 0.0;
     bp[5] = o0; bp[6] = o1; bp[7] = o2; bp[8] = (double)ow;
   }
+#undef por
+#undef vol
+#undef csol
+#undef tkdry
+#undef srcm
+#undef srce
+#undef upw
+#undef Dqm
+#undef Dqe
+#undef gfac
+#undef dist_up
+#undef dist_dn
+#undef area
+#undef dz
+#undef sp
 }
 
 }  // namespace mpp
