@@ -38,9 +38,9 @@ DT = 1800.0
 CHUNK = 65536                      # columns per seeded chunk (shards are unions of chunks)
 ALG_BYTES_PER_COLSTEP = 1224       # SURVEY.md section 8(d), VSFM-VG base variant
 # DRAM bytes per column-step of vsfm_step2_kernel measured by ncu (dram__bytes_read.sum + dram__bytes_write.sum over
-# 1 Mi columns, profiles/r1_vsfm_v6.md: 1.3087 GB + 0.6489 GB); the kernel also reads the six source arrays unsummed
+# 1 Mi columns, profiles/r1_vsfm_v12.md: 1.3087 GB + 0.6562 GB); the kernel also reads the six source arrays unsummed
 # and writes mass, smp and the committed solution, which the 1224 B base variant does not count
-TRAFFIC_BYTES_PER_COLSTEP = (1.308718e9 + 0.648915e9) / 1048576
+TRAFFIC_BYTES_PER_COLSTEP = (1.308749e9 + 0.656228e9) / 1048576
 SS_NAMES = ("infil", "et", "dew", "drain", "snow", "sublim")
 
 
@@ -402,7 +402,7 @@ def main():
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLSTEP,
                          "note": "fp64-latency bound, not HBM bound (2 log + 2 exp + 3 reciprocals per cell per residual evaluation, "
-                                 "%.1f evaluations and %.1f Newton iterations per column-step; fp64 pipe ~40 %% busy); see DESIGN.md" % (nf_mean, its_mean)},
+                                 "%.1f evaluations and %.1f Newton iterations per column-step; fp64 pipe ~53 %% busy); see DESIGN.md" % (nf_mean, its_mean)},
             "solver": {"converged_all": not glob["any_diverged"], "worst_reason": glob["worst_reason"], "newton_its_mean": its_mean, "newton_its_max": its_max,
                        "residual_evals_mean": nf_mean, "max_abs_mass_error_kg": float(maxs[0]), "last_step_kernel_ms": last_kernel_ms,
                        "columns_failed_last_step": int(nfailed[0]), "columns_with_dt_cuts_last_step": int(nfailed[1]),
