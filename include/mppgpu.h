@@ -91,6 +91,19 @@ int  mppgpu_vsfm_set_soils(mppgpu_handle h, const double *watsat, const double *
 int  mppgpu_thermal_set_soils(mppgpu_handle h, const double *watsat, const double *csol, const double *tkmg,
                               const double *tkdry, const int *lun_type, int nlevsoi, int istsoil);
 int  mppgpu_thermal_set_cnfac(mppgpu_handle h, double cnfac);
+/* ELM's real thermal column: adds the snow (nlevsno layers, variable active count) and standing-surface-water
+ * (one cell) governing equations next to the soil equation and couples the three into ONE linear system per column and step,
+ * i.e. everything add_meshes / add_goveqns / add_conditions_to_goveqns / allocate_auxvars of
+ * src/driver/alm/MPPThermalTBasedALM_Initialize.F90:150-727 set up: GE 1 snow, GE 2 standing water, GE 3 soil; boundary conditions
+ * 1 = heat flux at the top of snow, 2 = at the top of standing water, 3 = at the top of soil; sources 1 = absorbed solar
+ * radiation on the snow cells (ncol*nlevsno values), 2 = on the soil cells; COND_DIRICHLET_FRM_OTR_GOVEQ coupling snow<->soil and
+ * ssw<->soil (GoveqnThermalKSPTemperature{Snow,SSW,Soil}Type.F90).  soil_top_dist_dn[ncol] = z(c,1) - zi(c,0), the dist_dn the
+ * driver writes into the soil's coupling conditions (:630-639).  Call after mppgpu_set_mesh (soil mesh, MESH_ALONG_GRAVITY) and
+ * before any data is set; mppgpu_add_condition is not used in this configuration.  From then on every AUXVAR_INTERNAL array
+ * (set_data / set_idata / restart / get_data) has ncol*(nlevsno+1+nlev) entries in the reference's SoE order
+ * [snow cells, column-major | standing-water cells | soil cells], as MPPThermalTBasedALM_Driver.F90:204-452 packs them;
+ * inactive cells come back as 0 like the reference's identity rows.  nlevsno + 1 + nlev <= 32. */
+int  mppgpu_thermal_add_snow_ssw(mppgpu_handle h, int nlevsno, const double *soil_top_dist_dn);
 int  mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
                          const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,
                          int satfunc_type, int density_type, int int_energy_enthalpy_type);

@@ -22,6 +22,7 @@
 #include "vsfm_kernels2.cuh"
 #include "vsfm_generic_kernel.cuh"
 #include "thermal_kernels.cuh"
+#include "thermal_snow_kernels.cuh"
 #include "th_kernels.cuh"
 #include "th_kernels2.cuh"
 
@@ -102,6 +103,7 @@ static int thermal_set_idata(mppgpu_soe *h, ThermalState *t, int auxvar_type, in
 static int thermal_pre_step_dt(ThermalState *t);
 static int thermal_post_step_dt(ThermalState *t);
 static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt);
+static int thermal_add_snow_ssw(mppgpu_soe *h, ThermalState *t, int nlevsno, const double *soil_top_dist_dn);
 static int thermal_set_soils(mppgpu_soe *h, ThermalState *t, const double *watsat, const double *csol, const double *tkmg,
                              const double *tkdry, const int *lun_type, int nlevsoi, int istsoil);
 static int th_create(THState *t, int ncol, int nlev, cudaStream_t s);
@@ -394,6 +396,8 @@ extern "C" int mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int
       if ((int)h->sss.size() >= MAX_SS) return fail("mppgpu_add_condition: at most %d source/sink conditions", MAX_SS);
     }
   } else if (h->soe_itype == MPPGPU_SOE_THERMAL_TBASED) {
+    if (h->thermal && h->thermal->snow_mode)
+      return fail("mppgpu_add_condition: the snow + standing-water + soil configuration already holds ELM's conditions (mppgpu_thermal_add_snow_ssw)");
     if (ieqn != 1) return fail("mppgpu_add_condition: the soil thermal SoE has one governing equation here (ieqn = 1)");
     if (ss_or_bc == COND_BC && cond_type != COND_HEAT_FLUX && cond_type != COND_DIRICHLET)
       return fail("mppgpu_add_condition: thermal boundary condition type %d unsupported (COND_HEAT_FLUX 507, COND_DIRICHLET 505)", cond_type);
@@ -496,7 +500,8 @@ extern "C" int mppgpu_restart(mppgpu_handle h, const double *x, int n)
     return 0;
   }
   if (h->thermal) {
-    if ((size_t)n != h->ncells) return fail("mppgpu_restart: thermal expects ncells temperatures");
+    const size_t want = h->thermal->snow_mode ? h->thermal->nall : h->ncells;
+    if ((size_t)n != want) return fail("mppgpu_restart: thermal expects %zu temperatures", want);
     return thermal_set_temperature(h->thermal, x, true) ? fail("thermal restart failed") : 0;
   }
   if ((size_t)n != 2 * h->ncells) return fail("mppgpu_restart: TH expects 2*ncells values [P | T]");
@@ -897,6 +902,12 @@ extern "C" int mppgpu_thermal_set_cnfac(mppgpu_handle h, double cnfac)
   CHECK_H(h);
   if (!h->thermal) return fail("mppgpu_thermal_set_cnfac: handle is not a thermal SoE");
   h->thermal->cnfac = cnfac; return 0;
+}
+extern "C" int mppgpu_thermal_add_snow_ssw(mppgpu_handle h, int nlevsno, const double *soil_top_dist_dn)
+{
+  CHECK_H(h);
+  if (!h->thermal) return fail("mppgpu_thermal_add_snow_ssw: handle is not a thermal SoE");
+  return thermal_add_snow_ssw(h, h->thermal, nlevsno, soil_top_dist_dn);
 }
 extern "C" int mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
                                    const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,

@@ -37,6 +37,43 @@ static void thermal_destroy(ThermalState *t)
   if (t->lun_type) cudaFree(t->lun_type);
   if (t->nsnow) cudaFree(t->nsnow);
   if (t->active) cudaFree(t->active);
+  double *e[] = {t->soil_top_dist_dn, t->hs[0], t->hs[1], t->hs[2], t->dhs[0], t->dhs[1], t->dhs[2], t->frac_soil, t->sabg_snow, t->sabg_soil};
+  for (double *p : e) if (p) cudaFree(p);
+  if (t->snow_top_id) cudaFree(t->snow_top_id);
+}
+
+// MPPThermalTBasedALM_Initialize.F90:150-813 in one call: snow mesh (nlevsno layers) + standing-water mesh (1 cell) next to the soil
+// mesh, the three governing equations, their five conditions (heat flux at the top of snow / standing water / soil; absorbed
+// solar radiation on ALL_CELLS of snow and soil), the two coupling conditions snow<->soil and ssw<->soil with their coupling
+// variables, and the dist_dn = z(c,1) - zi(c,0) poked into the soil's coupling conditions (:630-639).
+static int thermal_add_snow_ssw(mppgpu_soe *h, ThermalState *t, int nlevsno, const double *soil_top_dist_dn)
+{
+  if (!h->mesh_set) return fail("mppgpu_thermal_add_snow_ssw: set the soil mesh first");
+  if (t->snow_mode) return fail("mppgpu_thermal_add_snow_ssw: already added");
+  if (!h->bcs.empty() || !h->sss.empty()) return fail("mppgpu_thermal_add_snow_ssw: the ELM configuration brings its own conditions; add none before");
+  if (h->orientation == MPPGPU_MESH_AGAINST_GRAVITY) return fail("mppgpu_thermal_add_snow_ssw: the ELM thermal meshes are MESH_ALONG_GRAVITY");
+  if (nlevsno < 0 || nlevsno + 1 + h->nlev > 32)
+    return fail("mppgpu_thermal_add_snow_ssw: nlevsno + 1 + nlev = %d rows per column; at most 32 are supported", nlevsno + 1 + h->nlev);
+  if (!soil_top_dist_dn) return fail("mppgpu_thermal_add_snow_ssw: null soil_top_dist_dn");
+  const size_t ncol = h->ncol, NA = ncol * (size_t)(nlevsno + 1 + h->nlev), NS = ncol * (size_t)nlevsno, NG = h->ncells;
+  cudaStream_t s = h->stream;
+  // the internal mailbox grows from soil-only to [snow | ssw | soil]
+  double **grow[] = {&t->T_clm, &t->T_work, &t->liq, &t->ice, &t->snow_water, &t->tuning, &t->frac, &t->aux_dz, &t->aux_dist_up, &t->aux_dist_dn};
+  const double fillv[] = {273.15, 273.15, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0};
+  for (int i = 0; i < 10; ++i) { if (*grow[i]) cudaFree(*grow[i]); *grow[i] = nullptr; if (th_alloc_d(grow[i], NA, fillv[i], s)) return fail("out of device memory"); }
+  cudaFree(t->nsnow); cudaFree(t->active); t->nsnow = t->active = nullptr;
+  CK(cudaMalloc((void **)&t->nsnow, NA * sizeof(int))); CK(cudaMalloc((void **)&t->active, NA * sizeof(int)));
+  CK(cudaMemsetAsync(t->nsnow, 0, NA * sizeof(int), s)); CK(cudaMemsetAsync(t->active, 0, NA * sizeof(int), s));
+  // soil cells of active columns start active (MPPThermalSetSoils); snow / ssw cells wait for VAR_ACTIVE from the host model
+  if (t->soils_set) fill_int_kernel<<<nblk(NG, 256), 256, 0, s>>>(t->active + (NA - NG), 1, (long long)NG);
+  for (int k = 0; k < 3; ++k) { if (th_alloc_d(&t->hs[k], ncol, 0.0, s) || th_alloc_d(&t->dhs[k], ncol, 0.0, s)) return fail("out of device memory"); }
+  if (th_alloc_d(&t->frac_soil, ncol, 0.0, s) || th_alloc_d(&t->sabg_snow, NS ? NS : 1, 0.0, s) || th_alloc_d(&t->sabg_soil, NG, 0.0, s) ||
+      th_alloc_d(&t->soil_top_dist_dn, ncol, 0.0, s)) return fail("out of device memory");
+  CK(cudaMalloc((void **)&t->snow_top_id, ncol * sizeof(int))); CK(cudaMemsetAsync(t->snow_top_id, 0, ncol * sizeof(int), s));
+  CK(cudaMemcpyAsync(t->soil_top_dist_dn, soil_top_dist_dn, ncol * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s));
+  t->T_cur = t->T_clm; t->snow_mode = true; t->nsno = nlevsno; t->nall = NA;
+  return 0;
 }
 
 static int thermal_set_mesh(ThermalState *t, int orientation, const double *d_dz, const double *d_area)
@@ -52,7 +89,8 @@ static int thermal_set_mesh(ThermalState *t, int orientation, const double *d_dz
 static int thermal_set_temperature(ThermalState *t, const double *T, bool)
 {
   // ThermalSOESetSolnPrevCLM (SystemOfEquationsThermalType.F90:171-199)
-  if (cudaMemcpyAsync(t->T_clm, T, (size_t)t->ncol * t->nlev * sizeof(double), cudaMemcpyHostToDevice, t->stream) != cudaSuccess) return 1;
+  const size_t n = t->snow_mode ? t->nall : (size_t)t->ncol * t->nlev;
+  if (cudaMemcpyAsync(t->T_clm, T, n * sizeof(double), cudaMemcpyHostToDevice, t->stream) != cudaSuccess) return 1;
   return cudaStreamSynchronize(t->stream) != cudaSuccess;
 }
 
@@ -74,7 +112,7 @@ static int thermal_set_soils(mppgpu_soe *h, ThermalState *t, const double *watsa
   if (!t->lun_type) CK(cudaMalloc((void **)&t->lun_type, h->ncol * sizeof(int)));
   CK(cudaMemcpyAsync(t->lun_type, lun_type, h->ncol * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   // every column active (filter_thermal = 1): aux_vars_in%is_active = .true. (MultiPhysicsProbThermal.F90:165-170)
-  fill_int_kernel<<<nblk(N, 256), 256, 0, h->stream>>>(t->active, 1, (long long)N);
+  fill_int_kernel<<<nblk(N, 256), 256, 0, h->stream>>>(t->active + (t->snow_mode ? t->nall - N : 0), 1, (long long)N);
   CK(cudaStreamSynchronize(h->stream));
   t->nlevsoi = nlevsoi; t->istsoil = istsoil; t->soils_set = true; h->soils_set = true;
   return 0;
@@ -88,7 +126,23 @@ static int thermal_lazy(double **p, size_t n, double fill, cudaStream_t s)
 
 static int thermal_field(mppgpu_soe *h, ThermalState *t, int auxvar_type, int var_type, int cond_id, bool for_set, double **p, size_t *cap)
 {
-  const size_t N = h->ncells;
+  const size_t N = t->snow_mode ? t->nall : h->ncells;
+  if (t->snow_mode && auxvar_type != AUXVAR_INTERNAL) {
+    // SoE-level condition ids of the ELM configuration (MPPThermalTBasedALM_Driver.F90:395-441):
+    //   AUXVAR_BC 1 top of snow, 2 top of standing water, 3 top of soil;  AUXVAR_SS 1 snow cells, 2 soil cells
+    if (auxvar_type == AUXVAR_BC && cond_id >= 1 && cond_id <= 3) {
+      *cap = h->ncol;
+      if (var_type == VAR_BC_SS_CONDITION) { *p = t->hs[cond_id - 1]; return 0; }
+      if (var_type == VAR_DHS_DT) { *p = t->dhs[cond_id - 1]; return 0; }
+      if (var_type == VAR_FRAC && cond_id == 3) { *p = t->frac_soil; return 0; }
+      return fail("SOEThermalAux%sRData: unknown var_type %d for boundary condition %d", for_set ? "Set" : "Get", var_type, cond_id);
+    }
+    if (auxvar_type == AUXVAR_SS && (cond_id == 1 || cond_id == 2) && var_type == VAR_BC_SS_CONDITION) {
+      *cap = (cond_id == 1) ? (size_t)h->ncol * t->nsno : h->ncells; *p = (cond_id == 1) ? t->sabg_snow : t->sabg_soil; return 0;
+    }
+    return fail("ThermalSOE%sRDataFromCLM: no condition %d of auxvar type %d / var_type %d in the snow + standing-water + soil configuration",
+                for_set ? "Set" : "Get", cond_id, auxvar_type, var_type);
+  }
   if (auxvar_type == AUXVAR_INTERNAL) {
     *cap = N;
     switch (var_type) {
@@ -97,7 +151,7 @@ static int thermal_field(mppgpu_soe *h, ThermalState *t, int auxvar_type, int va
     case VAR_ICE_AREAL_DEN: *p = t->ice; return 0;
     case VAR_SNOW_WATER:    *p = t->snow_water; return 0;
     case VAR_TUNING_FACTOR: *p = t->tuning; return 0;
-    // stored for the SoE mailbox; only the snow / standing-water coupling conditions read them (out of scope)
+    // stored for the SoE mailbox; read by the snow / standing-water equations and their coupling conditions
     case VAR_FRAC:          if (thermal_lazy(&t->frac, N, 0.0, h->stream)) return 1; *p = t->frac; return 0;
     case VAR_DZ:            if (thermal_lazy(&t->aux_dz, N, 0.0, h->stream)) return 1; *p = t->aux_dz; return 0;
     case VAR_DIST_UP:       if (thermal_lazy(&t->aux_dist_up, N, 0.0, h->stream)) return 1; *p = t->aux_dist_up; return 0;
@@ -130,7 +184,8 @@ static int thermal_set_idata(mppgpu_soe *h, ThermalState *t, int auxvar_type, in
 {
   (void)cond_id;
   if (auxvar_type != AUXVAR_INTERNAL) return fail("ThermalSOESetIDataFromCLM: only AUXVAR_INTERNAL is supported");
-  if ((size_t)n > h->ncells) return fail("size(data_1d) > nauxvar (%d > %zu)", n, h->ncells);
+  const size_t N = t->snow_mode ? t->nall : h->ncells;
+  if ((size_t)n > N) return fail("size(data_1d) > nauxvar (%d > %zu)", n, N);
   int *dst = nullptr;
   if (var_type == VAR_NUM_SNOW_LYR) dst = t->nsnow;
   else if (var_type == VAR_ACTIVE) dst = t->active;
@@ -143,10 +198,40 @@ static int thermal_set_idata(mppgpu_soe *h, ThermalState *t, int auxvar_type, in
 static int thermal_pre_step_dt(ThermalState *t) { t->T_cur = t->T_clm; return 0; }     // ThermalSOEPreStepDT :393-408
 static int thermal_post_step_dt(ThermalState *) { return 0; }
 
+static int thermal_snow_step(mppgpu_soe *h, ThermalState *t, double dt)
+{
+  ThermalSnowArgs A;
+  memset(&A, 0, sizeof(A));
+  ThermalArgs &S = A.S;
+  S.ncol = h->ncol; S.nlev = h->nlev; S.nlevsoi = t->nlevsoi;
+  S.istsoil = t->istsoil; S.istcrop = t->istcrop; S.istice = t->istice; S.istice_mec = t->istice_mec; S.istwet = t->istwet;
+  S.dt = dt; S.cnfac = t->cnfac;
+  S.por = t->por; S.tkmg = t->tkmg; S.tkdry = t->tkdry; S.csol = t->csol; S.dz = h->dz.p; S.area = h->area.p;
+  S.dist_up = t->custom_dist ? t->dist_up : nullptr; S.dist_dn = t->custom_dist ? t->dist_dn : nullptr;
+  S.dist_uniform = (t->custom_dist && t->dist_uniform) ? 1 : 0;
+  if (S.dist_uniform) { memcpy(S.lay_du, t->lay_du, sizeof(S.lay_du)); memcpy(S.lay_dd, t->lay_dd, sizeof(S.lay_dd)); }
+  S.lun_type = t->lun_type; S.stale_area = t->stale_area; S.top_is_first = 1;
+  A.nsno = t->nsno;
+  A.T_in = t->T_cur; A.liq = t->liq; A.ice = t->ice; A.snow_water = t->snow_water; A.mdz = t->aux_dz; A.dist_up = t->aux_dist_up;
+  A.dist_dn = t->aux_dist_dn; A.tuning = t->tuning; A.frac = t->frac; A.nsnow = t->nsnow; A.active = t->active;
+  for (int k = 0; k < 3; ++k) { A.hs[k] = t->hs[k]; A.dhsdT[k] = t->dhs[k]; }
+  A.frac_soil = t->frac_soil; A.sabg_snow = t->sabg_snow; A.sabg_soil = t->sabg_soil; A.soil_top_dist_dn = t->soil_top_dist_dn;
+  A.snow_top_id = t->snow_top_id;
+  A.T_out = (t->T_cur == t->T_clm) ? t->T_work : t->T_cur;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  thermal_snow_step_kernel<<<nblk((long long)h->ncol * 32, TH_TILE), TH_TILE, 0, h->stream>>>(A);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(h->ev1, h->stream));
+  h->launches += 1;
+  t->T_cur = A.T_out;
+  return 0;
+}
+
 static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
 {
   if (!h->mesh_set || !t->soils_set) return fail("mppgpu_step_dt: mesh and soils must be set first");
   if (!(dt > 0.0)) return fail("mppgpu_step_dt: dt must be positive");
+  if (t->snow_mode) return thermal_snow_step(h, t, dt);
   ThermalArgs A;
   memset(&A, 0, sizeof(A));
   A.ncol = h->ncol; A.nlev = h->nlev; A.nlevsoi = t->nlevsoi;

@@ -249,6 +249,32 @@ class Thermal(_SoE):
     GetSoln = get_soln
 
 
+class ThermalSnow(Thermal):
+    """sysofeqns_thermal_type with the three governing equations ELM uses: snow (nlevsno layers), standing surface water
+    (one cell) and soil, coupled into one linear system (MPPThermalTBasedALM_Initialize.F90:150-727).  Internal aux-var
+    arrays hold ncol*(nlevsno+1+nlev) values in the SoE order [snow | ssw | soil]."""
+
+    def __init__(self, ncol, nlev, nlevsno, device=0):
+        super().__init__(ncol, nlev, device)
+        self.nlevsno = int(nlevsno)
+        self.nsoil = self.ncells
+        self.ncells = self.ncol * (self.nlevsno + 1 + self.nlev)
+
+    def set_mesh(self, dz, area, conn_dist_up, conn_dist_dn, soil_top_dist_dn, snow_dz0=None):
+        """Soil mesh + internal connection distances (add_meshes, :150-500), then the snow / standing-water equations and
+        the coupling conditions (add_goveqns, add_conditions_to_goveqns, allocate_auxvars)."""
+        ncells, self.ncells = self.ncells, self.nsoil
+        try:
+            Thermal.set_mesh(self, K.MESH_ALONG_GRAVITY, dz, area)
+            self.set_connection_distances(conn_dist_up, conn_dist_dn)
+        finally:
+            self.ncells = ncells
+        st = _f64(soil_top_dist_dn)
+        if st.size != self.ncol:
+            raise ValueError("soil_top_dist_dn must have ncol entries")
+        check(self.L.mppgpu_thermal_add_snow_ssw(self.h, self.nlevsno, _dp(st)))
+
+
 class TH(_SoE):
     """sysofeqns_th_type: Richards (ieqn 1) + enthalpy (ieqn 2) on the same columns."""
     soe_itype = K.SOE_TH

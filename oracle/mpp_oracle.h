@@ -217,6 +217,23 @@ int       orc_thermal_step_dt(orc_thermal *p, double dt, int nstep, int *converg
 int       orc_thermal_get_soln(orc_thermal *p, double *T);
 int       orc_thermal_get_aux(orc_thermal *p, int var_type, double *data);
 
+/* snow + standing surface water + soil thermal system (ELM's real thermal column; parity unpinned, see thermal.c) */
+typedef struct orc_thermal3 orc_thermal3;
+orc_thermal3 *orc_thermal3_create(int ncol, int nlev, int nsno);
+void      orc_thermal3_destroy(orc_thermal3 *p);
+void      orc_thermal3_set_threads(orc_thermal3 *p, int nthreads);
+void      orc_thermal3_set_cnfac(orc_thermal3 *p, double cnfac);
+int       orc_thermal3_set_mesh(orc_thermal3 *p, const double *dz, const double *area, const double *conn_du, const double *conn_dd,
+                                const double *soil_top_dist_dn, const double *snow_dz0);
+int       orc_thermal3_set_soils(orc_thermal3 *p, const double *watsat, const double *csol, const double *tkmg,
+                                 const double *tkdry, const int *lun_type, int nlevsoi, int istsoil_id);
+int       orc_thermal3_set_soln_prev(orc_thermal3 *p, const double *T);
+int       orc_thermal3_set_rdata(orc_thermal3 *p, int auxvar_type, int var_type, int cond_id, const double *data, int n);
+int       orc_thermal3_set_idata(orc_thermal3 *p, int auxvar_type, int var_type, int cond_id, const int *data, int n);
+void      orc_thermal3_pre_step_dt(orc_thermal3 *p);
+int       orc_thermal3_step_dt(orc_thermal3 *p, double dt, int nstep, int *converged);
+int       orc_thermal3_get_soln(orc_thermal3 *p, double *T);
+
 /* TH (coupled Richards + enthalpy) */
 orc_th   *orc_th_create(int ncol, int nlev);
 void      orc_th_destroy(orc_th *p);

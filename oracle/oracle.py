@@ -30,7 +30,7 @@ def lib():
         _LIB = C.CDLL(build())
         L = _LIB
         L.orc_vsfm_create.restype = C.c_void_p
-        for name in ("orc_thermal_create", "orc_th_create"):
+        for name in ("orc_thermal_create", "orc_th_create", "orc_thermal3_create"):
             if hasattr(L, name):
                 getattr(L, name).restype = C.c_void_p
         L.orc_findgu_sbc_zerocoeff.restype = C.c_double
@@ -269,6 +269,72 @@ class OracleThermal:
         rc = self.L.orc_thermal_get_aux(self.h, int(var_type), dp(out))
         if rc:
             raise ValueError("get_aux rc=%d" % rc)
+        return out
+
+
+class OracleThermalSnow:
+    """Snow + standing-surface-water + soil thermal SoE (same call surface as mpp_b200.soe.ThermalSnow).  Arrays of the
+    internal aux vars have ncol*(nlevsno+1+nlev) entries in the reference's SoE order [snow | ssw | soil]."""
+
+    def __init__(self, ncol, nlev, nlevsno, nthreads=1, **kw):
+        self.L = lib()
+        self.ncol, self.nlev, self.nlevsno = ncol, nlev, nlevsno
+        self.ncells = ncol * (nlevsno + 1 + nlev)
+        self.h = C.c_void_p(self.L.orc_thermal3_create(ncol, nlev, nlevsno))
+        self.L.orc_thermal3_set_threads(self.h, int(nthreads))
+
+    def __del__(self):
+        try:
+            self.L.orc_thermal3_destroy(self.h)
+        except Exception:
+            pass
+
+    def set_mesh(self, dz, area, conn_dist_up, conn_dist_dn, soil_top_dist_dn, snow_dz0=None):
+        dz, area = table(dz, self.ncol, self.nlev), f64(area)
+        du, dd = table(conn_dist_up, self.ncol, self.nlev - 1), table(conn_dist_dn, self.ncol, self.nlev - 1)
+        st = f64(soil_top_dist_dn)
+        s0 = table(snow_dz0, self.ncol, self.nlevsno) if snow_dz0 is not None else None
+        return self.L.orc_thermal3_set_mesh(self.h, dp(dz), dp(area), dp(du), dp(dd), dp(st), dp(s0) if s0 is not None else None)
+
+    def set_soils(self, watsat, csol, tkmg, tkdry, lun_type, nlevsoi, istsoil=1):
+        a = [table(x, self.ncol, self.nlev) for x in (watsat, csol, tkmg, tkdry)]
+        lt = i32(lun_type)
+        return self.L.orc_thermal3_set_soils(self.h, *[dp(x) for x in a], ip(lt), int(nlevsoi), int(istsoil))
+
+    def set_cnfac(self, cnfac):
+        self.L.orc_thermal3_set_cnfac(self.h, C.c_double(cnfac))
+
+    def set_soln_prev(self, T):
+        T = f64(T)
+        assert T.size == self.ncells
+        self.L.orc_thermal3_set_soln_prev(self.h, dp(T))
+
+    def set_data(self, auxvar_type, var_type, cond_id, data, ieqn=1):
+        data = f64(data)
+        rc = self.L.orc_thermal3_set_rdata(self.h, int(auxvar_type), int(var_type), int(cond_id), dp(data), int(data.size))
+        if rc:
+            raise ValueError("set_rdata rc=%d" % rc)
+
+    def set_idata(self, auxvar_type, var_type, cond_id, data):
+        data = i32(data)
+        rc = self.L.orc_thermal3_set_idata(self.h, int(auxvar_type), int(var_type), int(cond_id), ip(data), int(data.size))
+        if rc:
+            raise ValueError("set_idata rc=%d" % rc)
+
+    def pre_step_dt(self):
+        self.L.orc_thermal3_pre_step_dt(self.h)
+
+    def post_step_dt(self):
+        pass
+
+    def step_dt(self, dt, nstep=1):
+        conv = C.c_int()
+        self.L.orc_thermal3_step_dt(self.h, C.c_double(dt), int(nstep), C.byref(conv))
+        return bool(conv.value), 0
+
+    def get_soln(self):
+        out = np.empty(self.ncells)
+        self.L.orc_thermal3_get_soln(self.h, dp(out))
         return out
 
 

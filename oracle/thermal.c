@@ -448,3 +448,373 @@ int orc_thermal_get_aux(orc_thermal *p, int var_type, double *data)
   }
   return 0;
 }
+
+/* =====================================================================================================================
+ * ELM's real thermal column: snow (<= nlevsno layers, variable active count) + standing surface water (1 cell) + soil,
+ * three governing equations coupled through COND_DIRICHLET_FRM_OTR_GOVEQ conditions into ONE linear system per step
+ * (SURVEY.md section 8f item 1).  Restates, for the configuration MPPThermalTBasedALM_Initialize.F90:524-639 builds:
+ *   src/mpp/auxvar/ThermalKSPTemperatureSnowAuxType.F90:58-84, ...SSWAuxType.F90:45-66     aux-var closures
+ *   src/mpp/ge/GoveqnThermalKSPTemperatureSnowType.F90:232-372, 572-702, 754-980, 1015-1300
+ *   src/mpp/ge/GoveqnThermalKSPTemperatureSSWType.F90:234-357, 554-648, 700-1130
+ *   src/mpp/ge/GoveqnThermalKSPTemperatureSoilType.F90:820-905 (coupling branches of Divergence), :1150-1190, :1232-1340
+ *   src/mpp/soe/SystemOfEquationsThermalType.F90:412-481 (PreSolve), :546-649 (RHS + exchange), :653-759 (operators)
+ *   src/driver/alm/MPPThermalTBasedALM_Driver.F90:150-420 (what the host model puts into the SoE mailbox)
+ * Unknown ordering = the reference's: [snow cells of all columns | ssw cells | soil cells], cell-ordered per column.
+ * PARITY UNPINNED for the snow/ssw equations: the reference has no regression baseline that exercises them (they are
+ * only reachable from ELM).  What IS checked: with snow and standing water inactive this path reproduces the soil-only
+ * restatement above (pinned to thermal_mms) bit for bit; the rest follows the Fortran statement by statement.
+ * TEST INFRASTRUCTURE ONLY.
+ * ===================================================================================================================== */
+#define ORC_TKAIR 0.023              /* mpp_varcon.F90:20 */
+#define THIN_SFCLAYER 1.0e-6         /* ThermalKSPTemperature{Snow,SSW}AuxType.F90 */
+
+typedef struct {                      /* therm_ksp_temp_{snow,ssw}_auxvar_type (+ base) */
+  double temperature; int is_active;
+  double frac, dhsdT, dist_up, dist_dn, therm_cond, heat_cap_pva;
+  double liq_areal_den, ice_areal_den; int num_snow_layer; double dz, tuning_factor;
+} saux;
+
+struct orc_thermal3 {
+  int ncol, nlev, nsno, nall, nthreads;
+  double cnfac, dtime;
+  /* soil mesh (static) */
+  double *dz, *area; orc_conn *conn_in; double *soil_top_dist_dn;
+  taux *soil;  int istsoil, istcrop, istice, istice_mec, istwet;
+  /* persistent per-cell state of the snow / ssw equations */
+  saux *snow, *ssw; double *snow_mesh_dz, *ssw_mesh_dz; int *snow_top_id;
+  /* persistent coupling aux vars (aux_vars_bc of the coupling conditions) */
+  double *sbc_T, *sbc_k, *sbc_frac, *sbc_dist_up; int *sbc_active;      /* soil <- snow bottom */
+  double *wbc_T, *wbc_k, *wbc_frac, *wbc_dz; int *wbc_active;           /* soil <- ssw */
+  double *soil_conn_du_snow, *soil_conn_du_ssw;                           /* conn dist_up of the soil's coupling conditions */
+  double *snow_conn_dd, *ssw_conn_dd;                                     /* conn dist_dn of the snow / ssw coupling conditions */
+  /* SoE mailbox, full length, SoE order */
+  double *T_clm, *soln, *liq, *ice, *snow_water, *mdz, *dist_up, *dist_dn, *tuning, *frac;
+  int *nsnow, *active;
+  double *hs[3], *dhsdT[3], *frac_soil;      /* BC 1 snow top, 2 ssw top, 3 soil top */
+  double *sabg_snow, *sabg_soil;             /* SS 1, SS 2 */
+};
+typedef struct orc_thermal3 orc_thermal3;
+
+static double *dalloc(size_t n, double v) { double *p = (double *)malloc(8 * (n ? n : 1)); size_t i; for (i = 0; i < n; i++) p[i] = v; return p; }
+
+orc_thermal3 *orc_thermal3_create(int ncol, int nlev, int nsno)
+{
+  orc_thermal3 *p = (orc_thermal3 *)calloc(1, sizeof(*p));
+  int i, k; size_t nall = (size_t)ncol * (nsno + 1 + nlev), ns = (size_t)ncol * nlev;
+  p->ncol = ncol; p->nlev = nlev; p->nsno = nsno; p->nall = (int)nall; p->nthreads = 1; p->cnfac = 0.5;
+  p->dz = dalloc(ns, 0.0); p->area = dalloc(ncol, 1.0); p->soil_top_dist_dn = dalloc(ncol, 0.0);
+  p->conn_in = (orc_conn *)calloc((size_t)ncol * (nlev > 1 ? nlev - 1 : 1), sizeof(orc_conn));
+  p->soil = (taux *)calloc(ns, sizeof(taux)); for (i = 0; i < (int)ns; i++) taux_init(&p->soil[i]);
+  p->snow = (saux *)calloc((size_t)ncol * nsno, sizeof(saux)); p->ssw = (saux *)calloc(ncol, sizeof(saux));
+  for (i = 0; i < ncol * nsno; i++) { p->snow[i].temperature = 273.15; p->snow[i].tuning_factor = 1.0; }
+  for (i = 0; i < ncol; i++) { p->ssw[i].temperature = 273.15; p->ssw[i].tuning_factor = 1.0; }
+  p->snow_mesh_dz = dalloc((size_t)ncol * nsno, 0.0); p->ssw_mesh_dz = dalloc(ncol, 1.0e-6);      /* ssw_dz = 1.d-6 (:277) */
+  p->snow_top_id = (int *)calloc(ncol, sizeof(int));                 /* SNOW_TOP_CELLS: first cell of the column */
+  p->sbc_T = dalloc(ncol, 273.15); p->sbc_k = dalloc(ncol, 0.0); p->sbc_frac = dalloc(ncol, 0.0); p->sbc_dist_up = dalloc(ncol, 0.0);
+  p->wbc_T = dalloc(ncol, 273.15); p->wbc_k = dalloc(ncol, 0.0); p->wbc_frac = dalloc(ncol, 0.0); p->wbc_dz = dalloc(ncol, 0.0);
+  p->sbc_active = (int *)calloc(ncol, sizeof(int)); p->wbc_active = (int *)calloc(ncol, sizeof(int));
+  p->soil_conn_du_snow = dalloc(ncol, 0.0); p->soil_conn_du_ssw = dalloc(ncol, 0.0);
+  p->snow_conn_dd = dalloc(ncol, 0.0); p->ssw_conn_dd = dalloc(ncol, 0.5e-6);
+  p->T_clm = dalloc(nall, 273.15); p->soln = dalloc(nall, 273.15);
+  p->liq = dalloc(nall, 0.0); p->ice = dalloc(nall, 0.0); p->snow_water = dalloc(nall, 0.0); p->mdz = dalloc(nall, 0.0);
+  p->dist_up = dalloc(nall, 0.0); p->dist_dn = dalloc(nall, 0.0); p->tuning = dalloc(nall, 1.0); p->frac = dalloc(nall, 0.0);
+  p->nsnow = (int *)calloc(nall, sizeof(int)); p->active = (int *)calloc(nall, sizeof(int));
+  for (k = 0; k < 3; k++) { p->hs[k] = dalloc(ncol, 0.0); p->dhsdT[k] = dalloc(ncol, 0.0); }
+  p->frac_soil = dalloc(ncol, 0.0);
+  p->sabg_snow = dalloc((size_t)ncol * nsno, 0.0); p->sabg_soil = dalloc(ns, 0.0);
+  p->istsoil = 1; p->istcrop = 2; p->istice = 3; p->istice_mec = 4; p->istwet = 6;
+  return p;
+}
+
+void orc_thermal3_destroy(orc_thermal3 *p)
+{
+  int k;
+  if (!p) return;
+  free(p->dz); free(p->area); free(p->soil_top_dist_dn); free(p->conn_in); free(p->soil); free(p->snow); free(p->ssw);
+  free(p->snow_mesh_dz); free(p->ssw_mesh_dz); free(p->snow_top_id);
+  free(p->sbc_T); free(p->sbc_k); free(p->sbc_frac); free(p->sbc_dist_up); free(p->sbc_active);
+  free(p->wbc_T); free(p->wbc_k); free(p->wbc_frac); free(p->wbc_dz); free(p->wbc_active);
+  free(p->soil_conn_du_snow); free(p->soil_conn_du_ssw); free(p->snow_conn_dd); free(p->ssw_conn_dd);
+  free(p->T_clm); free(p->soln); free(p->liq); free(p->ice); free(p->snow_water); free(p->mdz); free(p->dist_up); free(p->dist_dn);
+  free(p->tuning); free(p->frac); free(p->nsnow); free(p->active);
+  for (k = 0; k < 3; k++) { free(p->hs[k]); free(p->dhsdT[k]); }
+  free(p->frac_soil); free(p->sabg_snow); free(p->sabg_soil);
+  free(p);
+}
+
+void orc_thermal3_set_threads(orc_thermal3 *p, int n) { p->nthreads = n > 0 ? n : 1; }
+void orc_thermal3_set_cnfac(orc_thermal3 *p, double cnfac) { p->cnfac = cnfac; }
+
+/* soil mesh (dz as (ncol, nlev) Fortran order), internal soil connection distances ((ncol, nlev-1) Fortran order) and the
+ * dist_dn = z(c,1) - zi(c,0) the driver pokes into the soil's two coupling conditions (MPPThermalTBasedALM_Initialize.F90:630-639);
+ * snow_dz0 (ncol, nsno) = initial snow-mesh thickness col%dz (:295), may be NULL */
+int orc_thermal3_set_mesh(orc_thermal3 *p, const double *dz, const double *area, const double *conn_du, const double *conn_dd,
+                          const double *soil_top_dist_dn, const double *snow_dz0)
+{
+  int c, j, ncol = p->ncol, nlev = p->nlev;
+  for (c = 0; c < ncol; c++) {
+    p->area[c] = area[c]; p->soil_top_dist_dn[c] = soil_top_dist_dn[c];
+    for (j = 0; j < nlev; j++) p->dz[c * nlev + j] = dz[(size_t)j * ncol + c];
+    for (j = 0; j < nlev - 1; j++) {
+      orc_conn *cn = &p->conn_in[c * (nlev - 1) + j];
+      cn->id_up = c * nlev + j; cn->id_dn = cn->id_up + 1; cn->area = area[c];
+      cn->dist_up = conn_du ? conn_du[(size_t)j * ncol + c] : 0.5 * p->dz[cn->id_up];
+      cn->dist_dn = conn_dd ? conn_dd[(size_t)j * ncol + c] : 0.5 * p->dz[cn->id_dn];
+    }
+    for (j = 0; j < p->nsno; j++) if (snow_dz0) p->snow_mesh_dz[c * p->nsno + j] = snow_dz0[(size_t)j * ncol + c];
+  }
+  return 0;
+}
+
+int orc_thermal3_set_soils(orc_thermal3 *p, const double *watsat, const double *csol, const double *tkmg, const double *tkdry,
+                           const int *lun_type, int nlevsoi, int istsoil_id)
+{
+  int c, j, ncol = p->ncol, nlev = p->nlev;
+  if (istsoil_id > 0) p->istsoil = istsoil_id;
+  for (c = 0; c < ncol; c++) for (j = 0; j < nlev; j++) {
+    size_t t = (size_t)j * ncol + c; taux *a = &p->soil[c * nlev + j];
+    a->is_active = 1; a->is_soil_shallow = (j + 1 > nlevsoi) ? 0 : 1; a->itype = lun_type[c];
+    a->por = watsat[t]; a->therm_cond_minerals = tkmg[t]; a->therm_cond_dry = tkdry[t]; a->heat_cap_minerals_puv = csol[t];
+  }
+  return 0;
+}
+
+int orc_thermal3_set_soln_prev(orc_thermal3 *p, const double *T) { memcpy(p->T_clm, T, 8 * (size_t)p->nall); return 0; }
+
+int orc_thermal3_set_rdata(orc_thermal3 *p, int auxvar_type, int var_type, int cond_id, const double *data, int n)
+{
+  double *dst = NULL; int cap = 0, i;
+  if (auxvar_type == AUXVAR_INTERNAL) {
+    cap = p->nall;
+    switch (var_type) {
+    case VAR_TEMPERATURE: dst = p->T_clm; break;
+    case VAR_LIQ_AREAL_DEN: dst = p->liq; break;
+    case VAR_ICE_AREAL_DEN: dst = p->ice; break;
+    case VAR_SNOW_WATER: dst = p->snow_water; break;
+    case VAR_DZ: dst = p->mdz; break;
+    case VAR_DIST_UP: dst = p->dist_up; break;
+    case VAR_DIST_DN: dst = p->dist_dn; break;
+    case VAR_TUNING_FACTOR: dst = p->tuning; break;
+    case VAR_FRAC: dst = p->frac; break;
+    default: return 2;
+    }
+  } else if (auxvar_type == AUXVAR_BC) {
+    if (cond_id < 1 || cond_id > 3) return 3;
+    cap = p->ncol;
+    if (var_type == VAR_BC_SS_CONDITION) dst = p->hs[cond_id - 1];
+    else if (var_type == VAR_DHS_DT) dst = p->dhsdT[cond_id - 1];
+    else if (var_type == VAR_FRAC && cond_id == 3) dst = p->frac_soil;
+    else return 2;
+  } else if (auxvar_type == AUXVAR_SS) {
+    if (var_type != VAR_BC_SS_CONDITION) return 2;
+    if (cond_id == 1) { dst = p->sabg_snow; cap = p->ncol * p->nsno; }
+    else if (cond_id == 2) { dst = p->sabg_soil; cap = p->ncol * p->nlev; }
+    else return 3;
+  } else return 4;
+  if (n > cap) return 1;
+  for (i = 0; i < n; i++) dst[i] = data[i];
+  return 0;
+}
+
+int orc_thermal3_set_idata(orc_thermal3 *p, int auxvar_type, int var_type, int cond_id, const int *data, int n)
+{
+  int i, *dst; (void)cond_id;
+  if (auxvar_type != AUXVAR_INTERNAL || n > p->nall) return 1;
+  if (var_type == VAR_NUM_SNOW_LYR) dst = p->nsnow; else if (var_type == VAR_ACTIVE) dst = p->active; else return 2;
+  for (i = 0; i < n; i++) dst[i] = data[i];
+  return 0;
+}
+
+void orc_thermal3_pre_step_dt(orc_thermal3 *p) { memcpy(p->soln, p->T_clm, 8 * (size_t)p->nall); }   /* ThermalSOEPreStepDT */
+
+static double harm_cond(double kup, double kdn, double du, double dd) { return kup * kdn * (du + dd) / (kup * dd + kdn * du); }
+
+/* dense LU without pivoting in the SoE's natural order == PETSc's ILU(0) here (the column graph is a tree eliminated
+ * leaves first, so ILU(0) has no dropped fill and GMRES converges in one iteration) */
+static void dense_solve(int n, double *M, double *b, double *x)
+{
+  int i, j, k;
+  for (k = 0; k < n; k++) for (i = k + 1; i < n; i++) {
+    double f;
+    if (M[i * n + k] == 0.0) continue;
+    f = M[i * n + k] / M[k * n + k];
+    for (j = k; j < n; j++) M[i * n + j] -= f * M[k * n + j];
+    b[i] -= f * b[k];
+  }
+  for (i = n - 1; i >= 0; i--) { double s = b[i]; for (j = i + 1; j < n; j++) s -= M[i * n + j] * x[j]; x[i] = s / M[i * n + i]; }
+}
+
+static void step3_column(orc_thermal3 *p, int c, double stale_area)
+{
+  const int nlev = p->nlev, nsno = p->nsno, ncol = p->ncol, n = nsno + 1 + nlev;
+  const int o_sn = c * nsno, o_sw = ncol * nsno + c, o_so = ncol * (nsno + 1) + c * nlev;   /* offsets into SoE-ordered arrays */
+  const double dt = p->dtime, cnfac = p->cnfac, area = p->area[c];
+  saux *sn = &p->snow[c * nsno], *sw = &p->ssw[c]; taux *so = &p->soil[c * nlev];
+  double *M = (double *)calloc((size_t)n * n + 2 * n, 8), *b = M + (size_t)n * n, *x = b + n;
+  double snow_vol[64], ssw_vol, hv_snow = 0.0, hv_ssw = 0.0, hv_soil = 0.0;
+  int j, bot = nsno - 1, r_sw = nsno, r_so = nsno + 1, top;
+  /* ---------------- PreSolve ---------------- */
+  for (j = 0; j < nsno; j++) {                                    /* snow: GetFromSOEAuxVarsIntrn :232-277 */
+    saux *a = &sn[j];
+    a->temperature = p->soln[o_sn + j];
+    a->liq_areal_den = p->liq[o_sn + j]; a->ice_areal_den = p->ice[o_sn + j]; a->num_snow_layer = p->nsnow[o_sn + j];
+    a->is_active = p->active[o_sn + j]; a->frac = p->frac[o_sn + j]; a->tuning_factor = p->tuning[o_sn + j];
+    a->dz = p->mdz[o_sn + j]; a->dist_up = p->dist_up[o_sn + j]; a->dist_dn = p->dist_dn[o_sn + j];
+    if (a->is_active) p->snow_mesh_dz[c * nsno + j] = p->mdz[o_sn + j];
+    snow_vol[j] = a->is_active ? area * p->snow_mesh_dz[c * nsno + j] : 0.0;       /* UpdateInternalConn :572-614 (dx dy = area) */
+  }
+  if (nsno > 0 && sn[bot].is_active) {                            /* UpdateBoundaryConn :618-702 */
+    p->snow_top_id[c] = nsno - sn[bot].num_snow_layer;            /* iconn*nlevsno - num_snow_layer + 1, 0-based within the column */
+    p->snow_conn_dd[c] = sn[bot].dist_up;
+  }
+  top = p->snow_top_id[c];
+  if (nsno > 0 && (top < 0 || top >= nsno)) top = 0;
+  if (nsno > 0) hv_snow = p->hs[0][c] - p->dhsdT[0][c] * sn[top].temperature;      /* GetFromSOEAuxVarsBC :281-372 */
+  sw->temperature = p->soln[o_sw]; sw->is_active = p->active[o_sw]; sw->dz = p->mdz[o_sw]; sw->frac = p->frac[o_sw];   /* ssw :234-268 */
+  if (sw->is_active) {                                            /* UpdateInternalConn :554-589 */
+    if (sw->dz * sw->frac * 1.0e3 > THIN_SFCLAYER && sw->frac > THIN_SFCLAYER) p->ssw_mesh_dz[c] = fmax(THIN_SFCLAYER, sw->dz);
+    else p->ssw_mesh_dz[c] = THIN_SFCLAYER;
+    ssw_vol = area * p->ssw_mesh_dz[c];
+    p->ssw_conn_dd[c] = p->ssw_mesh_dz[c] / 2.0;                  /* UpdateBoundaryConn :593-648 */
+  } else ssw_vol = 0.0;
+  hv_ssw = p->hs[1][c] - p->dhsdT[1][c] * sw->temperature;
+  for (j = 0; j < nlev; j++) {                                    /* soil: GetFromSOEAuxVarsIntrn (soil GE :232-272) */
+    taux *a = &so[j];
+    a->temperature = p->soln[o_so + j];
+    a->liq_areal_den = p->liq[o_so + j]; a->ice_areal_den = p->ice[o_so + j]; a->snow_water = p->snow_water[o_so + j];
+    a->num_snow_layer = p->nsnow[o_so + j]; a->tuning_factor = p->tuning[o_so + j]; a->frac = p->frac[o_so + j];
+    a->dz = p->mdz[o_so + j]; a->is_active = p->active[o_so + j];
+  }
+  hv_soil = p->hs[2][c] - p->dhsdT[2][c] * so[0].temperature;
+  /* ---------------- ComputeRHS: aux vars, exchange ---------------- */
+  for (j = 0; j < nsno; j++) {                                    /* ThermKSPTempSnowAuxVarCompute :58-84 */
+    saux *a = &sn[j]; double dzm = p->snow_mesh_dz[c * nsno + j], bw;
+    if (!a->is_active) continue;
+    bw = (a->ice_areal_den + a->liq_areal_den) / (a->frac * dzm);
+    a->therm_cond = ORC_TKAIR + (7.75e-5 * bw + 1.105e-6 * bw * bw) * (ORC_TKICE - ORC_TKAIR);
+    if (a->frac > 0.0) a->heat_cap_pva = fmax(THIN_SFCLAYER, (ORC_CPLIQ * a->liq_areal_den + ORC_CPICE * a->ice_areal_den) / a->frac);
+    else a->heat_cap_pva = THIN_SFCLAYER;
+    a->heat_cap_pva = a->heat_cap_pva / dzm;
+  }
+  if (sw->is_active) {                                            /* ThermKSPTempSSWAuxVarCompute :45-66 */
+    double dzm = p->ssw_mesh_dz[c];
+    sw->therm_cond = ORC_TKWAT;
+    if (dzm * sw->frac * 1.0e3 > THIN_SFCLAYER && sw->frac > THIN_SFCLAYER) sw->heat_cap_pva = fmax(THIN_SFCLAYER, ORC_CPLIQ * ORC_DENH2O);
+    else sw->heat_cap_pva = THIN_SFCLAYER;
+  }
+  { orc_thermal tmp; memset(&tmp, 0, sizeof(tmp));
+    tmp.istsoil = p->istsoil; tmp.istcrop = p->istcrop; tmp.istice = p->istice; tmp.istice_mec = p->istice_mec; tmp.istwet = p->istwet;
+    for (j = 0; j < nlev; j++) taux_compute(&tmp, &so[j], p->dz[c * nlev + j], area * p->dz[c * nlev + j]); }
+  /* ThermalSOEGovEqnExchangeAuxVars :763-915 with the coupling variables of MPPThermalTBasedALM_Initialize.F90:672-727 */
+  if (nsno > 0) {
+    p->sbc_T[c] = sn[bot].temperature; p->sbc_k[c] = sn[bot].therm_cond; p->sbc_frac[c] = sn[bot].frac;
+    p->sbc_active[c] = sn[bot].is_active ? 1 : 0; p->sbc_dist_up[c] = sn[bot].dist_up;
+  }
+  p->wbc_T[c] = sw->temperature; p->wbc_k[c] = sw->therm_cond; p->wbc_frac[c] = sw->frac; p->wbc_active[c] = sw->is_active ? 1 : 0;
+  p->wbc_dz[c] = sw->dz;
+  /* soil UpdateBoundaryConn (soil GE :1343-1400) */
+  if (nsno > 0 && p->sbc_active[c]) p->soil_conn_du_snow[c] = p->sbc_dist_up[c];
+  if (p->wbc_active[c]) p->soil_conn_du_ssw[c] = p->wbc_dz[c] / 2.0;
+  /* ---------------- snow rows ---------------- */
+  for (j = 0; j < nsno; j++) {
+    const saux *a = &sn[j];
+    if (a->is_active) { M[j * n + j] = a->heat_cap_pva * snow_vol[j] / (dt * a->tuning_factor); b[j] = M[j * n + j] * a->temperature; }
+    else M[j * n + j] = 1.0;
+  }
+  for (j = 0; j + 1 < nsno; j++) {
+    const saux *up = &sn[j], *dn = &sn[j + 1]; double du, dd, k, flux, value;
+    if (!up->is_active || !dn->is_active) continue;
+    du = up->dist_up; dd = dn->dist_dn;                           /* SetDistUp(aux(up)%dist_up), SetDistDn(aux(dn)%dist_dn) */
+    k = harm_cond(up->therm_cond, dn->therm_cond, du, dd);
+    flux = -k * (up->temperature - dn->temperature) / (du + dd);
+    b[j] += cnfac * flux * area; b[j + 1] -= cnfac * flux * area;
+    value = (1.0 - cnfac) * k / (du + dd) * area;
+    M[j * n + j] += value; M[j * n + j + 1] += -value; M[(j + 1) * n + j] += -value; M[(j + 1) * n + j + 1] += value;
+  }
+  if (nsno > 0 && sn[top].is_active) {                            /* COND_HEAT_FLUX at the top active layer */
+    b[top] += hv_snow * area; M[top * n + top] += -p->dhsdT[0][c] * area;
+  }
+  if (nsno > 0 && sn[bot].is_active) {                            /* coupling with the soil: bc aux var = soil top cell (T, k) */
+    double du = 0.0, dd = p->snow_conn_dd[c], k = harm_cond(so[0].therm_cond, sn[bot].therm_cond, du, dd);
+    double flux = -k * (so[0].temperature - sn[bot].temperature) / (du + dd), value = (1.0 - cnfac) * k / (du + dd) * area;
+    b[bot] -= cnfac * flux * area;
+    M[bot * n + bot] += value; M[bot * n + r_so] += -value;
+  }
+  for (j = 0; j < nsno; j++) if (sn[j].is_active) b[j] += p->sabg_snow[c * nsno + j];
+  /* ---------------- ssw row ---------------- */
+  if (sw->is_active) {
+    double du = 0.0, dd_conn = p->ssw_conn_dd[c], dist = du + dd_conn, dd = sw->dz / 2.0;
+    double k = so[0].therm_cond * sw->therm_cond * (du + dd) / (so[0].therm_cond * dd + sw->therm_cond * du);
+    double flux = -k * (so[0].temperature - sw->temperature) / dist, coeff = (1.0 - cnfac) * k / dist * area;
+    M[r_sw * n + r_sw] = sw->heat_cap_pva * ssw_vol / dt; b[r_sw] = M[r_sw * n + r_sw] * sw->temperature;
+    b[r_sw] += hv_ssw * area; M[r_sw * n + r_sw] += -p->dhsdT[1][c] * area;
+    b[r_sw] -= cnfac * flux * area;
+    M[r_sw * n + r_sw] += coeff; M[r_sw * n + r_so] += -coeff;
+  } else M[r_sw * n + r_sw] = 1.0;
+  /* ---------------- soil rows ---------------- */
+  for (j = 0; j < nlev; j++) {
+    const taux *a = &so[j]; int r = r_so + j;
+    if (a->is_active) { M[r * n + r] = a->heat_cap_pva * (area * p->dz[c * nlev + j]) / (dt * a->tuning_factor); b[r] = M[r * n + r] * a->temperature; }
+    else M[r * n + r] = 1.0;
+  }
+  for (j = 0; j + 1 < nlev; j++) {
+    const orc_conn *cn = &p->conn_in[c * (nlev - 1) + j]; const taux *up = &so[j], *dn = &so[j + 1];
+    double k, flux, value; int r = r_so + j;
+    if (!up->is_active || !dn->is_active) continue;
+    k = harm_cond(up->therm_cond, dn->therm_cond, cn->dist_up, cn->dist_dn);
+    flux = -k * (up->temperature - dn->temperature) / (cn->dist_up + cn->dist_dn);
+    b[r] += cnfac * flux * cn->area; b[r + 1] -= cnfac * flux * cn->area;
+    value = (1.0 - cnfac) * k / (cn->dist_up + cn->dist_dn) * cn->area;
+    M[r * n + r] += value; M[r * n + r + 1] += -value; M[(r + 1) * n + r] += -value; M[(r + 1) * n + r + 1] += value;
+  }
+  if (so[0].is_active) {
+    int r = r_so; double a_stale;
+    /* condition 1: COND_HEAT_FLUX (sets `area`) */
+    b[r] += hv_soil * p->frac_soil[c] * area;
+    M[r * n + r] += -p->frac_soil[c] * pow(p->dhsdT[2][c], area);
+    a_stale = stale_area;          /* `area` left behind by the heat-flux loop over ALL columns = the last column's */
+    /* condition 2: coupling with snow (Divergence :843-876 else-branch; OperatorsDiag/OffDiag) */
+    if (nsno > 0 && p->sbc_active[c]) {
+      double du = p->soil_conn_du_snow[c], dd = p->soil_top_dist_dn[c];
+      double k = harm_cond(p->sbc_k[c], so[0].therm_cond, du, dd), flux = -k * (p->sbc_T[c] - so[0].temperature) / (du + dd);
+      double value = p->sbc_frac[c] * (1.0 - cnfac) * (p->sbc_k[c] * so[0].therm_cond * (du + dd) / (p->sbc_k[c] * dd + so[0].therm_cond * du)) / (du + dd) * area;
+      b[r] -= p->sbc_frac[c] * cnfac * flux * a_stale;
+      M[r * n + r] += value; M[r * n + bot] += -value;
+    }
+    /* condition 3: coupling with standing water (is_bc_sh2o branches) */
+    if (p->wbc_active[c]) {
+      double du = p->soil_conn_du_ssw[c], dd_conn = p->soil_top_dist_dn[c], dd = so[0].dz / 2.0, k, dist, flux, value;
+      k = p->wbc_k[c] * so[0].therm_cond * (du + dd) / (p->wbc_k[c] * dd + so[0].therm_cond * du);           /* Divergence: dist_dn = aux dz / 2 */
+      dist = dd + fmax(1.0e-6, du * 2.0) / 2.0;
+      flux = -k * (p->wbc_T[c] - so[0].temperature) / dist;
+      b[r] -= p->wbc_frac[c] * cnfac * flux * a_stale;
+      k = p->wbc_k[c] * so[0].therm_cond * (du + dd_conn) / (p->wbc_k[c] * dd_conn + so[0].therm_cond * du);   /* operators: the connection's dist_dn */
+      dist = dd_conn + fmax(1.0e-6, du * 2.0) / 2.0;
+      value = p->wbc_frac[c] * (1.0 - cnfac) * k / dist * area;
+      M[r * n + r] += value; M[r * n + r_sw] += -value;
+    }
+  }
+  for (j = 0; j < nlev; j++) if (so[j].is_active) b[r_so + j] += p->sabg_soil[c * nlev + j];
+  /* ---------------- KSPSolve + PostSolve ---------------- */
+  dense_solve(n, M, b, x);
+  for (j = 0; j < nsno; j++) p->soln[o_sn + j] = x[j];
+  p->soln[o_sw] = x[r_sw];
+  for (j = 0; j < nlev; j++) p->soln[o_so + j] = x[r_so + j];
+  free(M);
+}
+
+int orc_thermal3_step_dt(orc_thermal3 *p, double dt, int nstep, int *converged)
+{
+  int c; double stale = p->area[p->ncol - 1];
+  (void)nstep;
+  if (p->nsno > 64) return 1;
+  p->dtime = dt;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static) num_threads(p->nthreads)
+#endif
+  for (c = 0; c < p->ncol; c++) step3_column(p, c, stale);
+  if (converged) *converged = 1;
+  return 0;
+}
+
+int orc_thermal3_get_soln(orc_thermal3 *p, double *T) { memcpy(T, p->soln, 8 * (size_t)p->nall); return 0; }

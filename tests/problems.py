@@ -256,6 +256,149 @@ def elm_thermal_step(p, ids, d, T, dt=1800.0, nstep=1):
 
 
 # ---------------------------------------------------------------------------------------------------
+# ELM's real thermal column: snow + standing surface water + soil
+#   set-up    src/driver/alm/MPPThermalTBasedALM_Initialize.F90:150-813
+#   per step  src/driver/alm/MPPThermalTBasedALM_Driver.F90:150-452 (the packing below mirrors it index for index)
+# ---------------------------------------------------------------------------------------------------
+CAPR = 0.34                                                            # mpp_varcon.F90:30
+
+
+def elm_snow_thermal_inputs(ncol, nlev=15, nlevsno=5, seed=SEED, nlevsoi=10, snow="mixed", water="mixed"):
+    """ELM-like column state in ELM's own index space: soil layers 1..nlev, snow layers -nlevsno+1..0 (stored at array index
+    j + nlevsno), snl = -(active snow layers)."""
+    d = elm_thermal_inputs(ncol, nlev, seed, nlevsoi)
+    rng = np.random.default_rng(seed + 7)
+    z, zi, dz = elm_layers(nlev)
+    d["nlevsno"] = nlevsno
+    d["soil_top_dist_dn"] = np.full(ncol, z[0] - zi[0])              # z(c,1) - zi(c,0)  (Initialize.F90:575-577)
+    if snow == "none":
+        nsn = np.zeros(ncol, dtype=np.int64)
+    elif snow == "all":
+        nsn = rng.integers(1, nlevsno + 1, ncol)
+    else:
+        nsn = rng.integers(0, nlevsno + 1, ncol)
+    d["snl"] = -nsn
+    # snow geometry: layer thicknesses grow downward; z / zi negative upward from the soil surface (zi(c,0) = 0)
+    sdz = np.zeros((ncol, nlevsno)); sz = np.zeros((ncol, nlevsno)); szi = np.zeros((ncol, nlevsno + 1))   # szi[:, k] = zi(c, k - nlevsno)
+    for c in range(ncol):
+        th = rng.uniform(0.02, 0.25, nlevsno) * np.linspace(0.5, 2.0, nlevsno)
+        for k in range(nlevsno - 1, nlevsno - 1 - nsn[c], -1):       # from the bottom snow layer (j = 0) upwards
+            sdz[c, k] = th[k]
+            szi[c, k] = szi[c, k + 1] - th[k]
+            sz[c, k] = 0.5 * (szi[c, k] + szi[c, k + 1])
+    d["snow_dz"], d["snow_z"], d["snow_zi"] = sdz, sz, szi
+    d["frac_sno_eff"] = np.where(nsn > 0, rng.uniform(0.2, 1.0, ncol), 0.0)
+    rho = rng.uniform(80.0, 400.0, (ncol, nlevsno))                   # bulk density [kg m^-3]
+    tot = rho * sdz * d["frac_sno_eff"][:, None]
+    wet = rng.uniform(0.0, 0.1, (ncol, nlevsno))
+    d["snow_liq"], d["snow_ice"] = tot * wet, tot * (1.0 - wet)
+    d["h2osno"] = (d["snow_liq"] + d["snow_ice"]).sum(axis=1)
+    d["t_snow"] = np.where(sdz > 0, rng.uniform(250.0, 273.15, (ncol, nlevsno)), 0.0)
+    if water == "none":
+        fw = np.zeros(ncol)
+    elif water == "all":
+        fw = rng.uniform(0.01, 0.3, ncol)
+    else:
+        fw = np.where(rng.uniform(size=ncol) < 0.5, rng.uniform(1e-8, 0.3, ncol), 0.0)   # includes "thin layer" cases
+    fw = np.minimum(fw, 0.95 - d["frac_sno_eff"]).clip(min=0.0)
+    d["frac_h2osfc"] = fw
+    d["h2osfc"] = np.where(fw > 0, rng.uniform(1e-4, 30.0, ncol), 0.0)  # mm
+    d["t_h2osfc"] = rng.uniform(273.2, 285.0, ncol)
+    d["hs_top_snow"] = rng.uniform(-80.0, 60.0, ncol); d["hs_h2osfc"] = rng.uniform(-50.0, 150.0, ncol); d["hs_soil"] = d["hs"]
+    d["sabg_lyr"] = rng.uniform(0.0, 40.0, (ncol, nlevsno + 1))       # (c, -nlevsno+1 : 1)
+    d["t_soil"] = d["T0"].reshape(ncol, nlev).copy()
+    d["z"], d["zi"], d["dz1"] = z, zi, dz
+    return d
+
+
+def pack_elm_snow_thermal(d):
+    """MPPThermalTBasedALM_Driver.F90:204-330: ELM column state -> the 1-D SoE mailbox arrays [snow | ssw | soil]."""
+    ncol, nlev, nsno = d["ncol"], d["nlev"], d["nlevsno"]
+    N = ncol * (nlev + nsno + 1)
+    o = {"T": np.full(N, 273.15), "liq": np.zeros(N), "ice": np.zeros(N), "snow_water": np.zeros(N), "dz": np.zeros(N),
+         "dist_up": np.zeros(N), "dist_dn": np.zeros(N), "frac": np.ones(N), "nsnow": np.zeros(N, dtype=np.int32),
+         "active": np.zeros(N, dtype=np.int32), "tuning": np.ones(N),
+         "hs_snow": np.zeros(ncol), "hs_sh2o": np.zeros(ncol), "hs_soil": np.zeros(ncol), "dhsdT_snow": np.zeros(ncol),
+         "dhsdT_sh2o": np.zeros(ncol), "dhsdT_soil": np.zeros(ncol), "frac_soil": np.ones(ncol),
+         "sabg_snow": np.zeros(ncol * nsno), "sabg_soil": np.zeros(ncol * nlev)}
+    z, zi, dz = d["z"], d["zi"], d["dz1"]
+    snl = d["snl"]
+
+    def zs(c, j):                     # z(c, j) for j <= 0 snow, j >= 1 soil
+        return d["snow_z"][c, j + nsno - 1] if j <= 0 else z[j - 1]
+
+    def zis(c, j):                    # zi(c, j): interface below layer j
+        return d["snow_zi"][c, j + nsno] if j <= 0 else zi[j]
+    for c in range(ncol):
+        for j in range(-nsno + 1, 1):
+            if j >= snl[c] + 1:
+                k = j + nsno - 1
+                idx = c * nsno + k
+                o["T"][idx] = d["t_snow"][c, k]; o["dz"][idx] = d["snow_dz"][c, k]
+                o["liq"][idx] = d["snow_liq"][c, k]; o["ice"][idx] = d["snow_ice"][c, k]
+                o["nsnow"][idx] = -snl[c]; o["active"][idx] = 1
+                o["dist_up"][idx] = zis(c, j) - zs(c, j); o["dist_dn"][idx] = zs(c, j) - zis(c, j - 1)
+                o["frac"][idx] = d["frac_sno_eff"][c]
+                if j != snl[c] + 1:
+                    o["sabg_snow"][idx] = d["sabg_lyr"][c, k]
+                if j == snl[c] + 1:
+                    o["tuning"][idx] = d["snow_dz"][c, k] / (0.5 * (zs(c, j) - zis(c, j - 1) + CAPR * (zs(c, j + 1) - zis(c, j - 1))))
+                    o["hs_snow"][c] = d["hs_top_snow"][c]; o["dhsdT_snow"][c] = d["dhsdT"][c]
+                    o["frac_soil"][c] -= d["frac_sno_eff"][c]
+    off = ncol * nsno
+    for c in range(ncol):
+        if d["frac_h2osfc"][c] > 0.0:
+            idx = off + c
+            o["T"][idx] = d["t_h2osfc"][c]; o["dz"][idx] = 1.0e-3 * d["h2osfc"][c]; o["active"][idx] = 1
+            o["frac"][idx] = d["frac_h2osfc"][c]; o["dist_up"][idx] = o["dz"][idx] / 2.0; o["dist_dn"][idx] = o["dz"][idx] / 2.0
+            o["frac_soil"][c] -= d["frac_h2osfc"][c]; o["dhsdT_sh2o"][c] = d["dhsdT"][c]; o["hs_sh2o"][c] = d["hs_h2osfc"][c]
+    off = ncol * (nsno + 1)
+    liq, ice = d["liq"].reshape(ncol, nlev), d["ice"].reshape(ncol, nlev)
+    for c in range(ncol):
+        for j in range(1, nlev + 1):
+            idx = off + c * nlev + j - 1
+            o["T"][idx] = d["t_soil"][c, j - 1]; o["dz"][idx] = dz[j - 1]; o["active"][idx] = 1
+            o["liq"][idx] = liq[c, j - 1]; o["ice"][idx] = ice[c, j - 1]; o["frac"][idx] = 1.0
+            o["dist_up"][idx] = zi[j] - z[j - 1]; o["dist_dn"][idx] = zi[j] - z[j - 1]
+            if j == 1:
+                o["dz"][idx] = z[0] * 2.0; o["nsnow"][idx] = -snl[c]
+                if snl[c] != 0:
+                    o["sabg_soil"][c * nlev] = d["frac_sno_eff"][c] * d["sabg_lyr"][c, nsno]
+                    o["snow_water"][idx] = d["h2osno"][c]
+                else:
+                    o["tuning"][idx] = dz[0] / (0.5 * (z[0] - zi[0] + CAPR * (z[1] - zi[0])))
+                o["hs_soil"][c] = d["hs_soil"][c]; o["dhsdT_soil"][c] = d["dhsdT"][c]
+    return o
+
+
+def build_elm_snow_thermal(cls, d, **kw):
+    ncol, nlev, nsno = d["ncol"], d["nlev"], d["nlevsno"]
+    p = cls(ncol, nlev, nsno, **kw)
+    p.set_mesh(d["dz"], d["area"], d["dist_up"], d["dist_dn"], d["soil_top_dist_dn"])
+    p.set_soils(d["watsat"], d["csol"], d["tkmg"], d["tkdry"], d["lun_type"], d["nlevsoi"], K.ISTSOIL)
+    return p
+
+
+def elm_snow_thermal_step(p, o, dt=1800.0, nstep=1):
+    """The SetSolnPrevCLM / Set{R,I,B}DataFromCLM / PreStepDT / StepDT / GetSoln sequence of MPPThermalTBasedALM_Driver.F90:332-452."""
+    p.set_soln_prev(o["T"])
+    for var, key in ((K.VAR_LIQ_AREAL_DEN, "liq"), (K.VAR_ICE_AREAL_DEN, "ice"), (K.VAR_SNOW_WATER, "snow_water"), (K.VAR_DZ, "dz"),
+                     (K.VAR_DIST_UP, "dist_up"), (K.VAR_DIST_DN, "dist_dn"), (K.VAR_TUNING_FACTOR, "tuning"), (K.VAR_FRAC, "frac")):
+        p.set_data(K.AUXVAR_INTERNAL, var, 1, o[key])
+    p.set_idata(K.AUXVAR_INTERNAL, K.VAR_NUM_SNOW_LYR, 1, o["nsnow"])
+    p.set_idata(K.AUXVAR_INTERNAL, K.VAR_ACTIVE, 1, o["active"])
+    for cid, a, b in ((1, "hs_snow", "dhsdT_snow"), (2, "hs_sh2o", "dhsdT_sh2o"), (3, "hs_soil", "dhsdT_soil")):
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, cid, o[a])
+        p.set_data(K.AUXVAR_BC, K.VAR_DHS_DT, cid, o[b])
+    p.set_data(K.AUXVAR_BC, K.VAR_FRAC, 3, o["frac_soil"])
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, 1, o["sabg_snow"])
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, 2, o["sabg_soil"])
+    p.pre_step_dt()
+    conv, _ = p.step_dt(dt, nstep)
+    return conv, p.get_soln()
+
+
+# ---------------------------------------------------------------------------------------------------
 # TH mass_and_heat -- src/driver/standalone/thermal-e/mass_and_heat_model_problem.F90
 #   baseline regression_tests/th/mass_and_heat.regression.baseline (SURVEY.md Appendix C)
 # ---------------------------------------------------------------------------------------------------

@@ -204,3 +204,54 @@ def test_th_analytic_jacobian_blocks_vs_finite_differences(oracle, dens, iee):
     # the reference's dFT/dT uses the true temperature derivative of the mass flux but its dFP/dP keeps upwinded kr
     # frozen at the switch, so compare away from upwind switches: relative to the row scale
     assert np.max(np.abs(J - Jfd) / scale) < 5e-5
+
+
+def test_snow_ssw_soil_oracle_reduces_to_pinned_soil_oracle(oracle):
+    """The snow / standing-water extension has no reference baseline (parity unpinned); with both inactive it must reproduce the
+    soil-only restatement, which is pinned to thermal_mms."""
+    import problems as PB
+    ncol, nlev, nsno = 60, 15, 5
+    d = PB.elm_snow_thermal_inputs(ncol, nlev, nsno, snow="none", water="none")
+    o = PB.pack_elm_snow_thermal(d)
+    p = PB.build_elm_snow_thermal(oracle.OracleThermalSnow, d)
+    conv, T = PB.elm_snow_thermal_step(p, o)
+    off = ncol * (nsno + 1)
+    q, ids = PB.build_elm_thermal(oracle.OracleThermal, d)
+    d2 = dict(d); d2["tuning"] = o["tuning"][off:]; d2["frac"] = o["frac_soil"]; d2["sabg"] = o["sabg_soil"]
+    conv2, T2 = PB.elm_thermal_step(q, ids, d2, d["T0"])
+    assert np.max(np.abs(T[off:] - T2) / T2) < 1e-14
+    assert np.all(T[:off] == 0.0)
+
+
+def test_snow_ssw_soil_oracle_energy_budget(oracle):
+    """Independent check of the restated coupled system: with cnfac = 0 (fully implicit) each active row is
+    C (T_new - T_old) = sum of the implicit fluxes + sources; summing the rows weighted as the reference weights them is not
+    conservative (the snow->soil and soil->snow links differ by design), so check the rows of an all-snow, no-water column
+    set through a hand-built dense system instead."""
+    import problems as PB
+    ncol, nlev, nsno = 6, 15, 5
+    d = PB.elm_snow_thermal_inputs(ncol, nlev, nsno, snow="all", water="none")
+    o = PB.pack_elm_snow_thermal(d)
+    p = PB.build_elm_snow_thermal(oracle.OracleThermalSnow, d)
+    conv, T = PB.elm_snow_thermal_step(p, o)
+    # interior snow rows (neither top nor bottom active layer): C (Tn - To) = cnfac*(F_up - F_dn)(old) + (1-cnfac)*(F_up - F_dn)(new) + sabg
+    tkair, tkice, cpliq, cpice = 0.023, 2.29, 4.188e3, 2.11727e3
+    checked = 0
+    for c in range(ncol):
+        ns = -d["snl"][c]
+        for k in range(nsno - ns + 1, nsno - 1):
+            i = c * nsno + k
+            def cond(ii):
+                bw = (o["ice"][ii] + o["liq"][ii]) / (o["frac"][ii] * o["dz"][ii])
+                return tkair + (7.75e-5 * bw + 1.105e-6 * bw * bw) * (tkice - tkair)
+            def flux(Tv, up, dn):
+                du, dd = o["dist_up"][up], o["dist_dn"][dn]
+                ku, kd = cond(up), cond(dn)
+                kk = ku * kd * (du + dd) / (ku * dd + kd * du)
+                return -kk * (Tv[up] - Tv[dn]) / (du + dd)
+            C_ = max(1e-6, (cpliq * o["liq"][i] + cpice * o["ice"][i]) / o["frac"][i]) / o["dz"][i] * o["dz"][i] / (1800.0 * o["tuning"][i])
+            lhs = C_ * (T[i] - o["T"][i])
+            rhs = 0.5 * (flux(o["T"], i, i + 1) - flux(o["T"], i - 1, i)) + 0.5 * (flux(T, i, i + 1) - flux(T, i - 1, i)) + o["sabg_snow"][i]
+            assert abs(lhs - rhs) <= 1e-9 * max(abs(lhs), abs(rhs), 1.0), (c, k, lhs, rhs)
+            checked += 1
+    assert checked > 0

@@ -132,3 +132,55 @@ def test_th_residual_and_jacobian_blocks_match_oracle(mpp, oracle, dens, iee):
         a, b = a.reshape(n, 4), b.reshape(n, 4)
         scale = np.maximum(np.abs(jbo.reshape(n, 4)), 1e-300)      # compare each block entry with the matching diagonal-block entry
         assert np.max(np.abs(a - b) / scale) < 1e-9, (name, np.max(np.abs(a - b) / scale))
+
+
+@pytest.mark.parametrize("nlev", [15, 24])
+def test_th_pressure_and_temperature_dirichlet_boundaries(mpp, oracle, nlev):
+    """A water table under the column: Dirichlet pressure on the mass equation AND Dirichlet temperature (with the same boundary
+    pressure poked into the energy equation's boundary aux var, mass_and_heat_model_problem.F90:616-621) at the bottom face,
+    Dirichlet temperature at the top.  Exercises the boundary branches of both governing equations (RichardsFlux with
+    upweight 0, the advective + conductive boundary flux of ThermalEnthalpyFlux) in the lane-per-cell kernel (15 layers)
+    and in the generic one (24 layers)."""
+    ncol = 60 if nlev == 15 else 8
+    d = PB.elm_th_inputs(ncol, nlev)
+    rng = np.random.default_rng(31)
+    Pb0 = d["press_ic"].reshape(ncol, nlev)[:, -1]
+    Tb0 = d["temp_ic"].reshape(ncol, nlev)[:, -1]
+    dzb = np.broadcast_to(np.asarray(d["dz"]).reshape(-1, nlev), (ncol, nlev))[:, -1]
+    P_wt = Pb0 + 9.8e3 * 0.5 * dzb + rng.uniform(-3.0e3, 3.0e3, ncol)      # near hydrostatic balance with the bottom cell
+    T_wt = Tb0 + rng.uniform(-1.0, 1.0, ncol)
+
+    def build(cls, **kw):
+        p = cls(ncol, nlev, **kw)
+        p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"])
+        ids = dict(tb=p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS),
+                   pb=p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS),
+                   eb=p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS),
+                   heat=p.add_condition(2, K.COND_SS, K.COND_HEAT_RATE, K.SOIL_CELLS))
+        p.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], d["csol"], d["tkdry"], "van_genuchten",
+                    K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_CONSTANT)
+        p.restart(d["press_ic"], d["temp_ic"])
+        return p, ids
+    g, o = build(mpp.TH), build(oracle.OracleTH, per_column=True, nthreads=8)
+    for step in range(3):
+        for s, ids in (g, o):
+            s.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids["tb"], d["T_top"], ieqn=2)
+            s.set_data(K.AUXVAR_BC, K.VAR_PRESSURE, ids["tb"], d["P_top_bc"], ieqn=2)
+            s.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids["pb"], P_wt, ieqn=1)
+            s.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids["eb"], T_wt, ieqn=2)
+            s.set_data(K.AUXVAR_BC, K.VAR_PRESSURE, ids["eb"], P_wt, ieqn=2)
+            s.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["heat"], d["heat"], ieqn=2)
+        conv, reason = g[0].step_dt(1800.0, step + 1)
+        convo, reasono = o[0].step_dt(1800.0, step + 1)
+        assert conv == convo
+        sg, so_ = g[0].stats(), o[0].stats()
+        ok = (so_["reasons"] > 0) & (so_["dt_cuts"] == 0) & (sg["newton_its"] == so_["newton_its"])
+        assert ok.mean() > 0.9
+        for var, key, ieqn in ((K.VAR_PRESSURE, "P", 1), (K.VAR_TEMPERATURE, "T", 2)):
+            a = g[0].get_data(K.AUXVAR_INTERNAL, var, 1, ieqn=ieqn).reshape(ncol, nlev)
+            b = o[0].get_data(K.AUXVAR_INTERNAL, var, 1, ieqn=ieqn).reshape(ncol, nlev)
+            assert (relmax_p if key == "P" else relmax)(a[ok], b[ok]) < RTOL, (step, key)
+    # the boundaries act on the bottom cell
+    Tg = g[0].get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, 1, ieqn=2).reshape(ncol, nlev)
+    Pg = g[0].get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1, ieqn=1).reshape(ncol, nlev)
+    assert np.abs(Tg[:, -1] - Tb0).max() > 1e-4 and np.abs(Pg[:, -1] - Pb0).max() > 1.0

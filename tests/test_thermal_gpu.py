@@ -106,3 +106,84 @@ def test_thermal_error_behaviour(mpp):
         p.add_condition(1, K.COND_BC, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
     with pytest.raises(mpp.MPPError):
         p.set_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1, np.zeros(60))
+
+
+# ---- snow + standing surface water + soil (MPPThermalTBasedALM_{Initialize,Driver}.F90) ----------------------
+def _snow_advance(d, o, T, rng):
+    """Feed the solution back as ELM would (t_soisno / t_h2osfc) and perturb the forcing for the next step."""
+    ncol, nlev, nsno = d["ncol"], d["nlev"], d["nlevsno"]
+    act = o["active"] == 1
+    Tn = np.where(act, T, 273.15)
+    d["t_snow"] = np.where(d["snow_dz"] > 0, Tn[:ncol * nsno].reshape(ncol, nsno), 0.0)
+    d["t_h2osfc"] = np.where(d["frac_h2osfc"] > 0, Tn[ncol * nsno:ncol * (nsno + 1)], d["t_h2osfc"])
+    d["t_soil"] = Tn[ncol * (nsno + 1):].reshape(ncol, nlev)
+    d["hs_top_snow"] = d["hs_top_snow"] + rng.uniform(-5.0, 5.0, ncol)
+    d["hs_soil"] = d["hs_soil"] + rng.uniform(-5.0, 5.0, ncol)
+
+
+@pytest.mark.parametrize("ncol,nlev,nsno,snow,water", [(300, 15, 5, "mixed", "mixed"), (64, 15, 5, "all", "all"), (33, 10, 3, "mixed", "none"),
+                                                       (5, 26, 5, "mixed", "mixed"), (129, 15, 0, "none", "mixed")])
+def test_snow_ssw_soil_thermal_matches_oracle(mpp, oracle, ncol, nlev, nsno, snow, water):
+    d = PB.elm_snow_thermal_inputs(ncol, nlev, nsno, snow=snow, water=water, nlevsoi=min(10, nlev))
+    g = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    r = PB.build_elm_snow_thermal(oracle.OracleThermalSnow, d, nthreads=4)
+    rng = np.random.default_rng(3)
+    for step in range(3):
+        o = PB.pack_elm_snow_thermal(d)
+        conv, T = PB.elm_snow_thermal_step(g, o, 1800.0, step + 1)
+        convo, To = PB.elm_snow_thermal_step(r, o, 1800.0, step + 1)
+        assert conv and convo
+        act = o["active"] == 1
+        assert relmax(T[act], To[act]) < RTOL, (step, relmax(T[act], To[act]))
+        assert np.all(T[~act] == 0.0) and np.all(To[~act] == 0.0)          # identity rows with a zero right-hand side
+        assert np.abs(T[act] - o["T"][act]).max() > 1e-3                    # the step did something
+        _snow_advance(d, o, To, rng)
+
+
+def test_snow_mode_without_snow_or_water_equals_soil_only_kernel(mpp):
+    ncol, nlev, nsno = 200, 15, 5
+    d = PB.elm_snow_thermal_inputs(ncol, nlev, nsno, snow="none", water="none")
+    o = PB.pack_elm_snow_thermal(d)
+    g = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    conv, T = PB.elm_snow_thermal_step(g, o)
+    off = ncol * (nsno + 1)
+    s, ids = PB.build_elm_thermal(mpp.Thermal, d)
+    d2 = dict(d); d2["tuning"] = o["tuning"][off:]; d2["frac"] = o["frac_soil"]; d2["sabg"] = o["sabg_soil"]
+    conv2, T2 = PB.elm_thermal_step(s, ids, d2, d["T0"])
+    assert relmax(T[off:], T2) < 1e-12
+    assert np.all(T[:off] == 0.0)
+
+
+def test_snow_layer_count_changes_between_steps(mpp, oracle):
+    """The heat-flux condition follows the top ACTIVE snow layer (ThermKSPTempSnowUpdateBoundaryConn): grow, shrink and lose the pack."""
+    ncol = 40
+    d = PB.elm_snow_thermal_inputs(ncol, 15, 5, snow="all", water="none")
+    g = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    r = PB.build_elm_snow_thermal(oracle.OracleThermalSnow, d)
+    rng = np.random.default_rng(11)
+    for step, mode in enumerate(("all", "mixed", "none", "all")):
+        d2 = PB.elm_snow_thermal_inputs(ncol, 15, 5, seed=PB.SEED + step, snow=mode, water="none")
+        for k in ("snl", "snow_dz", "snow_z", "snow_zi", "frac_sno_eff", "snow_liq", "snow_ice", "h2osno", "t_snow"):
+            d[k] = d2[k]
+        o = PB.pack_elm_snow_thermal(d)
+        conv, T = PB.elm_snow_thermal_step(g, o, 1800.0, step + 1)
+        convo, To = PB.elm_snow_thermal_step(r, o, 1800.0, step + 1)
+        act = o["active"] == 1
+        assert relmax(T[act], To[act]) < RTOL, (step, mode)
+        _snow_advance(d, o, To, rng)
+
+
+def test_snow_mode_error_behaviour(mpp):
+    d = PB.elm_snow_thermal_inputs(4, 15, 5)
+    g = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    with pytest.raises(mpp.MPPError):
+        g.add_condition(1, K.COND_BC, K.COND_HEAT_FLUX, K.SOIL_TOP_CELLS)          # the configuration brings its own conditions
+    with pytest.raises(mpp.MPPError):
+        g.set_data(K.AUXVAR_INTERNAL, K.VAR_LIQ_AREAL_DEN, 1, np.zeros(g.ncells + 1))
+    with pytest.raises(mpp.MPPError):
+        g.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, 4, np.zeros(4))
+    with pytest.raises(mpp.MPPError):
+        g.restart(np.zeros(4 * 15))                                                  # soil-only length
+    big = mpp.ThermalSnow(2, 30, 5)
+    with pytest.raises(mpp.MPPError):                                                # 36 rows per column
+        big.set_mesh(np.ones((2, 30)), np.ones(2), np.ones((2, 29)), np.ones((2, 29)), np.ones(2))
