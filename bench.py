@@ -175,6 +175,21 @@ def other_workloads(device, stream):
     out["thermal_1Mi_x15"] = {"column_timesteps_per_sec": ncol / (m * 1e-3), "ms_per_step": m, "kernel": "thermal_step_kernel<16>",
                               "roofline": {"bound": "hbm", "algorithmic_bytes_per_column_step": 1224, "achieved": 1224 * ncol / (m * 1e-3) / 1e9, "unit": "GB/s"}}
     p.close()
+    # ELM's real thermal column: 5 snow layers (variable active count) + standing surface water + 15 soil layers
+    base = 4096
+    d0 = PB.elm_snow_thermal_inputs(base, NLEV, 5)
+    d, o = PB.tile_snow_thermal(d0, PB.pack_elm_snow_thermal(d0), ncol // base)
+    p = PB.build_elm_snow_thermal(mpp_b200.ThermalSnow, d, device=device)
+    p.set_stream(stream)
+    PB.elm_snow_thermal_step(p, o, DT, 1)
+    ms = []
+    for s in range(13):
+        p.step_dt(DT, s + 2); ms.append(p.last_step_ms())
+    m = float(np.mean(ms[3:]))
+    out["thermal_snow_ssw_soil_1Mi_x21"] = {"column_timesteps_per_sec": ncol / (m * 1e-3), "ms_per_step": m, "kernel": "thermal_snow_step_kernel<16>",
+                                            "roofline": {"bound": "hbm", "algorithmic_bytes_per_column_step": 2356,
+                                                         "achieved": 2356 * ncol / (m * 1e-3) / 1e9, "unit": "GB/s"}}
+    p.close()
     # TH: Tanaka density + constant heat capacity (the throughput variant of SURVEY.md section 8d)
     ncol = 1 << 18
     d = PB.elm_th_inputs(ncol, NLEV)

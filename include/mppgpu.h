@@ -102,7 +102,7 @@ int  mppgpu_thermal_set_cnfac(mppgpu_handle h, double cnfac);
  * before any data is set; mppgpu_add_condition is not used in this configuration.  From then on every AUXVAR_INTERNAL array
  * (set_data / set_idata / restart / get_data) has ncol*(nlevsno+1+nlev) entries in the reference's SoE order
  * [snow cells, column-major | standing-water cells | soil cells], as MPPThermalTBasedALM_Driver.F90:204-452 packs them;
- * inactive cells come back as 0 like the reference's identity rows.  nlevsno + 1 + nlev <= 32. */
+ * inactive cells come back as 0 like the reference's identity rows.  ceil(nlevsno/2) + ceil(nlev/2) <= 16. */
 int  mppgpu_thermal_add_snow_ssw(mppgpu_handle h, int nlevsno, const double *soil_top_dist_dn);
 int  mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
                          const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,

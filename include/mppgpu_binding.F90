@@ -33,6 +33,12 @@ module MPPGpuBinding
        real(c_double), intent(in) :: watsat(*), hksat(*), bsw(*), sucsat(*), residual_sat(*)
        integer(c_int), value      :: satfunc_type, density_type
      end function
+     integer(c_int) function mppgpu_thermal_add_snow_ssw(h, nlevsno, soil_top_dist_dn) bind(C, name="mppgpu_thermal_add_snow_ssw")
+       import :: c_int, c_ptr, c_double
+       type(c_ptr), value         :: h
+       integer(c_int), value      :: nlevsno
+       real(c_double), intent(in) :: soil_top_dist_dn(*)
+     end function
      integer(c_int) function mppgpu_set_tolerances(h, atol, rtol, stol, max_it, max_funcs) bind(C, name="mppgpu_set_tolerances")
        import :: c_int, c_ptr, c_double
        type(c_ptr), value    :: h
@@ -81,7 +87,7 @@ module MPPGpuBinding
      end function
   end interface
 
-  public :: mppgpu_create, mppgpu_set_mesh, mppgpu_add_condition, mppgpu_vsfm_set_soils, mppgpu_set_tolerances, &
+  public :: mppgpu_create, mppgpu_set_mesh, mppgpu_add_condition, mppgpu_vsfm_set_soils, mppgpu_thermal_add_snow_ssw, mppgpu_set_tolerances, &
             mppgpu_restart, mppgpu_set_data, mppgpu_get_data, mppgpu_pre_step_dt, mppgpu_step_dt, mppgpu_post_step_dt, &
             mppgpu_destroy, mppgpu_last_error
 end module MPPGpuBinding

@@ -52,8 +52,8 @@ static int thermal_add_snow_ssw(mppgpu_soe *h, ThermalState *t, int nlevsno, con
   if (t->snow_mode) return fail("mppgpu_thermal_add_snow_ssw: already added");
   if (!h->bcs.empty() || !h->sss.empty()) return fail("mppgpu_thermal_add_snow_ssw: the ELM configuration brings its own conditions; add none before");
   if (h->orientation == MPPGPU_MESH_AGAINST_GRAVITY) return fail("mppgpu_thermal_add_snow_ssw: the ELM thermal meshes are MESH_ALONG_GRAVITY");
-  if (nlevsno < 0 || nlevsno + 1 + h->nlev > 32)
-    return fail("mppgpu_thermal_add_snow_ssw: nlevsno + 1 + nlev = %d rows per column; at most 32 are supported", nlevsno + 1 + h->nlev);
+  if (nlevsno < 0 || (nlevsno + 1) / 2 + (h->nlev + 1) / 2 > 16)
+    return fail("mppgpu_thermal_add_snow_ssw: %d snow + %d soil layers per column; at most 32 rows (each block rounded up to even) are supported", nlevsno, h->nlev);
   if (!soil_top_dist_dn) return fail("mppgpu_thermal_add_snow_ssw: null soil_top_dist_dn");
   const size_t ncol = h->ncol, NA = ncol * (size_t)(nlevsno + 1 + h->nlev), NS = ncol * (size_t)nlevsno, NG = h->ncells;
   cudaStream_t s = h->stream;
@@ -219,7 +219,7 @@ static int thermal_snow_step(mppgpu_soe *h, ThermalState *t, double dt)
   A.snow_top_id = t->snow_top_id;
   A.T_out = (t->T_cur == t->T_clm) ? t->T_work : t->T_cur;
   CK(cudaEventRecord(h->ev0, h->stream));
-  thermal_snow_step_kernel<<<nblk((long long)h->ncol * 32, TH_TILE), TH_TILE, 0, h->stream>>>(A);
+  thermal_snow_step_kernel<16><<<nblk((long long)h->ncol * 16, TH_TILE), TH_TILE, 0, h->stream>>>(A);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
   h->launches += 1;

@@ -9,11 +9,12 @@
 //   soil   coupling branches  src/mpp/ge/GoveqnThermalKSPTemperatureSoilType.F90:820-905, 1150-1190, 1232-1400
 // Unknown / mailbox ordering = the reference's SoE vector: [snow cells of all columns | ssw cells | soil cells].
 //
-// Mapping: one warp per column, one matrix row per lane -- lanes [0, nsno) the snow layers (top to bottom), lanes
-// [nsno, nsno+nlev) the soil layers, lane nsno+nlev the standing-water cell.  The column graph is a chain
-// (snow - soil) with the standing-water cell hanging off the top soil row: that leaf is folded into the top soil row by
-// one Schur step over shuffles, the chain goes through normalised parallel cyclic reduction in registers, and the leaf
-// is back-substituted.  Every mailbox array is read once, coalesced per segment; nothing is staged in shared memory.
+// Mapping: 16 lanes per column (two columns per warp), two matrix rows per lane -- rows [0, nsno) the snow layers (top to
+// bottom), rows [nsno, nsno+nlev) the soil layers.  The column graph is a chain (snow - soil) with the standing-water cell
+// hanging off the top soil row: that leaf is computed by the lane that owns the top soil row and folded into it by one
+// Schur step, the chain's odd rows are eliminated in-lane and its even rows go through normalised parallel cyclic
+// reduction in registers (4 stages), then the odd rows and the leaf are back-substituted.  Every mailbox array is read
+// once, coalesced per segment; nothing is staged in shared memory.
 // The snow -> soil and soil -> snow links are NOT symmetric in the reference (the soil side weights by the snow-cover
 // fraction and uses the harmonic conductivity, the snow side uses its own conductivity over its own half thickness),
 // so the rows carry separate sub- and super-diagonals.
@@ -39,168 +40,244 @@ struct ThermalSnowArgs {
 constexpr double THIN_SFCLAYER = 1.0e-6;   // ThermalKSPTemperature{Snow,SSW}AuxType.F90
 constexpr double TKAIR = 0.023;            // mpp_varcon.F90:20
 
-__global__ void __launch_bounds__(TH_TILE, 6)
+// One matrix row of the chain (snow layers top to bottom, then soil layers): the state a neighbouring row needs travels by
+// shuffle (T, tk, act, du, x2, frac); everything else stays in the lane.
+struct SnowRow {
+  double T, tk, cap, du, x2, frac, mdz, src, bb, rhs, sub, sup;   // du: snow aux dist_up | soil connection dist_up; x2: snow aux dist_dn | soil connection dist_dn
+  int act, nsn;
+};
+
+__device__ __forceinline__ void snow_row_clear(SnowRow &r)
+{
+  r.T = 0.0; r.tk = 1.0; r.cap = 0.0; r.du = 0.5; r.x2 = 0.5; r.frac = 0.0; r.mdz = 0.0; r.src = 0.0; r.act = 0; r.nsn = 0;
+  r.sub = 0.0; r.sup = 0.0; r.bb = 1.0; r.rhs = 0.0;
+}
+
+// PreSolve + aux vars of snow layer s (0 = topmost of the nsno slots) of column `col`
+__device__ __forceinline__ void snow_layer_load(const ThermalSnowArgs &A, SnowRow &r, int s, int col, double area, double &liq, double &ice, double &tf)
+{
+  const long long idx = (long long)col * A.nsno + s;
+  r.T = A.T_in[idx]; r.mdz = A.mdz[idx]; r.frac = A.frac[idx]; r.act = A.active[idx]; r.nsn = A.nsnow[idx];
+  tf = A.tuning[idx]; liq = A.liq[idx]; ice = A.ice[idx];
+  r.du = A.dist_up[idx]; r.x2 = A.dist_dn[idx]; r.src = A.sabg_snow[idx];
+}
+__device__ __forceinline__ void snow_layer_aux(const ThermalSnowArgs &A, SnowRow &r, double area, double liq, double ice, double tf)
+{
+  if (r.act) {                                        // ThermKSPTempSnowAuxVarCompute; mesh dz = VAR_DZ of an active cell (:268-270)
+    const double bw = (ice + liq) * rcp(r.frac * r.mdz);
+    r.tk = TKAIR + (7.75e-5 * bw + 1.105e-6 * bw * bw) * (TKICE - TKAIR);
+    double hc = THIN_SFCLAYER;
+    if (r.frac > 0.0) { hc = (CPLIQ * liq + CPICE * ice) * rcp(r.frac); hc = (hc > THIN_SFCLAYER) ? hc : THIN_SFCLAYER; }
+    hc = hc * rcp(r.mdz);
+    r.cap = hc * (area * r.mdz) * rcp(A.S.dt * tf);
+    r.bb = r.cap; r.rhs = r.cap * r.T;
+  }
+}
+
+struct SoilIn { double liq, ice, snoww, tf, por, tkmg, tkdry, csol, sdz; };
+__device__ __forceinline__ void soil_layer_load(const ThermalSnowArgs &A, SnowRow &r, SoilIn &in, int j, int col)
+{
+  const int nlev = A.S.nlev;
+  const long long scell = (long long)col * nlev + j, idx = (long long)A.S.ncol * (A.nsno + 1) + scell;
+  r.T = A.T_in[idx]; r.mdz = A.mdz[idx]; r.frac = A.frac[idx]; r.act = A.active[idx]; r.nsn = A.nsnow[idx];
+  in.tf = A.tuning[idx]; in.liq = A.liq[idx]; in.ice = A.ice[idx]; in.snoww = A.snow_water[idx];
+  r.src = A.sabg_soil[scell];
+  in.sdz = A.S.dz[scell]; in.por = A.S.por[scell]; in.tkmg = A.S.tkmg[scell]; in.tkdry = A.S.tkdry[scell]; in.csol = A.S.csol[scell];
+  if (A.S.dist_uniform) { r.du = A.S.lay_du[j]; r.x2 = A.S.lay_dd[j]; }
+  else if (A.S.dist_up) { r.du = A.S.dist_up[scell]; r.x2 = A.S.dist_dn[scell]; }
+  else { r.du = 0.5 * in.sdz; r.x2 = (j + 1 < nlev) ? 0.5 * A.S.dz[scell + 1] : 0.5; }
+}
+__device__ __forceinline__ void soil_layer_aux(const ThermalSnowArgs &A, SnowRow &r, const SoilIn &in, int j, int lun, double area)
+{
+  double hc;
+  thermal_auxvar(A.S, lun, j < A.S.nlevsoi, r.T, in.liq, in.ice, in.snoww, r.nsn, in.por, in.tkmg, in.tkdry, in.csol, in.sdz, r.tk, hc);
+  if (r.act) { r.cap = hc * (area * in.sdz) * rcp(A.S.dt * in.tf); r.bb = r.cap; r.rhs = r.cap * r.T; }
+}
+
+// Contributions of the connection between an upper chain row U and the row D below it to both rows:
+//   kind 1 / 2  snow-snow / soil-soil   snow GE :817-858 / :1046-1083, soil GE as thermal_step_kernel (symmetric)
+//   kind 3      snow bottom | soil top  the two COND_DIRICHLET_FRM_OTR_GOVEQ conditions (snow GE :861-893, :1096-1137, :1202-1300;
+//                                       soil GE :843-876, :1150-1190, :1232-1340) -- not symmetric
+__device__ __forceinline__ void snow_connect(const ThermalSnowArgs &A, int kind, double area, double dd_top,
+                                             double UT, double Utk, int Uact, double Udu, double Ux2, double Ufrac,
+                                             double DT, double Dtk, int Dact, double Dx2,
+                                             double &U_rhs, double &U_bb, double &U_sup, double &D_rhs, double &D_bb, double &D_sub)
+{
+  const double cnfac = A.S.cnfac;
+  U_rhs = 0.0; U_bb = 0.0; U_sup = 0.0; D_rhs = 0.0; D_bb = 0.0; D_sub = 0.0;
+  if (kind == 3) {                                    // snow bottom (U) | soil top (D)
+    if (Uact) {
+      // snow side: boundary aux var = the soil's top cell; conn dist_up = 0, dist_dn = the snow cell's dist_up (:688-694)
+      const double kod = Dtk * Utk * rcp(Dtk * Udu) * area;
+      const double fl = -kod * (DT - UT);
+      U_rhs = -cnfac * fl;
+      U_bb = (1.0 - cnfac) * kod; U_sup = -U_bb;
+      if (Dact) {
+        // soil side: conn dist_up = the snow cell's dist_up, dist_dn = z(c,1) - zi(c,0); weighted by the snow-cover fraction;
+        // `area` of the flux term is stale in this branch of the reference (:843-876)
+        const double kos = Utk * Dtk * rcp(Utk * dd_top + Dtk * Udu);
+        const double fs = -kos * (UT - DT);
+        D_rhs = -Ufrac * cnfac * fs * A.S.stale_area;
+        D_bb = Ufrac * (1.0 - cnfac) * kos * area; D_sub = -D_bb;
+      }
+    }
+  } else if (kind != 0 && Uact && Dact) {
+    const double dd = (kind == 1) ? Dx2 : Ux2;        // snow: SetDistDn(aux(dn)%dist_dn); soil: the connection's own dist_dn
+    const double kod = Utk * Dtk * rcp(Utk * dd + Dtk * Udu) * area;
+    const double fl = -kod * (UT - DT);
+    const double cv = (1.0 - cnfac) * kod;
+    U_rhs = cnfac * fl; U_bb = cv; U_sup = -cv;
+    D_rhs = -cnfac * fl; D_bb = cv; D_sub = -cv;
+  }
+}
+
+// LPC lanes per column, two chain rows per lane, 32/LPC columns per warp.  A lane is either a snow lane or a soil lane (the snow
+// block is padded at the TOP to an even number of rows), so the two rows of a lane share one code path and their loads are
+// issued together; the bottom snow layer is always the second row of the last snow lane and the top soil layer the first row
+// of the first soil lane, which also owns the standing-water cell.
+#ifndef SNOW_MIN_BLOCKS
+#define SNOW_MIN_BLOCKS 4
+#endif
+template <int LPC>
+__global__ void __launch_bounds__(TH_TILE, SNOW_MIN_BLOCKS)
 thermal_snow_step_kernel(const ThermalSnowArgs A)
 {
   constexpr unsigned FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  const int col = blockIdx.x * (TH_TILE / 32) + (threadIdx.x >> 5);
-  if (col >= A.S.ncol) return;                       // whole warp
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = (int)(tid / LPC), l = (int)(tid % LPC);
   const int nsno = A.nsno, nlev = A.S.nlev, ncol = A.S.ncol;
-  const int l_so = nsno, l_sw = nsno + nlev, l_bot = nsno - 1;
-  const bool is_snow = lane < nsno, is_soil = lane >= l_so && lane < l_sw, is_ssw = lane == l_sw;
-  const bool valid = lane <= l_sw;
-  const int j = lane - nsno;                          // soil layer
-  const double dt = A.S.dt, cnfac = A.S.cnfac, area = A.S.area[col];
-  const long long scell = (long long)col * nlev + (is_soil ? j : 0);            // index into the soil-sized static tables
-  const long long idx = is_snow ? (long long)col * nsno + lane
-                      : is_soil ? (long long)ncol * (nsno + 1) + (long long)col * nlev + j
-                                : (long long)ncol * nsno + col;
+  const int pad = nsno & 1, ns2 = (nsno + pad) >> 1;
+  const bool col_ok = col < ncol;
+  const bool snow_lane = l < ns2;
+  const int sa = 2 * l - pad, sb = sa + 1;            // snow layers of a snow lane (sa = -1: the padding row)
+  const int ja = 2 * (l - ns2), jb = ja + 1;          // soil layers of a soil lane
+  const double cnfac = A.S.cnfac, dt = A.S.dt;
+  const double area = col_ok ? A.S.area[col] : 1.0;
+  const double dd_top = col_ok ? A.soil_top_dist_dn[col] : 1.0;
 
-  // ---- PreSolve: GetFromSOEAuxVarsIntrn of the three equations ----
-  double T = 0.0, mdz = 0.0, frac = 0.0, tf = 1.0, adu = 0.0, add_ = 0.0, liq = 0.0, ice = 0.0, snoww = 0.0, src = 0.0;
-  int act = 0, nsn = 0;
-  if (valid) {
-    T = A.T_in[idx]; mdz = A.mdz[idx]; frac = A.frac[idx]; act = A.active[idx];
-    if (!is_ssw) {
-      tf = A.tuning[idx]; liq = A.liq[idx]; ice = A.ice[idx]; nsn = A.nsnow[idx];
-      if (is_snow) { adu = A.dist_up[idx]; add_ = A.dist_dn[idx]; src = A.sabg_snow[(long long)col * nsno + lane]; }
-      else { snoww = A.snow_water[idx]; src = A.sabg_soil[scell]; }
+  // per-column scalars (conditions, standing-water cell, persistent top-of-snow id): issued up front with the row loads so the
+  // kernel pays one DRAM latency, not one per dependent stage; the 16 lanes of a column read the same sectors
+  const long long widx = (long long)ncol * nsno + col;
+  double H0 = 0.0, dH0 = 0.0, H1 = 0.0, dH1 = 0.0, H2 = 0.0, dH2 = 0.0, frs = 0.0, wT = 0.0, wmdz = 0.0, wfrac = 0.0;
+  int wact = 0, top_old = 0;
+  if (col_ok) {
+    H0 = A.hs[0][col]; dH0 = A.dhsdT[0][col]; H1 = A.hs[1][col]; dH1 = A.dhsdT[1][col]; H2 = A.hs[2][col]; dH2 = A.dhsdT[2][col];
+    frs = A.frac_soil[col]; top_old = A.snow_top_id[col];
+    wact = A.active[widx]; wT = A.T_in[widx]; wmdz = A.mdz[widx]; wfrac = A.frac[widx];
+  }
+  SnowRow a, b;
+  snow_row_clear(a); snow_row_clear(b);
+  bool va = false, vb = false;                        // the row exists
+  if (col_ok) {
+    if (snow_lane) {
+      double liq_a = 0.0, ice_a = 0.0, tf_a = 1.0, liq_b, ice_b, tf_b;
+      va = sa >= 0; vb = true;
+      if (va) snow_layer_load(A, a, sa, col, area, liq_a, ice_a, tf_a);
+      snow_layer_load(A, b, sb, col, area, liq_b, ice_b, tf_b);
+      if (va) snow_layer_aux(A, a, area, liq_a, ice_a, tf_a);
+      snow_layer_aux(A, b, area, liq_b, ice_b, tf_b);
+    } else if (ja < nlev) {
+      SoilIn ia, ib;
+      const int lun = A.S.lun_type[col];
+      va = true; vb = jb < nlev;
+      soil_layer_load(A, a, ia, ja, col);
+      if (vb) soil_layer_load(A, b, ib, jb, col);
+      soil_layer_aux(A, a, ia, ja, lun, area);
+      if (vb) soil_layer_aux(A, b, ib, jb, lun, area);
     }
   }
-  // ---- aux vars: conductivity tk, capacity term cap = heat_cap * vol / (dt * tuning) ----
-  double tk = 1.0, cap = 0.0, cdu = 0.5, cdd = 0.5;   // cdu / cdd: distances of the connection lane -> lane+1
-  double sw_dzm = THIN_SFCLAYER;
-  const double sdz = is_soil ? A.S.dz[scell] : 0.0;  // static soil mesh thickness
-  if (is_snow) {
-    if (act) {                                        // ThermKSPTempSnowAuxVarCompute; mesh dz = VAR_DZ of an active cell (:268-270)
-      const double bw = (ice + liq) * rcp(frac * mdz);
-      tk = TKAIR + (7.75e-5 * bw + 1.105e-6 * bw * bw) * (TKICE - TKAIR);
-      double hc = THIN_SFCLAYER;
-      if (frac > 0.0) { hc = (CPLIQ * liq + CPICE * ice) * rcp(frac); hc = (hc > THIN_SFCLAYER) ? hc : THIN_SFCLAYER; }
-      hc = hc * rcp(mdz);
-      cap = hc * (area * mdz) * rcp(dt * tf);
-    }
-    cdu = adu;                                        // UpdateInternalConn: SetDistUp(aux(up)%dist_up), SetDistDn(aux(dn)%dist_dn)
-  } else if (is_ssw) {
-    if (act) {                                        // SSW UpdateInternalConn (:554-589) + ThermKSPTempSSWAuxVarCompute
-      sw_dzm = (mdz * frac * 1.0e3 > THIN_SFCLAYER && frac > THIN_SFCLAYER) ? ((mdz > THIN_SFCLAYER) ? mdz : THIN_SFCLAYER) : THIN_SFCLAYER;
-      tk = TKWAT;
-      double hc = THIN_SFCLAYER;
-      if (sw_dzm * frac * 1.0e3 > THIN_SFCLAYER && frac > THIN_SFCLAYER) { hc = CPLIQ * DENH2O; hc = (hc > THIN_SFCLAYER) ? hc : THIN_SFCLAYER; }
-      cap = hc * (area * sw_dzm) * rcp(dt);
-    }
-  } else if (is_soil) {
-    double hc;
-    thermal_auxvar(A.S, A.S.lun_type[col], j < A.S.nlevsoi, T, liq, ice, snoww, nsn, A.S.por[scell], A.S.tkmg[scell], A.S.tkdry[scell],
-                   A.S.csol[scell], sdz, tk, hc);
-    if (act) cap = hc * (area * sdz) * rcp(dt * tf);
-    if (A.S.dist_uniform) { cdu = A.S.lay_du[j]; cdd = A.S.lay_dd[j]; }
-    else if (A.S.dist_up) { cdu = A.S.dist_up[scell]; cdd = A.S.dist_dn[scell]; }
-    else cdu = 0.5 * sdz;
+
+  // ---- connections: a|b in-lane, b|next lane's a ----
+  double u0, u1, u2, d0, d1, d2;
+  snow_connect(A, (va && vb) ? (snow_lane ? 1 : 2) : 0, area, dd_top, a.T, a.tk, a.act, a.du, a.x2, a.frac, b.T, b.tk, b.act, b.x2, u0, u1, u2, d0, d1, d2);
+  a.rhs += u0; a.bb += u1; a.sup = u2; b.rhs += d0; b.bb += d1; b.sub = d2;
+  {
+    // the connection (this lane's b | next lane's a) is evaluated once, by the upper lane; the lower lane receives its share
+    const double nT = __shfl_down_sync(FULL, a.T, 1, LPC), ntk = __shfl_down_sync(FULL, a.tk, 1, LPC), nx2 = __shfl_down_sync(FULL, a.x2, 1, LPC);
+    const int nact = __shfl_down_sync(FULL, a.act, 1, LPC), nva = __shfl_down_sync(FULL, (int)va, 1, LPC);
+    const int kn = (l + 1 < LPC && vb && nva) ? ((l + 1 < ns2) ? 1 : (l + 1 == ns2 ? 3 : 2)) : 0;
+    snow_connect(A, kn, area, dd_top, b.T, b.tk, b.act, b.du, b.x2, b.frac, nT, ntk, nact, nx2, u0, u1, u2, d0, d1, d2);
+    b.rhs += u0; b.bb += u1; b.sup = u2;
+    const double p0 = __shfl_up_sync(FULL, d0, 1, LPC), p1 = __shfl_up_sync(FULL, d1, 1, LPC), p2 = __shfl_up_sync(FULL, d2, 1, LPC);
+    if (l > 0) { a.rhs += p0; a.bb += p1; a.sub = p2; }
   }
-  // neighbour (lane + 1) state
-  const double T_d = __shfl_down_sync(FULL, T, 1), tk_d = __shfl_down_sync(FULL, tk, 1), add_d = __shfl_down_sync(FULL, add_, 1);
-  const int act_d = __shfl_down_sync(FULL, act, 1);
-  const double sdz_d = __shfl_down_sync(FULL, sdz, 1);
-  if (is_snow) cdd = add_d;
-  if (is_soil && !A.S.dist_uniform && !A.S.dist_up) cdd = 0.5 * sdz_d;
-  // ---- rows: accumulation ----
-  double bb, rhs, aa = 0.0, cc = 0.0;
-  if (act) { bb = cap; rhs = cap * T; } else { bb = 1.0; rhs = 0.0; }
-  // ---- internal connections lane -> lane+1 within the same equation (snow GE :817-858 / :1046-1083, soil GE as thermal_step_kernel) ----
-  const bool same_eq = (is_snow && lane + 1 < nsno) || (is_soil && lane + 1 < l_sw);
-  double cval = 0.0, flux = 0.0;
-  if (same_eq && act && act_d) {
-    const double kod = tk * tk_d * rcp(tk * cdd + tk_d * cdu) * area;
-    flux = -kod * (T - T_d);
-    cval = (1.0 - cnfac) * kod;
-  }
-  const double cval_m = __shfl_up_sync(FULL, cval, 1), flux_m = __shfl_up_sync(FULL, flux, 1);
-  rhs = rhs + cnfac * flux; bb += cval; cc = -cval;
-  if (lane > 0) { rhs = rhs - cnfac * flux_m; bb += cval_m; aa = -cval_m; }
-  // ---- snow: heat flux at the top ACTIVE layer, coupling with the soil at the bottom layer ----
-  const double T_m = __shfl_up_sync(FULL, T, 1), tk_m = __shfl_up_sync(FULL, tk, 1), frac_m = __shfl_up_sync(FULL, frac, 1);
-  const double adu_m = __shfl_up_sync(FULL, adu, 1);
-  const int act_m = __shfl_up_sync(FULL, act, 1);
+  // ---- heat flux at the top ACTIVE snow layer (UpdateBoundaryConn :680-686; :896-909, :1140-1155) ----
   if (nsno > 0) {
-    const int bot_act = __shfl_sync(FULL, act, l_bot), bot_nsn = __shfl_sync(FULL, nsn, l_bot);
-    int top;
-    if (bot_act) { top = nsno - bot_nsn; if (lane == 0) A.snow_top_id[col] = top; }     // UpdateBoundaryConn :680-686
-    else top = A.snow_top_id[col];
-    if (is_snow && lane == top && act) {                                               // COND_HEAT_FLUX (:896-909, :1140-1155)
-      const double H = A.hs[0][col], dH = A.dhsdT[0][col];
-      rhs = rhs + (H - dH * T) * area;
-      bb += -dH * area;
-    }
-    if (lane == l_bot && act) {
-      // boundary aux var = the soil's top cell (T, conductivity); conn dist_up = 0, dist_dn = this cell's dist_up (:688-694)
-      const double dd = adu;
-      const double kod = tk_d * tk * rcp(tk_d * dd) * area;
-      const double fl = -kod * (T_d - T);
-      rhs = rhs - cnfac * fl;
-      const double v = (1.0 - cnfac) * kod;
-      bb += v; cc = -v;
+    const int bot_act = __shfl_sync(FULL, b.act, ns2 - 1, LPC), bot_nsn = __shfl_sync(FULL, b.nsn, ns2 - 1, LPC);
+    if (col_ok && snow_lane) {
+      int top = top_old;
+      if (bot_act) { top = nsno - bot_nsn; if (l == 0 && top != top_old) A.snow_top_id[col] = top; }
+      if (va && sa == top && a.act) { a.rhs += (H0 - dH0 * a.T) * area; a.bb += -dH0 * area; }
+      if (sb == top && b.act) { b.rhs += (H0 - dH0 * b.T) * area; b.bb += -dH0 * area; }
     }
   }
-  // ---- standing water <-> top soil cell ----
-  const double T_w = __shfl_sync(FULL, T, l_sw), tk_w = __shfl_sync(FULL, tk, l_sw), frac_w = __shfl_sync(FULL, frac, l_sw);
-  const double mdz_w = __shfl_sync(FULL, mdz, l_sw);
-  const int act_w = __shfl_sync(FULL, act, l_sw);
-  const double T_s1 = __shfl_sync(FULL, T, l_so), tk_s1 = __shfl_sync(FULL, tk, l_so);
-  double cs = 0.0;                                    // ssw row: coefficient of the top soil unknown
-  if (is_ssw && act) {
-    const double H = A.hs[1][col], dH = A.dhsdT[1][col];
-    rhs = rhs + (H - dH * T) * area; bb += -dH * area;                                  // COND_HEAT_FLUX (:1086-1097, :790-803)
-    // coupling: conn dist_up = 0, conn dist_dn = mesh dz / 2 (-> dist), conductivity averaged with aux dz / 2 (:1052-1075)
-    const double dist = 0.5 * sw_dzm, dd = 0.5 * mdz;
-    const double k = tk_s1 * tk * dd * rcp(tk_s1 * dd);
-    const double kod = k * rcp(dist) * area;
-    const double fl = -kod * (T_s1 - T);
-    rhs = rhs - cnfac * fl;
-    const double v = (1.0 - cnfac) * kod;
-    bb += v; cs = -v;
-  }
-  double a1s = 0.0;                                   // top soil row: coefficient of the ssw unknown
-  if (lane == l_so && act) {
-    const double dd_conn = A.soil_top_dist_dn[col];
-    {                                                 // COND_HEAT_FLUX at the top of the soil (soil GE :886-903, :1196-1215)
-      const double H = A.hs[2][col], dH = A.dhsdT[2][col], fr = A.frac_soil[col];
-      rhs = rhs + (H - dH * T) * fr * area;
-      bb += -fr * ((area == 1.0) ? dH : pow(dH, area));
+  // ---- top soil row (first row of the first soil lane): heat-flux condition and the standing-water leaf ----
+  const bool top_lane = col_ok && l == ns2 && va;
+  double w_bb = 1.0, w_rhs = 0.0, w_cs = 0.0;         // standing-water row: diagonal, right-hand side, coefficient of the top soil unknown
+  if (top_lane) {
+    double t_rhs = 0.0, t_bb = 0.0;
+    if (a.act) {                                      // COND_HEAT_FLUX at the top of the soil (soil GE :886-903, :1196-1215)
+      t_rhs = (H2 - dH2 * a.T) * frs * area;
+      t_bb = -frs * ((area == 1.0) ? dH2 : pow(dH2, area));
     }
-    if (nsno > 0 && act_m) {                          // coupling with the bottom snow layer (lane - 1): conn dist_up = its dist_up
-      const double du = adu_m;
-      const double kod = tk_m * tk * rcp(tk_m * dd_conn + tk * du);
-      const double fl = -kod * (T_m - T);
-      rhs = rhs - frac_m * cnfac * fl * A.S.stale_area;               // `area` is stale in this branch of the reference (:843-876)
-      const double v = frac_m * (1.0 - cnfac) * kod * area;
-      bb += v; aa = -v;
+    double a1s = 0.0;
+    if (wact) {
+      // SSW UpdateInternalConn (:554-589) + ThermKSPTempSSWAuxVarCompute
+      const bool thick = wmdz * wfrac * 1.0e3 > THIN_SFCLAYER && wfrac > THIN_SFCLAYER;
+      const double dzm = thick ? ((wmdz > THIN_SFCLAYER) ? wmdz : THIN_SFCLAYER) : THIN_SFCLAYER;
+      double hc = THIN_SFCLAYER;
+      if (dzm * wfrac * 1.0e3 > THIN_SFCLAYER && wfrac > THIN_SFCLAYER) { hc = CPLIQ * DENH2O; hc = (hc > THIN_SFCLAYER) ? hc : THIN_SFCLAYER; }
+      const double cap = hc * (area * dzm) * rcp(dt);
+      w_bb = cap - dH1 * area; w_rhs = cap * wT + (H1 - dH1 * wT) * area;                 // Accum + COND_HEAT_FLUX (:1086-1097, :790-803)
+      {                                               // coupling, ssw side: conn dist_up = 0, dist = mesh dz / 2, averaging with aux dz / 2 (:1052-1075)
+        const double dist = 0.5 * dzm, dd = 0.5 * wmdz;
+        const double k = a.tk * TKWAT * dd * rcp(a.tk * dd);
+        const double kod = k * rcp(dist) * area;
+        const double fl = -kod * (a.T - wT);
+        w_rhs = w_rhs - cnfac * fl;
+        const double v = (1.0 - cnfac) * kod;
+        w_bb += v; w_cs = -v;
+      }
+      if (a.act) {                                    // coupling, soil side (is_bc_sh2o branches): Divergence averages with the soil cell's
+        const double du = 0.5 * wmdz, dd = 0.5 * a.mdz; // aux dz / 2, the operators with the connection's dist_dn
+        const double half = ((du * 2.0 > 1.0e-6) ? du * 2.0 : 1.0e-6) * 0.5;
+        const double k1 = TKWAT * a.tk * (du + dd) * rcp(TKWAT * dd + a.tk * du);
+        const double fl = -k1 * (wT - a.T) * rcp(dd + half);
+        t_rhs -= wfrac * cnfac * fl * A.S.stale_area;
+        const double k2 = TKWAT * a.tk * (du + dd_top) * rcp(TKWAT * dd_top + a.tk * du);
+        const double v = wfrac * (1.0 - cnfac) * k2 * rcp(dd_top + half) * area;
+        t_bb += v; a1s = -v;
+      }
     }
-    if (act_w) {                                      // coupling with the standing water (is_bc_sh2o branches)
-      const double du = 0.5 * mdz_w, dd = 0.5 * mdz;  // Divergence uses aux dz / 2 of the soil cell, the operators the connection's dist_dn
-      const double half = ((du * 2.0 > 1.0e-6) ? du * 2.0 : 1.0e-6) * 0.5;
-      const double k1 = tk_w * tk * (du + dd) * rcp(tk_w * dd + tk * du);
-      const double fl = -k1 * (T_w - T) * rcp(dd + half);
-      rhs = rhs - frac_w * cnfac * fl * A.S.stale_area;
-      const double k2 = tk_w * tk * (du + dd_conn) * rcp(tk_w * dd_conn + tk * du);
-      const double v = frac_w * (1.0 - cnfac) * k2 * rcp(dd_conn + half) * area;
-      bb += v; a1s = -v;
+    // fold the leaf into the top soil row (Schur step; identity when there is no standing water)
+    const double f = a1s * rcp(w_bb);
+    t_bb -= f * w_cs; t_rhs -= f * w_rhs;
+    a.rhs += t_rhs; a.bb += t_bb;
+  }
+  if (a.act) a.rhs += a.src;                          // COND_HEAT_RATE on ALL_CELLS (absorbed solar radiation)
+  if (b.act) b.rhs += b.src;
+
+  // ---- chain solve: second rows eliminated in-lane, first rows by normalised PCR over LPC lanes, second rows back-substituted ----
+  const double rbb = rcp(b.bb);
+  const double bs = b.sub * rbb, bu = b.sup * rbb, bf = b.rhs * rbb;         // x_b = bf - bs x_a(l) - bu x_a(l+1)
+  const double bs_p = __shfl_up_sync(FULL, bs, 1, LPC), bu_p = __shfl_up_sync(FULL, bu, 1, LPC), bf_p = __shfl_up_sync(FULL, bf, 1, LPC);
+  const double sub_a = (l > 0) ? a.sub : 0.0;
+  const double rB = rcp(a.bb - sub_a * bu_p - a.sup * bs);
+  const double al = (-sub_a * bs_p) * rB, ga = (-a.sup * bu) * rB, de = (a.rhs - sub_a * bf_p - a.sup * bf) * rB;
+  const double xa = thermal_pcr_unit<LPC>(al, ga, de);
+  const double xa_n = __shfl_down_sync(FULL, xa, 1, LPC);
+  const double xb = bf - bs * xa - ((l + 1 < LPC) ? bu * xa_n : 0.0);
+  if (col_ok) {
+    if (snow_lane) {
+      if (va) A.T_out[(long long)col * nsno + sa] = xa;
+      A.T_out[(long long)col * nsno + sb] = xb;
+    } else {
+      const long long base = (long long)ncol * (nsno + 1) + (long long)col * nlev;
+      if (va) A.T_out[base + ja] = xa;
+      if (vb) A.T_out[base + jb] = xb;
     }
+    if (top_lane) A.T_out[widx] = (w_rhs - w_cs * xa) * rcp(w_bb);
   }
-  if (act && !is_ssw) rhs = rhs + src;                // COND_HEAT_RATE on ALL_CELLS (absorbed solar radiation)
-  // ---- fold the standing-water leaf into the top soil row ----
-  const double bs = __shfl_sync(FULL, bb, l_sw), ds = __shfl_sync(FULL, rhs, l_sw), cs_b = __shfl_sync(FULL, cs, l_sw);
-  if (lane == l_so) {
-    const double f = a1s * rcp(bs);
-    bb -= f * cs_b; rhs -= f * ds;
-  }
-  // ---- chain solve (the ssw lane and the padding lanes are identity rows) ----
-  const bool chain = lane < l_sw;
-  const double x = thermal_pcr<32>(chain ? aa : 0.0, chain ? bb : 1.0, chain ? cc : 0.0, chain ? rhs : 0.0);
-  const double x1 = __shfl_sync(FULL, x, l_so);
-  if (chain) A.T_out[idx] = x;
-  else if (is_ssw) A.T_out[idx] = (rhs - cs * x1) * rcp(bb);
 }
 
 }  // namespace mpp

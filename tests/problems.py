@@ -371,6 +371,25 @@ def pack_elm_snow_thermal(d):
     return o
 
 
+def tile_snow_thermal(d, o, reps):
+    """Replicate a packed batch `reps` times (bench-sized inputs without the per-column Python packing loop): every segment of the
+    SoE order [snow | ssw | soil] is tiled on its own."""
+    ncol, nlev, nsno = d["ncol"], d["nlev"], d["nlevsno"]
+    D = dict(d); D["ncol"] = ncol * reps
+    for k in ("dz", "dist_up", "dist_dn", "watsat", "csol", "tkmg", "tkdry"):
+        D[k] = np.tile(d[k], (reps, 1))
+    for k in ("area", "lun_type", "soil_top_dist_dn"):
+        D[k] = np.tile(d[k], reps)
+    O = {}
+    a, b = ncol * nsno, ncol * (nsno + 1)
+    for k, v in o.items():
+        if v.size == ncol * (nsno + 1 + nlev):
+            O[k] = np.concatenate([np.tile(v[:a], reps), np.tile(v[a:b], reps), np.tile(v[b:], reps)])
+        else:
+            O[k] = np.tile(v, reps)
+    return D, O
+
+
 def build_elm_snow_thermal(cls, d, **kw):
     ncol, nlev, nsno = d["ncol"], d["nlev"], d["nlevsno"]
     p = cls(ncol, nlev, nsno, **kw)

@@ -31,6 +31,20 @@ elif mode == "th":
     m = float(np.mean(ms[2:]))
     print("th ncol", ncol, "dens", dens, "ms/step", ["%.2f" % x for x in ms], "col-steps/s %.3e" % (ncol / (m * 1e-3)),
           "alg GB/s (1824 B/col) %.0f" % (1824 * ncol / (m * 1e-3) / 1e9), "its mean %.2f nf mean %.2f conv %s" % (st["newton_its"].mean(), st["nfuncs"].mean(), conv))
+elif mode == "snow":
+    base = 4096
+    d0 = PB.elm_snow_thermal_inputs(base, 15, 5)
+    d, o = PB.tile_snow_thermal(d0, PB.pack_elm_snow_thermal(d0), max(1, ncol // base))
+    ncol = d["ncol"]
+    p = PB.build_elm_snow_thermal(mpp_b200.ThermalSnow, d)
+    conv, T = PB.elm_snow_thermal_step(p, o, 1800.0, 1)
+    ms = []
+    for s in range(10):
+        p.step_dt(1800.0, s + 2)
+        ms.append(p.last_step_ms())
+    m = float(np.mean(ms[3:]))
+    print("thermal snow+ssw+soil ncol", ncol, "ms/step", ["%.3f" % x for x in ms], "col-steps/s %.3e" % (ncol / (m * 1e-3)),
+          "alg GB/s (2356 B/col) %.0f" % (2356 * ncol / (m * 1e-3) / 1e9))
 else:
     d = PB.elm_thermal_inputs(ncol, 15)
     p, ids = PB.build_elm_thermal(mpp_b200.Thermal, d)
