@@ -29,6 +29,7 @@
  *   soe%PostStepDT                   SystemOfEquationsVSFMType.F90:926-940      mppgpu_post_step_dt
  *   per-column mass-balance check    MPPVSFMALM_Driver.F90:556-601, 845-863     mppgpu_vsfm_mass_balance
  *   ELM coupling step (set x7, step, get x4)  MPPVSFMALM_Driver.F90:379-705   mppgpu_vsfm_coupled_step
+ *   MPPVSFMALM_Solve (raw ELM arrays, packing, retry loop, unpacking)  MPPVSFMALM_Driver.F90:204-923   mppgpu_vsfm_elm_solve
  *
  * Conventions
  *   - plain pointers and sizes only; every array argument is a HOST pointer owned by the caller
@@ -142,6 +143,39 @@ int  mppgpu_post_step_dt(mppgpu_handle h);
 typedef struct { int ieqn, auxvar_type, var_type, cond_id; double *host; } mppgpu_xfer;
 int  mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, int nin, const mppgpu_xfer *in, int nout, const mppgpu_xfer *out,
                               int nchunks, int *converged, int *converged_reason);
+
+/* ---- MPPVSFMALM_Solve with ELM's raw column arrays (src/driver/alm/MPPVSFMALM_Driver.F90:204-923) -----------------
+ * Everything the host model's driver does around StepDT runs on the device: root-fraction weighting of transpiration over the patches
+ * of a column (:204-240, optional), source/sink packing incl. the drainage distribution below the water table (:325-404),
+ * frac_liq_sat from the ice fraction (:435-450), the retry loop (:628-923; <= 10 StepDT calls: a diverged step continues with the
+ * remaining time and stol = 1e-10, a second divergence sets frac_liq_sat = 1; a converged step whose mass-balance error is >= 1e-5 kg
+ * is redone from soln_prev_clm with rtol or stol tightened tenfold), and unpacking (h2osoi_liq / h2osoi_ice, smp_l [mm], soil
+ * pressure, water-table depth, qcharge = 0), then PostStepDT.  The reference takes the retry decisions per MPI rank; here per column.
+ * Lateral-flux and seepage branches are not part of the 1-D path (no boundary conditions allowed).  All arrays are HOST pointers;
+ * per-cell arrays are cell-ordered (c*nlev + j); `zi` has nlev+1 interfaces per column, zi(c,0) first.  nlev <= 32. */
+typedef struct {
+  /* patch level, optional (npft = 0: rootr_col is an input) -- col%pfti (0-based), col%npfts, pft%active, pft%wtcol, rootr_patch(p,j), qflx_tran_veg_patch */
+  int npft, max_patch_per_col;
+  const int *col_pfti, *col_npfts, *pft_active; const double *pft_wtcol, *rootr_pft, *qflx_tran_veg_pft;
+  /* column level */
+  double *rootr_col;                     /* ncells; input, or output when patches are given */
+  const double *qflx_tran_veg_col, *qflx_infl, *qflx_dew_snow, *qflx_dew_grnd, *qflx_sub_snow, *frac_h2osfc;   /* ncol, [mm/s] */
+  const int *snl;                        /* ncol, minus the number of snow layers */
+  double *qflx_drain, *zwt;              /* ncol, in/out */
+  double *h2osoi_liq, *h2osoi_ice;       /* ncells, in/out [kg/m^2] */
+  double *mflx_snowlyr_col;              /* ncol, in/out (zeroed) */
+  const double *mflx_neg_snow_col;       /* ncol */
+  const double *mflx_drain_perched;      /* ncells */
+  /* outputs */
+  double *smp_l, *soilp_col;             /* ncells: matric potential [mm], soil water pressure [Pa] */
+  double *qcharge;                       /* ncol */
+  double *abs_mass_error;                /* ncol or NULL */
+  int *iter_count, *status;              /* ncol or NULL: StepDT calls used; 1 = accepted, 0 = failed all retries (the reference would endrun) */
+} mppgpu_elm_columns;
+/* static part: interface depths zi (ncol*(nlev+1)), thicknesses dz (ncells, cell-ordered), nlevsoi, clm_varcon's watmin (0.01 mm), and the
+ * ids of the six COND_MASS_RATE sources in the order infiltration, ET, dew, drainage, snow, sublimation (MPPVSFMALM_Initialize.F90:836-858) */
+int  mppgpu_vsfm_elm_set_geometry(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids);
+int  mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, mppgpu_elm_columns *cols, int *nfailed, int *nattempts);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 /* per-column Newton iterations, SNES reason, dt cuts, residual evaluations of the last StepDT (any may be NULL) */

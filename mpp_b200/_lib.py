@@ -17,6 +17,18 @@ class Xfer(C.Structure):
     _fields_ = [("ieqn", C.c_int), ("auxvar_type", C.c_int), ("var_type", C.c_int), ("cond_id", C.c_int), ("host", C.POINTER(C.c_double))]
 
 
+class ElmColumns(C.Structure):
+    """mppgpu_elm_columns (include/mppgpu.h)."""
+    _fields_ = [("npft", C.c_int), ("max_patch_per_col", C.c_int),
+                ("col_pfti", c_ip), ("col_npfts", c_ip), ("pft_active", c_ip), ("pft_wtcol", c_dp), ("rootr_pft", c_dp), ("qflx_tran_veg_pft", c_dp),
+                ("rootr_col", c_dp),
+                ("qflx_tran_veg_col", c_dp), ("qflx_infl", c_dp), ("qflx_dew_snow", c_dp), ("qflx_dew_grnd", c_dp), ("qflx_sub_snow", c_dp), ("frac_h2osfc", c_dp),
+                ("snl", c_ip),
+                ("qflx_drain", c_dp), ("zwt", c_dp), ("h2osoi_liq", c_dp), ("h2osoi_ice", c_dp), ("mflx_snowlyr_col", c_dp),
+                ("mflx_neg_snow_col", c_dp), ("mflx_drain_perched", c_dp),
+                ("smp_l", c_dp), ("soilp_col", c_dp), ("qcharge", c_dp), ("abs_mass_error", c_dp), ("iter_count", c_ip), ("status", c_ip)]
+
+
 _SIGS = {
     "mppgpu_last_error": (C.c_char_p, []),
     "mppgpu_version": (C.c_int, []),
@@ -32,6 +44,8 @@ _SIGS = {
     "mppgpu_thermal_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_int]),
     "mppgpu_thermal_set_cnfac": (C.c_int, [C.c_void_p, C.c_double]),
     "mppgpu_thermal_add_snow_ssw": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "mppgpu_vsfm_elm_set_geometry": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, c_ip]),
+    "mppgpu_vsfm_elm_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(ElmColumns), c_ip, c_ip]),
     "mppgpu_th_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int]),
     "mppgpu_set_tolerances": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
     "mppgpu_set_step_budget": (C.c_int, [C.c_void_p, C.c_int]),

@@ -23,6 +23,7 @@
 #include "vsfm_generic_kernel.cuh"
 #include "thermal_kernels.cuh"
 #include "thermal_snow_kernels.cuh"
+#include "vsfm_elm_kernels.cuh"
 #include "th_kernels.cuh"
 #include "th_kernels2.cuh"
 
@@ -90,6 +91,7 @@ struct mppgpu_soe {
   bool result_pending = false;
   // ---- thermal / TH state lives in their own structs ----
   ThermalState *thermal = nullptr;
+  struct ElmState *elm = nullptr;          // mppgpu_vsfm_elm_solve (vsfm_elm_host.inl)
   THState *th = nullptr;
 };
 
@@ -104,6 +106,7 @@ static int thermal_pre_step_dt(ThermalState *t);
 static int thermal_post_step_dt(ThermalState *t);
 static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt);
 static int thermal_add_snow_ssw(mppgpu_soe *h, ThermalState *t, int nlevsno, const double *soil_top_dist_dn);
+static void elm_destroy(struct ElmState *e);
 static int thermal_set_soils(mppgpu_soe *h, ThermalState *t, const double *watsat, const double *csol, const double *tkmg,
                              const double *tkdry, const int *lun_type, int nlevsoi, int istsoil);
 static int th_create(THState *t, int ncol, int nlev, cudaStream_t s);
@@ -268,6 +271,7 @@ extern "C" int mppgpu_destroy(mppgpu_handle h)
   for (auto *c : h->sss) delete c;
   if (h->thermal) { thermal_destroy(h->thermal); delete h->thermal; }
   if (h->th) { th_destroy(h->th); delete h->th; }
+  if (h->elm) elm_destroy(h->elm);
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -642,7 +646,8 @@ static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 {
   const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
   const bool bc = A.nbc > 0 || A.dr_type != 0;        // the specialisation that carries boundary conditions and the down-regulated sink
-#define MPP_L2(SF) do { if (bc) vsfm_step2_kernel<LPC, SF, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
+#define MPP_L2(SF) do { if (A.retry_mask) vsfm_step2_kernel<LPC, SF, true, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
+                        else if (bc) vsfm_step2_kernel<LPC, SF, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
                         else    vsfm_step2_kernel<LPC, SF, false><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); } while (0)
   if (sf == SATFUNC_VG) MPP_L2(SATFUNC_VG); else if (sf == SATFUNC_BC) MPP_L2(SATFUNC_BC); else MPP_L2(SATFUNC_SBC);
 #undef MPP_L2
@@ -675,6 +680,8 @@ static void vsfm_offset_args(VsfmArgs &A, int nlev, long long col0, int n, long 
   A.stat_its += col0; A.stat_reason += col0; A.stat_cuts += col0; A.stat_nf += col0;
   A.col_mass += col0; A.col_err += col0; A.col_src += col0;
   A.block_partials += block0 * 9;
+  if (A.t_done) A.t_done += col0;
+  if (A.retry_mask) { A.retry_mask += col0; A.dt_col += col0; A.rtol_col += col0; A.stol_col += col0; A.x_redo += c; }
   A.ncol = n;
 }
 
@@ -920,4 +927,5 @@ extern "C" int mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const 
 }
 
 #include "thermal_host.inl"
+#include "vsfm_elm_host.inl"
 #include "th_host.inl"

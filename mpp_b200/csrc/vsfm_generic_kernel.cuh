@@ -341,6 +341,7 @@ vsfm_step_generic_kernel(const VsfmArgs A, const int satfunc)
       for (int k = 0; k < MAX_BC; ++k) if (bcCell[k] >= 0) { A.bc[k].flux[col] = bcFlux[k]; A.bc[k].mass_exc[col] += bcMassExc[k]; bexc += bcMassExc[k]; }
     }
     A.col_err[col] = err; A.col_src[col] = q_col;
+    if (A.t_done) A.t_done[col] = time_done;
   }
   __shared__ double red[9][VSFM_GENERIC_WARPS];
   if (lane == 0) {

@@ -64,6 +64,10 @@ struct VsfmArgs {
   // one optional down-regulated sink (COND_DOWNREG_MASS_RATE_CAMPBELL / _FETCH2, GoveqnRichards...:1900-1927, 2158-2188)
   int dr_type, dr_region; const double *dr_value, *dr_pc, *dr_n;
   long long *prof;         // development aid: per-section cycle counters (nullptr in production)
+  double *t_done;          // optional per-column output: time this StepDT did advance (soe%time, SystemOfEquationsBaseType.F90:511)
+  // RETRY specialisation only (the per-column retry loop of mppgpu_vsfm_elm_solve, MPPVSFMALM_Driver.F90:628-923):
+  const int *retry_mask;   // 0 skip the column, 1 continue from x_in (remaining time), 2 redo from x_redo (soln_prev_clm)
+  const double *dt_col, *rtol_col, *stol_col, *x_redo;
 };
 
 // Down-regulated mass sink: actual rate [kg/s] and the Jacobian diagonal term it adds (GoveqnRichards...:1900-1927, 2158-2188)

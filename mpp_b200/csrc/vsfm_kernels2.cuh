@@ -84,7 +84,8 @@ enum { PI_SATRES, PI_ALPHA, PI_M, PI_N, PI_POR, PI_VOL, PI_SRC, PI_UPW, PI_DQ, P
 template <int SATFUNC> struct ParCount { static constexpr int value = (SATFUNC == SATFUNC_VG) ? 18 : (SATFUNC == SATFUNC_BC ? 19 : 23); };
 
 template <int SATFUNC>
-__device__ __forceinline__ void cell_load(const VsfmArgs &A, Cell2<SATFUNC> &c, double (*par)[VSFM2_THREADS], bool valid, long long cell, double area, double &perm, double &dz)
+__device__ __forceinline__ void cell_load(const VsfmArgs &A, Cell2<SATFUNC> &c, double (*par)[VSFM2_THREADS], bool valid, long long cell, double area, double &perm, double &dz,
+                                          const double *x_src)
 {
   const int t = threadIdx.x;
   c.valid = valid;
@@ -96,7 +97,7 @@ __device__ __forceinline__ void cell_load(const VsfmArgs &A, Cell2<SATFUNC> &c, 
     if (SATFUNC == SATFUNC_VG)  n = A.vgn[cell];
     if (SATFUNC == SATFUNC_SBC) { pu = A.pu[cell]; ps = A.ps[cell]; b2 = A.b2[cell]; b3 = A.b3[cell]; }
     if (SATFUNC != SATFUNC_VG)  fl = A.frac_liq[cell];            // only the Brooks-Corey k_r reads it (SaturationFunction.F90:987)
-    c.X = A.x_in[cell];
+    c.X = x_src[cell];
   }
   par[PI_SATRES][t] = sat_res; par[PI_ALPHA][t] = alpha; par[PI_M][t] = m; par[PI_N][t] = n;
   par[PI_POR][t] = por; par[PI_VOL][t] = area * dz;               // MeshType.F90:427
@@ -159,7 +160,9 @@ __device__ __forceinline__ void rich_flux_deriv(double P_u, double kr_u, double 
 }
 
 // HAS_BC: the batch has boundary conditions and / or a down-regulated sink (compiled out for plain ELM-like batches)
-template <int LPC, int SATFUNC, bool HAS_BC>
+// RETRY: per-column remaining time, tolerances, start vector and a run mask (the retry loop of MPPVSFMALM_Solve); compiled as a
+// separate specialisation so that the common path keeps its register budget
+template <int LPC, int SATFUNC, bool HAS_BC, bool RETRY = false>
 __global__ void __launch_bounds__(VSFM2_THREADS, VSFM2_MIN_BLOCKS)
 vsfm_step2_kernel(const VsfmArgs A)
 {
@@ -172,7 +175,10 @@ vsfm_step2_kernel(const VsfmArgs A)
   const int lane = threadIdx.x & 31;
   const int nlev = A.nlev;
   const int j0 = 2 * l, j1 = 2 * l + 1;
-  const bool col_ok = (col < A.ncol) && (A.active == nullptr || A.active[col] != 0);
+  int rmask = 1;
+  if (RETRY) rmask = (col < A.ncol) ? A.retry_mask[col] : 0;
+  const bool col_ok = (col < A.ncol) && (A.active == nullptr || A.active[col] != 0) && (!RETRY || rmask != 0);
+  const double *x_src = (RETRY && rmask == 2) ? A.x_redo : A.x_in;
   const long long cell0 = (long long)col * nlev + j0;
   const double area = col_ok ? A.area[col] : 1.0;
 
@@ -184,8 +190,8 @@ vsfm_step2_kernel(const VsfmArgs A)
 #define PB(i) pb[i][tx]
   Cell2<SATFUNC> a, b;
   double perm0, dz0, perm1, dz1;
-  cell_load<SATFUNC>(A, a, pa, col_ok && j0 < nlev, cell0, area, perm0, dz0);
-  cell_load<SATFUNC>(A, b, pb, col_ok && j1 < nlev, cell0 + 1, area, perm1, dz1);
+  cell_load<SATFUNC>(A, a, pa, col_ok && j0 < nlev, cell0, area, perm0, dz0, x_src);
+  cell_load<SATFUNC>(A, b, pb, col_ok && j1 < nlev, cell0 + 1, area, perm1, dz1, x_src);
   {
     const double perm_n = __shfl_down_sync(FULL, perm0, 1, LPC), dz_n = __shfl_down_sync(FULL, dz0, 1, LPC);
     a.has_conn = b.valid;                            // 2l -> 2l+1
@@ -255,15 +261,23 @@ vsfm_step2_kernel(const VsfmArgs A)
 
   // ---- time-step / Newton state (uniform per column unless noted) ---------------------------------
   const SnesOpts so = A.so;
-  const double atol2 = so.atol * so.atol, rtol2 = so.rtol * so.rtol, stol2 = so.stol * so.stol;
+  const double atol2 = so.atol * so.atol, rtol2_u = so.rtol * so.rtol, stol2_u = so.stol * so.stol;
   const double divtol2 = so.divtol * so.divtol, maxstep2 = so.ls_maxstep * so.ls_maxstep;
   // per-column scalars that are touched once per sub-step or only while back-tracking live in shared memory as well
-  __shared__ double s_sc[3][VSFM2_THREADS];
+  __shared__ double s_sc[RETRY ? 6 : 3][VSFM2_THREADS];
 #define SC_TDONE   s_sc[0][tx]
 #define SC_LAMPREV s_sc[1][tx]
 #define SC_GPREV   s_sc[2][tx]
   SC_TDONE = 0.0; SC_LAMPREV = 1.0; SC_GPREV = 0.0;
-  double dt_iter = A.dt, dtInv = 1.0 / dt_iter;
+  if (RETRY) {
+    s_sc[RETRY ? 3 : 0][tx] = col_ok ? A.dt_col[col] : A.dt;
+    const double rt = col_ok ? A.rtol_col[col] : so.rtol, st = col_ok ? A.stol_col[col] : so.stol;
+    s_sc[RETRY ? 4 : 0][tx] = rt * rt; s_sc[RETRY ? 5 : 0][tx] = st * st;
+  }
+#define DT_TOT (RETRY ? s_sc[RETRY ? 3 : 0][tx] : A.dt)
+#define rtol2  (RETRY ? s_sc[RETRY ? 4 : 0][tx] : rtol2_u)
+#define stol2  (RETRY ? s_sc[RETRY ? 5 : 0][tx] : stol2_u)
+  double dt_iter = DT_TOT, dtInv = 1.0 / dt_iter;
   int    cuts = 0, tot_its = 0, tot_nf = 0, last_reason = 0, converged = 0;
   int    phase = col_ok ? PH_INIT : PH_DONE;
   int    its = 0, nfuncs = 0, ls_count = 0;
@@ -406,7 +420,7 @@ vsfm_step2_kernel(const VsfmArgs A)
 #pragma unroll
           for (int k = 0; k < NBC; ++k) if (bcOwn[k]) bcMassExc[k] += bcFlux[k] * dt_iter;
         }
-        if (time_done >= A.dt) phase = PH_DONE;
+        if (time_done >= DT_TOT) phase = PH_DONE;
         else { a.W = a.X; b.W = b.X; phase = PH_INIT; }
       }
       its = 0; nfuncs = 0;
@@ -628,6 +642,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       A.col_mass[col] = m_end;
     }
     A.col_err[col] = err; A.col_src[col] = q_col;
+    if (A.t_done) A.t_done[col] = SC_TDONE;
   }
 
   // ---- block partials for the global mass-balance / convergence reductions (deterministic order) ----------
@@ -670,6 +685,9 @@ vsfm_step2_kernel(const VsfmArgs A)
   }
 #undef PA
 #undef PB
+#undef DT_TOT
+#undef rtol2
+#undef stol2
 #undef SC_TDONE
 #undef SC_LAMPREV
 #undef SC_GPREV

@@ -211,6 +211,61 @@ class VSFM(_SoE):
         return bool(conv.value), reason.value
 
 
+    # -- MPPVSFMALM_Solve with ELM's raw column arrays (MPPVSFMALM_Driver.F90:204-923) --------------------------------
+    ELM_COND_ORDER = ("infil", "et", "dew", "drain", "snow", "sublim")
+    ELM_INOUT = ("rootr_col", "qflx_drain", "zwt", "h2osoi_liq", "h2osoi_ice", "mflx_snowlyr_col")
+
+    def elm_set_geometry(self, zi, dz, nlevsoi, ids, watmin=0.01):
+        """zi: (ncol, nlev+1) interface depths, dz: (ncol, nlev) thicknesses (ELM's col%zi(c,0:), col%dz); ids: the condition ids of
+        infiltration, ET, dew, drainage, snow, sublimation (dict as returned by the set-up, or a sequence in that order)."""
+        zi = np.ascontiguousarray(np.asarray(zi, dtype=np.float64).reshape(self.ncol, self.nlev + 1))
+        dz = np.ascontiguousarray(np.asarray(dz, dtype=np.float64).reshape(self.ncol, self.nlev))
+        cid = _i32([ids[k] for k in self.ELM_COND_ORDER] if isinstance(ids, dict) else list(ids))
+        check(self.L.mppgpu_vsfm_elm_set_geometry(self.h, _dp(zi), _dp(dz), int(nlevsoi), float(watmin), _ip(cid)))
+
+    def elm_solve(self, dt, st, nstep=1):
+        """One MPPVSFMALM_Solve.  `st`: dict of ELM's column arrays (float64 / int32, C-contiguous; cell arrays (ncol, nlev)); the in/out
+        ones (ELM_INOUT) are updated in place.  Returns dict(smp_l, soilp_col, qcharge, abs_mass_error, iter_count, status, nfailed, nattempts)."""
+        from ._lib import ElmColumns
+        ncol, n = self.ncol, self.ncells
+        cols = ElmColumns()
+        keep = []
+
+        def dptr(a, size, name):
+            if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"] or a.size != size:
+                raise ValueError("elm_solve: %s must be a C-contiguous float64 array of %d values" % (name, size))
+            keep.append(a)
+            return _dp(a)
+
+        def iptr(a, size, name):
+            if a.dtype != np.int32 or not a.flags["C_CONTIGUOUS"] or a.size != size:
+                raise ValueError("elm_solve: %s must be a C-contiguous int32 array of %d values" % (name, size))
+            keep.append(a)
+            return _ip(a)
+        if st.get("col_pfti") is not None:
+            npft = int(st["pft_wtcol"].size)
+            cols.npft, cols.max_patch_per_col = npft, int(st["max_patch_per_col"])
+            cols.col_pfti, cols.col_npfts = iptr(st["col_pfti"], ncol, "col_pfti"), iptr(st["col_npfts"], ncol, "col_npfts")
+            cols.pft_active, cols.pft_wtcol = iptr(st["pft_active"], npft, "pft_active"), dptr(st["pft_wtcol"], npft, "pft_wtcol")
+            cols.rootr_pft = dptr(st["rootr_pft"], npft * self.nlev, "rootr_pft")
+            cols.qflx_tran_veg_pft = dptr(st["qflx_tran_veg_pft"], npft, "qflx_tran_veg_pft")
+        for k in ("qflx_tran_veg_col", "qflx_infl", "qflx_dew_snow", "qflx_dew_grnd", "qflx_sub_snow", "frac_h2osfc", "qflx_drain", "zwt",
+                  "mflx_snowlyr_col", "mflx_neg_snow_col"):
+            setattr(cols, k, dptr(st[k], ncol, k))
+        for k in ("rootr_col", "h2osoi_liq", "h2osoi_ice", "mflx_drain_perched"):
+            setattr(cols, k, dptr(st[k], n, k))
+        cols.snl = iptr(st["snl"], ncol, "snl")
+        out = {"smp_l": np.zeros(n), "soilp_col": np.zeros(n), "qcharge": np.zeros(ncol), "abs_mass_error": np.zeros(ncol),
+               "iter_count": np.zeros(ncol, dtype=np.int32), "status": np.zeros(ncol, dtype=np.int32)}
+        for k in ("smp_l", "soilp_col", "qcharge", "abs_mass_error"):
+            setattr(cols, k, _dp(out[k]))
+        cols.iter_count, cols.status = _ip(out["iter_count"]), _ip(out["status"])
+        nf, na = C.c_int(), C.c_int()
+        check(self.L.mppgpu_vsfm_elm_solve(self.h, float(dt), int(nstep), C.byref(cols), C.byref(nf), C.byref(na)))
+        out["nfailed"], out["nattempts"] = nf.value, na.value
+        return out
+
+
 class Thermal(_SoE):
     """sysofeqns_thermal_type (soil governing equation, KSP path)."""
     soe_itype = K.SOE_THERMAL_TBASED

@@ -195,6 +195,16 @@ int       orc_vsfm_step_dt(orc_vsfm *p, double dt, int nstep, int *converged, in
  * or the single global values replicated */
 void      orc_vsfm_get_stats(orc_vsfm *p, int *newton_its /*ncol*/, int *reasons /*ncol*/, int *ncuts /*ncol*/, int *nfuncs /*ncol*/);
 /* raw residual / Jacobian at state x (for unit tests of the kernels' pieces) */
+void      orc_vsfm_fill_mailbox(orc_vsfm *p);
+/* MPPVSFMALM_Solve for a batch of independent columns (see vsfm.c); returns 0 or -(number of columns that failed all retries) */
+int       orc_vsfm_elm_solve(orc_vsfm *p, double dtime_full, int nlevsoi, double watmin, const int *cond_ids,
+                             int max_patch_per_col, const int *col_pfti, const int *col_npfts, const int *pft_active, const double *pft_wtcol,
+                             const double *rootr_pft, const double *qflx_tran_veg_pft,
+                             double *rootr_col, const double *qflx_tran_veg_col, const double *qflx_infl, const double *qflx_dew_snow,
+                             const double *qflx_dew_grnd, const double *qflx_sub_snow, const double *frac_h2osfc, const int *snl,
+                             double *qflx_drain, double *zwt, const double *zi, const double *dz, double *h2osoi_liq, double *h2osoi_ice,
+                             double *mflx_snowlyr_col, const double *mflx_neg_snow, const double *mflx_drain_perched,
+                             double *smp_l, double *soilp, double *qcharge, double *abs_mass_error, int *iter_count_out, int *status_out);
 void      orc_vsfm_eval(orc_vsfm *p, double dt, const double *x_prev, const double *x, double *f, double *ja, double *jb, double *jc);
 
 /* Thermal (KSP path) */

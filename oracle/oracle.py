@@ -145,6 +145,7 @@ class OracleVSFM:
         rc = self.L.orc_vsfm_set_soils(self.h, *[dp(x) for x in a], SATFUNC_NAMES[satfunc_type], int(density_type))
         if rc:
             raise ValueError("set_soils rc=%d" % rc)
+        self._soils_set = True
 
     def set_tolerances(self, atol, rtol, stol, max_it, max_funcs):
         self.L.orc_vsfm_set_tolerances(self.h, C.c_double(atol), C.c_double(rtol), C.c_double(stol), int(max_it), int(max_funcs))
@@ -152,7 +153,40 @@ class OracleVSFM:
     def restart(self, press):
         press = f64(press)
         assert press.size == self.ncells
-        return self.L.orc_vsfm_restart(self.h, dp(press))
+        rc = self.L.orc_vsfm_restart(self.h, dp(press))
+        if getattr(self, "_soils_set", False):
+            self.L.orc_vsfm_fill_mailbox(self.h)          # as mppgpu_restart does (ELM's initialisation leaves the mailbox consistent)
+        return rc
+
+    ELM_COND_ORDER = ("infil", "et", "dew", "drain", "snow", "sublim")
+
+    def elm_set_geometry(self, zi, dz, nlevsoi, ids, watmin=0.01):
+        self._zi = np.ascontiguousarray(np.asarray(zi, dtype=np.float64).reshape(self.ncol, self.nlev + 1))
+        self._dz = np.ascontiguousarray(np.asarray(dz, dtype=np.float64).reshape(self.ncol, self.nlev))
+        self._nlevsoi, self._watmin = int(nlevsoi), float(watmin)
+        self._cids = i32([ids[k] for k in self.ELM_COND_ORDER] if isinstance(ids, dict) else list(ids))
+
+    def elm_solve(self, dt, st, nstep=1):
+        ncol, n = self.ncol, self.ncells
+        out = {"smp_l": np.zeros(n), "soilp_col": np.zeros(n), "qcharge": np.zeros(ncol), "abs_mass_error": np.zeros(ncol),
+               "iter_count": np.zeros(ncol, dtype=np.int32), "status": np.zeros(ncol, dtype=np.int32)}
+        pat = st.get("col_pfti") is not None
+        nul_i, nul_d = C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+        self.L.orc_vsfm_elm_solve.restype = C.c_int
+        rc = self.L.orc_vsfm_elm_solve(
+            self.h, C.c_double(dt), C.c_int(self._nlevsoi), C.c_double(self._watmin), ip(self._cids),
+            C.c_int(int(st["max_patch_per_col"]) if pat else 0),
+            ip(st["col_pfti"]) if pat else nul_i, ip(st["col_npfts"]) if pat else nul_i, ip(st["pft_active"]) if pat else nul_i,
+            dp(st["pft_wtcol"]) if pat else nul_d, dp(st["rootr_pft"]) if pat else nul_d, dp(st["qflx_tran_veg_pft"]) if pat else nul_d,
+            dp(st["rootr_col"]), dp(st["qflx_tran_veg_col"]), dp(st["qflx_infl"]), dp(st["qflx_dew_snow"]), dp(st["qflx_dew_grnd"]),
+            dp(st["qflx_sub_snow"]), dp(st["frac_h2osfc"]), ip(st["snl"]), dp(st["qflx_drain"]), dp(st["zwt"]), dp(self._zi), dp(self._dz),
+            dp(st["h2osoi_liq"]), dp(st["h2osoi_ice"]), dp(st["mflx_snowlyr_col"]), dp(st["mflx_neg_snow_col"]), dp(st["mflx_drain_perched"]),
+            dp(out["smp_l"]), dp(out["soilp_col"]), dp(out["qcharge"]), dp(out["abs_mass_error"]), ip(out["iter_count"]), ip(out["status"]))
+        if rc > 0:
+            raise ValueError("orc_vsfm_elm_solve rc=%d" % rc)
+        out["nfailed"] = -rc
+        out["nattempts"] = int(out["iter_count"].max())
+        return out
 
     def set_data(self, auxvar_type, var_type, cond_id, data, ieqn=1):
         data = f64(data)

@@ -249,6 +249,22 @@ int orc_vsfm_restart(orc_vsfm *p, const double *press)
   return 0;
 }
 
+static void update_auxvars(orc_vsfm *p, int c0, int c1, const double *X);
+
+/* Not in VSFMMPPRestart: ELM's initialisation leaves the SoE mailbox (mass, saturation, matric potential, pressure) consistent
+ * with the initial pressures before the first MPPVSFMALM_Solve reads VAR_MASS (:425).  Mirrors mppgpu_restart, which fills it. */
+void orc_vsfm_fill_mailbox(orc_vsfm *p)
+{
+  int ic;
+  update_auxvars(p, 0, p->ncol, p->soln);
+  for (ic = 0; ic < p->ncells; ic++) if (p->is_active[ic]) {
+    const orc_rich_auxvar *a = &p->aux_in[ic];
+    p->soe_liq_sat[ic] = a->sat; p->soe_pressure[ic] = a->pressure;
+    p->soe_mass[ic] = a->por * a->den * ORC_FMWH2O * a->sat * p->vol[ic];
+    p->soe_smp[ic] = (a->pressure - ORC_PRESSURE_REF) / (a->den * ORC_FMWH2O * ORC_GRAVITY_CONSTANT);
+  }
+}
+
 /* VSFMSOESetDataFromCLM, SystemOfEquationsVSFMType.F90:663-724 */
 int orc_vsfm_set_data(orc_vsfm *p, int auxvar_type, int var_type, int cond_id, const double *data, int n)
 {
@@ -581,6 +597,7 @@ static void step_dt_range(orc_vsfm *p, int c0, int c1, double dt, int *converged
     if (time >= target_time) break;
   }
   *ncuts = num_time_cuts;
+  p->time = time;                             /* soe%time: what the failed / finished StepDT did advance (:511) */
   free((void *)sys.col_start); free(x);
 }
 
@@ -666,4 +683,149 @@ void orc_vsfm_eval(orc_vsfm *p, double dt, const double *x_prev, const double *x
   jacobian_range(p, 0, p->ncol, ja, jb, jc);
   memcpy(p->soln_prev, keep, nb);
   free(keep);
+}
+
+
+/* =====================================================================================================================
+ * MPPVSFMALM_Solve (src/driver/alm/MPPVSFMALM_Driver.F90:204-923) for a batch of independent columns: ELM's raw column
+ * arrays in, ELM's raw column arrays out.
+ *   :204-240   root-fraction weighting of transpiration over the patches of a column           (optional: patch arrays)
+ *   :325-372   source/sink packing: ET by root fraction, infiltration, dew, sublimation, drainage distributed over the
+ *              layers below the water table and limited by the liquid water there, snow-layer disappearance
+ *   :435-450   frac_ice / frac_liq_sat
+ *   :552-601   per-column mass and flux totals
+ *   :603-923   PreStepDT, the retry loop (<= 10 StepDT calls: a diverged step continues with the remaining time and
+ *              stol = 1e-10, a second divergence drops the ice impedance; a converged step whose mass-balance error is
+ *              >= 1e-5 kg is redone from the start with rtol or stol tightened tenfold), unpacking (h2osoi_liq/ice, smp_l
+ *              in mm, soil pressure, water-table depth by interpolation of the matric potential), PostStepDT
+ * The reference runs this loop once per MPI rank (global convergence flag, global maximum of the mass error); here every
+ * column is treated as the reference treats a rank holding only that column, in line with the per-column Newton iteration.
+ * Lateral / seepage branches (:452-551, :708-800) are not part of the 1-D path.  Cell arrays are cell-ordered (c*nlev + j),
+ * zi holds nlev+1 interfaces per column (zi(c,0) first).  PARITY UNPINNED (ELM-only code, no baseline).  TEST INFRASTRUCTURE ONLY.
+ * ===================================================================================================================== */
+int orc_vsfm_elm_solve(orc_vsfm *p, double dtime_full, int nlevsoi, double watmin, const int *cond_ids /* infil, et, dew, drainage, snow, sublimation */,
+                       /* optional patch level (NULL: rootr_col is used as given) */
+                       int max_patch_per_col, const int *col_pfti, const int *col_npfts, const int *pft_active, const double *pft_wtcol,
+                       const double *rootr_pft /* (npft, nlev) patch-major */, const double *qflx_tran_veg_pft,
+                       /* column level */
+                       double *rootr_col, const double *qflx_tran_veg_col, const double *qflx_infl, const double *qflx_dew_snow,
+                       const double *qflx_dew_grnd, const double *qflx_sub_snow, const double *frac_h2osfc, const int *snl,
+                       double *qflx_drain, double *zwt, const double *zi, const double *dz, double *h2osoi_liq, double *h2osoi_ice,
+                       double *mflx_snowlyr_col, const double *mflx_neg_snow, const double *mflx_drain_perched,
+                       /* outputs */
+                       double *smp_l, double *soilp, double *qcharge, double *abs_mass_error, int *iter_count_out, int *status_out)
+{
+  const int ncol = p->ncol, nlev = p->nlev, n = p->ncells;
+  const double area = 1.0, conv = area * ORC_DENH2O * 1.0e-3;          /* flux_unit_conversion [mm/s] -> [kg/s] (:330) */
+  const int max_iter_count = 10; const double max_abs_mass_error_col = 1.0e-5, stol_alternate = 1.0e-10;
+  vcond *c_inf = &p->ss[cond_ids[0] - 1], *c_et = &p->ss[cond_ids[1] - 1], *c_dew = &p->ss[cond_ids[2] - 1],
+        *c_drn = &p->ss[cond_ids[3] - 1], *c_snw = &p->ss[cond_ids[4] - 1], *c_sub = &p->ss[cond_ids[5] - 1];
+  double *w = (double *)malloc(sizeof(double) * (size_t)n * 4);
+  int c, nfail = 0;
+  if (!c_et->per_cell || !c_drn->per_cell || c_inf->per_cell || c_dew->per_cell || c_snw->per_cell || c_sub->per_cell) { free(w); return 1; }
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 16) num_threads(p->nthreads) reduction(+:nfail)
+#endif
+  for (c = 0; c < ncol; c++) {
+    orc_vsfm q = *p;                       /* private dtime / time / tolerances; the arrays are shared, this column's slices only */
+    const int off = c * nlev;
+    const double *zic = zi + (size_t)c * (nlev + 1);
+    double frac_ice[256];
+    double tot_et = 0.0, tot_drain = 0.0, mass_beg = 0.0, tot_flux, mass_end, err = 0.0;
+    double dtime = dtime_full, rtol = p->opts.rtol, stol = p->opts.stol;
+    int j, iter_count = 0, diverged_count = 0, ok = 0, conv_flag, reason, its, nf, cuts;
+    /* ---- :204-240 ---- */
+    if (col_pfti) {
+      double temp = 0.0; int pi;
+      for (j = 0; j < nlevsoi; j++) rootr_col[off + j] = 0.0;
+      for (pi = 0; pi < max_patch_per_col; pi++) if (pi < col_npfts[c]) {
+        int pp = col_pfti[c] + pi;
+        if (!pft_active[pp]) continue;
+        for (j = 0; j < nlevsoi; j++) rootr_col[off + j] = rootr_col[off + j] + rootr_pft[(size_t)pp * nlev + j] * qflx_tran_veg_pft[pp] * pft_wtcol[pp];
+        temp = temp + qflx_tran_veg_pft[pp] * pft_wtcol[pp];
+      }
+      if (temp != 0.0) for (j = 0; j < nlevsoi; j++) rootr_col[off + j] = rootr_col[off + j] / temp;
+    }
+    /* ---- :325-372 ---- */
+    for (j = 0; j < nlev; j++) { c_et->soe_value[off + j] = 0.0; c_drn->soe_value[off + j] = 0.0; }
+    for (j = 0; j < nlevsoi; j++) c_et->soe_value[off + j] = -qflx_tran_veg_col[c] * rootr_col[off + j] * conv;
+    c_inf->soe_value[c] = qflx_infl[c] * conv;
+    c_dew->soe_value[c] = 0.0; c_sub->soe_value[c] = 0.0;
+    if (snl[c] >= 0) {
+      c_dew->soe_value[c] = (qflx_dew_snow[c] + qflx_dew_grnd[c]) * (1.0 - frac_h2osfc[c]) * conv;
+      c_sub->soe_value[c] = -qflx_sub_snow[c] * (1.0 - frac_h2osfc[c]) * conv;
+    }
+    if (qflx_drain[c] > 0.0) {
+      int jwt = nlev; double dzsum = 0.0, tot = 0.0;          /* 1-based layer numbers as in the reference */
+      for (j = 1; j <= nlev; j++) if (zwt[c] <= zic[j]) { jwt = j - 1; break; }
+      if (jwt < 1) jwt = 1;
+      for (j = jwt; j <= nlev; j++) dzsum = dzsum + dz[off + j - 1];
+      for (j = jwt; j <= nlev; j++) {
+        double ql = qflx_drain[c] * dz[off + j - 1] / dzsum;
+        if (ql * dtime_full > (h2osoi_liq[off + j - 1] - watmin)) ql = (h2osoi_liq[off + j - 1] - watmin) / dtime_full;
+        tot = tot + ql;
+        c_drn->soe_value[off + j - 1] = -ql * conv;
+      }
+      qflx_drain[c] = tot;
+    }
+    c_snw->soe_value[c] = mflx_snowlyr_col[c] * area + mflx_neg_snow[c] * area;
+    mflx_snowlyr_col[c] = 0.0;
+    for (j = 0; j < nlev; j++) c_drn->soe_value[off + j] = c_drn->soe_value[off + j] + mflx_drain_perched[off + j];     /* :404 */
+    /* ---- :435-450 ---- */
+    for (j = 0; j < nlev; j++) {
+      frac_ice[j] = h2osoi_ice[off + j] / (h2osoi_liq[off + j] + h2osoi_ice[off + j]);
+      p->soe_frac_liq_sat[off + j] = 1.0 - frac_ice[j];
+    }
+    /* ---- :552-601 ---- */
+    for (j = 0; j < nlev; j++) {
+      tot_et = tot_et + c_et->soe_value[off + j]; tot_drain = tot_drain + c_drn->soe_value[off + j];
+      mass_beg = mass_beg + p->soe_mass[off + j];
+    }
+    tot_flux = tot_et + c_inf->soe_value[c] + c_dew->soe_value[c] + tot_drain + c_snw->soe_value[c] + c_sub->soe_value[c] + 0.0;
+    /* ---- PreStepDT (:603) ---- */
+    for (j = 0; j < nlev; j++) { p->soln_prev[off + j] = p->soln_prev_clm[off + j]; p->soln[off + j] = p->soln_prev_clm[off + j]; }
+    /* ---- retry loop (:628-923) ---- */
+    for (;;) {
+      iter_count++;
+      q.opts.rtol = rtol; q.opts.stol = stol;
+      step_dt_range(&q, c, c + 1, dtime, &conv_flag, &reason, w, w + n, w + 2 * n, w + 3 * n, &its, &nf, &cuts);
+      p->stat_its[c] = its; p->stat_reason[c] = reason; p->stat_cuts[c] = cuts; p->stat_nf[c] = nf;
+      if (!conv_flag) {
+        stol = stol_alternate; diverged_count++;
+        dtime = dtime - q.time;
+        if (diverged_count > 1) for (j = 0; j < nlev; j++) p->soe_frac_liq_sat[off + j] = 1.0;
+      } else {
+        int jwt = -1;
+        mass_end = 0.0;
+        for (j = nlev; j >= 1; j--) {
+          const int ic = off + j - 1;
+          h2osoi_liq[ic] = (1.0 - frac_ice[j - 1]) * p->soe_mass[ic] / area;
+          h2osoi_ice[ic] = frac_ice[j - 1] * p->soe_mass[ic] / area;
+          mass_end = mass_end + p->soe_mass[ic];
+          smp_l[ic] = p->soe_smp[ic] * 1000.0;
+          if (jwt == -1) { if (smp_l[ic] < 0.0) jwt = j; }
+        }
+        err = fabs(mass_beg - mass_end + tot_flux * dtime_full);
+        qcharge[c] = 0.0;
+        if (jwt == -1 || jwt == nlev) zwt[c] = zic[nlev];
+        else {
+          double z_dn = (zic[jwt - 1] + zic[jwt]) / 2.0, z_up = (zic[jwt] + zic[jwt + 1]) / 2.0;
+          zwt[c] = (0.0 - smp_l[off + jwt - 1]) / (smp_l[off + jwt - 1] - smp_l[off + jwt]) * (z_dn - z_up) + z_dn;
+        }
+        for (j = 0; j < nlev; j++) soilp[off + j] = p->soe_pressure[off + j];
+        if (err >= max_abs_mass_error_col) {
+          if (reason == 3) rtol = rtol / 10.0; else if (reason == 4) stol = stol / 10.0;
+          dtime = dtime_full;
+          for (j = 0; j < nlev; j++) { p->soln_prev[off + j] = p->soln_prev_clm[off + j]; p->soln[off + j] = p->soln_prev_clm[off + j]; }   /* PreStepDT */
+        } else ok = 1;
+      }
+      if (ok) break;
+      if (iter_count >= max_iter_count) break;         /* the reference calls endrun here */
+    }
+    for (j = 0; j < nlev; j++) p->soln_prev_clm[off + j] = p->soln_prev[off + j];     /* PostStepDT (:935) */
+    abs_mass_error[c] = err; iter_count_out[c] = iter_count; status_out[c] = ok;
+    if (!ok) nfail++;
+  }
+  free(w);
+  return nfail ? -nfail : 0;
 }

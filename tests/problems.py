@@ -157,6 +157,49 @@ def elm_vsfm_step(p, ids, d, dt=1800.0, nstep=1, scale=1.0):
     return conv, reason, out
 
 
+def elm_vsfm_raw_state(p, d, seed=SEED, patches=True, nlevsoi=10, drain_frac=0.7):
+    """ELM's raw column arrays for MPPVSFMALM_Solve (MPPVSFMALM_Driver.F90:110-200), consistent with the state of `p` (h2osoi_liq +
+    h2osoi_ice = the SoE's liquid mass, as ELM keeps them after every solve).  Cell arrays are (ncol, nlev), C order."""
+    ncol, nlev = d["ncol"], d["nlev"]
+    rng = np.random.default_rng(seed + 23)
+    z, zi, dz = elm_layers(nlev)
+    st = {"zi": np.tile(zi, (ncol, 1)), "dz": np.tile(dz, (ncol, 1)), "nlevsoi": nlevsoi}
+    mass = p.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1).reshape(ncol, nlev)
+    fi = np.where(rng.uniform(size=(ncol, nlev)) < 0.2, rng.uniform(0.0, 0.6, (ncol, nlev)), 0.0)
+    st["h2osoi_liq"] = np.ascontiguousarray((1.0 - fi) * mass); st["h2osoi_ice"] = np.ascontiguousarray(fi * mass)
+    w = np.exp(-z[:nlevsoi] * rng.uniform(0.5, 3.0, (ncol, 1))); w /= w.sum(axis=1, keepdims=True)
+    rootr = np.zeros((ncol, nlev)); rootr[:, :nlevsoi] = w
+    st["rootr_col"] = rootr
+    st["qflx_tran_veg_col"] = rng.uniform(0.0, 8e-5, ncol)
+    if patches:
+        npf = rng.integers(1, 4, ncol).astype(np.int32)
+        st["col_npfts"] = npf; st["col_pfti"] = np.concatenate([[0], np.cumsum(npf)[:-1]]).astype(np.int32)
+        npft = int(npf.sum()); st["max_patch_per_col"] = 3
+        st["pft_active"] = (rng.uniform(size=npft) < 0.9).astype(np.int32)
+        wt = rng.uniform(0.1, 1.0, npft)
+        owner = np.repeat(np.arange(ncol), npf)
+        wt /= np.bincount(owner, wt, ncol)[owner]
+        st["pft_wtcol"] = wt
+        rp = np.zeros((npft, nlev)); wp = np.exp(-z[:nlevsoi] * rng.uniform(0.5, 3.0, (npft, 1))); rp[:, :nlevsoi] = wp / wp.sum(axis=1, keepdims=True)
+        st["rootr_pft"] = rp
+        st["qflx_tran_veg_pft"] = rng.uniform(0.0, 1.2e-4, npft)
+        st["qflx_tran_veg_col"] = np.bincount(owner, st["qflx_tran_veg_pft"] * wt * st["pft_active"], ncol)
+    st["qflx_infl"] = rng.uniform(0.0, 2e-4, ncol)
+    st["qflx_dew_snow"] = rng.uniform(0.0, 1e-6, ncol); st["qflx_dew_grnd"] = rng.uniform(0.0, 2e-6, ncol); st["qflx_sub_snow"] = rng.uniform(0.0, 1e-6, ncol)
+    st["frac_h2osfc"] = np.where(rng.uniform(size=ncol) < 0.5, rng.uniform(0.0, 0.3, ncol), 0.0)
+    st["snl"] = -rng.integers(0, 3, ncol).astype(np.int32)
+    st["qflx_drain"] = np.where(rng.uniform(size=ncol) < drain_frac, rng.uniform(0.0, 5e-5, ncol), 0.0)
+    st["zwt"] = rng.uniform(0.3, 40.0, ncol)
+    st["mflx_snowlyr_col"] = np.where(rng.uniform(size=ncol) < 0.1, rng.uniform(0.0, 1e-5, ncol), 0.0)
+    st["mflx_neg_snow_col"] = np.where(rng.uniform(size=ncol) < 0.05, -rng.uniform(0.0, 1e-6, ncol), 0.0)
+    st["mflx_drain_perched"] = np.where(rng.uniform(size=(ncol, nlev)) < 0.05, -rng.uniform(0.0, 1e-6, (ncol, nlev)), 0.0)
+    return st
+
+
+def copy_state(st):
+    return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in st.items()}
+
+
 # ---------------------------------------------------------------------------------------------------
 # thermal_mms (1-D steady state, KSP path) -- src/driver/standalone/thermal/thermal_mms_problem.F90
 #   + thermal_mms_steady_state_problem_1D.F90; baseline regression_tests/thermal/thermal_mms.regression.baseline

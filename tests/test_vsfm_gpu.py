@@ -390,3 +390,141 @@ def test_down_regulated_sinks_match_oracle(mpp, oracle, cond_type, nlev):
     err = np.zeros(ncol, dtype=np.float64)
     sums, maxs = p.mass_balance()
     assert np.isfinite(maxs[0])
+
+
+# ---- MPPVSFMALM_Solve with ELM's raw column arrays (MPPVSFMALM_Driver.F90:204-923) ------------------------------
+def _elm_compare(st_g, st_o, og, oo, sel, tol=RTOL):
+    """In/out ELM arrays and outputs of the columns `sel` (boolean mask)."""
+    for k in ("h2osoi_liq", "h2osoi_ice", "rootr_col"):
+        a, b = st_g[k][sel], st_o[k][sel]
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-3)) < tol, k
+    for k in ("qflx_drain", "zwt", "mflx_snowlyr_col"):
+        a, b = st_g[k][sel], st_o[k][sel]
+        assert np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-6)) < 100 * tol, k        # zwt interpolates a difference of potentials
+    ncol = sel.size
+    a, b = og["soilp_col"].reshape(ncol, -1)[sel], oo["soilp_col"].reshape(ncol, -1)[sel]
+    # Saturated cells that receive a source (drainage below the water table) hold their water by compressibility alone
+    # (dF/dP ~ 5e-12 kmol/s/Pa): the liquid MASS above agrees to `tol`, the pressure that carries it only to ~1e-6 Pa.
+    sat = b > K.PRESSURE_REF
+    dev = np.abs(a - b) / np.maximum(np.abs(b), np.abs(b - K.PRESSURE_REF))
+    i = np.unravel_index(np.argmax(np.where(sat, 0.0, dev)), dev.shape)
+    assert dev[i] < tol, ("unsaturated pressure", i, a[i], b[i])
+    if sat.any():
+        assert np.max(dev[sat]) < max(tol, 1e-8), "saturated pressure"
+    a, b = og["smp_l"].reshape(ncol, -1)[sel], oo["smp_l"].reshape(ncol, -1)[sel]
+    a, b = np.where(sat, 0.0, a), np.where(sat, 0.0, b)
+    # [mm]; same scale as relmax_p: smp = (P - P_ref) / (rho g), and P_ref / (rho g) is about 1.03e4 mm
+    assert np.max(np.abs(a - b) / np.maximum(np.maximum(np.abs(b), np.abs(b + 1.03e4)), 1e4)) < tol
+    assert np.all(og["qcharge"] == 0.0)
+
+
+@pytest.mark.parametrize("patches", [True, False])
+def test_elm_solve_raw_arrays_match_oracle(mpp, oracle, patches):
+    ncol = 600
+    d = PB.elm_vsfm_inputs(ncol)
+    g, gids = PB.build_elm_vsfm(mpp.VSFM, d)
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
+    st_g = PB.elm_vsfm_raw_state(g, d, patches=patches)
+    st_o = PB.copy_state(st_g)
+    g.elm_set_geometry(st_g["zi"], st_g["dz"], st_g["nlevsoi"], gids)
+    o.elm_set_geometry(st_o["zi"], st_o["dz"], st_o["nlevsoi"], oids)
+    rng = np.random.default_rng(5)
+    for step in range(3):
+        og, oo = g.elm_solve(1800.0, st_g, step + 1), o.elm_solve(1800.0, st_o, step + 1)
+        same = (og["iter_count"] == oo["iter_count"]) & (og["status"] == oo["status"])
+        assert same.mean() > 0.99
+        easy = same & (oo["status"] == 1) & (oo["iter_count"] == 1) & (o.stats()["dt_cuts"] == 0)
+        assert easy.mean() > 0.9
+        # 1e-10 for the first solve from identical states; afterwards each side advances its OWN state, so the round-off of
+        # earlier steps rides along (seen: 1.2e-10 in one top cell at step 3)
+        _elm_compare(st_g, st_o, og, oo, easy, tol=RTOL if step == 0 else 10 * RTOL)
+        assert np.all(st_g["mflx_snowlyr_col"] == 0.0)
+        assert np.max(og["abs_mass_error"][og["status"] == 1]) < 1e-5
+        # the drainage actually withdrawn never exceeds what was asked for
+        # next step: ELM carries its state on; the GPU side continues from ITS OWN arrays only where both agree
+        for s_ in (st_g, st_o):
+            s_["qflx_infl"] = s_["qflx_infl"] * 0.8
+        fresh = rng.uniform(0.0, 5e-5, ncol)
+        st_g["qflx_drain"] = fresh.copy(); st_o["qflx_drain"] = fresh.copy()
+
+
+def test_elm_solve_tightens_tolerances_on_mass_balance_error(mpp, oracle):
+    """Loose SNES rtol: the first StepDT converges with a mass-balance error >= 1e-5 kg; MPPVSFMALM_Solve (:880-897) redoes the
+    step with rtol / 10 (or stol / 10) until the balance closes."""
+    ncol = 200
+    d = PB.elm_vsfm_inputs(ncol)
+    g, gids = PB.build_elm_vsfm(mpp.VSFM, d)
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
+    for s in (g, o):
+        s.set_tolerances(1e-50, 1e-2, 1e-10, 50, 10000)
+    st_g = PB.elm_vsfm_raw_state(g, d, patches=False)
+    st_o = PB.copy_state(st_g)
+    g.elm_set_geometry(st_g["zi"], st_g["dz"], st_g["nlevsoi"], gids)
+    o.elm_set_geometry(st_o["zi"], st_o["dz"], st_o["nlevsoi"], oids)
+    og, oo = g.elm_solve(1800.0, st_g), o.elm_solve(1800.0, st_o)
+    assert oo["iter_count"].max() >= 3 and og["nattempts"] == og["iter_count"].max()
+    same = (og["iter_count"] == oo["iter_count"]) & (og["status"] == oo["status"])
+    assert same.mean() > 0.95
+    ok = same & (oo["status"] == 1)
+    assert np.max(og["abs_mass_error"][og["status"] == 1]) < 1e-5
+    # a redone column was re-solved to a tolerance 10^k tighter: what is left is its own convergence error, not round-off
+    _elm_compare(st_g, st_o, og, oo, ok, tol=1e-6)
+    one = ok & (oo["iter_count"] == 1)
+    if one.any():
+        _elm_compare(st_g, st_o, og, oo, one)
+
+
+def test_elm_solve_continues_diverged_columns(mpp, oracle):
+    """Hard columns (tests/golden/hard_columns.json): a StepDT that runs out of dt cuts leaves the column part-way through the step;
+    the driver (:645-660) continues with the remaining time and stol = 1e-10, drops the ice impedance after a second failure, and
+    gives up after 10 calls.  Control flow must match the oracle's column for column."""
+    d = _hard_columns_inputs()
+    ncol = d["ncol"]
+    g, gids = PB.build_elm_vsfm(mpp.VSFM, d)
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
+    st_g = PB.elm_vsfm_raw_state(g, d, patches=False, drain_frac=0.0)
+    # reproduce the fixture's forcing through the raw arrays: infiltration and ET as the packed sources had them
+    st_g["qflx_infl"] = d["infil"].copy()                       # conv = 1 kg/s per mm/s
+    et = d["et"].reshape(ncol, -1)
+    tot = -et.sum(axis=1)
+    st_g["qflx_tran_veg_col"] = tot.copy()
+    st_g["rootr_col"] = np.where(tot[:, None] > 0, -et / np.where(tot > 0, tot, 1.0)[:, None], 0.0)
+    for k in ("qflx_dew_snow", "qflx_dew_grnd", "qflx_sub_snow", "mflx_snowlyr_col", "mflx_neg_snow_col"):
+        st_g[k] = np.zeros(ncol)
+    st_g["mflx_drain_perched"] = np.zeros_like(st_g["mflx_drain_perched"])
+    st_g["h2osoi_ice"] = np.zeros_like(st_g["h2osoi_ice"]); st_g["h2osoi_liq"] = g.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1).reshape(ncol, -1).copy()
+    st_o = PB.copy_state(st_g)
+    g.elm_set_geometry(st_g["zi"], st_g["dz"], 15, gids)
+    o.elm_set_geometry(st_o["zi"], st_o["dz"], 15, oids)
+    seen_retry = False
+    for step in range(2):
+        og, oo = g.elm_solve(1800.0, st_g, step + 1), o.elm_solve(1800.0, st_o, step + 1)
+        assert np.array_equal(og["status"], oo["status"])
+        assert np.all(np.abs(og["iter_count"] - oo["iter_count"]) <= 1)
+        assert og["nfailed"] == oo["nfailed"]
+        seen_retry |= bool(oo["iter_count"].max() > 1)
+        easy = (oo["status"] == 1) & (oo["iter_count"] == 1) & (og["iter_count"] == 1) & (o.stats()["dt_cuts"] == 0)
+        if easy.any():
+            _elm_compare(st_g, st_o, og, oo, easy)
+        # failed / sub-stepped columns may differ in the last digits: hand both sides the oracle's state for the next step
+        for k in ("h2osoi_liq", "h2osoi_ice", "zwt", "qflx_drain"):
+            st_g[k] = st_o[k].copy()
+    assert seen_retry, "fixture no longer exercises the retry path"
+
+
+def test_elm_solve_error_behaviour(mpp):
+    d = PB.elm_vsfm_inputs(8)
+    g, gids = PB.build_elm_vsfm(mpp.VSFM, d)
+    st = PB.elm_vsfm_raw_state(g, d, patches=False)
+    with pytest.raises(mpp.MPPError):
+        g.elm_solve(1800.0, st)                                   # geometry not set
+    with pytest.raises(mpp.MPPError):
+        g.elm_set_geometry(st["zi"], st["dz"], 10, [gids["et"], gids["infil"], gids["dew"], gids["drain"], gids["snow"], gids["sublim"]])   # wrong regions
+    g.elm_set_geometry(st["zi"], st["dz"], 10, gids)
+    with pytest.raises(mpp.MPPError):
+        g.elm_solve(-1.0, st)
+    with pytest.raises(ValueError):
+        bad = dict(st); bad["zwt"] = st["zwt"][:4].copy()
+        g.elm_solve(1800.0, bad)
+    out = g.elm_solve(1800.0, st)
+    assert out["nfailed"] == 0 and out["nattempts"] >= 1
