@@ -11,7 +11,7 @@ struct ElmState {
   DevBuf<int> snl;
   DevBuf<int> pfti, npfts, pactive; DevBuf<double> wtcol, rootr_pft, qtran_pft;         // optional patch level
   DevBuf<double> frac_ice, mass_beg, tot_flux, dt_rem, rtol, stol, t_done, smp_l, soilp, qcharge, abs_err;
-  DevBuf<int> iter_count, diverged, mask, status, pending;
+  DevBuf<int> iter_count, diverged, mask, status, pending, retry_list;
 };
 
 static void elm_destroy(ElmState *e) { delete e; }
@@ -48,7 +48,7 @@ extern "C" int mppgpu_vsfm_elm_set_geometry(mppgpu_handle h, const double *zi, c
   DevBuf<double> *colb[] = {&e->qtran, &e->qinfl, &e->dews, &e->dewg, &e->subs, &e->fh2osfc, &e->qdrain, &e->zwt, &e->snowlyr, &e->negsnow,
                             &e->mass_beg, &e->tot_flux, &e->dt_rem, &e->rtol, &e->stol, &e->t_done, &e->qcharge, &e->abs_err};
   for (auto b : colb) CK(b->alloc(ncol));
-  DevBuf<int> *coli[] = {&e->snl, &e->iter_count, &e->diverged, &e->mask, &e->status};
+  DevBuf<int> *coli[] = {&e->snl, &e->iter_count, &e->diverged, &e->mask, &e->status, &e->retry_list};
   for (auto b : coli) CK(b->alloc(ncol));
   CK(e->pending.alloc(1));
   CK(cudaStreamSynchronize(h->stream));
@@ -108,11 +108,11 @@ extern "C" int mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, m
   E.frac_liq = h->frac_liq.p; E.soe_mass = h->mass.p; E.soe_smp = h->smp.p; E.soe_pressure = h->pressure.p;
   E.frac_ice = e->frac_ice.p; E.mass_beg = e->mass_beg.p; E.tot_flux = e->tot_flux.p; E.dt_rem = e->dt_rem.p; E.rtol = e->rtol.p; E.stol = e->stol.p;
   E.t_done = e->t_done.p; E.iter_count = e->iter_count.p; E.diverged = e->diverged.p; E.mask = e->mask.p; E.status = e->status.p;
-  E.stat_reason = h->stat_reason.p; E.pending = e->pending.p;
+  E.stat_reason = h->stat_reason.p; E.pending = e->pending.p; E.retry_list = e->retry_list.p;
   E.smp_l = e->smp_l.p; E.soilp = e->soilp.p; E.qcharge = e->qcharge.p; E.abs_err = e->abs_err.p;
 
   CK(cudaEventRecord(h->ev0, s));
-  elm_pack_kernel<<<nblk(ncol, 128), 128, 0, s>>>(E);
+  if (h->nlev <= 16) elm_pack_kernel<16><<<nblk(ncol * 16, 128), 128, 0, s>>>(E); else elm_pack_kernel<32><<<nblk(ncol * 32, 128), 128, 0, s>>>(E);
   CK(cudaGetLastError());
   h->launches += 1;
   // ---- PreStepDT (:603) ----
@@ -133,12 +133,20 @@ extern "C" int mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, m
       // retries: only the columns the decision kernel marked, each with its own remaining time / tolerances / start vector, in place
       A.retry_mask = e->mask.p; A.dt_col = e->dt_rem.p; A.rtol_col = e->rtol.p; A.stol_col = e->stol.p; A.x_redo = h->x_committed;
       A.x_in = h->x_current; A.x_out = h->x_current;
+      A.retry_list = e->retry_list.p; A.nretry = pending;
     }
-    if (vsfm_launch_range(h, A, 0, h->ncol, 0, s)) return 1;
+    if (attempts == 0) { if (vsfm_launch_range(h, A, 0, h->ncol, 0, s)) return 1; }
+    else {
+      // sized by the columns that need it: a handful of warps, not a pass over the whole batch
+      if (h->nlev <= 16) launch_vsfm2<8>(h, A, nblk((long long)pending * 8, VSFM2_THREADS));
+      else               launch_vsfm2<16>(h, A, nblk((long long)pending * 16, VSFM2_THREADS));
+      CK(cudaGetLastError());
+      h->launches += 1;
+    }
     h->x_current = A.x_out;
     attempts++;
     CK(cudaMemsetAsync(e->pending.p, 0, sizeof(int), s));
-    elm_decide_kernel<<<nblk(ncol, 128), 128, 0, s>>>(E);
+    if (h->nlev <= 16) elm_decide_kernel<16><<<nblk(ncol * 16, 128), 128, 0, s>>>(E); else elm_decide_kernel<32><<<nblk(ncol * 32, 128), 128, 0, s>>>(E);
     CK(cudaGetLastError());
     h->launches += 1;
     CK(cudaMemcpyAsync(&pending, e->pending.p, sizeof(int), cudaMemcpyDeviceToHost, s));

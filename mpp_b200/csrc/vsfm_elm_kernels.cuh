@@ -14,10 +14,10 @@
 //                               mass-balance error is >= 1e-5 kg, redone from soln_prev_clm with rtol or stol tightened
 //                               tenfold according to the convergence reason; at most 10 StepDT calls
 // The reference takes these decisions once per MPI rank (global convergence flag, global maximum of the mass error); here each
-// column is its own "rank", consistent with the per-column Newton iteration of the step kernel.  One thread per column: the
-// drainage distribution and the water-table search are sequential in the layer index, and the arrays are cell-ordered, so a
-// warp's accesses to one layer are 8*nlev bytes apart -- every sector is still used in full over the layer loop (L1), i.e.
-// DRAM traffic stays at the algorithmic bytes; these kernels are a few percent of the step.
+// column is its own "rank", consistent with the per-column Newton iteration of the step kernel.  One lane per cell, G lanes per
+// column (every cell array is streamed once, coalesced); the parts that are sequential in the layer index -- the water-table
+// search, the thickness sum and the running drainage total, the column totals -- are evaluated redundantly by all lanes of a column
+// from shuffled values, in the reference's summation order, so the packed sources are bit-identical to a sequential evaluation.
 #pragma once
 #include <cuda_runtime.h>
 #include "physics.cuh"
@@ -42,132 +42,160 @@ struct ElmArgs {
   double *frac_ice, *mass_beg, *tot_flux, *dt_rem, *rtol, *stol; const double *t_done;
   int *iter_count, *diverged, *mask, *status; const int *stat_reason;
   int *pending;                            // number of columns that need another StepDT
+  int *retry_list;                         // ... and which ones (compacted, any order)
   // outputs
   double *smp_l, *soilp, *qcharge, *abs_err;
 };
 
+template <int G>
 __global__ void elm_pack_kernel(const ElmArgs A)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= A.ncol) return;
+  constexpr unsigned FULL = 0xffffffffu;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)(tid / G), j = (int)(tid % G);                    // lane j owns layer j + 1 of the reference
   const int nlev = A.nlev, nlevsoi = A.nlevsoi;
-  const long long off = (long long)c * nlev;
-  const bool on = (A.active == nullptr) || A.active[c] != 0;
-  A.iter_count[c] = 0; A.diverged[c] = 0; A.status[c] = 0; A.mask[c] = on ? 1 : 0;
-  A.rtol[c] = A.rtol0; A.stol[c] = A.stol0; A.dt_rem[c] = A.dtime; A.abs_err[c] = 0.0;
-  if (!on) return;
+  const bool col_ok = c < A.ncol;
+  const bool on = col_ok && ((A.active == nullptr) || A.active[c] != 0);
+  const bool cell = on && j < nlev;
+  const long long ic = (long long)c * nlev + j;
+  if (col_ok && j == 0) {
+    A.iter_count[c] = 0; A.diverged[c] = 0; A.status[c] = 0; A.mask[c] = on ? 1 : 0;
+    A.rtol[c] = A.rtol0; A.stol[c] = A.stol0; A.dt_rem[c] = A.dtime; A.abs_err[c] = 0.0;
+  }
   const double area = 1.0, conv = area * DENH2O * 1.0e-3;              // flux_unit_conversion [mm/s] -> [kg/s] (:330)
-  if (A.col_pfti) {                                                     // :204-240
-    double temp = 0.0;
-    for (int j = 0; j < nlevsoi; ++j) A.rootr_col[off + j] = 0.0;
+  // ---- loads ----
+  double rootr = 0.0, dz = 0.0, liq = 1.0, ice = 0.0, perched = 0.0, mass = 0.0, zi_j = 0.0;
+  double qtran = 0.0, qinfl = 0.0, dews = 0.0, dewg = 0.0, subs = 0.0, fh = 0.0, qd = 0.0, zw = 0.0, snowl = 0.0, negs = 0.0;
+  int snl = -1;
+  if (cell) {
+    rootr = A.rootr_col[ic]; dz = A.dz[ic]; liq = A.h2osoi_liq[ic]; ice = A.h2osoi_ice[ic]; perched = A.mflx_drain_perched[ic]; mass = A.soe_mass[ic];
+    zi_j = A.zi[(long long)c * (nlev + 1) + j + 1];                    // zi(c, j+1): interface below this layer
+  }
+  if (on) {
+    qtran = A.qflx_tran_veg_col[c]; qinfl = A.qflx_infl[c]; dews = A.qflx_dew_snow[c]; dewg = A.qflx_dew_grnd[c]; subs = A.qflx_sub_snow[c];
+    fh = A.frac_h2osfc[c]; qd = A.qflx_drain[c]; zw = A.zwt[c]; snowl = A.mflx_snowlyr_col[c]; negs = A.mflx_neg_snow[c]; snl = A.snl[c];
+  }
+  // ---- :204-240 root-fraction weighting over the patches of the column ----
+  if (A.col_pfti && on) {
     const int np = A.col_npfts[c], p0 = A.col_pfti[c];
+    double r = 0.0, temp = 0.0;
     for (int pi = 0; pi < A.max_patch_per_col; ++pi) if (pi < np) {
       const int pp = p0 + pi;
       if (!A.pft_active[pp]) continue;
       const double q = A.qflx_tran_veg_pft[pp], wt = A.pft_wtcol[pp];
-      for (int j = 0; j < nlevsoi; ++j) A.rootr_col[off + j] = A.rootr_col[off + j] + A.rootr_pft[(long long)pp * nlev + j] * q * wt;
+      if (cell && j < nlevsoi) r = r + A.rootr_pft[(long long)pp * nlev + j] * q * wt;
       temp = temp + q * wt;
     }
-    if (temp != 0.0) for (int j = 0; j < nlevsoi; ++j) A.rootr_col[off + j] = A.rootr_col[off + j] / temp;
+    if (cell && j < nlevsoi) { if (temp != 0.0) r = r / temp; rootr = r; A.rootr_col[ic] = r; }
   }
-  double tot_et = 0.0, tot_drain = 0.0, mass_beg = 0.0;
-  const double qtran = A.qflx_tran_veg_col[c];
-  for (int j = 0; j < nlev; ++j) A.c_drain[off + j] = 0.0;
-  const double infl = A.qflx_infl[c] * conv;
-  double dew = 0.0, sub = 0.0;
-  if (A.snl[c] >= 0) {
-    const double wet = 1.0 - A.frac_h2osfc[c];
-    dew = (A.qflx_dew_snow[c] + A.qflx_dew_grnd[c]) * wet * conv;
-    sub = -A.qflx_sub_snow[c] * wet * conv;
-  }
-  const double qd = A.qflx_drain[c];
-  if (qd > 0.0) {                                                       // :340-372, layer numbers 1-based as in the reference
-    const double *zic = A.zi + (long long)c * (nlev + 1);
-    const double zw = A.zwt[c];
-    int jwt = nlev;
-    for (int j = 1; j <= nlev; ++j) if (zw <= zic[j]) { jwt = j - 1; break; }
+  // ---- :340-372 drainage below the water table (1-based layer numbers as in the reference) ----
+  double drain = 0.0, qd_new = qd;
+  {
+    // jwt = (first layer with zwt <= zi) - 1, nlev if none; at least 1
+    const unsigned hit = __ballot_sync(FULL, cell && (zw <= zi_j));
+    const unsigned mine = (hit >> ((threadIdx.x & 31) / G * G)) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+    int jwt = mine ? (__ffs(mine) - 1) : nlev;                         // (j_first) - 1 in 1-based numbering == 0-based index of the first hit
     if (jwt < 1) jwt = 1;
     double dzsum = 0.0, tot = 0.0;
-    for (int j = jwt; j <= nlev; ++j) dzsum = dzsum + A.dz[off + j - 1];
-    for (int j = jwt; j <= nlev; ++j) {
-      double ql = qd * A.dz[off + j - 1] / dzsum;
-      const double avail = A.h2osoi_liq[off + j - 1] - A.watmin;
+    for (int k = 1; k <= nlev; ++k) { const double v = __shfl_sync(FULL, dz, k - 1, G); if (k >= jwt) dzsum = dzsum + v; }
+    double ql = 0.0;
+    if (qd > 0.0 && cell && (j + 1) >= jwt) {
+      ql = qd * dz / dzsum;
+      const double avail = liq - A.watmin;
       if (ql * A.dtime > avail) ql = avail / A.dtime;
-      tot = tot + ql;
-      A.c_drain[off + j - 1] = -ql * conv;
+      drain = -ql * conv;
     }
-    A.qflx_drain[c] = tot;
+    for (int k = 1; k <= nlev; ++k) { const double v = __shfl_sync(FULL, ql, k - 1, G); if (k >= jwt) tot = tot + v; }
+    if (qd > 0.0) qd_new = tot;
   }
-  const double snow = A.mflx_snowlyr_col[c] * area + A.mflx_neg_snow[c] * area;
-  A.mflx_snowlyr_col[c] = 0.0;
-  for (int j = 0; j < nlev; ++j) {
-    const double et = (j < nlevsoi) ? -qtran * A.rootr_col[off + j] * conv : 0.0;
-    const double dr = A.c_drain[off + j] + A.mflx_drain_perched[off + j];      // :404
-    A.c_et[off + j] = et; A.c_drain[off + j] = dr;
-    const double liq = A.h2osoi_liq[off + j], ice = A.h2osoi_ice[off + j];
-    const double fi = ice / (liq + ice);                                           // :441
-    A.frac_ice[off + j] = fi; A.frac_liq[off + j] = 1.0 - fi;
-    tot_et = tot_et + et; tot_drain = tot_drain + dr; mass_beg = mass_beg + A.soe_mass[off + j];
+  // ---- sources, frac_liq_sat, totals ----
+  const double et = (cell && j < nlevsoi) ? -qtran * rootr * conv : 0.0;
+  const double dr = drain + perched;                                    // :404
+  const double infl = qinfl * conv;
+  double dew = 0.0, sub = 0.0;
+  if (snl >= 0) { const double wet = 1.0 - fh; dew = (dews + dewg) * wet * conv; sub = -subs * wet * conv; }
+  const double snow = snowl * area + negs * area;
+  if (cell) {
+    A.c_et[ic] = et; A.c_drain[ic] = dr;
+    const double fi = ice / (liq + ice);                                // :441
+    A.frac_ice[ic] = fi; A.frac_liq[ic] = 1.0 - fi;
   }
-  A.c_infl[c] = infl; A.c_dew[c] = dew; A.c_snow[c] = snow; A.c_sub[c] = sub;
-  A.mass_beg[c] = mass_beg;
-  A.tot_flux[c] = tot_et + infl + dew + tot_drain + snow + sub + 0.0;             // :583-589 (no lateral flux on the 1-D path)
+  double tot_et = 0.0, tot_drain = 0.0, mass_beg = 0.0;
+  for (int k = 0; k < nlev; ++k) {
+    tot_et = tot_et + __shfl_sync(FULL, et, k, G); tot_drain = tot_drain + __shfl_sync(FULL, dr, k, G); mass_beg = mass_beg + __shfl_sync(FULL, mass, k, G);
+  }
+  if (on && j == 0) {
+    A.qflx_drain[c] = qd_new; A.mflx_snowlyr_col[c] = 0.0;
+    A.c_infl[c] = infl; A.c_dew[c] = dew; A.c_snow[c] = snow; A.c_sub[c] = sub;
+    A.mass_beg[c] = mass_beg;
+    A.tot_flux[c] = tot_et + infl + dew + tot_drain + snow + sub + 0.0;           // :583-589 (no lateral flux on the 1-D path)
+  }
 }
 
+template <int G>
 __global__ void elm_decide_kernel(const ElmArgs A)
 {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= A.ncol) return;
-  const int m = A.mask[c];
-  if (m == 0) return;                                                   // not part of the StepDT that just ran
+  constexpr unsigned FULL = 0xffffffffu;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)(tid / G), j = (int)(tid % G);
   const int nlev = A.nlev;
-  const long long off = (long long)c * nlev;
+  const bool col_ok = c < A.ncol;
+  const int m = col_ok ? A.mask[c] : 0;
+  if (__all_sync(FULL, m == 0)) return;                                 // no column of this warp took part in the StepDT that just ran
+  const bool run = m != 0, cell = run && j < nlev;
+  const long long ic = (long long)c * nlev + j;
   const double area = 1.0;
-  const int iter = A.iter_count[c] + 1;
-  A.iter_count[c] = iter;
-  const int reason = A.stat_reason[c];
+  int reason = 0, iter = 0, dv = 0;
+  double dt_rem = 0.0, t_done = 0.0, mass_beg = 0.0, tot_flux = 0.0, rtol = 0.0, stol = 0.0;
+  if (run) {
+    reason = A.stat_reason[c]; iter = A.iter_count[c] + 1; dv = A.diverged[c]; dt_rem = A.dt_rem[c]; t_done = A.t_done[c];
+    mass_beg = A.mass_beg[c]; tot_flux = A.tot_flux[c]; rtol = A.rtol[c]; stol = A.stol[c];
+  }
+  const bool conv = run && reason > 0;
+  double fi = 0.0, mass = 0.0, smp = 0.0, pres = 0.0;
+  if (cell && conv) { fi = A.frac_ice[ic]; mass = A.soe_mass[ic]; smp = A.soe_smp[ic] * 1000.0; pres = A.soe_pressure[ic]; }   // [m] -> [mm]
   int next = 0, ok = 0;
-  if (reason <= 0) {                                                    // .not. converged (:645-660)
-    A.stol[c] = 1.0e-10;
-    const int dv = A.diverged[c] + 1; A.diverged[c] = dv;
-    A.dt_rem[c] = A.dt_rem[c] - A.t_done[c];
-    if (dv > 1) for (int j = 0; j < nlev; ++j) A.frac_liq[off + j] = 1.0;
+  if (run && !conv) {                                                   // .not. converged (:645-660)
+    stol = 1.0e-10; dv += 1; dt_rem = dt_rem - t_done;
+    if (dv > 1 && cell) A.frac_liq[ic] = 1.0;
     next = 1;
-  } else {                                                              // :662-905
+  }
+  // converged (:662-905): unpack, water table, mass balance
+  if (cell && conv) {
+    A.h2osoi_liq[ic] = (1.0 - fi) * mass / area; A.h2osoi_ice[ic] = fi * mass / area;
+    A.smp_l[ic] = smp; A.soilp[ic] = pres;
+  }
+  double mass_end = 0.0;
+  for (int k = nlev; k >= 1; --k) mass_end = mass_end + __shfl_sync(FULL, mass, k - 1, G);   // the reference sums from the bottom up
+  // jwt: the deepest layer with a negative matric potential (1-based), -1 if none
+  const unsigned neg = __ballot_sync(FULL, cell && conv && smp < 0.0);
+  const unsigned mine = (neg >> ((threadIdx.x & 31) / G * G)) & ((G == 32) ? 0xffffffffu : ((1u << G) - 1u));
+  const int jwt = mine ? (32 - __clz(mine)) : -1;
+  const int ja = (jwt >= 1 && jwt < nlev) ? jwt : 1;
+  const double s0 = __shfl_sync(FULL, smp, ja - 1, G), s1 = __shfl_sync(FULL, smp, ja, G);
+  if (conv && j == 0) {
     const double *zic = A.zi + (long long)c * (nlev + 1);
-    int jwt = -1;
-    double mass_end = 0.0;
-    for (int j = nlev; j >= 1; --j) {
-      const long long ic = off + j - 1;
-      const double fi = A.frac_ice[ic], mass = A.soe_mass[ic];
-      A.h2osoi_liq[ic] = (1.0 - fi) * mass / area;
-      A.h2osoi_ice[ic] = fi * mass / area;
-      mass_end = mass_end + mass;
-      const double smp = A.soe_smp[ic] * 1000.0;                        // [m] -> [mm]
-      A.smp_l[ic] = smp;
-      if (jwt == -1 && smp < 0.0) jwt = j;
-      A.soilp[ic] = A.soe_pressure[ic];
-    }
-    const double err = fabs(A.mass_beg[c] - mass_end + A.tot_flux[c] * A.dtime);
+    const double err = fabs(mass_beg - mass_end + tot_flux * A.dtime);
     A.abs_err[c] = err;
     A.qcharge[c] = 0.0;
     if (jwt == -1 || jwt == nlev) A.zwt[c] = zic[nlev];
     else {
       const double z_dn = (zic[jwt - 1] + zic[jwt]) / 2.0, z_up = (zic[jwt] + zic[jwt + 1]) / 2.0;
-      const double s0 = A.smp_l[off + jwt - 1], s1 = A.smp_l[off + jwt];
       A.zwt[c] = (0.0 - s0) / (s0 - s1) * (z_dn - z_up) + z_dn;
     }
     if (err >= 1.0e-5) {                                                // max_abs_mass_error_col (:880-897)
-      if (reason == SNES_CONVERGED_FNORM_RELATIVE) A.rtol[c] = A.rtol[c] / 10.0;
-      else if (reason == SNES_CONVERGED_SNORM_RELATIVE) A.stol[c] = A.stol[c] / 10.0;
-      A.dt_rem[c] = A.dtime;
+      if (reason == SNES_CONVERGED_FNORM_RELATIVE) rtol = rtol / 10.0;
+      else if (reason == SNES_CONVERGED_SNORM_RELATIVE) stol = stol / 10.0;
+      dt_rem = A.dtime;
       next = 2;                                                         // PreStepDT: back to soln_prev_clm
     } else ok = 1;
   }
-  if (!ok && iter >= 10) next = 0;                                      // max_iter_count: the reference calls endrun here
-  A.status[c] = ok;
-  A.mask[c] = next;
-  if (next) atomicAdd(A.pending, 1);
+  if (run && j == 0) {
+    if (!ok && iter >= 10) next = 0;                                    // max_iter_count: the reference calls endrun here
+    A.iter_count[c] = iter; A.diverged[c] = dv; A.dt_rem[c] = dt_rem; A.rtol[c] = rtol; A.stol[c] = stol;
+    A.status[c] = ok; A.mask[c] = next;
+    if (next) A.retry_list[atomicAdd(A.pending, 1)] = c;
+  }
 }
 
 }  // namespace mpp

@@ -67,6 +67,7 @@ struct VsfmArgs {
   double *t_done;          // optional per-column output: time this StepDT did advance (soe%time, SystemOfEquationsBaseType.F90:511)
   // RETRY specialisation only (the per-column retry loop of mppgpu_vsfm_elm_solve, MPPVSFMALM_Driver.F90:628-923):
   const int *retry_mask;   // 0 skip the column, 1 continue from x_in (remaining time), 2 redo from x_redo (soln_prev_clm)
+  const int *retry_list; int nretry;   // compacted column indices: the retry launch is sized by the columns that need it
   const double *dt_col, *rtol_col, *stol_col, *x_redo;
 };
 

@@ -170,7 +170,8 @@ vsfm_step2_kernel(const VsfmArgs A)
   constexpr double RVIS = 1.0 / VISCOSITY, RFMW = 1.0 / FMWH2O;
   constexpr int NBC = HAS_BC ? MAX_BC : 1;
   const int tid  = blockIdx.x * blockDim.x + threadIdx.x;
-  const int col  = tid / LPC;
+  int col = tid / LPC;
+  if (RETRY) col = (col < A.nretry) ? A.retry_list[col] : A.ncol;
   const int l    = tid % LPC;                        // lane within the column; owns layers 2l and 2l+1
   const int lane = threadIdx.x & 31;
   const int nlev = A.nlev;

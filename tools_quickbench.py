@@ -31,6 +31,17 @@ elif mode == "th":
     m = float(np.mean(ms[2:]))
     print("th ncol", ncol, "dens", dens, "ms/step", ["%.2f" % x for x in ms], "col-steps/s %.3e" % (ncol / (m * 1e-3)),
           "alg GB/s (1824 B/col) %.0f" % (1824 * ncol / (m * 1e-3) / 1e9), "its mean %.2f nf mean %.2f conv %s" % (st["newton_its"].mean(), st["nfuncs"].mean(), conv))
+elif mode == "elm":
+    d = bench.shard_inputs(0, ncol)
+    p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
+    st = PB.elm_vsfm_raw_state(p, d, patches=True)
+    p.elm_set_geometry(st["zi"], st["dz"], st["nlevsoi"], ids)
+    if len(sys.argv) > 3:
+        p.set_step_budget(int(sys.argv[3]))
+    for s in range(5):
+        t0 = time.time(); out = p.elm_solve(1800.0, st, s + 1); wall = time.time() - t0
+        print("elm_solve ncol", ncol, "device ms %.2f wall ms %.1f attempts %d nfailed %d max its %d" % (p.last_step_ms(), wall * 1e3, out["nattempts"], out["nfailed"], out["iter_count"].max()),
+              "col-steps/s device %.3e e2e %.3e" % (ncol / (p.last_step_ms() * 1e-3), ncol / wall))
 elif mode == "snow":
     base = 4096
     d0 = PB.elm_snow_thermal_inputs(base, 15, 5)
