@@ -191,15 +191,15 @@ def other_workloads(device, stream):
                                                          "achieved": 2356 * ncol / (m * 1e-3) / 1e9, "unit": "GB/s"}}
     p.close()
     # MPPVSFMALM_Solve with ELM's raw column arrays: packing, StepDT, per-column retry loop, unpacking on the device.
-    # Synthetic forcing is not state-aware (ELM would cut infiltration into a saturated column), so a few columns fail every retry;
-    # the opt-in step budget keeps those from dominating the timing (a failing column otherwise burns ~1e6 residual evaluations).
+    # Synthetic forcing is not state-aware (ELM would cut infiltration into a saturated column), so a column may fail every retry;
+    # the opt-in step budget keeps such a column from dominating the timing (it otherwise burns ~1e6 residual evaluations per call).
     ncol = 1 << 20
     d = shard_inputs(0, ncol)
     p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d, device=device)
     p.set_stream(stream)
     st = PB.elm_vsfm_raw_state(p, d, patches=True)
     p.elm_set_geometry(st["zi"], st["dz"], st["nlevsoi"], ids)
-    p.set_step_budget(400)
+    p.set_step_budget(2000)
     ms, wall, att, nf = [], [], [], []
     for s in range(3):
         t0 = time.perf_counter(); o = p.elm_solve(DT, st, s + 1); wall.append(time.perf_counter() - t0)
@@ -208,7 +208,7 @@ def other_workloads(device, stream):
     out["vsfm_elm_solve_1Mi_x15"] = {"column_timesteps_per_sec_device": ncol / (m * 1e-3), "ms_per_solve_device": m,
                                      "column_timesteps_per_sec_host_arrays": ncol / float(np.mean(wall)), "stepdt_calls": att, "columns_failed": nf,
                                      "kernels": "elm_pack_kernel<16> + vsfm_step2_kernel + elm_decide_kernel<16> (+ RETRY specialisation on the columns that need it)",
-                                     "note": "step budget 400 residual evaluations per column per StepDT; host arrays are pageable numpy buffers"}
+                                     "note": "step budget 2000 residual evaluations per column per StepDT; host arrays are pageable numpy buffers"}
     p.close()
     # TH: Tanaka density + constant heat capacity (the throughput variant of SURVEY.md section 8d)
     ncol = 1 << 18
@@ -449,7 +449,8 @@ def main():
             peak_ = peak
             line["other_workloads"] = other_workloads(local_rank, stream.cuda_stream)
             for v in line["other_workloads"].values():
-                v["roofline"]["peak"] = peak_; v["roofline"]["frac"] = v["roofline"]["achieved"] / peak_
+                if "roofline" in v:
+                    v["roofline"]["peak"] = peak_; v["roofline"]["frac"] = v["roofline"]["achieved"] / peak_
         if not args.no_cpu and world == 1:
             cb, _, _ = cpu_baseline(args.steps, args.warmup)
             line["cpu_baseline"] = cb

@@ -152,7 +152,8 @@ int  mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, int nin, co
  * is redone from soln_prev_clm with rtol or stol tightened tenfold), and unpacking (h2osoi_liq / h2osoi_ice, smp_l [mm], soil
  * pressure, water-table depth, qcharge = 0), then PostStepDT.  The reference takes the retry decisions per MPI rank; here per column.
  * Lateral-flux and seepage branches are not part of the 1-D path (no boundary conditions allowed).  All arrays are HOST pointers;
- * per-cell arrays are cell-ordered (c*nlev + j); `zi` has nlev+1 interfaces per column, zi(c,0) first.  nlev <= 32. */
+ * per-cell arrays are cell-ordered (c*nlev + j); `zi` has nlev+1 interfaces per column, zi(c,0) first.  nlev <= 32.  Columns filtered out by
+ * mppgpu_set_mesh's col_active keep their in/out arrays and read 0 in the pure outputs (smp_l, soilp_col, qcharge, status). */
 typedef struct {
   /* patch level, optional (npft = 0: rootr_col is an input) -- col%pfti (0-based), col%npfts, pft%active, pft%wtcol, rootr_patch(p,j), qflx_tran_veg_patch */
   int npft, max_patch_per_col;

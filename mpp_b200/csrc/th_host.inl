@@ -161,7 +161,7 @@ static int th_fill_args(mppgpu_soe *h, THState *t, THArgs &A, double dt)
 static int th_launch(mppgpu_soe *h, THState *, THArgs &A, int *nblocks_out)
 {
   const bool fast = h->nlev <= 16;
-  const int nblocks = fast ? nblk((long long)h->ncol * 16, 128) : h->ncol;
+  const int nblocks = fast ? nblk((long long)h->ncol * 16, TH2_THREADS) : h->ncol;
   if (!A.eval_x) {
     if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
     A.block_partials = h->block_partials.p;
@@ -169,11 +169,11 @@ static int th_launch(mppgpu_soe *h, THState *, THArgs &A, int *nblocks_out)
   if (fast) {
     // the two model combinations the reference's drivers use get compile-time specialisations; anything else dispatches at run time
     if (A.satfunc == SATFUNC_VG && A.density_type == DENSITY_TGDPB01 && A.iee_type == INT_ENERGY_ENTHALPY_CONSTANT)
-      th_step2_kernel<16, SATFUNC_VG, DENSITY_TGDPB01, INT_ENERGY_ENTHALPY_CONSTANT><<<nblocks, 128, 0, h->stream>>>(A);
+      th_step2_kernel<16, SATFUNC_VG, DENSITY_TGDPB01, INT_ENERGY_ENTHALPY_CONSTANT><<<nblocks, TH2_THREADS, 0, h->stream>>>(A);
     else if (A.satfunc == SATFUNC_VG && A.density_type == DENSITY_IFC67 && A.iee_type == INT_ENERGY_ENTHALPY_IFC67)
-      th_step2_kernel<16, SATFUNC_VG, DENSITY_IFC67, INT_ENERGY_ENTHALPY_IFC67><<<nblocks, 128, 0, h->stream>>>(A);
+      th_step2_kernel<16, SATFUNC_VG, DENSITY_IFC67, INT_ENERGY_ENTHALPY_IFC67><<<nblocks, TH2_THREADS, 0, h->stream>>>(A);
     else
-      th_step2_kernel<16, -1, -1, -1><<<nblocks, 128, 0, h->stream>>>(A);
+      th_step2_kernel<16, -1, -1, -1><<<nblocks, TH2_THREADS, 0, h->stream>>>(A);
   } else {
     const size_t smem = (size_t)TH_NARR * h->nlev * sizeof(double);
     if (smem > 200 * 1024) return fail("mppgpu_step_dt: nlev = %d exceeds the TH kernel's shared-memory budget", h->nlev);

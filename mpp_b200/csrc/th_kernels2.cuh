@@ -19,8 +19,13 @@
 
 namespace mpp {
 
+// One warp per block (two columns): a warp whose columns are done retires at once and frees its registers / shared memory for the
+// next block instead of idling at the block's final barrier behind a column that is cutting dt.
+#ifndef TH2_THREADS
+#define TH2_THREADS 32
+#endif
 #ifndef TH2_MIN_BLOCKS
-#define TH2_MIN_BLOCKS 3
+#define TH2_MIN_BLOCKS (384 / TH2_THREADS)
 #endif
 
 struct M2 { double a, b, c, d; };     // row-major 2x2: [a b; c d]
@@ -61,20 +66,20 @@ __device__ __forceinline__ void block_pcr(M2 A, M2 B, M2 C, double d0, double d1
   y0 = e0; y1 = e1;
 }
 
-__device__ __forceinline__ void ax_store(double (*s)[128], int t, const THCell &c)
+__device__ __forceinline__ void ax_store(double (*s)[TH2_THREADS], int t, const THCell &c)
 {
   s[0][t] = c.sat; s[1][t] = c.kr; s[2][t] = c.dsat; s[3][t] = c.dkr; s[4][t] = c.den_m; s[5][t] = c.ddenP_m; s[6][t] = c.ddenT_m;
   s[7][t] = c.den_e; s[8][t] = c.ddenP_e; s[9][t] = c.ddenT_e; s[10][t] = c.ul; s[11][t] = c.hl; s[12][t] = c.dulT; s[13][t] = c.dhlT;
   s[14][t] = c.dulP; s[15][t] = c.dhlP; s[16][t] = c.tc; s[17][t] = c.dtcP;
 }
-__device__ __forceinline__ void ax_load(double (*s)[128], int t, THCell &c)
+__device__ __forceinline__ void ax_load(double (*s)[TH2_THREADS], int t, THCell &c)
 {
   c.sat = s[0][t]; c.kr = s[1][t]; c.dsat = s[2][t]; c.dkr = s[3][t]; c.den_m = s[4][t]; c.ddenP_m = s[5][t]; c.ddenT_m = s[6][t];
   c.den_e = s[7][t]; c.ddenP_e = s[8][t]; c.ddenT_e = s[9][t]; c.ul = s[10][t]; c.hl = s[11][t]; c.dulT = s[12][t]; c.dhlT = s[13][t];
   c.dulP = s[14][t]; c.dhlP = s[15][t]; c.tc = s[16][t]; c.dtcP = s[17][t];
 }
 
-__device__ __forceinline__ SatParams th_load_sp(double (*s)[128], int t)
+__device__ __forceinline__ SatParams th_load_sp(double (*s)[TH2_THREADS], int t)
 {
   SatParams p;
   p.sat_res = s[14][t]; p.alpha = s[15][t]; p.m = s[16][t]; p.n = s[17][t]; p.pu = s[18][t]; p.ps = s[19][t]; p.b2 = s[20][t]; p.b3 = s[21][t];
@@ -82,7 +87,7 @@ __device__ __forceinline__ SatParams th_load_sp(double (*s)[128], int t)
 }
 
 template <int G, int SF, int DT, int IEE>
-__global__ void __launch_bounds__(128, TH2_MIN_BLOCKS)
+__global__ void __launch_bounds__(TH2_THREADS, TH2_MIN_BLOCKS)
 th_step2_kernel(const THArgs A)
 {
   constexpr unsigned FULL = FULL_MASK;
@@ -145,7 +150,7 @@ th_step2_kernel(const THArgs A)
 
   // Static per-cell data goes to shared memory ([field][thread]) and is re-read where used: ~45 registers less per lane, i.e. a
   // third (and fourth) block per SM for this latency-bound kernel.  The macros below shadow the set-up variables from here on.
-  __shared__ double s_tp[22][128];
+  __shared__ double s_tp[22][TH2_THREADS];
   {
     const int t = threadIdx.x;
     s_tp[0][t] = por; s_tp[1][t] = vol; s_tp[2][t] = csol; s_tp[3][t] = tkdry; s_tp[4][t] = srcm; s_tp[5][t] = srce; s_tp[6][t] = upw;
@@ -175,7 +180,7 @@ th_step2_kernel(const THArgs A)
   double Pp = P, Tp = T, Wm = P, We = T, Fm = 0.0, Fe = 0.0, Ym = 0.0, Ye = 0.0, accm = 0.0, acce = 0.0;
   // aux vars of both equations at the accepted iterate: 18 doubles per cell parked in shared memory ([field][thread],
   // conflict-free); the Jacobian reads the cell's own copy and the next cell's (thread + 1) without any shuffle
-  __shared__ double s_ax[18][128];
+  __shared__ double s_ax[18][TH2_THREADS];
   {
     THCell z;
     z.sat = 1.0; z.kr = 1.0; z.dsat = 0.0; z.dkr = 0.0; z.den_m = 55.0; z.ddenP_m = 0.0; z.ddenT_m = 0.0; z.den_e = 55.0; z.ddenP_e = 0.0;
@@ -440,8 +445,8 @@ th_step2_kernel(const THArgs A)
     vits = fmax(vits, __shfl_xor_sync(FULL, vits, s)); vdiv = fmax(vdiv, __shfl_xor_sync(FULL, vdiv, s)); vcut = fmax(vcut, __shfl_xor_sync(FULL, vcut, s));
     worst = min(worst, __shfl_xor_sync(FULL, worst, s));
   }
-  __shared__ double red[3][128 / 32];
-  __shared__ int redw[128 / 32];
+  __shared__ double red[3][TH2_THREADS / 32];
+  __shared__ int redw[TH2_THREADS / 32];
   const int warp = threadIdx.x >> 5;
   if (lane == 0) { red[0][warp] = vits; red[1][warp] = vdiv; red[2][warp] = vcut; redw[warp] = worst; }
   __syncthreads();

@@ -44,12 +44,12 @@ extern "C" int mppgpu_vsfm_elm_set_geometry(mppgpu_handle h, const double *zi, c
   CK(cudaMemcpyAsync(e->zi.p, zi, ncol * (h->nlev + 1) * 8, cudaMemcpyHostToDevice, h->stream));
   CK(cudaMemcpyAsync(e->dz.p, dz, N * 8, cudaMemcpyHostToDevice, h->stream));
   DevBuf<double> *cellb[] = {&e->rootr, &e->liq, &e->ice, &e->perched, &e->frac_ice, &e->smp_l, &e->soilp};
-  for (auto b : cellb) CK(b->alloc(N));
+  for (auto b : cellb) { CK(b->alloc(N)); CK(cudaMemsetAsync(b->p, 0, N * 8, h->stream)); }    // outputs of filtered-out columns read 0
   DevBuf<double> *colb[] = {&e->qtran, &e->qinfl, &e->dews, &e->dewg, &e->subs, &e->fh2osfc, &e->qdrain, &e->zwt, &e->snowlyr, &e->negsnow,
                             &e->mass_beg, &e->tot_flux, &e->dt_rem, &e->rtol, &e->stol, &e->t_done, &e->qcharge, &e->abs_err};
-  for (auto b : colb) CK(b->alloc(ncol));
+  for (auto b : colb) { CK(b->alloc(ncol)); CK(cudaMemsetAsync(b->p, 0, ncol * 8, h->stream)); }
   DevBuf<int> *coli[] = {&e->snl, &e->iter_count, &e->diverged, &e->mask, &e->status, &e->retry_list};
-  for (auto b : coli) CK(b->alloc(ncol));
+  for (auto b : coli) { CK(b->alloc(ncol)); CK(cudaMemsetAsync(b->p, 0, ncol * sizeof(int), h->stream)); }
   CK(e->pending.alloc(1));
   CK(cudaStreamSynchronize(h->stream));
   e->nlevsoi = nlevsoi; e->watmin = watmin; e->geometry_set = true;

@@ -188,7 +188,7 @@ def elm_vsfm_raw_state(p, d, seed=SEED, patches=True, nlevsoi=10, drain_frac=0.7
     st["qflx_dew_snow"] = rng.uniform(0.0, 1e-6, ncol); st["qflx_dew_grnd"] = rng.uniform(0.0, 2e-6, ncol); st["qflx_sub_snow"] = rng.uniform(0.0, 1e-6, ncol)
     st["frac_h2osfc"] = np.where(rng.uniform(size=ncol) < 0.5, rng.uniform(0.0, 0.3, ncol), 0.0)
     st["snl"] = -rng.integers(0, 3, ncol).astype(np.int32)
-    st["qflx_drain"] = np.where(rng.uniform(size=ncol) < drain_frac, rng.uniform(0.0, 1e-5, ncol), 0.0)
+    st["qflx_drain"] = np.where(rng.uniform(size=ncol) < drain_frac, rng.uniform(0.0, 1e-6, ncol), 0.0)     # baseflow-sized: <= 0.09 mm/day
     # water table where the initial pressure profile crosses P_ref (ELM diagnoses zwt from the VSFM solution, :866-876); a table
     # placed at random would have the drainage pull water out of dry layers, which no Newton iteration can deliver
     P0 = np.asarray(d["press_ic"]).reshape(ncol, nlev)[:, 0]

@@ -528,3 +528,30 @@ def test_elm_solve_error_behaviour(mpp):
         g.elm_solve(1800.0, bad)
     out = g.elm_solve(1800.0, st)
     assert out["nfailed"] == 0 and out["nattempts"] >= 1
+
+
+def test_elm_solve_respects_the_column_filter(mpp, oracle):
+    """filter_hydrologyc: columns switched off in the mesh are neither packed, stepped nor unpacked."""
+    ncol = 64
+    d = PB.elm_vsfm_inputs(ncol)
+    act = (np.arange(ncol) % 3 != 0).astype(np.int32)
+    g = mpp.VSFM(ncol, 15)
+    g.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"], act)
+    ids = {}
+    for name, region in (("infil", K.SOIL_TOP_CELLS), ("et", K.SOIL_CELLS), ("dew", K.SOIL_TOP_CELLS), ("drain", K.SOIL_CELLS),
+                         ("snow", K.SOIL_TOP_CELLS), ("sublim", K.SOIL_TOP_CELLS)):
+        ids[name] = g.add_condition(1, K.COND_SS, K.COND_MASS_RATE, region)
+    g.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], d["satfunc"], K.DENSITY_TGDPB01)
+    g.restart(d["press_ic"])
+    full, fids = PB.build_elm_vsfm(mpp.VSFM, d)
+    st = PB.elm_vsfm_raw_state(full, d, patches=False)
+    st_f = PB.copy_state(st)
+    for s_, p_, i_ in ((st, g, ids), (st_f, full, fids)):
+        p_.elm_set_geometry(s_["zi"], s_["dz"], s_["nlevsoi"], i_)
+    liq0 = st["h2osoi_liq"].copy()
+    og, of = g.elm_solve(1800.0, st), full.elm_solve(1800.0, st_f)
+    on = act == 1
+    assert og["nfailed"] == 0
+    assert np.array_equal(st["h2osoi_liq"][~on], liq0[~on]) and np.all(og["status"][~on] == 0) and np.all(og["smp_l"].reshape(ncol, -1)[~on] == 0.0)
+    assert np.array_equal(st["h2osoi_liq"][on], st_f["h2osoi_liq"][on])          # same kernels, same inputs: bit-identical to the unfiltered run
+    assert np.array_equal(og["soilp_col"].reshape(ncol, -1)[on], of["soilp_col"].reshape(ncol, -1)[on])
