@@ -1,5 +1,6 @@
 """The reference's own regression harness (regression_tests/regression_tests.py, unmodified, run from where it lies) against
-tools/standalone_mpp, the drop-in for the reference's driver executable.  Needs /root/reference (this container only); the suite
+tools/standalone_mpp, the drop-in for the reference's driver executable (here, without a GPU, through tests/oracle_standalone_mpp, the
+same driver code with the CPU oracle's classes plugged in).  Needs /root/reference (this container only); the suite
 configuration is the reference's own, filtered to the problem types on the 1-D column path.  Scratch files stay inside the repo."""
 import os
 import shutil
@@ -24,6 +25,10 @@ def _filtered_cfg(src, keep):
     return "".join(out)
 
 
+def _exe(backend):
+    return os.path.join(ROOT, "tools", "standalone_mpp") if backend == "gpu" else os.path.join(ROOT, "tests", "oracle_standalone_mpp")
+
+
 def _run_harness(suite, backend, scratch):
     d = os.path.join(scratch, suite)
     os.makedirs(d, exist_ok=True)
@@ -32,9 +37,8 @@ def _run_harness(suite, backend, scratch):
     for t in SUPPORTED[suite]:
         for ext in (".namelist", ".regression.baseline"):
             shutil.copy(os.path.join(REF, suite, t + ext), d)
-    env = dict(os.environ, MPP_BACKEND=backend)
-    r = subprocess.run([sys.executable, os.path.join(REF, "regression_tests.py"), "--executable", os.path.join(ROOT, "tools", "standalone_mpp"),
-                        "--config", os.path.join(d, suite + ".cfg")], cwd=d, env=env, capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(REF, "regression_tests.py"), "--executable", _exe(backend),
+                        "--config", os.path.join(d, suite + ".cfg")], cwd=d, capture_output=True, text=True, timeout=600)
     return r
 
 
@@ -58,8 +62,7 @@ def test_reference_harness_passes_on_the_oracle_backend(suite, scratch):
 def test_driver_executable_refuses_problems_off_the_column_path(scratch):
     nl = os.path.join(scratch, "vsfm_vchannel.namelist")
     open(nl, "w").write("&mpp_driver\n  problem_type = 'vsfm_vchannel'\n/\n&regression_test\n  write_regression_output = .true.\n  num_cells = 5\n/\n")
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "standalone_mpp"), "-namelist", nl], cwd=scratch,
-                       env=dict(os.environ, MPP_BACKEND="oracle"), capture_output=True, text=True, timeout=120)
+    r = subprocess.run([sys.executable, _exe("oracle"), "-namelist", nl], cwd=scratch, capture_output=True, text=True, timeout=120)
     assert r.returncode == 3 and "not on the 1-D column path" in r.stdout
 
 
@@ -77,8 +80,7 @@ def test_driver_executable_on_the_gpu_meets_the_reference_tolerances(test, scrat
     import problems as PB
     nl = os.path.join(scratch, test + ".namelist")
     open(nl, "w").write("&mpp_driver\n  problem_type = '%s'\n/\n&regression_test\n  write_regression_output = .true.\n  num_cells = 5\n/\n" % test)
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "standalone_mpp"), "-namelist", nl], cwd=scratch,
-                       env=dict(os.environ, MPP_BACKEND="gpu"), capture_output=True, text=True, timeout=600)
+    r = subprocess.run([sys.executable, _exe("gpu"), "-namelist", nl], cwd=scratch, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout + r.stderr
     got = PB.parse_regression(os.path.join(scratch, test + ".regression"))
     ref = golden[test]

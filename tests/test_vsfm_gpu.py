@@ -418,10 +418,11 @@ def _elm_compare(st_g, st_o, og, oo, sel, tol=RTOL):
     assert np.all(og["qcharge"] == 0.0)
 
 
-@pytest.mark.parametrize("patches", [True, False])
-def test_elm_solve_raw_arrays_match_oracle(mpp, oracle, patches):
+@pytest.mark.parametrize("patches,satfunc", [(True, "van_genuchten"), (False, "van_genuchten"), (False, "brooks_corey")])
+def test_elm_solve_raw_arrays_match_oracle(mpp, oracle, patches, satfunc):
+    # Brooks-Corey: the only curve whose relative permeability reads frac_liq_sat (the ice impedance the driver computes, :435-450)
     ncol = 600
-    d = PB.elm_vsfm_inputs(ncol)
+    d = PB.elm_vsfm_inputs(ncol, satfunc=satfunc)
     g, gids = PB.build_elm_vsfm(mpp.VSFM, d)
     o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
     st_g = PB.elm_vsfm_raw_state(g, d, patches=patches)
