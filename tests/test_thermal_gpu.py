@@ -187,3 +187,35 @@ def test_snow_mode_error_behaviour(mpp):
     big = mpp.ThermalSnow(2, 30, 5)
     with pytest.raises(mpp.MPPError):                                                # 36 rows per column
         big.set_mesh(np.ones((2, 30)), np.ones(2), np.ones((2, 29)), np.ones((2, 29)), np.ones(2))
+
+
+@pytest.mark.parametrize("snow", [False, True])
+def test_thermal_landunit_types(mpp, oracle, snow):
+    """ThermKSPTempSoilAuxVarCompute branches on the landunit type (ThermalKSPTemperatureSoilAuxType.F90:71-171): soil / crop (Johansen
+    conductivity, bedrock below nlevsoi), wetland (ice / water conductivity, no mineral heat capacity), land ice and ice_mec."""
+    ncol, nlev, nsno = 120, 15, 5
+    types = np.array([K.ISTSOIL, K.ISTCROP, K.ISTICE, K.ISTICE_MEC, K.ISTWET], dtype=np.int32)
+    if snow:
+        d = PB.elm_snow_thermal_inputs(ncol, nlev, nsno)
+        d["lun_type"] = types[np.arange(ncol) % 5]
+        g = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+        r = PB.build_elm_snow_thermal(oracle.OracleThermalSnow, d)
+        o = PB.pack_elm_snow_thermal(d)
+        conv, T = PB.elm_snow_thermal_step(g, o)
+        convo, To = PB.elm_snow_thermal_step(r, o)
+        act = o["active"] == 1
+        assert relmax(T[act], To[act]) < RTOL
+    else:
+        d = PB.elm_thermal_inputs(ncol, nlev)
+        d["lun_type"] = types[np.arange(ncol) % 5]
+        d["snow_water"] = np.where(np.arange(ncol * nlev) % nlev == 0, 3.0, 0.0)       # h2osno enters the top layer's heat capacity when snl = 0
+        g, ids = PB.build_elm_thermal(mpp.Thermal, d)
+        r, rids = PB.build_elm_thermal(oracle.OracleThermal, d)
+        T, To = d["T0"].copy(), d["T0"].copy()
+        for step in range(2):
+            conv, T = PB.elm_thermal_step(g, ids, d, T, 1800.0, step + 1)
+            convo, To = PB.elm_thermal_step(r, rids, d, To, 1800.0, step + 1)
+            assert relmax(T, To) < RTOL, step
+    # the types really take different branches: same forcing, different temperatures
+    Tt = (T[-ncol * nlev:] if snow else T).reshape(ncol, nlev)
+    assert np.abs(Tt[0::5].mean() - Tt[2::5].mean()) > 1e-3
