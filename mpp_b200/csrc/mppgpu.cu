@@ -187,7 +187,7 @@ __global__ void vsfm_restart_mailbox_kernel(int satfunc, VsfmArgs A)
     const double X = A.x_in[cell];
     SatState st; double den, dden;
     sat_values_rt(satfunc, sp, X, A.frac_liq[cell], st);
-    density_fixedT(A.dtab, X, den, dden);
+    density_fixedT_x<true>(A.dtab, X, den, dden);
     const double mass = A.por[cell] * den * FMWH2O * st.sat * (area * A.dz[cell]);
     A.liq_sat[cell] = st.sat; A.pressure[cell] = X; A.mass[cell] = mass;
     A.smp[cell] = (X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
@@ -443,7 +443,6 @@ extern "C" int mppgpu_vsfm_set_soils(mppgpu_handle h, const double *watsat, cons
   if (!watsat || !hksat || !bsw || !sucsat || !residual_sat) return fail("mppgpu_vsfm_set_soils: null table");
   if (satfunc_type < 0 || satfunc_type > 3) return fail("ERROR:: Unknown vsfm_satfunc_type = %d", satfunc_type);   // MultiPhysicsProbVSFM.F90:415
   if (density_type < DENSITY_CONSTANT || density_type > DENSITY_IFC67) return fail("Unknown value for VAR_DENSITY_TYPE %d", density_type);
-  if (density_type == DENSITY_IFC67) return fail("mppgpu_vsfm_set_soils: DENSITY_IFC67 is only wired for the TH SoE");
   const size_t N = h->ncells;
   DevBuf<double> t[5]; const double *src[5] = {watsat, hksat, bsw, sucsat, residual_sat};
   for (int i = 0; i < 5; ++i) if (upload_table(h, src[i], t[i])) return 1;
@@ -645,7 +644,8 @@ template <int LPC>
 static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 {
   const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
-  const bool bc = A.nbc > 0 || A.dr_type != 0;        // the specialisation that carries boundary conditions and the down-regulated sink
+  // the specialisation that carries boundary conditions, the down-regulated sink and the IFC-67 density polynomial
+  const bool bc = A.nbc > 0 || A.dr_type != 0 || A.dtab.type == DENSITY_IFC67;
 #define MPP_L2(SF) do { if (A.retry_mask) vsfm_step2_kernel<LPC, SF, true, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
                         else if (bc) vsfm_step2_kernel<LPC, SF, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
                         else    vsfm_step2_kernel<LPC, SF, false><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); } while (0)

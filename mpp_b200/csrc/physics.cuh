@@ -560,6 +560,15 @@ MPP_HD void density_ifc67(double t, double p, double &dwmol, double &dwp, double
   dwp = cnv * vrpp * upc1;
 }
 
+// density at the VSFM aux vars' fixed 298.15 K for every density model; EXT = false compiles the IFC-67 polynomial out (the common
+// specialisation of the step kernel), EXT = true dispatches on the run-time type
+template <bool EXT>
+MPP_HD void density_fixedT_x(const DensityTable &t, double p, double &den, double &dden_dp)
+{
+  if (EXT && t.type == DENSITY_IFC67) { double dT; density_ifc67(25.0, p, den, dden_dp, dT); }
+  else density_fixedT(t, p, den, dden_dp);
+}
+
 // EnthalpyIFC67, EOSWaterMod.F90:347-565 (t in Celsius).  hw [J kmol^-1]
 MPP_HD void enthalpy_ifc67(double t, double p, double &hw, double &hwp, double &hwt)
 {

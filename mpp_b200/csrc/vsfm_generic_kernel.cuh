@@ -197,7 +197,7 @@ vsfm_step_generic_kernel(const VsfmArgs A, const int satfunc)
       SatState st;
       sat_values_rt(satfunc, sp, W[j], fl_liq[j], st);
       double ds, dk; sat_derivs_rt(satfunc, sp, st, fl_liq[j], ds, dk);
-      double dn, ddn; density_fixedT(A.dtab, W[j], dn, ddn);
+      double dn, ddn; density_fixedT_x<true>(A.dtab, W[j], dn, ddn);
       kr[j] = st.kr; sat[j] = st.sat; dsat[j] = ds; dkr[j] = dk; den[j] = dn; dden[j] = ddn;
     }
     __syncwarp();

@@ -299,8 +299,8 @@ vsfm_step2_kernel(const VsfmArgs A)
       const bool nw = (phase == PH_NEWTON);
       __syncwarp();                                  // (also keeps the compiler from hoisting the shared-memory reads out of the loop)
       double den_a, dden_a, den_b, dden_b;
-      density_fixedT(A.dtab, a.X, den_a, dden_a);
-      density_fixedT(A.dtab, b.X, den_b, dden_b);
+      density_fixedT_x<HAS_BC>(A.dtab, a.X, den_a, dden_a);
+      density_fixedT_x<HAS_BC>(A.dtab, b.X, den_b, dden_b);
       // aux vars at X of this lane's cells, and of the first cell of the next lane (dn side of connection b) straight from
       // shared memory; only the pressure itself lives in a register and needs a shuffle
       const double kr_a = PA(PI_KR), dkr_a_ = PA(PI_DKR), sat_a = PA(PI_SAT), dsat_a_ = PA(PI_DSAT);
@@ -309,7 +309,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       const double krn = pa[PI_KR][txn], dkrn = pa[PI_DKR][txn];
       const double Xn = __shfl_down_sync(FULL, a.X, 1, LPC);
       double denn, ddenn;
-      density_fixedT(A.dtab, Xn, denn, ddenn);
+      density_fixedT_x<HAS_BC>(A.dtab, Xn, denn, ddenn);
       // both connections evaluated unconditionally (all inputs are finite on padding lanes) and masked afterwards: no divergent
       // branch, and the two derivative chains overlap
       double Jup_a, Jdn_a, Jup_b, Jdn_b;
@@ -445,8 +445,8 @@ vsfm_step2_kernel(const VsfmArgs A)
     const long long pt1b = clock64(); pt_curves += pt1b - pt1 + (long long)(1e-300 * (sa.kr + sb.kr));
 #endif
     double dena, ddena, denb, ddenb, Ga, Gb, G_bcflux[NBC];
-    density_fixedT(A.dtab, a.W, dena, ddena);
-    density_fixedT(A.dtab, b.W, denb, ddenb);
+    density_fixedT_x<HAS_BC>(A.dtab, a.W, dena, ddena);
+    density_fixedT_x<HAS_BC>(A.dtab, b.W, denb, ddenb);
     {
       const double acc_a = PA(PI_POR) * dena * sa.sat * PA(PI_VOL) * dtInv;       // Accum (:1626-1630)
       const double acc_b = PB(PI_POR) * denb * sb.sat * PB(PI_VOL) * dtInv;
@@ -597,7 +597,7 @@ vsfm_step2_kernel(const VsfmArgs A)
   if (a.valid) {
     A.x_out[cell0] = a.X;
     if (converged) {
-      double den, dden; density_fixedT(A.dtab, a.X, den, dden);
+      double den, dden; density_fixedT_x<HAS_BC>(A.dtab, a.X, den, dden);
       const double sat = PA(PI_SAT);
       const double m = PA(PI_POR) * den * FMWH2O * sat * PA(PI_VOL);
       A.liq_sat[cell0] = sat; A.pressure[cell0] = a.X; A.mass[cell0] = m;
@@ -608,7 +608,7 @@ vsfm_step2_kernel(const VsfmArgs A)
   if (b.valid) {
     A.x_out[cell0 + 1] = b.X;
     if (converged) {
-      double den, dden; density_fixedT(A.dtab, b.X, den, dden);
+      double den, dden; density_fixedT_x<HAS_BC>(A.dtab, b.X, den, dden);
       const double sat = PB(PI_SAT);
       const double m = PB(PI_POR) * den * FMWH2O * sat * PB(PI_VOL);
       A.liq_sat[cell0 + 1] = sat; A.pressure[cell0 + 1] = b.X; A.mass[cell0 + 1] = m;

@@ -139,7 +139,7 @@ def build_elm_vsfm(cls, d, **kw):
     ids["drain"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_CELLS)
     ids["snow"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
     ids["sublim"] = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
-    p.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], d["satfunc"], K.DENSITY_TGDPB01)
+    p.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], d["satfunc"], d.get("density_type", K.DENSITY_TGDPB01))
     p.restart(d["press_ic"])
     return p, ids
 

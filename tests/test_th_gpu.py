@@ -184,3 +184,27 @@ def test_th_pressure_and_temperature_dirichlet_boundaries(mpp, oracle, nlev):
     Tg = g[0].get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, 1, ieqn=2).reshape(ncol, nlev)
     Pg = g[0].get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1, ieqn=1).reshape(ncol, nlev)
     assert np.abs(Tg[:, -1] - Tb0).max() > 1e-4 and np.abs(Pg[:, -1] - Pb0).max() > 1.0
+
+
+@pytest.mark.parametrize("satfunc,dens,iee", [("brooks_corey", K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_CONSTANT),
+                                              ("van_genuchten", K.DENSITY_CONSTANT, K.INT_ENERGY_ENTHALPY_CONSTANT),
+                                              ("van_genuchten", K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_IFC67),
+                                              ("smooth_brooks_corey_bz2", K.DENSITY_IFC67, K.INT_ENERGY_ENTHALPY_CONSTANT)])
+def test_th_model_combinations_through_the_runtime_dispatch(mpp, oracle, satfunc, dens, iee):
+    """Only the two combinations of the reference's drivers have compile-time specialisations of the TH kernel; every other mix of
+    saturation curve, density and enthalpy model goes through the run-time-dispatch instance (th_step2_kernel<16,-1,-1,-1>)."""
+    ncol = 120
+    d = PB.elm_th_inputs(ncol, 15, satfunc=satfunc, density_type=dens, iee_type=iee)
+    p, ids = PB.build_elm_th(mpp.TH, d)
+    o, oids = PB.build_elm_th(oracle.OracleTH, d, per_column=True, nthreads=8)
+    for step in range(2):
+        conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, step + 1)
+        convo, reasono, outo = PB.elm_th_step(o, oids, d, 1800.0, step + 1)
+        assert conv == convo
+        sg, so_ = p.stats(), o.stats()
+        same = (sg["newton_its"] == so_["newton_its"]) & (so_["dt_cuts"] == 0) & (so_["reasons"] > 0)
+        assert same.mean() > 0.9
+        ifc = dens == K.DENSITY_IFC67 or iee == K.INT_ENERGY_ENTHALPY_IFC67
+        for k in ("pressure", "temperature", "sat"):
+            a, b = out[k].reshape(ncol, 15)[same], outo[k].reshape(ncol, 15)[same]
+            assert (relmax_p if k == "pressure" else relmax)(a, b) < (1e-9 if (ifc and k == "pressure") else RTOL), (step, k)

@@ -556,3 +556,24 @@ def test_elm_solve_respects_the_column_filter(mpp, oracle):
     assert np.array_equal(st["h2osoi_liq"][~on], liq0[~on]) and np.all(og["status"][~on] == 0) and np.all(og["smp_l"].reshape(ncol, -1)[~on] == 0.0)
     assert np.array_equal(st["h2osoi_liq"][on], st_f["h2osoi_liq"][on])          # same kernels, same inputs: bit-identical to the unfiltered run
     assert np.array_equal(og["soilp_col"].reshape(ncol, -1)[on], of["soilp_col"].reshape(ncol, -1)[on])
+
+
+@pytest.mark.parametrize("dens", [K.DENSITY_CONSTANT, K.DENSITY_IFC67])
+def test_elm_like_batch_other_density_models(mpp, oracle, dens):
+    """EOSWaterMod.F90:38-344: constant density and IFC-67 next to the Tanaka default (VSFM evaluates them at the fixed 298.15 K)."""
+    ncol = 300
+    d = PB.elm_vsfm_inputs(ncol, 15)
+    d["density_type"] = dens
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
+    for step in range(2):
+        conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, step + 1)
+        convo, reasono, outo = PB.elm_vsfm_step(o, oids, d, 1800.0, step + 1)
+        assert conv == convo and conv
+        same = p.stats()["newton_its"] == o.stats()["newton_its"]
+        assert same.mean() > 0.97
+        a, b = out["pressure"].reshape(ncol, 15)[same], outo["pressure"].reshape(ncol, 15)[same]
+        # constant density: a saturated cell has dF/dP = 0 exactly (no compressibility at all) -- its pressure is set by its neighbours
+        # through the fluxes only; IFC-67 carries ~1e-13 of polynomial round-off (see the TH tests)
+        assert relmax_p(a, b) < (1e-9 if dens == K.DENSITY_IFC67 else RTOL), (dens, step)
+        assert relmax(out["mass"].reshape(ncol, 15)[same], outo["mass"].reshape(ncol, 15)[same]) < RTOL
