@@ -105,6 +105,22 @@ int  mppgpu_thermal_set_cnfac(mppgpu_handle h, double cnfac);
  * [snow cells, column-major | standing-water cells | soil cells], as MPPThermalTBasedALM_Driver.F90:204-452 packs them;
  * inactive cells come back as 0 like the reference's identity rows.  ceil(nlevsno/2) + ceil(nlev/2) <= 16. */
 int  mppgpu_thermal_add_snow_ssw(mppgpu_handle h, int nlevsno, const double *soil_top_dist_dn);
+/* MPPThermalTBasedALM_Solve (src/driver/alm/MPPThermalTBasedALM_Driver.F90:150-452) with ELM's raw column arrays: the packing into the
+ * SoE mailbox (:204-330: active snow layers, the standing-water cell, tuning factors, fractions, heat fluxes and absorbed radiation),
+ * SetSolnPrevCLM / Set{R,I,B}DataFromCLM, PreStepDT, StepDT, GetSoln and the unpacking into tvector (:460-505) run on the device.
+ * Arrays are HOST pointers in ELM's own (c, j) Fortran order (column index fastest): value of column c at layer j sits at
+ * [(j - jlo)*ncol + c], with jlo = -nlevsno+1 for z, dz, t_soisno, h2osoi_liq, h2osoi_ice, sabg_lyr (up to j = 1) and jlo = -nlevsno
+ * for zi and tvector.  Needs mppgpu_thermal_add_snow_ssw; columns filtered out by mppgpu_set_mesh's col_active are skipped. */
+typedef struct {
+  const int *snl;                                          /* ncol: minus the number of snow layers */
+  const double *z, *dz, *zi;                               /* col%z, col%dz (ncol, -nlevsno+1:nlev), col%zi (ncol, -nlevsno:nlev) */
+  const double *t_soisno, *h2osoi_liq, *h2osoi_ice;        /* (ncol, -nlevsno+1:nlev) */
+  const double *frac_sno_eff, *h2osno, *h2osfc, *frac_h2osfc, *t_h2osfc;   /* ncol */
+  const double *sabg_lyr;                                  /* (ncol, -nlevsno+1:1) */
+  const double *dhsdT, *hs_soil, *hs_top_snow, *hs_h2osfc; /* ncol */
+  double *tvector;                                         /* in/out (ncol, -nlevsno:nlev): only the entries the driver assigns change */
+} mppgpu_elm_thermal_columns;
+int  mppgpu_thermal_elm_solve(mppgpu_handle h, double dtime, int nstep, const mppgpu_elm_thermal_columns *cols, double capr);
 int  mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
                          const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,
                          int satfunc_type, int density_type, int int_energy_enthalpy_type);

@@ -29,6 +29,13 @@ class ElmColumns(C.Structure):
                 ("smp_l", c_dp), ("soilp_col", c_dp), ("qcharge", c_dp), ("abs_mass_error", c_dp), ("iter_count", c_ip), ("status", c_ip)]
 
 
+class ElmThermalColumns(C.Structure):
+    """mppgpu_elm_thermal_columns (include/mppgpu.h)."""
+    _fields_ = [("snl", c_ip), ("z", c_dp), ("dz", c_dp), ("zi", c_dp), ("t_soisno", c_dp), ("h2osoi_liq", c_dp), ("h2osoi_ice", c_dp),
+                ("frac_sno_eff", c_dp), ("h2osno", c_dp), ("h2osfc", c_dp), ("frac_h2osfc", c_dp), ("t_h2osfc", c_dp), ("sabg_lyr", c_dp),
+                ("dhsdT", c_dp), ("hs_soil", c_dp), ("hs_top_snow", c_dp), ("hs_h2osfc", c_dp), ("tvector", c_dp)]
+
+
 _SIGS = {
     "mppgpu_last_error": (C.c_char_p, []),
     "mppgpu_version": (C.c_int, []),
@@ -44,6 +51,7 @@ _SIGS = {
     "mppgpu_thermal_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int, C.c_int]),
     "mppgpu_thermal_set_cnfac": (C.c_int, [C.c_void_p, C.c_double]),
     "mppgpu_thermal_add_snow_ssw": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
+    "mppgpu_thermal_elm_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(ElmThermalColumns), C.c_double]),
     "mppgpu_vsfm_elm_set_geometry": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, c_ip]),
     "mppgpu_vsfm_elm_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(ElmColumns), c_ip, c_ip]),
     "mppgpu_th_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int]),

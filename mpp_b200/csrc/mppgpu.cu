@@ -107,6 +107,7 @@ static int thermal_post_step_dt(ThermalState *t);
 static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt);
 static int thermal_add_snow_ssw(mppgpu_soe *h, ThermalState *t, int nlevsno, const double *soil_top_dist_dn);
 static void elm_destroy(struct ElmState *e);
+static int thermal_elm_solve(mppgpu_soe *h, ThermalState *t, double dtime, const mppgpu_elm_thermal_columns *cols, double capr);
 static int thermal_set_soils(mppgpu_soe *h, ThermalState *t, const double *watsat, const double *csol, const double *tkmg,
                              const double *tkdry, const int *lun_type, int nlevsoi, int istsoil);
 static int th_create(THState *t, int ncol, int nlev, cudaStream_t s);
@@ -915,6 +916,14 @@ extern "C" int mppgpu_thermal_add_snow_ssw(mppgpu_handle h, int nlevsno, const d
   CHECK_H(h);
   if (!h->thermal) return fail("mppgpu_thermal_add_snow_ssw: handle is not a thermal SoE");
   return thermal_add_snow_ssw(h, h->thermal, nlevsno, soil_top_dist_dn);
+}
+extern "C" int mppgpu_thermal_elm_solve(mppgpu_handle h, double dtime, int nstep, const mppgpu_elm_thermal_columns *cols, double capr)
+{
+  CHECK_H(h);
+  (void)nstep;
+  if (!h->thermal) return fail("mppgpu_thermal_elm_solve: handle is not a thermal SoE");
+  if (!(dtime > 0.0)) return fail("mppgpu_thermal_elm_solve: dtime must be positive");
+  return thermal_elm_solve(h, h->thermal, dtime, cols, capr);
 }
 extern "C" int mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
                                    const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,

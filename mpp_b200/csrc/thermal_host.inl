@@ -40,6 +40,8 @@ static void thermal_destroy(ThermalState *t)
   double *e[] = {t->soil_top_dist_dn, t->hs[0], t->hs[1], t->hs[2], t->dhs[0], t->dhs[1], t->dhs[2], t->frac_soil, t->sabg_snow, t->sabg_soil};
   for (double *p : e) if (p) cudaFree(p);
   if (t->snow_top_id) cudaFree(t->snow_top_id);
+  if (t->elm_stage) cudaFree(t->elm_stage);
+  if (t->elm_snl) cudaFree(t->elm_snl);
 }
 
 // MPPThermalTBasedALM_Initialize.F90:150-813 in one call: snow mesh (nlevsno layers) + standing-water mesh (1 cell) next to the soil
@@ -271,5 +273,59 @@ static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
   CK(cudaEventRecord(h->ev1, h->stream));
   h->launches += 1;
   t->T_cur = A.T_out;                              // PostSolve: soln -> soln_prev (SOEBasePostSolve :650-668)
+  return 0;
+}
+
+
+// MPPThermalTBasedALM_Solve (src/driver/alm/MPPThermalTBasedALM_Driver.F90:150-452): ELM's raw column arrays in, tvector out
+static int thermal_elm_solve(mppgpu_soe *h, ThermalState *t, double dtime, const mppgpu_elm_thermal_columns *cols, double capr)
+{
+  if (!t->snow_mode) return fail("mppgpu_thermal_elm_solve: call mppgpu_thermal_add_snow_ssw first (the ELM configuration)");
+  if (!t->soils_set) return fail("mppgpu_thermal_elm_solve: soils must be set first");
+  if (!cols) return fail("mppgpu_thermal_elm_solve: null column arrays");
+  const void *req[] = {cols->snl, cols->z, cols->dz, cols->zi, cols->t_soisno, cols->h2osoi_liq, cols->h2osoi_ice, cols->frac_sno_eff, cols->h2osno,
+                       cols->h2osfc, cols->frac_h2osfc, cols->t_h2osfc, cols->sabg_lyr, cols->dhsdT, cols->hs_soil, cols->hs_top_snow, cols->hs_h2osfc, cols->tvector};
+  for (const void *q : req) if (!q) return fail("mppgpu_thermal_elm_solve: null column array");
+  const size_t ncol = h->ncol, nsno = t->nsno, nlev = h->nlev, nl = nsno + nlev, nrow = nl + 1;
+  cudaStream_t s = h->stream;
+  // staging layout: z, dz, t, liq, ice (ncol*nl each) | zi (ncol*(nl+1)) | sabg (ncol*(nsno+1)) | 9 per-column arrays | tvector (ncol*nrow)
+  const size_t total = 5 * ncol * nl + ncol * (nl + 1) + ncol * (nsno + 1) + 9 * ncol + ncol * nrow;
+  if (!t->elm_stage) { CK(cudaMalloc((void **)&t->elm_stage, total * 8)); CK(cudaMalloc((void **)&t->elm_snl, ncol * sizeof(int))); }
+  double *p = t->elm_stage;
+  auto up = [&](const double *src, size_t cnt) -> double * {
+    double *dst = p; p += cnt;
+    cudaMemcpyAsync(dst, src, cnt * 8, cudaMemcpyHostToDevice, s);
+    return dst;
+  };
+  ElmThermalArgs E;
+  memset(&E, 0, sizeof(E));
+  E.ncol = h->ncol; E.nlev = h->nlev; E.nsno = t->nsno; E.capr = capr;
+  E.active_col = h->has_active ? h->active.p : nullptr;
+  E.z = up(cols->z, ncol * nl); E.dz = up(cols->dz, ncol * nl); E.t_soisno = up(cols->t_soisno, ncol * nl);
+  E.h2osoi_liq = up(cols->h2osoi_liq, ncol * nl); E.h2osoi_ice = up(cols->h2osoi_ice, ncol * nl);
+  E.zi = up(cols->zi, ncol * (nl + 1)); E.sabg_lyr = up(cols->sabg_lyr, ncol * (nsno + 1));
+  E.frac_sno_eff = up(cols->frac_sno_eff, ncol); E.h2osno = up(cols->h2osno, ncol); E.h2osfc = up(cols->h2osfc, ncol);
+  E.frac_h2osfc = up(cols->frac_h2osfc, ncol); E.t_h2osfc = up(cols->t_h2osfc, ncol); E.dhsdT = up(cols->dhsdT, ncol);
+  E.hs_soil = up(cols->hs_soil, ncol); E.hs_top_snow = up(cols->hs_top_snow, ncol); E.hs_h2osfc = up(cols->hs_h2osfc, ncol);
+  E.tvector = up(cols->tvector, ncol * nrow);                      // entries the driver does not assign keep the caller's values
+  CK(cudaMemcpyAsync(t->elm_snl, cols->snl, ncol * sizeof(int), cudaMemcpyHostToDevice, s));
+  CK(cudaGetLastError());
+  E.snl = t->elm_snl;
+  // SetSolnPrevCLM + Set{R,I,B}DataFromCLM + PreStepDT (:332-441): written straight into the mailbox
+  E.T = t->T_clm; E.liq = t->liq; E.ice = t->ice; E.snow_water = t->snow_water; E.mdz = t->aux_dz; E.dist_up = t->aux_dist_up; E.dist_dn = t->aux_dist_dn;
+  E.tuning = t->tuning; E.frac = t->frac; E.nsnow = t->nsnow; E.active = t->active;
+  for (int k = 0; k < 3; ++k) { E.hs[k] = t->hs[k]; E.dhs[k] = t->dhs[k]; }
+  E.frac_soil = t->frac_soil; E.sabg_snow = t->sabg_snow; E.sabg_soil = t->sabg_soil;
+  elm_thermal_pack_kernel<<<nblk(ncol * nrow, 256), 256, 0, s>>>(E);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  t->T_cur = t->T_clm;                                               // PreStepDT
+  if (thermal_snow_step(h, t, dtime)) return 1;                      // StepDT
+  E.T_out = t->T_cur;                                                // GetSoln
+  elm_thermal_unpack_kernel<<<nblk(ncol * nrow, 256), 256, 0, s>>>(E);
+  CK(cudaGetLastError());
+  h->launches += 1;
+  CK(cudaMemcpyAsync(cols->tvector, E.tvector, ncol * nrow * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
   return 0;
 }

@@ -425,6 +425,8 @@ struct ThermalState {
   double *soil_top_dist_dn = nullptr, *hs[3] = {nullptr, nullptr, nullptr}, *dhs[3] = {nullptr, nullptr, nullptr},
          *frac_soil = nullptr, *sabg_snow = nullptr, *sabg_soil = nullptr;
   int *snow_top_id = nullptr;
+  // staging for mppgpu_thermal_elm_solve (ELM's raw column arrays); one allocation, carved up
+  double *elm_stage = nullptr; int *elm_snl = nullptr;
 };
 
 }  // namespace mpp

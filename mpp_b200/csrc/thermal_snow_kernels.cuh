@@ -280,4 +280,100 @@ thermal_snow_step_kernel(const ThermalSnowArgs A)
   }
 }
 
+// ---- MPPThermalTBasedALM_Solve (src/driver/alm/MPPThermalTBasedALM_Driver.F90:150-452) on the device -------------------------------
+// ELM's own column arrays -- Fortran (c, j) order, layer-major, j = -nlevsno+1 .. nlevgrnd (zi and tvector from -nlevsno) -- in and out;
+// the packing into the SoE mailbox (:204-330) and the unpacking of the solution (:460-505) are kernels, so nothing is packed on the CPU.
+struct ElmThermalArgs {
+  int ncol, nlev, nsno;
+  double capr;                               // mpp_varcon.F90:30
+  const int *active_col;                     // column filter (col%active and not lake / urban) or nullptr
+  const int *snl;
+  const double *z, *dz, *zi, *t_soisno, *h2osoi_liq, *h2osoi_ice;
+  const double *frac_sno_eff, *h2osno, *h2osfc, *frac_h2osfc, *t_h2osfc, *sabg_lyr, *dhsdT, *hs_soil, *hs_top_snow, *hs_h2osfc;
+  // SoE mailbox (see ThermalSnowArgs)
+  double *T, *liq, *ice, *snow_water, *mdz, *dist_up, *dist_dn, *tuning, *frac; int *nsnow, *active;
+  double *hs[3], *dhs[3], *frac_soil, *sabg_snow, *sabg_soil;
+  const double *T_out; double *tvector;
+};
+
+// one thread per (row, column), column fastest: ELM's layer-major arrays are read coalesced
+__global__ void elm_thermal_pack_kernel(const ElmThermalArgs A)
+{
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncol = A.ncol, nsno = A.nsno, nlev = A.nlev, nrow = nsno + 1 + nlev;
+  if (tid >= (long long)ncol * nrow) return;
+  const int c = (int)(tid % ncol), r = (int)(tid / ncol);
+  const bool on = (A.active_col == nullptr) || A.active_col[c] != 0;
+  const int snl = A.snl[c];
+  // ELM layer j lives at array column (j + nsno - 1) of the (-nsno+1 : nlev) arrays and at (j + nsno) of zi
+#define EL(a, j)  (a)[(long long)((j) + nsno - 1) * ncol + c]
+#define ZI(j)     A.zi[(long long)((j) + nsno) * ncol + c]
+  if (r < nsno) {                                                        // snow layer j = r - nsno + 1 (:204-240)
+    const int j = r - nsno + 1;
+    const long long idx = (long long)c * nsno + r;
+    double T = 273.15, liq = 0.0, ice = 0.0, dz = 0.0, du = 0.0, dd = 0.0, frac = 1.0, tun = 1.0, sabg = 0.0; int ns = 0, act = 0;
+    if (on && j >= snl + 1) {
+      T = EL(A.t_soisno, j); dz = EL(A.dz, j); liq = EL(A.h2osoi_liq, j); ice = EL(A.h2osoi_ice, j); ns = -snl; act = 1;
+      du = ZI(j) - EL(A.z, j); dd = EL(A.z, j) - ZI(j - 1); frac = A.frac_sno_eff[c];
+      if (j != snl + 1) sabg = A.sabg_lyr[(long long)(j + nsno - 1) * ncol + c];
+      else tun = EL(A.dz, j) / (0.5 * __dadd_rn(EL(A.z, j) - ZI(j - 1), __dmul_rn(A.capr, EL(A.z, j + 1) - ZI(j - 1))));   // no FMA contraction: bit-identical to the driver
+    }
+    A.T[idx] = T; A.liq[idx] = liq; A.ice[idx] = ice; A.snow_water[idx] = 0.0; A.mdz[idx] = dz; A.dist_up[idx] = du; A.dist_dn[idx] = dd;
+    A.frac[idx] = frac; A.tuning[idx] = tun; A.nsnow[idx] = ns; A.active[idx] = act; A.sabg_snow[idx] = sabg;
+  } else if (r == nsno) {                                                // standing surface water (:243-262) + the per-column conditions
+    const long long idx = (long long)ncol * nsno + c;
+    double T = 273.15, dz = 0.0, frac = 1.0, du = 0.0; int act = 0;
+    double frac_soil = 1.0, hs0 = 0.0, dh0 = 0.0, hs1 = 0.0, dh1 = 0.0, hs2 = 0.0, dh2 = 0.0;
+    if (on) {
+      if (snl < 0) { hs0 = A.hs_top_snow[c]; dh0 = A.dhsdT[c]; frac_soil = frac_soil - A.frac_sno_eff[c]; }     // at j == snl+1 (:229-233)
+      const double fw = A.frac_h2osfc[c];
+      if (fw > 0.0) {
+        T = A.t_h2osfc[c]; dz = 1.0e-3 * A.h2osfc[c]; act = 1; frac = fw; du = dz / 2.0;
+        frac_soil = frac_soil - fw; dh1 = A.dhsdT[c]; hs1 = A.hs_h2osfc[c];
+      }
+      hs2 = A.hs_soil[c]; dh2 = A.dhsdT[c];                              // at soil layer 1 (:322-323)
+    }
+    A.T[idx] = T; A.liq[idx] = 0.0; A.ice[idx] = 0.0; A.snow_water[idx] = 0.0; A.mdz[idx] = dz; A.dist_up[idx] = du; A.dist_dn[idx] = du;
+    A.frac[idx] = frac; A.tuning[idx] = 1.0; A.nsnow[idx] = 0; A.active[idx] = act;
+    A.hs[0][c] = hs0; A.dhs[0][c] = dh0; A.hs[1][c] = hs1; A.dhs[1][c] = dh1; A.hs[2][c] = hs2; A.dhs[2][c] = dh2; A.frac_soil[c] = frac_soil;
+  } else {                                                               // soil layer j = r - nsno (:268-327)
+    const int j = r - nsno;
+    const long long sc = (long long)c * nlev + (j - 1), idx = (long long)ncol * (nsno + 1) + sc;
+    double T = 273.15, liq = 0.0, ice = 0.0, dz = 0.0, du = 0.0, frac = 1.0, tun = 1.0, sabg = 0.0, sw = 0.0; int ns = 0, act = 0;
+    if (on) {
+      T = EL(A.t_soisno, j); dz = EL(A.dz, j); act = 1; liq = EL(A.h2osoi_liq, j); ice = EL(A.h2osoi_ice, j);
+      du = ZI(j) - EL(A.z, j);
+      if (j == 1) {
+        dz = EL(A.z, j) * 2.0; ns = -snl;
+        if (snl != 0) { sabg = A.frac_sno_eff[c] * A.sabg_lyr[(long long)(j + nsno - 1) * ncol + c]; sw = A.h2osno[c]; }
+        else tun = EL(A.dz, j) / (0.5 * __dadd_rn(EL(A.z, j) - ZI(j - 1), __dmul_rn(A.capr, EL(A.z, j + 1) - ZI(j - 1))));   // no FMA contraction: bit-identical to the driver
+      }
+    }
+    A.T[idx] = T; A.liq[idx] = liq; A.ice[idx] = ice; A.snow_water[idx] = sw; A.mdz[idx] = dz; A.dist_up[idx] = du; A.dist_dn[idx] = du;
+    A.frac[idx] = frac; A.tuning[idx] = tun; A.nsnow[idx] = ns; A.active[idx] = act; A.sabg_soil[sc] = sabg;
+  }
+}
+
+// tvector(c, j-1) = snow layer j (active layers), tvector(c, 0) = standing water (when present), tvector(c, j) = soil layer j (:460-505)
+__global__ void elm_thermal_unpack_kernel(const ElmThermalArgs A)
+{
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int ncol = A.ncol, nsno = A.nsno, nlev = A.nlev, nrow = nsno + 1 + nlev;
+  if (tid >= (long long)ncol * nrow) return;
+  const int c = (int)(tid % ncol), r = (int)(tid / ncol);
+  if (A.active_col != nullptr && A.active_col[c] == 0) return;
+  const int snl = A.snl[c];
+  if (r < nsno) {
+    const int j = r - nsno + 1;
+    if (j >= snl + 1) A.tvector[(long long)(j - 1 + nsno) * ncol + c] = A.T_out[(long long)c * nsno + r];
+  } else if (r == nsno) {
+    if (A.frac_h2osfc[c] > 0.0) A.tvector[(long long)(0 + nsno) * ncol + c] = A.T_out[(long long)ncol * nsno + c];
+  } else {
+    const int j = r - nsno;
+    A.tvector[(long long)(j + nsno) * ncol + c] = A.T_out[(long long)ncol * (nsno + 1) + (long long)c * nlev + (j - 1)];
+  }
+#undef EL
+#undef ZI
+}
+
 }  // namespace mpp

@@ -329,6 +329,34 @@ class ThermalSnow(Thermal):
             raise ValueError("soil_top_dist_dn must have ncol entries")
         check(self.L.mppgpu_thermal_add_snow_ssw(self.h, self.nlevsno, _dp(st)))
 
+    ELM_FIELDS = ("z", "dz", "zi", "t_soisno", "h2osoi_liq", "h2osoi_ice", "frac_sno_eff", "h2osno", "h2osfc", "frac_h2osfc", "t_h2osfc",
+                  "sabg_lyr", "dhsdT", "hs_soil", "hs_top_snow", "hs_h2osfc")
+
+    def elm_solve(self, dt, elm, nstep=1, capr=0.34):
+        """MPPThermalTBasedALM_Solve (MPPThermalTBasedALM_Driver.F90:150-452).  `elm`: dict of ELM's column arrays in Fortran (c, j)
+        order, i.e. numpy arrays of shape (nlayers, ncol), C-contiguous: z, dz, t_soisno, h2osoi_liq, h2osoi_ice over j = -nlevsno+1..nlev;
+        zi and tvector over j = -nlevsno..nlev; sabg_lyr over j = -nlevsno+1..1; the rest (ncol,).  `tvector` is updated in place."""
+        from ._lib import ElmThermalColumns
+        cols = ElmThermalColumns()
+        keep = []
+        for k in self.ELM_FIELDS + ("tvector",):
+            a = elm[k]
+            if a.dtype != np.float64 or not a.flags["C_CONTIGUOUS"]:
+                raise ValueError("elm_solve: %s must be a C-contiguous float64 array" % k)
+            keep.append(a)
+            setattr(cols, k, _dp(a))
+        snl = elm["snl"]
+        if snl.dtype != np.int32 or snl.size != self.ncol:
+            raise ValueError("elm_solve: snl must be int32 with ncol entries")
+        cols.snl = _ip(snl)
+        nl = self.nlevsno + self.nlev
+        want = {"z": nl, "dz": nl, "t_soisno": nl, "h2osoi_liq": nl, "h2osoi_ice": nl, "zi": nl + 1, "tvector": nl + 1, "sabg_lyr": self.nlevsno + 1}
+        for k, n in want.items():
+            if elm[k].size != n * self.ncol:
+                raise ValueError("elm_solve: %s must hold %d layers x ncol values" % (k, n))
+        check(self.L.mppgpu_thermal_elm_solve(self.h, float(dt), int(nstep), C.byref(cols), float(capr)))
+        return elm["tvector"]
+
 
 class TH(_SoE):
     """sysofeqns_th_type: Richards (ieqn 1) + enthalpy (ieqn 2) on the same columns."""

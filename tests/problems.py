@@ -436,6 +436,37 @@ def tile_snow_thermal(d, o, reps):
     return D, O
 
 
+def elm_thermal_raw_arrays(d):
+    """The same column state as ELM holds it (MPPThermalTBasedALM_Driver.F90:60-150): Fortran (c, j) arrays, here numpy (nlayers, ncol)."""
+    ncol, nlev, nsno = d["ncol"], d["nlev"], d["nlevsno"]
+    z, zi, dz = d["z"], d["zi"], d["dz1"]
+    col = lambda a: np.ascontiguousarray(a.T)
+    e = {"snl": d["snl"].astype(np.int32),
+         "z": col(np.hstack([d["snow_z"], np.tile(z, (ncol, 1))])), "dz": col(np.hstack([d["snow_dz"], np.tile(dz, (ncol, 1))])),
+         "zi": col(np.hstack([d["snow_zi"], np.tile(zi[1:], (ncol, 1))])),
+         "t_soisno": col(np.hstack([d["t_snow"], d["t_soil"]])),
+         "h2osoi_liq": col(np.hstack([d["snow_liq"], d["liq"].reshape(ncol, nlev)])), "h2osoi_ice": col(np.hstack([d["snow_ice"], d["ice"].reshape(ncol, nlev)])),
+         "sabg_lyr": col(d["sabg_lyr"]), "tvector": np.full((nsno + 1 + nlev, ncol), -999.0)}
+    for k in ("frac_sno_eff", "h2osno", "h2osfc", "frac_h2osfc", "t_h2osfc", "dhsdT", "hs_soil", "hs_top_snow", "hs_h2osfc"):
+        e[k] = np.ascontiguousarray(d[k], dtype=np.float64)
+    return e
+
+
+def unpack_elm_snow_thermal(d, o, T, tvector):
+    """MPPThermalTBasedALM_Driver.F90:460-505: SoE solution -> tvector(c, -nlevsno:nlev), here (nlayers, ncol)."""
+    ncol, nlev, nsno = d["ncol"], d["nlev"], d["nlevsno"]
+    snl = d["snl"]
+    for c in range(ncol):
+        for j in range(-nsno + 1, 1):
+            if j >= snl[c] + 1:
+                tvector[j - 1 + nsno, c] = T[c * nsno + j + nsno - 1]
+        if d["frac_h2osfc"][c] > 0.0:
+            tvector[nsno, c] = T[ncol * nsno + c]
+        for j in range(1, nlev + 1):
+            tvector[j + nsno, c] = T[ncol * (nsno + 1) + c * nlev + j - 1]
+    return tvector
+
+
 def build_elm_snow_thermal(cls, d, **kw):
     ncol, nlev, nsno = d["ncol"], d["nlev"], d["nlevsno"]
     p = cls(ncol, nlev, nsno, **kw)

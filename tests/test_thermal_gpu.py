@@ -219,3 +219,46 @@ def test_thermal_landunit_types(mpp, oracle, snow):
     # the types really take different branches: same forcing, different temperatures
     Tt = (T[-ncol * nlev:] if snow else T).reshape(ncol, nlev)
     assert np.abs(Tt[0::5].mean() - Tt[2::5].mean()) > 1e-3
+
+
+@pytest.mark.parametrize("ncol,snow,water", [(257, "mixed", "mixed"), (64, "none", "none"), (100, "all", "all")])
+def test_thermal_elm_solve_raw_arrays(mpp, oracle, ncol, snow, water):
+    """mppgpu_thermal_elm_solve: ELM's (c, j) arrays in, tvector out, against the driver's packing restated in Python
+    (pack_elm_snow_thermal / unpack_elm_snow_thermal = MPPThermalTBasedALM_Driver.F90:204-330, 460-505) around the oracle's StepDT."""
+    nlev, nsno = 15, 5
+    d = PB.elm_snow_thermal_inputs(ncol, nlev, nsno, snow=snow, water=water)
+    g = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    r = PB.build_elm_snow_thermal(oracle.OracleThermalSnow, d, nthreads=4)
+    rng = np.random.default_rng(17)
+    for step in range(2):
+        e = PB.elm_thermal_raw_arrays(d)
+        tv = g.elm_solve(1800.0, e, step + 1)
+        o = PB.pack_elm_snow_thermal(d)
+        conv, To = PB.elm_snow_thermal_step(r, o, 1800.0, step + 1)
+        tvo = PB.unpack_elm_snow_thermal(d, o, To, np.full((nsno + 1 + nlev, ncol), -999.0))
+        untouched = tvo == -999.0
+        assert np.array_equal(tv == -999.0, untouched)                       # only the entries the driver assigns change
+        assert relmax(tv[~untouched], tvo[~untouched]) < RTOL, step
+        # the packed mailbox itself is bit-identical to the driver's
+        for var, key in ((K.VAR_TUNING_FACTOR, "tuning"), (K.VAR_DZ, "dz"), (K.VAR_DIST_UP, "dist_up"), (K.VAR_FRAC, "frac"), (K.VAR_LIQ_AREAL_DEN, "liq")):
+            assert np.array_equal(g.get_data(K.AUXVAR_INTERNAL, var, 1), o[key]), key
+        assert np.array_equal(g.get_data(K.AUXVAR_BC, K.VAR_FRAC, 3, n=ncol), o["frac_soil"])
+        assert np.array_equal(g.get_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, 1, n=ncol * nsno), o["sabg_snow"])
+        _snow_advance(d, o, To, rng)
+
+
+def test_thermal_elm_solve_error_behaviour(mpp):
+    d = PB.elm_thermal_inputs(4, 15)
+    p, ids = PB.build_elm_thermal(mpp.Thermal, d)
+    d2 = PB.elm_snow_thermal_inputs(4, 15, 5)
+    e = PB.elm_thermal_raw_arrays(d2)
+    from mpp_b200._lib import ElmThermalColumns
+    import ctypes as C
+    cols = ElmThermalColumns()
+    assert p.L.mppgpu_thermal_elm_solve(p.h, 1800.0, 1, C.byref(cols), 0.34) != 0      # soil-only handle: snow / ssw equations not added
+    g = PB.build_elm_snow_thermal(mpp.ThermalSnow, d2)
+    with pytest.raises(ValueError):
+        bad = dict(e); bad["zi"] = e["z"]
+        g.elm_solve(1800.0, bad)
+    with pytest.raises(mpp.MPPError):
+        g.elm_solve(0.0, e)
