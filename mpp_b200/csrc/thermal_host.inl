@@ -282,6 +282,7 @@ static int thermal_elm_solve(mppgpu_soe *h, ThermalState *t, double dtime, const
 {
   if (!t->snow_mode) return fail("mppgpu_thermal_elm_solve: call mppgpu_thermal_add_snow_ssw first (the ELM configuration)");
   if (!t->soils_set) return fail("mppgpu_thermal_elm_solve: soils must be set first");
+  if (h->nlev < 2) return fail("mppgpu_thermal_elm_solve: the surface tuning factor reads z(c,2): at least two soil layers are needed");
   if (!cols) return fail("mppgpu_thermal_elm_solve: null column arrays");
   const void *req[] = {cols->snl, cols->z, cols->dz, cols->zi, cols->t_soisno, cols->h2osoi_liq, cols->h2osoi_ice, cols->frac_sno_eff, cols->h2osno,
                        cols->h2osfc, cols->frac_h2osfc, cols->t_h2osfc, cols->sabg_lyr, cols->dhsdT, cols->hs_soil, cols->hs_top_snow, cols->hs_h2osfc, cols->tvector};
