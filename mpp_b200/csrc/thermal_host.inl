@@ -221,7 +221,11 @@ static int thermal_snow_step(mppgpu_soe *h, ThermalState *t, double dt)
   A.snow_top_id = t->snow_top_id;
   A.T_out = (t->T_cur == t->T_clm) ? t->T_work : t->T_cur;
   CK(cudaEventRecord(h->ev0, h->stream));
-  thermal_snow_step_kernel<16><<<nblk((long long)h->ncol * 16, TH_TILE), TH_TILE, 0, h->stream>>>(A);
+  // ELM's 5 + 15 layout (and anything else that fits 8 lanes of three rows): four columns per warp; otherwise 16 lanes of two rows
+  if ((t->nsno + 2) / 3 + (h->nlev + 2) / 3 <= 8 && !t->force_two_rows)
+    thermal_snow_step3_kernel<8><<<nblk((long long)h->ncol * 8, TH_TILE), TH_TILE, 0, h->stream>>>(A);
+  else
+    thermal_snow_step_kernel<16><<<nblk((long long)h->ncol * 16, TH_TILE), TH_TILE, 0, h->stream>>>(A);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));
   h->launches += 1;

@@ -421,7 +421,7 @@ struct ThermalState {
   int *nsnow = nullptr, *active = nullptr;
   double stale_area = 1.0;
   // snow + standing-surface-water coupling (thermal_snow_kernels.cuh): mailbox arrays then hold ncol*(nsno+1+nlev) entries
-  bool snow_mode = false; int nsno = 0; size_t nall = 0;
+  bool snow_mode = false, force_two_rows = false; int nsno = 0; size_t nall = 0;
   double *soil_top_dist_dn = nullptr, *hs[3] = {nullptr, nullptr, nullptr}, *dhs[3] = {nullptr, nullptr, nullptr},
          *frac_soil = nullptr, *sabg_snow = nullptr, *sabg_soil = nullptr;
   int *snow_top_id = nullptr;

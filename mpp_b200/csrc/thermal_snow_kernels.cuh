@@ -9,7 +9,8 @@
 //   soil   coupling branches  src/mpp/ge/GoveqnThermalKSPTemperatureSoilType.F90:820-905, 1150-1190, 1232-1400
 // Unknown / mailbox ordering = the reference's SoE vector: [snow cells of all columns | ssw cells | soil cells].
 //
-// Mapping: 16 lanes per column (two columns per warp), two matrix rows per lane -- rows [0, nsno) the snow layers (top to
+// Mapping (thermal_snow_step_kernel; thermal_snow_step3_kernel below holds three rows per lane on 8 lanes and is the one ELM's
+// 5 + 15 layout runs on): 16 lanes per column (two columns per warp), two matrix rows per lane -- rows [0, nsno) the snow layers (top to
 // bottom), rows [nsno, nsno+nlev) the soil layers.  The column graph is a chain (snow - soil) with the standing-water cell
 // hanging off the top soil row: that leaf is computed by the lane that owns the top soil row and folded into it by one
 // Schur step, the chain's odd rows are eliminated in-lane and its even rows go through normalised parallel cyclic
@@ -275,6 +276,168 @@ thermal_snow_step_kernel(const ThermalSnowArgs A)
       const long long base = (long long)ncol * (nsno + 1) + (long long)col * nlev;
       if (va) A.T_out[base + ja] = xa;
       if (vb) A.T_out[base + jb] = xb;
+    }
+    if (top_lane) A.T_out[widx] = (w_rhs - w_cs * xa) * rcp(w_bb);
+  }
+}
+
+// Three chain rows per lane (a, m, b), LPC lanes per column, 32/LPC columns per warp: ELM's 5 snow + 15 soil layers fill 7 of 8 lanes
+// (snow block padded at the top to a multiple of three), four columns per warp.  The middle row of every lane is eliminated
+// in-lane first; what remains is exactly the two-rows-per-lane system of thermal_snow_step_kernel (second rows eliminated in-lane,
+// first rows by a 3-stage normalised PCR), then the middle rows are back-substituted.
+#ifndef SNOW3_MIN_BLOCKS
+#define SNOW3_MIN_BLOCKS 4
+#endif
+template <int LPC>
+__global__ void __launch_bounds__(TH_TILE, SNOW3_MIN_BLOCKS)
+thermal_snow_step3_kernel(const ThermalSnowArgs A)
+{
+  constexpr unsigned FULL = 0xffffffffu;
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int col = (int)(tid / LPC), l = (int)(tid % LPC);
+  const int nsno = A.nsno, nlev = A.S.nlev, ncol = A.S.ncol;
+  const int ns3 = (nsno + 2) / 3, pad = 3 * ns3 - nsno;
+  const bool col_ok = col < ncol;
+  const bool snow_lane = l < ns3;
+  const int s0 = 3 * l - pad;                          // snow layers s0, s0+1, s0+2 of a snow lane (negative: padding rows)
+  const int j0 = 3 * (l - ns3);                        // soil layers j0, j0+1, j0+2 of a soil lane
+  const double cnfac = A.S.cnfac, dt = A.S.dt;
+  const double area = col_ok ? A.S.area[col] : 1.0;
+  const double dd_top = col_ok ? A.soil_top_dist_dn[col] : 1.0;
+
+  const long long widx = (long long)ncol * nsno + col;
+  double H0 = 0.0, dH0 = 0.0, H1 = 0.0, dH1 = 0.0, H2 = 0.0, dH2 = 0.0, frs = 0.0, wT = 0.0, wmdz = 0.0, wfrac = 0.0;
+  int wact = 0, top_old = 0;
+  if (col_ok) {
+    H0 = A.hs[0][col]; dH0 = A.dhsdT[0][col]; H1 = A.hs[1][col]; dH1 = A.dhsdT[1][col]; H2 = A.hs[2][col]; dH2 = A.dhsdT[2][col];
+    frs = A.frac_soil[col]; top_old = A.snow_top_id[col];
+    wact = A.active[widx]; wT = A.T_in[widx]; wmdz = A.mdz[widx]; wfrac = A.frac[widx];
+  }
+  SnowRow a, m, b;
+  snow_row_clear(a); snow_row_clear(m); snow_row_clear(b);
+  bool va = false, vm = false, vb = false;             // the row exists
+  if (col_ok) {
+    if (snow_lane) {
+      double la = 0.0, ia = 0.0, ta = 1.0, lm = 0.0, im = 0.0, tm = 1.0, lb, ib, tb;
+      va = s0 >= 0; vm = s0 + 1 >= 0; vb = true;
+      if (va) snow_layer_load(A, a, s0, col, area, la, ia, ta);
+      if (vm) snow_layer_load(A, m, s0 + 1, col, area, lm, im, tm);
+      snow_layer_load(A, b, s0 + 2, col, area, lb, ib, tb);
+      if (va) snow_layer_aux(A, a, area, la, ia, ta);
+      if (vm) snow_layer_aux(A, m, area, lm, im, tm);
+      snow_layer_aux(A, b, area, lb, ib, tb);
+    } else if (j0 < nlev) {
+      SoilIn ia, im, ib;
+      const int lun = A.S.lun_type[col];
+      va = true; vm = j0 + 1 < nlev; vb = j0 + 2 < nlev;
+      soil_layer_load(A, a, ia, j0, col);
+      if (vm) soil_layer_load(A, m, im, j0 + 1, col);
+      if (vb) soil_layer_load(A, b, ib, j0 + 2, col);
+      soil_layer_aux(A, a, ia, j0, lun, area);
+      if (vm) soil_layer_aux(A, m, im, j0 + 1, lun, area);
+      if (vb) soil_layer_aux(A, b, ib, j0 + 2, lun, area);
+    }
+  }
+
+  // ---- connections: a|m and m|b in-lane, b|next lane's a ----
+  const int kin = snow_lane ? 1 : 2;
+  double u0, u1, u2, d0, d1, d2;
+  snow_connect(A, (va && vm) ? kin : 0, area, dd_top, a.T, a.tk, a.act, a.du, a.x2, a.frac, m.T, m.tk, m.act, m.x2, u0, u1, u2, d0, d1, d2);
+  a.rhs += u0; a.bb += u1; a.sup = u2; m.rhs += d0; m.bb += d1; m.sub = d2;
+  snow_connect(A, (vm && vb) ? kin : 0, area, dd_top, m.T, m.tk, m.act, m.du, m.x2, m.frac, b.T, b.tk, b.act, b.x2, u0, u1, u2, d0, d1, d2);
+  m.rhs += u0; m.bb += u1; m.sup = u2; b.rhs += d0; b.bb += d1; b.sub = d2;
+  {
+    const double nT = __shfl_down_sync(FULL, a.T, 1, LPC), ntk = __shfl_down_sync(FULL, a.tk, 1, LPC), nx2 = __shfl_down_sync(FULL, a.x2, 1, LPC);
+    const int nact = __shfl_down_sync(FULL, a.act, 1, LPC), nva = __shfl_down_sync(FULL, (int)va, 1, LPC);
+    const int kn = (l + 1 < LPC && vb && nva) ? ((l + 1 < ns3) ? 1 : (l + 1 == ns3 ? 3 : 2)) : 0;
+    snow_connect(A, kn, area, dd_top, b.T, b.tk, b.act, b.du, b.x2, b.frac, nT, ntk, nact, nx2, u0, u1, u2, d0, d1, d2);
+    b.rhs += u0; b.bb += u1; b.sup = u2;
+    const double p0 = __shfl_up_sync(FULL, d0, 1, LPC), p1 = __shfl_up_sync(FULL, d1, 1, LPC), p2 = __shfl_up_sync(FULL, d2, 1, LPC);
+    if (l > 0) { a.rhs += p0; a.bb += p1; a.sub = p2; }
+  }
+  // ---- heat flux at the top ACTIVE snow layer (UpdateBoundaryConn :680-686; :896-909, :1140-1155) ----
+  if (nsno > 0) {
+    const int bot_act = __shfl_sync(FULL, b.act, ns3 - 1, LPC), bot_nsn = __shfl_sync(FULL, b.nsn, ns3 - 1, LPC);
+    if (col_ok && snow_lane) {
+      int top = top_old;
+      if (bot_act) { top = nsno - bot_nsn; if (l == 0 && top != top_old) A.snow_top_id[col] = top; }
+      if (va && s0 == top && a.act) { a.rhs += (H0 - dH0 * a.T) * area; a.bb += -dH0 * area; }
+      if (vm && s0 + 1 == top && m.act) { m.rhs += (H0 - dH0 * m.T) * area; m.bb += -dH0 * area; }
+      if (s0 + 2 == top && b.act) { b.rhs += (H0 - dH0 * b.T) * area; b.bb += -dH0 * area; }
+    }
+  }
+  // ---- top soil row (first row of the first soil lane): heat-flux condition and the standing-water leaf ----
+  const bool top_lane = col_ok && l == ns3 && va;
+  double w_bb = 1.0, w_rhs = 0.0, w_cs = 0.0;
+  if (top_lane) {
+    double t_rhs = 0.0, t_bb = 0.0;
+    if (a.act) {
+      t_rhs = (H2 - dH2 * a.T) * frs * area;
+      t_bb = -frs * ((area == 1.0) ? dH2 : pow(dH2, area));
+    }
+    double a1s = 0.0;
+    if (wact) {
+      const bool thick = wmdz * wfrac * 1.0e3 > THIN_SFCLAYER && wfrac > THIN_SFCLAYER;
+      const double dzm = thick ? ((wmdz > THIN_SFCLAYER) ? wmdz : THIN_SFCLAYER) : THIN_SFCLAYER;
+      double hc = THIN_SFCLAYER;
+      if (dzm * wfrac * 1.0e3 > THIN_SFCLAYER && wfrac > THIN_SFCLAYER) { hc = CPLIQ * DENH2O; hc = (hc > THIN_SFCLAYER) ? hc : THIN_SFCLAYER; }
+      const double cap = hc * (area * dzm) * rcp(dt);
+      w_bb = cap - dH1 * area; w_rhs = cap * wT + (H1 - dH1 * wT) * area;
+      {
+        const double dist = 0.5 * dzm, dd = 0.5 * wmdz;
+        const double k = a.tk * TKWAT * dd * rcp(a.tk * dd);
+        const double kod = k * rcp(dist) * area;
+        const double fl = -kod * (a.T - wT);
+        w_rhs = w_rhs - cnfac * fl;
+        const double v = (1.0 - cnfac) * kod;
+        w_bb += v; w_cs = -v;
+      }
+      if (a.act) {
+        const double du = 0.5 * wmdz, dd = 0.5 * a.mdz;
+        const double half = ((du * 2.0 > 1.0e-6) ? du * 2.0 : 1.0e-6) * 0.5;
+        const double k1 = TKWAT * a.tk * (du + dd) * rcp(TKWAT * dd + a.tk * du);
+        const double fl = -k1 * (wT - a.T) * rcp(dd + half);
+        t_rhs -= wfrac * cnfac * fl * A.S.stale_area;
+        const double k2 = TKWAT * a.tk * (du + dd_top) * rcp(TKWAT * dd_top + a.tk * du);
+        const double v = wfrac * (1.0 - cnfac) * k2 * rcp(dd_top + half) * area;
+        t_bb += v; a1s = -v;
+      }
+    }
+    const double f = a1s * rcp(w_bb);
+    t_bb -= f * w_cs; t_rhs -= f * w_rhs;
+    a.rhs += t_rhs; a.bb += t_bb;
+  }
+  if (a.act) a.rhs += a.src;
+  if (m.act) m.rhs += m.src;
+  if (b.act) b.rhs += b.src;
+
+  // ---- eliminate the middle row: x_m = mf - ms x_a - mu x_b ----
+  const double rmb = rcp(m.bb);
+  const double ms = m.sub * rmb, mu = m.sup * rmb, mf = m.rhs * rmb;
+  const double a_bb = a.bb - a.sup * ms, a_sup = -a.sup * mu, a_rhs = a.rhs - a.sup * mf;
+  const double b_sub = -b.sub * ms, b_bb = b.bb - b.sub * mu, b_rhs = b.rhs - b.sub * mf;
+  // ---- two rows per lane (a', b'): second rows eliminated in-lane, first rows by normalised PCR, back-substitution ----
+  const double rbb = rcp(b_bb);
+  const double bs = b_sub * rbb, bu = b.sup * rbb, bf = b_rhs * rbb;          // x_b = bf - bs x_a(l) - bu x_a(l+1)
+  const double bs_p = __shfl_up_sync(FULL, bs, 1, LPC), bu_p = __shfl_up_sync(FULL, bu, 1, LPC), bf_p = __shfl_up_sync(FULL, bf, 1, LPC);
+  const double sub_a = (l > 0) ? a.sub : 0.0;
+  const double rB = rcp(a_bb - sub_a * bu_p - a_sup * bs);
+  const double al = (-sub_a * bs_p) * rB, ga = (-a_sup * bu) * rB, de = (a_rhs - sub_a * bf_p - a_sup * bf) * rB;
+  const double xa = thermal_pcr_unit<LPC>(al, ga, de);
+  const double xa_n = __shfl_down_sync(FULL, xa, 1, LPC);
+  const double xb = bf - bs * xa - ((l + 1 < LPC) ? bu * xa_n : 0.0);
+  const double xm = mf - ms * xa - mu * xb;
+  if (col_ok) {
+    if (snow_lane) {
+      const long long base = (long long)col * nsno + s0;
+      if (va) A.T_out[base] = xa;
+      if (vm) A.T_out[base + 1] = xm;
+      A.T_out[base + 2] = xb;
+    } else {
+      const long long base = (long long)ncol * (nsno + 1) + (long long)col * nlev + j0;
+      if (va) A.T_out[base] = xa;
+      if (vm) A.T_out[base + 1] = xm;
+      if (vb) A.T_out[base + 2] = xb;
     }
     if (top_lane) A.T_out[widx] = (w_rhs - w_cs * xa) * rcp(w_bb);
   }
