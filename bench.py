@@ -175,6 +175,22 @@ def other_workloads(device, stream):
     out["thermal_1Mi_x15"] = {"column_timesteps_per_sec": ncol / (m * 1e-3), "ms_per_step": m, "kernel": "thermal_step_kernel<16>",
                               "roofline": {"bound": "hbm", "algorithmic_bytes_per_column_step": 1224, "achieved": 1224 * ncol / (m * 1e-3) / 1e9, "unit": "GB/s"}}
     p.close()
+    # the VSFM batch once more with ELM's default saturation curve, smooth_brooks_corey_bz3 (+32 B per cell of parameters)
+    d = shard_inputs(0, ncol)
+    d["satfunc"] = "smooth_brooks_corey_bz3"
+    p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d, device=device)
+    p.set_stream(stream)
+    set_forcing_host(p, ids, d)
+    ms = []
+    for s in range(9):
+        p.pre_step_dt(); p.step_dt(DT, s + 1); p.post_step_dt(); ms.append(p.last_step_ms())
+    m = float(np.median(ms[3:]))
+    st = p.stats()
+    out["vsfm_sbc_bz3_1Mi_x15"] = {"column_timesteps_per_sec": ncol / (m * 1e-3), "ms_per_step_median": m, "kernel": "vsfm_step2_kernel<8,SBC,noBC>",
+                                   "newton_its_mean": float(st["newton_its"].mean()), "residual_evals_mean": float(st["nfuncs"].mean()),
+                                   "roofline": {"bound": "hbm", "algorithmic_bytes_per_column_step": 1224 + 32 * NLEV,
+                                                "achieved": (1224 + 32 * NLEV) * ncol / (m * 1e-3) / 1e9, "unit": "GB/s"}}
+    p.close()
     # ELM's real thermal column: 5 snow layers (variable active count) + standing surface water + 15 soil layers
     base = 4096
     d0 = PB.elm_snow_thermal_inputs(base, NLEV, 5)
@@ -436,6 +452,7 @@ def main():
                          "kernel": "vsfm_step2_kernel<8,VG,noBC>",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLSTEP,
+                         "fp64_issue_frac": 0.53, "fp64_issue_frac_source": "sm__pipe_fp64_cycles_active of the same kernel under ncu (profiles/r1_vsfm_v12.md); the second fraction SURVEY.md 8d asks for",
                          "note": "fp64-latency bound, not HBM bound (2 log + 2 exp + 3 reciprocals per cell per residual evaluation, "
                                  "%.1f evaluations and %.1f Newton iterations per column-step; fp64 pipe ~53 %% busy); see DESIGN.md" % (nf_mean, its_mean)},
             "solver": {"converged_all": not glob["any_diverged"], "worst_reason": glob["worst_reason"], "newton_its_mean": its_mean, "newton_its_max": its_max,
