@@ -326,6 +326,34 @@ MPP_HD void sat_derivs(const SatParams &sp, const SatState &s, double frac_liq, 
   }
 }
 
+// Brooks-Corey and smoothed Brooks-Corey, generic over double / d2 and branch-free (the fast VSFM kernel): one lean log and two lean
+// exp per cell whatever the regime.  With Lse = ln(Se):  regime A (pc <= pu; plain BC: -alpha pc > 1)  Lse = -lambda ln(-alpha pc);
+// regime B (SBC cubic, pu < pc < ps)  Se = 1 + dpc^2 (b2 + dpc b3), Lse = ln(Se);  saturated  Lse = 0.  kr = exp((2.5 + 2/lambda) Lse).
+// Same functions as sat_values<SATFUNC_BC / SATFUNC_SBC> (SaturationFunction.F90:900-1140), regrouped.
+template <class T>
+MPP_HD void bc_sbc_values(T sat_res, T alpha, T lam, T ps, T b2, T b3, T pc, bool Aa, bool Ab, bool Ba, bool Bb, T &sat, T &kr, T &Se)
+{
+  const T one = vbc<T>(1.0);
+  const T dpc = pc - ps;
+  const T SeB = one + dpc * dpc * (b2 + dpc * b3);
+  const T arg = vsel(Aa, Ab, -alpha * pc, vsel(Ba, Bb, SeB, one));
+  const T L = mpp_log(arg);
+  const T Lse = vsel(Aa, Ab, -lam * L, L);
+  Se = vsel(Aa, Ab, mpp_exp(Lse), vsel(Ba, Bb, SeB, one));
+  kr = mpp_exp((vbc<T>(2.5) + vbc<T>(2.0) * rcp(lam)) * Lse);
+  sat = vsel(Aa || Ba, Ab || Bb, sat_res + (one - sat_res) * Se, one);
+}
+template <class T>
+MPP_HD void bc_sbc_derivs(T sat_res, T lam, T ps, T b2, T b3, T pc, T Se, T kr, bool Aa, bool Ab, bool Ba, bool Bb, T &dsat_dP, T &dkr_dP)
+{
+  const T one = vbc<T>(1.0), zero = vbc<T>(0.0);
+  const T dpc = pc - ps;
+  const T pcs = vsel(Aa, Ab, pc, one);                                  // keep the reciprocal finite outside regime A
+  const T dSe = vsel(Aa, Ab, -lam * Se * rcp(pcs), vsel(Ba, Bb, dpc * (vbc<T>(2.0) * b2 + vbc<T>(3.0) * dpc * b3), zero));
+  dsat_dP = (one - sat_res) * dSe;
+  dkr_dP  = (vbc<T>(2.5) + vbc<T>(2.0) * rcp(lam)) * kr * rcp(Se) * dSe;   // kr carries frac_liq for BC
+}
+
 // two cells at once (the fast VSFM kernel): van Genuchten goes through the pair instantiation, the others call the scalar code twice
 template <int SATFUNC>
 MPP_HD void sat_values_pair(const SatParams &pa, const SatParams &pb, double Pa, double Pb, double fla, double flb, SatState &sa, SatState &sb)
@@ -338,8 +366,16 @@ MPP_HD void sat_values_pair(const SatParams &pa, const SatParams &pb, double Pa,
     sa.pc = pc.a; sa.sat = o.sat.a; sa.kr = o.kr.a; sa.Se = o.Se.a; sa.AA = o.pcn.a; sa.AAm = o.AAm.a; sa.L2 = o.rS.a; sa.rx = o.rx.a; sa.regime = ua ? 1 : 0;
     sb.pc = pc.b; sb.sat = o.sat.b; sb.kr = o.kr.b; sb.Se = o.Se.b; sb.AA = o.pcn.b; sb.AAm = o.AAm.b; sb.L2 = o.rS.b; sb.rx = o.rx.b; sb.regime = ub ? 1 : 0;
   } else {
-    sat_values<SATFUNC>(pa, Pa, fla, sa);
-    sat_values<SATFUNC>(pb, Pb, flb, sb);
+    const d2 pc = d2{Pa - PRESSURE_REF, Pb - PRESSURE_REF};
+    bool Aa, Ab, Ba = false, Bb = false;
+    if (SATFUNC == SATFUNC_BC) { Aa = (-pa.alpha * pc.a > 1.0); Ab = (-pb.alpha * pc.b > 1.0); }
+    else { Aa = (pc.a <= pa.pu); Ab = (pc.b <= pb.pu); Ba = !Aa && (pc.a < pa.ps); Bb = !Ab && (pc.b < pb.ps); }
+    d2 sat, kr, Se;
+    bc_sbc_values<d2>(d2{pa.sat_res, pb.sat_res}, d2{pa.alpha, pb.alpha}, d2{pa.m, pb.m}, d2{pa.ps, pb.ps}, d2{pa.b2, pb.b2}, d2{pa.b3, pb.b3},
+                      pc, Aa, Ab, Ba, Bb, sat, kr, Se);
+    if (SATFUNC == SATFUNC_BC) { kr.a = fla * kr.a; kr.b = flb * kr.b; }    // SaturationFunction.F90:987
+    sa.pc = pc.a; sa.sat = sat.a; sa.kr = kr.a; sa.Se = Se.a; sa.regime = Aa ? 1 : (Ba ? 2 : 0);
+    sb.pc = pc.b; sb.sat = sat.b; sb.kr = kr.b; sb.Se = Se.b; sb.regime = Ab ? 1 : (Bb ? 2 : 0);
   }
 }
 template <int SATFUNC>
@@ -353,8 +389,11 @@ MPP_HD void sat_derivs_pair(const SatParams &pa, const SatParams &pb, const SatS
     vg_derivs<d2>(d2{pa.sat_res, pb.sat_res}, d2{pa.alpha, pb.alpha}, d2{pa.m, pb.m}, d2{pa.n, pb.n}, sa.regime != 0, sb.regime != 0, o, ds, dk);
     dsat_a = ds.a; dkr_a = dk.a; dsat_b = ds.b; dkr_b = dk.b;
   } else {
-    sat_derivs<SATFUNC>(pa, sa, fla, dsat_a, dkr_a);
-    sat_derivs<SATFUNC>(pb, sb, flb, dsat_b, dkr_b);
+    d2 ds, dk;
+    bc_sbc_derivs<d2>(d2{pa.sat_res, pb.sat_res}, d2{pa.m, pb.m}, d2{pa.ps, pb.ps}, d2{pa.b2, pb.b2}, d2{pa.b3, pb.b3}, d2{sa.pc, sb.pc},
+                      d2{sa.Se, sb.Se}, d2{sa.kr, sb.kr}, sa.regime == 1, sb.regime == 1, sa.regime == 2, sb.regime == 2, ds, dk);
+    dsat_a = ds.a; dkr_a = dk.a; dsat_b = ds.b; dkr_b = dk.b;
+    (void)fla; (void)flb;
   }
 }
 
