@@ -701,9 +701,10 @@ MPP_HD void internal_energy_enthalpy(int itype, double P, double t_K, double den
   const double u0 = (double)4.217f * 1.e3;
   if (itype == INT_ENERGY_ENTHALPY_CONSTANT) {
     U = u0 * (t_K - 273.15); dU_dT = u0; dU_dP = 0.0;
-    H = U + P / den;
-    dH_dT = dU_dT - P / (den * den) * dden_dT;
-    dH_dP = dU_dP + 1.0 / den - P / (den * den) * dden_dP;
+    const double r = rcp(den), Pr2 = P * r * r;        // one lean reciprocal instead of four divisions
+    H = U + P * r;
+    dH_dT = dU_dT - Pr2 * dden_dT;
+    dH_dP = dU_dP + r - Pr2 * dden_dP;
     U *= FMWH2O; H *= FMWH2O; dU_dT *= FMWH2O; dH_dT *= FMWH2O; dH_dP *= FMWH2O;
   } else {
     enthalpy_ifc67(t_K - 273.15, P, H, dH_dP, dH_dT);

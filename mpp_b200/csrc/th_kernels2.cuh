@@ -213,12 +213,13 @@ th_step2_kernel(const THArgs A)
         th_rich_flux(um, dm, upw, Dqm, gfac, area, fl, mJup, mJdn, dTu, dTd);
         th_rich_flux(ue, de, upw, Dqe, gfac, area, mfl, eJup, eJdn, edTu, edTd);
         const double ku = ax.tc, kd = tcd;
-        const double kod = (ku * kd) / (dist_up * kd + dist_dn * ku);
+        const double kod = (ku * kd) * rcp(dist_up * kd + dist_dn * ku);
         const double h = (mfl <= 0.0) ? ax.hl : hld;
         const double dhT_u = (mfl < 0.0) ? ax.dhlT : 0.0, dhT_d = (mfl < 0.0) ? 0.0 : dhlTd;
         const double dhP_u = (mfl < 0.0) ? ax.dhlP : 0.0, dhP_d = (mfl < 0.0) ? 0.0 : dhlPd;
         JTT_u = edTu * h + mfl * dhT_u + (-kod * area); JTT_d = edTd * h + mfl * dhT_d + (+kod * area);
-        const double dDk_u = (kod * kod) / (ku * ku) * dist_up * ax.dtcP, dDk_d = (kod * kod) / (kd * kd) * dist_dn * dtcPd;
+        const double rku = kod * rcp(ku), rkd = kod * rcp(kd);
+        const double dDk_u = rku * rku * dist_up * ax.dtcP, dDk_d = rkd * rkd * dist_dn * dtcPd;
         const double dTud = T - Td;
         JTP_u = (-eJup) * h + mfl * dhP_u + (-dDk_u * dTud * area); JTP_d = (-eJdn) * h + mfl * dhP_d + (-dDk_d * dTud * area);
       }
@@ -321,7 +322,7 @@ th_step2_kernel(const THArgs A)
         double a1, a2, a3, a4, mfl;
         th_rich_flux(um, dm, upw, Dqm, gfac, area, fm, a1, a2, a3, a4);
         th_rich_flux(ue, de, upw, Dqe, gfac, area, mfl, a1, a2, a3, a4);
-        const double kod = (c.tc * tcd) / (dist_up * tcd + dist_dn * c.tc);
+        const double kod = (c.tc * tcd) * rcp(dist_up * tcd + dist_dn * c.tc);
         const double h = (mfl <= 0.0) ? c.hl : hld;
         fe = mfl * h + (-kod * (We - Wed) * area);
       }
