@@ -118,3 +118,33 @@ def test_th_256Ki_columns_sampled_parity(mpp, oracle):
     for k in ("pressure", "temperature", "sat"):
         a, b = out[k].reshape(ncol, nlev)[cols][same], outo[k].reshape(-1, nlev)[same]
         assert (relmax_p if k == "pressure" else relmax)(a, b) < RTOL, k
+
+
+def test_snow_thermal_1Mi_columns_uniform_state_is_a_fixed_point_and_sampled_parity(mpp, oracle):
+    """Snow + standing water + soil at bench size.  (i) With every heat flux, its derivative and the absorbed radiation set to zero, a
+    column at one uniform temperature must stay there whatever its snow / water configuration: all conduction terms vanish and each
+    row reduces to C T_new = C T_old.  (ii) The oracle on a random sample of the forced batch's own columns."""
+    base, reps, nlev, nsno = 4096, 256, 15, 5
+    d0 = PB.elm_snow_thermal_inputs(base, nlev, nsno)
+    o0 = PB.pack_elm_snow_thermal(d0)
+    d, o = PB.tile_snow_thermal(d0, o0, reps)
+    ncol = d["ncol"]
+    g = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    # (ii) forced step, sample = the first `base` columns (the tile itself: every column of the batch is one of them)
+    conv, T = PB.elm_snow_thermal_step(g, o)
+    r = PB.build_elm_snow_thermal(oracle.OracleThermalSnow, d0, nthreads=8)
+    convo, To = PB.elm_snow_thermal_step(r, o0)
+    a0, a1, a2 = ncol * nsno, ncol * (nsno + 1), base * nsno
+    act0 = o0["active"] == 1
+    Tt = np.concatenate([T[:a2], T[a0:a0 + base], T[a1:a1 + base * nlev]])
+    assert relmax(Tt[act0], To[act0]) < RTOL
+    # every replica of the tile gives the same answer: determinism across the batch
+    assert np.array_equal(T[a1:].reshape(reps, base * nlev)[0], T[a1:].reshape(reps, base * nlev)[reps - 1])
+    # (i) fixed point
+    q = dict(o)
+    act = o["active"] == 1
+    q["T"] = np.where(act, 268.0, 273.15)
+    for k in ("hs_snow", "hs_sh2o", "hs_soil", "dhsdT_snow", "dhsdT_sh2o", "dhsdT_soil", "sabg_snow", "sabg_soil"):
+        q[k] = np.zeros_like(o[k])
+    conv, T = PB.elm_snow_thermal_step(g, q)
+    assert np.max(np.abs(T[act] - 268.0)) < 1e-9
