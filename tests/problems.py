@@ -46,6 +46,38 @@ def run_celia(p, top, bot, nstep=24, dt=3600.0):
 
 
 # ---------------------------------------------------------------------------------------------------
+# vsfm_wt_dynamics -- src/driver/standalone/vsfm/vsfm_wt_dynamics_problem.F90 (no regression baseline exists for it):
+#   the Celia column (:11, :58-60, :366-369) with a hydrostatic start whose water table sits at mid-height (:435-444), a mass-rate
+#   source of 0.025 kg/s into the top cell and a constant-head Dirichlet condition at the bottom (:326-332, :462-476), 24 x 3600 s
+# ---------------------------------------------------------------------------------------------------
+def build_wt_dynamics(cls, nz=100, **kw):
+    p = cls(1, nz, **kw)
+    dz = 1.0 / nz
+    p.set_mesh(K.MESH_AGAINST_GRAVITY, np.full((1, nz), dz), np.array([1.0]))
+    top = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)
+    bot = p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS)
+    porosity, lam, alpha, perm = 0.368, 0.5, 3.4257e-4, 8.3913e-12
+    hksat = perm / 0.001002 * (1000.0 * K.GRAV) / 0.001
+    sucsat = 1.0 / (alpha * K.GRAVITY_CONSTANT)
+    full = lambda v: np.full((1, nz), v)
+    p.set_soils(full(porosity), full(hksat), full(1.0 / lam), full(sucsat), full(0.2772), "van_genuchten", K.DENSITY_TGDPB01)
+    z = dz / 2.0 + dz * np.arange(nz)
+    p.restart(101325.0 + (0.5 - z) * 997.16 * 9.80868)
+    return p, top, bot
+
+
+def run_wt_dynamics(p, top, bot, nstep=24, dt=3600.0):
+    its = []
+    for istep in range(nstep):
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, top, np.array([2.5e-5 * 1e3]))
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, bot, np.array([101325.0 + 0.5 * 997.16 * 9.80868]))
+        conv, reason = p.step_dt(dt, istep + 1)
+        assert conv, "wt_dynamics step %d did not converge (reason %d)" % (istep + 1, reason)
+        its.append(int(p.stats()["newton_its"][0]))
+    return p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, -1), p.get_data(K.AUXVAR_INTERNAL, K.VAR_LIQ_SAT, -1), its
+
+
+# ---------------------------------------------------------------------------------------------------
 # regression file format -- src/driver/standalone/util/regression.F90:76-124
 # ---------------------------------------------------------------------------------------------------
 def regression_block(name, category, data, num_cells):

@@ -577,3 +577,18 @@ def test_elm_like_batch_other_density_models(mpp, oracle, dens):
         # through the fluxes only; IFC-67 carries ~1e-13 of polynomial round-off (see the TH tests)
         assert relmax_p(a, b) < (1e-9 if dens == K.DENSITY_IFC67 else RTOL), (dens, step)
         assert relmax(out["mass"].reshape(ncol, 15)[same], outo["mass"].reshape(ncol, 15)[same]) < RTOL
+
+
+@pytest.mark.parametrize("nz", [100, 16, 30])
+def test_wt_dynamics_driver_matches_oracle(mpp, oracle, nz):
+    """src/driver/standalone/vsfm/vsfm_wt_dynamics_problem.F90 (no reference baseline): water table at mid-height, rain into the top
+    cell, constant head at the bottom; the column fills up and reaches the steady state where SNES converges at iteration 0."""
+    p, t, b = PB.build_wt_dynamics(mpp.VSFM, nz=nz)
+    o, to, bo = PB.build_wt_dynamics(oracle.OracleVSFM, nz=nz, per_column=True)
+    P, S, its = PB.run_wt_dynamics(p, t, b)
+    Po, So, itso = PB.run_wt_dynamics(o, to, bo)
+    # the last steps sit at a floating-point fixed point: whether the residual is exactly zero there (0 iterations) or one ulp off
+    # (1 iteration that changes nothing) may differ between the two implementations
+    assert its[:5] == itso[:5] and all(abs(a - c) <= 1 for a, c in zip(its, itso))
+    assert relmax_p(P, Po) < RTOL and relmax(S, So) < RTOL
+    assert S.min() > 0.9 and abs(S.max() - 1.0) < 1e-12
