@@ -171,20 +171,23 @@ int  mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, int nin, co
  * per-cell arrays are cell-ordered (c*nlev + j); `zi` has nlev+1 interfaces per column, zi(c,0) first.  nlev <= 32.  Columns filtered out by
  * mppgpu_set_mesh's col_active keep their in/out arrays and read 0 in the pure outputs (smp_l, soilp_col, qcharge, status). */
 typedef struct {
+  /* layout of the per-cell arrays marked (cells) below: 0 = cell-ordered 1-D vectors (c*nlev + j), 1 = ELM's own (c, j) Fortran arrays
+   * (column index fastest: value of column c at layer j = 1..nlev at [(j-1)*ncol + c]; pass the address of element (begc, 1)) */
+  int fortran_order;
   /* patch level, optional (npft = 0: rootr_col is an input) -- col%pfti (0-based), col%npfts, pft%active, pft%wtcol, rootr_patch(p,j), qflx_tran_veg_patch */
   int npft, max_patch_per_col;
   const int *col_pfti, *col_npfts, *pft_active; const double *pft_wtcol, *rootr_pft, *qflx_tran_veg_pft;
   /* column level */
-  double *rootr_col;                     /* ncells; input, or output when patches are given */
+  double *rootr_col;                     /* (cells); input, or output when patches are given */
   const double *qflx_tran_veg_col, *qflx_infl, *qflx_dew_snow, *qflx_dew_grnd, *qflx_sub_snow, *frac_h2osfc;   /* ncol, [mm/s] */
   const int *snl;                        /* ncol, minus the number of snow layers */
   double *qflx_drain, *zwt;              /* ncol, in/out */
-  double *h2osoi_liq, *h2osoi_ice;       /* ncells, in/out [kg/m^2] */
+  double *h2osoi_liq, *h2osoi_ice;       /* (cells), in/out [kg/m^2] */
   double *mflx_snowlyr_col;              /* ncol, in/out (zeroed) */
   const double *mflx_neg_snow_col;       /* ncol */
-  const double *mflx_drain_perched;      /* ncells */
+  const double *mflx_drain_perched;      /* ncells, always cell-ordered (ELM keeps it as mflx_drain_perched_col_1d) */
   /* outputs */
-  double *smp_l, *soilp_col;             /* ncells: matric potential [mm], soil water pressure [Pa] */
+  double *smp_l, *soilp_col;             /* (cells): matric potential [mm], soil water pressure [Pa] */
   double *qcharge;                       /* ncol */
   double *abs_mass_error;                /* ncol or NULL */
   int *iter_count, *status;              /* ncol or NULL: StepDT calls used; 1 = accepted, 0 = failed all retries (the reference would endrun) */
@@ -192,6 +195,8 @@ typedef struct {
 /* static part: interface depths zi (ncol*(nlev+1)), thicknesses dz (ncells, cell-ordered), nlevsoi, clm_varcon's watmin (0.01 mm), and the
  * ids of the six COND_MASS_RATE sources in the order infiltration, ET, dew, drainage, snow, sublimation (MPPVSFMALM_Initialize.F90:836-858) */
 int  mppgpu_vsfm_elm_set_geometry(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids);
+/* the same with ELM's (c, j) arrays: zi = address of col%zi(begc, 0) (nlev+1 layers), dz = address of col%dz(begc, 1) */
+int  mppgpu_vsfm_elm_set_geometry_f(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids);
 int  mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, mppgpu_elm_columns *cols, int *nfailed, int *nattempts);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */

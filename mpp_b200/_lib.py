@@ -19,7 +19,7 @@ class Xfer(C.Structure):
 
 class ElmColumns(C.Structure):
     """mppgpu_elm_columns (include/mppgpu.h)."""
-    _fields_ = [("npft", C.c_int), ("max_patch_per_col", C.c_int),
+    _fields_ = [("fortran_order", C.c_int), ("npft", C.c_int), ("max_patch_per_col", C.c_int),
                 ("col_pfti", c_ip), ("col_npfts", c_ip), ("pft_active", c_ip), ("pft_wtcol", c_dp), ("rootr_pft", c_dp), ("qflx_tran_veg_pft", c_dp),
                 ("rootr_col", c_dp),
                 ("qflx_tran_veg_col", c_dp), ("qflx_infl", c_dp), ("qflx_dew_snow", c_dp), ("qflx_dew_grnd", c_dp), ("qflx_sub_snow", c_dp), ("frac_h2osfc", c_dp),
@@ -53,6 +53,7 @@ _SIGS = {
     "mppgpu_thermal_add_snow_ssw": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "mppgpu_thermal_elm_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(ElmThermalColumns), C.c_double]),
     "mppgpu_vsfm_elm_set_geometry": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, c_ip]),
+    "mppgpu_vsfm_elm_set_geometry_f": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, c_ip]),
     "mppgpu_vsfm_elm_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(ElmColumns), c_ip, c_ip]),
     "mppgpu_th_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int]),
     "mppgpu_set_tolerances": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),

@@ -6,7 +6,7 @@ struct ElmState {
   int nlevsoi = 0, cond_ids[6] = {0, 0, 0, 0, 0, 0};
   double watmin = 0.01;
   size_t npft_cap = 0;
-  DevBuf<double> zi, dz;                                                               // static geometry
+  DevBuf<double> zi, dz, stage;                                                        // static geometry; staging for Fortran-order arrays
   DevBuf<double> rootr, qtran, qinfl, dews, dewg, subs, fh2osfc, qdrain, zwt, liq, ice, snowlyr, negsnow, perched;   // inputs
   DevBuf<int> snl;
   DevBuf<int> pfti, npfts, pactive; DevBuf<double> wtcol, rootr_pft, qtran_pft;         // optional patch level
@@ -23,7 +23,20 @@ static int elm_need(mppgpu_soe *h)
   return 0;
 }
 
+__global__ void transpose_from_cells_kernel(const double *__restrict__ cells, double *__restrict__ t, int ncol, int nlev)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;        // i runs over the Fortran-order table: coalesced writes
+  const long long n = (long long)ncol * nlev;
+  if (i < n) { const int j = (int)(i / ncol), c = (int)(i % ncol); t[i] = cells[(size_t)c * nlev + j]; }
+}
+
+static int elm_set_geometry(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids, bool fortran_order);
 extern "C" int mppgpu_vsfm_elm_set_geometry(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids)
+{ return elm_set_geometry(h, zi, dz, nlevsoi, watmin, cond_ids, false); }
+extern "C" int mppgpu_vsfm_elm_set_geometry_f(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids)
+{ return elm_set_geometry(h, zi, dz, nlevsoi, watmin, cond_ids, true); }
+
+static int elm_set_geometry(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids, bool fortran_order)
 {
   CHECK_H(h);
   if (elm_need(h)) return 1;
@@ -41,8 +54,21 @@ extern "C" int mppgpu_vsfm_elm_set_geometry(mppgpu_handle h, const double *zi, c
   }
   const size_t ncol = h->ncol, N = h->ncells;
   CK(e->zi.alloc(ncol * (h->nlev + 1))); CK(e->dz.alloc(N));
-  CK(cudaMemcpyAsync(e->zi.p, zi, ncol * (h->nlev + 1) * 8, cudaMemcpyHostToDevice, h->stream));
-  CK(cudaMemcpyAsync(e->dz.p, dz, N * 8, cudaMemcpyHostToDevice, h->stream));
+  if (!fortran_order) {
+    CK(cudaMemcpyAsync(e->zi.p, zi, ncol * (h->nlev + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    CK(cudaMemcpyAsync(e->dz.p, dz, N * 8, cudaMemcpyHostToDevice, h->stream));
+  } else {
+    DevBuf<double> tmp;
+    CK(tmp.alloc(ncol * (h->nlev + 1)));
+    CK(cudaMemcpyAsync(tmp.p, zi, ncol * (h->nlev + 1) * 8, cudaMemcpyHostToDevice, h->stream));
+    transpose_to_cells_kernel<<<nblk(ncol * (h->nlev + 1), 256), 256, 0, h->stream>>>(tmp.p, e->zi.p, h->ncol, h->nlev + 1);
+    CK(cudaStreamSynchronize(h->stream));
+    CK(cudaMemcpyAsync(tmp.p, dz, N * 8, cudaMemcpyHostToDevice, h->stream));
+    transpose_to_cells_kernel<<<nblk(N, 256), 256, 0, h->stream>>>(tmp.p, e->dz.p, h->ncol, h->nlev);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+  }
+  CK(e->stage.alloc(N));
   DevBuf<double> *cellb[] = {&e->rootr, &e->liq, &e->ice, &e->perched, &e->frac_ice, &e->smp_l, &e->soilp};
   for (auto b : cellb) { CK(b->alloc(N)); CK(cudaMemsetAsync(b->p, 0, N * 8, h->stream)); }    // outputs of filtered-out columns read 0
   DevBuf<double> *colb[] = {&e->qtran, &e->qinfl, &e->dews, &e->dewg, &e->subs, &e->fh2osfc, &e->qdrain, &e->zwt, &e->snowlyr, &e->negsnow,
@@ -79,6 +105,20 @@ extern "C" int mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, m
   cudaStream_t s = h->stream;
   // ---- host -> device: ELM's raw arrays ----
 #define UP(buf, src, cnt) CK(cudaMemcpyAsync((buf).p, (src), (cnt) * sizeof(*(buf).p), cudaMemcpyHostToDevice, s))
+  const bool fo = cols->fortran_order != 0;
+  // a per-cell array in ELM's (c, j) order goes through the staging buffer and a transpose into the cell order the kernels stream
+  auto up_cells = [&](DevBuf<double> &buf, const double *src) -> int {
+    if (!fo) return cudaMemcpyAsync(buf.p, src, N * 8, cudaMemcpyHostToDevice, s) != cudaSuccess;
+    if (cudaMemcpyAsync(e->stage.p, src, N * 8, cudaMemcpyHostToDevice, s) != cudaSuccess) return 1;
+    transpose_to_cells_kernel<<<nblk(N, 256), 256, 0, s>>>(e->stage.p, buf.p, h->ncol, h->nlev);
+    return cudaGetLastError() != cudaSuccess;
+  };
+  auto down_cells = [&](double *dst, DevBuf<double> &buf) -> int {
+    if (!fo) return cudaMemcpyAsync(dst, buf.p, N * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess;
+    transpose_from_cells_kernel<<<nblk(N, 256), 256, 0, s>>>(buf.p, e->stage.p, h->ncol, h->nlev);
+    if (cudaGetLastError() != cudaSuccess) return 1;
+    return cudaMemcpyAsync(dst, e->stage.p, N * 8, cudaMemcpyDeviceToHost, s) != cudaSuccess;
+  };
   if (patches) {
     const size_t np = cols->npft;
     if (e->npft_cap < np) {
@@ -88,10 +128,11 @@ extern "C" int mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, m
     UP(e->pfti, cols->col_pfti, ncol); UP(e->npfts, cols->col_npfts, ncol); UP(e->pactive, cols->pft_active, np); UP(e->wtcol, cols->pft_wtcol, np);
     UP(e->rootr_pft, cols->rootr_pft, np * h->nlev); UP(e->qtran_pft, cols->qflx_tran_veg_pft, np);
   }
-  UP(e->rootr, cols->rootr_col, N);                  // with patches only layers 1..nlevsoi are recomputed (:206-240); the rest keeps ELM's values
+  if (up_cells(e->rootr, cols->rootr_col)) return fail("mppgpu_vsfm_elm_solve: upload failed");   // with patches only layers 1..nlevsoi are recomputed (:206-240); the rest keeps ELM's values
   UP(e->qtran, cols->qflx_tran_veg_col, ncol); UP(e->qinfl, cols->qflx_infl, ncol); UP(e->dews, cols->qflx_dew_snow, ncol); UP(e->dewg, cols->qflx_dew_grnd, ncol);
   UP(e->subs, cols->qflx_sub_snow, ncol); UP(e->fh2osfc, cols->frac_h2osfc, ncol); UP(e->snl, cols->snl, ncol); UP(e->qdrain, cols->qflx_drain, ncol);
-  UP(e->zwt, cols->zwt, ncol); UP(e->liq, cols->h2osoi_liq, N); UP(e->ice, cols->h2osoi_ice, N); UP(e->snowlyr, cols->mflx_snowlyr_col, ncol);
+  UP(e->zwt, cols->zwt, ncol); UP(e->snowlyr, cols->mflx_snowlyr_col, ncol);
+  if (up_cells(e->liq, cols->h2osoi_liq) || up_cells(e->ice, cols->h2osoi_ice)) return fail("mppgpu_vsfm_elm_solve: upload failed");
   UP(e->negsnow, cols->mflx_neg_snow_col, ncol); UP(e->perched, cols->mflx_drain_perched, N);
 #undef UP
   ElmArgs E;
@@ -159,9 +200,12 @@ extern "C" int mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, m
   CK(cudaEventRecord(h->ev1, s));
   // ---- device -> host: ELM's raw arrays ----
 #define DOWN(dst, buf, cnt) CK(cudaMemcpyAsync((dst), (buf).p, (cnt) * sizeof(*(buf).p), cudaMemcpyDeviceToHost, s))
-  if (patches) DOWN(cols->rootr_col, e->rootr, N);
-  DOWN(cols->qflx_drain, e->qdrain, ncol); DOWN(cols->zwt, e->zwt, ncol); DOWN(cols->h2osoi_liq, e->liq, N); DOWN(cols->h2osoi_ice, e->ice, N);
-  DOWN(cols->mflx_snowlyr_col, e->snowlyr, ncol); DOWN(cols->smp_l, e->smp_l, N); DOWN(cols->soilp_col, e->soilp, N); DOWN(cols->qcharge, e->qcharge, ncol);
+  // (the staging buffer is reused array by array: stream order keeps transpose -> copy -> next transpose apart)
+  if (patches && down_cells(cols->rootr_col, e->rootr)) return fail("mppgpu_vsfm_elm_solve: download failed");
+  if (down_cells(cols->h2osoi_liq, e->liq) || down_cells(cols->h2osoi_ice, e->ice) || down_cells(cols->smp_l, e->smp_l) || down_cells(cols->soilp_col, e->soilp))
+    return fail("mppgpu_vsfm_elm_solve: download failed");
+  DOWN(cols->qflx_drain, e->qdrain, ncol); DOWN(cols->zwt, e->zwt, ncol);
+  DOWN(cols->mflx_snowlyr_col, e->snowlyr, ncol); DOWN(cols->qcharge, e->qcharge, ncol);
   if (cols->abs_mass_error) DOWN(cols->abs_mass_error, e->abs_err, ncol);
   if (cols->iter_count) DOWN(cols->iter_count, e->iter_count, ncol);
   std::vector<int> status(ncol);

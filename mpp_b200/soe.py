@@ -215,20 +215,27 @@ class VSFM(_SoE):
     ELM_COND_ORDER = ("infil", "et", "dew", "drain", "snow", "sublim")
     ELM_INOUT = ("rootr_col", "qflx_drain", "zwt", "h2osoi_liq", "h2osoi_ice", "mflx_snowlyr_col")
 
-    def elm_set_geometry(self, zi, dz, nlevsoi, ids, watmin=0.01):
+    def elm_set_geometry(self, zi, dz, nlevsoi, ids, watmin=0.01, fortran_order=False):
         """zi: (ncol, nlev+1) interface depths, dz: (ncol, nlev) thicknesses (ELM's col%zi(c,0:), col%dz); ids: the condition ids of
-        infiltration, ET, dew, drainage, snow, sublimation (dict as returned by the set-up, or a sequence in that order)."""
+        infiltration, ET, dew, drainage, snow, sublimation (dict as returned by the set-up, or a sequence in that order).
+        fortran_order: the arrays are ELM's own (c, j) arrays, i.e. numpy (nlev+1, ncol) / (nlev, ncol)."""
+        cid = _i32([ids[k] for k in self.ELM_COND_ORDER] if isinstance(ids, dict) else list(ids))
+        if fortran_order:
+            zi = np.ascontiguousarray(np.asarray(zi, dtype=np.float64).reshape(self.nlev + 1, self.ncol))
+            dz = np.ascontiguousarray(np.asarray(dz, dtype=np.float64).reshape(self.nlev, self.ncol))
+            check(self.L.mppgpu_vsfm_elm_set_geometry_f(self.h, _dp(zi), _dp(dz), int(nlevsoi), float(watmin), _ip(cid)))
+            return
         zi = np.ascontiguousarray(np.asarray(zi, dtype=np.float64).reshape(self.ncol, self.nlev + 1))
         dz = np.ascontiguousarray(np.asarray(dz, dtype=np.float64).reshape(self.ncol, self.nlev))
-        cid = _i32([ids[k] for k in self.ELM_COND_ORDER] if isinstance(ids, dict) else list(ids))
         check(self.L.mppgpu_vsfm_elm_set_geometry(self.h, _dp(zi), _dp(dz), int(nlevsoi), float(watmin), _ip(cid)))
 
-    def elm_solve(self, dt, st, nstep=1):
+    def elm_solve(self, dt, st, nstep=1, fortran_order=False):
         """One MPPVSFMALM_Solve.  `st`: dict of ELM's column arrays (float64 / int32, C-contiguous; cell arrays (ncol, nlev)); the in/out
         ones (ELM_INOUT) are updated in place.  Returns dict(smp_l, soilp_col, qcharge, abs_mass_error, iter_count, status, nfailed, nattempts)."""
         from ._lib import ElmColumns
         ncol, n = self.ncol, self.ncells
         cols = ElmColumns()
+        cols.fortran_order = 1 if fortran_order else 0      # rootr_col, h2osoi_liq/ice, smp_l, soilp_col as (nlev, ncol) = ELM's (c, j)
         keep = []
 
         def dptr(a, size, name):

@@ -592,3 +592,28 @@ def test_wt_dynamics_driver_matches_oracle(mpp, oracle, nz):
     assert its[:5] == itso[:5] and all(abs(a - c) <= 1 for a, c in zip(its, itso))
     assert relmax_p(P, Po) < RTOL and relmax(S, So) < RTOL
     assert S.min() > 0.9 and abs(S.max() - 1.0) < 1e-12
+
+
+def test_elm_solve_accepts_elms_own_array_order(mpp):
+    """fortran_order = 1: rootr_col, h2osoi_liq / h2osoi_ice, smp_l, soilp_col, zi, dz are ELM's (c, j) arrays (column index fastest).
+    Same kernels behind a transpose: bit-identical to the cell-ordered call."""
+    ncol, nlev = 300, 15
+    d = PB.elm_vsfm_inputs(ncol)
+    a, aids = PB.build_elm_vsfm(mpp.VSFM, d)
+    b, bids = PB.build_elm_vsfm(mpp.VSFM, d)
+    st = PB.elm_vsfm_raw_state(a, d, patches=True)
+    sf = PB.copy_state(st)
+    for k in ("rootr_col", "h2osoi_liq", "h2osoi_ice"):
+        sf[k] = np.ascontiguousarray(st[k].reshape(ncol, nlev).T)
+    a.elm_set_geometry(st["zi"], st["dz"], st["nlevsoi"], aids)
+    b.elm_set_geometry(np.ascontiguousarray(st["zi"].T), np.ascontiguousarray(st["dz"].T), st["nlevsoi"], bids, fortran_order=True)
+    for step in range(2):
+        oa = a.elm_solve(1800.0, st, step + 1)
+        ob = b.elm_solve(1800.0, sf, step + 1, fortran_order=True)
+        for k in ("rootr_col", "h2osoi_liq", "h2osoi_ice"):
+            assert np.array_equal(st[k].reshape(ncol, nlev), sf[k].reshape(nlev, ncol).T), k
+        for k in ("smp_l", "soilp_col"):
+            assert np.array_equal(oa[k].reshape(ncol, nlev), ob[k].reshape(nlev, ncol).T), k
+        for k in ("zwt", "qflx_drain"):
+            assert np.array_equal(st[k], sf[k]), k
+        assert np.array_equal(oa["status"], ob["status"])
