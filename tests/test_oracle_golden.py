@@ -255,3 +255,51 @@ def test_snow_ssw_soil_oracle_energy_budget(oracle):
             assert abs(lhs - rhs) <= 1e-9 * max(abs(lhs), abs(rhs), 1.0), (c, k, lhs, rhs)
             checked += 1
     assert checked > 0
+
+
+def test_elm_driver_restatement_agrees_with_an_independent_numpy_packing(oracle):
+    """orc_vsfm_elm_solve (the C restatement of MPPVSFMALM_Solve) against the plain SetData / StepDT / GetData sequence fed with
+    sources packed here in numpy from the same raw ELM arrays (MPPVSFMALM_Driver.F90:325-372, 404, 435-450)."""
+    import problems as PB
+    ncol, nlev, nlevsoi, dt = 80, 15, 10, 1800.0
+    d = PB.elm_vsfm_inputs(ncol)
+    a, aids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True)
+    b, bids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True)
+    st = PB.elm_vsfm_raw_state(a, d, patches=False)
+    raw = PB.copy_state(st)
+    a.elm_set_geometry(st["zi"], st["dz"], nlevsoi, aids)
+    out = a.elm_solve(dt, st)
+    assert out["nfailed"] == 0 and out["iter_count"].max() == 1
+    # --- numpy packing ---
+    conv = 1.0 * 1000.0 * 1.0e-3
+    et = np.zeros((ncol, nlev)); et[:, :nlevsoi] = -raw["qflx_tran_veg_col"][:, None] * raw["rootr_col"][:, :nlevsoi] * conv
+    nosnow = raw["snl"] >= 0
+    dew = np.where(nosnow, (raw["qflx_dew_snow"] + raw["qflx_dew_grnd"]) * (1.0 - raw["frac_h2osfc"]) * conv, 0.0)
+    sub = np.where(nosnow, -raw["qflx_sub_snow"] * (1.0 - raw["frac_h2osfc"]) * conv, 0.0)
+    drain = np.zeros((ncol, nlev)); qd_new = raw["qflx_drain"].copy()
+    zi, dz = raw["zi"], raw["dz"]
+    for c in range(ncol):
+        if raw["qflx_drain"][c] > 0.0:
+            hits = np.nonzero(raw["zwt"][c] <= zi[c, 1:])[0]
+            jwt = max((hits[0] + 1) - 1 if hits.size else nlev, 1)
+            js = np.arange(jwt, nlev + 1)
+            ql = raw["qflx_drain"][c] * dz[c, js - 1] / dz[c, js - 1].sum()
+            ql = np.minimum(ql, (raw["h2osoi_liq"][c, js - 1] - 0.01) / dt)
+            drain[c, js - 1] = -ql * conv
+            qd_new[c] = ql.sum()
+    drain += raw["mflx_drain_perched"]
+    snow = raw["mflx_snowlyr_col"] + raw["mflx_neg_snow_col"]
+    fliq = 1.0 - raw["h2osoi_ice"] / (raw["h2osoi_liq"] + raw["h2osoi_ice"])
+    for name, val in (("infil", raw["qflx_infl"] * conv), ("et", et.reshape(-1)), ("dew", dew), ("drain", drain.reshape(-1)), ("snow", snow), ("sublim", sub)):
+        b.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, bids[name], val)
+    b.set_data(K.AUXVAR_INTERNAL, K.VAR_FRAC_LIQ_SAT, 1, fliq.reshape(-1))
+    b.pre_step_dt(); conv_b, reason = b.step_dt(dt, 1); b.post_step_dt()
+    assert conv_b
+    P = b.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1)
+    mass = b.get_data(K.AUXVAR_INTERNAL, K.VAR_MASS, 1).reshape(ncol, nlev)
+    smp = b.get_data(K.AUXVAR_INTERNAL, K.VAR_SOIL_MATRIX_POT, 1)
+    # summation order of the drained thickness differs (numpy pairwise vs the driver's running sum): 1e-13, not bitwise
+    assert np.max(np.abs(out["soilp_col"] - P) / np.maximum(np.abs(P), 1e4)) < 1e-12
+    assert np.max(np.abs(out["smp_l"] - smp * 1000.0) / np.maximum(np.abs(smp * 1000.0), 1e3)) < 1e-11
+    assert np.max(np.abs(st["h2osoi_liq"] + st["h2osoi_ice"] - mass) / mass) < 1e-12
+    assert np.max(np.abs(st["qflx_drain"] - qd_new)) < 1e-18 + 1e-12 * np.max(qd_new)
