@@ -453,7 +453,7 @@ def main():
                          "kernel": "vsfm_step2_kernel<8,VG,noBC>",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)" if peaks else "fallback 6650 GB/s",
                          "algorithmic_bytes_per_column_step": ALG_BYTES_PER_COLSTEP,
-                         "fp64_issue_frac": 0.53, "fp64_issue_frac_source": "sm__pipe_fp64_cycles_active of the same kernel under ncu (profiles/r1_vsfm_v12.md); the second fraction SURVEY.md 8d asks for",
+                         "fp64_issue_frac": 0.53, "fp64_issue_frac_source": "sm__pipe_fp64_cycles_active of the same kernel under ncu (profiles/r1_vsfm_v13.md); the second fraction SURVEY.md 8d asks for",
                          "note": "fp64-latency bound, not HBM bound (2 log + 2 exp + 3 reciprocals per cell per residual evaluation, "
                                  "%.1f evaluations and %.1f Newton iterations per column-step; fp64 pipe ~53 %% busy); see DESIGN.md" % (nf_mean, its_mean)},
             "solver": {"converged_all": not glob["any_diverged"], "worst_reason": glob["worst_reason"], "newton_its_mean": its_mean, "newton_its_max": its_max,
