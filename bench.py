@@ -361,11 +361,15 @@ def main():
     l0 = p.launch_count()
     sampler = ClockSampler(local_rank)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     ev0.record(stream)
+    marks[0].record(stream)
     for s in range(args.steps):
         step(args.warmup + s + 1)
+        marks[s + 1].record(stream)                  # per-step times (no synchronisation): shows which steps carried a slow column
     ev1.record(stream)
     barrier()
+    per_step_ms = [round(marks[i].elapsed_time(marks[i + 1]), 3) for i in range(args.steps)]
     clocks = sampler.stop()
     ms = ev0.elapsed_time(ev1)
     launches = p.launch_count() - l0
@@ -458,6 +462,7 @@ def main():
                                  "%.1f evaluations and %.1f Newton iterations per column-step; fp64 pipe ~53 %% busy); see DESIGN.md" % (nf_mean, its_mean)},
             "solver": {"converged_all": not glob["any_diverged"], "worst_reason": glob["worst_reason"], "newton_its_mean": its_mean, "newton_its_max": its_max,
                        "residual_evals_mean": nf_mean, "max_abs_mass_error_kg": float(maxs[0]), "last_step_kernel_ms": last_kernel_ms,
+                       "ms_per_step_all": per_step_ms,
                        "columns_failed_last_step": int(nfailed[0]), "columns_with_dt_cuts_last_step": int(nfailed[1]),
                        "global_reductions_last_step": glob,
                        "note": "the reference algorithm at its default tolerances cuts dt / fails on a handful of the 4 Mi synthetic columns; "
