@@ -197,6 +197,7 @@ typedef struct {
 int  mppgpu_vsfm_elm_set_geometry(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids);
 /* the same with ELM's (c, j) arrays: zi = address of col%zi(begc, 0) (nlev+1 layers), dz = address of col%dz(begc, 1) */
 int  mppgpu_vsfm_elm_set_geometry_f(mppgpu_handle h, const double *zi, const double *dz, int nlevsoi, double watmin, const int *cond_ids);
+/* After the call mppgpu_vsfm_mass_balance / mppgpu_reduction_buffer_device describe the whole solve (retries included). */
 int  mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, mppgpu_elm_columns *cols, int *nfailed, int *nattempts);
 
 /* ---- diagnostics ------------------------------------------------------------------------------ */

@@ -196,7 +196,16 @@ extern "C" int mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, m
   }
   // ---- PostStepDT (:935): soln_prev_clm = soln_prev ----
   h->x_committed = h->x_current;
-  h->nblocks_last = nblocks;
+  {
+    // the handle's reductions for the whole solve (mppgpu_vsfm_mass_balance, mppgpu_reduction_buffer_device)
+    const int cb = nblk(ncol, 256);
+    elm_column_partials_kernel<<<cb, 256, 0, s>>>(h->ncol, dtime, h->has_active ? h->active.p : nullptr, e->mass_beg.p, h->col_mass.p, e->tot_flux.p,
+                                                 e->abs_err.p, e->status.p, h->stat_its.p, h->stat_reason.p, h->stat_cuts.p, h->block_partials.p);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    VsfmArgs R; memset(&R, 0, sizeof(R)); R.x_out = h->x_current;
+    if (vsfm_finish_step(h, R, cb)) return 1;
+  }
   CK(cudaEventRecord(h->ev1, s));
   // ---- device -> host: ELM's raw arrays ----
 #define DOWN(dst, buf, cnt) CK(cudaMemcpyAsync((dst), (buf).p, (cnt) * sizeof(*(buf).p), cudaMemcpyDeviceToHost, s))

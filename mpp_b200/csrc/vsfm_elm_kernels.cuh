@@ -198,4 +198,34 @@ __global__ void elm_decide_kernel(const ElmArgs A)
   }
 }
 
+// Per-block partials of the handle's nine reductions (sums: mass before / after, sources * dt, boundary exchange; maxima: |mass error|,
+// Newton iterations, any column failed, dt cuts; worst SNES reason) after an elm_solve, from the per-column arrays -- same
+// [nblocks][9] layout as the step kernels write, folded by reduce_partials_kernel, so mppgpu_vsfm_mass_balance and the NCCL
+// gather of parallel.py see the whole MPPVSFMALM_Solve (retries included), not its last launch.
+__global__ void elm_column_partials_kernel(int ncol, double dtime, const int *active, const double *mass_beg, const double *col_mass, const double *tot_flux,
+                                           const double *abs_err, const int *status, const int *stat_its, const int *stat_reason, const int *stat_cuts,
+                                           double *partials)
+{
+  __shared__ double sh[9][256];
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  double v[9];
+  for (int k = 0; k < 8; ++k) v[k] = 0.0;
+  v[8] = 2147483647.0;
+  if (c < ncol && (active == nullptr || active[c] != 0)) {
+    v[0] = mass_beg[c]; v[1] = col_mass[c]; v[2] = tot_flux[c] * dtime; v[4] = abs_err[c]; v[5] = (double)stat_its[c];
+    v[6] = status[c] ? 0.0 : 1.0; v[7] = (double)stat_cuts[c]; v[8] = (double)stat_reason[c];
+  }
+  for (int k = 0; k < 9; ++k) sh[k][threadIdx.x] = v[k];
+  __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+    if ((int)threadIdx.x < s) {
+      for (int k = 0; k < 4; ++k) sh[k][threadIdx.x] += sh[k][threadIdx.x + s];
+      for (int k = 4; k < 8; ++k) sh[k][threadIdx.x] = fmax(sh[k][threadIdx.x], sh[k][threadIdx.x + s]);
+      sh[8][threadIdx.x] = fmin(sh[8][threadIdx.x], sh[8][threadIdx.x + s]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) for (int k = 0; k < 9; ++k) partials[(size_t)blockIdx.x * 9 + k] = sh[k][0];
+}
+
 }  // namespace mpp

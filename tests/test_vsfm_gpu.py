@@ -441,6 +441,13 @@ def test_elm_solve_raw_arrays_match_oracle(mpp, oracle, patches, satfunc):
         _elm_compare(st_g, st_o, og, oo, easy, tol=RTOL if step == 0 else 10 * RTOL)
         assert np.all(st_g["mflx_snowlyr_col"] == 0.0)
         assert np.max(og["abs_mass_error"][og["status"] == 1]) < 1e-5
+        # the handle's reductions describe the whole solve (what the NCCL gather of parallel.py ships)
+        sums, maxs = g.mass_balance(1800.0)
+        assert abs(sums[1] - (st_g["h2osoi_liq"] + st_g["h2osoi_ice"]).sum()) <= 1e-9 * sums[1]
+        if og["nfailed"] == 0:                       # (a column that failed every retry keeps whatever its last accepted attempt left)
+            assert abs(sums[0] - sums[1] + sums[2]) <= 1e-5 * ncol
+        assert abs(maxs[0] - og["abs_mass_error"].max()) <= 1e-18
+        assert int(maxs[2]) == (1 if og["nfailed"] else 0)
         # the drainage actually withdrawn never exceeds what was asked for
         # next step: ELM carries its state on; the GPU side continues from ITS OWN arrays only where both agree
         for s_ in (st_g, st_o):
