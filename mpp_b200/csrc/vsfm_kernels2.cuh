@@ -220,7 +220,6 @@ vsfm_step2_kernel(const VsfmArgs A)
         if (m1) v1[k] = __ldg(p + (percell ? 1 : 0));
       }
     }
-#pragma unroll
     double sa_ = 0.0, sb_ = 0.0;
 #pragma unroll
     for (int k = 0; k < MAX_SS; ++k) { sa_ += v0[k] * RFMW; sb_ += v1[k] * RFMW; src_kg += v0[k] + v1[k]; }
