@@ -200,6 +200,15 @@ int  mppgpu_vsfm_elm_set_geometry_f(mppgpu_handle h, const double *zi, const dou
 /* After the call mppgpu_vsfm_mass_balance / mppgpu_reduction_buffer_device describe the whole solve (retries included). */
 int  mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, mppgpu_elm_columns *cols, int *nfailed, int *nattempts);
 
+/* ---- host arrays ------------------------------------------------------------------------------ */
+/* Page-lock a host array the caller owns for the rest of the run (ELM's column arrays are allocated once:
+ * clm_instMod / ColumnDataType), so that every later copy of it by this library (mppgpu_set_data, mppgpu_get_data,
+ * mppgpu_vsfm_coupled_step, mppgpu_*_elm_solve) is a direct PCIe DMA instead of a staged pageable copy.  A host model
+ * written in Fortran needs no CUDA runtime binding for this.  Unregister before the array is freed.  Optional: every
+ * entry point accepts pageable memory. */
+int  mppgpu_host_register(void *ptr, long long nbytes);
+int  mppgpu_host_unregister(void *ptr);
+
 /* ---- diagnostics ------------------------------------------------------------------------------ */
 /* per-column Newton iterations, SNES reason, dt cuts, residual evaluations of the last StepDT (any may be NULL) */
 int  mppgpu_get_column_stats(mppgpu_handle h, int *newton_its, int *reasons, int *dt_cuts, int *nfuncs);

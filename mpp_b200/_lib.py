@@ -73,6 +73,8 @@ _SIGS = {
     "mppgpu_get_column_stats": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_ip]),
     "mppgpu_vsfm_mass_balance": (C.c_int, [C.c_void_p, C.c_double, c_dp, c_dp]),
     "mppgpu_reduction_buffer_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mppgpu_host_register": (C.c_int, [C.c_void_p, C.c_longlong]),
+    "mppgpu_host_unregister": (C.c_int, [C.c_void_p]),
     "mppgpu_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),
     "mppgpu_last_step_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mppgpu_eval": (C.c_int, [C.c_void_p, C.c_double, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),

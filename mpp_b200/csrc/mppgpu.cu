@@ -878,6 +878,20 @@ extern "C" int mppgpu_vsfm_mass_balance(mppgpu_handle h, double dt, double sums[
 extern "C" int mppgpu_reduction_buffer_device(mppgpu_handle h, double **d_buf)
 { CHECK_H(h); if (!d_buf) return fail("null"); *d_buf = h->red_out.p; return 0; }
 
+extern "C" int mppgpu_host_register(void *ptr, long long nbytes)
+{
+  if (!ptr || nbytes <= 0) return fail("mppgpu_host_register: null pointer or non-positive size");
+  const cudaError_t e = cudaHostRegister(ptr, (size_t)nbytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail("mppgpu_host_register: %s", cudaGetErrorString(e)); }   // not sticky: clear it
+  return 0;
+}
+extern "C" int mppgpu_host_unregister(void *ptr)
+{
+  if (!ptr) return fail("mppgpu_host_unregister: null pointer");
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { (void)cudaGetLastError(); return fail("mppgpu_host_unregister: %s", cudaGetErrorString(e)); }
+  return 0;
+}
 extern "C" int mppgpu_launch_count(mppgpu_handle h, long long *n) { CHECK_H(h); if (n) *n = h->launches; return 0; }
 extern "C" int mppgpu_last_step_ms(mppgpu_handle h, float *ms)
 {

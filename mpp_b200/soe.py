@@ -31,6 +31,18 @@ def _ip(a):
     return a.ctypes.data_as(c_ip)
 
 
+def host_register(a):
+    """mppgpu_host_register: page-lock a numpy array the caller keeps for the run (copies of it become direct DMA)."""
+    if not a.flags["C_CONTIGUOUS"] or a.nbytes == 0:
+        raise ValueError("host_register: a non-empty C-contiguous array is required")
+    check(lib().mppgpu_host_register(C.c_void_p(a.ctypes.data), int(a.nbytes)))
+    return a
+
+
+def host_unregister(a):
+    check(lib().mppgpu_host_unregister(C.c_void_p(a.ctypes.data)))
+
+
 def _table(a, ncol, nlev):
     """(ncol, nlev) array -> Fortran column-major flat buffer t[j*ncol + c]."""
     a = np.asarray(a, dtype=np.float64)
@@ -229,9 +241,10 @@ class VSFM(_SoE):
         dz = np.ascontiguousarray(np.asarray(dz, dtype=np.float64).reshape(self.ncol, self.nlev))
         check(self.L.mppgpu_vsfm_elm_set_geometry(self.h, _dp(zi), _dp(dz), int(nlevsoi), float(watmin), _ip(cid)))
 
-    def elm_solve(self, dt, st, nstep=1, fortran_order=False):
+    def elm_solve(self, dt, st, nstep=1, fortran_order=False, out=None):
         """One MPPVSFMALM_Solve.  `st`: dict of ELM's column arrays (float64 / int32, C-contiguous; cell arrays (ncol, nlev)); the in/out
-        ones (ELM_INOUT) are updated in place.  Returns dict(smp_l, soilp_col, qcharge, abs_mass_error, iter_count, status, nfailed, nattempts)."""
+        ones (ELM_INOUT) are updated in place.  Returns dict(smp_l, soilp_col, qcharge, abs_mass_error, iter_count, status, nfailed, nattempts);
+        pass a previous result as `out` to write into the same (possibly page-locked) arrays again."""
         from ._lib import ElmColumns
         ncol, n = self.ncol, self.ncells
         cols = ElmColumns()
@@ -262,11 +275,12 @@ class VSFM(_SoE):
         for k in ("rootr_col", "h2osoi_liq", "h2osoi_ice", "mflx_drain_perched"):
             setattr(cols, k, dptr(st[k], n, k))
         cols.snl = iptr(st["snl"], ncol, "snl")
-        out = {"smp_l": np.zeros(n), "soilp_col": np.zeros(n), "qcharge": np.zeros(ncol), "abs_mass_error": np.zeros(ncol),
-               "iter_count": np.zeros(ncol, dtype=np.int32), "status": np.zeros(ncol, dtype=np.int32)}
-        for k in ("smp_l", "soilp_col", "qcharge", "abs_mass_error"):
-            setattr(cols, k, _dp(out[k]))
-        cols.iter_count, cols.status = _ip(out["iter_count"]), _ip(out["status"])
+        if out is None:
+            out = {"smp_l": np.zeros(n), "soilp_col": np.zeros(n), "qcharge": np.zeros(ncol), "abs_mass_error": np.zeros(ncol),
+                   "iter_count": np.zeros(ncol, dtype=np.int32), "status": np.zeros(ncol, dtype=np.int32)}
+        for k, size in (("smp_l", n), ("soilp_col", n), ("qcharge", ncol), ("abs_mass_error", ncol)):
+            setattr(cols, k, dptr(out[k], size, k))
+        cols.iter_count, cols.status = iptr(out["iter_count"], ncol, "iter_count"), iptr(out["status"], ncol, "status")
         nf, na = C.c_int(), C.c_int()
         check(self.L.mppgpu_vsfm_elm_solve(self.h, float(dt), int(nstep), C.byref(cols), C.byref(nf), C.byref(na)))
         out["nfailed"], out["nattempts"] = nf.value, na.value

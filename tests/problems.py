@@ -235,6 +235,20 @@ def copy_state(st):
     return {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in st.items()}
 
 
+def page_aligned_copy(a, page=4096):
+    """A copy of `a` that owns whole pages (what a host model's large allocations look like), for mppgpu_host_register."""
+    nb = (a.nbytes + page - 1) // page * page
+    raw = np.empty(nb + page, dtype=np.uint8)
+    off = (-raw.ctypes.data) % page
+    out = raw[off:off + a.nbytes].view(a.dtype).reshape(a.shape)
+    out[...] = a
+    return out
+
+
+def page_aligned_state(st):
+    return {k: (page_aligned_copy(v) if isinstance(v, np.ndarray) and v.nbytes else v) for k, v in st.items()}
+
+
 # ---------------------------------------------------------------------------------------------------
 # thermal_mms (1-D steady state, KSP path) -- src/driver/standalone/thermal/thermal_mms_problem.F90
 #   + thermal_mms_steady_state_problem_1D.F90; baseline regression_tests/thermal/thermal_mms.regression.baseline

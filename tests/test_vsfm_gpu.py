@@ -624,3 +624,41 @@ def test_elm_solve_accepts_elms_own_array_order(mpp):
         for k in ("zwt", "qflx_drain"):
             assert np.array_equal(st[k], sf[k]), k
         assert np.array_equal(oa["status"], ob["status"])
+
+
+def test_elm_solve_with_page_locked_host_arrays(mpp):
+    """mppgpu_host_register: the caller's arrays page-locked in place (what a host model does once at start-up).  Same results bit
+    for bit as with pageable arrays; registering twice / unregistering an unknown pointer is an error that leaves the library usable."""
+    ncol = 300
+    d = PB.elm_vsfm_inputs(ncol)
+    a, aids = PB.build_elm_vsfm(mpp.VSFM, d)
+    b, bids = PB.build_elm_vsfm(mpp.VSFM, d)
+    st = PB.elm_vsfm_raw_state(a, d, patches=True)
+    sp = PB.page_aligned_state(st)
+    a.elm_set_geometry(st["zi"], st["dz"], st["nlevsoi"], aids)
+    b.elm_set_geometry(sp["zi"], sp["dz"], sp["nlevsoi"], bids)
+    pinned = [v for v in sp.values() if isinstance(v, np.ndarray) and v.nbytes]
+    for v in pinned:
+        mpp.host_register(v)
+    with pytest.raises(mpp.MPPError):
+        mpp.host_register(pinned[0])
+    ob = None
+    for step in range(2):
+        oa = a.elm_solve(1800.0, st, step + 1)
+        if ob is None:
+            ob = PB.page_aligned_state(b.elm_solve(1800.0, sp, step + 1))
+            outs = [v for v in ob.values() if isinstance(v, np.ndarray)]
+            for v in outs:
+                mpp.host_register(v)
+        else:
+            ob = b.elm_solve(1800.0, sp, step + 1, out=ob)
+        for k in ("h2osoi_liq", "h2osoi_ice", "zwt", "qflx_drain", "mflx_drain_perched"):
+            assert np.array_equal(st[k], sp[k]), k
+        for k in ("smp_l", "soilp_col", "qcharge", "abs_mass_error", "iter_count", "status"):
+            assert np.array_equal(oa[k], ob[k]), k
+    for v in pinned + outs:
+        mpp.host_unregister(v)
+    with pytest.raises(mpp.MPPError):
+        mpp.host_unregister(pinned[0])
+    oa = a.elm_solve(1800.0, st, 3)                      # a failed (un)register leaves no stale CUDA error behind
+    assert oa["nattempts"] >= 1

@@ -42,6 +42,37 @@ elif mode == "elm":
         t0 = time.time(); out = p.elm_solve(1800.0, st, s + 1); wall = time.time() - t0
         print("elm_solve ncol", ncol, "device ms %.2f wall ms %.1f attempts %d nfailed %d max its %d" % (p.last_step_ms(), wall * 1e3, out["nattempts"], out["nfailed"], out["iter_count"].max()),
               "col-steps/s device %.3e e2e %.3e" % (ncol / (p.last_step_ms() * 1e-3), ncol / wall))
+elif mode == "elmhost":
+    import torch
+    d = bench.shard_inputs(0, ncol)
+    p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
+    st = PB.elm_vsfm_raw_state(p, d, patches=True)
+    p.elm_set_geometry(st["zi"], st["dz"], st["nlevsoi"], ids)
+    p.set_step_budget(2000)
+    o = p.elm_solve(1800.0, st, 1)
+    nbytes = sum(v.nbytes for v in list(st.values()) + list(o.values()) if isinstance(v, np.ndarray))
+    print("bytes of all state + output arrays %.1f MB, npft %d" % (nbytes / 1e6, st["pft_wtcol"].size))
+    x = torch.empty(ncol * 15, dtype=torch.float64).pin_memory(); g = torch.empty_like(x, device="cuda")
+    for name, f in (("h2d", lambda: g.copy_(x, non_blocking=True)), ("d2h", lambda: x.copy_(g, non_blocking=True))):
+        f(); torch.cuda.synchronize(); t0 = time.time()
+        for _ in range(5):
+            f()
+        torch.cuda.synchronize(); print("raw pinned %s %.1f GB/s" % (name, 5 * x.nbytes / (time.time() - t0) / 1e9))
+    def run(tag, S, O):
+        for s in range(3):
+            t0 = time.time(); p.elm_solve(1800.0, S, s + 2, out=O); w = time.time() - t0
+            print(tag, "wall ms %.1f device ms %.2f" % (w * 1e3, p.last_step_ms()))
+    run("pageable", st, o)
+    sp, op = PB.page_aligned_state(st), PB.page_aligned_state(o)
+    lk = [v for v in list(sp.values()) + list(op.values()) if isinstance(v, np.ndarray) and v.nbytes]
+    for v in lk:
+        mpp_b200.host_register(v)
+    run("host_register", sp, op)
+    for v in lk:
+        mpp_b200.host_unregister(v)
+    pin = lambda S: {k: (torch.from_numpy(v).pin_memory().numpy() if isinstance(v, np.ndarray) and v.nbytes else v) for k, v in S.items()}
+    keep = (pin(st), pin(o))
+    run("torch pin_memory", *keep)
 elif mode == "snow":
     base = 4096
     d0 = PB.elm_snow_thermal_inputs(base, 15, 5)
