@@ -82,6 +82,15 @@ module MPPGpuBinding
        import :: c_int, c_ptr
        type(c_ptr), value :: h
      end function
+     integer(c_int) function mppgpu_host_register(ptr, nbytes) bind(C, name="mppgpu_host_register")
+       import :: c_int, c_ptr, c_long_long
+       type(c_ptr), value          :: ptr
+       integer(c_long_long), value :: nbytes
+     end function
+     integer(c_int) function mppgpu_host_unregister(ptr) bind(C, name="mppgpu_host_unregister")
+       import :: c_int, c_ptr
+       type(c_ptr), value :: ptr
+     end function
      type(c_ptr) function mppgpu_last_error() bind(C, name="mppgpu_last_error")
        import :: c_ptr
      end function
@@ -89,5 +98,5 @@ module MPPGpuBinding
 
   public :: mppgpu_create, mppgpu_set_mesh, mppgpu_add_condition, mppgpu_vsfm_set_soils, mppgpu_thermal_add_snow_ssw, mppgpu_set_tolerances, &
             mppgpu_restart, mppgpu_set_data, mppgpu_get_data, mppgpu_pre_step_dt, mppgpu_step_dt, mppgpu_post_step_dt, &
-            mppgpu_destroy, mppgpu_last_error
+            mppgpu_destroy, mppgpu_last_error, mppgpu_host_register, mppgpu_host_unregister
 end module MPPGpuBinding
