@@ -224,8 +224,7 @@ extern "C" int mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, m
   cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
   int nf = 0;
   for (size_t c = 0; c < ncol; ++c) {
-    const bool on = true;
-    if (on && !status[c]) nf++;
+    if (!status[c]) nf++;
     if (cols->status) cols->status[c] = status[c];
   }
   if (h->has_active) {   // filtered-out columns are not failures
