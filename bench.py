@@ -205,6 +205,21 @@ def other_workloads(device, stream):
     out["thermal_snow_ssw_soil_1Mi_x21"] = {"column_timesteps_per_sec": ncol / (m * 1e-3), "ms_per_step": m, "kernel": "thermal_snow_step3_kernel<8>",
                                             "roofline": {"bound": "hbm", "algorithmic_bytes_per_column_step": 2356,
                                                          "achieved": 2356 * ncol / (m * 1e-3) / 1e9, "unit": "GB/s"}}
+    # the whole MPPThermalTBasedALM_Solve on the same columns with ELM's (c, j) HOST arrays, page-locked in place once
+    e0 = PB.elm_thermal_raw_arrays(d0)
+    reps = ncol // base
+    e = PB.page_aligned_state({k: (np.tile(v, (1, reps)) if v.ndim == 2 else np.tile(v, reps)) for k, v in e0.items()})
+    for v in e.values():
+        mpp_b200.host_register(v)
+    wall, dms = [], []
+    for s in range(4):
+        t0 = time.perf_counter(); p.elm_solve(DT, e, s + 20); wall.append(time.perf_counter() - t0); dms.append(p.last_step_ms())
+    for v in e.values():
+        mpp_b200.host_unregister(v)
+    out["thermal_snow_ssw_soil_1Mi_x21"]["elm_solve_host_arrays_page_locked"] = {
+        "column_timesteps_per_sec": ncol / float(np.median(wall[1:])), "ms_per_solve": [round(w * 1e3, 2) for w in wall],
+        "host_bytes_per_solve": int(sum(v.nbytes for v in e.values())),
+        "api": "mppgpu_thermal_elm_solve: elm_thermal_pack_kernel + thermal_snow_step3_kernel + elm_thermal_unpack_kernel between the copies"}
     p.close()
     # MPPVSFMALM_Solve with ELM's raw column arrays: packing, StepDT, per-column retry loop, unpacking on the device.
     # Synthetic forcing is not state-aware (ELM would cut infiltration into a saturated column), so a column may fail every retry;
