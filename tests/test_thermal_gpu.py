@@ -247,6 +247,25 @@ def test_thermal_elm_solve_raw_arrays(mpp, oracle, ncol, snow, water):
         _snow_advance(d, o, To, rng)
 
 
+def test_thermal_elm_solve_page_locked_arrays(mpp):
+    """The caller's arrays page-locked in place with mppgpu_host_register: same tvector bit for bit."""
+    d = PB.elm_snow_thermal_inputs(257, 15, 5)
+    a = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    b = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    e = PB.elm_thermal_raw_arrays(d)
+    el = PB.page_aligned_state(e)
+    for v in el.values():
+        mpp.host_register(v)
+    for step in range(2):
+        ta = a.elm_solve(1800.0, e, step + 1).copy()
+        tb = b.elm_solve(1800.0, el, step + 1)
+        assert np.array_equal(ta, tb)
+        e["t_soisno"][...] = ta[1:]; el["t_soisno"][...] = tb[1:]
+        e["t_soisno"][ta[1:] == -999.0] = 270.0; el["t_soisno"][tb[1:] == -999.0] = 270.0
+    for v in el.values():
+        mpp.host_unregister(v)
+
+
 def test_thermal_elm_solve_error_behaviour(mpp):
     d = PB.elm_thermal_inputs(4, 15)
     p, ids = PB.build_elm_thermal(mpp.Thermal, d)
