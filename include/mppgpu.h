@@ -205,7 +205,8 @@ int  mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, mppgpu_elm_
  * clm_instMod / ColumnDataType), so that every later copy of it by this library (mppgpu_set_data, mppgpu_get_data,
  * mppgpu_vsfm_coupled_step, mppgpu_*_elm_solve) is a direct PCIe DMA instead of a staged pageable copy.  A host model
  * written in Fortran needs no CUDA runtime binding for this.  Unregister before the array is freed.  Optional: every
- * entry point accepts pageable memory. */
+ * entry point accepts pageable memory.  Registering a range twice (or two small arrays that share a page) is refused by
+ * the CUDA driver and reported as an error; the library stays usable. */
 int  mppgpu_host_register(void *ptr, long long nbytes);
 int  mppgpu_host_unregister(void *ptr);
 
