@@ -131,6 +131,10 @@ int  mppgpu_set_tolerances(mppgpu_handle h, double atol, double rtol, double sto
  * evaluations inside one StepDT gives up exactly like one that ran out of dt cuts: converged = 0, reason
  * SNES_DIVERGED_FUNCTION_COUNT (-2), solution left at the last converged sub-step. */
 int  mppgpu_set_step_budget(mppgpu_handle h, int max_residual_evaluations);
+/* NOT in the reference (scheduling only, results are identical either way; VSFM, nlev <= 32).  mode 1 (default): the step kernel
+ * visits the columns grouped by the number of residual evaluations their previous StepDT needed, most expensive first, so that
+ * the four columns a warp advances finish together; mode 0: batch order. */
+int  mppgpu_set_column_ordering(mppgpu_handle h, int mode);
 /* VSFM/thermal: x has ncells entries (pressure or temperature); TH: 2*ncells, [P(0..N-1) | T(0..N-1)] */
 int  mppgpu_restart(mppgpu_handle h, const double *x, int n);
 
@@ -221,6 +225,21 @@ int  mppgpu_get_column_stats(mppgpu_handle h, int *newton_its, int *reasons, int
  * multi-GPU driver can all-reduce them with NCCL without a host round trip. */
 int  mppgpu_vsfm_mass_balance(mppgpu_handle h, double dt, double sums[4], double maxs[4]);
 int  mppgpu_reduction_buffer_device(mppgpu_handle h, double **d_buf);
+
+/* ---- global reductions over the ranks of a column-sharded batch ------------------
+ * The reference keeps the mass bookkeeping of MPPVSFMALM_Driver.F90:124-133, 556-601, 845-898 per MPI rank; with the batch
+ * sharded by column over the GPUs of one box these calls give the global figures: ONE ncclAllGather of the 9 doubles above
+ * per rank per step on the handle's stream, folded on the device in rank order.  NCCL is loaded with dlopen by
+ * mppgpu_comm_unique_id / mppgpu_comm_init (no link-time dependency).  Usage from an MPI host model: rank 0 calls
+ * mppgpu_comm_unique_id, MPI_Bcast of the MPPGPU_COMM_ID_BYTES bytes, every rank calls mppgpu_comm_init(h, nranks, rank, id)
+ * once per handle; then after every StepDT every rank calls mppgpu_global_mass_balance (collective; blocks until the result
+ * is on the host) or mppgpu_global_reduce_async (collective; only queues the work, a later mppgpu_global_mass_balance returns
+ * it).  nranks = 1 needs no id and no NCCL.  worst_reason is the minimum SNESConvergedReason over all columns of all ranks. */
+#define MPPGPU_COMM_ID_BYTES 128
+int  mppgpu_comm_unique_id(void *id128);
+int  mppgpu_comm_init(mppgpu_handle h, int nranks, int rank, const void *id128);
+int  mppgpu_global_reduce_async(mppgpu_handle h);
+int  mppgpu_global_mass_balance(mppgpu_handle h, double sums[4], double maxs[4], int *worst_reason);
 /* launches made by the library since creation, and device-time of the last StepDT kernel(s) in ms */
 int  mppgpu_launch_count(mppgpu_handle h, long long *n);
 int  mppgpu_last_step_ms(mppgpu_handle h, float *ms);

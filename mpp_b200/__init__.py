@@ -4,6 +4,6 @@ The product is the CUDA library libmppgpu.so (mpp_b200/csrc, C ABI in include/mp
 thin Python mirror of the reference's sysofeqns interface used by the tests and the benchmark.
 """
 from . import constants  # noqa: F401
-from .soe import VSFM, Thermal, ThermalSnow, TH, MPPError, host_register, host_unregister  # noqa: F401
+from .soe import VSFM, Thermal, ThermalSnow, TH, MPPError, host_register, host_unregister, comm_unique_id  # noqa: F401
 
-__all__ = ["constants", "VSFM", "Thermal", "ThermalSnow", "TH", "MPPError", "host_register", "host_unregister"]
+__all__ = ["constants", "VSFM", "Thermal", "ThermalSnow", "TH", "MPPError", "host_register", "host_unregister", "comm_unique_id"]

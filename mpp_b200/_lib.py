@@ -58,6 +58,7 @@ _SIGS = {
     "mppgpu_th_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int]),
     "mppgpu_set_tolerances": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
     "mppgpu_set_step_budget": (C.c_int, [C.c_void_p, C.c_int]),
+    "mppgpu_set_column_ordering": (C.c_int, [C.c_void_p, C.c_int]),
     "mppgpu_restart": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
     "mppgpu_set_data": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_dp, C.c_int]),
     "mppgpu_set_idata": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_ip, C.c_int]),
@@ -73,6 +74,10 @@ _SIGS = {
     "mppgpu_get_column_stats": (C.c_int, [C.c_void_p, c_ip, c_ip, c_ip, c_ip]),
     "mppgpu_vsfm_mass_balance": (C.c_int, [C.c_void_p, C.c_double, c_dp, c_dp]),
     "mppgpu_reduction_buffer_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "mppgpu_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "mppgpu_comm_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "mppgpu_global_reduce_async": (C.c_int, [C.c_void_p]),
+    "mppgpu_global_mass_balance": (C.c_int, [C.c_void_p, c_dp, c_dp, c_ip]),
     "mppgpu_host_register": (C.c_int, [C.c_void_p, C.c_longlong]),
     "mppgpu_host_unregister": (C.c_int, [C.c_void_p]),
     "mppgpu_launch_count": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong)]),

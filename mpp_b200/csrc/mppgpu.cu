@@ -87,13 +87,18 @@ struct mppgpu_soe {
   DevBuf<int> stat_its, stat_reason, stat_cuts, stat_nf;
   DevBuf<double> col_mass, col_err, col_src, block_partials, red_out, red_scratch; DevBuf<unsigned int> red_counter;
   double *h_red = nullptr;     // pinned mirror of red_out (9 doubles)
+  // launch order of the step kernel (vsfm_kernels.cuh "launch order"): built after every StepDT from its per-column cost
+  DevBuf<int> order, order_counts; bool order_valid = false; int order_chunks = 0; long long order_per = 0; int ordering = 1;
   int nblocks_last = 0;
   bool result_pending = false;
   // ---- thermal / TH state lives in their own structs ----
   ThermalState *thermal = nullptr;
   struct ElmState *elm = nullptr;          // mppgpu_vsfm_elm_solve (vsfm_elm_host.inl)
   THState *th = nullptr;
+  struct CommState *comm = nullptr; bool comm_pending = false;   // comm_host.inl
 };
+static inline bool &c_pending(mppgpu_soe *h) { return h->comm_pending; }
+static void comm_destroy(struct CommState *c);
 
 // host-side pieces of the thermal / TH systems (thermal_host.inl, th_host.inl)
 static int thermal_create(ThermalState *t, int ncol, int nlev, cudaStream_t s);
@@ -273,6 +278,7 @@ extern "C" int mppgpu_destroy(mppgpu_handle h)
   if (h->thermal) { thermal_destroy(h->thermal); delete h->thermal; }
   if (h->th) { th_destroy(h->th); delete h->th; }
   if (h->elm) elm_destroy(h->elm);
+  if (h->comm) comm_destroy(h->comm);
   if (h->h_red) cudaFreeHost(h->h_red);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
@@ -480,6 +486,14 @@ extern "C" int mppgpu_set_step_budget(mppgpu_handle h, int max_residual_evaluati
   return 0;
 }
 
+extern "C" int mppgpu_set_column_ordering(mppgpu_handle h, int mode)
+{
+  CHECK_H(h);
+  if (mode != 0 && mode != 1) return fail("mppgpu_set_column_ordering: mode must be 0 (batch order) or 1 (by the previous step's cost)");
+  h->ordering = mode; h->order_valid = false;
+  return 0;
+}
+
 extern "C" int mppgpu_restart(mppgpu_handle h, const double *x, int n)
 {
   CHECK_H(h);
@@ -488,7 +502,7 @@ extern "C" int mppgpu_restart(mppgpu_handle h, const double *x, int n)
     if ((size_t)n != h->ncells) return fail("VSFMMPPRestart: size(data_1d) /= ncells_local (%d vs %zu)", n, h->ncells);
     // soln, soln_prev and soln_prev_clm all take the restart vector (MultiPhysicsProbVSFM.F90:675-686)
     CK(cudaMemcpyAsync(h->xA.p, x, h->ncells * 8, cudaMemcpyHostToDevice, h->stream));
-    h->x_committed = h->xA.p; h->x_current = h->xA.p;
+    h->x_committed = h->xA.p; h->x_current = h->xA.p; h->order_valid = false;
     if (h->mesh_set && h->soils_set) {
       VsfmArgs A;
       vsfm_fill_args(h, A, 1.0);
@@ -682,6 +696,7 @@ static void vsfm_offset_args(VsfmArgs &A, int nlev, long long col0, int n, long 
   A.col_mass += col0; A.col_err += col0; A.col_src += col0;
   A.block_partials += block0 * 9;
   if (A.t_done) A.t_done += col0;
+  if (A.order) A.order += col0;
   if (A.retry_mask) { A.retry_mask += col0; A.dt_col += col0; A.rtol_col += col0; A.stol_col += col0; A.x_redo += c; }
   A.ncol = n;
 }
@@ -730,6 +745,27 @@ static int vsfm_prepare_step(mppgpu_soe *h, double dt, VsfmArgs &A)
   return 0;
 }
 
+// Build the launch order of columns [col0, col0 + n) for the NEXT StepDT from the cost (residual evaluations) of the one that has just
+// been queued on `s`: three small kernels (count, scan, stable scatter), range-local indices at order[col0 ...].
+static int vsfm_build_order(mppgpu_soe *h, long long col0, int n, cudaStream_t s)
+{
+  if (!h->ordering || h->nlev > 32) return 0;
+  if (h->order.n < (size_t)h->ncol) CK(h->order.alloc(h->ncol));
+  const int nb = nblk(n, ORDER_BLOCK);
+  if (col0 % ORDER_BLOCK) return fail("vsfm_build_order: ranges must start at a multiple of %d columns", ORDER_BLOCK);
+  const size_t c0 = (size_t)(col0 / ORDER_BLOCK) * ORDER_BUCKETS;                      // disjoint scratch per range
+  const size_t need = (size_t)(nblk(h->ncol, ORDER_BLOCK) + 1) * ORDER_BUCKETS;
+  if (h->order_counts.n < need) { CK(cudaStreamSynchronize(h->stream)); CK(h->order_counts.alloc(need)); }
+  int *counts = h->order_counts.p + c0;
+  if (c0 + (size_t)nb * ORDER_BUCKETS > h->order_counts.n) return fail("vsfm_build_order: scratch overflow");
+  order_count_kernel<<<nb, ORDER_BLOCK, 0, s>>>(h->stat_nf.p + col0, n, counts);
+  order_scan_kernel<<<1, 1024, 0, s>>>(counts, nb * ORDER_BUCKETS);
+  order_scatter_kernel<<<nb, ORDER_BLOCK, 0, s>>>(h->stat_nf.p + col0, n, counts, h->order.p + col0);
+  CK(cudaGetLastError());
+  h->launches += 3;
+  return 0;
+}
+
 static int vsfm_finish_step(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
 {
   reduce_partials_kernel<<<nblocks < REDUCE_BLOCKS ? 1 : REDUCE_BLOCKS, 256, 0, h->stream>>>(h->block_partials.p, nblocks, h->red_scratch.p, h->red_counter.p, h->red_out.p);
@@ -750,7 +786,10 @@ static int vsfm_step(mppgpu_soe *h, double dt)
   if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
   A.block_partials = h->block_partials.p;
   CK(cudaEventRecord(h->ev0, h->stream));
+  A.order = (h->order_valid && h->order_chunks == 1) ? h->order.p : nullptr;
   if (vsfm_launch_range(h, A, 0, h->ncol, 0, h->stream)) return 1;
+  if (vsfm_build_order(h, 0, h->ncol, h->stream)) return 1;
+  h->order_valid = (h->ordering != 0 && h->nlev <= 32); h->order_chunks = 1; h->order_per = h->ncol;
   if (vsfm_finish_step(h, A, nblocks)) return 1;
   CK(cudaEventRecord(h->ev1, h->stream));
   return 0;
@@ -837,14 +876,17 @@ extern "C" int mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, i
       CK(cudaMemcpyAsync(f.dev + col0 * f.per_col, f.host + col0 * f.per_col, (size_t)n * f.per_col * 8, cudaMemcpyHostToDevice, h->copy_in));
     CK(cudaEventRecord(h->ev_in[k], h->copy_in));
     CK(cudaStreamWaitEvent(h->stream, h->ev_in[k], 0));
+    A.order = (h->order_valid && h->order_per == per && h->order_chunks == nchunks) ? h->order.p : nullptr;
     if (vsfm_launch_range(h, A, col0, n, block0, h->stream)) return 1;
     CK(cudaEventRecord(h->ev_comp[k], h->stream));
+    if (vsfm_build_order(h, col0, n, h->stream)) return 1;
     CK(cudaStreamWaitEvent(h->copy_out, h->ev_comp[k], 0));
     for (const Field &f : fout)
       CK(cudaMemcpyAsync(f.host + col0 * f.per_col, f.dev + col0 * f.per_col, (size_t)n * f.per_col * 8, cudaMemcpyDeviceToHost, h->copy_out));
     block0 += vsfm_blocks_for(h, n);
   }
   CK(cudaEventRecord(h->ev_out_done, h->copy_out));
+  h->order_valid = (h->ordering != 0 && h->nlev <= 32); h->order_chunks = nchunks; h->order_per = per;
   if (vsfm_finish_step(h, A, (int)total_blocks)) return 1;
   CK(cudaEventRecord(h->ev1, h->stream));
   CK(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));          // later work on the handle's stream sees the host arrays complete
@@ -949,6 +991,7 @@ extern "C" int mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const 
   return th_set_soils(h, h->th, watsat, hksat, bsw, sucsat, residual_sat, csol, tkdry, satfunc_type, density_type, int_energy_enthalpy_type);
 }
 
+#include "comm_host.inl"
 #include "thermal_host.inl"
 #include "vsfm_elm_host.inl"
 #include "th_host.inl"

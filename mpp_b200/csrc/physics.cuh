@@ -49,11 +49,17 @@ namespace mpp {
   /* 9..18 exp: c2..c11 */ \
   0x1.0000000000001p-1, 0x1.5555555555556p-3, 0x1.5555555553d63p-5, 0x1.11111111109b3p-7, 0x1.6c16c1788bd90p-10, \
   0x1.a01a01a7c41d5p-13, 0x1.a019b90d2ae7ap-16, 0x1.71de0dae63bb3p-19, 0x1.289185613a3d6p-22, 0x1.af38a9b0ec855p-26, \
-  /* 19..21 1/ln2, ln2 split for exp (hi has 11 trailing zero bits) */ 1.4426950408889634, 0.6931471805598903, 5.497923018708371e-14 }
+  /* 19..21 1/ln2, ln2 split for exp (hi has 11 trailing zero bits) */ 1.4426950408889634, 0.6931471805598903, 5.497923018708371e-14, \
+  /* 22..27 table log: Taylor coefficients of log1p(r) / r - 1 */ -0.5, 1.0 / 3.0, -0.25, 0.2, -1.0 / 6.0, 1.0 / 7.0, \
+  /* 28,29 table log: ln2 split */ MPP_LOG_LN2_HI, MPP_LOG_LN2_LO, \
+  /* 30..32 table exp: 128/ln2, ln2/128 split */ MPP_EXP_INVLN2N, MPP_EXP_LN2N_HI, MPP_EXP_LN2N_LO, \
+  /* 33..36 table exp: 1/2!, 1/3!, 1/4!, 1/5! */ 0.5, 1.0 / 6.0, 1.0 / 24.0, 1.0 / 120.0, \
+  /* 37 round-to-integer magic 1.5 * 2^52 */ 6755399441055744.0 }
+#include "math_tables.inc"
 #ifdef __CUDACC__
-static __constant__ double mpp_cmath_dev[22] = MPP_CMATH_TABLE;
+static __constant__ double mpp_cmath_dev[38] = MPP_CMATH_TABLE;
 #endif
-static const double mpp_cmath_host[22] = MPP_CMATH_TABLE;
+static const double mpp_cmath_host[38] = MPP_CMATH_TABLE;
 #ifdef __CUDA_ARCH__
 #define MPPC(i) mpp_cmath_dev[i]
 #else
@@ -140,7 +146,7 @@ MPP_HD void log_reduce(double x, double &f, double &dk)
 MPP_HD void log_reduce(d2 x, d2 &f, d2 &dk) { log_reduce(x.a, f.a, dk.a); log_reduce(x.b, f.b, dk.b); }
 
 // natural logarithm of positive, finite, normal doubles
-template <class T> MPP_HD T mpp_log(T x)
+template <class T> MPP_HD T mpp_log_poly(T x)
 {
   T f, dk;
   log_reduce(x, f, dk);
@@ -171,7 +177,7 @@ MPP_HD double exp_scale(double fn)
 MPP_HD d2 exp_scale(d2 fn) { return d2{exp_scale(fn.a), exp_scale(fn.b)}; }
 
 // exponential; the argument is clamped to [-708, 708] (results stay normal and finite)
-template <class T> MPP_HD T mpp_exp(T x)
+template <class T> MPP_HD T mpp_exp_poly(T x)
 {
   x = exp_clamp(x);
   const T magic = vbc<T>(6755399441055744.0);
@@ -188,6 +194,101 @@ template <class T> MPP_HD T mpp_exp(T x)
   const T e = vfma(r2, q, r) + vbc<T>(1.0);
   return e * exp_scale(fn);
 }
+
+// ------------------------------------------------------------------------------------------------
+// Table-driven log / exp (round 2).  The polynomial versions above cost 28 / 18 fp64 instructions and a full-precision
+// reciprocal inside the log; the step kernels are bound by fp64 issue and by the length of exactly these dependent chains
+// (profiles/r1_vsfm_v13.md), and each cell evaluation needs two of each.  With a 128-entry table (tools/gen_math_tables.py):
+//   log x:  x = 2^k z, z in [0.6875, 1.375); interval i = top 7 mantissa bits of z; r = z invc_i - 1 (one exact-product FMA,
+//           |r| <= 2^-8); log x = k ln2 + logc_i + log1p(r), log1p by its Taylor series through r^7 (truncation < 2^-59 |r|);
+//           logc_i = -log(invc_i) for the STORED invc_i, so the identity is exact.  12 fp64 instructions, no reciprocal.
+//   exp x:  k = round(128 x / ln2), r = x - k ln2/128 (|r| <= ln2/256), exp x = 2^(k>>7) T[k & 127] (1 + r + r^2/2 + ... + r^5/120)
+//           (truncation < 2^-60).  10 fp64 instructions.
+// The tables (3 KB) sit in global memory and are read through the read-only L1 path; lanes index them independently.
+// Accuracy against libm: < 1.5 ulp over the ranges the soil curves produce (tests/test_physics_host.py).
+// ------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+static __device__ const double mpp_log_tab_dev[256] = MPP_LOG_TABLE;
+static __device__ const double mpp_exp_tab_dev[128] = MPP_EXP_TABLE;
+#endif
+static const double mpp_log_tab_host[256] = MPP_LOG_TABLE;
+static const double mpp_exp_tab_host[128] = MPP_EXP_TABLE;
+
+MPP_HD void log_tab_reduce(double x, double &r, double &w)
+{
+  int hi; unsigned lo;
+  mpp_split(x, hi, lo);
+  const int tmp = hi - 0x3fe60000;
+  const int i = (tmp >> 13) & 127;
+  const int k = tmp >> 20;                                     // arithmetic shift: floor
+  const double z = mpp_join(hi - (tmp & (int)0xfff00000), lo);
+#ifdef __CUDA_ARCH__
+  const double2 t = __ldg(reinterpret_cast<const double2 *>(mpp_log_tab_dev) + i);
+  const double invc = t.x, logc = t.y;
+#else
+  const double invc = mpp_log_tab_host[2 * i], logc = mpp_log_tab_host[2 * i + 1];
+#endif
+  r = fma(z, invc, -1.0);
+  w = fma((double)k, MPPC(28), logc);                          // exact: ln2_hi has 21 trailing zero bits, |k| < 2^11
+  w = fma((double)k, MPPC(29), w);
+}
+MPP_HD void log_tab_reduce(d2 x, d2 &r, d2 &w) { log_tab_reduce(x.a, r.a, w.a); log_tab_reduce(x.b, r.b, w.b); }
+
+// natural logarithm of positive, finite, normal doubles
+template <class T> MPP_HD T mpp_log_tab(T x)
+{
+  T r, w;
+  log_tab_reduce(x, r, w);
+  const T r2 = r * r;
+  const T q01 = vfma(r, vbc<T>(MPPC(23)), vbc<T>(MPPC(22)));
+  const T q23 = vfma(r, vbc<T>(MPPC(25)), vbc<T>(MPPC(24)));
+  const T q45 = vfma(r, vbc<T>(MPPC(27)), vbc<T>(MPPC(26)));
+  T t = vfma(r2, q45, q23);
+  t = vfma(r2, t, q01);
+  return w + vfma(r2, t, r);
+}
+
+MPP_HD double exp_tab_scale(double fn)
+{
+  int hi; unsigned lo;
+  mpp_split(fn, hi, lo);                                       // fn = 1.5 * 2^52 + round(128 x / ln2): the low word holds the integer k
+  const int k = (int)lo;
+#ifdef __CUDA_ARCH__
+  const double T = __ldg(mpp_exp_tab_dev + (k & 127));
+#else
+  const double T = mpp_exp_tab_host[k & 127];
+#endif
+  int th; unsigned tl;
+  mpp_split(T, th, tl);
+  return mpp_join(th + ((k >> 7) << 20), tl);                  // 2^(k >> 7) T[k & 127]; stays normal for |x| <= 708
+}
+MPP_HD d2 exp_tab_scale(d2 fn) { return d2{exp_tab_scale(fn.a), exp_tab_scale(fn.b)}; }
+
+// exponential; the argument is clamped to [-708, 708] (results stay normal and finite)
+template <class T> MPP_HD T mpp_exp_tab(T x)
+{
+  x = exp_clamp(x);
+  const T magic = vbc<T>(MPPC(37));
+  const T fn = vfma(x, vbc<T>(MPPC(30)), magic);
+  const T kd = fn - magic;
+  T r = vfma(-kd, vbc<T>(MPPC(31)), x);                        // exact: ln2/128_hi has 24 trailing zero bits, |k| < 2^18
+  r = vfma(-kd, vbc<T>(MPPC(32)), r);
+  const T s = exp_tab_scale(fn);
+  const T r2 = r * r;
+  const T q1 = vfma(r, vbc<T>(MPPC(34)), vbc<T>(MPPC(33)));
+  const T q2 = vfma(r, vbc<T>(MPPC(36)), vbc<T>(MPPC(35)));
+  const T t = vfma(r2, q2, q1);
+  const T p = vfma(r2, t, r);
+  return vfma(s, p, s);
+}
+
+#ifndef MPP_POLY_MATH
+template <class T> MPP_HD T mpp_log(T x) { return mpp_log_tab(x); }
+template <class T> MPP_HD T mpp_exp(T x) { return mpp_exp_tab(x); }
+#else
+template <class T> MPP_HD T mpp_log(T x) { return mpp_log_poly(x); }
+template <class T> MPP_HD T mpp_exp(T x) { return mpp_exp_poly(x); }
+#endif
 
 // MultiPhysicsProbConstants.F90:199-202, mpp_varcon.F90:12-28
 constexpr double PRESSURE_REF     = 101325.0;

@@ -172,6 +172,7 @@ vsfm_step2_kernel(const VsfmArgs A)
   const int tid  = blockIdx.x * blockDim.x + threadIdx.x;
   int col = tid / LPC;
   if (RETRY) col = (col < A.nretry) ? A.retry_list[col] : A.ncol;
+  else if (A.order) col = (col < A.ncol) ? A.order[col] : A.ncol;
   const int l    = tid % LPC;                        // lane within the column; owns layers 2l and 2l+1
   const int lane = threadIdx.x & 31;
   const int nlev = A.nlev;

@@ -3,10 +3,10 @@
 Soil columns never interact in the hot path (vertical-only discretisation; the reference's Jacobian is block diagonal
 per column, MeshType.F90:509-530), so the data path needs no collective at all.  What the reference keeps per MPI rank
 and a batch driver wants globally are the mass-balance sums and the convergence flags of MPPVSFMALM_Driver.F90:556-601,
-845-898.  Every StepDT leaves them in a 9-double device buffer owned by the library
-(mppgpu_reduction_buffer_device: 4 sums, 4 maxima, worst SNES reason); `GlobalReductions.step()` gathers the 9 doubles
-of every rank with ONE NCCL all-gather on the library's stream and folds them on the device.  torch.distributed is
-plumbing only: rendezvous, the communicator and the stream.
+845-898.  The collective itself lives behind the C ABI (mppgpu_comm_init / mppgpu_global_reduce_async /
+mppgpu_global_mass_balance: one ncclAllGather of 9 doubles per rank on the library's stream, folded on the device), so a
+Fortran + MPI host model reaches it exactly as this module does; what is left here is the rendezvous -- getting rank 0's
+NCCL unique id to every rank -- and, for the CPU test-suite, the same fold under gloo.
 """
 import torch
 import torch.distributed as dist
@@ -22,7 +22,8 @@ def shard_range(ncol_total, rank, world):
 
 
 def fold(gathered):
-    """(world, 9) per-rank reduction buffers -> (9,) global: sums add, maxima take the max, the SNES reason the minimum."""
+    """(world, 9) per-rank reduction buffers -> (9,) global: sums add, maxima take the max, the SNES reason the minimum
+    (the host restatement of fold_reductions_kernel, used by the gloo tests)."""
     out = torch.empty(NRED, dtype=gathered.dtype, device=gathered.device)
     out[0:4] = gathered[:, 0:4].sum(dim=0)
     out[4:8] = gathered[:, 4:8].max(dim=0).values
@@ -30,19 +31,33 @@ def fold(gathered):
     return out
 
 
-def device_view(ptr, n, device):
-    """torch view of `n` doubles at raw device pointer `ptr` (no copy, no ownership)."""
-    class _V:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
-    return torch.as_tensor(_V(), device=device)
+def rendezvous_unique_id(make_id, group=None):
+    """Rank 0 calls `make_id()` (mpp_b200.comm_unique_id); every rank returns the same 128 bytes.  Uses whatever
+    torch.distributed backend is initialised (an MPI host model would MPI_Bcast instead)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return make_id()
+    box = [make_id() if dist.get_rank(group) == 0 else None]
+    dist.broadcast_object_list(box, src=0, group=group)
+    return box[0]
+
+
+def init_comm(p, group=None):
+    """Attach the library's NCCL communicator to solver handle `p` (one per handle); returns (rank, world)."""
+    import mpp_b200
+    if dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    else:
+        rank, world = 0, 1
+    uid = rendezvous_unique_id(mpp_b200.comm_unique_id, group) if world > 1 else None
+    p.comm_init(world, rank, uid)
+    return rank, world
 
 
 class GlobalReductions:
-    """Per-step global mass-balance / convergence reductions of one solver handle."""
+    """Host-side mirror of the library's global reduction for tensors that do not live in a solver handle (the gloo tests of the
+    CPU suite): all-gather of the (9,) local buffer + `fold`."""
 
     def __init__(self, local, group=None):
-        """`local`: (9,) float64 tensor holding this rank's reduction buffer (the library's device buffer on a GPU,
-        any CPU tensor under gloo)."""
         self.local = local
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -50,7 +65,6 @@ class GlobalReductions:
         self.result = torch.empty(NRED, dtype=local.dtype, device=local.device)
 
     def step(self):
-        """One collective: all ranks end up with the folded (9,) result (asynchronous on the current stream)."""
         if self.world == 1:
             self.result.copy_(self.local)
         else:

@@ -106,6 +106,10 @@ class _SoE:
         """Optional give-up budget per column per StepDT (not in the reference; 0 = unlimited): see include/mppgpu.h."""
         check(self.L.mppgpu_set_step_budget(self.h, int(max_residual_evaluations)))
 
+    def set_column_ordering(self, mode):
+        """Scheduling only (include/mppgpu.h): 1 = visit columns grouped by their previous step's cost (default), 0 = batch order."""
+        check(self.L.mppgpu_set_column_ordering(self.h, int(mode)))
+
     def restart(self, x):
         x = _f64(x)
         check(self.L.mppgpu_restart(self.h, _dp(x), int(x.size)))
@@ -177,6 +181,23 @@ class _SoE:
         check(self.L.mppgpu_vsfm_mass_balance(self.h, float(dt), _dp(sums), _dp(maxs)))
         return sums, maxs
 
+    # -- global reductions over ranks (include/mppgpu.h "global reductions") -----------------------------
+    def comm_init(self, nranks=1, rank=0, unique_id=None):
+        """`unique_id`: the MPPGPU_COMM_ID_BYTES bytes of mpp_b200.comm_unique_id(), identical on every rank (None for one rank)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128) if unique_id is not None else None
+        check(self.L.mppgpu_comm_init(self.h, int(nranks), int(rank), buf))
+
+    def global_reduce_async(self):
+        check(self.L.mppgpu_global_reduce_async(self.h))
+
+    def global_mass_balance(self):
+        """Collective.  -> dict of the global sums / maxima / worst SNES reason of the last StepDT over all ranks."""
+        sums, maxs, worst = np.zeros(4), np.zeros(4), C.c_int()
+        check(self.L.mppgpu_global_mass_balance(self.h, _dp(sums), _dp(maxs), C.byref(worst)))
+        return {"mass_begin": sums[0], "mass_end": sums[1], "source_dt": sums[2], "boundary_exchanged": sums[3],
+                "max_abs_mass_error": maxs[0], "max_newton_its": int(maxs[1]), "any_diverged": bool(maxs[2]),
+                "max_dt_cuts": int(maxs[3]), "worst_reason": int(worst.value)}
+
     def reduction_buffer_ptr(self):
         p = C.c_void_p()
         check(self.L.mppgpu_reduction_buffer_device(self.h, C.byref(p)))
@@ -191,6 +212,13 @@ class _SoE:
         ms = C.c_float()
         check(self.L.mppgpu_last_step_ms(self.h, C.byref(ms)))
         return ms.value
+
+
+def comm_unique_id():
+    """The NCCL unique id (bytes) rank 0 creates and hands to every rank's `comm_init` (mppgpu_comm_unique_id)."""
+    buf = C.create_string_buffer(128)
+    check(lib().mppgpu_comm_unique_id(buf))
+    return buf.raw
 
 
 class VSFM(_SoE):

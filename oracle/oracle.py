@@ -24,10 +24,19 @@ def build(force=False):
     return so
 
 
+_LIB_PATH = None
+
+
+def use_library(path):
+    """Bind to another build of the same sources (bench.py's timing-only -O3 -march=native build); must precede the first lib()."""
+    global _LIB, _LIB_PATH
+    _LIB, _LIB_PATH = None, path
+
+
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        _LIB = C.CDLL(_LIB_PATH or build())
         L = _LIB
         L.orc_vsfm_create.restype = C.c_void_p
         for name in ("orc_thermal_create", "orc_th_create", "orc_thermal3_create"):

@@ -2,7 +2,7 @@
 same columns can be replayed through the oracle on the CPU (tools_failcols.py replay)."""
 import json, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import problems as PB, bench
 from mpp_b200 import constants as K

@@ -53,7 +53,7 @@ def main():
     print("Numbers under a profiler are never bench values; they explain the CUDA-event timings in bench.py.\n")
     peaks = {}
     try:
-        peaks = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "MEASURED_PEAKS.json")))
+        peaks = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))
     except Exception:
         pass
     for r in rows:

@@ -1,23 +1,28 @@
 """Quick device-resident timing of the step kernels (development aid; not the headline bench)."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tests"))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import problems as PB, bench
 import mpp_b200
 from mpp_b200 import constants as K
 mode = sys.argv[1] if len(sys.argv) > 1 else "vsfm"
 ncol = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20
 if mode == "vsfm":
-    d = bench.shard_inputs(0, ncol)
-    p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
-    bench.set_forcing_host(p, ids, d)
-    ms = []
-    for s in range(8):
-        p.pre_step_dt(); p.step_dt(1800.0, s + 1); p.post_step_dt()
-        ms.append(p.last_step_ms())
-    st = p.stats()
-    print(os.environ.get("MPPGPU_LIB_PATH", "default"), "vsfm ncol", ncol, "ms/step", ["%.2f" % m for m in ms], "col-steps/s %.3e" % (ncol / (np.mean(ms[3:]) * 1e-3)),
-          "its mean %.2f nf mean %.2f" % (st["newton_its"].mean(), st["nfuncs"].mean()))
+    zmin = float(os.environ.get("ZWT_MIN", "2.0"))
+    d = bench.shard_inputs(0, ncol, zwt_min=zmin)
+    for ordering in ([int(os.environ["ORDERING"])] if "ORDERING" in os.environ else [0, 1]):
+        p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
+        p.set_column_ordering(ordering)
+        bench.set_forcing_host(p, ids, d)
+        ms, bad = [], 0
+        for s in range(12):
+            p.pre_step_dt(); conv, reason = p.step_dt(1800.0, s + 1); p.post_step_dt()
+            ms.append(p.last_step_ms()); bad += (not conv)
+        st = p.stats(); sums, maxs = p.mass_balance()
+        print(os.environ.get("MPPGPU_LIB_PATH", "default"), "vsfm ncol", ncol, "zwt_min", zmin, "ordering", ordering, "ms/step", ["%.2f" % m for m in ms],
+              "col-steps/s %.3e" % (ncol / (np.mean(ms[4:]) * 1e-3)), "its mean %.2f nf mean %.2f nf max %d" % (st["newton_its"].mean(), st["nfuncs"].mean(), st["nfuncs"].max()),
+              "steps not converged", bad, "cuts", int((st["dt_cuts"] > 0).sum()), "max mass err %.2e" % maxs[0], "warp waste (batch order) %.3f" % bench.warp_waste(st["nfuncs"]), flush=True)
+        p.close()
 elif mode == "th":
     dens = K.DENSITY_IFC67 if (len(sys.argv) > 3 and sys.argv[3] == "ifc67") else K.DENSITY_TGDPB01
     iee = K.INT_ENERGY_ENTHALPY_IFC67 if dens == K.DENSITY_IFC67 else K.INT_ENERGY_ENTHALPY_CONSTANT
