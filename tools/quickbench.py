@@ -1,9 +1,10 @@
 """Quick device-resident timing of the step kernels (development aid; not the headline bench)."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import problems as PB, bench
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import bench
 import mpp_b200
+from mpp_b200 import problems as PB
 from mpp_b200 import constants as K
 mode = sys.argv[1] if len(sys.argv) > 1 else "vsfm"
 ncol = int(sys.argv[2]) if len(sys.argv) > 2 else 1 << 20

@@ -1,8 +1,9 @@
-"""Development aid: per-section cycle counters of vsfm_step2_kernel (needs the -DVSFM2_PROFILE build in mpp_b200/variants)."""
+"""Development aid: per-section cycle counters of vsfm_step2_kernel (needs the -DVSFM2_PROFILE build in build/variants)."""
 import ctypes as C, os, sys, numpy as np
-os.environ["MPPGPU_LIB_PATH"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "mpp_b200", "variants", "libmppgpu_prof.so")
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import problems as PB, bench, mpp_b200
+os.environ["MPPGPU_LIB_PATH"] = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "variants", "libmppgpu_prof.so")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+import bench, mpp_b200
+from mpp_b200 import problems as PB
 from mpp_b200._lib import lib
 ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 1 << 20
 d = bench.shard_inputs(0, ncol)
