@@ -48,9 +48,9 @@ def shard_inputs(c0, c1, chunk=CHUNK, zwt_min=None):
     return PB.shard_inputs(c0, c1, chunk=chunk, nlev=NLEV, zwt_min=ZWT_MIN if zwt_min is None else zwt_min)
 
 
-def shard_inputs_th(c0, c1, chunk=CHUNK):
+def shard_inputs_th(c0, c1, chunk=CHUNK, satfunc="smooth_brooks_corey_bz3"):
     return PB.shard_inputs(c0, c1, chunk=chunk, nlev=NLEV,
-                           builder=lambda n, nl, seed: PB.elm_th_inputs(n, nl, seed=seed, zwt_min=ZWT_MIN))
+                           builder=lambda n, nl, seed: PB.elm_th_inputs(n, nl, seed=seed, zwt_min=ZWT_MIN, satfunc=satfunc))
 
 
 def measured_kernel_facts():
@@ -529,13 +529,14 @@ def main():
         tot = sum_over_ranks([float(st["nfuncs"].sum()), float(st["newton_its"].sum()), float(st["nfuncs"].size), float((st["dt_cuts"] > 0).sum())])
         m = ms / steps
         ach = ALG_BYTES_TH * (c1 - c0) / (m * 1e-3) / 1e9
-        kname = "th_step2_kernel<16,VG,TGDPB01,const>"
+        kname = "th_step2_kernel<16,SBC,TGDPB01,const>"
         f = facts.get(kname, {})
         out = {"column_timesteps_per_sec": ncol_total * steps / (ms * 1e-3), "ms_per_step": m, "ms_per_step_all_rank0": [round(x, 2) for x in per_step],
                "ncol_total": ncol_total, "ncol_per_gpu": c1 - c0, "scaling": "strong",
                "workload": "coupled thermal-hydrology (BASELINE.json configs[4]): %d columns x %d layers in total over %d GPU(s); VSFM soils + csol, tkdry; "
-                           "Tanaka density + constant heat capacity; Dirichlet surface temperature, mass-rate infiltration, heat-rate source; "
-                           "2x2 block-tridiagonal Newton system per column" % (ncol_total, NLEV, world),
+                           "ELM's default curve smooth_brooks_corey_bz3 (mpp_varctl.F90:17; with van Genuchten the reference algorithm stalls on the cell "
+                           "that holds the water table, mpp_b200/problems.py); Tanaka density + constant heat capacity; Dirichlet surface temperature, "
+                           "mass-rate infiltration, heat-rate source; 2x2 block-tridiagonal Newton system per column" % (ncol_total, NLEV, world),
                "converged_all": not glob["any_diverged"], "worst_reason": glob["worst_reason"], "max_dt_cuts": glob["max_dt_cuts"],
                "columns_with_dt_cuts_last_step": int(tot[3]), "newton_its_mean": tot[1] / tot[2], "residual_evals_mean": tot[0] / tot[2],
                "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "kernel": kname,

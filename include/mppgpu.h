@@ -16,6 +16,7 @@
  *   VSFMMPPSetSoils                  MultiPhysicsProbVSFM.F90:211-475           mppgpu_vsfm_set_soils
  *   MPPThermalSetSoils               MultiPhysicsProbThermal.F90:76-208         mppgpu_thermal_set_soils
  *   MPPTHSetSoils                    MultiPhysicsProbTH.F90:75-401              mppgpu_th_set_soils
+ *   goveq_enthalpy%SetSoilPermeability GoveqnThermalEnthalpySoilType.F90:2454  mppgpu_th_set_energy_permeability
  *   SNESSetTolerances                MultiPhysicsProbBaseType.F90:1110-1196,
  *                                    MPPVSFMALM_Driver.F90:632-640              mppgpu_set_tolerances
  *   mpp%Restart(data_1d)             MultiPhysicsProbVSFM.F90:603-707           mppgpu_restart
@@ -124,6 +125,10 @@ int  mppgpu_thermal_elm_solve(mppgpu_handle h, double dtime, int nstep, const mp
 int  mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
                          const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,
                          int satfunc_type, int density_type, int int_energy_enthalpy_type);
+/* goveq_enthalpy%SetSoilPermeability (GoveqnThermalEnthalpySoilType.F90:2454-2480, called by th_mms_problem.F90:739 and
+ * mass_and_heat_model_problem.F90): per-cell permeability [m^2] of the ENERGY equation's aux vars, cell order, n = ncol*nlev.  MPPTHSetSoils
+ * leaves them at the aux-var default 8.3913e-12 (MultiPhysicsProbTH.F90:293 is commented out); so does this library until this is called. */
+int  mppgpu_th_set_energy_permeability(mppgpu_handle h, const double *perm, int n);
 int  mppgpu_set_tolerances(mppgpu_handle h, double atol, double rtol, double stol, int max_it, int max_funcs);
 /* NOT in the reference (default 0 = off = the reference's behaviour).  The reference's StepDT halves dt up to 20 times and then
  * sub-steps with the smallest dt that converged, so one pathological column can spend millions of residual evaluations in one

@@ -56,6 +56,7 @@ _SIGS = {
     "mppgpu_vsfm_elm_set_geometry_f": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, c_ip]),
     "mppgpu_vsfm_elm_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(ElmColumns), c_ip, c_ip]),
     "mppgpu_th_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int]),
+    "mppgpu_th_set_energy_permeability": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
     "mppgpu_set_tolerances": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
     "mppgpu_set_step_budget": (C.c_int, [C.c_void_p, C.c_int]),
     "mppgpu_set_column_ordering": (C.c_int, [C.c_void_p, C.c_int]),

@@ -26,6 +26,7 @@
 #include "vsfm_elm_kernels.cuh"
 #include "th_kernels.cuh"
 #include "th_kernels2.cuh"
+#include "step_launch.h"
 
 using namespace mpp;
 
@@ -661,11 +662,10 @@ static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
   const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
   // the specialisation that carries boundary conditions, the down-regulated sink and the IFC-67 density polynomial
   const bool bc = A.nbc > 0 || A.dr_type != 0 || A.dtab.type == DENSITY_IFC67;
-#define MPP_L2(SF) do { if (A.retry_mask) vsfm_step2_kernel<LPC, SF, true, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
-                        else if (bc) vsfm_step2_kernel<LPC, SF, true><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); \
-                        else    vsfm_step2_kernel<LPC, SF, false><<<nblocks, VSFM2_THREADS, 0, h->stream>>>(A); } while (0)
-  if (sf == SATFUNC_VG) MPP_L2(SATFUNC_VG); else if (sf == SATFUNC_BC) MPP_L2(SATFUNC_BC); else MPP_L2(SATFUNC_SBC);
-#undef MPP_L2
+  const int variant = A.retry_mask ? 2 : (bc ? 1 : 0);
+  // the 18 instances live in vsfm_step2_inst.cu, one translation unit per (LPC, saturation function)
+  if (LPC == 8) { if (sf == SATFUNC_VG) vsfm2_launch_8_0(A, variant, nblocks, h->stream); else if (sf == SATFUNC_BC) vsfm2_launch_8_1(A, variant, nblocks, h->stream); else vsfm2_launch_8_2(A, variant, nblocks, h->stream); }
+  else          { if (sf == SATFUNC_VG) vsfm2_launch_16_0(A, variant, nblocks, h->stream); else if (sf == SATFUNC_BC) vsfm2_launch_16_1(A, variant, nblocks, h->stream); else vsfm2_launch_16_2(A, variant, nblocks, h->stream); }
 }
 
 #ifdef VSFM2_PROFILE
@@ -989,6 +989,15 @@ extern "C" int mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const 
   if (!h->th) return fail("mppgpu_th_set_soils: handle is not a TH SoE");
   if (!h->mesh_set) return fail("mppgpu_th_set_soils: set the mesh first");
   return th_set_soils(h, h->th, watsat, hksat, bsw, sucsat, residual_sat, csol, tkdry, satfunc_type, density_type, int_energy_enthalpy_type);
+}
+
+static int th_set_energy_permeability(mppgpu_soe *h, THState *t, const double *perm);
+extern "C" int mppgpu_th_set_energy_permeability(mppgpu_handle h, const double *perm, int n)
+{
+  CHECK_H(h);
+  if (!h->th) return fail("mppgpu_th_set_energy_permeability: handle is not a TH SoE");
+  if (!perm || n != h->ncells) return fail("No. of values for soil permeability is not equal to no. of grid cells.");     // GoveqnThermalEnthalpySoilType.F90:2471-2475
+  return th_set_energy_permeability(h, h->th, perm);
 }
 
 #include "comm_host.inl"

@@ -27,7 +27,7 @@ static int th_create(THState *t, int ncol, int nlev, cudaStream_t s)
 
 static void th_destroy(THState *t)
 {
-  double *d[] = {t->por, t->perm, t->sat_res, t->alpha, t->lam, t->vgn, t->pu, t->ps, t->b2, t->b3, t->tkdry, t->csol,
+  double *d[] = {t->por, t->perm, t->sat_res, t->alpha, t->lam, t->vgn, t->pu, t->ps, t->b2, t->b3, t->tkdry, t->csol, t->perm_e,
                  t->x, t->Pout, t->Tout, t->liq_sat, t->mass};
   for (double *p : d) if (p) cudaFree(p);
 }
@@ -84,6 +84,16 @@ static int th_set_soils(mppgpu_soe *h, THState *t, const double *watsat, const d
   return 0;
 }
 
+// goveq_enthalpy%SetSoilPermeability (GoveqnThermalEnthalpySoilType.F90:2454-2480): per-cell permeability of the ENERGY equation's aux vars
+static int th_set_energy_permeability(mppgpu_soe *h, THState *t, const double *perm)
+{
+  const size_t N = (size_t)h->ncells;
+  if (!t->perm_e && cudaMalloc((void **)&t->perm_e, N * sizeof(double)) != cudaSuccess) return fail("cudaMalloc failed (energy permeability)");
+  CK(cudaMemcpyAsync(t->perm_e, perm, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 static int th_refresh_views(mppgpu_soe *h, THState *t)
 {
   if (!t->views_stale) return 0;
@@ -135,7 +145,7 @@ static int th_fill_args(mppgpu_soe *h, THState *t, THArgs &A, double dt)
   A.vgn = (A.satfunc == SATFUNC_VG) ? t->vgn : nullptr;
   const bool sbc = (A.satfunc == SATFUNC_SBC);
   A.pu = sbc ? t->pu : nullptr; A.ps = sbc ? t->ps : nullptr; A.b2 = sbc ? t->b2 : nullptr; A.b3 = sbc ? t->b3 : nullptr;
-  A.dz = h->dz.p; A.area = h->area.p; A.tkdry = t->tkdry; A.csol = t->csol;
+  A.dz = h->dz.p; A.area = h->area.p; A.tkdry = t->tkdry; A.csol = t->csol; A.perm_e = t->perm_e;
   A.x_in = t->x; A.x_out = t->x;
   for (auto *c : h->bcs) {
     if (A.nbc >= 4) return fail("mppgpu_step_dt: at most 4 TH boundary conditions");
@@ -167,13 +177,13 @@ static int th_launch(mppgpu_soe *h, THState *, THArgs &A, int *nblocks_out)
     A.block_partials = h->block_partials.p;
   }
   if (fast) {
-    // the two model combinations the reference's drivers use get compile-time specialisations; anything else dispatches at run time
-    if (A.satfunc == SATFUNC_VG && A.density_type == DENSITY_TGDPB01 && A.iee_type == INT_ENERGY_ENTHALPY_CONSTANT)
-      th_step2_kernel<16, SATFUNC_VG, DENSITY_TGDPB01, INT_ENERGY_ENTHALPY_CONSTANT><<<nblocks, TH2_THREADS, 0, h->stream>>>(A);
-    else if (A.satfunc == SATFUNC_VG && A.density_type == DENSITY_IFC67 && A.iee_type == INT_ENERGY_ENTHALPY_IFC67)
-      th_step2_kernel<16, SATFUNC_VG, DENSITY_IFC67, INT_ENERGY_ENTHALPY_IFC67><<<nblocks, TH2_THREADS, 0, h->stream>>>(A);
-    else
-      th_step2_kernel<16, -1, -1, -1><<<nblocks, TH2_THREADS, 0, h->stream>>>(A);
+    // the model combinations the reference's drivers use (and ELM's default curve) get compile-time specialisations in th_step2_inst.cu;
+    // anything else dispatches at run time
+    const bool tanaka_const = A.density_type == DENSITY_TGDPB01 && A.iee_type == INT_ENERGY_ENTHALPY_CONSTANT;
+    if (A.satfunc == SATFUNC_VG && tanaka_const) th2_launch_0(A, nblocks, h->stream);
+    else if (A.satfunc == SATFUNC_VG && A.density_type == DENSITY_IFC67 && A.iee_type == INT_ENERGY_ENTHALPY_IFC67) th2_launch_1(A, nblocks, h->stream);
+    else if (A.satfunc == SATFUNC_SBC && tanaka_const) th2_launch_2(A, nblocks, h->stream);     // ELM's default curve (mpp_varctl.F90:17)
+    else th2_launch_3(A, nblocks, h->stream);
   } else {
     const size_t smem = (size_t)TH_NARR * h->nlev * sizeof(double);
     if (smem > 200 * 1024) return fail("mppgpu_step_dt: nlev = %d exceeds the TH kernel's shared-memory budget", h->nlev);

@@ -29,6 +29,7 @@ struct THArgs {
   int satfunc, density_type, iee_type;
   const double *por, *perm, *sat_res, *alpha, *lam, *vgn, *pu, *ps, *b2, *b3, *dz, *area;
   const double *tkdry, *csol;
+  const double *perm_e;                        // energy equation's own permeability (mppgpu_th_set_energy_permeability); nullptr: the aux-var default
   const double *x_in; double *x_out;           // cell-interleaved (P, T)
   int nbc, nss;
   THCondDev bc[4], ss[4];
@@ -57,9 +58,19 @@ __device__ __forceinline__ void th_cell_compute(const THArgs &A, const SatParams
 {
   const int dtype = (DT >= 0) ? DT : A.density_type, itype = (IEE >= 0) ? IEE : A.iee_type;
   SatState st;
-  if (SF >= 0) { sat_values<(SF >= 0 ? SF : 0)>(sp, P, 1.0, st); sat_derivs<(SF >= 0 ? SF : 0)>(sp, st, 1.0, c.dsat, c.dkr); }
-  else { sat_values_rt(A.satfunc, sp, P, 1.0, st); sat_derivs_rt(A.satfunc, sp, st, 1.0, c.dsat, c.dkr); }
-  c.sat = st.sat; c.kr = st.kr;
+  if (SF == SATFUNC_SBC || SF == SATFUNC_BC) {
+    // the lean branch-free Brooks-Corey / smoothed Brooks-Corey curves of the fast VSFM kernel (physics.cuh:bc_sbc_values): one log and
+    // two exp whatever the regime; frac_liq_sat = 1 in the TH model
+    const double pc = P - PRESSURE_REF;
+    const bool rA = (SF == SATFUNC_BC) ? (-sp.alpha * pc > 1.0) : (pc <= sp.pu), rB = (SF == SATFUNC_SBC) && !rA && (pc < sp.ps);
+    double Se;
+    bc_sbc_values<double>(sp.sat_res, sp.alpha, sp.m, sp.ps, sp.b2, sp.b3, pc, rA, rA, rB, rB, c.sat, c.kr, Se);
+    bc_sbc_derivs<double>(sp.sat_res, sp.m, sp.ps, sp.b2, sp.b3, pc, Se, c.kr, rA, rA, rB, rB, c.dsat, c.dkr);
+  } else {
+    if (SF >= 0) { sat_values<(SF >= 0 ? SF : 0)>(sp, P, 1.0, st); sat_derivs<(SF >= 0 ? SF : 0)>(sp, st, 1.0, c.dsat, c.dkr); }
+    else { sat_values_rt(A.satfunc, sp, P, 1.0, st); sat_derivs_rt(A.satfunc, sp, st, 1.0, c.dsat, c.dkr); }
+    c.sat = st.sat; c.kr = st.kr;
+  }
   const double Pe = (P < PRESSURE_REF) ? PRESSURE_REF : P;                 // ThermalEnthalpySoilAuxType.F90:251-252
   if (DT == DENSITY_TGDPB01) {                                              // one temperature part for both pressures
     const TanakaT tt = tanaka_T(T);
@@ -103,6 +114,7 @@ __device__ __forceinline__ void th_rich_flux(const FluxIn &u, const FluxIn &d, d
   dT_dn = -(dqT_dn * den_ave - q * ((1.0 - upw) * d.ddenT));
 }
 
+#ifndef MPP_STEP_KERNEL_TU   // the generic (one warp per column) kernel is compiled once, in mppgpu.cu
 // all per-cell arrays live in shared memory; this view indexes them
 struct THView {
   double *P, *T, *Pp, *Tp, *accm, *acce, *Fm, *Fe, *Ym, *Ye, *Wm, *We, *Gm, *Ge;
@@ -129,7 +141,9 @@ th_step_generic_kernel(const THArgs A)
   const SnesOpts so = A.so;
   const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
   const double area = col_ok ? A.area[col] : 1.0;
-  const double PERM_E = 8.3913e-12;        // energy-equation aux vars keep the default permeability (ThermalEnthalpySoilAuxType.F90:93)
+  // energy-equation aux vars keep the default permeability (ThermalEnthalpySoilAuxType.F90:93) unless the driver set its own
+  // (goveq_enthalpy%SetSoilPermeability, th_mms_problem.F90:739)
+#define PERM_E_AT(jj) (A.perm_e ? A.perm_e[c0 + (jj)] : 8.3913e-12)
 
   if (col_ok) {
     for (int j = lane; j < nlev; j += 32) {
@@ -173,7 +187,7 @@ th_step_generic_kernel(const THArgs A)
       // energy-equation boundary aux var: temperature = condition value; pressure is whatever the driver poked
       // (mass_and_heat_model_problem.F90:616-621), default 0 (RichardsODEPressureAuxType.F90:90)
       bcs[k].T = bcs[k].val; bcs[k].P = A.bc[k].bc_pressure ? A.bc[k].bc_pressure[col] : 0.0;
-      bcs[k].Dq = PERM_E / (0.0 + 0.5 * dzc);
+      bcs[k].Dq = PERM_E_AT(jc_) / (0.0 + 0.5 * dzc);
       th_cell_compute(A, sp, A.tkdry[c0 + jc_], bcs[k].P, bcs[k].T, bc);
       bcs[k].fin = {bcs[k].P, bc.kr, bc.dkr, bc.den_e, bc.ddenP_e, bc.ddenT_e};
       bcs[k].hl = bc.hl; bcs[k].dhlT = bc.dhlT; bcs[k].dhlP = bc.dhlP; bcs[k].tc = bc.tc;
@@ -202,7 +216,8 @@ th_step_generic_kernel(const THArgs A)
           const double gfac = FMWH2O * ((dist_up + dist_dn) * (A.uz * (-GRAVITY_CONSTANT)));
           const double pmu = A.perm[c0 + ju], pmd = A.perm[c0 + jd];
           const double Dqm = (pmu * pmd) / (dist_up * pmd + dist_dn * pmu);
-          const double Dqe = (PERM_E * PERM_E) / (dist_up * PERM_E + dist_dn * PERM_E);
+          const double peu = PERM_E_AT(ju), ped = PERM_E_AT(jd);
+          const double Dqe = (peu * ped) / (dist_up * ped + dist_dn * peu);
           FluxIn um = {v.P[ju], v.kr[ju], v.dkr[ju], v.denm[ju], v.dPm[ju], v.dTm[ju]}, dm = {v.P[jd], v.kr[jd], v.dkr[jd], v.denm[jd], v.dPm[jd], v.dTm[jd]};
           FluxIn ue = {v.P[ju], v.kr[ju], v.dkr[ju], v.dene[ju], v.dPe[ju], v.dTe[ju]}, de = {v.P[jd], v.kr[jd], v.dkr[jd], v.dene[jd], v.dPe[jd], v.dTe[jd]};
           double fl, mJup, mJdn, dTu, dTd;
@@ -346,7 +361,8 @@ th_step_generic_kernel(const THArgs A)
       const double gfac = FMWH2O * ((dist_up + dist_dn) * (A.uz * (-GRAVITY_CONSTANT)));
       const double pmu = A.perm[c0 + j], pmd = A.perm[c0 + j + 1];
       const double Dqm = (pmu * pmd) / (dist_up * pmd + dist_dn * pmu);
-      const double Dqe = (PERM_E * PERM_E) / (dist_up * PERM_E + dist_dn * PERM_E);
+      const double peu = PERM_E_AT(j), ped = PERM_E_AT(j + 1);
+      const double Dqe = (peu * ped) / (dist_up * ped + dist_dn * peu);
       FluxIn um = {v.Wm[j], v.kr[j], 0, v.denm[j], 0, 0}, dm = {v.Wm[j + 1], v.kr[j + 1], 0, v.denm[j + 1], 0, 0};
       FluxIn ue = {v.Wm[j], v.kr[j], 0, v.dene[j], 0, 0}, de = {v.Wm[j + 1], v.kr[j + 1], 0, v.dene[j + 1], 0, 0};
       double fl, a1, a2, a3, a4, mfl;
@@ -485,6 +501,8 @@ th_step_generic_kernel(const THArgs A)
   }
 }
 
+#undef PERM_E_AT
+
 struct THState {
   cudaStream_t stream = nullptr;
   int ncol = 0, nlev = 0, orientation = 311;
@@ -493,10 +511,12 @@ struct THState {
   int satfunc_name = 0, density_type = DENSITY_TGDPB01, iee_type = INT_ENERGY_ENTHALPY_CONSTANT;
   const double *d_dz = nullptr, *d_area = nullptr;
   double *por = nullptr, *perm = nullptr, *sat_res = nullptr, *alpha = nullptr, *lam = nullptr, *vgn = nullptr,
-         *pu = nullptr, *ps = nullptr, *b2 = nullptr, *b3 = nullptr, *tkdry = nullptr, *csol = nullptr;
+         *pu = nullptr, *ps = nullptr, *b2 = nullptr, *b3 = nullptr, *tkdry = nullptr, *csol = nullptr, *perm_e = nullptr;
   double *x = nullptr;              // interleaved (P,T), 2*ncells
   double *Pout = nullptr, *Tout = nullptr, *liq_sat = nullptr, *mass = nullptr;   // de-interleaved views for GetDataForCLM
   bool views_stale = true;
 };
+
+#endif  // MPP_STEP_KERNEL_TU
 
 }  // namespace mpp

@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(TH2_THREADS, TH2_MIN_BLOCKS)
 th_step2_kernel(const THArgs A)
 {
   constexpr unsigned FULL = FULL_MASK;
-  constexpr double PERM_E = 8.3913e-12;      // energy-equation aux vars keep the default permeability (ThermalEnthalpySoilAuxType.F90:93)
+  // energy-equation aux vars keep the default permeability (ThermalEnthalpySoilAuxType.F90:93) unless the driver set its own
+  // (goveq_enthalpy%SetSoilPermeability -> mppgpu_th_set_energy_permeability)
+  constexpr double PERM_E_DEFAULT = 8.3913e-12;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
   const int col = tid / G, j = tid % G, lane = threadIdx.x & 31;
   const int nlev = A.nlev;
@@ -104,9 +106,10 @@ th_step2_kernel(const THArgs A)
 
   // ---- static per-cell data ------------------------------------------------------------------------------------------
   SatParams sp; sp.sat_res = 0.0; sp.alpha = 1.0; sp.m = 0.5; sp.n = 2.0; sp.pu = sp.ps = sp.b2 = sp.b3 = 0.0;
-  double por = 0.5, perm = 1.0, dz = 1.0, area = 1.0, tkdry = 1.0, csol = 1.0, P = PRESSURE_REF, T = 283.15, srcm = 0.0, srce = 0.0;
+  double por = 0.5, perm = 1.0, dz = 1.0, area = 1.0, tkdry = 1.0, csol = 1.0, P = PRESSURE_REF, T = 283.15, srcm = 0.0, srce = 0.0, perm_e = PERM_E_DEFAULT;
   if (valid) {
     por = A.por[cell]; perm = A.perm[cell]; dz = A.dz[cell]; area = A.area[col]; tkdry = A.tkdry[cell]; csol = A.csol[cell];
+    if (A.perm_e) perm_e = A.perm_e[cell];
     sp.sat_res = A.sat_res[cell]; sp.alpha = A.alpha[cell]; sp.m = A.lam[cell]; sp.n = A.vgn ? A.vgn[cell] : 0.0;
     if (A.pu) { sp.pu = A.pu[cell]; sp.ps = A.ps[cell]; sp.b2 = A.b2[cell]; sp.b3 = A.b3[cell]; }
     P = A.x_in[2 * cell]; T = A.x_in[2 * cell + 1];
@@ -124,7 +127,8 @@ th_step2_kernel(const THArgs A)
   const double dist_up = 0.5 * dz, dist_dn = 0.5 * dz_d, upw = dist_up / (dist_up + dist_dn);
   const double gfac = FMWH2O * ((dist_up + dist_dn) * (A.uz * (-GRAVITY_CONSTANT)));
   const double Dqm = (perm * perm_d) / (dist_up * perm_d + dist_dn * perm);
-  const double Dqe = (PERM_E * PERM_E) / (dist_up * PERM_E + dist_dn * PERM_E);
+  const double perm_e_d = __shfl_down_sync(FULL, perm_e, 1, G);
+  const double Dqe = (perm_e * perm_e_d) / (dist_up * perm_e_d + dist_dn * perm_e);
 
   // boundary conditions owned by this lane (at most one per region and equation)
   struct BCL { int ieqn; double P, T, bgf, Dq; FluxIn fin; double hl, tc; };
@@ -142,7 +146,7 @@ th_step2_kernel(const THArgs A)
       th_cell_compute<SF, DT, IEE>(A, sp, tkdry, b.P, b.T, c);
       b.fin = FluxIn{b.P, c.kr, c.dkr, c.den_m, c.ddenP_m, c.ddenT_m}; b.hl = 0.0; b.tc = 0.0;
     } else {                 // energy equation: temperature = condition value; pressure as poked by the driver (default 0)
-      b.T = A.bc[k].value[col]; b.P = A.bc[k].bc_pressure ? A.bc[k].bc_pressure[col] : 0.0; b.Dq = PERM_E / (0.0 + 0.5 * dz);
+      b.T = A.bc[k].value[col]; b.P = A.bc[k].bc_pressure ? A.bc[k].bc_pressure[col] : 0.0; b.Dq = perm_e / (0.0 + 0.5 * dz);
       th_cell_compute<SF, DT, IEE>(A, sp, tkdry, b.P, b.T, c);
       b.fin = FluxIn{b.P, c.kr, c.dkr, c.den_e, c.ddenP_e, c.ddenT_e}; b.hl = c.hl; b.tc = c.tc;
     }

@@ -92,6 +92,8 @@ enum { PH_INIT = 0, PH_NEWTON = 1, PH_LS_FULL = 2, PH_LS_QUAD = 3, PH_LS_CUBIC =
 // (measured: 26% of all executed instructions in the first version, profiles/r1_vsfm_first.md).
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+#ifndef MPP_STEP_KERNEL_TU   // the support kernels below are compiled once, in mppgpu.cu
+
 // Second stage of the deterministic reduction: `gridDim.x` blocks each fold a contiguous slice of the per-block
 // partials (fixed order), the last block to finish folds the slice results (fixed order) into out[0..8]:
 // out[0..3] sums, out[4..7] maxima, out[8] worst (minimum) SNES reason.  scratch: gridDim.x*9 doubles + 1 counter.
@@ -205,5 +207,7 @@ __global__ void order_scatter_kernel(const int *__restrict__ nf, int n, const in
     order[offsets[b * gridDim.x + blockIdx.x] + before + rank] = i;
   }
 }
+
+#endif  // MPP_STEP_KERNEL_TU
 
 }  // namespace mpp

@@ -24,7 +24,7 @@ def build_celia(cls, nz=100, **kw):
     porosity, lam, alpha, perm = 0.368, 0.5, 3.4257e-4, 8.3913e-12    # :295-298
     vish2o, denh2o, grav = 0.001002, 1000.0, K.GRAV
     hksat = perm / vish2o * (denh2o * grav) / 0.001                   # :325
-    sucsat = 1.0 / (alpha * K.GRAVITY_CONSTANT)                       # :327
+    sucsat = 1.0 / (alpha * K.GRAVITY_CONSTANT)                       # :327 (the driver itself inverts with 9.80665; VSFMMPPSetSoils converts with 9.80616)
     full = lambda v: np.full((1, nz), v)
     p.set_soils(full(porosity), full(hksat), full(1.0 / lam), full(sucsat), full(0.2772),
                 "van_genuchten", K.DENSITY_TGDPB01)                   # :331-335
@@ -594,7 +594,7 @@ def build_mass_and_heat(cls, nx=100, **kw):
     b1 = p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS)              # cell nx, unit vector (-1,0,0) :312-327
     porosity, lam, alpha, perm = 0.368, 0.5, 3.4257e-4, 8.3913e-12
     hksat = perm / 0.001002 * (1000.0 * K.GRAV) / 0.001
-    sucsat = 1.0 / (alpha * K.GRAVITY_CONSTANT)
+    sucsat = 1.0 / (alpha * K.GRAVITY_CONSTANT)                                             # mass_and_heat_model_problem.F90:458 (the driver inverts with 9.80665, MPPTHSetSoils converts with 9.80616)
     full = lambda v: np.full((1, nx), v)
     p.set_soils(full(porosity), full(hksat), full(1.0 / lam), full(sucsat), full(0.2772), full(837.0), full(0.25),
                 "van_genuchten", K.DENSITY_IFC67, K.INT_ENERGY_ENTHALPY_IFC67)             # :458-472
@@ -608,6 +608,120 @@ def run_mass_and_heat(p, b0, b1, dt=3600.0):
     p.set_data(K.AUXVAR_BC, K.VAR_PRESSURE, b0, np.array([91325.0]), ieqn=2)               # :616-621 (pokes aux_vars_bc%pressure)
     p.set_data(K.AUXVAR_BC, K.VAR_PRESSURE, b1, np.array([91325.0]), ieqn=2)
     conv, reason = p.step_dt(dt, 1)
+    P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, -1, ieqn=1)
+    T = p.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, -1, ieqn=2)
+    return conv, reason, P, T
+
+
+# ---------------------------------------------------------------------------------------------------
+# TH th_mms -- src/driver/standalone/thermal-e/th_mms_problem.F90 (manufactured steady state, 20 cells along x)
+#   baseline regression_tests/th/th_mms.regression.baseline; registered in regression_tests/th/th.cfg:8-9 (temperature 1e-8 K)
+# `phys` supplies the scalar EOS / saturation-function calls the reference's driver makes while building its source terms
+# (set_variable_for_problem :1158-1458): oracle.OraclePhysics for the oracle, mpp_b200.hostphysics.HostPhysics for the CUDA path.
+# ---------------------------------------------------------------------------------------------------
+def th_mms_data(phys, nx=20):
+    x_min, x_max = 0.0, 10.0                                                         # set_default_problem :937-955
+    xlim = x_max - x_min
+    dx = (x_max - x_min) / nx                                                        # set_problem :958-988
+    pi = 4.0 * np.arctan(1.0)
+    dens_type, iee_type = K.DENSITY_CONSTANT, K.INT_ENERGY_ENTHALPY_IFC67            # :962-964 (the second assignment wins)
+    FMW = K.FMWH2O
+    xc = np.array([dx / 2.0 + dx * i + x_min for i in range(nx)])                    # mpp_mesh_utils.F90:212
+
+    def pres(x):                                                                     # compute_pressure_or_deriv :991-1020
+        a0, a1 = 15000.0, -20000.0
+        return (a0 * np.sin((x - x_min) / xlim * pi) + a1 + K.PRESSURE_REF, a0 * pi / xlim * np.cos((x - x_min) / xlim * pi),
+                -a0 * pi * pi / xlim / xlim * np.sin((x - x_min) / xlim * pi))
+
+    def temp(x):                                                                     # compute_temperature_or_deriv :1023-1043 (second set)
+        a0, a1 = 5.0, 290.0
+        return (a0 * np.sin((x - x_min) / xlim * pi) * 1.0 + a1, a0 * pi / xlim * np.cos((x - x_min) / xlim * pi) * 1.0,
+                -a0 * pi * pi / xlim / xlim * np.sin((x - x_min) / xlim * pi) * 1.0)
+
+    def perm(x):                                                                     # compute_permeability_or_deriv :1046-1059
+        p0 = 1.0e-11
+        return p0 * (2.0 - np.cos((x - x_min) / xlim * pi)), p0 * pi / xlim * (+np.sin((x - x_min) / xlim * pi))
+
+    alpha, lam, sat_res, kdry, kwet, talpha, pert = 1.0 / 4000.0, 0.5, 0.0, 0.25, 1.3, 0.45, 1.0e-6     # :1062-1155, :1203
+    d = {"nx": nx, "dx": dx, "xc": xc, "alpha": alpha, "lam": lam, "sat_res": sat_res, "tkdry": kdry,
+         "density_type": dens_type, "iee_type": iee_type}
+    d["perm"] = np.array([perm(x)[0] for x in xc])
+    Pex = np.array([pres(x)[0] for x in xc]); Tex = np.array([temp(x)[0] for x in xc])
+    d["P_exact"], d["T_exact"] = Pex, Tex
+    P0 = 0.0
+    for v in Pex:
+        P0 = P0 + 1.0 / nx * v                                                       # DATA_INITIAL_PRESSURE :1212-1219
+    T0 = 0.0
+    for v in Tex:
+        T0 = T0 + 1.0 / nx * v
+    d["press_ic"], d["temp_ic"] = np.full(nx, P0), np.full(nx, T0)
+    d["pres_bc"] = np.array([pres(xc[0] - dx / 2.0)[0], pres(xc[-1] + dx / 2.0)[0]])  # DATA_PRESSURE_BC :1250-1262
+    d["temp_bc"] = np.array([temp(xc[0] - dx / 2.0)[0], temp(xc[-1] + dx / 2.0)[0]])
+    msrc, hsrc = np.zeros(nx), np.zeros(nx)
+    for i, x in enumerate(xc):
+        xp, xn = x + pert, x - pert
+        k, dk_dx = perm(x)
+        P, dP_dx, d2P_dx2 = pres(x)
+        T, dT_dx, d2T_dx2 = temp(x)
+        mu = phys.viscosity(P, T)
+        rho, drho_dP, drho_dT = phys.density(P, T, dens_type)
+        rho, drho_dP, drho_dT = rho * FMW, drho_dP * FMW, drho_dT * FMW
+        U, H, dU_dT, dH_dT, dU_dP, dH_dP = phys.internal_energy_enthalpy(P, T, iee_type, rho, drho_dT, drho_dP)
+        se, dse_dP = phys.vg_sat(P, sat_res, alpha, lam)
+        kr, dkr_dP = phys.vg_relperm(P, sat_res, alpha, lam)
+        dkr_dx = dkr_dP * dP_dx                                                      # (+ dkr_dse * dse_dp0 * dp0_dx with dse_dp0 = dp0_dx = 0)
+        Pp, Tp, Pn, Tn = pres(xp)[0], temp(xp)[0], pres(xn)[0], temp(xn)[0]
+        rp, rp_dP, rp_dT = phys.density(Pp, Tp, dens_type)
+        rn, rn_dP, rn_dT = phys.density(Pn, Tn, dens_type)
+        rp, rn = rp * FMW, rn * FMW
+        drho_dx = (rp - rn) / pert / 2.0
+        drhoq_dx = -((k * kr / mu) * drho_dx + (rho * kr / mu) * dk_dx + (rho * k / mu) * dkr_dx) * (dP_dx) - (rho * k * kr / mu) * (d2P_dx2)
+        msrc[i] = drhoq_dx * dx                                                      # DATA_MASS_SOURCE :1264-1311
+        rhoq = -rho * (k * kr / mu * dP_dx)
+        Ke = (se + 1.e-6) ** (talpha)
+        sep = phys.vg_sat(Pp, sat_res, alpha, lam)[0]; sen = phys.vg_sat(Pn, sat_res, alpha, lam)[0]
+        dKe_dx = ((sep + 1.e-6) ** (talpha) - (sen + 1.e-6) ** (talpha)) / pert / 2.0
+        kappa = kwet * Ke + kdry * (1.0 - Ke)
+        dkappa_dx = 0.0 * Ke + 0.0 * (1.0 - Ke) + (kwet - kdry) * dKe_dx
+        Hp = phys.internal_energy_enthalpy(Pp, Tp, iee_type, rp, rp_dT * FMW, rp_dP * FMW)[1]
+        Hn = phys.internal_energy_enthalpy(Pn, Tn, iee_type, rn, rn_dT * FMW, rn_dP * FMW)[1]
+        dH_dx = (Hp - Hn) / pert / 2.0
+        hsrc[i] = -(drhoq_dx * H / FMW + rhoq * dH_dx / FMW - dkappa_dx * dT_dx - kappa * d2T_dx2) * dx     # DATA_HEAT_SOURCE :1353-1449
+    d["mass_source"], d["heat_source"] = msrc, hsrc
+    return d
+
+
+def build_th_mms(cls, phys, nx=20, **kw):
+    d = th_mms_data(phys, nx)
+    p = cls(1, nx, **kw)
+    p.set_mesh(K.MESH_HORIZONTAL, np.full((1, nx), d["dx"]), np.array([1.0]))             # connections along x, area = dy*dz = 1 (:205-292)
+    ids = {"p0": p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS),       # 'Pressure BC', both ends (:343-355)
+           "p1": p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS),
+           "msrc": p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_CELLS),         # 'Source term for MMS', ALL_CELLS (:357-362)
+           "t0": p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS),       # 'Temperature BC' (:373-385)
+           "t1": p.add_condition(2, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS),
+           "hsrc": p.add_condition(2, K.COND_SS, K.COND_HEAT_RATE, K.SOIL_CELLS)}         # (:387-392)
+    # the setter takes ELM's tables: invert VSFMMPPSetSoilsCLM's conversions (as build_mass_and_heat does)
+    hksat = d["perm"] / 0.001002 * (1000.0 * K.GRAV) / 0.001
+    sucsat = 1.0 / (d["alpha"] * K.GRAV)                                                  # this driver sets alpha directly (:671): invert MPPTHSetSoils exactly, alpha = 1 / (sucsat * grav), MultiPhysicsProbTH.F90:283
+    full = lambda v: np.full((1, nx), v)
+    p.set_soils(full(0.0), hksat.reshape(1, nx), full(1.0 / d["lam"]), full(sucsat), full(d["sat_res"]), full(0.0), full(d["tkdry"]),
+                "van_genuchten", d["density_type"], d["iee_type"])                        # porosity 0, heat capacity 0: a steady state (:1221-1224, :1313-1316)
+    p.set_energy_permeability(d["perm"])                                                  # goveq_enthalpy%SetSoilPermeability (:739)
+    p.restart(d["press_ic"], d["temp_ic"])
+    return p, ids, d
+
+
+def run_th_mms(p, ids, d):
+    """set_source_sink_conditions + set_boundary_conditions + one StepDT(1 s) (run_th_mms_problem :89-141)."""
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["msrc"], d["mass_source"], ieqn=1)
+    p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["hsrc"], d["heat_source"], ieqn=2)
+    for k, key in ((0, "p0"), (1, "p1")):
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids[key], d["pres_bc"][k:k + 1], ieqn=1)
+    for k, key in ((0, "t0"), (1, "t1")):
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids[key], d["temp_bc"][k:k + 1], ieqn=2)
+        p.set_data(K.AUXVAR_BC, K.VAR_PRESSURE, ids[key], d["pres_bc"][k:k + 1], ieqn=2)   # aux_vars_bc%pressure poked by the driver (:858-868)
+    conv, reason = p.step_dt(1.0, 1)
     P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, -1, ieqn=1)
     T = p.get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, -1, ieqn=2)
     return conv, reason, P, T

@@ -419,6 +419,11 @@ class TH(_SoE):
 
     MPPTHSetSoils = set_soils
 
+    def set_energy_permeability(self, perm):
+        """goveq_enthalpy%SetSoilPermeability: per-cell permeability of the energy equation's aux vars (cell order)."""
+        perm = _f64(perm)
+        check(self.L.mppgpu_th_set_energy_permeability(self.h, _dp(perm), int(perm.size)))
+
     def restart(self, press, temp=None):
         x = _f64(press) if temp is None else np.concatenate([_f64(press), _f64(temp)])
         check(self.L.mppgpu_restart(self.h, _dp(x), int(x.size)))

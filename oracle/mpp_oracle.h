@@ -253,6 +253,7 @@ int       orc_th_add_condition(orc_th *p, int ieqn /*1=mass,2=energy*/, int ss_o
 int       orc_th_set_soils(orc_th *p, const double *watsat, const double *hksat, const double *bsw, const double *sucsat,
                            const double *residual_sat, const double *csol /*J/kg/K*/, const double *tkdry,
                            int satfunc_name, int density_type, int int_energy_enthalpy_type);
+int       orc_th_set_energy_perm(orc_th *p, const double *perm /*ncells*/);
 void      orc_th_set_tolerances(orc_th *p, double atol, double rtol, double stol, int max_it, int max_funcs);
 int       orc_th_restart(orc_th *p, const double *press, const double *temp);
 int       orc_th_set_data(orc_th *p, int ieqn, int auxvar_type, int var_type, int cond_id, const double *data, int n);

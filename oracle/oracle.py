@@ -122,6 +122,31 @@ def press_to_relperm(sp, press, frac_liq=1.0):
     return k.value, dk.value
 
 
+
+class OraclePhysics:
+    """The reference's scalar EOS / saturation-function calls (EOSWaterMod.F90, SaturationFunction.F90 as restated in eos_water.c /
+    satfunc.c) for problem set-up code (manufactured sources of th_mms).  Same five calls as mpp_b200.hostphysics.HostPhysics."""
+
+    def density(self, P, T, itype):
+        return density(P, T, itype)
+
+    def viscosity(self, P, T):
+        v, a, b = C.c_double(), C.c_double(), C.c_double()
+        lib().orc_viscosity(C.c_double(P), C.c_double(T), C.byref(v), C.byref(a), C.byref(b))
+        return v.value
+
+    def internal_energy_enthalpy(self, P, T, itype, rho, drho_dT, drho_dP):
+        o = [C.c_double() for _ in range(6)]
+        lib().orc_internal_energy_enthalpy(C.c_double(P), C.c_double(T), C.c_int(itype), C.c_double(rho), C.c_double(drho_dT), C.c_double(drho_dP),
+                                           *[C.byref(x) for x in o])
+        return tuple(x.value for x in o)            # U, H, dU_dT, dH_dT, dU_dP, dH_dP
+
+    def vg_sat(self, P, sat_res, alpha, m):
+        return press_to_sat(satparams("van_genuchten", sat_res, alpha, m), P)
+
+    def vg_relperm(self, P, sat_res, alpha, m):
+        return press_to_relperm(satparams("van_genuchten", sat_res, alpha, m), P, 1.0)
+
 SATFUNC_NAMES = {"van_genuchten": 0, "brooks_corey": 1, "smooth_brooks_corey_bz2": 2, "smooth_brooks_corey_bz3": 3}
 
 
@@ -409,6 +434,11 @@ class OracleTH:
         rc = self.L.orc_th_set_soils(self.h, *[dp(x) for x in a], SATFUNC_NAMES[satfunc_type], int(density_type), int(int_energy_enthalpy_type))
         if rc:
             raise ValueError("set_soils rc=%d" % rc)
+
+    def set_energy_permeability(self, perm):
+        perm = f64(perm)
+        assert perm.size == self.ncells
+        self.L.orc_th_set_energy_perm(self.h, dp(perm))
 
     def set_tolerances(self, atol=1e-50, rtol=1e-8, stol=1e-10, max_it=50, max_funcs=10000):
         self.L.orc_th_set_tolerances(self.h, C.c_double(atol), C.c_double(rtol), C.c_double(stol), int(max_it), int(max_funcs))

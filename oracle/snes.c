@@ -21,9 +21,18 @@
  * NaN/Inf back-off, max_funcs exhaustion.
  */
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "mpp_oracle.h"
+
+/* ORC_SNES_MONITOR=1 in the environment prints one line per Newton iteration (debugging aid for hard columns) */
+static int snes_monitor(void)
+{
+  static int on = -1;
+  if (on < 0) { const char *e = getenv("ORC_SNES_MONITOR"); on = (e && e[0] == '1') ? 1 : 0; }
+  return on;
+}
 
 void orc_snes_default_opts(orc_snes_opts *o)
 {
@@ -285,11 +294,18 @@ ls_done:
     }
     its = it + 1;                                 /* snes->iter */
     reason = converged_default(o, its, xnorm, ynorm, fnorm, &ttol, &rnorm0, nfuncs);
+    if (snes_monitor()) {
+      int im = 0, iy = 0;
+      for (i = 1; i < n; i++) { if (fabs(F[i]) > fabs(F[im])) im = i; if (fabs(Y[i]) > fabs(Y[iy])) iy = i; }
+      fprintf(stderr, "  snes it %d fnorm %.6e ynorm %.6e xnorm %.6e lambda %.3e nfuncs %d reason %d | max|F| at %d: F %.3e X %.9e | max|Y| at %d: Y %.3e X %.9e\n",
+              its, fnorm, ynorm, xnorm, lambda, nfuncs, reason, im, F[im], X[im], iy, Y[iy], X[iy]);
+    }
     if (reason) break;
   }
   if (!reason) reason = SNES_DIVERGED_MAX_IT;
 
 done:
+  if (snes_monitor()) fprintf(stderr, "snes done: reason %d its %d nfuncs %d fnorm0 %.6e fnorm %.6e ynorm %.6e lambda %.3e\n", reason, its, nfuncs, res->fnorm0, fnorm, ynorm, lambda);
   res->reason = reason; res->its = its; res->nfuncs = nfuncs;
   res->fnorm = fnorm; res->xnorm = xnorm; res->ynorm = ynorm; res->last_lambda = lambda;
   free(F); free(ja);

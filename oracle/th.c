@@ -254,6 +254,23 @@ int orc_th_set_soils(orc_th *p, const double *watsat, const double *hksat, const
   return rc;
 }
 
+/* ThermEnthalpySetSoilPermeability -> ThermalEnthalpySoilAuxVarSetAbsPerm (GoveqnThermalEnthalpySoilType.F90:2454-2480,
+ * ThermalEnthalpySoilAuxMod.F90): internal aux vars, then every boundary aux var copies its cell's value.  Called by the
+ * standalone drivers (th_mms_problem.F90:739); MPPTHSetSoils does not (MultiPhysicsProbTH.F90:293). */
+int orc_th_set_energy_perm(orc_th *p, const double *perm)
+{
+  int i, k;
+  for (i = 0; i < p->ncells; i++) p->ea[i].r.perm[0] = p->ea[i].r.perm[1] = p->ea[i].r.perm[2] = perm[i];
+  for (k = 0; k < p->nbc; k++) for (i = 0; i < p->bc[k].nconn; i++) {
+    if (p->bc[k].raux) continue;
+    {
+      eaux *a = &p->bc[k].eaux_[i]; const eaux *s = &p->ea[p->bc[k].conn[i].id_dn];
+      a->r.perm[0] = s->r.perm[0]; a->r.perm[1] = s->r.perm[1]; a->r.perm[2] = s->r.perm[2];
+    }
+  }
+  return 0;
+}
+
 int orc_th_restart(orc_th *p, const double *press, const double *temp)
 {
   int i;

@@ -54,12 +54,10 @@ def test_vsfm_4Mi_columns_mass_balance_determinism_and_sampled_parity(mpp, oracl
         p.close()
     P, m0, m1, st = runs[0]
     assert np.array_equal(P, runs[1][0]) and np.array_equal(st["newton_its"], runs[1][3]["newton_its"])
-    ok = (st["reasons"] > 0)
-    assert ok.mean() > 0.99999                                           # a handful of hard columns may fail
+    assert conv and (st["reasons"] > 0).all() and (st["dt_cuts"] == 0).all()    # the benchmark batch converges column by column, no dt cut
     q = d["infil"] + d["et"].reshape(ncol, nlev).sum(1)
     err = np.abs(m0 - m1 + q * 1800.0)
-    clean = ok & (st["dt_cuts"] == 0)
-    assert err[clean].max() < 1e-5
+    assert err.max() < 1e-5                                              # the reference's gate, MPPVSFMALM_Driver.F90:140
     assert np.isfinite(P).all()
     rng = np.random.default_rng(7)
     cols = np.sort(rng.choice(ncol, 1024, replace=False))
@@ -70,10 +68,10 @@ def test_vsfm_4Mi_columns_mass_balance_determinism_and_sampled_parity(mpp, oracl
     for step in range(2):
         convo, reasono, outo = PB.elm_vsfm_step(o, oids, ds, 1800.0, step + 1)
     so = o.stats()
-    same = (so["dt_cuts"] == 0) & (so["reasons"] > 0)
+    assert convo and (so["dt_cuts"] == 0).all()
     Pg = P.reshape(ncol, nlev)[cols]
-    assert relmax_p(Pg[same], outo["pressure"].reshape(-1, nlev)[same]) < RTOL
-    assert np.array_equal(st["newton_its"][cols][same], so["newton_its"][same])
+    assert relmax_p(Pg, outo["pressure"].reshape(-1, nlev)) < RTOL       # every sampled column
+    assert np.mean(st["newton_its"][cols] != so["newton_its"]) < 0.005   # (a convergence test may sit on a rounding edge)
 
 
 def test_thermal_1Mi_columns_energy_balance_and_sampled_parity(mpp, oracle):
@@ -98,26 +96,33 @@ def test_thermal_1Mi_columns_energy_balance_and_sampled_parity(mpp, oracle):
 
 
 def test_th_256Ki_columns_sampled_parity(mpp, oracle):
-    """configs[4] per-GPU share (2 Mi columns over 8 GPUs): 256 Ki columns x 15 layers, one step; 256 sampled columns vs the oracle."""
+    """configs[4] per-GPU share (2 Mi columns over 8 GPUs): 256 Ki columns x 15 layers of the benchmark's TH batch (ELM's default curve
+    smooth_brooks_corey_bz3), two steps; every column converges, and 512 sampled columns agree with the oracle to 1e-10 -- all of them,
+    including any that needed a dt cut."""
+    import bench
     ncol, nlev = 1 << 18, 15
-    d = PB.elm_th_inputs(ncol, nlev)
+    d = bench.shard_inputs_th(0, ncol)
     p, ids = PB.build_elm_th(mpp.TH, d)
-    conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, 1)
+    for step in range(2):
+        conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, step + 1)
+        assert conv
     st = p.stats()
-    assert (st["reasons"] > 0).mean() > 0.9999 and np.isfinite(out["pressure"]).all() and np.isfinite(out["temperature"]).all()
+    assert (st["reasons"] > 0).all() and np.isfinite(out["pressure"]).all() and np.isfinite(out["temperature"]).all()
     rng = np.random.default_rng(9)
-    cols = np.sort(rng.choice(ncol, 256, replace=False))
+    cols = np.sort(np.unique(np.concatenate([rng.choice(ncol, 512, replace=False), np.nonzero(st["dt_cuts"] > 0)[0][:16]])))
     ds = _take_columns(d, cols, ("dz", "watsat", "hksat", "bsw", "sucsat", "residual_sat", "area", "infil", "dew", "snow", "sublim", "csol", "tkdry", "T_top", "P_top_bc"),
                        ("press_ic", "et", "drain", "frac_liq", "temp_ic", "heat"), nlev)
-    ds.update(ncol=len(cols), nlev=nlev, satfunc="van_genuchten", density_type=d["density_type"], iee_type=d["iee_type"])
+    ds.update(ncol=len(cols), nlev=nlev, satfunc=d["satfunc"], density_type=d["density_type"], iee_type=d["iee_type"])
     o, oids = PB.build_elm_th(oracle.OracleTH, ds, per_column=True, nthreads=8)
-    convo, reasono, outo = PB.elm_th_step(o, oids, ds, 1800.0, 1)
+    for step in range(2):
+        convo, reasono, outo = PB.elm_th_step(o, oids, ds, 1800.0, step + 1)
+        assert convo
     so = o.stats()
-    same = (so["dt_cuts"] == 0) & (so["reasons"] > 0) & (so["newton_its"] == st["newton_its"][cols])
-    assert same.mean() > 0.97
+    assert np.array_equal(so["dt_cuts"], st["dt_cuts"][cols])
     for k in ("pressure", "temperature", "sat"):
-        a, b = out[k].reshape(ncol, nlev)[cols][same], outo[k].reshape(-1, nlev)[same]
-        assert (relmax_p if k == "pressure" else relmax)(a, b) < RTOL, k
+        a, b = out[k].reshape(ncol, nlev)[cols], outo[k].reshape(-1, nlev)
+        rm = (relmax_p if k == "pressure" else relmax)(a, b)
+        assert rm < RTOL, (k, rm)
 
 
 def test_snow_thermal_1Mi_columns_uniform_state_is_a_fixed_point_and_sampled_parity(mpp, oracle):

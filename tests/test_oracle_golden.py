@@ -172,6 +172,36 @@ def test_mass_and_heat_reproduces_reference_baseline(oracle, golden):
             assert abs(ours - val) <= 1e-11 * abs(val), (name, key, ours, val)
 
 
+# th_mms temperature bar.  The reference solves every Newton system INEXACTLY (GMRES + ILU(0) on the segregated [P | T] ordering, KSP
+# rtol 1e-5), so its last iterate is only as converged as its own SNES test demands: ||F|| <= 1e-8 ||F0|| = 3.3e-6 W here, which a
+# smooth temperature error of a few 1e-5 K satisfies (second differences of a smooth error are tiny).  With constant density the mass
+# equation does not see the temperature at all, its Newton systems are tridiagonal and the reference's ILU(0) is exact for them -- and
+# there the restatement reproduces EVERY printed digit of the baseline's pressures.  The exact-Newton restatement converges the
+# temperature eight orders further than the reference did; the two then differ by the reference's own stopping error (measured 2.1e-5 K
+# at most).  The reference suite's 1e-8 K (regression_tests/th/th.cfg:8-9) only holds against the same inexact solver.
+TH_MMS_T_ABS = 5.0e-5
+
+
+def test_th_mms_reproduces_reference_baseline(oracle, golden):
+    """regression_tests/th/th_mms.regression.baseline (src/driver/standalone/thermal-e/th_mms_problem.F90: manufactured steady state,
+    20 cells along x, constant density, IFC-67 enthalpy, per-cell permeability in BOTH governing equations, Dirichlet P and T at both ends,
+    per-cell mass and heat sources built from the driver's own finite-difference formulas)."""
+    p, ids, d = PB.build_th_mms(oracle.OracleTH, oracle.OraclePhysics())
+    conv, reason, P, T = PB.run_th_mms(p, ids, d)
+    assert conv and reason == 3
+    for name, data, check in (("liquid_pressure", P, lambda a, b: "%.13E" % a == "%.13E" % b or abs(a - b) <= 1e-8),
+                              ("temperature", T, lambda a, b: abs(a - b) <= TH_MMS_T_ABS)):
+        for key, val in golden["th_mms"][name].items():
+            if key == "category":
+                continue
+            ours = {"min": data.min(), "max": data.max(), "mean": data.sum() / data.size}.get(key)
+            if ours is None:
+                ours = data[int(key.split()[1]) - 1]
+            assert check(ours, val), (name, key, ours, val)
+    # and the discrete solution sits where a second-order scheme on 20 cells should: within 1 % of the manufactured fields
+    assert np.max(np.abs(P - d["P_exact"])) < 1e-2 * 15000.0 * 7 and np.max(np.abs(T - d["T_exact"])) < 0.3
+
+
 @pytest.mark.parametrize("dens,iee", [(K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_CONSTANT), (K.DENSITY_IFC67, K.INT_ENERGY_ENTHALPY_IFC67)])
 def test_th_analytic_jacobian_blocks_vs_finite_differences(oracle, dens, iee):
     """The 2x2 block-tridiagonal Jacobian restated from GoveqnRichards...:1941-2200, 2333-2613 and

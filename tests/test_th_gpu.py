@@ -49,31 +49,82 @@ def test_mass_and_heat_vs_reference_baseline(mpp, golden, oracle):
             assert abs(ours - val) <= 1e-11 * abs(val), (name, key, ours, val)
 
 
-@pytest.mark.parametrize("dens,iee", [(K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_CONSTANT), (K.DENSITY_IFC67, K.INT_ENERGY_ENTHALPY_IFC67)])
-def test_elm_like_th_batch_matches_oracle(mpp, oracle, dens, iee):
+def test_th_mms_vs_reference_baseline(mpp, golden, oracle):
+    """regression_tests/th/th_mms.regression.baseline: 20 cells (generic kernel), constant density + IFC-67 enthalpy, the energy
+    equation's own per-cell permeability (mppgpu_th_set_energy_permeability), Dirichlet P and T at both ends, per-cell sources.
+    GPU vs oracle 1e-10 on every cell; against the baseline: pressure to 1e-8 Pa (its printed resolution), temperature within the
+    reference's own inexact-solve stopping error (tests/test_oracle_golden.py:TH_MMS_T_ABS)."""
+    from mpp_b200.hostphysics import HostPhysics
+    p, ids, d = PB.build_th_mms(mpp.TH, HostPhysics())
+    conv, reason, P, T = PB.run_th_mms(p, ids, d)
+    o, oids, do = PB.build_th_mms(oracle.OracleTH, oracle.OraclePhysics(), per_column=True)
+    convo, reasono, Po, To = PB.run_th_mms(o, oids, do)
+    assert conv and convo and reason == reasono == 3
+    # the two set-ups build their manufactured sources with their own EOS code: identical to round-off
+    assert relmax(d["heat_source"], do["heat_source"]) < 1e-9 and relmax(d["mass_source"], do["mass_source"]) < 1e-12
+    assert relmax_p(P, Po) < RTOL and relmax(T, To) < RTOL
+    assert int(p.stats()["newton_its"][0]) == int(o.stats()["newton_its"][0])
+    for name, data, tol in (("liquid_pressure", P, 2e-8), ("temperature", T, 5.0e-5)):
+        for key, val in golden["th_mms"][name].items():
+            if key == "category":
+                continue
+            ours = {"min": data.min(), "max": data.max(), "mean": data.sum() / data.size}.get(key)
+            if ours is None:
+                ours = data[int(key.split()[1]) - 1]
+            assert abs(ours - val) <= tol, (name, key, ours, val)
+
+
+# IFC-67 exception (DESIGN.md section 2).  The IFC-67 density / enthalpy polynomials carry ~1e-13 of relative round-off, and the
+# accumulation term (energy now - energy at soln_prev) cancels three more digits, so the residual norm bottoms out near 1e-9 ||F0||:
+# the reference's own stopping test (rtol 1e-8) sits on that noise, the tolerances cannot be tightened (at rtol 1e-9 the oracle itself
+# starts cutting dt), and two correct implementations may stop one Newton update apart.  In saturated cells the pressure is set by
+# compressibility alone (dF/dP ~ 5e-12 kmol/s/Pa), which turns the same noise into ~1e-5 Pa.  Bound used for EVERY column: 1e-9.
+IFC67_TOL = 1e-9
+
+
+@pytest.mark.parametrize("satfunc,dens,iee", [("van_genuchten", K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_CONSTANT),
+                                              ("smooth_brooks_corey_bz3", K.DENSITY_TGDPB01, K.INT_ENERGY_ENTHALPY_CONSTANT),
+                                              ("van_genuchten", K.DENSITY_IFC67, K.INT_ENERGY_ENTHALPY_IFC67)])
+def test_elm_like_th_batch_matches_oracle(mpp, oracle, satfunc, dens, iee):
+    """Reference tolerances (rtol 1e-8, stol 1e-10): identical control flow (dt cuts, convergence) and 1e-10 on EVERY column for the
+    Tanaka / constant-c_p models (van Genuchten and ELM's default smooth_brooks_corey_bz3, the benchmark's TH batch)."""
     ncol = 500
-    d = PB.elm_th_inputs(ncol, 15, density_type=dens, iee_type=iee)
+    d = PB.elm_th_inputs(ncol, 15, satfunc=satfunc, density_type=dens, iee_type=iee)
     p, ids = PB.build_elm_th(mpp.TH, d)
     o, oids = PB.build_elm_th(oracle.OracleTH, d, per_column=True, nthreads=8)
+    ifc = dens == K.DENSITY_IFC67
     for step in range(3):
         conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, step + 1)
         convo, reasono, outo = PB.elm_th_step(o, oids, d, 1800.0, step + 1)
         assert conv == convo and conv
         sg, so_ = p.stats(), o.stats()
         assert np.array_equal(sg["dt_cuts"], so_["dt_cuts"])
-        # Same algorithm, same path => 1e-10.  Where the final ||F|| <= rtol ||F0|| test sits inside the rounding noise of the
-        # IFC-67 enthalpy polynomials (accumulation - accumulation_prev cancels ~3 digits), the two implementations may stop one
-        # Newton iteration apart; those columns then differ by their last update (<= 1e-8), as two builds of the reference would.
-        same = sg["newton_its"] == so_["newton_its"]
-        assert np.mean(~same) < 0.03
+        assert np.mean(sg["newton_its"] != so_["newton_its"]) < (0.03 if ifc else 0.005)
         for k in ("pressure", "temperature", "sat", "mass"):
-            a, b = out[k].reshape(ncol, 15), outo[k].reshape(ncol, 15)
             rm = relmax_p if k == "pressure" else relmax
-            # IFC-67 density carries ~1e-13 of relative round-off (long polynomial with cancellation); in saturated cells the
-            # pressure is set by compressibility alone (dF/dP ~ 5e-12 kmol/s/Pa), which turns that noise into ~1e-5 Pa
-            tol = 1e-9 if (k == "pressure" and dens == K.DENSITY_IFC67) else RTOL
-            assert rm(a[same], b[same]) < tol, (step, k, rm(a[same], b[same]))
-            assert rm(a, b) < 1e-8, (step, k, rm(a, b))
+            tol = (IFC67_TOL if k != "temperature" else RTOL) if ifc else RTOL
+            assert rm(out[k], outo[k]) < tol, (step, k, rm(out[k], outo[k]))
+
+
+@pytest.mark.parametrize("satfunc", ["van_genuchten", "smooth_brooks_corey_bz3"])
+def test_elm_like_th_batch_tight_tolerances_every_column(mpp, oracle, satfunc):
+    """Both implementations pushed onto the same fixed point (rtol 1e-10, stol 1e-12: one Newton update beyond the reference's defaults;
+    the residual's round-off floor is ~1e-11 ||F0||, below that the reference algorithm itself fails its line search): pressure,
+    temperature, saturation and mass agree to 1e-10 on 100 % of the columns, no column excluded."""
+    ncol = 500
+    d = PB.elm_th_inputs(ncol, 15, satfunc=satfunc)
+    p, ids = PB.build_elm_th(mpp.TH, d)
+    o, oids = PB.build_elm_th(oracle.OracleTH, d, per_column=True, nthreads=8)
+    for s in (p, o):
+        s.set_tolerances(1e-50, 1e-10, 1e-12, 50, 10000)
+    for step in range(3):
+        conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, step + 1)
+        convo, reasono, outo = PB.elm_th_step(o, oids, d, 1800.0, step + 1)
+        assert conv and convo
+        assert np.array_equal(p.stats()["dt_cuts"], o.stats()["dt_cuts"])
+        for k in ("pressure", "temperature", "sat", "mass"):
+            rm = relmax_p if k == "pressure" else relmax
+            assert rm(out[k], outo[k]) < RTOL, (satfunc, step, k, rm(out[k], outo[k]))
 
 
 @pytest.mark.parametrize("ncol,nlev", [(1, 1), (3, 2), (5, 16), (2, 40), (37, 15)])
@@ -174,12 +225,12 @@ def test_th_pressure_and_temperature_dirichlet_boundaries(mpp, oracle, nlev):
         convo, reasono = o[0].step_dt(1800.0, step + 1)
         assert conv == convo
         sg, so_ = g[0].stats(), o[0].stats()
-        ok = (so_["reasons"] > 0) & (so_["dt_cuts"] == 0) & (sg["newton_its"] == so_["newton_its"])
-        assert ok.mean() > 0.9
+        assert np.array_equal(sg["dt_cuts"], so_["dt_cuts"]) and np.array_equal(sg["reasons"] > 0, so_["reasons"] > 0)
+        assert conv and convo                                      # every column converges (some after dt cuts)
         for var, key, ieqn in ((K.VAR_PRESSURE, "P", 1), (K.VAR_TEMPERATURE, "T", 2)):
             a = g[0].get_data(K.AUXVAR_INTERNAL, var, 1, ieqn=ieqn).reshape(ncol, nlev)
             b = o[0].get_data(K.AUXVAR_INTERNAL, var, 1, ieqn=ieqn).reshape(ncol, nlev)
-            assert (relmax_p if key == "P" else relmax)(a[ok], b[ok]) < RTOL, (step, key)
+            assert (relmax_p if key == "P" else relmax)(a, b) < RTOL, (step, key, (relmax_p if key == "P" else relmax)(a, b))
     # the boundaries act on the bottom cell
     Tg = g[0].get_data(K.AUXVAR_INTERNAL, K.VAR_TEMPERATURE, 1, ieqn=2).reshape(ncol, nlev)
     Pg = g[0].get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1, ieqn=1).reshape(ncol, nlev)
@@ -202,9 +253,10 @@ def test_th_model_combinations_through_the_runtime_dispatch(mpp, oracle, satfunc
         convo, reasono, outo = PB.elm_th_step(o, oids, d, 1800.0, step + 1)
         assert conv == convo
         sg, so_ = p.stats(), o.stats()
-        same = (sg["newton_its"] == so_["newton_its"]) & (so_["dt_cuts"] == 0) & (so_["reasons"] > 0)
-        assert same.mean() > 0.9
+        assert np.array_equal(sg["dt_cuts"], so_["dt_cuts"]) and np.array_equal(sg["reasons"] > 0, so_["reasons"] > 0)
         ifc = dens == K.DENSITY_IFC67 or iee == K.INT_ENERGY_ENTHALPY_IFC67
+        okc = so_["reasons"] > 0                                   # a column out of dt cuts leaves no mailbox to compare
         for k in ("pressure", "temperature", "sat"):
-            a, b = out[k].reshape(ncol, 15)[same], outo[k].reshape(ncol, 15)[same]
-            assert (relmax_p if k == "pressure" else relmax)(a, b) < (1e-9 if (ifc and k == "pressure") else RTOL), (step, k)
+            a, b = out[k].reshape(ncol, 15)[okc], outo[k].reshape(ncol, 15)[okc]
+            rm = (relmax_p if k == "pressure" else relmax)(a, b)
+            assert rm < ((IFC67_TOL if k != "temperature" else RTOL) if ifc else RTOL), (step, k, rm)
