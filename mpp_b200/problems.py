@@ -691,8 +691,10 @@ def th_mms_data(phys, nx=20):
     return d
 
 
-def build_th_mms(cls, phys, nx=20, **kw):
-    d = th_mms_data(phys, nx)
+def build_th_mms(cls, phys, nx=20, data=None, **kw):
+    """`data`: a th_mms_data() result to reuse (parity tests hand both implementations the SAME source arrays: the driver's
+    finite-difference formulas, step 1e-6, amplify the last-ulp differences between two EOS implementations to ~1e-5 relative)."""
+    d = data if data is not None else th_mms_data(phys, nx)
     p = cls(1, nx, **kw)
     p.set_mesh(K.MESH_HORIZONTAL, np.full((1, nx), d["dx"]), np.array([1.0]))             # connections along x, area = dy*dz = 1 (:205-292)
     ids = {"p0": p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS),       # 'Pressure BC', both ends (:343-355)

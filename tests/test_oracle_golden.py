@@ -172,13 +172,14 @@ def test_mass_and_heat_reproduces_reference_baseline(oracle, golden):
             assert abs(ours - val) <= 1e-11 * abs(val), (name, key, ours, val)
 
 
-# th_mms temperature bar.  The reference solves every Newton system INEXACTLY (GMRES + ILU(0) on the segregated [P | T] ordering, KSP
-# rtol 1e-5), so its last iterate is only as converged as its own SNES test demands: ||F|| <= 1e-8 ||F0|| = 3.3e-6 W here, which a
-# smooth temperature error of a few 1e-5 K satisfies (second differences of a smooth error are tiny).  With constant density the mass
-# equation does not see the temperature at all, its Newton systems are tridiagonal and the reference's ILU(0) is exact for them -- and
-# there the restatement reproduces EVERY printed digit of the baseline's pressures.  The exact-Newton restatement converges the
-# temperature eight orders further than the reference did; the two then differ by the reference's own stopping error (measured 2.1e-5 K
-# at most).  The reference suite's 1e-8 K (regression_tests/th/th.cfg:8-9) only holds against the same inexact solver.
+# th_mms temperature bar.  Two things keep the reference's 1e-8 K (regression_tests/th/th.cfg:8-9) out of reach of anything but the
+# reference binary itself.  (i) Its driver differentiates the enthalpy and the Kersten number NUMERICALLY with a step of 1e-6 m
+# (th_mms_problem.F90:1203, 1396-1440): the ~1e-13 relative round-off of the IFC-67 polynomials is divided by 2e-6, so the heat source
+# depends on the EOS implementation's last ulp to ~1e-5 relative (measured between this repo's two EOS implementations: 7e-6), and the
+# temperature to ~1e-5 K.  (ii) The reference solves every Newton system inexactly (GMRES + ILU(0) on the segregated [P | T] ordering,
+# KSP rtol 1e-5), so its last iterate is only as converged as ||F|| <= 1e-8 ||F0|| = 3.3e-6 W demands.  With constant density the mass
+# equation sees neither effect -- no numerical derivative survives, its Newton systems are tridiagonal (ILU(0) exact) -- and there the
+# restatement reproduces EVERY printed digit of the baseline's pressures.  Measured temperature deviation: 2.1e-5 K at most.
 TH_MMS_T_ABS = 5.0e-5
 
 

@@ -52,18 +52,26 @@ def test_mass_and_heat_vs_reference_baseline(mpp, golden, oracle):
 def test_th_mms_vs_reference_baseline(mpp, golden, oracle):
     """regression_tests/th/th_mms.regression.baseline: 20 cells (generic kernel), constant density + IFC-67 enthalpy, the energy
     equation's own per-cell permeability (mppgpu_th_set_energy_permeability), Dirichlet P and T at both ends, per-cell sources.
-    GPU vs oracle 1e-10 on every cell; against the baseline: pressure to 1e-8 Pa (its printed resolution), temperature within the
-    reference's own inexact-solve stopping error (tests/test_oracle_golden.py:TH_MMS_T_ABS)."""
+    GPU vs oracle 1e-10 on every cell (same source arrays); against the baseline: pressure to 2e-8 Pa (its printed resolution), temperature
+    within what the driver's finite-difference source terms allow (tests/test_oracle_golden.py:TH_MMS_T_ABS)."""
     from mpp_b200.hostphysics import HostPhysics
-    p, ids, d = PB.build_th_mms(mpp.TH, HostPhysics())
+    p, ids, d = PB.build_th_mms(mpp.TH, HostPhysics())                     # as tools/standalone_mpp runs it: sources from the product's own EOS code
     conv, reason, P, T = PB.run_th_mms(p, ids, d)
     o, oids, do = PB.build_th_mms(oracle.OracleTH, oracle.OraclePhysics(), per_column=True)
     convo, reasono, Po, To = PB.run_th_mms(o, oids, do)
     assert conv and convo and reason == reasono == 3
-    # the two set-ups build their manufactured sources with their own EOS code: identical to round-off
-    assert relmax(d["heat_source"], do["heat_source"]) < 1e-9 and relmax(d["mass_source"], do["mass_source"]) < 1e-12
-    assert relmax_p(P, Po) < RTOL and relmax(T, To) < RTOL
-    assert int(p.stats()["newton_its"][0]) == int(o.stats()["newton_its"][0])
+    # The driver differentiates the enthalpy and the Kersten number numerically with a step of 1e-6 m (th_mms_problem.F90:1203, 1396-1440):
+    # that divides the ~1e-13 relative round-off of the IFC-67 polynomials by 2e-6, so two correct EOS implementations (this library's
+    # lean device math compiled for the host, the oracle's libm restatement, the reference's Fortran) get heat sources that differ by
+    # ~1e-5 relative, and temperatures that differ by ~1e-5 K.  The mass source has no such term (constant density) and agrees to round-off.
+    assert relmax(d["mass_source"], do["mass_source"]) < 1e-12 and relmax(d["heat_source"], do["heat_source"]) < 1e-4
+    assert relmax_p(P, Po) < RTOL and np.max(np.abs(T - To)) < 5.0e-5
+    # parity proper: the SAME source arrays through both implementations, 1e-10 on every cell
+    g2, ids2, _ = PB.build_th_mms(mpp.TH, None, data=do)
+    conv2, reason2, P2, T2 = PB.run_th_mms(g2, ids2, do)
+    assert conv2 and reason2 == 3
+    assert relmax_p(P2, Po) < RTOL and relmax(T2, To) < RTOL
+    assert int(g2.stats()["newton_its"][0]) == int(o.stats()["newton_its"][0])
     for name, data, tol in (("liquid_pressure", P, 2e-8), ("temperature", T, 5.0e-5)):
         for key, val in golden["th_mms"][name].items():
             if key == "category":
