@@ -23,6 +23,8 @@
  *   soe%SetDataFromCLM               SystemOfEquationsVSFMType.F90:663-724      mppgpu_set_data
  *   soe%SetSolnPrevCLM/SetRDataFromCLM/SetIDataFromCLM/SetBDataFromCLM
  *                                    SystemOfEquationsThermalType.F90:171-330   mppgpu_set_data / mppgpu_set_idata
+ *   soe%GetDataForCLM(AUXVAR_CONN_INTERNAL, VAR_MASS_FLUX): SystemOfEquationsVSFMType.F90:824 -> mppgpu_get_data(.., 704, 644, ..),
+ *                                    ncol*(nlev-1) internal-connection mass fluxes [kg/s], connection j->j+1 of column c at c*(nlev-1)+j
  *   soe%GetDataForCLM, GetSoln       SystemOfEquationsVSFMType.F90:781-845,
  *                                    SystemOfEquationsThermalType.F90:336       mppgpu_get_data
  *   soe%PreStepDT                    SystemOfEquationsVSFMType.F90:892-923      mppgpu_pre_step_dt
@@ -248,7 +250,12 @@ int  mppgpu_global_mass_balance(mppgpu_handle h, double sums[4], double maxs[4],
 /* launches made by the library since creation, and device-time of the last StepDT kernel(s) in ms */
 int  mppgpu_launch_count(mppgpu_handle h, long long *n);
 int  mppgpu_last_step_ms(mppgpu_handle h, float *ms);
-/* one residual + Jacobian evaluation (VSFM: f, ja, jb, jc of ncells; TH: 2N / 4N blocks) for kernel unit tests */
+/* One residual + Jacobian evaluation at x with the accumulation term of the start of the step taken at x_prev: the finer seam of the
+ * reference, SOEResidual / SOEJacobian (SystemOfEquationsBasePointerType.F90:40-109 -> VSFMSOEResidual / VSFMJacobian
+ * SystemOfEquationsVSFMType.F90:94-403, SOETHResidual / SOETHJacobian SystemOfEquationsTHType.F90:736-1004), as a debugging cross-check.
+ * VSFM (nlev <= 32): f and the sub-, main and super-diagonal ja, jb, jc of the tridiagonal Jacobian, ncells values each, cell order,
+ * written by the EVAL instance of the fused step kernel (the same assembly code the time step runs).  TH: x interleaved (P, T) per
+ * cell, f of 2N, 2x2 row-major blocks ja, jb, jc of 4N each.  Not available for the (linear) thermal SoE. */
 int  mppgpu_eval(mppgpu_handle h, double dt, const double *x_prev, const double *x, double *f, double *ja, double *jb, double *jc);
 
 #ifdef __cplusplus

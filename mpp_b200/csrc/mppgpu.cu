@@ -38,7 +38,7 @@ enum { VAR_PRESSURE = 604, VAR_TEMPERATURE = 605, VAR_BC_SS_CONDITION = 607, VAR
        VAR_ICE_AREAL_DEN = 617, VAR_FRAC = 618, VAR_SNOW_WATER = 619, VAR_NUM_SNOW_LYR = 620, VAR_DHS_DT = 621,
        VAR_THERMAL_COND = 622, VAR_HEAT_CAP = 623, VAR_ACTIVE = 624, VAR_DZ = 627, VAR_DIST_UP = 628,
        VAR_DIST_DN = 629, VAR_TUNING_FACTOR = 630, VAR_POT_MASS_SINK_PRESSURE = 638, VAR_POT_MASS_SINK_EXPONENT = 639, VAR_MASS_FLUX = 644 };
-enum { AUXVAR_INTERNAL = 701, AUXVAR_BC = 702, AUXVAR_SS = 703 };
+enum { AUXVAR_INTERNAL = 701, AUXVAR_BC = 702, AUXVAR_SS = 703, AUXVAR_CONN_INTERNAL = 704 };
 
 static thread_local std::string g_err;
 static int fail(const char *fmt, ...)
@@ -89,6 +89,7 @@ struct mppgpu_soe {
   DevBuf<double> col_mass, col_err, col_src, block_partials, red_out, red_scratch; DevBuf<unsigned int> red_counter;
   double *h_red = nullptr;     // pinned mirror of red_out (9 doubles)
   // launch order of the step kernel (vsfm_kernels.cuh "launch order"): built after every StepDT from its per-column cost
+  DevBuf<double> conn_flux;          // internal-connection mass fluxes, filled on demand (vsfm_conn_flux_kernel)
   DevBuf<int> order, order_counts; bool order_valid = false; int order_chunks = 0; long long order_per = 0; int ordering = 1;
   int nblocks_last = 0;
   bool result_pending = false;
@@ -553,6 +554,22 @@ static int vsfm_field(mppgpu_soe *h, int auxvar_type, int var_type, int cond_id,
     }
     return fail("In VSFMSOEAuxVar%sValue: unknown var_type %d", for_set ? "Set" : "Get", var_type);
   }
+  if (auxvar_type == AUXVAR_CONN_INTERNAL) {
+    // SystemOfEquationsVSFMType.F90:824: one aux var per internal connection, mass_flux [kg/s] of the committed state
+    if (for_set || var_type != VAR_MASS_FLUX) return fail("In VSFMSOEAuxVar%sValue: unknown var_type %d", for_set ? "Set" : "Get", var_type);
+    if (!h->mesh_set || !h->soils_set) return fail("VSFMSOEGetDataForCLM: mesh and soils must be set first");
+    const size_t nconn = (size_t)h->ncol * (size_t)(h->nlev > 1 ? h->nlev - 1 : 0);
+    *cap = nconn;
+    if (!nconn) { *p = nullptr; return 0; }
+    if (h->conn_flux.n < nconn && h->conn_flux.alloc(nconn) != cudaSuccess) return fail("alloc conn_flux");
+    VsfmArgs A;
+    vsfm_fill_args(h, A, 1.0);
+    const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
+    vsfm_conn_flux_kernel<<<nblk((long long)nconn, 256), 256, 0, h->stream>>>(A, sf, h->pressure.p, h->conn_flux.p);
+    CK(cudaGetLastError());
+    h->launches += 1;
+    *p = h->conn_flux.p; return 0;
+  }
   if (auxvar_type != AUXVAR_BC && auxvar_type != AUXVAR_SS) return fail("VSFMSOE%sData: Unknown soe_auxvar_type %d", for_set ? "Set" : "Get", auxvar_type);
   HostCond *c = find_cond(h, auxvar_type, cond_id);
   if (!c) return fail("VSFMSOE%sData: condition id %d out of range", for_set ? "Set" : "Get", cond_id);
@@ -657,12 +674,14 @@ static int vsfm_fill_args(mppgpu_soe *h, VsfmArgs &A, double dt)
 }
 
 template <int LPC>
-static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A, int nblocks)
+static void launch_vsfm2(mppgpu_soe *h, const VsfmArgs &A0, int nblocks)
 {
+  VsfmArgs A = A0;
+  vsfm_compact_sources(A);
   const int sf = (h->satfunc_name == MPPGPU_SATFUNC_VAN_GENUCHTEN) ? SATFUNC_VG : (h->satfunc_name == MPPGPU_SATFUNC_BROOKS_COREY ? SATFUNC_BC : SATFUNC_SBC);
   // the specialisation that carries boundary conditions, the down-regulated sink and the IFC-67 density polynomial
   const bool bc = A.nbc > 0 || A.dr_type != 0 || A.dtab.type == DENSITY_IFC67;
-  const int variant = A.retry_mask ? 2 : (bc ? 1 : 0);
+  const int variant = A.eval_x ? 3 : (A.retry_mask ? 2 : (bc ? 1 : 0));
   // the 18 instances live in vsfm_step2_inst.cu, one translation unit per (LPC, saturation function)
   if (LPC == 8) { if (sf == SATFUNC_VG) vsfm2_launch_8_0(A, variant, nblocks, h->stream); else if (sf == SATFUNC_BC) vsfm2_launch_8_1(A, variant, nblocks, h->stream); else vsfm2_launch_8_2(A, variant, nblocks, h->stream); }
   else          { if (sf == SATFUNC_VG) vsfm2_launch_16_0(A, variant, nblocks, h->stream); else if (sf == SATFUNC_BC) vsfm2_launch_16_1(A, variant, nblocks, h->stream); else vsfm2_launch_16_2(A, variant, nblocks, h->stream); }
@@ -697,6 +716,7 @@ static void vsfm_offset_args(VsfmArgs &A, int nlev, long long col0, int n, long 
   A.block_partials += block0 * 9;
   if (A.t_done) A.t_done += col0;
   if (A.order) A.order += col0;
+  if (A.eval_x) { A.eval_x += c; A.eval_f += c; A.eval_ja += c; A.eval_jb += c; A.eval_jc += c; }
   if (A.retry_mask) { A.retry_mask += col0; A.dt_col += col0; A.rtol_col += col0; A.stol_col += col0; A.x_redo += c; }
   A.ncol = n;
 }
@@ -944,10 +964,39 @@ extern "C" int mppgpu_last_step_ms(mppgpu_handle h, float *ms)
   return 0;
 }
 
+// VSFMSOEResidual + VSFMJacobian (SystemOfEquationsVSFMType.F90:94-403) at x, with the accumulation of the start of the step taken at
+// x_prev: the EVAL instance of the fused step kernel dumps the residual and the three Jacobian bands it assembles (N values each, cell order)
+static int vsfm_eval(mppgpu_soe *h, double dt, const double *x_prev, const double *x, double *f, double *ja, double *jb, double *jc)
+{
+  if (!h->mesh_set || !h->soils_set) return fail("mppgpu_eval: mesh and soils must be set first");
+  if (!x_prev || !x || !f || !ja || !jb || !jc) return fail("mppgpu_eval: null argument");
+  if (h->nlev > 32) return fail("mppgpu_eval: the VSFM probe covers the fused kernel (nlev <= 32); nlev = %d runs on the generic kernel", h->nlev);
+  if (!(dt > 0.0)) return fail("mppgpu_eval: dt must be positive");
+  const size_t N = h->ncells;
+  DevBuf<double> dxp, dx, df, da, db, dc;
+  CK(dxp.alloc(N)); CK(dx.alloc(N)); CK(df.alloc(N)); CK(da.alloc(N)); CK(db.alloc(N)); CK(dc.alloc(N));
+  CK(cudaMemcpyAsync(dxp.p, x_prev, N * 8, cudaMemcpyHostToDevice, h->stream));
+  CK(cudaMemcpyAsync(dx.p, x, N * 8, cudaMemcpyHostToDevice, h->stream));
+  VsfmArgs A;
+  vsfm_fill_args(h, A, dt);
+  A.x_in = dxp.p; A.x_out = dxp.p;
+  A.eval_x = dx.p; A.eval_f = df.p; A.eval_ja = da.p; A.eval_jb = db.p; A.eval_jc = dc.p;
+  const int nblocks = vsfm_blocks_for(h, h->ncol);
+  if (h->block_partials.n < (size_t)nblocks * 9) CK(h->block_partials.alloc((size_t)nblocks * 9));
+  A.block_partials = h->block_partials.p;
+  if (vsfm_launch_range(h, A, 0, h->ncol, 0, h->stream)) return 1;
+  CK(cudaMemcpyAsync(f, df.p, N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(ja, da.p, N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(jb, db.p, N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaMemcpyAsync(jc, dc.p, N * 8, cudaMemcpyDeviceToHost, h->stream));
+  CK(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
 extern "C" int mppgpu_eval(mppgpu_handle h, double dt, const double *x_prev, const double *x, double *f, double *ja, double *jb, double *jc)
 {
   CHECK_H(h);
-  if (h->soe_itype == MPPGPU_SOE_RE_ODE) return fail("mppgpu_eval: VSFM residual/Jacobian probes are exercised through StepDT parity (not implemented)");
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) return vsfm_eval(h, dt, x_prev, x, f, ja, jb, jc);
   if (h->th) return th_eval(h, h->th, dt, x_prev, x, f, ja, jb, jc);
   return fail("mppgpu_eval: not available for the thermal SoE");
 }

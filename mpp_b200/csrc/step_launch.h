@@ -8,7 +8,8 @@ namespace mpp {
 struct VsfmArgs;
 struct THArgs;
 
-// variant: 0 plain (no boundary conditions), 1 boundary conditions / down-regulated sink / IFC-67 density, 2 the RETRY specialisation
+// variant: 0 plain (no boundary conditions), 1 boundary conditions / down-regulated sink / IFC-67 density, 2 the RETRY specialisation,
+// 3 the residual / Jacobian probe (mppgpu_eval)
 #define MPP_DECL_VSFM2(LPC, SF) void vsfm2_launch_##LPC##_##SF(const VsfmArgs &A, int variant, int nblocks, cudaStream_t s);
 MPP_DECL_VSFM2(8, 0) MPP_DECL_VSFM2(8, 1) MPP_DECL_VSFM2(8, 2) MPP_DECL_VSFM2(16, 0) MPP_DECL_VSFM2(16, 1) MPP_DECL_VSFM2(16, 2)
 #undef MPP_DECL_VSFM2

@@ -51,6 +51,10 @@ struct VsfmArgs {
   double *x_out;           // soln after the step (may alias x_in)
   int nss, nbc;
   CondDev ss[MAX_SS], bc[MAX_BC];
+  // the COND_MASS_RATE members of ss[] once more, sorted by region (filled by the launcher, vsfm_compact_sources): the fast kernel
+  // loads them without looking at types and regions
+  int nss_cell, nss_top, nss_bot;
+  const double *ss_cell[MAX_SS], *ss_top[MAX_SS], *ss_bot[MAX_SS];
   // SoE mailbox outputs (VSFMSOEPostSolve)
   double *liq_sat, *pressure, *mass, *smp;
   // per-column diagnostics
@@ -69,9 +73,23 @@ struct VsfmArgs {
   const int *retry_mask;   // 0 skip the column, 1 continue from x_in (remaining time), 2 redo from x_redo (soln_prev_clm)
   const int *retry_list; int nretry;   // compacted column indices: the retry launch is sized by the columns that need it
   const double *dt_col, *rtol_col, *stol_col, *x_redo;
+  // EVAL specialisation only (mppgpu_eval, the residual / Jacobian probe of the unit tests): accumulation taken at x_in, residual and the
+  // three Jacobian bands (sub, diagonal, super; cell order) at eval_x, no time step
+  const double *eval_x; double *eval_f, *eval_ja, *eval_jb, *eval_jc;
   // optional launch order (column indices of this launch range, most expensive first by the previous step's cost); nullptr = batch order
   const int *order;
 };
+
+inline void vsfm_compact_sources(VsfmArgs &A)
+{
+  A.nss_cell = A.nss_top = A.nss_bot = 0;
+  for (int k = 0; k < A.nss; ++k) {
+    if (A.ss[k].itype != CT_MASS_RATE) continue;
+    if (A.ss[k].region == REGION_CELLS)    A.ss_cell[A.nss_cell++] = A.ss[k].value;
+    else if (A.ss[k].region == REGION_TOP) A.ss_top[A.nss_top++] = A.ss[k].value;
+    else                                   A.ss_bot[A.nss_bot++] = A.ss[k].value;
+  }
+}
 
 // Down-regulated mass sink: actual rate [kg/s] and the Jacobian diagonal term it adds (GoveqnRichards...:1900-1927, 2158-2188)
 __device__ __forceinline__ void downreg_sink(int type, double value, double Pc, double n, double P, double &rate, double &djac)
@@ -93,6 +111,45 @@ enum { PH_INIT = 0, PH_NEWTON = 1, PH_LS_FULL = 2, PH_LS_QUAD = 3, PH_LS_CUBIC =
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
 #ifndef MPP_STEP_KERNEL_TU   // the support kernels below are compiled once, in mppgpu.cu
+
+// Internal-connection mass fluxes [kg/s] of the committed state, on demand (GetDataForCLM(AUXVAR_CONN_INTERNAL, VAR_MASS_FLUX):
+// SystemOfEquationsVSFMType.F90:824, internal_flux = flux * FMWH2O GoveqnRichards...:1809, 1199-1222).  One thread per connection
+// j -> j+1 of column c, output index c * (nlev - 1) + j (the connection set's order, MeshType.F90:509-530); the aux vars are
+// re-evaluated from the mailbox pressure with the same device functions the step kernel uses (frac_liq from the mailbox).
+// Identical to the reference's value except after a stagnation exit (reason 4 through a failed line search), where the reference keeps
+// the flux of the rejected trial point, O(stol) away from the iterate it returns.
+__device__ __forceinline__ void conn_coeffs(double perm_up, double dz_up, double perm_dn, double dz_dn, double uz, double &upw, double &Dq, double &gfac)
+{
+  const double dist_up = 0.5 * dz_up, dist_dn = 0.5 * dz_dn;
+  upw  = dist_up / (dist_up + dist_dn);
+  Dq   = (perm_up * perm_dn) / (dist_up * perm_dn + dist_dn * perm_up);
+  gfac = FMWH2O * ((dist_up + dist_dn) * (uz * (-GRAVITY_CONSTANT)));
+}
+__global__ void vsfm_conn_flux_kernel(const VsfmArgs A, int satfunc, const double *__restrict__ press, double *__restrict__ out)
+{
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int nc = A.nlev - 1;
+  if (nc <= 0 || i >= (long long)A.ncol * nc) return;
+  const long long col = i / nc; const int j = (int)(i % nc);
+  const long long cu = col * A.nlev + j, cd = cu + 1;
+  double den[2], kr[2], P[2];
+  for (int s = 0; s < 2; ++s) {
+    const long long c = s ? cd : cu;
+    SatParams sp; sp.sat_res = A.sat_res[c]; sp.alpha = A.alpha[c]; sp.m = A.lam[c]; sp.n = (satfunc == SATFUNC_VG) ? A.vgn[c] : 0.0;
+    sp.pu = sp.ps = sp.b2 = sp.b3 = 0.0;
+    if (satfunc == SATFUNC_SBC) { sp.pu = A.pu[c]; sp.ps = A.ps[c]; sp.b2 = A.b2[c]; sp.b3 = A.b3[c]; }
+    SatState st; P[s] = press[c];
+    sat_values_rt(satfunc, sp, P[s], A.frac_liq[c], st);
+    kr[s] = st.kr;
+    double dd; density_fixedT(A.dtab, P[s], den[s], dd);
+  }
+  double upw, Dq, gfac;
+  conn_coeffs(A.perm[cu], A.dz[cu], A.perm[cd], A.dz[cd], A.uz, upw, Dq, gfac);
+  const double den_ave = upw * den[0] + (1.0 - upw) * den[1];
+  const double dphi = P[0] - P[1] + den_ave * gfac;
+  const double ukvr = ((dphi >= 0.0) ? kr[0] : kr[1]) * (1.0 / VISCOSITY);
+  out[i] = (((-Dq * ukvr * dphi) * A.area[col]) * den_ave) * FMWH2O;
+}
 
 // Second stage of the deterministic reduction: `gridDim.x` blocks each fold a contiguous slice of the per-block
 // partials (fixed order), the last block to finish folds the slice results (fixed order) into out[0..8]:

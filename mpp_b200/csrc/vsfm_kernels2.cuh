@@ -33,6 +33,11 @@ namespace mpp {
 #ifndef VSFM2_THREADS
 #define VSFM2_THREADS 32
 #endif
+#ifdef VSFM2_COLD_HINTS
+#define MPP_RARE(x) __builtin_expect(!!(x), 0)
+#else
+#define MPP_RARE(x) (x)
+#endif
 #ifndef VSFM2_MIN_BLOCKS
 #define VSFM2_MIN_BLOCKS 16
 #endif
@@ -122,8 +127,9 @@ __device__ __forceinline__ SatParams par_sp(double (*par)[VSFM2_THREADS])
 __device__ __forceinline__ void conn_setup(double perm_up, double dz_up, double perm_dn, double dz_dn, double uz, double &upw, double &Dq, double &gfac)
 {
   const double dist_up = 0.5 * dz_up, dist_dn = 0.5 * dz_dn;
-  upw  = dist_up / (dist_up + dist_dn);
-  Dq   = (perm_up * perm_dn) / (dist_up * perm_dn + dist_dn * perm_up);
+  // (lean reciprocals, <= 1 ulp: the last bit of a static coefficient is far below the 1e-10 parity bar)
+  upw  = dist_up * rcp(dist_up + dist_dn);
+  Dq   = (perm_up * perm_dn) * rcp(dist_up * perm_dn + dist_dn * perm_up);
   gfac = FMWH2O * ((dist_up + dist_dn) * (uz * (-GRAVITY_CONSTANT)));       // FMWH2O * dist_gravity
 }
 
@@ -162,7 +168,10 @@ __device__ __forceinline__ void rich_flux_deriv(double P_u, double kr_u, double 
 // HAS_BC: the batch has boundary conditions and / or a down-regulated sink (compiled out for plain ELM-like batches)
 // RETRY: per-column remaining time, tolerances, start vector and a run mask (the retry loop of MPPVSFMALM_Solve); compiled as a
 // separate specialisation so that the common path keeps its register budget
-template <int LPC, int SATFUNC, bool HAS_BC, bool RETRY = false>
+// EVAL: the residual / Jacobian probe (mppgpu_eval): evaluate at x_in (accumulation of the start of the step), then at eval_x, run the
+// Newton set-up once, write F and the assembled Jacobian rows, and leave -- the SAME fused assembly code the time step runs
+constexpr int PH_VEVAL = 6;
+template <int LPC, int SATFUNC, bool HAS_BC, bool RETRY = false, bool EVAL = false>
 __global__ void __launch_bounds__(VSFM2_THREADS, VSFM2_MIN_BLOCKS)
 vsfm_step2_kernel(const VsfmArgs A)
 {
@@ -184,6 +193,9 @@ vsfm_step2_kernel(const VsfmArgs A)
   const long long cell0 = (long long)col * nlev + j0;
   const double area = col_ok ? A.area[col] : 1.0;
 
+#ifdef MPP_SMEM_MATH_TABLES
+  mpp_math_tables_to_smem();
+#endif
   // ---- static per-cell data -----------------------------------------------------------------------
   __shared__ double s_par[2][ParCount<SATFUNC>::value][VSFM2_THREADS];
   double (*const pa)[VSFM2_THREADS] = s_par[0], (*const pb)[VSFM2_THREADS] = s_par[1];
@@ -194,6 +206,46 @@ vsfm_step2_kernel(const VsfmArgs A)
   double perm0, dz0, perm1, dz1;
   cell_load<SATFUNC>(A, a, pa, col_ok && j0 < nlev, cell0, area, perm0, dz0, x_src);
   cell_load<SATFUNC>(A, b, pb, col_ok && j1 < nlev, cell0 + 1, area, perm1, dz1, x_src);
+  // mass-rate source/sinks (GoveqnRichards...:1871-1875): F -= value / FMWH2O.  The launcher has sorted the conditions by region
+  // (vsfm_compact_sources), so no type / region logic runs here; the first NC per-cell, NT top and NB bottom conditions (ELM: 2 + 4 + 0)
+  // are loaded up front under uniform predicates, any further ones in a plain loop.
+  const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
+  double src_kg = 0.0;
+  {
+    constexpr int NC = 4, NT = 6, NB = 2;
+    const bool top_a = a.valid && j0 == jtop, top_b = b.valid && j1 == jtop, bot_a = a.valid && j0 == jbot, bot_b = b.valid && j1 == jbot;
+    const bool own_top = top_a || top_b, own_bot = bot_a || bot_b;
+    double c0[NC], c1[NC], tp[NT], bt[NB];
+#pragma unroll
+    for (int k = 0; k < NC; ++k) {
+      c0[k] = 0.0; c1[k] = 0.0;
+      if (k < A.nss_cell) { const double *p = A.ss_cell[k] + cell0; if (a.valid) c0[k] = __ldg(p); if (b.valid) c1[k] = __ldg(p + 1); }
+    }
+#pragma unroll
+    for (int k = 0; k < NT; ++k) { tp[k] = 0.0; if (k < A.nss_top && own_top) tp[k] = __ldg(A.ss_top[k] + col); }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) { bt[k] = 0.0; if (k < A.nss_bot && own_bot) bt[k] = __ldg(A.ss_bot[k] + col); }
+    double sa_ = 0.0, sb_ = 0.0, st_ = 0.0, sbt_ = 0.0;
+#pragma unroll
+    for (int k = 0; k < NC; ++k) { sa_ += c0[k] * RFMW; sb_ += c1[k] * RFMW; src_kg += c0[k] + c1[k]; }
+#pragma unroll
+    for (int k = 0; k < NT; ++k) { st_ += tp[k] * RFMW; src_kg += tp[k]; }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) { sbt_ += bt[k] * RFMW; src_kg += bt[k]; }
+    for (int k = NC; k < A.nss_cell; ++k) {
+      const double *p = A.ss_cell[k] + cell0;
+      const double v0 = a.valid ? __ldg(p) : 0.0, v1 = b.valid ? __ldg(p + 1) : 0.0;
+      sa_ += v0 * RFMW; sb_ += v1 * RFMW; src_kg += v0 + v1;
+    }
+    for (int k = NT; k < A.nss_top; ++k) { const double v = own_top ? __ldg(A.ss_top[k] + col) : 0.0; st_ += v * RFMW; src_kg += v; }
+    for (int k = NB; k < A.nss_bot; ++k) { const double v = own_bot ? __ldg(A.ss_bot[k] + col) : 0.0; sbt_ += v * RFMW; src_kg += v; }
+    sa_ += (top_a ? st_ : 0.0) + (bot_a ? sbt_ : 0.0);
+    sb_ += (top_b ? st_ : 0.0) + (bot_b ? sbt_ : 0.0);
+    PA(PI_SRC) = sa_; PB(PI_SRC) = sb_;
+  }
+
+  // connections (after the source loads above were issued: the shuffles below wait for the soil tables, and anything placed behind them
+  // would start a second trip to DRAM)
   {
     const double perm_n = __shfl_down_sync(FULL, perm0, 1, LPC), dz_n = __shfl_down_sync(FULL, dz0, 1, LPC);
     a.has_conn = b.valid;                            // 2l -> 2l+1
@@ -201,30 +253,6 @@ vsfm_step2_kernel(const VsfmArgs A)
     double upw, Dq, gfac;
     conn_setup(perm0, dz0, perm1, dz1, A.uz, upw, Dq, gfac);   PA(PI_UPW) = upw; PA(PI_DQ) = Dq; PA(PI_GFAC) = gfac;
     conn_setup(perm1, dz1, perm_n, dz_n, A.uz, upw, Dq, gfac); PB(PI_UPW) = upw; PB(PI_DQ) = Dq; PB(PI_GFAC) = gfac;
-  }
-
-  // mass-rate source/sinks (GoveqnRichards...:1871-1875): F -= value / FMWH2O.  All loads are issued up front.
-  const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
-  double src_kg = 0.0;
-  {
-    double v0[MAX_SS], v1[MAX_SS];
-#pragma unroll
-    for (int k = 0; k < MAX_SS; ++k) {
-      v0[k] = 0.0; v1[k] = 0.0;
-      if (k < A.nss && A.ss[k].itype == CT_MASS_RATE) {
-        const CondDev &c = A.ss[k];
-        const bool percell = (c.region == REGION_CELLS);
-        const int jown = (c.region == REGION_TOP) ? jtop : jbot;
-        const bool m0 = a.valid && (percell || j0 == jown), m1 = b.valid && (percell || j1 == jown);
-        const double *p = c.value + (percell ? cell0 : (long long)col);
-        if (m0) v0[k] = __ldg(p);
-        if (m1) v1[k] = __ldg(p + (percell ? 1 : 0));
-      }
-    }
-    double sa_ = 0.0, sb_ = 0.0;
-#pragma unroll
-    for (int k = 0; k < MAX_SS; ++k) { sa_ += v0[k] * RFMW; sb_ += v1[k] * RFMW; src_kg += v0[k] + v1[k]; }
-    PA(PI_SRC) = sa_; PB(PI_SRC) = sb_;
   }
 
   // optional down-regulated sink: which of this lane's cells it touches, and where its per-connection data sits
@@ -356,6 +384,11 @@ vsfm_step2_kernel(const VsfmArgs A)
         if (dr_b) { downreg_sink(A.dr_type, A.dr_value[dr_ib], A.dr_pc[dr_ib], A.dr_n[dr_ib], b.X, rate, dj); dia_b += dj; }
       }
 
+      if (EVAL) {
+        if (a.valid) { A.eval_f[cell0] = PA(PI_F); A.eval_ja[cell0] = sub_a; A.eval_jb[cell0] = dia_a; A.eval_jc[cell0] = sup_a; }
+        if (b.valid) { A.eval_f[cell0 + 1] = PB(PI_F); A.eval_ja[cell0 + 1] = sub_b; A.eval_jb[cell0 + 1] = dia_b; A.eval_jc[cell0 + 1] = sup_b; }
+        return;                                       // every column of the warp reaches this point in the same pass
+      }
 #ifdef VSFM2_PROFILE
       const long long pn1 = clock64() + (long long)(1e-300 * (dia_a + dia_b)); pt_nasm += pn1 - pt0;
 #endif
@@ -393,7 +426,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       lambda = nw ? 1.0 : lambda; ls_count = nw ? 0 : ls_count;
       a.W = nw ? a.X - Ya : a.W; b.W = nw ? b.X - Yb : b.W;           // W = X - lambda Y with lambda = 1
       phase = nw ? PH_LS_FULL : phase;
-      if (nw && (yn2 == 0.0 || yn2 > maxstep2 || (nfuncs >= so.max_funcs && so.max_funcs >= 0))) {
+      if (MPP_RARE(nw && (yn2 == 0.0 || yn2 > maxstep2 || (nfuncs >= so.max_funcs && so.max_funcs >= 0)))) {
         if (y2 == 0.0) {
           // zero step: line search "fails"; stol*xnorm > ynorm => SNES_CONVERGED_SNORM_RELATIVE (ls.c)
           last_reason = (stol2 * x2 > y2) ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
@@ -409,7 +442,7 @@ vsfm_step2_kernel(const VsfmArgs A)
     // ================= end-of-SNES bookkeeping (SOEBaseStepDT_SNES :481-536) =================
     if (phase == -1) {
       tot_nf += nfuncs;
-      if (last_reason < 0) {
+      if (MPP_RARE(last_reason < 0)) {
         cuts += 1; dt_iter = 0.5 * dt_iter; dtInv = 1.0 / dt_iter;
         a.X = PA(PI_XPREV); b.X = PB(PI_XPREV);             // VecCopy(soln_prev, soln)
         if (cuts > 20) { converged = 0; phase = PH_DONE; }
@@ -510,7 +543,7 @@ vsfm_step2_kernel(const VsfmArgs A)
     const double ls_rhs = .5 * f2 + lambda * so.ls_alpha * initslope;   // sufficient decrease: <= for the full step, < afterwards
     const bool suff = !g_bad && (is_full ? (.5 * g2 <= ls_rhs) : (.5 * g2 < ls_rhs));
     // (PETSc leaves the cubic loop after max_its fits and keeps the last point)
-    const bool take = is_init || (is_full && suff) || (is_bt && !g_bad && (suff || ls_count >= so.ls_max_its));
+    const bool take = is_init || (EVAL && phase == PH_VEVAL) || (is_full && suff) || (is_bt && !g_bad && (suff || ls_count >= so.ls_max_its));
 
     if (take) {
       // "copy the solution over": X <- W, F <- G; the aux vars of this point feed the next Jacobian / PostSolve
@@ -535,7 +568,11 @@ vsfm_step2_kernel(const VsfmArgs A)
       if (is_init) reason = g_bad ? SNES_DIVERGED_FNORM_NAN : ((g2 < atol2) ? SNES_CONVERGED_FNORM_ABS : 0);
       last_reason = reason ? reason : last_reason;
       phase = reason ? -1 : PH_NEWTON;
-    } else if (is_full) {
+      if (EVAL) {                                     // probe: x_in -> eval_x -> Newton set-up, whatever the norms say
+        if (is_init) { if (a.valid) a.W = A.eval_x[cell0]; if (b.valid) b.W = A.eval_x[cell0 + 1]; phase = PH_VEVAL; }
+        else phase = PH_NEWTON;
+      }
+    } else if (MPP_RARE(is_full)) {
       if (g_bad) {
         if (lambda <= so.ls_minlambda) { last_reason = SNES_DIVERGED_FNORM_NAN; phase = -1; }
         else if (out_of_funcs)         { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
@@ -552,7 +589,7 @@ vsfm_step2_kernel(const VsfmArgs A)
         lambda = (lt <= .1 * lambda) ? .1 * lambda : lt;
         a.W = fma(-lambda, PA(PI_Y), a.X); b.W = fma(-lambda, PB(PI_Y), b.X); phase = PH_LS_QUAD; ls_count = 0;
       }
-    } else if (is_bt) {
+    } else if (MPP_RARE(is_bt)) {
       const int ls_fail = tiny_step ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
       if (g_bad) {
         last_reason = ls_fail; phase = -1;
@@ -593,6 +630,8 @@ vsfm_step2_kernel(const VsfmArgs A)
 #endif
 
   // ---- VSFMSOEPostSolve -> SetDataInSOEAuxVar (GoveqnRichards...:1170-1195) ---------------------------------
+  const bool leader = col_ok && (l == 0);
+  const double m_beg = leader ? A.col_mass[col] : 0.0;        // issued here so that the round trip hides behind the mailbox stores
   double mass = 0.0;
   if (a.valid) {
     A.x_out[cell0] = a.X;
@@ -601,7 +640,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       const double sat = PA(PI_SAT);
       const double m = PA(PI_POR) * den * FMWH2O * sat * PA(PI_VOL);
       A.liq_sat[cell0] = sat; A.pressure[cell0] = a.X; A.mass[cell0] = m;
-      A.smp[cell0] = (a.X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
+      A.smp[cell0] = (a.X - PRESSURE_REF) * rcp(den * FMWH2O * GRAVITY_CONSTANT);
       mass += m;
     }
   }
@@ -612,7 +651,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       const double sat = PB(PI_SAT);
       const double m = PB(PI_POR) * den * FMWH2O * sat * PB(PI_VOL);
       A.liq_sat[cell0 + 1] = sat; A.pressure[cell0 + 1] = b.X; A.mass[cell0 + 1] = m;
-      A.smp[cell0 + 1] = (b.X - PRESSURE_REF) / (den * FMWH2O * GRAVITY_CONSTANT);
+      A.smp[cell0 + 1] = (b.X - PRESSURE_REF) * rcp(den * FMWH2O * GRAVITY_CONSTANT);
       mass += m;
     }
   }
@@ -633,11 +672,9 @@ vsfm_step2_kernel(const VsfmArgs A)
   const double m_end = col_sum<LPC>(mass);
   const double q_col = col_sum<LPC>(src_kg);
   if (HAS_BC) bc_exc = col_sum<LPC>(bc_exc);
-  const bool leader = col_ok && (l == 0);
-  double err = 0.0, m_beg = 0.0;
+  double err = 0.0;
   if (leader) {
     A.stat_its[col] = tot_its; A.stat_reason[col] = last_reason; A.stat_cuts[col] = cuts; A.stat_nf[col] = tot_nf;
-    m_beg = A.col_mass[col];
     if (converged) {
       err = fabs(m_beg - m_end + q_col * A.dt);
       A.col_mass[col] = m_end;
@@ -647,42 +684,34 @@ vsfm_step2_kernel(const VsfmArgs A)
   }
 
   // ---- block partials for the global mass-balance / convergence reductions (deterministic order) ----------
-  // only the column leaders (lanes 0, LPC, 2 LPC, ...) carry values: fold them with log2(32 / LPC) shuffles
-  double v[8];
+  // only the column leaders (lanes 0, LPC, 2 LPC, ...) carry values.  Sums: log2(32 / LPC) shuffle stages in a fixed order.  Maxima and
+  // the worst reason: integer warp reductions (REDUX); the mass error is non-negative, so its IEEE bit pattern orders like an integer.
+  double v[4];
   v[0] = leader ? m_beg : 0.0;                                  // sum mass before
   v[1] = leader ? (converged ? m_end : m_beg) : 0.0;            // sum mass after
   v[2] = leader ? q_col * A.dt : 0.0;                           // sum sources * dt
   v[3] = leader ? bc_exc : 0.0;                                 // sum boundary mass exchanged
-  v[4] = leader ? err : 0.0;                                    // max |mass error|
-  v[5] = leader ? (double)tot_its : 0.0;                        // max Newton its
-  v[6] = leader ? (converged ? 0.0 : 1.0) : 0.0;                // any diverged
-  v[7] = leader ? (double)cuts : 0.0;                           // max dt cuts
-  int worst = leader ? last_reason : 0x7fffffff;
 #pragma unroll
   for (int s = 16; s >= LPC; s >>= 1) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) v[k] += __shfl_xor_sync(FULL, v[k], s);
-#pragma unroll
-    for (int k = 4; k < 8; ++k) v[k] = fmax(v[k], __shfl_xor_sync(FULL, v[k], s));
-    worst = min(worst, __shfl_xor_sync(FULL, worst, s));
   }
-  __shared__ double red[8][VSFM2_THREADS / 32];
-  __shared__ int redw[VSFM2_THREADS / 32];
-  const int warp = threadIdx.x >> 5;
-  if (lane == 0) { for (int k = 0; k < 8; ++k) red[k][warp] = v[k]; redw[warp] = worst; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const int nw = blockDim.x >> 5;
-    double o[8]; int ow = 0x7fffffff;
-    for (int k = 0; k < 8; ++k) o[k] = 0.0;
-    for (int w = 0; w < nw; ++w) {
-      for (int k = 0; k < 4; ++k) o[k] += red[k][w];
-      for (int k = 4; k < 8; ++k) o[k] = fmax(o[k], red[k][w]);
-      ow = min(ow, redw[w]);
-    }
+  const unsigned ehi = leader ? (unsigned)__double2hiint(err) : 0u, elo = leader ? (unsigned)__double2loint(err) : 0u;
+  const unsigned mhi = __reduce_max_sync(FULL, ehi);
+  const unsigned mlo = __reduce_max_sync(FULL, (ehi == mhi) ? elo : 0u);
+  const int mits = __reduce_max_sync(FULL, leader ? tot_its : 0);
+  const int mdiv = __reduce_max_sync(FULL, (leader && !converged) ? 1 : 0);
+  const int mcut = __reduce_max_sync(FULL, leader ? cuts : 0);
+  const int worst = __reduce_min_sync(FULL, leader ? last_reason : 0x7fffffff);
+  static_assert(VSFM2_THREADS == 32, "one warp per block: the block partials are the warp's");
+  if (lane == 0) {
     double *bp = A.block_partials + (size_t)blockIdx.x * 9;
-    for (int k = 0; k < 8; ++k) bp[k] = o[k];
-    bp[8] = (double)ow;
+    bp[0] = v[0]; bp[1] = v[1]; bp[2] = v[2]; bp[3] = v[3];
+    bp[4] = __hiloint2double((int)mhi, (int)mlo);               // max |mass error|
+    bp[5] = (double)mits;                                       // max Newton its
+    bp[6] = (double)mdiv;                                       // any diverged
+    bp[7] = (double)mcut;                                       // max dt cuts
+    bp[8] = (double)worst;
   }
 #undef PA
 #undef PB

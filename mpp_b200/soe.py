@@ -225,6 +225,14 @@ class VSFM(_SoE):
     """sysofeqns_vsfm_type + mpp_vsfm_type for batches of independent soil columns."""
     soe_itype = K.SOE_RE_ODE
 
+    def eval(self, dt, x_prev, x):
+        """Residual and the three Jacobian bands (sub, diagonal, super; N values each) the fused step kernel assembles at x, with the
+        accumulation of the start of the step taken at x_prev (VSFMSOEResidual / VSFMJacobian, SystemOfEquationsVSFMType.F90:94-403)."""
+        x_prev, x = _f64(x_prev), _f64(x)
+        f, ja, jb, jc = (np.zeros(self.ncells) for _ in range(4))
+        check(self.L.mppgpu_eval(self.h, float(dt), _dp(x_prev), _dp(x), _dp(f), _dp(ja), _dp(jb), _dp(jc)))
+        return f, ja, jb, jc
+
     def set_soils(self, watsat, hksat, bsw, sucsat, residual_sat, satfunc_type="van_genuchten", density_type=K.DENSITY_TGDPB01):
         """VSFMMPPSetSoils (MultiPhysicsProbVSFM.F90:211-475); tables are (ncol, nlev)."""
         if satfunc_type not in K.SATFUNC:

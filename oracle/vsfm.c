@@ -297,6 +297,13 @@ int orc_vsfm_set_data(orc_vsfm *p, int auxvar_type, int var_type, int cond_id, c
 int orc_vsfm_get_data(orc_vsfm *p, int auxvar_type, int var_type, int cond_id, double *data, int n)
 {
   int i;
+  if (auxvar_type == 704 /* AUXVAR_CONN_INTERNAL, SystemOfEquationsVSFMType.F90:824 */) {
+    int nconn = p->ncol * (p->nlev > 1 ? p->nlev - 1 : 0);
+    if (var_type != VAR_MASS_FLUX) return 2;
+    if (n > nconn) return 1;
+    for (i = 0; i < n; i++) data[i] = p->internal_flux[i];     /* RichardsODEPressureSetDataInSOEAuxVar :1199-1222 */
+    return 0;
+  }
   if (auxvar_type == AUXVAR_INTERNAL) {
     const double *src = NULL;
     if (n > p->ncells) return 1;

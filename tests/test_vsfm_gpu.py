@@ -153,6 +153,82 @@ def test_inactive_columns_are_left_untouched(mpp):
     assert np.all(P[active == 0] == 0.0)
 
 
+@pytest.mark.parametrize("satfunc,nlev,bc", [("van_genuchten", 15, False), ("smooth_brooks_corey_bz3", 15, False), ("brooks_corey", 24, False),
+                                            ("van_genuchten", 16, True)])
+def test_vsfm_residual_and_jacobian_bands_match_oracle(mpp, oracle, satfunc, nlev, bc):
+    """mppgpu_eval on the VSFM SoE: the residual and the three Jacobian bands the FUSED step kernel assembles (its EVAL instance: same code
+    path as the time step up to the linear solve) at a perturbed state vs the oracle's VSFMSOEResidual / VSFMJacobian restatement
+    (oracle/richards.c, which tests/test_oracle_golden.py checks against finite differences).  A wrong Jacobian that still converges
+    cannot hide here.  With Dirichlet / seepage boundary conditions too (the HAS_BC assembly)."""
+    ncol = 64
+    d = PB.elm_vsfm_inputs(ncol, nlev, satfunc=satfunc)
+
+    def build(cls, **kw):
+        if not bc:
+            return PB.build_elm_vsfm(cls, d, **kw)
+        p = cls(ncol, nlev, **kw)
+        p.set_mesh(K.MESH_ALONG_GRAVITY, d["dz"], d["area"])
+        ids = {"top": p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_TOP_CELLS),
+               "bot": p.add_condition(1, K.COND_BC, K.COND_SEEPAGE_BC, K.SOIL_BOTTOM_CELLS),
+               "et": p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_CELLS)}
+        p.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], satfunc, K.DENSITY_TGDPB01)
+        p.restart(d["press_ic"])
+        return p, ids
+    rng = np.random.default_rng(17)
+    pr = d["press_ic"].reshape(ncol, nlev)
+    P_top = pr[:, 0] + rng.uniform(-2.0e3, 2.0e3, ncol)
+    P_bot = np.where(rng.uniform(size=ncol) < 0.5, K.PRESSURE_REF - 50.0, pr[:, -1] + 3.0e3)      # half of the seepage faces active
+    res = []
+    for cls, kw in ((mpp.VSFM, {}), (oracle.OracleVSFM, {"per_column": True})):
+        p, ids = build(cls, **kw)
+        if bc:
+            p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids["top"], P_top)
+            p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, ids["bot"], P_bot)
+            p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["et"], d["et"])
+            p.pre_step_dt(); p.step_dt(1800.0, 1); p.post_step_dt()
+        else:
+            PB.elm_vsfm_step(p, ids, d, 1800.0, 1)                # loads the conditions
+        xp = d["press_ic"].copy()
+        x = xp + np.random.default_rng(23).uniform(-300.0, 300.0, xp.size)
+        res.append(p.eval(1800.0, xp, x))
+    (f, ja, jb, jc), (fo, jao, jbo, jco) = res
+    fs = np.abs(fo).max()
+    assert np.max(np.abs(f - fo)) < 1e-11 * fs, np.max(np.abs(f - fo)) / fs
+    scale = np.maximum(np.abs(jbo), 1e-300)                       # each band entry against its row's diagonal
+    for a, b, name in ((ja, jao, "sub"), (jb, jbo, "diag"), (jc, jco, "super")):
+        assert np.max(np.abs(a - b) / scale) < 1e-10, (name, np.max(np.abs(a - b) / scale))
+    assert np.abs(jao).max() > 0 and np.abs(jco).max() > 0
+
+
+def test_internal_connection_mass_fluxes_match_oracle(mpp, oracle):
+    """GetDataForCLM(AUXVAR_CONN_INTERNAL, VAR_MASS_FLUX) (SystemOfEquationsVSFMType.F90:824, internal_flux = flux * FMWH2O
+    GoveqnRichards...:1809): ncol * (nlev - 1) fluxes of the committed state, and they close each cell's balance with the storage change."""
+    ncol, nlev = 200, 15
+    d = PB.elm_vsfm_inputs(ncol, nlev, zwt_min=2.0)
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    o, oids = PB.build_elm_vsfm(oracle.OracleVSFM, d, per_column=True, nthreads=8)
+    for step in range(2):
+        conv, reason, out = PB.elm_vsfm_step(p, ids, d, 1800.0, step + 1)
+        convo, reasono, outo = PB.elm_vsfm_step(o, oids, d, 1800.0, step + 1)
+        assert conv and convo
+        m_prev = out["mass"] if step == 0 else m_prev
+        if step == 0:
+            continue
+        q = p.get_data(K.AUXVAR_CONN_INTERNAL, K.VAR_MASS_FLUX, -1, n=ncol * (nlev - 1))
+        qo = o.get_data(K.AUXVAR_CONN_INTERNAL, K.VAR_MASS_FLUX, -1, n=ncol * (nlev - 1))
+        scale = np.abs(qo).max()
+        assert np.max(np.abs(q - qo)) < 1e-9 * scale, np.max(np.abs(q - qo)) / scale
+        # cell balance.  RichardsFlux is negative for flow from the up cell to the dn cell, and the residual takes ff(up) -= flux,
+        # ff(dn) += flux (GoveqnRichards...:1805-1806): (m_new - m_old) / dt = +flux of the connection below - flux of the one above + sources
+        Q = q.reshape(ncol, nlev - 1)
+        net = np.zeros((ncol, nlev)); net[:, :-1] += Q; net[:, 1:] -= Q
+        src = d["et"].reshape(ncol, nlev).copy(); src[:, 0] += d["infil"]
+        dm = (out["mass"] - m_prev).reshape(ncol, nlev) / 1800.0
+        assert np.max(np.abs(dm - net - src)) < 1e-8 * max(np.abs(src).max(), np.abs(Q).max())
+    with pytest.raises(mpp.MPPError):
+        p.get_data(K.AUXVAR_CONN_INTERNAL, K.VAR_PRESSURE, -1, n=10)
+
+
 def test_dt_cut_path_matches_oracle(mpp, oracle):
     """Force SNES failures (max_it = 2) so the dt-halving branch of SOEBaseStepDT_SNES (:500-507) runs."""
     d = PB.elm_vsfm_inputs(200, 15)
