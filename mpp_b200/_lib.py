@@ -58,6 +58,7 @@ _SIGS = {
     "mppgpu_th_set_soils": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, C.c_int, C.c_int, C.c_int]),
     "mppgpu_th_set_energy_permeability": (C.c_int, [C.c_void_p, c_dp, C.c_int]),
     "mppgpu_set_tolerances": (C.c_int, [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int]),
+    "mppgpu_thermal_set_bulk_copy": (C.c_int, [C.c_void_p, C.c_int]),
     "mppgpu_set_step_budget": (C.c_int, [C.c_void_p, C.c_int]),
     "mppgpu_set_column_ordering": (C.c_int, [C.c_void_p, C.c_int]),
     "mppgpu_restart": (C.c_int, [C.c_void_p, c_dp, C.c_int]),

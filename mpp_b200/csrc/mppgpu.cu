@@ -51,9 +51,16 @@ static int fail(const char *fmt, ...)
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
 #define CHECK_H(h) do { if (!(h)) return fail("null handle"); CK(cudaSetDevice((h)->device)); } while (0)
 
+// every device buffer carries MPP_ALLOC_SLACK bytes of slack: the tile kernels (thermal_step2_tma_kernel) copy whole tiles and may
+// read up to one tile past the end of the batch
+#ifndef MPP_ALLOC_SLACK
+#define MPP_ALLOC_SLACK 4096
+#endif
+static inline cudaError_t mpp_dmalloc(void **p, size_t bytes) { return cudaMalloc(p, bytes + MPP_ALLOC_SLACK); }
+
 template <class T> struct DevBuf {
   T *p = nullptr; size_t n = 0;
-  cudaError_t alloc(size_t count) { release(); n = count; if (!count) return cudaSuccess; return cudaMalloc((void **)&p, count * sizeof(T)); }
+  cudaError_t alloc(size_t count) { release(); n = count; if (!count) return cudaSuccess; return mpp_dmalloc((void **)&p, count * sizeof(T)); }
   void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
   ~DevBuf() { release(); }
 };
@@ -89,6 +96,7 @@ struct mppgpu_soe {
   DevBuf<double> col_mass, col_err, col_src, block_partials, red_out, red_scratch; DevBuf<unsigned int> red_counter;
   double *h_red = nullptr;     // pinned mirror of red_out (9 doubles)
   // launch order of the step kernel (vsfm_kernels.cuh "launch order"): built after every StepDT from its per-column cost
+  int sm_count = 148;
   DevBuf<double> conn_flux;          // internal-connection mass fluxes, filled on demand (vsfm_conn_flux_kernel)
   DevBuf<int> order, order_counts; bool order_valid = false; int order_chunks = 0; long long order_per = 0; int ordering = 1;
   int nblocks_last = 0;
@@ -219,6 +227,7 @@ static int upload_table(mppgpu_soe *h, const double *host, DevBuf<double> &tmp)
 }
 
 // ---- life cycle ---------------------------------------------------------------------------------------------
+extern "C" int mppgpu_destroy(mppgpu_handle h);
 extern "C" int mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppgpu_handle *out)
 {
   if (!out) return fail("mppgpu_create: out is null");
@@ -232,6 +241,8 @@ extern "C" int mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppg
   if (device < 0 || device >= ndev) return fail("mppgpu_create: device %d out of range (0..%d)", device, ndev - 1);
   CK(cudaSetDevice(device));
   mppgpu_soe *h = new mppgpu_soe();
+  struct Guard { mppgpu_soe *h; ~Guard() { if (h) mppgpu_destroy(h); } } guard{h};     // any failure below releases what was created so far
+  CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
   h->soe_itype = soe_itype; h->ncol = ncol; h->nlev = nlev; h->device = device;
   h->ncells = (size_t)ncol * (size_t)nlev;
   default_snes(h->so);
@@ -266,6 +277,7 @@ extern "C" int mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppg
     if (th_create(h->th, ncol, nlev, h->stream)) return fail("th_create failed: %s", cudaGetErrorString(cudaGetLastError()));
   }
   CK(cudaStreamSynchronize(h->stream));
+  guard.h = nullptr;
   *out = h;
   return 0;
 }
@@ -274,7 +286,7 @@ extern "C" int mppgpu_destroy(mppgpu_handle h)
 {
   if (!h) return 0;
   cudaSetDevice(h->device);
-  cudaStreamSynchronize(h->stream);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto *c : h->bcs) delete c;
   for (auto *c : h->sss) delete c;
   if (h->thermal) { thermal_destroy(h->thermal); delete h->thermal; }
@@ -361,7 +373,7 @@ extern "C" int mppgpu_set_connection_distances(mppgpu_handle h, const double *di
   for (int i = 0; i < 2; ++i) {
     DevBuf<double> tmp; CK(tmp.alloc(nconn));
     CK(cudaMemcpyAsync(tmp.p, src[i], nconn * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    if (!*dst[i]) CK(cudaMalloc((void **)dst[i], h->ncells * sizeof(double)));
+    if (!*dst[i]) CK(mpp_dmalloc((void **)dst[i], h->ncells * sizeof(double)));
     conn_table_to_cells_kernel<<<nblk(h->ncells, 256), 256, 0, h->stream>>>(tmp.p, *dst[i], h->ncol, h->nlev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
@@ -414,12 +426,14 @@ extern "C" int mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int
     if (ieqn != 1) return fail("mppgpu_add_condition: the soil thermal SoE has one governing equation here (ieqn = 1)");
     if (ss_or_bc == COND_BC && cond_type != COND_HEAT_FLUX && cond_type != COND_DIRICHLET)
       return fail("mppgpu_add_condition: thermal boundary condition type %d unsupported (COND_HEAT_FLUX 507, COND_DIRICHLET 505)", cond_type);
+    if (ss_or_bc == COND_BC && region == REGION_CELLS) return fail("mppgpu_add_condition: boundary conditions live on SOIL_TOP_CELLS / SOIL_BOTTOM_CELLS");
     if (ss_or_bc == COND_SS && cond_type != COND_HEAT_RATE)
       return fail("mppgpu_add_condition: thermal source type %d unsupported (COND_HEAT_RATE 511)", cond_type);
   } else {
     if (ieqn != 1 && ieqn != 2) return fail("mppgpu_add_condition: TH has ieqn 1 (mass) and 2 (energy)");
   }
   HostCond *c = new HostCond();
+  struct CondGuard { HostCond *c; ~CondGuard() { delete c; } } cguard{c};       // released below once the handle owns the condition
   c->ieqn = ieqn; c->ss_or_bc = ss_or_bc; c->itype = cond_type; c->region = region;
   c->n = (region == REGION_CELLS) ? h->ncells : (size_t)h->ncol;
   CK(c->value.alloc(c->n)); CK(cudaMemsetAsync(c->value.p, 0, c->n * 8, h->stream));
@@ -435,10 +449,10 @@ extern "C" int mppgpu_add_condition(mppgpu_handle h, int ieqn, int ss_or_bc, int
       CK(c->dhsdT.alloc(c->n)); CK(cudaMemsetAsync(c->dhsdT.p, 0, c->n * 8, h->stream));
       CK(c->frac.alloc(c->n));  CK(cudaMemsetAsync(c->frac.p, 0, c->n * 8, h->stream));     // ThermalKSPTemperatureBaseAuxType.F90:60
     }
-    h->bcs.push_back(c);
+    h->bcs.push_back(c); cguard.c = nullptr;
     if (cond_id) *cond_id = (int)h->bcs.size();
   } else {
-    h->sss.push_back(c);
+    h->sss.push_back(c); cguard.c = nullptr;
     if (cond_id) *cond_id = (int)h->sss.size();
   }
   return 0;
@@ -485,6 +499,15 @@ extern "C" int mppgpu_set_step_budget(mppgpu_handle h, int max_residual_evaluati
   if (max_residual_evaluations < 0) return fail("mppgpu_set_step_budget: the budget must be >= 0 (0 = unlimited, the reference's behaviour)");
   h->so.step_budget = max_residual_evaluations;
   if (h->th) h->th->so = h->so;
+  return 0;
+}
+
+extern "C" int mppgpu_thermal_set_bulk_copy(mppgpu_handle h, int mode)
+{
+  CHECK_H(h);
+  if (!h->thermal) return fail("mppgpu_thermal_set_bulk_copy: handle is not a thermal SoE");
+  if (mode != 0 && mode != 1) return fail("mppgpu_thermal_set_bulk_copy: mode must be 0 (register loads) or 1 (bulk-async copies where the shape fits)");
+  h->thermal->bulk_copy = (mode != 0);
   return 0;
 }
 
@@ -734,7 +757,7 @@ static int vsfm_launch_range(mppgpu_soe *h, const VsfmArgs &A0, long long col0, 
   VsfmArgs A = A0;
   vsfm_offset_args(A, h->nlev, col0, n, block0);
 #ifdef VSFM2_PROFILE
-  if (!g_prof) { cudaMalloc((void **)&g_prof, 12 * sizeof(long long)); cudaMemset(g_prof, 0, 12 * sizeof(long long)); }
+  if (!g_prof) { mpp_dmalloc((void **)&g_prof, 12 * sizeof(long long)); cudaMemset(g_prof, 0, 12 * sizeof(long long)); }
   A.prof = g_prof;
 #endif
   const int nlev = h->nlev, nblocks = vsfm_blocks_for(h, n);
@@ -824,11 +847,20 @@ extern "C" int mppgpu_step_dt_async(mppgpu_handle h, double dt, int nstep)
   return th_step(h, h->th, dt);
 }
 
+// device time between the events around the last StepDT; events that were never recorded (no step yet, or a step that bailed out early)
+// make cudaEventElapsedTime fail, and a failure must not linger as the thread's "last error" for the next launch check
+static void step_elapsed(mppgpu_soe *h)
+{
+  float ms = 0.0f;
+  if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms;
+  else (void)cudaGetLastError();
+}
+
 extern "C" int mppgpu_step_result(mppgpu_handle h, int *converged, int *converged_reason)
 {
   CHECK_H(h);
   CK(cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  step_elapsed(h);
   h->result_pending = false;
   if (h->thermal) { if (converged) *converged = 1; if (converged_reason) *converged_reason = 0; return 0; }   // KSP path: tridiagonal solve cannot diverge
   const double *r = h->h_red;
@@ -959,7 +991,7 @@ extern "C" int mppgpu_last_step_ms(mppgpu_handle h, float *ms)
 {
   CHECK_H(h);
   CK(cudaStreamSynchronize(h->stream));
-  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  step_elapsed(h);
   if (ms) *ms = h->last_ms;
   return 0;
 }

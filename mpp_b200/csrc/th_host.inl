@@ -42,7 +42,7 @@ static int th_restart(THState *t, const double *x)
 {
   const size_t N = (size_t)t->ncol * t->nlev;
   double *tmp = nullptr;
-  if (cudaMalloc((void **)&tmp, 2 * N * sizeof(double)) != cudaSuccess) return 1;
+  if (mpp_dmalloc((void **)&tmp, 2 * N * sizeof(double)) != cudaSuccess) return 1;
   int rc = 0;
   if (cudaMemcpyAsync(tmp, x, 2 * N * sizeof(double), cudaMemcpyHostToDevice, t->stream) != cudaSuccess) rc = 1;
   if (!rc) {
@@ -67,7 +67,7 @@ static int th_set_soils(mppgpu_soe *h, THState *t, const double *watsat, const d
   DevBuf<double> tb[7]; const double *src[7] = {watsat, hksat, bsw, sucsat, residual_sat, csol, tkdry};
   for (int i = 0; i < 7; ++i) if (upload_table(h, src[i], tb[i])) return 1;
   double **need[] = {&t->por, &t->perm, &t->sat_res, &t->alpha, &t->lam, &t->vgn, &t->pu, &t->ps, &t->b2, &t->b3, &t->tkdry, &t->csol};
-  for (double **p : need) if (!*p) CK(cudaMalloc((void **)p, N * sizeof(double)));
+  for (double **p : need) if (!*p) CK(mpp_dmalloc((void **)p, N * sizeof(double)));
   DevBuf<int> bad; CK(bad.alloc(1)); CK(cudaMemsetAsync(bad.p, 0, sizeof(int), h->stream));
   convert_soils_kernel<<<nblk(N, 128), 128, 0, h->stream>>>(satfunc_type, tb[0].p, tb[1].p, tb[2].p, tb[3].p, tb[4].p, h->ncol, h->nlev,
       t->por, t->perm, t->sat_res, t->alpha, t->lam, t->vgn, t->pu, t->ps, t->b2, t->b3, bad.p);
@@ -88,7 +88,7 @@ static int th_set_soils(mppgpu_soe *h, THState *t, const double *watsat, const d
 static int th_set_energy_permeability(mppgpu_soe *h, THState *t, const double *perm)
 {
   const size_t N = (size_t)h->ncells;
-  if (!t->perm_e && cudaMalloc((void **)&t->perm_e, N * sizeof(double)) != cudaSuccess) return fail("cudaMalloc failed (energy permeability)");
+  if (!t->perm_e && mpp_dmalloc((void **)&t->perm_e, N * sizeof(double)) != cudaSuccess) return fail("cudaMalloc failed (energy permeability)");
   CK(cudaMemcpyAsync(t->perm_e, perm, N * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CK(cudaStreamSynchronize(h->stream));
   return 0;

@@ -3,7 +3,7 @@
 
 static int th_alloc_d(double **p, size_t n, double fill, cudaStream_t s)
 {
-  if (cudaMalloc((void **)p, n * sizeof(double)) != cudaSuccess) return 1;
+  if (mpp_dmalloc((void **)p, n * sizeof(double)) != cudaSuccess) return 1;
   if (fill == 0.0) cudaMemsetAsync(*p, 0, n * sizeof(double), s);
   else fill_kernel<<<nblk(n, 256), 256, 0, s>>>(*p, fill, (long long)n);
   return 0;
@@ -22,8 +22,8 @@ static int thermal_create(ThermalState *t, int ncol, int nlev, cudaStream_t s)
   rc |= th_alloc_d(&t->T_clm, N, 273.15, s); rc |= th_alloc_d(&t->T_work, N, 273.15, s);
   rc |= th_alloc_d(&t->liq, N, 0.0, s); rc |= th_alloc_d(&t->ice, N, 0.0, s); rc |= th_alloc_d(&t->snow_water, N, 0.0, s);
   rc |= th_alloc_d(&t->tuning, N, 1.0, s);                      // ThermalKSPTemperatureSoilAuxType.F90:56
-  if (cudaMalloc((void **)&t->nsnow, N * sizeof(int)) != cudaSuccess) rc = 1;
-  if (cudaMalloc((void **)&t->active, N * sizeof(int)) != cudaSuccess) rc = 1;
+  if (mpp_dmalloc((void **)&t->nsnow, N * sizeof(int)) != cudaSuccess) rc = 1;
+  if (mpp_dmalloc((void **)&t->active, N * sizeof(int)) != cudaSuccess) rc = 1;
   if (!rc) { cudaMemsetAsync(t->nsnow, 0, N * sizeof(int), s); cudaMemsetAsync(t->active, 0, N * sizeof(int), s); }
   t->T_cur = t->T_clm;
   return rc;
@@ -64,14 +64,14 @@ static int thermal_add_snow_ssw(mppgpu_soe *h, ThermalState *t, int nlevsno, con
   const double fillv[] = {273.15, 273.15, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0};
   for (int i = 0; i < 10; ++i) { if (*grow[i]) cudaFree(*grow[i]); *grow[i] = nullptr; if (th_alloc_d(grow[i], NA, fillv[i], s)) return fail("out of device memory"); }
   cudaFree(t->nsnow); cudaFree(t->active); t->nsnow = t->active = nullptr;
-  CK(cudaMalloc((void **)&t->nsnow, NA * sizeof(int))); CK(cudaMalloc((void **)&t->active, NA * sizeof(int)));
+  CK(mpp_dmalloc((void **)&t->nsnow, NA * sizeof(int))); CK(mpp_dmalloc((void **)&t->active, NA * sizeof(int)));
   CK(cudaMemsetAsync(t->nsnow, 0, NA * sizeof(int), s)); CK(cudaMemsetAsync(t->active, 0, NA * sizeof(int), s));
   // soil cells of active columns start active (MPPThermalSetSoils); snow / ssw cells wait for VAR_ACTIVE from the host model
   if (t->soils_set) fill_int_kernel<<<nblk(NG, 256), 256, 0, s>>>(t->active + (NA - NG), 1, (long long)NG);
   for (int k = 0; k < 3; ++k) { if (th_alloc_d(&t->hs[k], ncol, 0.0, s) || th_alloc_d(&t->dhs[k], ncol, 0.0, s)) return fail("out of device memory"); }
   if (th_alloc_d(&t->frac_soil, ncol, 0.0, s) || th_alloc_d(&t->sabg_snow, NS ? NS : 1, 0.0, s) || th_alloc_d(&t->sabg_soil, NG, 0.0, s) ||
       th_alloc_d(&t->soil_top_dist_dn, ncol, 0.0, s)) return fail("out of device memory");
-  CK(cudaMalloc((void **)&t->snow_top_id, ncol * sizeof(int))); CK(cudaMemsetAsync(t->snow_top_id, 0, ncol * sizeof(int), s));
+  CK(mpp_dmalloc((void **)&t->snow_top_id, ncol * sizeof(int))); CK(cudaMemsetAsync(t->snow_top_id, 0, ncol * sizeof(int), s));
   CK(cudaMemcpyAsync(t->soil_top_dist_dn, soil_top_dist_dn, ncol * 8, cudaMemcpyHostToDevice, s));
   CK(cudaStreamSynchronize(s));
   t->T_cur = t->T_clm; t->snow_mode = true; t->nsno = nlevsno; t->nall = NA;
@@ -106,12 +106,12 @@ static int thermal_set_soils(mppgpu_soe *h, ThermalState *t, const double *watsa
   for (int i = 0; i < 4; ++i) {
     DevBuf<double> tmp;
     if (upload_table(h, src[i], tmp)) return 1;
-    if (!*dst[i]) CK(cudaMalloc((void **)dst[i], N * sizeof(double)));
+    if (!*dst[i]) CK(mpp_dmalloc((void **)dst[i], N * sizeof(double)));
     transpose_to_cells_kernel<<<nblk(N, 256), 256, 0, h->stream>>>(tmp.p, *dst[i], h->ncol, h->nlev);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
   }
-  if (!t->lun_type) CK(cudaMalloc((void **)&t->lun_type, h->ncol * sizeof(int)));
+  if (!t->lun_type) CK(mpp_dmalloc((void **)&t->lun_type, h->ncol * sizeof(int)));
   CK(cudaMemcpyAsync(t->lun_type, lun_type, h->ncol * sizeof(int), cudaMemcpyHostToDevice, h->stream));
   // every column active (filter_thermal = 1): aux_vars_in%is_active = .true. (MultiPhysicsProbThermal.F90:165-170)
   fill_int_kernel<<<nblk(N, 256), 256, 0, h->stream>>>(t->active + (t->snow_mode ? t->nall - N : 0), 1, (long long)N);
@@ -233,6 +233,35 @@ static int thermal_snow_step(mppgpu_soe *h, ThermalState *t, double dt)
   return 0;
 }
 
+// which arrays a tile of the bulk-async kernel carries, in the order the kernel lays out its stage; false: shape not covered
+static bool thermal_tma_plan(const ThermalArgs &A, ThermalTmaPlan &P)
+{
+  memset(&P, 0, sizeof(P));
+  if (A.dist_up && !A.dist_uniform) return false;
+  for (int k = 0; k < 2; ++k) if (A.bc_type[k] != 0 && A.bc_type[k] != 507) return false;
+  int ncell_ss = 0, ncol_ss = 0;
+  for (int k = 0; k < A.nss; ++k) { if (A.ss_region[k] == 403) ncell_ss++; else ncol_ss++; }
+  if (ncell_ss > TMA_MAX_SS_CELL || ncol_ss > TMA_MAX_SS_COL) return false;
+  const void *cd[] = {A.T_in, A.dz, A.tuning, A.liq, A.ice, A.snow_water, A.por, A.tkmg, A.tkdry, A.csol};
+  for (const void *q : cd) P.cell_d[P.n_cell_d++] = q;
+  for (int k = 0; k < A.nss; ++k) if (A.ss_region[k] == 403) P.cell_d[P.n_cell_d++] = A.ss_value[k];
+  P.cell_i[P.n_cell_i++] = A.active; P.cell_i[P.n_cell_i++] = A.nsnow;
+  P.col_d[P.n_col_d++] = A.area;
+  for (int k = 0; k < 2; ++k) if (A.bc_type[k] == 507) { P.col_d[P.n_col_d++] = A.bc_value[k]; P.col_d[P.n_col_d++] = A.bc_dhsdT[k]; P.col_d[P.n_col_d++] = A.bc_frac[k]; }
+  for (int k = 0; k < A.nss; ++k) if (A.ss_region[k] != 403) P.col_d[P.n_col_d++] = A.ss_value[k];
+  P.col_i[P.n_col_i++] = A.lun_type;
+  for (int i = 0; i < P.n_cell_d; ++i) if (!P.cell_d[i] || ((uintptr_t)P.cell_d[i] & 15)) return false;
+  for (int i = 0; i < P.n_col_d; ++i) if (!P.col_d[i] || ((uintptr_t)P.col_d[i] & 15)) return false;
+  if (!A.active || !A.nsnow || !A.lun_type || ((uintptr_t)A.active & 15) || ((uintptr_t)A.nsnow & 15) || ((uintptr_t)A.lun_type & 15)) return false;
+  const int cells = TMA_TILE_COLS * A.nlev;
+  P.stage_bytes = P.n_cell_d * cells * 8 + P.n_cell_i * cells * 4 + P.n_col_d * TMA_TILE_COLS * 8 + P.n_col_i * TMA_TILE_COLS * 4;
+  P.ntiles = (A.ncol + TMA_TILE_COLS - 1) / TMA_TILE_COLS;
+  if ((size_t)TMA_WARPS * P.stage_bytes > 44 * 1024) return false;
+  // the last tile may hang over the end of the batch by up to TMA_TILE_COLS - 1 columns: covered by the allocation slack
+  if ((size_t)(TMA_TILE_COLS - 1) * A.nlev * 8 > MPP_ALLOC_SLACK) return false;
+  return true;
+}
+
 static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
 {
   if (!h->mesh_set || !t->soils_set) return fail("mppgpu_step_dt: mesh and soils must be set first");
@@ -266,11 +295,19 @@ static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
   if (t->therm_cond && t->heat_cap) { A.therm_cond = t->therm_cond; A.heat_cap = t->heat_cap; t->diagnostics = true; }
   CK(cudaEventRecord(h->ev0, h->stream));
   const int nlev = h->nlev;
-  if (nlev <= 32) {
+  // bulk-async (1-D TMA) persistent variant for the shapes it covers and batches that fill the machine (thermal_kernels.cuh)
+  ThermalTmaPlan P;
+  const bool tma = t->bulk_copy && nlev <= 16 && thermal_tma_plan(A, P) && P.ntiles >= 2 * TMA_WARPS * TMA_BLOCKS_PER_SM * h->sm_count;
+  if (tma) {
+    const size_t smem = (size_t)TMA_WARPS * P.stage_bytes;
+    if (!t->tma_attr_set) { CK(cudaFuncSetAttribute(thermal_step2_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 44 * 1024)); t->tma_attr_set = true; }
+    const int grid = std::min((P.ntiles + TMA_WARPS - 1) / TMA_WARPS, h->sm_count * TMA_BLOCKS_PER_SM);
+    thermal_step2_tma_kernel<8><<<grid, TH_TILE, smem, h->stream>>>(A, P);
+  } else if (nlev <= 32) {
     if (nlev <= 16) thermal_step2_kernel<8><<<nblk((long long)h->ncol * 8, TH_TILE), TH_TILE, 0, h->stream>>>(A);
     else            thermal_step_kernel<32><<<nblk((long long)h->ncol * 32, TH_TILE), TH_TILE, 0, h->stream>>>(A);
   } else {
-    if (!t->work) CK(cudaMalloc((void **)&t->work, 4 * h->ncells * sizeof(double)));
+    if (!t->work) CK(mpp_dmalloc((void **)&t->work, 4 * h->ncells * sizeof(double)));
     thermal_step_generic_kernel<<<nblk(h->ncol, 64), 64, 0, h->stream>>>(A, t->work);
   }
   CK(cudaGetLastError());
@@ -295,7 +332,7 @@ static int thermal_elm_solve(mppgpu_soe *h, ThermalState *t, double dtime, const
   cudaStream_t s = h->stream;
   // staging layout: z, dz, t, liq, ice (ncol*nl each) | zi (ncol*(nl+1)) | sabg (ncol*(nsno+1)) | 9 per-column arrays | tvector (ncol*nrow)
   const size_t total = 5 * ncol * nl + ncol * (nl + 1) + ncol * (nsno + 1) + 9 * ncol + ncol * nrow;
-  if (!t->elm_stage) { CK(cudaMalloc((void **)&t->elm_stage, total * 8)); CK(cudaMalloc((void **)&t->elm_snl, ncol * sizeof(int))); }
+  if (!t->elm_stage) { CK(mpp_dmalloc((void **)&t->elm_stage, total * 8)); CK(mpp_dmalloc((void **)&t->elm_snl, ncol * sizeof(int))); }
   double *p = t->elm_stage;
   auto up = [&](const double *src, size_t cnt) -> double * {
     double *dst = p; p += cnt;

@@ -221,7 +221,7 @@ extern "C" int mppgpu_vsfm_elm_solve(mppgpu_handle h, double dtime, int nstep, m
   CK(cudaMemcpyAsync(status.data(), e->status.p, ncol * sizeof(int), cudaMemcpyDeviceToHost, s));
 #undef DOWN
   CK(cudaStreamSynchronize(s));
-  cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1);
+  { float ms_ = 0.0f; if (cudaEventElapsedTime(&ms_, h->ev0, h->ev1) == cudaSuccess) h->last_ms = ms_; else (void)cudaGetLastError(); }
   int nf = 0;
   for (size_t c = 0; c < ncol; ++c) {
     if (!status[c]) nf++;

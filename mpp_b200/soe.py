@@ -335,6 +335,10 @@ class Thermal(_SoE):
 
     MPPThermalSetSoils = set_soils
 
+    def set_bulk_copy(self, mode):
+        """1 (default): the persistent bulk-async (1-D TMA) kernel where its shape fits; 0: register loads.  Results are bit-identical."""
+        check(self.L.mppgpu_thermal_set_bulk_copy(self.h, int(mode)))
+
     def set_cnfac(self, cnfac):
         check(self.L.mppgpu_thermal_set_cnfac(self.h, float(cnfac)))
 

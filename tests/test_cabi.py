@@ -74,3 +74,30 @@ def test_plain_c_program_steps_four_columns(tmp_path):
     r = subprocess.run([_build_c_smoke(tmp_path), "run"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.strip().endswith("ok")
+
+
+def test_fortran_binding_covers_every_entry_point_and_is_current():
+    """include/mppgpu_binding.F90 is generated from the C prototypes (tools/gen_fortran_binding.py): one bind(C) interface per entry point
+    of include/mppgpu.h with as many dummy arguments as the C function has parameters, the three structs as bind(C) derived types with
+    the header's member order, and the committed file is what the generator writes today."""
+    import importlib.util
+    import re
+    spec = importlib.util.spec_from_file_location("gen_fortran_binding", os.path.join(ROOT, "tools", "gen_fortran_binding.py"))
+    g = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(g)
+    src, names = g.generate()
+    assert open(os.path.join(ROOT, "include", "mppgpu_binding.F90")).read() == src, "run python tools/gen_fortran_binding.py"
+    assert set(names) == set(declared_symbols())
+    hdr = open(os.path.join(ROOT, "include", "mppgpu.h")).read()
+    for ret, name, args in g.prototypes(hdr):
+        nargs = 0 if args in ("", "void") else len(args.split(","))
+        m = re.search(r"function %s\(([^)]*)\)\s*(?:&\s*)?bind\(C" % name, src.replace("&\n          ", ""))
+        assert m, name
+        dummies = [a for a in m.group(1).replace("&", "").split(",") if a.strip()]
+        assert len(dummies) == nargs, (name, dummies, nargs)
+    from mpp_b200 import _lib
+    for sname, cls in (("mppgpu_xfer", _lib.Xfer), ("mppgpu_elm_columns", _lib.ElmColumns), ("mppgpu_elm_thermal_columns", _lib.ElmThermalColumns)):
+        fields = dict(g.structs(hdr))[sname]
+        assert [f[0] for f in fields] == [f[0] for f in cls._fields_], sname          # header order == ctypes mirror == Fortran type
+        block = src[src.index("type, bind(C), public :: %s" % sname):src.index("end type %s" % sname)]
+        assert [ln.split("::")[1].strip() for ln in block.splitlines()[1:] if "::" in ln] == [f[0] for f in fields]

@@ -46,6 +46,11 @@ def to_float(s):
 def main():
     rep, title = sys.argv[1], sys.argv[2]
     alg_bytes = float(sys.argv[3]) if len(sys.argv) > 3 else None
+    # optional: --json "<kernel key of bench.py>" <units (columns) per launch>: record the measured DRAM bytes per unit and the fp64 pipe
+    # share of this capture in profiles/roofline_measured.json, which bench.py reads (nothing is typed into bench.py)
+    jkey = junits = None
+    if "--json" in sys.argv:
+        i = sys.argv.index("--json"); jkey, junits = sys.argv[i + 1], float(sys.argv[i + 2])
     raw = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "raw", "--csv"]))))
     hdr, units, rows = raw[0], raw[1], raw[2:]
     print("# %s\n" % title)
@@ -75,6 +80,16 @@ def main():
                 print("| algorithmic bytes per launch (DESIGN.md) | %.4g GB (traffic / algorithmic = %.2f) |" % (alg_bytes / 1e9, traffic / alg_bytes))
                 if peaks.get("hbm_gbs"):
                     print("| algorithmic GB/s under ncu / measured HBM peak %.0f GB/s | %.0f GB/s = %.3f |" % (peaks["hbm_gbs"], alg_bytes / t / 1e9, alg_bytes / t / 1e9 / peaks["hbm_gbs"]))
+            if jkey:
+                jp = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "roofline_measured.json")
+                try:
+                    facts = json.load(open(jp))
+                except Exception:
+                    facts = {}
+                fp64 = to_float(g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active") or "")
+                facts[jkey] = {"dram_bytes_per_unit": traffic / junits, "fp64_pipe_frac": (fp64 / 100.0) if fp64 is not None else None,
+                               "kernel_ms_under_ncu": t * 1e3, "units_per_launch": junits, "source": "profiles/" + os.path.basename(rep).replace(".ncu-rep", ".md")}
+                json.dump(facts, open(jp, "w"), indent=1, sort_keys=True)
         print()
     src = list(csv.reader(io.StringIO(ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"]))))
     cur, h = None, None

@@ -95,13 +95,16 @@ elif mode == "snow":
           "alg GB/s (2356 B/col) %.0f" % (2356 * ncol / (m * 1e-3) / 1e9))
 else:
     d = PB.elm_thermal_inputs(ncol, 15)
-    p, ids = PB.build_elm_thermal(mpp_b200.Thermal, d)
-    T = d["T0"]
-    conv, T = PB.elm_thermal_step(p, ids, d, T, 1800.0, 1)
-    ms = []
-    for s in range(10):
-        p.step_dt(1800.0, s + 2)           # device-resident chain: soln -> soln_prev
-        ms.append(p.last_step_ms())
-    m = float(np.mean(ms[3:]))
-    print("thermal ncol", ncol, "ms/step", ["%.3f" % x for x in ms], "col-steps/s %.3e" % (ncol / (m * 1e-3)),
-          "alg GB/s (1224 B/col) %.0f" % (1224 * ncol / (m * 1e-3) / 1e9))
+    for mode in (0, 1):
+        p, ids = PB.build_elm_thermal(mpp_b200.Thermal, d)
+        p.set_bulk_copy(mode)
+        T = d["T0"]
+        conv, T = PB.elm_thermal_step(p, ids, d, T, 1800.0, 1)
+        ms = []
+        for s in range(12):
+            p.step_dt(1800.0, s + 2)           # device-resident chain: soln -> soln_prev
+            ms.append(p.last_step_ms())
+        m = float(np.mean(ms[3:]))
+        print("thermal ncol", ncol, "bulk_copy", mode, "ms/step", ["%.3f" % x for x in ms], "col-steps/s %.3e" % (ncol / (m * 1e-3)),
+              "alg GB/s (1224 B/col) %.0f" % (1224 * ncol / (m * 1e-3) / 1e9), flush=True)
+        p.close()
