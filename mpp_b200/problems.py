@@ -78,6 +78,46 @@ def run_wt_dynamics(p, top, bot, nstep=24, dt=3600.0):
 
 
 # ---------------------------------------------------------------------------------------------------
+# Srivastava & Yeh (1991) layered-soil infiltration -- src/driver/standalone/vsfm/vsfm_sy1991_problem.F90
+#   2 m column, 200 cells, bottom-up mesh, low-permeability lower half under a ten times more permeable upper half, constant recharge at
+#   the top (mass-rate source), constant head at the bottom (Dirichlet): the transient between the steady states of two recharge rates.
+#   `ic`: the driver's initial-pressure table of the chosen problem (200 values; tests/golden/sy1991_ic.json).  No regression baseline exists.
+# ---------------------------------------------------------------------------------------------------
+def build_sy1991(cls, ic, nz=200, **kw):
+    ic = np.asarray(ic, dtype=np.float64)
+    assert ic.size == nz
+    p = cls(1, nz, **kw)
+    p.set_mesh(K.MESH_AGAINST_GRAVITY, np.full((1, nz), 2.0 / nz), np.array([1.0]))        # MeshCreate, z_column = 2 m (:293-294)
+    top = p.add_condition(1, K.COND_SS, K.COND_MASS_RATE, K.SOIL_TOP_CELLS)                  # 'Constant flux condition at top' (:348-350)
+    bot = p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS)               # 'Constant head condition at bottom' (:352-354)
+    porosity, lam, alpha, perm_high, perm_low = 0.4, 0.5455, 4.0e-4, 2.5281e-12, 2.5281e-13  # :388-392
+    vish2o, denh2o, grav = 0.001002, 1000.0, K.GRAV
+    hksat = np.empty((1, nz))
+    hksat[:, :nz // 2] = perm_low / vish2o * (denh2o * grav) / 0.001                          # :422-423
+    hksat[:, nz // 2:] = perm_high / vish2o * (denh2o * grav) / 0.001
+    full = lambda v: np.full((1, nz), v)
+    p.set_soils(full(porosity), hksat, full(1.0 / lam), full(1.0 / (alpha * K.GRAVITY_CONSTANT)), full(0.15),
+                "van_genuchten", K.DENSITY_TGDPB01)                                          # :424-433
+    p.restart(ic)                                                                            # :446-463
+    return p, top, bot
+
+
+def run_sy1991(p, top, bot, ic, problem="drying", nstep=24, dt=3600.0, first_step=1):
+    recharge = {"wetting": 2.5e-6, "drying": 2.7778e-7}[problem] * 997.16                    # :476-492
+    its = []
+    for step in range(first_step, first_step + nstep):
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, top, np.array([recharge]))
+        p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, bot, np.array([ic[0]]))
+        conv, reason = p.step_dt(dt, step)
+        if not conv:
+            raise RuntimeError("sy1991 step %d did not converge (reason %d)" % (step, reason))
+        its.append(int(p.stats()["newton_its"][0]))
+    P = p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, -1)
+    sat = p.get_data(K.AUXVAR_INTERNAL, K.VAR_LIQ_SAT, -1)
+    return P, sat, its
+
+
+# ---------------------------------------------------------------------------------------------------
 # regression file format -- src/driver/standalone/util/regression.F90:76-124
 # ---------------------------------------------------------------------------------------------------
 def regression_block(name, category, data, num_cells):

@@ -6,7 +6,10 @@ the reference tree at run time.  Sources (paths relative to the reference root):
   regression_tests/thermal/thermal_mms.regression.baseline      (+ regression_tests/thermal/thermal.cfg)
   regression_tests/th/mass_and_heat.regression.baseline, th_mms.regression.baseline (+ regression_tests/th/th.cfg)
   src/tests/test_eos_{constant,tgdp01,ifc67}_density.F90:16-25  (known answers, typed in below)
+  src/driver/standalone/vsfm/vsfm_sy1991_problem.F90:17-106     (the two 200-value initial-pressure tables of the Srivastava & Yeh (1991)
+                                                                 driver: input DATA of that problem, extracted into sy1991_ic.json)
 """
+import re
 import json
 import os
 import sys
@@ -45,6 +48,17 @@ def main():
         "ifc67": {"den": 55.323696656461536, "dden_dp": 2.4854904480147891e-8, "dden_dT": -1.5298638598102345e-2},
         "tol": {"den": 1e-11, "dden_dp": 1e-16, "dden_dT": 1e-15},
     }
+    # initial conditions of vsfm_sy1991_problem.F90 (data tables, not code)
+    txt = open(os.path.join(REF, "src/driver/standalone/vsfm/vsfm_sy1991_problem.F90")).read()
+    ic = {}
+    for name in ("press_ic_wetting", "press_ic_drying"):
+        m = re.search(r"%s\(200\)\s*=\s*\(/(.*?)/\)" % name, txt, flags=re.S)
+        vals = [float(v.replace("d", "e")) for v in re.findall(r"[-+]?\d+\.\d*d[-+]?\d+", m.group(1))]
+        assert len(vals) == 200, (name, len(vals))
+        ic[name] = vals
+    ic["_source"] = "src/driver/standalone/vsfm/vsfm_sy1991_problem.F90:17-106, extracted by tests/golden/make_golden.py"
+    with open(os.path.join(HERE, "sy1991_ic.json"), "w") as f:
+        json.dump(ic, f)
     with open(os.path.join(HERE, "reference_baselines.json"), "w") as f:
         json.dump(g, f, indent=1, sort_keys=True)
     print("wrote", os.path.join(HERE, "reference_baselines.json"))

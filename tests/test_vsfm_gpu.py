@@ -763,3 +763,18 @@ def test_elm_solve_with_page_locked_host_arrays(mpp):
         mpp.host_unregister(pinned[0])
     oa = a.elm_solve(1800.0, st, 3)                      # a failed (un)register leaves no stale CUDA error behind
     assert oa["nattempts"] >= 1
+
+
+@pytest.mark.parametrize("problem", ["drying", "wetting"])
+def test_sy1991_layered_column_matches_oracle(mpp, oracle, problem):
+    """vsfm_sy1991_problem.F90 (two-layer permeability contrast, mass-rate recharge at the top, Dirichlet head at the bottom, 200 cells:
+    the generic kernel) over the driver's 24 hourly steps: CUDA path vs the oracle, identical Newton iteration counts."""
+    import json, os
+    ic = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "sy1991_ic.json")))
+    start = np.array(ic["press_ic_%s" % problem])
+    g = PB.build_sy1991(mpp.VSFM, start)
+    o = PB.build_sy1991(oracle.OracleVSFM, start, per_column=True)
+    P, S, its = PB.run_sy1991(*g, start, problem)
+    Po, So, its_o = PB.run_sy1991(*o, start, problem)
+    assert relmax_p(P, Po) < RTOL and relmax(S, So) < RTOL
+    assert its == its_o
