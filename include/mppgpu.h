@@ -143,9 +143,10 @@ int  mppgpu_set_step_budget(mppgpu_handle h, int max_residual_evaluations);
  * the four columns a warp advances finish together; mode 0: batch order. */
 int  mppgpu_set_column_ordering(mppgpu_handle h, int mode);
 /* VSFM/thermal: x has ncells entries (pressure or temperature); TH: 2*ncells, [P(0..N-1) | T(0..N-1)] */
-/* NOT in the reference (scheduling only, results are bit-identical either way; soil thermal SoE, nlev <= 16).  mode 1 (default): batches
- * that fill the GPU run on the persistent kernel whose inputs arrive by bulk-async copies (cp.async.bulk, the 1-D TMA path) into
- * shared-memory stages; mode 0: every warp loads its own columns into registers. */
+/* NOT in the reference (scheduling only, results are bit-identical either way; soil thermal SoE, nlev <= 16).  mode 0 (default): every
+ * warp loads its own columns into registers; mode 1: batches that fill the GPU run on the persistent kernel whose inputs arrive by
+ * bulk-async copies (cp.async.bulk, the 1-D TMA path) into shared-memory stages -- measured 23 % slower on B200 (DESIGN.md section 4.2:
+ * the step is bound by the latency of its fp64 chains, not by its loads) and kept as an option for shapes where that may differ. */
 int  mppgpu_thermal_set_bulk_copy(mppgpu_handle h, int mode);
 int  mppgpu_restart(mppgpu_handle h, const double *x, int n);
 

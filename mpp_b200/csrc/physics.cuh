@@ -204,24 +204,13 @@ template <class T> MPP_HD T mpp_exp_poly(T x)
 //           logc_i = -log(invc_i) for the STORED invc_i, so the identity is exact.  12 fp64 instructions, no reciprocal.
 //   exp x:  k = round(128 x / ln2), r = x - k ln2/128 (|r| <= ln2/256), exp x = 2^(k>>7) T[k & 127] (1 + r + r^2/2 + ... + r^5/120)
 //           (truncation < 2^-60).  10 fp64 instructions.
-// The tables (3 KB) sit in global memory and are read through the read-only L1 path; lanes index them independently.
+// The tables (3 KB) sit in global memory and are read through the read-only L1 path; lanes index them independently.  (A per-block copy
+// in shared memory measured slower: 2.21 vs 2.05 ms per Mi columns in the VSFM step kernel, round 2.)
 // Accuracy against libm: < 1.5 ulp over the ranges the soil curves produce (tests/test_physics_host.py).
 // ------------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
 static __device__ const double mpp_log_tab_dev[256] = MPP_LOG_TABLE;
 static __device__ const double mpp_exp_tab_dev[128] = MPP_EXP_TABLE;
-#endif
-#if defined(__CUDACC__) && defined(MPP_SMEM_MATH_TABLES)
-// experiment: a per-block copy of both tables in shared memory (filled by mpp_math_tables_to_smem at kernel entry)
-__shared__ double mpp_tab_smem[384];
-__device__ __forceinline__ void mpp_math_tables_to_smem()
-{
-  for (int i = threadIdx.x; i < 192; i += blockDim.x) {
-    const double2 t = (i < 128) ? reinterpret_cast<const double2 *>(mpp_log_tab_dev)[i] : reinterpret_cast<const double2 *>(mpp_exp_tab_dev)[i - 128];
-    reinterpret_cast<double2 *>(mpp_tab_smem)[i] = t;
-  }
-  __syncthreads();
-}
 #endif
 static const double mpp_log_tab_host[256] = MPP_LOG_TABLE;
 static const double mpp_exp_tab_host[128] = MPP_EXP_TABLE;
@@ -234,10 +223,7 @@ MPP_HD void log_tab_reduce(double x, double &r, double &w)
   const int i = (tmp >> 13) & 127;
   const int k = tmp >> 20;                                     // arithmetic shift: floor
   const double z = mpp_join(hi - (tmp & (int)0xfff00000), lo);
-#if defined(__CUDA_ARCH__) && defined(MPP_SMEM_MATH_TABLES)
-  const double2 t = reinterpret_cast<const double2 *>(mpp_tab_smem)[i];
-  const double invc = t.x, logc = t.y;
-#elif defined(__CUDA_ARCH__)
+#ifdef __CUDA_ARCH__
   const double2 t = __ldg(reinterpret_cast<const double2 *>(mpp_log_tab_dev) + i);
   const double invc = t.x, logc = t.y;
 #else
@@ -268,9 +254,7 @@ MPP_HD double exp_tab_scale(double fn)
   int hi; unsigned lo;
   mpp_split(fn, hi, lo);                                       // fn = 1.5 * 2^52 + round(128 x / ln2): the low word holds the integer k
   const int k = (int)lo;
-#if defined(__CUDA_ARCH__) && defined(MPP_SMEM_MATH_TABLES)
-  const double T = mpp_tab_smem[256 + (k & 127)];
-#elif defined(__CUDA_ARCH__)
+#ifdef __CUDA_ARCH__
   const double T = __ldg(mpp_exp_tab_dev + (k & 127));
 #else
   const double T = mpp_exp_tab_host[k & 127];

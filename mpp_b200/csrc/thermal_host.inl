@@ -256,7 +256,7 @@ static bool thermal_tma_plan(const ThermalArgs &A, ThermalTmaPlan &P)
   const int cells = TMA_TILE_COLS * A.nlev;
   P.stage_bytes = P.n_cell_d * cells * 8 + P.n_cell_i * cells * 4 + P.n_col_d * TMA_TILE_COLS * 8 + P.n_col_i * TMA_TILE_COLS * 4;
   P.ntiles = (A.ncol + TMA_TILE_COLS - 1) / TMA_TILE_COLS;
-  if ((size_t)TMA_WARPS * P.stage_bytes > 44 * 1024) return false;
+  if ((size_t)TMA_STAGES * P.stage_bytes > 100 * 1024) return false;
   // the last tile may hang over the end of the batch by up to TMA_TILE_COLS - 1 columns: covered by the allocation slack
   if ((size_t)(TMA_TILE_COLS - 1) * A.nlev * 8 > MPP_ALLOC_SLACK) return false;
   return true;
@@ -297,11 +297,11 @@ static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
   const int nlev = h->nlev;
   // bulk-async (1-D TMA) persistent variant for the shapes it covers and batches that fill the machine (thermal_kernels.cuh)
   ThermalTmaPlan P;
-  const bool tma = t->bulk_copy && nlev <= 16 && thermal_tma_plan(A, P) && P.ntiles >= 2 * TMA_WARPS * TMA_BLOCKS_PER_SM * h->sm_count;
+  const bool tma = t->bulk_copy && nlev <= 16 && thermal_tma_plan(A, P) && P.ntiles >= 2 * h->sm_count;
   if (tma) {
-    const size_t smem = (size_t)TMA_WARPS * P.stage_bytes;
-    if (!t->tma_attr_set) { CK(cudaFuncSetAttribute(thermal_step2_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 44 * 1024)); t->tma_attr_set = true; }
-    const int grid = std::min((P.ntiles + TMA_WARPS - 1) / TMA_WARPS, h->sm_count * TMA_BLOCKS_PER_SM);
+    const size_t smem = (size_t)TMA_STAGES * P.stage_bytes;
+    if (!t->tma_attr_set) { CK(cudaFuncSetAttribute(thermal_step2_tma_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); t->tma_attr_set = true; }
+    const int grid = std::min(P.ntiles, h->sm_count * TMA_BLOCKS_PER_SM);
     thermal_step2_tma_kernel<8><<<grid, TH_TILE, smem, h->stream>>>(A, P);
   } else if (nlev <= 32) {
     if (nlev <= 16) thermal_step2_kernel<8><<<nblk((long long)h->ncol * 8, TH_TILE), TH_TILE, 0, h->stream>>>(A);

@@ -258,77 +258,41 @@ __device__ __forceinline__ double thermal_pcr_unit(double al, double ga, double 
   return de;
 }
 
-// ---- phase A: everything a lane needs from memory, issued in one go (cell inputs, the column's area / land-unit type, and the heat-flux
-// boundary values of the lane that owns the top / bottom cell) --------------------------------------------------------------------
-struct ThermalRaw {
-  double T, dz, tf, liq, ice, snoww, por, tkmg, tkdry, csol, ssum, du, dd;
-  int act, nsnow;
-};
-struct ThermalColRaw {
-  double area; int itype;
-  double H[2], dH[2], fr[2];      // COND_HEAT_FLUX value, dhsdT, frac per region slot (0 where this lane does not own that cell)
-};
-
-__device__ __forceinline__ void thermal_raw_load(const ThermalArgs &A, const ThermalPtrs &V, ThermalRaw &r, bool valid, long long cell, int col, int j, int jtop, int jbot)
+__device__ __forceinline__ void thermal_cell_load(const ThermalArgs &A, const ThermalPtrs &V, ThermalCell &c, bool valid, long long cell, int col, int j, int jtop, int jbot)
 {
-  r.T = 0.0; r.dz = 1.0; r.tf = 1.0; r.liq = 0.0; r.ice = 0.0; r.snoww = 0.0; r.por = 0.5; r.tkmg = 1.0; r.tkdry = 1.0; r.csol = 0.0;
-  r.ssum = 0.0; r.du = 0.5; r.dd = 0.5; r.act = 0; r.nsnow = 0;
+  c.T = 0.0; c.tk = 1.0; c.hc = 0.0; c.dz = 1.0; c.tf = 1.0; c.du = 0.5; c.dd = 0.5; c.ssum = 0.0; c.act = 0;
   if (valid) {
-    r.T = V.T_in[cell]; r.dz = V.dz[cell]; r.tf = V.tuning[cell]; r.act = V.active[cell];
-    r.liq = V.liq[cell]; r.ice = V.ice[cell]; r.snoww = V.snow_water[cell];
-    r.por = V.por[cell]; r.tkmg = V.tkmg[cell]; r.tkdry = V.tkdry[cell]; r.csol = V.csol[cell];
-    r.nsnow = V.nsnow[cell];
-    if (A.dist_uniform) { r.du = A.lay_du[j]; r.dd = A.lay_dd[j]; }
-    else if (A.dist_up) { r.du = A.dist_up[cell]; r.dd = A.dist_dn[cell]; }
+    c.T = V.T_in[cell]; c.dz = V.dz[cell]; c.tf = V.tuning[cell]; c.act = V.active[cell];
+    const double liq = V.liq[cell], ice = V.ice[cell], snoww = V.snow_water[cell];
+    const double por = V.por[cell], tkmg = V.tkmg[cell], tkdry = V.tkdry[cell], csol = V.csol[cell];
+    const int nsnow = V.nsnow[cell];
+    if (A.dist_uniform) { c.du = A.lay_du[j]; c.dd = A.lay_dd[j]; }
+    else if (A.dist_up) { c.du = A.dist_up[cell]; c.dd = A.dist_dn[cell]; }
 #pragma unroll
     for (int k = 0; k < TH_MAX_SS; ++k) if (k < A.nss) {          // COND_HEAT_RATE
-      if (A.ss_region[k] == 403) r.ssum += V.ss_value[k][cell];
-      else if (j == (A.ss_region[k] == 401 ? jtop : jbot)) r.ssum += V.ss_value[k][col];
+      if (A.ss_region[k] == 403) c.ssum += V.ss_value[k][cell];
+      else if (j == (A.ss_region[k] == 401 ? jtop : jbot)) c.ssum += V.ss_value[k][col];
     }
-  }
-}
-
-__device__ __forceinline__ void thermal_col_load(const ThermalArgs &A, const ThermalPtrs &V, ThermalColRaw &c, bool col_ok, int col, bool own_top, bool own_bot)
-{
-  c.area = 1.0; c.itype = 0;
-#pragma unroll
-  for (int k = 0; k < 2; ++k) { c.H[k] = 0.0; c.dH[k] = 0.0; c.fr[k] = 0.0; }
-  if (col_ok) {
-    c.area = V.area[col]; c.itype = V.lun_type[col];
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      if (A.bc_type[k] == 507 && (k == 0 ? own_top : own_bot)) { c.H[k] = V.bc_value[k][col]; c.dH[k] = V.bc_dhsdT[k][col]; c.fr[k] = V.bc_frac[k][col]; }
-  }
-}
-
-// ---- phase B ------------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void thermal_cell_aux(const ThermalArgs &A, const ThermalPtrs &V, const ThermalRaw &r, const ThermalColRaw &cr, ThermalCell &c,
-                                                 bool valid, long long cell, int j)
-{
-  c.T = r.T; c.tk = 1.0; c.hc = 0.0; c.dz = r.dz; c.tf = r.tf; c.du = r.du; c.dd = r.dd; c.ssum = r.ssum; c.act = r.act;
-  if (valid) {
-    thermal_auxvar(A, cr.itype, j < A.nlevsoi, r.T, r.liq, r.ice, r.snoww, r.nsnow, r.por, r.tkmg, r.tkdry, r.csol, r.dz, c.tk, c.hc);
+    thermal_auxvar(A, V.lun_type[col], j < A.nlevsoi, c.T, liq, ice, snoww, nsnow, por, tkmg, tkdry, csol, c.dz, c.tk, c.hc);
     if (V.therm_cond) { V.therm_cond[cell] = c.tk; V.heat_cap[cell] = c.hc; }
   }
 }
 
 // boundary-condition terms of the cell that sits at the top / bottom of its column (as thermal_step_kernel)
-__device__ __forceinline__ void thermal_cell_bc(const ThermalArgs &A, const ThermalPtrs &V, const ThermalRaw &r, const ThermalColRaw &cr, ThermalCell &c,
-                                                long long cell, int col, int j, int jtop, int jbot, double area)
+__device__ __forceinline__ void thermal_cell_bc(const ThermalArgs &A, const ThermalPtrs &V, ThermalCell &c, long long cell, int col, int j, int jtop, int jbot, double area)
 {
   const double cnfac = A.cnfac;
 #pragma unroll
   for (int k = 0; k < 2; ++k) {
     if (A.bc_type[k] == 0 || j != (k == 0 ? jtop : jbot)) continue;
     if (A.bc_type[k] == 507) {                    // COND_HEAT_FLUX: value = H - dH/dT * T_cell (GoveqnThermalKSP...:344-348)
-      const double H = cr.H[k], dH = cr.dH[k], fr = cr.fr[k];
+      const double H = V.bc_value[k][col], dH = V.bc_dhsdT[k][col], fr = V.bc_frac[k][col];
       c.rhs = c.rhs + (H - dH * c.T) * fr * area;
       c.bb += -fr * ((area == 1.0) ? dH : pow(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
-    } else if (V.bc_active[k][col] != 0.0) {      // COND_DIRICHLET (rare path: its values are loaded here)
+    } else if (V.bc_active[k][col] != 0.0) {      // COND_DIRICHLET
       double tkb, hcb;
       const double Tb = V.bc_value[k][col];
-      // boundary aux vars never receive is_soil_shallow / water contents (MultiPhysicsProbThermal.F90:195-203)
-      thermal_auxvar(A, cr.itype, false, Tb, 0.0, 0.0, 0.0, 0, r.por, r.tkmg, r.tkdry, r.csol, c.dz, tkb, hcb);
+      thermal_auxvar(A, V.lun_type[col], false, Tb, 0.0, 0.0, 0.0, 0, V.por[cell], V.tkmg[cell], V.tkdry[cell], V.csol[cell], c.dz, tkb, hcb);
       const double bdu = 0.0, bdd = 0.5 * c.dz, dist = bdu + bdd;
       const double kav = tkb * c.tk * dist / (tkb * bdd + c.tk * bdu);
       c.rhs = c.rhs + kav / dist * Tb * A.stale_area;
@@ -339,9 +303,8 @@ __device__ __forceinline__ void thermal_cell_bc(const ThermalArgs &A, const Ther
 
 // The step of one column group: `V` holds the launch's own arrays (global memory, `col` a batch column) or a tile-local view whose
 // input pointers aim at a shared-memory stage filled by bulk-async copies (`col` a column of the tile): the arithmetic is the same code.
-// RELEASE(): called once every input has been read into registers (the bulk-async kernel hands its stage back to the copy engine there).
-template <int LPC, class Release>
-__device__ __forceinline__ void thermal_step2_body(const ThermalArgs &A, const ThermalPtrs &V, int col, int l, Release release)
+template <int LPC>
+__device__ __forceinline__ void thermal_step2_body(const ThermalArgs &A, const ThermalPtrs &V, int col, int l)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const int nlev = A.nlev;
@@ -350,17 +313,11 @@ __device__ __forceinline__ void thermal_step2_body(const ThermalArgs &A, const T
   const double dt = A.dt, cnfac = A.cnfac;
   const bool col_ok = col < V.ncol, va = col_ok && j0 < nlev, vb = col_ok && j1 < nlev;
   const long long cell0 = (long long)col * nlev + j0;
+  const double area = col_ok ? V.area[col] : 1.0;
 
-  ThermalRaw ra, rb;
-  ThermalColRaw cr;
-  thermal_col_load(A, V, cr, col_ok, col, (va && j0 == jtop) || (vb && j1 == jtop), (va && j0 == jbot) || (vb && j1 == jbot));
-  thermal_raw_load(A, V, ra, va, cell0, col, j0, jtop, jbot);
-  thermal_raw_load(A, V, rb, vb, cell0 + 1, col, j1, jtop, jbot);
-  release();
-  const double area = cr.area;
   ThermalCell a, b;
-  thermal_cell_aux(A, V, ra, cr, a, va, cell0, j0);
-  thermal_cell_aux(A, V, rb, cr, b, vb, cell0 + 1, j1);
+  thermal_cell_load(A, V, a, va, cell0, col, j0, jtop, jbot);
+  thermal_cell_load(A, V, b, vb, cell0 + 1, col, j1, jtop, jbot);
 
   // connections 2l -> 2l+1 (in-lane) and 2l+1 -> 2(l+1) (the next lane's first cell)
   const double T_n = __shfl_down_sync(FULL, a.T, 1, LPC), tk_n = __shfl_down_sync(FULL, a.tk, 1, LPC), dz_n = __shfl_down_sync(FULL, a.dz, 1, LPC);
@@ -383,15 +340,15 @@ __device__ __forceinline__ void thermal_step2_body(const ThermalArgs &A, const T
   if (l > 0) { a.rhs = a.rhs - cnfac * fl_p; a.bb += cv_p; }
   b.rhs = b.rhs + cnfac * fl_b; b.bb += cv_b;
   b.rhs = b.rhs - cnfac * fl_a; b.bb += cv_a;
-  if (va && a.act) { thermal_cell_bc(A, V, ra, cr, a, cell0, col, j0, jtop, jbot, area); a.rhs = a.rhs + a.ssum; }
-  if (vb && b.act) { thermal_cell_bc(A, V, rb, cr, b, cell0 + 1, col, j1, jtop, jbot, area); b.rhs = b.rhs + b.ssum; }
+  if (va && a.act) { thermal_cell_bc(A, V, a, cell0, col, j0, jtop, jbot, area); a.rhs = a.rhs + a.ssum; }
+  if (vb && b.act) { thermal_cell_bc(A, V, b, cell0 + 1, col, j1, jtop, jbot, area); b.rhs = b.rhs + b.ssum; }
   if (!va) { a.bb = 1.0; a.rhs = 0.0; }
   if (!vb) { b.bb = 1.0; b.rhs = 0.0; }
 
   // symmetric tridiagonal rows: sub_a = -cv_p, sup_a = sub_b = -cv_a, sup_b = -cv_b   (KSPSolve: exact for a tridiagonal matrix)
   const double sub_a = (l > 0) ? -cv_p : 0.0, sup_a = -cv_a, sub_b = -cv_a, sup_b = -cv_b;
-  const double rb_ = rcp(b.bb);
-  const double bs = sub_b * rb_, bu = sup_b * rb_, bf = b.rhs * rb_;       // y_b = bf - bs y_a(l) - bu y_a(l+1)
+  const double rb = rcp(b.bb);
+  const double bs = sub_b * rb, bu = sup_b * rb, bf = b.rhs * rb;          // y_b = bf - bs y_a(l) - bu y_a(l+1)
   const double bs_p = __shfl_up_sync(FULL, bs, 1, LPC), bu_p = __shfl_up_sync(FULL, bu, 1, LPC), bf_p = __shfl_up_sync(FULL, bf, 1, LPC);
   const double rB = rcp(a.bb - sub_a * bu_p - sup_a * bs);
   const double al = (-sub_a * bs_p) * rB, ga = (-sup_a * bu) * rB, de = (a.rhs - sub_a * bf_p - sup_a * bf) * rB;
@@ -403,33 +360,33 @@ __device__ __forceinline__ void thermal_step2_body(const ThermalArgs &A, const T
 }
 
 #ifndef THERMAL2_MIN_BLOCKS
-#define THERMAL2_MIN_BLOCKS 6
+#define THERMAL2_MIN_BLOCKS 8      // 64 registers (a 100-byte spill), 32 warps per SM: 0.376 ms per Mi columns against 0.390 at 6 blocks / 79 registers
 #endif
 template <int LPC>
 __global__ void __launch_bounds__(TH_TILE, THERMAL2_MIN_BLOCKS)
 thermal_step2_kernel(const ThermalArgs A)
 {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  thermal_step2_body<LPC>(A, thermal_ptrs(A), (int)(tid / LPC), (int)(tid % LPC), [] {});
+  thermal_step2_body<LPC>(A, thermal_ptrs(A), (int)(tid / LPC), (int)(tid % LPC));
 }
 
-// ---- bulk-async (1-D TMA) variant ------------------------------------------------------------------------------------------------
-// thermal_step2_kernel issues its ~13 input streams as ordinary loads at the top of each warp's life and then computes: 40 % of its
-// stall samples sit on the first use of the loaded values and DRAM runs at half its copy rate (profiles/r1_thermal_v4.md).
-// Here the loads leave the warps' instruction streams.  Warps are persistent; each walks over tiles of 4 columns (its own lanes' 60
-// cells).  For every tile the warp's lane 0 issues one cp.async.bulk per input array (contiguous in the reference's cell order:
-// 4 * nlev * 8 B each) into the warp's private shared-memory stage and arms the warp's mbarrier with the byte count.  When the data
-// has landed the lanes pull their values into registers (phase A of thermal_step2_body), hand the stage straight back to the copy
-// engine for the NEXT tile, and only then compute (phase B): the copy of tile i+1 runs under the arithmetic of tile i, with one
-// stage (5.9 KB) per warp and no block-wide barrier anywhere.
-// Supported shape (anything else uses thermal_step2_kernel): nlev <= 16, heat-flux or no boundary condition per region, at most
-// TMA_MAX_SS_CELL per-cell and TMA_MAX_SS_COL per-column heat-rate sources, default or per-layer-uniform connection distances.
-// The last tile may hang over the end of the batch: every device buffer of the library carries MPP_ALLOC_SLACK bytes of slack, and the
-// over-read columns are masked like any padding lane.
-constexpr int TMA_TILE_COLS = 4, TMA_MAX_SS_CELL = 2, TMA_MAX_SS_COL = 2, TMA_WARPS = TH_TILE / 32;
-#ifndef TMA_BLOCKS_PER_SM
-#define TMA_BLOCKS_PER_SM 5
-#endif
+// ---- bulk-async (1-D TMA) variant: measured, slower, kept as an option --------------------------------------------------------------
+// Question: thermal_step2_kernel issues its ~13 input streams as ordinary loads at the top of each warp's life and
+// then computes; 40 % of its stall samples sit on the first use of a loaded value and DRAM runs at half its copy rate
+// (profiles/r1_thermal_v4.md).  Does taking the loads out of the warps' instruction streams -- persistent blocks, one cp.async.bulk per
+// input array and tile into a shared-memory stage, an mbarrier armed with the byte count, the copy of tile i+1 under the arithmetic
+// of tile i -- reach the HBM roofline?
+// Answer, measured on B200 at 1 Mi columns x 15: no.  This kernel (2 stages per block of 4 warps, 4 blocks per
+// SM) needs 0.481 ms against 0.390 ms for the register kernel; a per-warp pipeline (one 5.9 KB stage per warp, the stage handed back
+// to the copy engine as soon as the lanes hold their inputs in registers) needs 0.565 ms with 16 warps per SM, 0.59 ms with 20
+// (spilling) and 0.68 ms with 12.  Time goes DOWN with the number of resident warps and does not care whether the inputs are already
+// in shared memory: the step is bound by the issue / dependent latency of its fp64 chains (log, exp, four reciprocals, three PCR
+// stages per lane), and shared-memory staging costs warps (11.8 KB of stage per warp against ~10 KB of registers).
+// The kernel stays selectable (mppgpu_thermal_set_bulk_copy(h, 1)) and bit-identical to the register kernel (same device function).
+// Supported shape: nlev <= 16, heat-flux or no boundary condition per region, at most TMA_MAX_SS_CELL per-cell and TMA_MAX_SS_COL
+// per-column heat-rate sources, default or per-layer-uniform connection distances.  The last tile may hang over the end of the
+// batch: every device buffer of the library carries MPP_ALLOC_SLACK bytes of slack, and the over-read columns are computed and dropped.
+constexpr int TMA_TILE_COLS = 16, TMA_STAGES = 2, TMA_MAX_SS_CELL = 2, TMA_MAX_SS_COL = 2, TMA_BLOCKS_PER_SM = 4;
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count)
@@ -450,7 +407,7 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 struct ThermalTmaPlan {            // which arrays travel, in stage order (host-built: thermal_tma_plan)
   int n_cell_d, n_cell_i, n_col_d, n_col_i;      // counts of per-cell double / int and per-column double / int arrays
   const void *cell_d[16], *cell_i[2], *col_d[12], *col_i[1];
-  int stage_bytes;                 // one warp's stage
+  int stage_bytes;
   int ntiles;                      // tiles of TMA_TILE_COLS columns
 };
 
@@ -458,62 +415,63 @@ template <int LPC>
 __global__ void __launch_bounds__(TH_TILE, TMA_BLOCKS_PER_SM)
 thermal_step2_tma_kernel(const ThermalArgs A, const ThermalTmaPlan P)
 {
-  static_assert(32 / LPC == TMA_TILE_COLS, "one tile = the columns one warp advances");
+  static_assert(TH_TILE / LPC == TMA_TILE_COLS, "one tile = the columns one block advances");
   extern __shared__ __align__(128) unsigned char tma_smem[];
-  __shared__ unsigned long long full_bar[TMA_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ unsigned long long full_bar[TMA_STAGES];
   const int nlev = A.nlev, cells = TMA_TILE_COLS * nlev;
   const unsigned cd_bytes = (unsigned)cells * 8u, ci_bytes = (unsigned)cells * 4u, kd_bytes = TMA_TILE_COLS * 8u, ki_bytes = TMA_TILE_COLS * 4u;
-  unsigned char *const stage = tma_smem + (size_t)warp * P.stage_bytes;
-  unsigned long long *const bar = &full_bar[warp];
-  if (lane == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-  __syncwarp();
-
-  auto issue = [&](int tile) {                                // lane 0 only
-    unsigned char *dst = stage;
-    const size_t c0 = (size_t)tile * cells, k0 = (size_t)tile * TMA_TILE_COLS;
-    mbar_arrive_expect_tx(bar, (unsigned)P.stage_bytes);
-    for (int i = 0; i < P.n_cell_d; ++i) { bulk_g2s(dst, (const double *)P.cell_d[i] + c0, cd_bytes, bar); dst += cd_bytes; }
-    for (int i = 0; i < P.n_cell_i; ++i) { bulk_g2s(dst, (const int *)P.cell_i[i] + c0, ci_bytes, bar); dst += ci_bytes; }
-    for (int i = 0; i < P.n_col_d; ++i)  { bulk_g2s(dst, (const double *)P.col_d[i] + k0, kd_bytes, bar); dst += kd_bytes; }
-    for (int i = 0; i < P.n_col_i; ++i)  { bulk_g2s(dst, (const int *)P.col_i[i] + k0, ki_bytes, bar); dst += ki_bytes; }
-  };
-  const int first = blockIdx.x * TMA_WARPS + warp, stride = gridDim.x * TMA_WARPS;
-  if (lane == 0 && first < P.ntiles) issue(first);
-
-  // tile-local view of the warp's stage: the same field order as thermal_tma_plan (fixed for the whole launch)
-  ThermalPtrs V = thermal_ptrs(A);
-  {
-    const unsigned char *q = stage;
-    auto takeD = [&](unsigned bytes) { const double *r = (const double *)q; q += bytes; return r; };
-    auto takeI = [&](unsigned bytes) { const int *r = (const int *)q; q += bytes; return r; };
-    V.T_in = takeD(cd_bytes); V.dz = takeD(cd_bytes); V.tuning = takeD(cd_bytes); V.liq = takeD(cd_bytes); V.ice = takeD(cd_bytes);
-    V.snow_water = takeD(cd_bytes); V.por = takeD(cd_bytes); V.tkmg = takeD(cd_bytes); V.tkdry = takeD(cd_bytes); V.csol = takeD(cd_bytes);
-#pragma unroll
-    for (int k = 0; k < TH_MAX_SS; ++k) if (k < A.nss && A.ss_region[k] == 403) V.ss_value[k] = takeD(cd_bytes);
-    V.active = takeI(ci_bytes); V.nsnow = takeI(ci_bytes);
-    V.area = takeD(kd_bytes);
-#pragma unroll
-    for (int k = 0; k < 2; ++k) if (A.bc_type[k] == 507) { V.bc_value[k] = takeD(kd_bytes); V.bc_dhsdT[k] = takeD(kd_bytes); V.bc_frac[k] = takeD(kd_bytes); }
-#pragma unroll
-    for (int k = 0; k < TH_MAX_SS; ++k) if (k < A.nss && A.ss_region[k] != 403) V.ss_value[k] = takeD(kd_bytes);
-    V.lun_type = takeI(ki_bytes);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) mbar_init(&full_bar[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  unsigned parity = 0;
-  for (int tile = first; tile < P.ntiles; tile += stride, parity ^= 1u) {
-    mbar_wait(bar, parity);
+  __syncthreads();
+
+  auto issue = [&](int tile, int stage) {                     // thread 0 only
+    unsigned char *dst = tma_smem + (size_t)stage * P.stage_bytes;
+    const size_t c0 = (size_t)tile * cells, k0 = (size_t)tile * TMA_TILE_COLS;
+    mbar_arrive_expect_tx(&full_bar[stage], (unsigned)P.stage_bytes);
+    for (int i = 0; i < P.n_cell_d; ++i) { bulk_g2s(dst, (const double *)P.cell_d[i] + c0, cd_bytes, &full_bar[stage]); dst += cd_bytes; }
+    for (int i = 0; i < P.n_cell_i; ++i) { bulk_g2s(dst, (const int *)P.cell_i[i] + c0, ci_bytes, &full_bar[stage]); dst += ci_bytes; }
+    for (int i = 0; i < P.n_col_d; ++i)  { bulk_g2s(dst, (const double *)P.col_d[i] + k0, kd_bytes, &full_bar[stage]); dst += kd_bytes; }
+    for (int i = 0; i < P.n_col_i; ++i)  { bulk_g2s(dst, (const int *)P.col_i[i] + k0, ki_bytes, &full_bar[stage]); dst += ki_bytes; }
+  };
+  const int first = blockIdx.x, stride = gridDim.x;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TMA_STAGES; ++s) if (first + s * stride < P.ntiles) issue(first + s * stride, s);
+  }
+  const int col_local = threadIdx.x / LPC, l = threadIdx.x % LPC;
+  int it = 0;
+  for (int tile = first; tile < P.ntiles; tile += stride, ++it) {
+    const int stage = it % TMA_STAGES;
+    mbar_wait(&full_bar[stage], (unsigned)((it / TMA_STAGES) & 1));
+    // tile-local view of the stage: the same field order as thermal_tma_plan
+    ThermalPtrs V = thermal_ptrs(A);
+    {
+      const unsigned char *q = tma_smem + (size_t)stage * P.stage_bytes;
+      auto takeD = [&](unsigned bytes) { const double *r = (const double *)q; q += bytes; return r; };
+      auto takeI = [&](unsigned bytes) { const int *r = (const int *)q; q += bytes; return r; };
+      V.T_in = takeD(cd_bytes); V.dz = takeD(cd_bytes); V.tuning = takeD(cd_bytes); V.liq = takeD(cd_bytes); V.ice = takeD(cd_bytes);
+      V.snow_water = takeD(cd_bytes); V.por = takeD(cd_bytes); V.tkmg = takeD(cd_bytes); V.tkdry = takeD(cd_bytes); V.csol = takeD(cd_bytes);
+#pragma unroll
+      for (int k = 0; k < TH_MAX_SS; ++k) if (k < A.nss && A.ss_region[k] == 403) V.ss_value[k] = takeD(cd_bytes);
+      V.active = takeI(ci_bytes); V.nsnow = takeI(ci_bytes);
+      V.area = takeD(kd_bytes);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) if (A.bc_type[k] == 507) { V.bc_value[k] = takeD(kd_bytes); V.bc_dhsdT[k] = takeD(kd_bytes); V.bc_frac[k] = takeD(kd_bytes); }
+#pragma unroll
+      for (int k = 0; k < TH_MAX_SS; ++k) if (k < A.nss && A.ss_region[k] != 403) V.ss_value[k] = takeD(kd_bytes);
+      V.lun_type = takeI(ki_bytes);
+    }
     const long long cbase = (long long)tile * cells;
     V.ncol = min(TMA_TILE_COLS, A.ncol - tile * TMA_TILE_COLS);
     V.T_out = A.T_out + cbase;
     if (A.therm_cond) { V.therm_cond = A.therm_cond + cbase; V.heat_cap = A.heat_cap + cbase; }
-    const int next = tile + stride;
-    thermal_step2_body<LPC>(A, V, lane / LPC, lane % LPC, [&] {
-      __syncwarp();                                            // every lane holds its inputs in registers: the stage is free
-      if (lane == 0 && next < P.ntiles) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads above, async-proxy writes below
-        issue(next);
-      }
-    });
+    thermal_step2_body<LPC>(A, V, col_local, l);
+    __syncthreads();                                            // every thread is done with this stage
+    if (threadIdx.x == 0 && tile + TMA_STAGES * stride < P.ntiles) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy reads above, async-proxy writes below
+      issue(tile + TMA_STAGES * stride, stage);
+    }
   }
 }
 
@@ -604,7 +562,7 @@ struct ThermalState {
   double stale_area = 1.0;
   // snow + standing-surface-water coupling (thermal_snow_kernels.cuh): mailbox arrays then hold ncol*(nsno+1+nlev) entries
   bool snow_mode = false, force_two_rows = false; int nsno = 0; size_t nall = 0;
-  bool bulk_copy = true, tma_attr_set = false;      // mppgpu_thermal_set_bulk_copy: the bulk-async (1-D TMA) kernel where its shape fits
+  bool bulk_copy = false, tma_attr_set = false;      // mppgpu_thermal_set_bulk_copy: the bulk-async (1-D TMA) kernel where its shape fits
   double *soil_top_dist_dn = nullptr, *hs[3] = {nullptr, nullptr, nullptr}, *dhs[3] = {nullptr, nullptr, nullptr},
          *frac_soil = nullptr, *sabg_snow = nullptr, *sabg_soil = nullptr;
   int *snow_top_id = nullptr;

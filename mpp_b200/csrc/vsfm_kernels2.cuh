@@ -33,11 +33,6 @@ namespace mpp {
 #ifndef VSFM2_THREADS
 #define VSFM2_THREADS 32
 #endif
-#ifdef VSFM2_COLD_HINTS
-#define MPP_RARE(x) __builtin_expect(!!(x), 0)
-#else
-#define MPP_RARE(x) (x)
-#endif
 #ifndef VSFM2_MIN_BLOCKS
 #define VSFM2_MIN_BLOCKS 16
 #endif
@@ -193,9 +188,6 @@ vsfm_step2_kernel(const VsfmArgs A)
   const long long cell0 = (long long)col * nlev + j0;
   const double area = col_ok ? A.area[col] : 1.0;
 
-#ifdef MPP_SMEM_MATH_TABLES
-  mpp_math_tables_to_smem();
-#endif
   // ---- static per-cell data -----------------------------------------------------------------------
   __shared__ double s_par[2][ParCount<SATFUNC>::value][VSFM2_THREADS];
   double (*const pa)[VSFM2_THREADS] = s_par[0], (*const pb)[VSFM2_THREADS] = s_par[1];
@@ -426,7 +418,7 @@ vsfm_step2_kernel(const VsfmArgs A)
       lambda = nw ? 1.0 : lambda; ls_count = nw ? 0 : ls_count;
       a.W = nw ? a.X - Ya : a.W; b.W = nw ? b.X - Yb : b.W;           // W = X - lambda Y with lambda = 1
       phase = nw ? PH_LS_FULL : phase;
-      if (MPP_RARE(nw && (yn2 == 0.0 || yn2 > maxstep2 || (nfuncs >= so.max_funcs && so.max_funcs >= 0)))) {
+      if (nw && (yn2 == 0.0 || yn2 > maxstep2 || (nfuncs >= so.max_funcs && so.max_funcs >= 0))) {
         if (y2 == 0.0) {
           // zero step: line search "fails"; stol*xnorm > ynorm => SNES_CONVERGED_SNORM_RELATIVE (ls.c)
           last_reason = (stol2 * x2 > y2) ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
@@ -442,7 +434,7 @@ vsfm_step2_kernel(const VsfmArgs A)
     // ================= end-of-SNES bookkeeping (SOEBaseStepDT_SNES :481-536) =================
     if (phase == -1) {
       tot_nf += nfuncs;
-      if (MPP_RARE(last_reason < 0)) {
+      if (last_reason < 0) {
         cuts += 1; dt_iter = 0.5 * dt_iter; dtInv = 1.0 / dt_iter;
         a.X = PA(PI_XPREV); b.X = PB(PI_XPREV);             // VecCopy(soln_prev, soln)
         if (cuts > 20) { converged = 0; phase = PH_DONE; }
@@ -572,7 +564,7 @@ vsfm_step2_kernel(const VsfmArgs A)
         if (is_init) { if (a.valid) a.W = A.eval_x[cell0]; if (b.valid) b.W = A.eval_x[cell0 + 1]; phase = PH_VEVAL; }
         else phase = PH_NEWTON;
       }
-    } else if (MPP_RARE(is_full)) {
+    } else if (is_full) {
       if (g_bad) {
         if (lambda <= so.ls_minlambda) { last_reason = SNES_DIVERGED_FNORM_NAN; phase = -1; }
         else if (out_of_funcs)         { last_reason = SNES_DIVERGED_FUNCTION_COUNT; phase = -1; }
@@ -589,7 +581,7 @@ vsfm_step2_kernel(const VsfmArgs A)
         lambda = (lt <= .1 * lambda) ? .1 * lambda : lt;
         a.W = fma(-lambda, PA(PI_Y), a.X); b.W = fma(-lambda, PB(PI_Y), b.X); phase = PH_LS_QUAD; ls_count = 0;
       }
-    } else if (MPP_RARE(is_bt)) {
+    } else if (is_bt) {
       const int ls_fail = tiny_step ? SNES_CONVERGED_SNORM_RELATIVE : SNES_DIVERGED_LINE_SEARCH;
       if (g_bad) {
         last_reason = ls_fail; phase = -1;

@@ -336,7 +336,8 @@ class Thermal(_SoE):
     MPPThermalSetSoils = set_soils
 
     def set_bulk_copy(self, mode):
-        """1 (default): the persistent bulk-async (1-D TMA) kernel where its shape fits; 0: register loads.  Results are bit-identical."""
+        """0 (default): register loads; 1: the persistent bulk-async (1-D TMA) kernel where its shape fits (measured slower on B200).
+        Results are bit-identical."""
         check(self.L.mppgpu_thermal_set_bulk_copy(self.h, int(mode)))
 
     def set_cnfac(self, cnfac):
