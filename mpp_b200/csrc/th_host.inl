@@ -161,6 +161,8 @@ static int th_fill_args(mppgpu_soe *h, THState *t, THArgs &A, double dt)
     THCondDev &d = A.ss[A.nss++];
     d.value = c->value.p; d.bc_pressure = nullptr; d.ieqn = c->ieqn; d.itype = c->itype; d.region = c->region;
   }
+  // one Dirichlet temperature at the top of columns of <= 15 layers: the boundary connection rides on the kernel's padding lane
+  A.bc_on_pad_lane = (h->nlev <= 15 && A.top_is_first && A.nbc == 1 && A.bc[0].ieqn == 2 && A.bc[0].region == REGION_TOP && A.bc[0].itype == COND_DIRICHLET) ? 1 : 0;
   A.liq_sat = t->liq_sat; A.mass = t->mass;
   A.stat_its = h->stat_its.p; A.stat_reason = h->stat_reason.p; A.stat_cuts = h->stat_cuts.p; A.stat_nf = h->stat_nf.p;
   A.dt = dt; A.so = h->so;

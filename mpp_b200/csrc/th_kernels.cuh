@@ -38,6 +38,9 @@ struct THArgs {
   double *block_partials;
   double dt;
   SnesOpts so;
+  // the only boundary condition is a Dirichlet temperature at the top of a column of <= 15 layers (the ELM-like TH batch): the fast
+  // kernel treats the boundary aux var as one more cell on the padding lane (th_kernels2.cuh) instead of a one-lane loop
+  int bc_on_pad_lane;
   // kernel unit-test probe (mppgpu_eval): accumulation at x_in, residual + Jacobian blocks at eval_x, no time step
   const double *eval_x; double *eval_f, *eval_ja, *eval_jb, *eval_jc;
 };

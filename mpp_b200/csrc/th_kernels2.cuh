@@ -99,21 +99,32 @@ th_step2_kernel(const THArgs A)
   const int nlev = A.nlev;
   const bool col_ok = col < A.ncol;
   const bool valid = col_ok && j < nlev;
-  const bool has_conn = valid && j < nlev - 1;
-  const long long cell = (long long)col * nlev + j;
+  // Boundary connection on the padding lane (A.bc_on_pad_lane: one Dirichlet temperature at the top, nlev <= 15, top cell first).  A
+  // Dirichlet face is an internal connection with dist_up = 0 whose up side is the boundary aux var (ThermalEnthalpyFlux,
+  // ThermalEnthalpyMod.F90:27-165; upweight 0, RichardsMod.F90:262-264).  Lane G-1 has no cell: it carries that aux var as its "cell"
+  // (state = the condition's T and poked P, static data = the top cell's) and owns the connection boundary -> cell 0, so the boundary
+  // flux and its four derivative blocks are computed by the same instructions, at the same time, as every interior connection --
+  // instead of a loop that one lane in sixteen runs alone out of a local-memory array.
+  const bool pad = (A.bc_on_pad_lane != 0) && col_ok && (j == G - 1);
+  const bool has_conn = (valid && j < nlev - 1) || pad;
+  const long long cell = (long long)col * nlev + (pad ? 0 : j);      // the padding lane reads the top cell's static data
+  const int src_dn = pad ? lane - (G - 1) : ((j == G - 1) ? lane : lane + 1);                      // lane of the connection's dn cell
+  const int src_up = (A.bc_on_pad_lane != 0 && j == 0) ? lane + (G - 1) : ((j == 0) ? lane : lane - 1);   // lane that owns the connection above
+  const bool has_up = (j > 0) || (A.bc_on_pad_lane != 0);
   const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
   const SnesOpts so = A.so;
 
   // ---- static per-cell data ------------------------------------------------------------------------------------------
   SatParams sp; sp.sat_res = 0.0; sp.alpha = 1.0; sp.m = 0.5; sp.n = 2.0; sp.pu = sp.ps = sp.b2 = sp.b3 = 0.0;
   double por = 0.5, perm = 1.0, dz = 1.0, area = 1.0, tkdry = 1.0, csol = 1.0, P = PRESSURE_REF, T = 283.15, srcm = 0.0, srce = 0.0, perm_e = PERM_E_DEFAULT;
-  if (valid) {
+  if (valid || pad) {
     por = A.por[cell]; perm = A.perm[cell]; dz = A.dz[cell]; area = A.area[col]; tkdry = A.tkdry[cell]; csol = A.csol[cell];
     if (A.perm_e) perm_e = A.perm_e[cell];
     sp.sat_res = A.sat_res[cell]; sp.alpha = A.alpha[cell]; sp.m = A.lam[cell]; sp.n = A.vgn ? A.vgn[cell] : 0.0;
     if (A.pu) { sp.pu = A.pu[cell]; sp.ps = A.ps[cell]; sp.b2 = A.b2[cell]; sp.b3 = A.b3[cell]; }
-    P = A.x_in[2 * cell]; T = A.x_in[2 * cell + 1];
-    for (int k = 0; k < A.nss; ++k) {
+    if (pad) { T = A.bc[0].value[col]; P = A.bc[0].bc_pressure ? A.bc[0].bc_pressure[col] : 0.0; }     // energy-equation boundary aux var
+    else     { P = A.x_in[2 * cell]; T = A.x_in[2 * cell + 1]; }
+    for (int k = 0; k < (pad ? 0 : A.nss); ++k) {
       const THCondDev &c = A.ss[k];
       double val = 0.0; bool mine = false;
       if (c.region == REGION_CELLS) { val = c.value[cell]; mine = true; }
@@ -123,17 +134,25 @@ th_step2_kernel(const THArgs A)
   }
   const double vol = area * dz;
   // connection j -> j+1 (owned by lane j)
-  const double perm_d = __shfl_down_sync(FULL, perm, 1, G), dz_d = __shfl_down_sync(FULL, dz, 1, G);
-  const double dist_up = 0.5 * dz, dist_dn = 0.5 * dz_d, upw = dist_up / (dist_up + dist_dn);
-  const double gfac = FMWH2O * ((dist_up + dist_dn) * (A.uz * (-GRAVITY_CONSTANT)));
-  const double Dqm = (perm * perm_d) / (dist_up * perm_d + dist_dn * perm);
-  const double perm_e_d = __shfl_down_sync(FULL, perm_e, 1, G);
-  const double Dqe = (perm_e * perm_e_d) / (dist_up * perm_e_d + dist_dn * perm_e);
+  const double perm_d = __shfl_sync(FULL, perm, src_dn), dz_d = __shfl_sync(FULL, dz, src_dn);
+  const double perm_e_d = __shfl_sync(FULL, perm_e, src_dn);
+  double dist_up = 0.5 * dz, dist_dn = 0.5 * dz_d, upw = dist_up / (dist_up + dist_dn);
+  double gfac = FMWH2O * ((dist_up + dist_dn) * (A.uz * (-GRAVITY_CONSTANT)));
+  double Dqm = (perm * perm_d) / (dist_up * perm_d + dist_dn * perm);
+  double Dqe = (perm_e * perm_e_d) / (dist_up * perm_e_d + dist_dn * perm_e);
+  if (pad) {
+    // boundary connection (MeshType.F90:723-806): dist_up = 0, dist_dn = dz/2 of the top cell, unit vector (0,0,-1); no mass-equation
+    // boundary exists in this configuration, so the Richards flux of the mass equation through this face is switched off
+    dist_up = 0.0; dist_dn = 0.5 * dz; upw = 0.0;
+    gfac = FMWH2O * ((0.0 + 0.5 * dz) * (((A.uz == 0.0) ? 0.0 : -1.0) * (-GRAVITY_CONSTANT)));
+    Dqm = 0.0; Dqe = perm_e / (0.0 + 0.5 * dz);
+    por = 0.0; csol = 0.0;
+  }
 
   // boundary conditions owned by this lane (at most one per region and equation)
   struct BCL { int ieqn; double P, T, bgf, Dq; FluxIn fin; double hl, tc; };
   BCL bcs[4]; int nmybc = 0;
-  for (int k = 0; k < A.nbc; ++k) {
+  for (int k = 0; k < (A.bc_on_pad_lane ? 0 : A.nbc); ++k) {
     const bool top = (A.bc[k].region == REGION_TOP);
     if (!valid || j != (top ? jtop : jbot) || nmybc >= 4) continue;
     BCL &b = bcs[nmybc++];
@@ -203,8 +222,8 @@ th_step2_kernel(const THArgs A)
       __syncwarp();                              // aux vars were stored under per-column control flow
       THCell ax, ad;                             // this cell and the dn side of connection j (the next lane's cell)
       ax_load(s_ax, threadIdx.x, ax);
-      ax_load(s_ax, has_conn ? threadIdx.x + 1 : threadIdx.x, ad);
-      const double Pd = __shfl_down_sync(FULL, P, 1, G), Td = __shfl_down_sync(FULL, T, 1, G);
+      ax_load(s_ax, has_conn ? threadIdx.x + (src_dn - lane) : threadIdx.x, ad);
+      const double Pd = __shfl_sync(FULL, P, src_dn), Td = __shfl_sync(FULL, T, src_dn);
       const double krd = ad.kr, dkrd = ad.dkr, denmd = ad.den_m, dPmd = ad.ddenP_m, dTmd = ad.ddenT_m;
       const double dened = ad.den_e, dPed = ad.ddenP_e, dTed = ad.ddenT_e, hld = ad.hl, dhlTd = ad.dhlT, dhlPd = ad.dhlP;
       const double tcd = ad.tc, dtcPd = ad.dtcP;
@@ -229,15 +248,15 @@ th_step2_kernel(const THArgs A)
       }
       // this cell as "up" of connection j, as "dn" of connection j-1 (values handed down by lane j-1)
       M2 Ja{0.0, 0.0, 0.0, 0.0}, Jb{1.0, 0.0, 0.0, 1.0}, Jc{0.0, 0.0, 0.0, 0.0};
-      const double p_mJup = __shfl_up_sync(FULL, mJup, 1, G), p_mJdn = __shfl_up_sync(FULL, mJdn, 1, G);
-      const double p_dTu = __shfl_up_sync(FULL, dTu, 1, G), p_dTd = __shfl_up_sync(FULL, dTd, 1, G);
-      const double p_JTTu = __shfl_up_sync(FULL, JTT_u, 1, G), p_JTTd = __shfl_up_sync(FULL, JTT_d, 1, G);
-      const double p_JTPu = __shfl_up_sync(FULL, JTP_u, 1, G), p_JTPd = __shfl_up_sync(FULL, JTP_d, 1, G);
+      const double p_mJup = __shfl_sync(FULL, mJup, src_up), p_mJdn = __shfl_sync(FULL, mJdn, src_up);
+      const double p_dTu = __shfl_sync(FULL, dTu, src_up), p_dTd = __shfl_sync(FULL, dTd, src_up);
+      const double p_JTTu = __shfl_sync(FULL, JTT_u, src_up), p_JTTd = __shfl_sync(FULL, JTT_d, src_up);
+      const double p_JTPu = __shfl_sync(FULL, JTP_u, src_up), p_JTPd = __shfl_sync(FULL, JTP_d, src_up);
       if (valid) {
         double b00 = mJup, b01 = -dTu, b10 = -JTP_u, b11 = -JTT_u;                 // zero where there is no connection j -> j+1
         Jc = M2{mJdn, -dTd, -JTP_d, -JTT_d};
-        if (j > 0) {
-          Ja = M2{-p_mJup, p_dTu, p_JTPu, p_JTTu};
+        if (has_up) {
+          if (j > 0) Ja = M2{-p_mJup, p_dTu, p_JTPu, p_JTTu};      // (j = 0: the up side is the boundary aux var, not an unknown)
           b00 += -p_mJdn; b01 += p_dTd; b11 += p_JTTd; b10 += p_JTPd;
         }
         for (int k = 0; k < nmybc; ++k) {
@@ -316,9 +335,9 @@ th_step2_kernel(const THArgs A)
     th_cell_compute<SF, DT, IEE>(A, sp, tkdry, Wm, We, c);
     double Gm, Ge;
     {
-      const double Wmd = __shfl_down_sync(FULL, Wm, 1, G), Wed = __shfl_down_sync(FULL, We, 1, G);
-      const double krd = __shfl_down_sync(FULL, c.kr, 1, G), denmd = __shfl_down_sync(FULL, c.den_m, 1, G), dened = __shfl_down_sync(FULL, c.den_e, 1, G);
-      const double hld = __shfl_down_sync(FULL, c.hl, 1, G), tcd = __shfl_down_sync(FULL, c.tc, 1, G);
+      const double Wmd = __shfl_sync(FULL, Wm, src_dn), Wed = __shfl_sync(FULL, We, src_dn);
+      const double krd = __shfl_sync(FULL, c.kr, src_dn), denmd = __shfl_sync(FULL, c.den_m, src_dn), dened = __shfl_sync(FULL, c.den_e, src_dn);
+      const double hld = __shfl_sync(FULL, c.hl, src_dn), tcd = __shfl_sync(FULL, c.tc, src_dn);
       double fm = 0.0, fe = 0.0;
       if (has_conn) {
         const FluxIn um = {Wm, c.kr, 0, c.den_m, 0, 0}, dm = {Wmd, krd, 0, denmd, 0, 0};
@@ -330,12 +349,12 @@ th_step2_kernel(const THArgs A)
         const double h = (mfl <= 0.0) ? c.hl : hld;
         fe = mfl * h + (-kod * (We - Wed) * area);
       }
-      const double fm_p = __shfl_up_sync(FULL, fm, 1, G), fe_p = __shfl_up_sync(FULL, fe, 1, G);
+      const double fm_p = __shfl_sync(FULL, fm, src_up), fe_p = __shfl_sync(FULL, fe, src_up);
       const double am = por * c.den_m * c.sat * vol * dtInv;
       const double ae = (por * c.den_e * c.sat * c.ul + (1.0 - por) * 2700.0 * csol * (We - 273.15)) * vol * dtInv;
       if (phase == PH_INIT) { accm = am; acce = ae; }
       Gm = am - accm; Ge = ae - acce;
-      if (j > 0) { Gm = Gm + fm_p; Ge = Ge + fe_p; }
+      if (has_up) { Gm = Gm + fm_p; Ge = Ge + fe_p; }
       if (has_conn) { Gm = Gm - fm; Ge = Ge - fe; }
       for (int k = 0; k < nmybc; ++k) {
         const BCL &b = bcs[k];
