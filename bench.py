@@ -296,8 +296,12 @@ def other_workloads(device, stream):
         "host_bytes_per_solve": int(sum(v.nbytes for v in e.values())),
         "api": "mppgpu_thermal_elm_solve: elm_thermal_pack_kernel + thermal_snow_step3_kernel + elm_thermal_unpack_kernel between the copies"}
     p.close()
-    # MPPVSFMALM_Solve with ELM's raw column arrays: packing, StepDT, per-column retry loop, unpacking on the device
+    # MPPVSFMALM_Solve with ELM's raw column arrays: packing, StepDT, per-column retry loop, unpacking on the device.
+    # With ELM's own default curve (smooth_brooks_corey_bz3, mpp_varctl.F90:17): the driver drains water from the saturated layers below
+    # the water table, which pulls cells through pc = 0 every step -- with van Genuchten that is exactly where the reference algorithm
+    # halves dt a dozen times (one column of 1 Mi then needs 10^4 - 10^6 residual evaluations per solve, oracle and GPU alike)
     d = shard_inputs(0, ncol)
+    d["satfunc"] = "smooth_brooks_corey_bz3"
     p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d, device=device)
     p.set_stream(stream)
     st0 = PB.elm_vsfm_raw_state(p, d, patches=True)
@@ -319,7 +323,8 @@ def other_workloads(device, stream):
                                      "ms_per_solve_host_arrays_page_locked": [round(w * 1e3, 2) for w in wall], "ms_per_solve_device": msd,
                                      "stepdt_calls": att, "columns_failed": nf,
                                      "kernels": "elm_pack_kernel<16> + vsfm_step2_kernel + elm_decide_kernel<16> (+ RETRY specialisation on the columns that need it)",
-                                     "note": "no step budget: reference behaviour; host arrays page-locked in place with mppgpu_host_register"}
+                                     "satfunc": "smooth_brooks_corey_bz3",
+                                     "note": "ELM's default curve; no step budget: reference behaviour; host arrays page-locked in place with mppgpu_host_register"}
     p.close()
     return out
 

@@ -309,7 +309,11 @@ def elm_vsfm_raw_state(p, d, seed=SEED, patches=True, nlevsoi=10, drain_frac=0.7
     st["zwt"] = 0.5 * (zi[0] + zi[1]) + (K.PRESSURE_REF - P0) / (997.16 * K.GRAVITY_CONSTANT)
     st["mflx_snowlyr_col"] = np.where(rng.uniform(size=ncol) < 0.1, rng.uniform(0.0, 1e-5, ncol), 0.0)
     st["mflx_neg_snow_col"] = np.where(rng.uniform(size=ncol) < 0.05, -rng.uniform(0.0, 1e-6, ncol), 0.0)
-    st["mflx_drain_perched"] = np.where(rng.uniform(size=(ncol, nlev)) < 0.05, -rng.uniform(0.0, 1e-6, (ncol, nlev)), 0.0)
+    # perched drainage only where perched water can be: cells at or near saturation (ELM diagnoses a perched table from the saturated
+    # layers above a frozen one); a sink drawn at random would pull water out of dry or frozen cells, and the reference algorithm then
+    # halves dt a dozen times and grinds through 10^4 - 10^6 residual evaluations on that one column
+    wet = np.asarray(d["press_ic"]).reshape(ncol, nlev) > K.PRESSURE_REF - 5.0e3
+    st["mflx_drain_perched"] = np.where((rng.uniform(size=(ncol, nlev)) < 0.05) & wet, -rng.uniform(0.0, 1e-6, (ncol, nlev)), 0.0)
     return st
 
 

@@ -38,7 +38,7 @@ elif mode == "th":
           "alg GB/s (1824 B/col) %.0f" % (1824 * ncol / (m * 1e-3) / 1e9), "its mean %.2f nf mean %.2f nf max %d conv %s cuts %d" % (
               st["newton_its"].mean(), st["nfuncs"].mean(), st["nfuncs"].max(), conv, int((st["dt_cuts"] > 0).sum())))
 elif mode == "elm":
-    d = bench.shard_inputs(0, ncol)
+    d = bench.shard_inputs(0, ncol); d["satfunc"] = os.environ.get("ELM_SATFUNC", "smooth_brooks_corey_bz3")
     p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
     st = PB.elm_vsfm_raw_state(p, d, patches=True)
     p.elm_set_geometry(st["zi"], st["dz"], st["nlevsoi"], ids)
