@@ -876,24 +876,11 @@ extern "C" int mppgpu_step_dt(mppgpu_handle h, double dt, int nstep, int *conver
 }
 
 // ---- ELM coupling step, pipelined over column chunks -------------------------------------------------------------------
-extern "C" int mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, int nin, const mppgpu_xfer *in, int nout, const mppgpu_xfer *out,
-                                        int nchunks, int *converged, int *converged_reason)
+struct CoupledField { double *dev; size_t per_col; double *host; };
+static int vsfm_coupled_pipeline(mppgpu_soe *h, double dt, const std::vector<CoupledField> &fin, const std::vector<CoupledField> &fout, int nchunks,
+                                 int *converged, int *converged_reason)
 {
-  CHECK_H(h);
-  (void)nstep;
-  if (h->soe_itype != MPPGPU_SOE_RE_ODE) return fail("mppgpu_vsfm_coupled_step: handle is not a VSFM SoE");
-  if ((nin > 0 && !in) || (nout > 0 && !out) || nin < 0 || nout < 0) return fail("mppgpu_vsfm_coupled_step: bad transfer lists");
-  struct Field { double *dev; size_t per_col; double *host; };
-  std::vector<Field> fin(nin), fout(nout);
-  for (int i = 0; i < nin + nout; ++i) {
-    const bool is_in = i < nin;
-    const mppgpu_xfer &x = is_in ? in[i] : out[i - nin];
-    if (!x.host) return fail("mppgpu_vsfm_coupled_step: null host array");
-    double *p = nullptr; size_t cap = 0;
-    if (vsfm_field(h, x.auxvar_type, x.var_type, x.cond_id, is_in, &p, &cap)) return 1;
-    Field f{p, cap / (size_t)h->ncol, x.host};
-    if (is_in) fin[i] = f; else fout[i - nin] = f;
-  }
+  typedef CoupledField Field;
   // VSFMSPreStepDT (SystemOfEquationsVSFMType.F90:892-923)
   h->x_current = h->x_committed;
   for (auto *c : h->bcs) CK(cudaMemsetAsync(c->mass_exc.p, 0, c->n * 8, h->stream));
@@ -944,6 +931,40 @@ extern "C" int mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, i
   CK(cudaStreamWaitEvent(h->stream, h->ev_out_done, 0));          // later work on the handle's stream sees the host arrays complete
   CK(cudaStreamSynchronize(h->copy_out));                         // the caller may read its arrays as soon as this returns
   return mppgpu_step_result(h, converged, converged_reason);
+}
+
+extern "C" int mppgpu_vsfm_coupled_step(mppgpu_handle h, double dt, int nstep, int nin, const mppgpu_xfer *in, int nout, const mppgpu_xfer *out,
+                                        int nchunks, int *converged, int *converged_reason)
+{
+  CHECK_H(h);
+  (void)nstep;
+  if (h->soe_itype != MPPGPU_SOE_RE_ODE) return fail("mppgpu_vsfm_coupled_step: handle is not a VSFM SoE");
+  if ((nin > 0 && !in) || (nout > 0 && !out) || nin < 0 || nout < 0) return fail("mppgpu_vsfm_coupled_step: bad transfer lists");
+  typedef CoupledField Field;
+  std::vector<Field> fin(nin), fout(nout);
+  for (int i = 0; i < nin + nout; ++i) {
+    const bool is_in = i < nin;
+    const mppgpu_xfer &x = is_in ? in[i] : out[i - nin];
+    if (!x.host) return fail("mppgpu_vsfm_coupled_step: null host array");
+    double *p = nullptr; size_t cap = 0;
+    if (vsfm_field(h, x.auxvar_type, x.var_type, x.cond_id, is_in, &p, &cap)) return 1;
+    Field f{p, cap / (size_t)h->ncol, x.host};
+    if (is_in) fin[i] = f; else fout[i - nin] = f;
+  }
+  // On any failure inside the pipeline, copies to and from the CALLER's host arrays may still be queued on the copy streams: drain all three
+  // streams before returning (the caller may free or reuse its buffers), and put the handle back where it was (soln, launch order).
+  double *const x_before = h->x_current;
+  if (vsfm_coupled_pipeline(h, dt, fin, fout, nchunks, converged, converged_reason)) {
+    const std::string msg = g_err;
+    if (h->copy_in) cudaStreamSynchronize(h->copy_in);
+    if (h->copy_out) cudaStreamSynchronize(h->copy_out);
+    cudaStreamSynchronize(h->stream);
+    (void)cudaGetLastError();
+    h->x_current = x_before; h->order_valid = false; h->result_pending = false;
+    g_err = msg;
+    return 1;
+  }
+  return 0;
 }
 
 // ---- diagnostics --------------------------------------------------------------------------------------------------

@@ -291,6 +291,13 @@ template <class T> MPP_HD T mpp_log(T x) { return mpp_log_poly(x); }
 template <class T> MPP_HD T mpp_exp(T x) { return mpp_exp_poly(x); }
 #endif
 
+// pow() kept out of line for the rare calls on hot paths (the reference's `dhsdT**area` with area != 1): inlined, the CUDA library's pow
+// hoists ~50 instructions of argument classification above the guarding branch, which every lane then executes on every call
+// (profiles/r2_thermal_v1.md: 10 % of the soil thermal kernel's instructions)
+#ifdef __CUDACC__
+static __device__ __noinline__ double mpp_pow_rare(double x, double y) { return pow(x, y); }
+#endif
+
 // MultiPhysicsProbConstants.F90:199-202, mpp_varcon.F90:12-28
 constexpr double PRESSURE_REF     = 101325.0;
 constexpr double GRAVITY_CONSTANT = 9.80665;

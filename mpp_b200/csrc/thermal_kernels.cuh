@@ -188,7 +188,7 @@ thermal_step_kernel(const ThermalArgs A)
       if (A.bc_type[k] == 507) {                    // COND_HEAT_FLUX: value = H - dH/dT * T_cell (GoveqnThermalKSP...:344-348)
         const double H = bcH[k], dH = bcdH[k], fr = bcfr[k];
         rhs = rhs + (H - dH * T) * fr * area;
-        bb += -fr * ((area == 1.0) ? dH : pow(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
+        bb += -fr * ((area == 1.0) ? dH : mpp_pow_rare(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
       } else if (A.bc_active[k][col] != 0.0) {      // COND_DIRICHLET
         double tkb, hcb;
         const double Tb = A.bc_value[k][col];
@@ -288,7 +288,7 @@ __device__ __forceinline__ void thermal_cell_bc(const ThermalArgs &A, const Ther
     if (A.bc_type[k] == 507) {                    // COND_HEAT_FLUX: value = H - dH/dT * T_cell (GoveqnThermalKSP...:344-348)
       const double H = V.bc_value[k][col], dH = V.bc_dhsdT[k][col], fr = V.bc_frac[k][col];
       c.rhs = c.rhs + (H - dH * c.T) * fr * area;
-      c.bb += -fr * ((area == 1.0) ? dH : pow(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
+      c.bb += -fr * ((area == 1.0) ? dH : mpp_pow_rare(dH, area));   // `-frac*dhsdT**area*factor` (:1215); x**1 == x exactly
     } else if (V.bc_active[k][col] != 0.0) {      // COND_DIRICHLET
       double tkb, hcb;
       const double Tb = V.bc_value[k][col];
@@ -517,7 +517,7 @@ __global__ void thermal_step_generic_kernel(const ThermalArgs A, double *work /*
     if (A.bc_type[k] == 507) {
       const double H = A.bc_value[k][col], dH = A.bc_dhsdT[k][col], fr = A.bc_frac[k][col];
       d[j] = d[j] + (H - dH * T) * fr * area;
-      b[j] += -fr * ((area == 1.0) ? dH : pow(dH, area));
+      b[j] += -fr * ((area == 1.0) ? dH : mpp_pow_rare(dH, area));
     } else if (A.bc_active[k][col] != 0.0) {
       double tkb, hcb;
       const double Tb = A.bc_value[k][col];

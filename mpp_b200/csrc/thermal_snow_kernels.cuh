@@ -219,7 +219,7 @@ thermal_snow_step_kernel(const ThermalSnowArgs A)
     double t_rhs = 0.0, t_bb = 0.0;
     if (a.act) {                                      // COND_HEAT_FLUX at the top of the soil (soil GE :886-903, :1196-1215)
       t_rhs = (H2 - dH2 * a.T) * frs * area;
-      t_bb = -frs * ((area == 1.0) ? dH2 : pow(dH2, area));
+      t_bb = -frs * ((area == 1.0) ? dH2 : mpp_pow_rare(dH2, area));
     }
     double a1s = 0.0;
     if (wact) {
@@ -373,7 +373,7 @@ thermal_snow_step3_kernel(const ThermalSnowArgs A)
     double t_rhs = 0.0, t_bb = 0.0;
     if (a.act) {
       t_rhs = (H2 - dH2 * a.T) * frs * area;
-      t_bb = -frs * ((area == 1.0) ? dH2 : pow(dH2, area));
+      t_bb = -frs * ((area == 1.0) ? dH2 : mpp_pow_rare(dH2, area));
     }
     double a1s = 0.0;
     if (wact) {
