@@ -124,6 +124,13 @@ typedef struct {
   double *tvector;                                         /* in/out (ncol, -nlevsno:nlev): only the entries the driver assigns change */
 } mppgpu_elm_thermal_columns;
 int  mppgpu_thermal_elm_solve(mppgpu_handle h, double dtime, int nstep, const mppgpu_elm_thermal_columns *cols, double capr);
+/* The two ELM solve entry points (mppgpu_thermal_elm_solve above, mppgpu_vsfm_elm_solve below) are software-pipelined over column chunks
+ * on three CUDA streams -- chunk k+1's host->device copies, chunk k's kernels and chunk k-1's device->host copies overlap -- with results
+ * bit-identical to an unpipelined solve.  nchunks: number of chunks (0 = default: 8, none smaller than 32768 columns; 1 = no pipelining).
+ * static_soil_geometry (thermal SoE only): 1 = the soil rows (j >= 1) of z / dz / zi are ELM's fixed vertical grid (initVertical); they are
+ * uploaded by the first solve after this call and only the snow rows (and zi(c,0)) on later solves; 0 (default) = every row, every solve.
+ * Host arrays should be page-locked (mppgpu_host_register) for the copies to overlap. */
+int  mppgpu_elm_set_pipeline(mppgpu_handle h, int nchunks, int static_soil_geometry);
 int  mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
                          const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,
                          int satfunc_type, int density_type, int int_energy_enthalpy_type);

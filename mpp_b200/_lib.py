@@ -52,6 +52,7 @@ _SIGS = {
     "mppgpu_thermal_set_cnfac": (C.c_int, [C.c_void_p, C.c_double]),
     "mppgpu_thermal_add_snow_ssw": (C.c_int, [C.c_void_p, C.c_int, c_dp]),
     "mppgpu_thermal_elm_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(ElmThermalColumns), C.c_double]),
+    "mppgpu_elm_set_pipeline": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "mppgpu_vsfm_elm_set_geometry": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, c_ip]),
     "mppgpu_vsfm_elm_set_geometry_f": (C.c_int, [C.c_void_p, c_dp, c_dp, C.c_int, C.c_double, c_ip]),
     "mppgpu_vsfm_elm_solve": (C.c_int, [C.c_void_p, C.c_double, C.c_int, C.POINTER(ElmColumns), c_ip, c_ip]),

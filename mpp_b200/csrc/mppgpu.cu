@@ -122,6 +122,8 @@ static int thermal_post_step_dt(ThermalState *t);
 static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt);
 static int thermal_add_snow_ssw(mppgpu_soe *h, ThermalState *t, int nlevsno, const double *soil_top_dist_dn);
 static void elm_destroy(struct ElmState *e);
+static int elm_need(mppgpu_soe *h);
+static void elm_set_chunks(struct ElmState *e, int nchunks);
 static int thermal_elm_solve(mppgpu_soe *h, ThermalState *t, double dtime, const mppgpu_elm_thermal_columns *cols, double capr);
 static int thermal_set_soils(mppgpu_soe *h, ThermalState *t, const double *watsat, const double *csol, const double *tkmg,
                              const double *tkdry, const int *lun_type, int nlevsoi, int istsoil);
@@ -1082,6 +1084,23 @@ extern "C" int mppgpu_thermal_elm_solve(mppgpu_handle h, double dtime, int nstep
   if (!h->thermal) return fail("mppgpu_thermal_elm_solve: handle is not a thermal SoE");
   if (!(dtime > 0.0)) return fail("mppgpu_thermal_elm_solve: dtime must be positive");
   return thermal_elm_solve(h, h->thermal, dtime, cols, capr);
+}
+extern "C" int mppgpu_elm_set_pipeline(mppgpu_handle h, int nchunks, int static_soil_geometry)
+{
+  CHECK_H(h);
+  if (nchunks < 0 || nchunks > 1024) return fail("mppgpu_elm_set_pipeline: nchunks must be within 0..1024 (0: default)");
+  if (static_soil_geometry != 0 && static_soil_geometry != 1) return fail("mppgpu_elm_set_pipeline: static_soil_geometry must be 0 or 1");
+  if (h->soe_itype == MPPGPU_SOE_RE_ODE) {
+    if (static_soil_geometry) return fail("mppgpu_elm_set_pipeline: static_soil_geometry applies to the thermal SoE (the VSFM geometry is set once by mppgpu_vsfm_elm_set_geometry)");
+    if (elm_need(h)) return 1;
+    elm_set_chunks(h->elm, nchunks);
+    return 0;
+  }
+  if (!h->thermal) return fail("mppgpu_elm_set_pipeline: handle has no ELM solve entry point");
+  h->thermal->elm_chunks = nchunks;
+  h->thermal->elm_static_soil = (static_soil_geometry != 0);
+  h->thermal->elm_soil_loaded = false;
+  return 0;
 }
 extern "C" int mppgpu_th_set_soils(mppgpu_handle h, const double *watsat, const double *hksat, const double *bsw,
                                    const double *sucsat, const double *residual_sat, const double *csol, const double *tkdry,

@@ -200,7 +200,8 @@ static int thermal_set_idata(mppgpu_soe *h, ThermalState *t, int auxvar_type, in
 static int thermal_pre_step_dt(ThermalState *t) { t->T_cur = t->T_clm; return 0; }     // ThermalSOEPreStepDT :393-408
 static int thermal_post_step_dt(ThermalState *) { return 0; }
 
-static int thermal_snow_step(mppgpu_soe *h, ThermalState *t, double dt)
+// queue the coupled snow / standing-water / soil step kernel on columns [c0, c0 + n) of the batch (mailbox pointers are whole-batch)
+static int thermal_snow_launch(mppgpu_soe *h, ThermalState *t, double dt, long long c0, int n, double *T_out)
 {
   ThermalSnowArgs A;
   memset(&A, 0, sizeof(A));
@@ -219,17 +220,25 @@ static int thermal_snow_step(mppgpu_soe *h, ThermalState *t, double dt)
   for (int k = 0; k < 3; ++k) { A.hs[k] = t->hs[k]; A.dhsdT[k] = t->dhs[k]; }
   A.frac_soil = t->frac_soil; A.sabg_snow = t->sabg_snow; A.sabg_soil = t->sabg_soil; A.soil_top_dist_dn = t->soil_top_dist_dn;
   A.snow_top_id = t->snow_top_id;
-  A.T_out = (t->T_cur == t->T_clm) ? t->T_work : t->T_cur;
-  CK(cudaEventRecord(h->ev0, h->stream));
+  A.T_out = T_out;
+  A.col0 = (int)c0; A.col_end = (int)c0 + n;
   // ELM's 5 + 15 layout (and anything else that fits 8 lanes of three rows): four columns per warp; otherwise 16 lanes of two rows
   if ((t->nsno + 2) / 3 + (h->nlev + 2) / 3 <= 8 && !t->force_two_rows)
-    thermal_snow_step3_kernel<8><<<nblk((long long)h->ncol * 8, TH_TILE), TH_TILE, 0, h->stream>>>(A);
+    thermal_snow_step3_kernel<8><<<nblk((long long)n * 8, TH_TILE), TH_TILE, 0, h->stream>>>(A);
   else
-    thermal_snow_step_kernel<16><<<nblk((long long)h->ncol * 16, TH_TILE), TH_TILE, 0, h->stream>>>(A);
+    thermal_snow_step_kernel<16><<<nblk((long long)n * 16, TH_TILE), TH_TILE, 0, h->stream>>>(A);
   CK(cudaGetLastError());
-  CK(cudaEventRecord(h->ev1, h->stream));
   h->launches += 1;
-  t->T_cur = A.T_out;
+  return 0;
+}
+
+static int thermal_snow_step(mppgpu_soe *h, ThermalState *t, double dt)
+{
+  double *T_out = (t->T_cur == t->T_clm) ? t->T_work : t->T_cur;
+  CK(cudaEventRecord(h->ev0, h->stream));
+  if (thermal_snow_launch(h, t, dt, 0, h->ncol, T_out)) return 1;
+  CK(cudaEventRecord(h->ev1, h->stream));
+  t->T_cur = T_out;
   return 0;
 }
 
@@ -318,7 +327,10 @@ static int thermal_step(mppgpu_soe *h, ThermalState *t, double dt)
 }
 
 
-// MPPThermalTBasedALM_Solve (src/driver/alm/MPPThermalTBasedALM_Driver.F90:150-452): ELM's raw column arrays in, tvector out
+// MPPThermalTBasedALM_Solve (src/driver/alm/MPPThermalTBasedALM_Driver.F90:150-452): ELM's raw column arrays in, tvector out.
+// Software-pipelined over column chunks: chunk k's rows go up on `copy_in` (one strided copy per array: the arrays are layer-major), are
+// packed, stepped and unpacked on the handle's stream, and its tvector rows come down on `copy_out` while chunk k+1 computes.
+static int thermal_elm_pipeline(mppgpu_soe *h, ThermalState *t, double dtime, const mppgpu_elm_thermal_columns *cols, double capr);
 static int thermal_elm_solve(mppgpu_soe *h, ThermalState *t, double dtime, const mppgpu_elm_thermal_columns *cols, double capr)
 {
   if (!t->snow_mode) return fail("mppgpu_thermal_elm_solve: call mppgpu_thermal_add_snow_ssw first (the ELM configuration)");
@@ -328,46 +340,108 @@ static int thermal_elm_solve(mppgpu_soe *h, ThermalState *t, double dtime, const
   const void *req[] = {cols->snl, cols->z, cols->dz, cols->zi, cols->t_soisno, cols->h2osoi_liq, cols->h2osoi_ice, cols->frac_sno_eff, cols->h2osno,
                        cols->h2osfc, cols->frac_h2osfc, cols->t_h2osfc, cols->sabg_lyr, cols->dhsdT, cols->hs_soil, cols->hs_top_snow, cols->hs_h2osfc, cols->tvector};
   for (const void *q : req) if (!q) return fail("mppgpu_thermal_elm_solve: null column array");
+  double *const T_before = t->T_cur;
+  if (thermal_elm_pipeline(h, t, dtime, cols, capr)) {
+    // copies to and from the caller's arrays may still be queued: drain the three streams before handing the arrays back
+    const std::string msg = g_err;
+    if (h->copy_in) cudaStreamSynchronize(h->copy_in);
+    if (h->copy_out) cudaStreamSynchronize(h->copy_out);
+    cudaStreamSynchronize(h->stream);
+    (void)cudaGetLastError();
+    t->T_cur = T_before; t->elm_soil_loaded = false;
+    g_err = msg;
+    return 1;
+  }
+  return 0;
+}
+
+static int thermal_elm_pipeline(mppgpu_soe *h, ThermalState *t, double dtime, const mppgpu_elm_thermal_columns *cols, double capr)
+{
   const size_t ncol = h->ncol, nsno = t->nsno, nlev = h->nlev, nl = nsno + nlev, nrow = nl + 1;
   cudaStream_t s = h->stream;
-  // staging layout: z, dz, t, liq, ice (ncol*nl each) | zi (ncol*(nl+1)) | sabg (ncol*(nsno+1)) | 9 per-column arrays | tvector (ncol*nrow)
+  if (!h->copy_in)  CK(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+  if (!h->copy_out) CK(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+  if (!h->ev_out_done) { CK(cudaEventCreateWithFlags(&h->ev_out_done, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming)); }
+  int nchunks = t->elm_chunks > 0 ? t->elm_chunks : 8;
+  const long long align = 1024;
+  long long per = ((long long)ncol + nchunks - 1) / nchunks;
+  per = ((per + align - 1) / align) * align;
+  if (t->elm_chunks <= 0 && per < 32768) per = 32768;
+  nchunks = (int)(((long long)ncol + per - 1) / per);
+  while ((int)h->ev_in.size() < nchunks) {
+    cudaEvent_t a, b; CK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    h->ev_in.push_back(a); h->ev_comp.push_back(b);
+  }
+  // staging tables in the caller's own layer-major layout: z, dz, t, liq, ice (nl rows of ncol) | zi (nl+1) | sabg (nsno+1) | 9 per-column rows | tvector (nrow)
   const size_t total = 5 * ncol * nl + ncol * (nl + 1) + ncol * (nsno + 1) + 9 * ncol + ncol * nrow;
-  if (!t->elm_stage) { CK(mpp_dmalloc((void **)&t->elm_stage, total * 8)); CK(mpp_dmalloc((void **)&t->elm_snl, ncol * sizeof(int))); }
+  if (!t->elm_stage) { CK(mpp_dmalloc((void **)&t->elm_stage, total * 8)); CK(mpp_dmalloc((void **)&t->elm_snl, ncol * sizeof(int))); t->elm_soil_loaded = false; }
+  // the soil rows of z / dz / zi are ELM's fixed vertical grid: with mppgpu_elm_set_pipeline(h, ., 1) they go up with the first solve only
+  const bool snow_rows_only = t->elm_static_soil && t->elm_soil_loaded;
+  struct Table { double *dev; const double *host; size_t rows; };
   double *p = t->elm_stage;
-  auto up = [&](const double *src, size_t cnt) -> double * {
-    double *dst = p; p += cnt;
-    cudaMemcpyAsync(dst, src, cnt * 8, cudaMemcpyHostToDevice, s);
-    return dst;
-  };
+  auto table = [&](const double *src, size_t rows_total, size_t rows_up) -> Table { Table x{p, src, rows_up}; p += rows_total * ncol; return x; };
+  Table up[16];
+  int nup = 0;
   ElmThermalArgs E;
   memset(&E, 0, sizeof(E));
   E.ncol = h->ncol; E.nlev = h->nlev; E.nsno = t->nsno; E.capr = capr;
   E.active_col = h->has_active ? h->active.p : nullptr;
-  E.z = up(cols->z, ncol * nl); E.dz = up(cols->dz, ncol * nl); E.t_soisno = up(cols->t_soisno, ncol * nl);
-  E.h2osoi_liq = up(cols->h2osoi_liq, ncol * nl); E.h2osoi_ice = up(cols->h2osoi_ice, ncol * nl);
-  E.zi = up(cols->zi, ncol * (nl + 1)); E.sabg_lyr = up(cols->sabg_lyr, ncol * (nsno + 1));
-  E.frac_sno_eff = up(cols->frac_sno_eff, ncol); E.h2osno = up(cols->h2osno, ncol); E.h2osfc = up(cols->h2osfc, ncol);
-  E.frac_h2osfc = up(cols->frac_h2osfc, ncol); E.t_h2osfc = up(cols->t_h2osfc, ncol); E.dhsdT = up(cols->dhsdT, ncol);
-  E.hs_soil = up(cols->hs_soil, ncol); E.hs_top_snow = up(cols->hs_top_snow, ncol); E.hs_h2osfc = up(cols->hs_h2osfc, ncol);
-  E.tvector = up(cols->tvector, ncol * nrow);                      // entries the driver does not assign keep the caller's values
-  CK(cudaMemcpyAsync(t->elm_snl, cols->snl, ncol * sizeof(int), cudaMemcpyHostToDevice, s));
-  CK(cudaGetLastError());
+  up[nup] = table(cols->z, nl, snow_rows_only ? nsno : nl); E.z = up[nup++].dev;
+  up[nup] = table(cols->dz, nl, snow_rows_only ? nsno : nl); E.dz = up[nup++].dev;
+  up[nup] = table(cols->t_soisno, nl, nl); E.t_soisno = up[nup++].dev;
+  up[nup] = table(cols->h2osoi_liq, nl, nl); E.h2osoi_liq = up[nup++].dev;
+  up[nup] = table(cols->h2osoi_ice, nl, nl); E.h2osoi_ice = up[nup++].dev;
+  up[nup] = table(cols->zi, nl + 1, snow_rows_only ? nsno + 1 : nl + 1); E.zi = up[nup++].dev;
+  up[nup] = table(cols->sabg_lyr, nsno + 1, nsno + 1); E.sabg_lyr = up[nup++].dev;
+  up[nup] = table(cols->frac_sno_eff, 1, 1); E.frac_sno_eff = up[nup++].dev;
+  up[nup] = table(cols->h2osno, 1, 1); E.h2osno = up[nup++].dev;
+  up[nup] = table(cols->h2osfc, 1, 1); E.h2osfc = up[nup++].dev;
+  up[nup] = table(cols->frac_h2osfc, 1, 1); E.frac_h2osfc = up[nup++].dev;
+  up[nup] = table(cols->t_h2osfc, 1, 1); E.t_h2osfc = up[nup++].dev;
+  up[nup] = table(cols->dhsdT, 1, 1); E.dhsdT = up[nup++].dev;
+  up[nup] = table(cols->hs_soil, 1, 1); E.hs_soil = up[nup++].dev;
+  up[nup] = table(cols->hs_top_snow, 1, 1); E.hs_top_snow = up[nup++].dev;
+  up[nup] = table(cols->hs_h2osfc, 1, 1); E.hs_h2osfc = up[nup++].dev;
+  E.tvector = p;                                                     // entries the driver does not assign keep the caller's values
   E.snl = t->elm_snl;
   // SetSolnPrevCLM + Set{R,I,B}DataFromCLM + PreStepDT (:332-441): written straight into the mailbox
   E.T = t->T_clm; E.liq = t->liq; E.ice = t->ice; E.snow_water = t->snow_water; E.mdz = t->aux_dz; E.dist_up = t->aux_dist_up; E.dist_dn = t->aux_dist_dn;
   E.tuning = t->tuning; E.frac = t->frac; E.nsnow = t->nsnow; E.active = t->active;
   for (int k = 0; k < 3; ++k) { E.hs[k] = t->hs[k]; E.dhs[k] = t->dhs[k]; }
   E.frac_soil = t->frac_soil; E.sabg_snow = t->sabg_snow; E.sabg_soil = t->sabg_soil;
-  elm_thermal_pack_kernel<<<nblk(ncol * nrow, 256), 256, 0, s>>>(E);
-  CK(cudaGetLastError());
-  h->launches += 1;
   t->T_cur = t->T_clm;                                               // PreStepDT
-  if (thermal_snow_step(h, t, dtime)) return 1;                      // StepDT
-  E.T_out = t->T_cur;                                                // GetSoln
-  elm_thermal_unpack_kernel<<<nblk(ncol * nrow, 256), 256, 0, s>>>(E);
-  CK(cudaGetLastError());
-  h->launches += 1;
-  CK(cudaMemcpyAsync(cols->tvector, E.tvector, ncol * nrow * 8, cudaMemcpyDeviceToHost, s));
+  double *const T_out = t->T_work;
+  E.T_out = T_out;                                                   // GetSoln
+
+  CK(cudaEventRecord(h->ev_start, s));
+  CK(cudaStreamWaitEvent(h->copy_in, h->ev_start, 0));
+  CK(cudaStreamWaitEvent(h->copy_out, h->ev_start, 0));
+  CK(cudaEventRecord(h->ev0, s));
+  const size_t pitch = ncol * 8;
+  for (int k = 0; k < nchunks; ++k) {
+    const long long c0 = k * per; const int n = (int)std::min<long long>(per, (long long)ncol - c0);
+    for (int a = 0; a < nup; ++a)
+      CK(cudaMemcpy2DAsync(up[a].dev + c0, pitch, up[a].host + c0, pitch, (size_t)n * 8, up[a].rows, cudaMemcpyHostToDevice, h->copy_in));
+    CK(cudaMemcpy2DAsync(E.tvector + c0, pitch, cols->tvector + c0, pitch, (size_t)n * 8, nrow, cudaMemcpyHostToDevice, h->copy_in));
+    CK(cudaMemcpyAsync(t->elm_snl + c0, cols->snl + c0, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->copy_in));
+    CK(cudaEventRecord(h->ev_in[k], h->copy_in));
+    CK(cudaStreamWaitEvent(s, h->ev_in[k], 0));
+    E.col0 = (int)c0; E.ncols = n;
+    elm_thermal_pack_kernel<<<nblk((long long)n * nrow, 256), 256, 0, s>>>(E);
+    CK(cudaGetLastError());
+    if (thermal_snow_launch(h, t, dtime, c0, n, T_out)) return 1;     // StepDT
+    elm_thermal_unpack_kernel<<<nblk((long long)n * nrow, 256), 256, 0, s>>>(E);
+    CK(cudaGetLastError());
+    h->launches += 2;
+    CK(cudaEventRecord(h->ev_comp[k], s));
+    CK(cudaStreamWaitEvent(h->copy_out, h->ev_comp[k], 0));
+    CK(cudaMemcpy2DAsync(cols->tvector + c0, pitch, E.tvector + c0, pitch, (size_t)n * 8, nrow, cudaMemcpyDeviceToHost, h->copy_out));
+  }
+  CK(cudaEventRecord(h->ev_out_done, h->copy_out));
+  CK(cudaStreamWaitEvent(s, h->ev_out_done, 0));
+  CK(cudaEventRecord(h->ev1, s));
+  t->T_cur = T_out;
   CK(cudaStreamSynchronize(s));
+  t->elm_soil_loaded = true;
   return 0;
 }

@@ -569,6 +569,8 @@ struct ThermalState {
   int *snow_top_id = nullptr;
   // staging for mppgpu_thermal_elm_solve (ELM's raw column arrays); one allocation, carved up
   double *elm_stage = nullptr; int *elm_snl = nullptr;
+  int elm_chunks = 0;                      // column chunks of the ELM solve pipeline (0: default)
+  bool elm_static_soil = false, elm_soil_loaded = false;   // soil rows of z / dz / zi go up once (mppgpu_elm_set_pipeline)
 };
 
 }  // namespace mpp

@@ -27,6 +27,7 @@ namespace mpp {
 struct ThermalSnowArgs {
   ThermalArgs S;                        // soil statics (ncol, nlev, nlevsoi, landunit ids, dt, cnfac, tables, distances, stale_area)
   int nsno;
+  int col0, col_end;                    // the columns this launch covers (a chunk of the ELM solve pipeline, or the whole batch)
   // SoE mailbox, ncol*(nsno+1+nlev) entries each, SoE order
   const double *T_in, *liq, *ice, *snow_water, *mdz, *dist_up, *dist_dn, *tuning, *frac;
   const int *nsnow, *active;
@@ -145,10 +146,10 @@ thermal_snow_step_kernel(const ThermalSnowArgs A)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int col = (int)(tid / LPC), l = (int)(tid % LPC);
+  const int col = A.col0 + (int)(tid / LPC), l = (int)(tid % LPC);
   const int nsno = A.nsno, nlev = A.S.nlev, ncol = A.S.ncol;
   const int pad = nsno & 1, ns2 = (nsno + pad) >> 1;
-  const bool col_ok = col < ncol;
+  const bool col_ok = col < A.col_end;
   const bool snow_lane = l < ns2;
   const int sa = 2 * l - pad, sb = sa + 1;            // snow layers of a snow lane (sa = -1: the padding row)
   const int ja = 2 * (l - ns2), jb = ja + 1;          // soil layers of a soil lane
@@ -294,10 +295,10 @@ thermal_snow_step3_kernel(const ThermalSnowArgs A)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int col = (int)(tid / LPC), l = (int)(tid % LPC);
+  const int col = A.col0 + (int)(tid / LPC), l = (int)(tid % LPC);
   const int nsno = A.nsno, nlev = A.S.nlev, ncol = A.S.ncol;
   const int ns3 = (nsno + 2) / 3, pad = 3 * ns3 - nsno;
-  const bool col_ok = col < ncol;
+  const bool col_ok = col < A.col_end;
   const bool snow_lane = l < ns3;
   const int s0 = 3 * l - pad;                          // snow layers s0, s0+1, s0+2 of a snow lane (negative: padding rows)
   const int j0 = 3 * (l - ns3);                        // soil layers j0, j0+1, j0+2 of a soil lane
@@ -448,6 +449,7 @@ thermal_snow_step3_kernel(const ThermalSnowArgs A)
 // the packing into the SoE mailbox (:204-330) and the unpacking of the solution (:460-505) are kernels, so nothing is packed on the CPU.
 struct ElmThermalArgs {
   int ncol, nlev, nsno;
+  int col0, ncols;                           // the columns this launch covers
   double capr;                               // mpp_varcon.F90:30
   const int *active_col;                     // column filter (col%active and not lake / urban) or nullptr
   const int *snl;
@@ -464,8 +466,8 @@ __global__ void elm_thermal_pack_kernel(const ElmThermalArgs A)
 {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ncol = A.ncol, nsno = A.nsno, nlev = A.nlev, nrow = nsno + 1 + nlev;
-  if (tid >= (long long)ncol * nrow) return;
-  const int c = (int)(tid % ncol), r = (int)(tid / ncol);
+  if (tid >= (long long)A.ncols * nrow) return;
+  const int c = A.col0 + (int)(tid % A.ncols), r = (int)(tid / A.ncols);
   const bool on = (A.active_col == nullptr) || A.active_col[c] != 0;
   const int snl = A.snl[c];
   // ELM layer j lives at array column (j + nsno - 1) of the (-nsno+1 : nlev) arrays and at (j + nsno) of zi
@@ -522,8 +524,8 @@ __global__ void elm_thermal_unpack_kernel(const ElmThermalArgs A)
 {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int ncol = A.ncol, nsno = A.nsno, nlev = A.nlev, nrow = nsno + 1 + nlev;
-  if (tid >= (long long)ncol * nrow) return;
-  const int c = (int)(tid % ncol), r = (int)(tid / ncol);
+  if (tid >= (long long)A.ncols * nrow) return;
+  const int c = A.col0 + (int)(tid % A.ncols), r = (int)(tid / A.ncols);
   if (A.active_col != nullptr && A.active_col[c] == 0) return;
   const int snl = A.snl[c];
   if (r < nsno) {

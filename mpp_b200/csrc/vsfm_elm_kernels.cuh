@@ -26,6 +26,7 @@ namespace mpp {
 
 struct ElmArgs {
   int ncol, nlev, nlevsoi, max_patch_per_col;
+  int col0, col_end;                       // the columns this launch covers (a chunk of the pipeline, or the whole batch)
   double dtime, watmin, rtol0, stol0;
   const int *active;                       // column filter or nullptr
   // patch level (optional)
@@ -52,9 +53,9 @@ __global__ void elm_pack_kernel(const ElmArgs A)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = (int)(tid / G), j = (int)(tid % G);                    // lane j owns layer j + 1 of the reference
+  const int c = A.col0 + (int)(tid / G), j = (int)(tid % G);           // lane j owns layer j + 1 of the reference
   const int nlev = A.nlev, nlevsoi = A.nlevsoi;
-  const bool col_ok = c < A.ncol;
+  const bool col_ok = c < A.col_end;
   const bool on = col_ok && ((A.active == nullptr) || A.active[c] != 0);
   const bool cell = on && j < nlev;
   const long long ic = (long long)c * nlev + j;
@@ -137,9 +138,9 @@ __global__ void elm_decide_kernel(const ElmArgs A)
 {
   constexpr unsigned FULL = 0xffffffffu;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = (int)(tid / G), j = (int)(tid % G);
+  const int c = A.col0 + (int)(tid / G), j = (int)(tid % G);
   const int nlev = A.nlev;
-  const bool col_ok = c < A.ncol;
+  const bool col_ok = c < A.col_end;
   const int m = col_ok ? A.mask[c] : 0;
   if (__all_sync(FULL, m == 0)) return;                                 // no column of this warp took part in the StepDT that just ran
   const bool run = m != 0, cell = run && j < nlev;
@@ -196,6 +197,15 @@ __global__ void elm_decide_kernel(const ElmArgs A)
     A.status[c] = ok; A.mask[c] = next;
     if (next) A.retry_list[atomicAdd(A.pending, 1)] = c;
   }
+}
+
+// columns whose solve failed (status 0), not counting the ones the column filter excludes
+__global__ void elm_count_failed_kernel(int ncol, const int *active, const int *status, int *nfailed)
+{
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool bad = c < ncol && (active == nullptr || active[c] != 0) && status[c] == 0;
+  const unsigned m = __ballot_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(nfailed, __popc(m));
 }
 
 // Per-block partials of the handle's nine reductions (sums: mass before / after, sources * dt, boundary exchange; maxima: |mass error|,

@@ -66,6 +66,11 @@ class _SoE:
             self.L.mppgpu_destroy(self.h)
             self.h = None
 
+    def elm_set_pipeline(self, nchunks=0, static_soil_geometry=False):
+        """How the ELM solve entry points (VSFM.elm_solve, Thermal.elm_solve) pipeline their host copies: number of column chunks (0 default,
+        1 none); thermal only: upload the soil rows of z / dz / zi (ELM's fixed vertical grid) with the first solve only."""
+        check(self.L.mppgpu_elm_set_pipeline(self.h, int(nchunks), 1 if static_soil_geometry else 0))
+
     def __del__(self):
         try:
             self.close()

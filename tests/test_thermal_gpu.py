@@ -294,6 +294,44 @@ def test_thermal_elm_solve_page_locked_arrays(mpp):
         mpp.host_unregister(v)
 
 
+def test_thermal_elm_solve_pipeline_is_bit_identical(mpp):
+    """mppgpu_elm_set_pipeline on the thermal SoE: column chunks on three streams (ragged last chunk) and the soil rows of z / dz / zi
+    uploaded by the first solve only -- same tvector and the same packed mailbox bit for bit as the unpipelined solve that uploads
+    every row every time, while the snow pack (snow rows of z / dz / zi, snl) changes from step to step."""
+    ncol, nlev, nsno = 2500, 15, 5
+    d = PB.elm_snow_thermal_inputs(ncol, nlev, nsno)
+    a = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    b = PB.build_elm_snow_thermal(mpp.ThermalSnow, d)
+    a.elm_set_pipeline(1)
+    b.elm_set_pipeline(3, static_soil_geometry=True)
+    rng = np.random.default_rng(23)
+    e = PB.elm_thermal_raw_arrays(d)
+    el = PB.page_aligned_state(e)
+    for v in el.values():
+        mpp.host_register(v)
+    for step in range(3):
+        ta = a.elm_solve(1800.0, e, step + 1).copy()
+        if step > 0:
+            # what a stale upload would pick up: the soil rows of the caller's z / dz / zi are NOT read again on this handle
+            for k, r0 in (("z", nsno), ("dz", nsno), ("zi", nsno + 1)):
+                el[k][r0:] = np.nan
+        tb = b.elm_solve(1800.0, el, step + 1)
+        assert np.array_equal(ta, tb), step
+        for var in (K.VAR_TUNING_FACTOR, K.VAR_DZ, K.VAR_DIST_UP, K.VAR_DIST_DN, K.VAR_FRAC, K.VAR_LIQ_AREAL_DEN, K.VAR_TEMPERATURE):
+            assert np.array_equal(a.get_data(K.AUXVAR_INTERNAL, var, 1), b.get_data(K.AUXVAR_INTERNAL, var, 1)), var
+        # next step: temperatures carried on, the snow pack settles (thinner snow layers: the snow rows of z / dz / zi move)
+        for s_ in (e, el):
+            s_["t_soisno"][...] = np.where(ta[1:] == -999.0, 270.0, ta[1:])
+            shrink = 1.0 - 0.05 * (step + 1)
+            s_["dz"][:nsno] *= shrink; s_["z"][:nsno] *= shrink; s_["zi"][:nsno] *= shrink
+            s_["hs_soil"] += 3.0
+    for v in el.values():
+        mpp.host_unregister(v)
+    # asking again re-arms the one-time upload
+    b.elm_set_pipeline(3, static_soil_geometry=True)
+    assert np.isnan(b.elm_solve(1800.0, el, 4)).any()                 # the NaN soil rows are read this time
+
+
 def test_thermal_elm_solve_error_behaviour(mpp):
     d = PB.elm_thermal_inputs(4, 15)
     p, ids = PB.build_elm_thermal(mpp.Thermal, d)

@@ -765,6 +765,54 @@ def test_elm_solve_with_page_locked_host_arrays(mpp):
     assert oa["nattempts"] >= 1
 
 
+@pytest.mark.parametrize("fortran_order", [False, True])
+def test_elm_solve_pipeline_chunks_are_bit_identical(mpp, fortran_order):
+    """mppgpu_elm_set_pipeline: the solve cut into column chunks on three streams (ragged last chunk, page-locked arrays so that the
+    copies really are asynchronous) returns every array bit for bit as the unpipelined solve does -- including the columns that the
+    first StepDT did not settle, which are redone after the pipeline and downloaded a second time (loose rtol forces such columns)."""
+    ncol, nlev = 3000, 15
+    d = PB.elm_vsfm_inputs(ncol)
+    a, aids = PB.build_elm_vsfm(mpp.VSFM, d)
+    b, bids = PB.build_elm_vsfm(mpp.VSFM, d)
+    for s_ in (a, b):
+        s_.set_tolerances(1e-50, 1e-2, 1e-10, 50, 10000)
+    a.elm_set_pipeline(1)
+    b.elm_set_pipeline(3)                                   # 1024 + 1024 + 952 columns
+    st = PB.elm_vsfm_raw_state(a, d, patches=True)
+    if fortran_order:
+        for k in ("rootr_col", "h2osoi_liq", "h2osoi_ice"):
+            st[k] = np.ascontiguousarray(st[k].reshape(ncol, nlev).T)
+        zi, dz = np.ascontiguousarray(st["zi"].T), np.ascontiguousarray(st["dz"].T)
+    else:
+        zi, dz = st["zi"], st["dz"]
+    sp = PB.page_aligned_state(st)
+    a.elm_set_geometry(zi, dz, st["nlevsoi"], aids, fortran_order=fortran_order)
+    b.elm_set_geometry(zi, dz, sp["nlevsoi"], bids, fortran_order=fortran_order)
+    pinned = [v for v in sp.values() if isinstance(v, np.ndarray) and v.nbytes]
+    for v in pinned:
+        mpp.host_register(v)
+    retried = False
+    for step in range(2):
+        oa = a.elm_solve(1800.0, st, step + 1, fortran_order=fortran_order)
+        ob = b.elm_solve(1800.0, sp, step + 1, fortran_order=fortran_order)
+        retried |= oa["nattempts"] > 1
+        assert oa["nattempts"] == ob["nattempts"] and oa["nfailed"] == ob["nfailed"]
+        for k in ("rootr_col", "h2osoi_liq", "h2osoi_ice", "zwt", "qflx_drain", "mflx_snowlyr_col"):
+            assert np.array_equal(st[k], sp[k]), k
+        for k in ("smp_l", "soilp_col", "qcharge", "abs_mass_error", "iter_count", "status"):
+            assert np.array_equal(oa[k], ob[k]), k
+        assert np.array_equal(a.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1), b.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1))
+        (sa, ma), (sb, mb) = a.mass_balance(1800.0), b.mass_balance(1800.0)
+        assert np.array_equal(ma, mb) and np.allclose(sa, sb, rtol=1e-13, atol=0.0)      # the sums fold per-block partials: same values, same order
+    assert retried, "no column needed a second StepDT: the re-download path was not exercised"
+    for v in pinned:
+        mpp.host_unregister(v)
+    with pytest.raises(mpp.MPPError):
+        a.elm_set_pipeline(-1)
+    with pytest.raises(mpp.MPPError):
+        a.elm_set_pipeline(2, static_soil_geometry=True)    # thermal only
+
+
 @pytest.mark.parametrize("problem", ["drying", "wetting"])
 def test_sy1991_layered_column_matches_oracle(mpp, oracle, problem):
     """vsfm_sy1991_problem.F90 (two-layer permeability contrast, mass-rate recharge at the top, Dirichlet head at the bottom, 200 cells:

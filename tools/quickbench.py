@@ -79,6 +79,43 @@ elif mode == "elmhost":
     pin = lambda S: {k: (torch.from_numpy(v).pin_memory().numpy() if isinstance(v, np.ndarray) and v.nbytes else v) for k, v in S.items()}
     keep = (pin(st), pin(o))
     run("torch pin_memory", *keep)
+elif mode == "elmpipe":
+    # the two ELM solve entry points with page-locked host arrays, over the number of pipeline chunks
+    d = bench.shard_inputs(0, ncol); d["satfunc"] = "smooth_brooks_corey_bz3"
+    p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
+    st = PB.elm_vsfm_raw_state(p, d, patches=True)
+    p.elm_set_geometry(st["zi"], st["dz"], st["nlevsoi"], ids)
+    sp = PB.page_aligned_state(st)
+    op = PB.page_aligned_state(p.elm_solve(1800.0, sp, 1))
+    lk = [v for v in list(sp.values()) + list(op.values()) if isinstance(v, np.ndarray) and v.nbytes]
+    for v in lk:
+        mpp_b200.host_register(v)
+    for nch in (1, 2, 4, 8, 16, 32):
+        p.elm_set_pipeline(nch)
+        w = []
+        for s in range(4):
+            t0 = time.time(); r = p.elm_solve(1800.0, sp, s + 2, out=op); w.append((time.time() - t0) * 1e3)
+        print("vsfm elm_solve chunks %2d wall ms %s span ms %.2f attempts %d" % (nch, ["%.1f" % x for x in w], p.last_step_ms(), r["nattempts"]), flush=True)
+    for v in lk:
+        mpp_b200.host_unregister(v)
+    p.close()
+    base = 4096
+    d0 = PB.elm_snow_thermal_inputs(base, 15, 5)
+    d, o = PB.tile_snow_thermal(d0, PB.pack_elm_snow_thermal(d0), max(1, ncol // base))
+    p = PB.build_elm_snow_thermal(mpp_b200.ThermalSnow, d)
+    e0 = PB.elm_thermal_raw_arrays(d0); reps = ncol // base
+    e = PB.page_aligned_state({k: (np.tile(v, (1, reps)) if v.ndim == 2 else np.tile(v, reps)) for k, v in e0.items()})
+    for v in e.values():
+        mpp_b200.host_register(v)
+    for static in (False, True):
+        for nch in (1, 4, 8, 16):
+            p.elm_set_pipeline(nch, static_soil_geometry=static)
+            w = []
+            for s in range(4):
+                t0 = time.time(); p.elm_solve(1800.0, e, s + 2); w.append((time.time() - t0) * 1e3)
+            print("thermal elm_solve static_soil %d chunks %2d wall ms %s span ms %.2f" % (static, nch, ["%.1f" % x for x in w], p.last_step_ms()), flush=True)
+    for v in e.values():
+        mpp_b200.host_unregister(v)
 elif mode == "snow":
     base = 4096
     d0 = PB.elm_snow_thermal_inputs(base, 15, 5)
