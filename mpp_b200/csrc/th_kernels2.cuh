@@ -43,14 +43,24 @@ __device__ __forceinline__ double grp_sum(double v)
 }
 
 // Block PCR: A y[l-1] + B y[l] + C y[l+1] = (d0, d1), one block row per lane; identity rows pad the group.
+// TH2_PCR_ROLLED=1 runs the stages before the last as ONE loop body with a run-time shuffle distance (-240 instructions of a hot loop
+// that is larger than the 32 KB second-level instruction cache).  Measured SLOWER on 1 Mi columns (6.46 vs 6.15 ms per step): the
+// unrolled stages overlap their shuffles with the previous stage's arithmetic, and that is worth more than the fetch misses.
+#ifndef TH2_PCR_ROLLED
+#define TH2_PCR_ROLLED 0
+#endif
 template <int G>
 __device__ __forceinline__ void block_pcr(M2 A, M2 B, M2 C, double d0, double d1, double &y0, double &y1)
 {
   M2 Bi = m2inv(B);
   A = m2mul(Bi, A); C = m2mul(Bi, C);
   double e0 = Bi.a * d0 + Bi.b * d1, e1 = Bi.c * d0 + Bi.d * d1;
+#if TH2_PCR_ROLLED
+#pragma unroll 1
+#else
 #pragma unroll
-  for (int s = 1; s < G; s <<= 1) {
+#endif
+  for (int s = 1; s < G / 2; s <<= 1) {
     const M2 Am = m2up<G>(A, s), Cm = m2up<G>(C, s), Ap = m2dn<G>(A, s), Cp = m2dn<G>(C, s);
     const double e0m = __shfl_up_sync(FULL_MASK, e0, s, G), e1m = __shfl_up_sync(FULL_MASK, e1, s, G);
     const double e0p = __shfl_down_sync(FULL_MASK, e0, s, G), e1p = __shfl_down_sync(FULL_MASK, e1, s, G);
@@ -61,6 +71,19 @@ __device__ __forceinline__ void block_pcr(M2 A, M2 B, M2 C, double d0, double d1
     const M2 An = m2mul(A, Am), Cn = m2mul(C, Cp);
     Bi = m2inv(Bn);
     A = m2mul(Bi, M2{-An.a, -An.b, -An.c, -An.d}); C = m2mul(Bi, M2{-Cn.a, -Cn.b, -Cn.c, -Cn.d});
+    e0 = Bi.a * f0 + Bi.b * f1; e1 = Bi.c * f0 + Bi.d * f1;
+  }
+  {
+    // last stage (distance G/2): rows l and l +- G/2 decouple from everything else; only the right-hand side is carried on
+    constexpr int s = G / 2;
+    const M2 Cm = m2up<G>(C, s), Ap = m2dn<G>(A, s);
+    const double e0m = __shfl_up_sync(FULL_MASK, e0, s, G), e1m = __shfl_up_sync(FULL_MASK, e1, s, G);
+    const double e0p = __shfl_down_sync(FULL_MASK, e0, s, G), e1p = __shfl_down_sync(FULL_MASK, e1, s, G);
+    const M2 ACm = m2mul(A, Cm), CAp = m2mul(C, Ap);
+    const M2 Bn{1.0 - ACm.a - CAp.a, -ACm.b - CAp.b, -ACm.c - CAp.c, 1.0 - ACm.d - CAp.d};
+    const double f0 = e0 - (A.a * e0m + A.b * e1m) - (C.a * e0p + C.b * e1p);
+    const double f1 = e1 - (A.c * e0m + A.d * e1m) - (C.c * e0p + C.d * e1p);
+    Bi = m2inv(Bn);
     e0 = Bi.a * f0 + Bi.b * f1; e1 = Bi.c * f0 + Bi.d * f1;
   }
   y0 = e0; y1 = e1;

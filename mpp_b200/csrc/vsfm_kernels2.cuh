@@ -36,6 +36,12 @@ namespace mpp {
 #ifndef VSFM2_MIN_BLOCKS
 #define VSFM2_MIN_BLOCKS 16
 #endif
+// the instances with boundary conditions / per-column retries / the evaluation probe carry more live state: at 16 blocks per SM (128
+// registers) they spilled 170-200 bytes; 12 blocks (168 registers, no spills) measured 7 % faster on 1 Mi columns with a Dirichlet head
+// at the bottom (2.65 vs 2.85 ms per step)
+#ifndef VSFM2_MIN_BLOCKS_BC
+#define VSFM2_MIN_BLOCKS_BC 12
+#endif
 
 template <int LPC>
 __device__ __forceinline__ double col_sum(double v)
@@ -167,7 +173,7 @@ __device__ __forceinline__ void rich_flux_deriv(double P_u, double kr_u, double 
 // Newton set-up once, write F and the assembled Jacobian rows, and leave -- the SAME fused assembly code the time step runs
 constexpr int PH_VEVAL = 6;
 template <int LPC, int SATFUNC, bool HAS_BC, bool RETRY = false, bool EVAL = false>
-__global__ void __launch_bounds__(VSFM2_THREADS, VSFM2_MIN_BLOCKS)
+__global__ void __launch_bounds__(VSFM2_THREADS, (HAS_BC || RETRY || EVAL) ? VSFM2_MIN_BLOCKS_BC : VSFM2_MIN_BLOCKS)
 vsfm_step2_kernel(const VsfmArgs A)
 {
   constexpr unsigned FULL = FULL_MASK;

@@ -15,6 +15,12 @@ if mode == "vsfm":
         p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
         p.set_column_ordering(ordering)
         bench.set_forcing_host(p, ids, d)
+        if os.environ.get("STEP_BUDGET"):
+            p.set_step_budget(int(os.environ["STEP_BUDGET"]))
+        if os.environ.get("WITH_BC"):           # a Dirichlet head at the bottom of every column: the HAS_BC instance of the step kernel
+            bot = p.add_condition(1, K.COND_BC, K.COND_DIRICHLET, K.SOIL_BOTTOM_CELLS)
+            # hydrostatic continuation of the initial profile to the bottom face: no flux through it at the start
+            p.set_data(K.AUXVAR_BC, K.VAR_BC_SS_CONDITION, bot, d["press_ic"].reshape(ncol, -1)[:, -1] + 998.2 * 9.80665 * 0.5 * d["dz"].reshape(ncol, -1)[:, -1])
         ms, bad = [], 0
         for s in range(12):
             p.pre_step_dt(); conv, reason = p.step_dt(1800.0, s + 1); p.post_step_dt()
