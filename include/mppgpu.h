@@ -74,7 +74,9 @@ const char *mppgpu_last_error(void);
 int  mppgpu_version(void);
 int  mppgpu_device_count(void);
 
-/* ---- life cycle ------------------------------------------------------------------------------- */
+/* ---- life cycle -------------------------------------------------------------------------------
+ * A handle lives on the CUDA device it was created on.  Every entry point selects that device for the duration of the call and hands the
+ * caller's current device back on return. */
 int  mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppgpu_handle *out);
 int  mppgpu_destroy(mppgpu_handle h);
 /* run all work of this handle on a caller-provided cudaStream_t (NULL = the handle's own stream) */

@@ -49,7 +49,18 @@ static int fail(const char *fmt, ...)
   return 1;
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); } while (0)
-#define CHECK_H(h) do { if (!(h)) return fail("null handle"); CK(cudaSetDevice((h)->device)); } while (0)
+// Every entry point runs on the handle's device and hands the caller's current device back on return (a host model, or torch in the
+// same process, may be working on another one).
+struct DeviceScope {
+  int prev = -1, cur = -1; cudaError_t err = cudaSuccess;
+  explicit DeviceScope(int dev) : cur(dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceScope() { if (prev >= 0 && prev != cur) (void)cudaSetDevice(prev); }
+};
+#define CHECK_H(h) if (!(h)) return fail("null handle"); DeviceScope device_scope_((h)->device); \
+                   if (device_scope_.err != cudaSuccess) return fail("cannot select device %d: %s", (h)->device, cudaGetErrorString(device_scope_.err))
 
 // every device buffer carries MPP_ALLOC_SLACK bytes of slack: the tile kernels (thermal_step2_tma_kernel) copy whole tiles and may
 // read up to one tile past the end of the batch
@@ -241,7 +252,8 @@ extern "C" int mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppg
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("mppgpu_create: no CUDA device available (this library has no CPU fallback)");
   if (device < 0 || device >= ndev) return fail("mppgpu_create: device %d out of range (0..%d)", device, ndev - 1);
-  CK(cudaSetDevice(device));
+  DeviceScope device_scope_(device);
+  if (device_scope_.err != cudaSuccess) return fail("mppgpu_create: cannot select device %d: %s", device, cudaGetErrorString(device_scope_.err));
   mppgpu_soe *h = new mppgpu_soe();
   struct Guard { mppgpu_soe *h; ~Guard() { if (h) mppgpu_destroy(h); } } guard{h};     // any failure below releases what was created so far
   CK(cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, device));
@@ -287,7 +299,7 @@ extern "C" int mppgpu_create(int soe_itype, int ncol, int nlev, int device, mppg
 extern "C" int mppgpu_destroy(mppgpu_handle h)
 {
   if (!h) return 0;
-  cudaSetDevice(h->device);
+  DeviceScope device_scope_(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (auto *c : h->bcs) delete c;
   for (auto *c : h->sss) delete c;

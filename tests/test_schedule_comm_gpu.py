@@ -144,3 +144,29 @@ def test_global_mass_balance_two_ranks_nccl_without_torch_distributed(mpp, tmp_p
     assert abs(one["mass_end"] - g["mass_end"]) <= 1e-12 * abs(g["mass_end"])
     assert one["max_abs_mass_error"] == g["max_abs_mass_error"] and one["max_newton_its"] == g["max_newton_its"]
     assert one["worst_reason"] == g["worst_reason"] and not g["any_diverged"]
+
+
+def test_entry_points_hand_the_callers_device_back(mpp):
+    """A handle lives on the device it was created on; every call selects it and restores whatever device the caller had current
+    (a host model, or torch in the same process, may be working on another one).  With one GPU the check is trivial but still runs."""
+    import ctypes
+    from mpp_b200._lib import lib
+    rt = ctypes.CDLL("libcudart.so.12")
+    cur = ctypes.c_int(-1)
+    ndev = lib().mppgpu_device_count()
+    mine, other = 0, (1 if ndev >= 2 else 0)
+    assert rt.cudaSetDevice(mine) == 0
+    d = PB.elm_vsfm_inputs(64)
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d, device=other)
+    assert rt.cudaGetDevice(ctypes.byref(cur)) == 0 and cur.value == mine
+    conv, reason, out = PB.elm_vsfm_step(p, ids, d)
+    assert conv
+    assert rt.cudaGetDevice(ctypes.byref(cur)) == 0 and cur.value == mine
+    p.close()
+    assert rt.cudaGetDevice(ctypes.byref(cur)) == 0 and cur.value == mine
+    if ndev >= 2:
+        # same columns on the other device: same numbers
+        q, qids = PB.build_elm_vsfm(mpp.VSFM, d, device=mine)
+        conv2, reason2, out2 = PB.elm_vsfm_step(q, qids, d)
+        assert np.array_equal(out["pressure"], out2["pressure"])
+        q.close()
