@@ -639,9 +639,10 @@ def test_elm_solve_error_behaviour(mpp):
     assert out["nfailed"] == 0 and out["nattempts"] >= 1
 
 
-def test_elm_solve_respects_the_column_filter(mpp, oracle):
-    """filter_hydrologyc: columns switched off in the mesh are neither packed, stepped nor unpacked."""
-    ncol = 64
+@pytest.mark.parametrize("ncol,nchunks", [(64, 0), (2200, 3)])
+def test_elm_solve_respects_the_column_filter(mpp, oracle, ncol, nchunks):
+    """filter_hydrologyc: columns switched off in the mesh are neither packed, stepped nor unpacked (also when the solve is pipelined over
+    column chunks, the filtered run with three chunks against the unfiltered one with a single chunk)."""
     d = PB.elm_vsfm_inputs(ncol)
     act = (np.arange(ncol) % 3 != 0).astype(np.int32)
     g = mpp.VSFM(ncol, 15)
@@ -653,6 +654,8 @@ def test_elm_solve_respects_the_column_filter(mpp, oracle):
     g.set_soils(d["watsat"], d["hksat"], d["bsw"], d["sucsat"], d["residual_sat"], d["satfunc"], K.DENSITY_TGDPB01)
     g.restart(d["press_ic"])
     full, fids = PB.build_elm_vsfm(mpp.VSFM, d)
+    g.elm_set_pipeline(nchunks)
+    full.elm_set_pipeline(1 if nchunks else 0)
     st = PB.elm_vsfm_raw_state(full, d, patches=False)
     st_f = PB.copy_state(st)
     for s_, p_, i_ in ((st, g, ids), (st_f, full, fids)):
@@ -660,7 +663,7 @@ def test_elm_solve_respects_the_column_filter(mpp, oracle):
     liq0 = st["h2osoi_liq"].copy()
     og, of = g.elm_solve(1800.0, st), full.elm_solve(1800.0, st_f)
     on = act == 1
-    assert og["nfailed"] == 0
+    assert og["nfailed"] == int((of["status"][on] == 0).sum())
     assert np.array_equal(st["h2osoi_liq"][~on], liq0[~on]) and np.all(og["status"][~on] == 0) and np.all(og["smp_l"].reshape(ncol, -1)[~on] == 0.0)
     assert np.array_equal(st["h2osoi_liq"][on], st_f["h2osoi_liq"][on])          # same kernels, same inputs: bit-identical to the unfiltered run
     assert np.array_equal(og["soilp_col"].reshape(ncol, -1)[on], of["soilp_col"].reshape(ncol, -1)[on])
