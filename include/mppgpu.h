@@ -147,9 +147,9 @@ int  mppgpu_set_tolerances(mppgpu_handle h, double atol, double rtol, double sto
  * evaluations inside one StepDT gives up exactly like one that ran out of dt cuts: converged = 0, reason
  * SNES_DIVERGED_FUNCTION_COUNT (-2), solution left at the last converged sub-step. */
 int  mppgpu_set_step_budget(mppgpu_handle h, int max_residual_evaluations);
-/* NOT in the reference (scheduling only, results are identical either way; VSFM, nlev <= 32).  mode 1 (default): the step kernel
- * visits the columns grouped by the number of residual evaluations their previous StepDT needed, most expensive first, so that
- * the four columns a warp advances finish together; mode 0: batch order. */
+/* NOT in the reference (scheduling only, results are identical either way; VSFM with nlev <= 32, TH with nlev <= 16).  mode 1 (default):
+ * the step kernel visits the columns grouped by the number of residual evaluations their previous StepDT needed, most expensive first, so
+ * that the columns a warp advances (four, TH: two) finish together and the longest jobs start first; mode 0: batch order. */
 int  mppgpu_set_column_ordering(mppgpu_handle h, int mode);
 /* VSFM/thermal: x has ncells entries (pressure or temperature); TH: 2*ncells, [P(0..N-1) | T(0..N-1)] */
 /* NOT in the reference (scheduling only, results are bit-identical either way; soil thermal SoE, nlev <= 16).  mode 0 (default): every

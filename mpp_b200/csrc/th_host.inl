@@ -205,7 +205,11 @@ static int th_step(mppgpu_soe *h, THState *t, double dt)
   if (th_fill_args(h, t, A, dt)) return 1;
   int nblocks = 0;
   CK(cudaEventRecord(h->ev0, h->stream));
+  const bool ordered = h->ordering != 0 && h->nlev <= 16;               // the register kernel; columns are independent: results do not depend on it
+  A.order = (ordered && h->order_valid && h->order_chunks == 1 && h->order_per == h->ncol) ? h->order.p : nullptr;
   if (th_launch(h, t, A, &nblocks)) return 1;
+  if (ordered) { if (vsfm_build_order(h, 0, h->ncol, h->stream)) return 1; }
+  h->order_valid = ordered; h->order_chunks = 1; h->order_per = h->ncol;
   reduce_partials_kernel<<<nblocks < REDUCE_BLOCKS ? 1 : REDUCE_BLOCKS, 256, 0, h->stream>>>(h->block_partials.p, nblocks, h->red_scratch.p, h->red_counter.p, h->red_out.p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(h->ev1, h->stream));

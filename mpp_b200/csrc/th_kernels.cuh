@@ -36,6 +36,7 @@ struct THArgs {
   double *liq_sat, *mass;
   int *stat_its, *stat_reason, *stat_cuts, *stat_nf;
   double *block_partials;
+  const int *order;                     // launch order of the columns (most expensive of the previous step first) or nullptr: batch order
   double dt;
   SnesOpts so;
   // the only boundary condition is a Dirichlet temperature at the top of a column of <= 15 layers (the ELM-like TH batch): the fast

@@ -118,9 +118,11 @@ th_step2_kernel(const THArgs A)
   // (goveq_enthalpy%SetSoilPermeability -> mppgpu_th_set_energy_permeability)
   constexpr double PERM_E_DEFAULT = 8.3913e-12;
   const int tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const int col = tid / G, j = tid % G, lane = threadIdx.x & 31;
+  const int slot = tid / G, j = tid % G, lane = threadIdx.x & 31;
   const int nlev = A.nlev;
-  const bool col_ok = col < A.ncol;
+  const bool col_ok = slot < A.ncol;
+  // the warp's two columns: batch order, or grouped by the cost of their previous StepDT (mppgpu_set_column_ordering; as vsfm_step2_kernel)
+  const int col = (col_ok && A.order) ? A.order[slot] : slot;
   const bool valid = col_ok && j < nlev;
   // Boundary connection on the padding lane (A.bc_on_pad_lane: one Dirichlet temperature at the top, nlev <= 15, top cell first).  A
   // Dirichlet face is an internal connection with dist_up = 0 whose up side is the boundary aux var (ThermalEnthalpyFlux,

@@ -211,9 +211,13 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partials, int 
 constexpr int ORDER_BUCKETS = 12, ORDER_BLOCK = 1024;
 __device__ __forceinline__ int order_bucket(int nf)
 {
-  // 0: >= 48, 1: 24-47, 2: 14-23, 3: 10-13, 4: 9, 5: 8, 6: 7, 7: 6, 8: 5, 9: 4, 10: 3, 11: <= 2
-  if (nf >= 10) return (nf >= 48) ? 0 : (nf >= 24 ? 1 : (nf >= 14 ? 2 : 3));
-  return (nf <= 2) ? 11 : 13 - nf;
+  // 0: <= 3, 1: >= 48, 2: 24-47, 3: 14-23, 4: 10-13, 5: 9, 6: 8, 7: 7, 8: 6, 9: 5, 10: 4
+  // The cheapest columns go FIRST, not last: a column that converged at once in the previous step is the likeliest to stall in this one
+  // (TH benchmark batch: 3 % of the columns needed <= 3 evaluations, and half of the columns that then need 60 - 2400 come from them --
+  // tools/th_stragglers.py), and a straggler that starts with the last wave of the launch is all tail.
+  if (nf <= 3) return 0;
+  if (nf >= 10) return (nf >= 48) ? 1 : (nf >= 24 ? 2 : (nf >= 14 ? 3 : 4));
+  return 14 - nf;
 }
 // pass 1: per-block bucket counts, counts[bucket * nblocks + block]
 __global__ void order_count_kernel(const int *__restrict__ nf, int n, int *__restrict__ counts)

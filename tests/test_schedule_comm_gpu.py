@@ -60,6 +60,31 @@ def test_cost_ordered_launch_is_bit_identical_per_column(mpp, zwt_min):
     assert np.allclose(sums0, sums1, rtol=1e-13, atol=0.0)
 
 
+@pytest.mark.parametrize("satfunc", ["smooth_brooks_corey_bz3", "van_genuchten"])
+def test_cost_ordered_launch_th_is_bit_identical_per_column(mpp, satfunc):
+    """The TH register kernel visits its columns in the same cost order (two columns per warp): same solution, same counters, column
+    for column.  van Genuchten from 1 m water tables brings dt cuts and very uneven costs into the batch."""
+    d = PB.elm_th_inputs(3000, 15, satfunc=satfunc, zwt_min=(2.0 if satfunc != "van_genuchten" else 1.0))
+    res = []
+    for ordering in (0, 1):
+        p, ids = PB.build_elm_th(mpp.TH, d)
+        p.set_column_ordering(ordering)
+        p.set_step_budget(3000)                              # (bounds the van Genuchten stragglers; same budget on both sides)
+        outs, stats = [], []
+        for s in range(4):
+            conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, s + 1)
+            outs.append(out); stats.append({k: v.copy() for k, v in p.stats().items()})
+        res.append((outs, stats))
+        p.close()
+    for a, b in zip(res[0][0], res[1][0]):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    for a, b in zip(res[0][1], res[1][1]):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    assert max(st["nfuncs"].max() for st in res[0][1]) > 8   # the costs really differ
+
+
 def test_cost_ordered_launch_in_the_chunked_coupling_step(mpp):
     d = PB.elm_vsfm_inputs(6144, 15, zwt_min=2.0)
     o0, s0, _, _ = _run(mpp, d, 0, 4, coupled_chunks=3)

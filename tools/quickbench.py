@@ -34,8 +34,10 @@ elif mode == "th":
     # the benchmark's TH batch (ELM's default curve, water tables from 2 m); TH_SATFUNC=van_genuchten for the survey's original draw
     d = bench.shard_inputs_th(0, ncol, satfunc=os.environ.get("TH_SATFUNC", "smooth_brooks_corey_bz3"))
     p, ids = PB.build_elm_th(mpp_b200.TH, d)
+    if "ORDERING" in os.environ:
+        p.set_column_ordering(int(os.environ["ORDERING"]))
     ms = []
-    for s in range(8):
+    for s in range(int(os.environ.get("NSTEPS", "8"))):
         conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, s + 1)
         ms.append(p.last_step_ms())
     st = p.stats()
