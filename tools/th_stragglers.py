@@ -1,8 +1,12 @@
-import sys, os
-sys.path.insert(0, "/root/repo")
+"""Development aid: where the expensive columns of a TH step come from -- for every step of the benchmark's TH batch, the columns that need more
+than 60 residual evaluations and what the SAME columns needed in the step before (the evidence behind the launch order of
+vsfm_kernels.cuh:order_bucket).  Runs on a GPU:  python tools/th_stragglers.py [ncol]"""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, bench, mpp_b200
 from mpp_b200 import problems as PB
-ncol = 2097152
+ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 2097152
 d = bench.shard_inputs_th(0, ncol)
 p, ids = PB.build_elm_th(mpp_b200.TH, d)
 p.set_column_ordering(0)
