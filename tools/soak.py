@@ -1,0 +1,49 @@
+"""Development aid: long runs of the benchmark batches (many coupling steps on the same handle) -- convergence, mass balance and step time
+must stay put.  The opt-in step budget is ON here (mppgpu_set_step_budget): over days of simulated time some van Genuchten columns reach the
+pc = 0 kink, where the reference algorithm needs 10^4 - 10^6 evaluations per step -- the run reports how many give up.
+Runs on a GPU:  python tools/soak.py [ncol] [vsfm_steps] [th_steps] [budget]"""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import bench
+import mpp_b200
+from mpp_b200 import problems as PB
+
+ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 1048576
+nv = int(sys.argv[2]) if len(sys.argv) > 2 else 300
+nt = int(sys.argv[3]) if len(sys.argv) > 3 else 100
+budget = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
+
+d = bench.shard_inputs(0, ncol)
+p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
+bench.set_forcing_host(p, ids, d)
+p.set_step_budget(budget)
+failed_cols = 0
+ms, bad, worst_err, worst_nf, cuts = [], 0, 0.0, 0, 0
+for s in range(nv):
+    p.pre_step_dt(); conv, reason = p.step_dt(1800.0, s + 1); p.post_step_dt()
+    ms.append(p.last_step_ms()); bad += (not conv)
+    sums, maxs = p.mass_balance()
+    worst_err = max(worst_err, maxs[0]); worst_nf = max(worst_nf, int(p.stats()["nfuncs"].max())) if s % 25 == 0 else worst_nf
+    cuts = max(cuts, int(maxs[3]))
+    if not conv:
+        failed_cols = max(failed_cols, int((p.stats()["reasons"] < 0).sum()))
+    if s % 50 == 49:
+        print("  vsfm step %d: %.2f ms, steps with a failed column so far %d (most failed columns in one step %d)" % (s + 1, ms[-1], bad, failed_cols), flush=True)
+print("vsfm %d columns x %d steps: not converged %d, worst |mass error| %.2e kg, max dt cuts %d, max evaluations (sampled) %d, ms/step first 5 %s last 5 %s" % (
+    ncol, nv, bad, worst_err, cuts, worst_nf, ["%.2f" % x for x in ms[1:6]], ["%.2f" % x for x in ms[-5:]]), flush=True)
+p.close()
+
+d = bench.shard_inputs_th(0, ncol)
+p, ids = PB.build_elm_th(mpp_b200.TH, d)
+p.set_step_budget(budget)
+ms, bad, worst_nf = [], 0, 0
+for s in range(nt):
+    conv, reason, out = PB.elm_th_step(p, ids, d, 1800.0, s + 1)
+    ms.append(p.last_step_ms()); bad += (not conv)
+    if s % 10 == 0:
+        worst_nf = max(worst_nf, int(p.stats()["nfuncs"].max()))
+        assert np.isfinite(out["pressure"]).all() and np.isfinite(out["temperature"]).all()
+print("th %d columns x %d steps: not converged %d, max evaluations (sampled) %d, T range %.2f..%.2f K, ms/step first 5 %s last 5 %s" % (
+    ncol, nt, bad, worst_nf, out["temperature"].min(), out["temperature"].max(), ["%.2f" % x for x in ms[1:6]], ["%.2f" % x for x in ms[-5:]]), flush=True)
