@@ -1,6 +1,7 @@
 """Development aid: long runs of the benchmark batches (many coupling steps on the same handle) -- convergence, mass balance and step time
-must stay put.  The opt-in step budget is ON here (mppgpu_set_step_budget): over days of simulated time some van Genuchten columns reach the
-pc = 0 kink, where the reference algorithm needs 10^4 - 10^6 evaluations per step -- the run reports how many give up.
+must stay put.  The opt-in step budget is ON here (mppgpu_set_step_budget): after ~45 steps of the SAME synthetic forcing the columns whose draw
+has strong transpiration and no infiltration have dried their root zone, and a fixed-rate sink on a dry cell is not solvable (DESIGN.md
+section 2) -- the run reports how many give up.
 Runs on a GPU:  python tools/soak.py [ncol] [vsfm_steps] [th_steps] [budget]"""
 import os
 import sys
@@ -16,6 +17,7 @@ nt = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 budget = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
 
 d = bench.shard_inputs(0, ncol)
+d["satfunc"] = os.environ.get("SATFUNC", d["satfunc"])          # e.g. SATFUNC=smooth_brooks_corey_bz3: ELM's default curve
 p, ids = PB.build_elm_vsfm(mpp_b200.VSFM, d)
 bench.set_forcing_host(p, ids, d)
 p.set_step_budget(budget)
@@ -31,7 +33,7 @@ for s in range(nv):
         failed_cols = max(failed_cols, int((p.stats()["reasons"] < 0).sum()))
     if s % 50 == 49:
         print("  vsfm step %d: %.2f ms, steps with a failed column so far %d (most failed columns in one step %d)" % (s + 1, ms[-1], bad, failed_cols), flush=True)
-print("vsfm %d columns x %d steps: not converged %d, worst |mass error| %.2e kg, max dt cuts %d, max evaluations (sampled) %d, ms/step first 5 %s last 5 %s" % (
+print(d["satfunc"], "vsfm %d columns x %d steps: not converged %d, worst |mass error| %.2e kg, max dt cuts %d, max evaluations (sampled) %d, ms/step first 5 %s last 5 %s" % (
     ncol, nv, bad, worst_err, cuts, worst_nf, ["%.2f" % x for x in ms[1:6]], ["%.2f" % x for x in ms[-5:]]), flush=True)
 p.close()
 
@@ -45,5 +47,6 @@ for s in range(nt):
     if s % 10 == 0:
         worst_nf = max(worst_nf, int(p.stats()["nfuncs"].max()))
         assert np.isfinite(out["pressure"]).all() and np.isfinite(out["temperature"]).all()
-print("th %d columns x %d steps: not converged %d, max evaluations (sampled) %d, T range %.2f..%.2f K, ms/step first 5 %s last 5 %s" % (
-    ncol, nt, bad, worst_nf, out["temperature"].min(), out["temperature"].max(), ["%.2f" % x for x in ms[1:6]], ["%.2f" % x for x in ms[-5:]]), flush=True)
+if nt:
+    print("th %d columns x %d steps: not converged %d, max evaluations (sampled) %d, T range %.2f..%.2f K, ms/step first 5 %s last 5 %s" % (
+        ncol, nt, bad, worst_nf, out["temperature"].min(), out["temperature"].max(), ["%.2f" % x for x in ms[1:6]], ["%.2f" % x for x in ms[-5:]]), flush=True)
