@@ -15,6 +15,8 @@ ncol = int(sys.argv[1]) if len(sys.argv) > 1 else 1048576
 nv = int(sys.argv[2]) if len(sys.argv) > 2 else 300
 nt = int(sys.argv[3]) if len(sys.argv) > 3 else 100
 budget = int(sys.argv[4]) if len(sys.argv) > 4 else 2000
+btran = bool(int(os.environ.get("BTRAN", "0")))   # BTRAN=1: transpiration falls with the soil water, as a host model's does (ELM's btran)
+from mpp_b200 import constants as K
 
 d = bench.shard_inputs(0, ncol)
 d["satfunc"] = os.environ.get("SATFUNC", d["satfunc"])          # e.g. SATFUNC=smooth_brooks_corey_bz3: ELM's default curve
@@ -24,6 +26,11 @@ p.set_step_budget(budget)
 failed_cols = 0
 ms, bad, worst_err, worst_nf, cuts = [], 0, 0.0, 0, 0
 for s in range(nv):
+    if btran and s:
+        # plant wilting factor of ELM's canopy fluxes: 1 above the potential at which stomata are fully open (smpso = -66 m of water),
+        # 0 below the one at which they close (smpsc = -255 m)
+        psi = (p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1) - K.PRESSURE_REF) / (998.2 * 9.80665)      # [m]
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["et"], d["et"] * np.clip((psi + 255.0) / (255.0 - 66.0), 0.0, 1.0))
     p.pre_step_dt(); conv, reason = p.step_dt(1800.0, s + 1); p.post_step_dt()
     ms.append(p.last_step_ms()); bad += (not conv)
     sums, maxs = p.mass_balance()
@@ -33,7 +40,7 @@ for s in range(nv):
         failed_cols = max(failed_cols, int((p.stats()["reasons"] < 0).sum()))
     if s % 50 == 49:
         print("  vsfm step %d: %.2f ms, steps with a failed column so far %d (most failed columns in one step %d)" % (s + 1, ms[-1], bad, failed_cols), flush=True)
-print(d["satfunc"], "vsfm %d columns x %d steps: not converged %d, worst |mass error| %.2e kg, max dt cuts %d, max evaluations (sampled) %d, ms/step first 5 %s last 5 %s" % (
+print(d["satfunc"], "btran" if btran else "fixed-rate ET", "vsfm %d columns x %d steps: not converged %d, worst |mass error| %.2e kg, max dt cuts %d, max evaluations (sampled) %d, ms/step first 5 %s last 5 %s" % (
     ncol, nv, bad, worst_err, cuts, worst_nf, ["%.2f" % x for x in ms[1:6]], ["%.2f" % x for x in ms[-5:]]), flush=True)
 p.close()
 
