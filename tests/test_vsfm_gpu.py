@@ -829,3 +829,32 @@ def test_sy1991_layered_column_matches_oracle(mpp, oracle, problem):
     Po, So, its_o = PB.run_sy1991(*o, start, problem)
     assert relmax_p(P, Po) < RTOL and relmax(S, So) < RTOL
     assert its == its_o
+
+
+def test_long_horizon_with_host_model_transpiration_stays_converged(mpp):
+    """150 coupling steps (3 simulated days) on one handle.  The transpiration sink is scaled between steps the way a host model scales
+    it -- ELM's plant wilting factor between the potentials at which stomata are fully open (-66 m) and closed (-255 m), from the
+    pressures of the last step -- so no cell is asked for water it does not hold (a FIXED-rate sink dries the root zone of the columns
+    without infiltration within ~50 steps, and neither the reference algorithm nor anything else converges there: DESIGN.md section 2,
+    tools/soak.py).  Every column must converge in every step, with the reference's mass-balance gate."""
+    ncol = 8192
+    d = PB.elm_vsfm_inputs(ncol, 15, zwt_min=2.0)
+    p, ids = PB.build_elm_vsfm(mpp.VSFM, d)
+    for name in ("infil", "et", "dew", "drain", "snow", "sublim"):
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids[name], d[name])
+    p.set_data(K.AUXVAR_INTERNAL, K.VAR_FRAC_LIQ_SAT, 1, d["frac_liq"])
+    p.set_step_budget(5000)                                  # a regression must fail the test, not hang it
+    worst = 0.0
+    for s in range(150):
+        if s:
+            psi = (p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1) - K.PRESSURE_REF) / (998.2 * 9.80665)
+            p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["et"], d["et"] * np.clip((psi + 255.0) / (255.0 - 66.0), 0.0, 1.0))
+        p.pre_step_dt()
+        conv, reason = p.step_dt(1800.0, s + 1)
+        p.post_step_dt()
+        assert conv, (s, reason, int((p.stats()["reasons"] < 0).sum()))
+        sums, maxs = p.mass_balance(1800.0)
+        worst = max(worst, maxs[0])
+    assert worst < 1e-5                                      # max_abs_mass_error_col of MPPVSFMALM_Driver.F90:140
+    st = p.stats()
+    assert st["dt_cuts"].max() <= 2 and st["nfuncs"].max() < 200
