@@ -14,9 +14,12 @@ struct THArgs;
 MPP_DECL_VSFM2(8, 0) MPP_DECL_VSFM2(8, 1) MPP_DECL_VSFM2(8, 2) MPP_DECL_VSFM2(16, 0) MPP_DECL_VSFM2(16, 1) MPP_DECL_VSFM2(16, 2)
 #undef MPP_DECL_VSFM2
 
-// combo: 0 VG + Tanaka + constant c_p, 1 VG + IFC-67 + IFC-67, 2 smoothed Brooks-Corey + Tanaka + constant c_p, 3 run-time dispatch
+// combo: 0 VG + Tanaka + constant c_p, 1 VG + IFC-67 + IFC-67, 2 smoothed Brooks-Corey + Tanaka + constant c_p, 3 run-time dispatch;
+// 0p / 2p (INST_COMBO 4 / 5): combos 0 / 2 with the boundary connection on the padding lane fixed at compile time
 void th2_launch_0(const THArgs &A, int nblocks, cudaStream_t s);
 void th2_launch_1(const THArgs &A, int nblocks, cudaStream_t s);
 void th2_launch_2(const THArgs &A, int nblocks, cudaStream_t s);
 void th2_launch_3(const THArgs &A, int nblocks, cudaStream_t s);
+void th2_launch_0p(const THArgs &A, int nblocks, cudaStream_t s);
+void th2_launch_2p(const THArgs &A, int nblocks, cudaStream_t s);
 }  // namespace mpp

@@ -182,9 +182,10 @@ static int th_launch(mppgpu_soe *h, THState *, THArgs &A, int *nblocks_out)
     // the model combinations the reference's drivers use (and ELM's default curve) get compile-time specialisations in th_step2_inst.cu;
     // anything else dispatches at run time
     const bool tanaka_const = A.density_type == DENSITY_TGDPB01 && A.iee_type == INT_ENERGY_ENTHALPY_CONSTANT;
-    if (A.satfunc == SATFUNC_VG && tanaka_const) th2_launch_0(A, nblocks, h->stream);
+    const bool padbc = A.bc_on_pad_lane != 0 && !A.eval_x;
+    if (A.satfunc == SATFUNC_VG && tanaka_const) { if (padbc) th2_launch_0p(A, nblocks, h->stream); else th2_launch_0(A, nblocks, h->stream); }
     else if (A.satfunc == SATFUNC_VG && A.density_type == DENSITY_IFC67 && A.iee_type == INT_ENERGY_ENTHALPY_IFC67) th2_launch_1(A, nblocks, h->stream);
-    else if (A.satfunc == SATFUNC_SBC && tanaka_const) th2_launch_2(A, nblocks, h->stream);     // ELM's default curve (mpp_varctl.F90:17)
+    else if (A.satfunc == SATFUNC_SBC && tanaka_const) { if (padbc) th2_launch_2p(A, nblocks, h->stream); else th2_launch_2(A, nblocks, h->stream); }   // ELM's default curve (mpp_varctl.F90:17)
     else th2_launch_3(A, nblocks, h->stream);
   } else {
     const size_t smem = (size_t)TH_NARR * h->nlev * sizeof(double);

@@ -27,6 +27,9 @@ namespace mpp {
 #ifndef TH2_MIN_BLOCKS
 #define TH2_MIN_BLOCKS (384 / TH2_THREADS)
 #endif
+#ifndef TH2_MIN_BLOCKS_PAD
+#define TH2_MIN_BLOCKS_PAD TH2_MIN_BLOCKS
+#endif
 
 struct M2 { double a, b, c, d; };     // row-major 2x2: [a b; c d]
 __device__ __forceinline__ M2 m2mul(const M2 &x, const M2 &y) { return M2{x.a * y.a + x.b * y.c, x.a * y.b + x.b * y.d, x.c * y.a + x.d * y.c, x.c * y.b + x.d * y.d}; }
@@ -109,10 +112,14 @@ __device__ __forceinline__ SatParams th_load_sp(double (*s)[TH2_THREADS], int t)
   return p;
 }
 
-template <int G, int SF, int DT, int IEE>
-__global__ void __launch_bounds__(TH2_THREADS, TH2_MIN_BLOCKS)
+// PADBC: the boundary connection is KNOWN to ride on the padding lane (the host launches this instance only when A.bc_on_pad_lane is set): the
+// per-lane boundary-condition loops and their local-memory array are compiled out, which takes ~5 KB out of a hot loop that is larger than the
+// 32 KB second-level instruction cache.  PADBC = false keeps both paths behind the run-time flag.
+template <int G, int SF, int DT, int IEE, bool PADBC = false>
+__global__ void __launch_bounds__(TH2_THREADS, PADBC ? TH2_MIN_BLOCKS_PAD : TH2_MIN_BLOCKS)
 th_step2_kernel(const THArgs A)
 {
+  const bool bc_on_pad = PADBC || (A.bc_on_pad_lane != 0);
   constexpr unsigned FULL = FULL_MASK;
   // energy-equation aux vars keep the default permeability (ThermalEnthalpySoilAuxType.F90:93) unless the driver set its own
   // (goveq_enthalpy%SetSoilPermeability -> mppgpu_th_set_energy_permeability)
@@ -130,12 +137,12 @@ th_step2_kernel(const THArgs A)
   // (state = the condition's T and poked P, static data = the top cell's) and owns the connection boundary -> cell 0, so the boundary
   // flux and its four derivative blocks are computed by the same instructions, at the same time, as every interior connection --
   // instead of a loop that one lane in sixteen runs alone out of a local-memory array.
-  const bool pad = (A.bc_on_pad_lane != 0) && col_ok && (j == G - 1);
+  const bool pad = bc_on_pad && col_ok && (j == G - 1);
   const bool has_conn = (valid && j < nlev - 1) || pad;
   const long long cell = (long long)col * nlev + (pad ? 0 : j);      // the padding lane reads the top cell's static data
   const int src_dn = pad ? lane - (G - 1) : ((j == G - 1) ? lane : lane + 1);                      // lane of the connection's dn cell
-  const int src_up = (A.bc_on_pad_lane != 0 && j == 0) ? lane + (G - 1) : ((j == 0) ? lane : lane - 1);   // lane that owns the connection above
-  const bool has_up = (j > 0) || (A.bc_on_pad_lane != 0);
+  const int src_up = (bc_on_pad && j == 0) ? lane + (G - 1) : ((j == 0) ? lane : lane - 1);   // lane that owns the connection above
+  const bool has_up = (j > 0) || bc_on_pad;
   const int jtop = A.top_is_first ? 0 : nlev - 1, jbot = A.top_is_first ? nlev - 1 : 0;
   const SnesOpts so = A.so;
 
@@ -177,7 +184,7 @@ th_step2_kernel(const THArgs A)
   // boundary conditions owned by this lane (at most one per region and equation)
   struct BCL { int ieqn; double P, T, bgf, Dq; FluxIn fin; double hl, tc; };
   BCL bcs[4]; int nmybc = 0;
-  for (int k = 0; k < (A.bc_on_pad_lane ? 0 : A.nbc); ++k) {
+  for (int k = 0; k < ((PADBC || bc_on_pad) ? 0 : A.nbc); ++k) {
     const bool top = (A.bc[k].region == REGION_TOP);
     if (!valid || j != (top ? jtop : jbot) || nmybc >= 4) continue;
     BCL &b = bcs[nmybc++];
