@@ -249,7 +249,7 @@ th_step2_kernel(const THArgs A)
 
   for (;;) {
     // ================= Newton step set-up: Jacobian blocks, block PCR, line-search initialisation =================
-    if (__any_sync(FULL, phase == PH_NEWTON || phase == PH_EVAL_J)) {
+    if (__any_sync(FULL, phase == PH_NEWTON || (!PADBC && phase == PH_EVAL_J))) {      // (the PADBC instances never serve mppgpu_eval)
       const bool nw = (phase == PH_NEWTON);
       __syncwarp();                              // aux vars were stored under per-column control flow
       THCell ax, ad;                             // this cell and the dn side of connection j (the next lane's cell)
@@ -317,7 +317,7 @@ th_step2_kernel(const THArgs A)
         b10 += (por * ax.ddenP_e * ax.sat * ax.ul + por * ax.den_e * ax.dsat * ax.ul + por * ax.den_e * ax.sat * ax.dulP) * vol * dtInv;
         Jb = M2{b00, b01, b10, b11};
       }
-      if (phase == PH_EVAL_J) {               // kernel unit-test probe: dump the blocks, no solve
+      if (!PADBC && phase == PH_EVAL_J) {     // kernel unit-test probe: dump the blocks, no solve
         if (valid) {
           double *ja = A.eval_ja + 4 * cell, *jb = A.eval_jb + 4 * cell, *jc = A.eval_jc + 4 * cell;
           ja[0] = Ja.a; ja[1] = Ja.b; ja[2] = Ja.c; ja[3] = Ja.d; jb[0] = Jb.a; jb[1] = Jb.b; jb[2] = Jb.c; jb[3] = Jb.d;
@@ -416,10 +416,10 @@ th_step2_kernel(const THArgs A)
     const bool g_bad = !(g2 == g2) || (g2 > 1.7e308);
     const bool out_of_funcs = (nfuncs >= so.max_funcs && so.max_funcs >= 0);
     const bool tiny_step = (stol2 * x2 > y2);
-    if (A.eval_x && phase == PH_INIT) {
+    if (!PADBC && A.eval_x && phase == PH_INIT) {
       if (valid) { Wm = A.eval_x[2 * cell]; We = A.eval_x[2 * cell + 1]; }
       phase = PH_EVAL;
-    } else if (phase == PH_EVAL) {
+    } else if (!PADBC && phase == PH_EVAL) {
       P = Wm; T = We; Fm = Gm; Fe = Ge; ax_store(s_ax, threadIdx.x, c);
       if (valid) { A.eval_f[2 * cell] = Gm; A.eval_f[2 * cell + 1] = Ge; }
       phase = PH_EVAL_J;
@@ -481,7 +481,7 @@ th_step2_kernel(const THArgs A)
     }
   }
 
-  if (A.eval_x) return;
+  if (!PADBC && A.eval_x) return;
   // ---- SOETHPostSolve: solution, mailbox, statistics ------------------------------------------------------------
   if (valid) {
     A.x_out[2 * cell] = P; A.x_out[2 * cell + 1] = T;
