@@ -271,6 +271,15 @@ def elm_vsfm_step(p, ids, d, dt=1800.0, nstep=1, scale=1.0):
     return conv, reason, out
 
 
+def plant_wilting_factor(pressure):
+    """What a host model multiplies its transpiration demand with before it hands it to the VSFM (ELM's plant wilting factor in its
+    canopy fluxes): 1 above the soil water potential at which stomata are fully open (smpso = -66 m of water), 0 below the one at which
+    they close (smpsc = -255 m), linear in between.  The synthetic forcing of this module is otherwise fixed-rate, which over many
+    coupling steps keeps pulling water out of cells that have none left (tools/soak.py)."""
+    psi = (np.asarray(pressure) - K.PRESSURE_REF) / (998.2 * 9.80665)          # [m]
+    return np.clip((psi + 255.0) / (255.0 - 66.0), 0.0, 1.0)
+
+
 def elm_vsfm_raw_state(p, d, seed=SEED, patches=True, nlevsoi=10, drain_frac=0.7):
     """ELM's raw column arrays for MPPVSFMALM_Solve (MPPVSFMALM_Driver.F90:110-200), consistent with the state of `p` (h2osoi_liq +
     h2osoi_ice = the SoE's liquid mass, as ELM keeps them after every solve).  Cell arrays are (ncol, nlev), C order."""

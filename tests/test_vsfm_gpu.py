@@ -847,8 +847,7 @@ def test_long_horizon_with_host_model_transpiration_stays_converged(mpp):
     worst = 0.0
     for s in range(150):
         if s:
-            psi = (p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1) - K.PRESSURE_REF) / (998.2 * 9.80665)
-            p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["et"], d["et"] * np.clip((psi + 255.0) / (255.0 - 66.0), 0.0, 1.0))
+            p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["et"], d["et"] * PB.plant_wilting_factor(p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1)))
         p.pre_step_dt()
         conv, reason = p.step_dt(1800.0, s + 1)
         p.post_step_dt()

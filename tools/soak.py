@@ -27,10 +27,8 @@ failed_cols = 0
 ms, bad, worst_err, worst_nf, cuts = [], 0, 0.0, 0, 0
 for s in range(nv):
     if btran and s:
-        # plant wilting factor of ELM's canopy fluxes: 1 above the potential at which stomata are fully open (smpso = -66 m of water),
-        # 0 below the one at which they close (smpsc = -255 m)
-        psi = (p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1) - K.PRESSURE_REF) / (998.2 * 9.80665)      # [m]
-        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["et"], d["et"] * np.clip((psi + 255.0) / (255.0 - 66.0), 0.0, 1.0))
+        # what the host model does between two steps (ELM's plant wilting factor, problems.plant_wilting_factor)
+        p.set_data(K.AUXVAR_SS, K.VAR_BC_SS_CONDITION, ids["et"], d["et"] * PB.plant_wilting_factor(p.get_data(K.AUXVAR_INTERNAL, K.VAR_PRESSURE, 1)))
     p.pre_step_dt(); conv, reason = p.step_dt(1800.0, s + 1); p.post_step_dt()
     ms.append(p.last_step_ms()); bad += (not conv)
     sums, maxs = p.mass_balance()
@@ -77,8 +75,8 @@ if ne:
     for s in range(1, ne):
         # what the host model does between two solves: transpiration demand times the root-weighted wilting factor (ELM's btran) of the
         # matric potentials the last solve returned
-        psi = out["smp_l"].reshape(ncol, -1) * 1.0e-3                                      # [mm] -> [m]
-        st["qflx_tran_veg_col"][...] = qtran0 * (rootr * np.clip((psi + 255.0) / (255.0 - 66.0), 0.0, 1.0)).sum(axis=1)
+        wilt = PB.plant_wilting_factor(K.PRESSURE_REF + out["smp_l"].reshape(ncol, -1) * 1.0e-3 * (998.2 * 9.80665))    # smp_l [mm] -> [Pa]
+        st["qflx_tran_veg_col"][...] = qtran0 * (rootr * wilt).sum(axis=1)
         t0 = time.perf_counter(); r = p.elm_solve(1800.0, st, s + 1, out=out); wall.append((time.perf_counter() - t0) * 1e3)
         nfail = max(nfail, r["nfailed"]); natt = max(natt, r["nattempts"]); worst = max(worst, float(out["abs_mass_error"][out["status"] == 1].max()))
         if s % 25 == 0:
