@@ -710,10 +710,21 @@ MPP_HD void density_ifc67(double t, double p, double &dwmol, double &dwp, double
 
 // density at the VSFM aux vars' fixed 298.15 K for every density model; EXT = false compiles the IFC-67 polynomial out (the common
 // specialisation of the step kernel), EXT = true dispatches on the run-time type
+// On the device the IFC-67 evaluation stays out of line: the step kernel calls this at seven sites inside its Newton loop, and seven
+// inlined copies of the polynomial were most of the 60 KB that loop spanned (a 32 KB instruction cache).
+#ifdef __CUDACC__
+static __device__ __noinline__ void density_ifc67_25C_rare(double p, double &den, double &dden_dp) { double dT; density_ifc67(25.0, p, den, dden_dp, dT); }
+#endif
 template <bool EXT>
 MPP_HD void density_fixedT_x(const DensityTable &t, double p, double &den, double &dden_dp)
 {
-  if (EXT && t.type == DENSITY_IFC67) { double dT; density_ifc67(25.0, p, den, dden_dp, dT); }
+  if (EXT && t.type == DENSITY_IFC67) {
+#ifdef __CUDA_ARCH__
+    density_ifc67_25C_rare(p, den, dden_dp);
+#else
+    double dT; density_ifc67(25.0, p, den, dden_dp, dT);
+#endif
+  }
   else density_fixedT(t, p, den, dden_dp);
 }
 

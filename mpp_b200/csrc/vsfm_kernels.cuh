@@ -92,7 +92,9 @@ inline void vsfm_compact_sources(VsfmArgs &A)
 }
 
 // Down-regulated mass sink: actual rate [kg/s] and the Jacobian diagonal term it adds (GoveqnRichards...:1900-1927, 2158-2188)
-__device__ __forceinline__ void downreg_sink(int type, double value, double Pc, double n, double P, double &rate, double &djac)
+// (out of line: inlined at its six call sites in the step kernel, its pow and exp were ~10 KB of a Newton loop that has to fit a 32 KB
+// instruction cache; the sink is a rare configuration and sits behind a uniform branch)
+static __device__ __noinline__ void downreg_sink(int type, double value, double Pc, double n, double P, double &rate, double &djac)
 {
   const double dP = P - PRESSURE_REF;
   rate = value; djac = 0.0;
